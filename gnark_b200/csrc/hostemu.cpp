@@ -1,0 +1,147 @@
+// CPU emulation harness for the arithmetic / MSM / NTT templates (TEST ONLY).
+// Compiles the SAME field.cuh / curve.cuh / msm.cuh / ntt.cuh per-thread logic for
+// the host, with the PTX carry-chain primitives emulated (ptx.cuh), so the
+// "not gpu" test-suite can check the device algorithms against the oracle on a
+// box without a GPU.  This library is NOT loaded by the product (gnark_b200/lib.py
+// loads libgnark_b200.so only and fails loudly without CUDA).
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <numeric>
+#include <vector>
+
+#include "msm.cuh"
+#include "ntt.cuh"
+
+using namespace gb200;
+
+namespace {
+
+template <class F>
+int field_op(int op, const void* a_, const void* b_, void* out_) {
+  const F& a = *reinterpret_cast<const F*>(a_);
+  F r;
+  switch (op) {
+    case 0: r = a + *reinterpret_cast<const F*>(b_); break;
+    case 1: r = a - *reinterpret_cast<const F*>(b_); break;
+    case 2: r = a * *reinterpret_cast<const F*>(b_); break;
+    case 3: r = a.inverse(); break;
+    case 4: r = a.neg(); break;
+    case 5: r = a.sqr(); break;
+    case 6: r = a.dbl(); break;
+    default: return -1;
+  }
+  *reinterpret_cast<F*>(out_) = r;
+  return 0;
+}
+
+template <class Fr, class F>
+int msm_emu(const void* points_, const void* scalars_, uint32_t n, int c, int precomp, uint32_t task_len,
+            uint32_t chunk, void* out_jac) {
+  const Affine<F>* points = reinterpret_cast<const Affine<F>*>(points_);
+  const Fr* scalars = reinterpret_cast<const Fr*>(scalars_);
+  MsmPlan pl = msm_make_plan(n, n, 0, Fr::Params::BITS, c, precomp, task_len, chunk);
+  // table
+  std::vector<Affine<F>> table(points, points + n);
+  if (precomp) {
+    table.resize((size_t)n * pl.nwin);
+    for (int w = 1; w < pl.nwin; w++)
+      for (uint32_t i = 0; i < n; i++) table[(size_t)w * n + i] = msm_shift_point(table[(size_t)(w - 1) * n + i], c);
+  }
+  const size_t m = (size_t)n * pl.nwin;
+  std::vector<uint32_t> keys(m), vals(m);
+  for (uint32_t i = 0; i < n; i++) msm_decompose_one<Fr>(pl, i, scalars, keys.data(), vals.data());
+  std::vector<uint32_t> order(m);
+  std::iota(order.begin(), order.end(), 0u);
+  std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return keys[x] < keys[y]; });
+  std::vector<uint32_t> skeys(m), svals(m);
+  for (size_t k = 0; k < m; k++) { skeys[k] = keys[order[k]]; svals[k] = vals[order[k]]; }
+  // offsets
+  std::vector<uint32_t> off(pl.total_buckets + 1);
+  for (uint32_t b = 0; b <= pl.total_buckets; b++)
+    off[b] = (uint32_t)(std::lower_bound(skeys.begin(), skeys.end(), b) - skeys.begin());
+  // accumulate with tasks, then combine
+  std::vector<XYZZ<F>> buckets(pl.total_buckets);
+  for (uint32_t b = 0; b < pl.total_buckets; b++) {
+    XYZZ<F> acc = XYZZ<F>::inf();
+    for (uint32_t s = off[b]; s < off[b + 1]; s += pl.task_len) {
+      uint32_t e = std::min(off[b + 1], s + pl.task_len);
+      acc.add(msm_accumulate_range<F>(table.data(), svals.data(), s, e));
+    }
+    buckets[b] = acc;
+  }
+  // reduce
+  std::vector<XYZZ<F>> set_sums(pl.nsets);
+  for (int s = 0; s < pl.nsets; s++) {
+    XYZZ<F> tot = XYZZ<F>::inf();
+    for (uint32_t lo = 0; lo < pl.set_size; lo += pl.chunk) {
+      uint32_t hi = std::min(pl.set_size, lo + pl.chunk);
+      tot.add(msm_reduce_chunk<F>(buckets.data() + (size_t)s * pl.set_size, lo, hi));
+    }
+    set_sums[s] = tot;
+  }
+  XYZZ<F> res = msm_horner<F>(set_sums.data(), pl.nsets, c);
+  *reinterpret_cast<Jacobian<F>*>(out_jac) = res.to_jacobian();
+  return 0;
+}
+
+template <class Fr>
+int ntt_emu(void* data_, unsigned logn, int inverse, int decimation, int on_coset, const void* gen_mont,
+            const void* coset_mont) {
+  Fr* data = reinterpret_cast<Fr*>(data_);
+  NttDomainHost<Fr> dom;
+  dom.init(logn, gen_mont ? reinterpret_cast<const Fr*>(gen_mont) : nullptr,
+           coset_mont ? reinterpret_cast<const Fr*>(coset_mont) : nullptr);
+  dom.transform(data, inverse != 0, decimation, on_coset != 0);
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+// field_id = curve*2 + (0: fp, 1: fr)
+int emu_field_op(int field_id, int op, const void* a, const void* b, void* out) {
+  switch (field_id) {
+    case 0: return field_op<bn254_fp>(op, a, b, out);
+    case 1: return field_op<bn254_fr>(op, a, b, out);
+    case 2: return field_op<bls12_381_fp>(op, a, b, out);
+    case 3: return field_op<bls12_381_fr>(op, a, b, out);
+    case 4: return field_op<bls12_377_fp>(op, a, b, out);
+    case 5: return field_op<bls12_377_fr>(op, a, b, out);
+    case 6: return field_op<bw6_761_fp>(op, a, b, out);
+    case 7: return field_op<bw6_761_fr>(op, a, b, out);
+    case 100: return field_op<bn254_fp2>(op, a, b, out);
+    case 102: return field_op<bls12_381_fp2>(op, a, b, out);
+    case 104: return field_op<bls12_377_fp2>(op, a, b, out);
+  }
+  return -1;
+}
+
+int emu_msm(int curve, int group, const void* points, const void* scalars, uint32_t n, int c, int precomp,
+            uint32_t task_len, uint32_t chunk, void* out_jac) {
+  switch (curve * 2 + (group - 1)) {
+    case 0: return msm_emu<bn254_fr, bn254_fp>(points, scalars, n, c, precomp, task_len, chunk, out_jac);
+    case 1: return msm_emu<bn254_fr, bn254_fp2>(points, scalars, n, c, precomp, task_len, chunk, out_jac);
+    case 2: return msm_emu<bls12_381_fr, bls12_381_fp>(points, scalars, n, c, precomp, task_len, chunk, out_jac);
+    case 3: return msm_emu<bls12_381_fr, bls12_381_fp2>(points, scalars, n, c, precomp, task_len, chunk, out_jac);
+    case 4: return msm_emu<bls12_377_fr, bls12_377_fp>(points, scalars, n, c, precomp, task_len, chunk, out_jac);
+    case 5: return msm_emu<bls12_377_fr, bls12_377_fp2>(points, scalars, n, c, precomp, task_len, chunk, out_jac);
+    case 6:
+    case 7: return msm_emu<bw6_761_fr, bw6_761_fp>(points, scalars, n, c, precomp, task_len, chunk, out_jac);
+  }
+  return -1;
+}
+
+int emu_ntt(int curve, void* data, unsigned logn, int inverse, int decimation, int on_coset, const void* gen_mont,
+            const void* coset_mont) {
+  switch (curve) {
+    case 0: return ntt_emu<bn254_fr>(data, logn, inverse, decimation, on_coset, gen_mont, coset_mont);
+    case 1: return ntt_emu<bls12_381_fr>(data, logn, inverse, decimation, on_coset, gen_mont, coset_mont);
+    case 2: return ntt_emu<bls12_377_fr>(data, logn, inverse, decimation, on_coset, gen_mont, coset_mont);
+    case 3: return ntt_emu<bw6_761_fr>(data, logn, inverse, decimation, on_coset, gen_mont, coset_mont);
+  }
+  return -1;
+}
+
+}  // extern "C"

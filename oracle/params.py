@@ -1,0 +1,113 @@
+"""Curve / field parameters for the CPU oracle.  TEST INFRASTRUCTURE ONLY.
+
+Nothing under ``oracle/`` is part of the shipped product: only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl reference``
+legs may import it (as the checker / the timed CPU arm).
+
+PARITY UNPINNED: the reference holds no golden vectors for this path
+(SURVEY.md §8c); the arithmetic lives in the un-vendored module
+github.com/consensys/gnark-crypto v0.21.0 (go.mod:9).  The moduli below are
+the in-tree statements of the fields
+(std/math/emulated/emparams/emparams.go:142-330); curve coefficients a=0,b from
+std/algebra/emulated/sw_emulated/params.go:68-170 and
+std/algebra/native/sw_bls12377/pairing2.go:470-482.  Generators, 2-adic roots
+of unity and FrMultiplicativeGen are the public standard values of gnark-crypto
+and are property-checked in tests/test_oracle_params.py (on-curve, r*G = inf,
+w^(2^s) = 1, w^(2^(s-1)) = -1, g a quadratic non-residue).
+"""
+
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+
+@dataclass(frozen=True)
+class CurveParams:
+    name: str
+    curve_id: int            # id used across the C-ABI (include/gnark_b200.h)
+    p: int                   # base field modulus
+    r: int                   # scalar field modulus
+    fp_limbs: int            # 64-bit limbs of fp.Element
+    fr_limbs: int            # 64-bit limbs of fr.Element
+    b: int                   # G1: y^2 = x^3 + b
+    g1: Tuple[int, int]      # a point of order r on G1
+    fp2_nonresidue: Optional[int]   # u^2 = nonresidue; None => G2 is over Fp (BW6-761)
+    g2: Optional[tuple]      # a point on the twist ((x0,x1),(y0,y1)) or (x,y) for BW6
+    two_adicity: int         # s with 2^s | r-1
+    root_of_unity: int       # primitive 2^s-th root of unity in Fr (gnark-crypto's constant)
+    mult_gen: int            # fft.Domain.FrMultiplicativeGen
+
+    @property
+    def fp_bytes(self):
+        return 8 * self.fp_limbs
+
+    @property
+    def fr_bytes(self):
+        return 8 * self.fr_limbs
+
+    @property
+    def g2_degree(self):
+        return 1 if self.fp2_nonresidue is None else 2
+
+
+BN254 = CurveParams(
+    name="bn254", curve_id=0,
+    p=0x30644e72e131a029b85045b68181585d97816a916871ca8d3c208c16d87cfd47,
+    r=0x30644e72e131a029b85045b68181585d2833e84879b9709143e1f593f0000001,
+    fp_limbs=4, fr_limbs=4, b=3, g1=(1, 2),
+    fp2_nonresidue=-1,
+    g2=((10857046999023057135944570762232829481370756359578518086990519993285655852781,
+         11559732032986387107991004021392285783925812861821192530917403151452391805634),
+        (8495653923123431417604973247489272438418190587263600148770280649306958101930,
+         4082367875863433681332203403145435568316851327593401208105741076214120093531)),
+    two_adicity=28,
+    root_of_unity=19103219067921713944291392827692070036145651957329286315305642004821462161904,
+    mult_gen=5,
+)
+
+BLS12_381 = CurveParams(
+    name="bls12-381", curve_id=1,
+    p=0x1a0111ea397fe69a4b1ba7b6434bacd764774b84f38512bf6730d2a0f6b0f6241eabfffeb153ffffb9feffffffffaaab,
+    r=0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001,
+    fp_limbs=6, fr_limbs=4, b=4,
+    g1=(0x17f1d3a73197d7942695638c4fa9ac0fc3688c4f9774b905a14e3a3f171bac586c55e83ff97a1aeffb3af00adb22c6bb,
+        0x08b3f481e3aaa0f1a09e30ed741d8ae4fcf5e095d5d00af600db18cb2c04b3edd03cc744a2888ae40caa232946c5e7e1),
+    fp2_nonresidue=-1,
+    g2=((0x024aa2b2f08f0a91260805272dc51051c6e47ad4fa403b02b4510b647ae3d1770bac0326a805bbefd48056c8c121bdb8,
+         0x13e02b6052719f607dacd3a088274f65596bd0d09920b61ab5da61bbdc7f5049334cf11213945d57e5ac7d055d042b7e),
+        (0x0ce5d527727d6e118cc9cdc6da2e351aadfd9baa8cbdd3a76d429a695160d12c923ac9cc3baca289e193548608b82801,
+         0x0606c4a02ea734cc32acd2b02bc28b99cb3e287e85a763af267492ab572e99ab3f370d275cec1da1aaa9075ff05f79be)),
+    two_adicity=32,
+    root_of_unity=10238227357739495823651030575849232062558860180284477541189508159991286009131,
+    mult_gen=7,
+)
+
+BLS12_377 = CurveParams(
+    name="bls12-377", curve_id=2,
+    p=0x1ae3a4617c510eac63b05c06ca1493b1a22d9f300f5138f1ef3622fba094800170b5d44300000008508c00000000001,
+    r=0x12ab655e9a2ca55660b44d1e5c37b00159aa76fed00000010a11800000000001,
+    fp_limbs=6, fr_limbs=4, b=1,
+    # derived in oracle/derive.py when the recalled public value fails its property check
+    g1=(0x008848defe740a67c8fc6225bf87ff5485951e2caa9d41bb188282c8bd37cb5cd5481512ffcd394eeab9b16eb21be9ef,
+        0x01914a69c5102eff1f674f5d30afeec4bd7fb348ca3e52d96d182ad44fb82305c2fe3d3634a9591afd82de55559c8ea6),
+    fp2_nonresidue=-5,
+    g2=None,
+    two_adicity=47,
+    root_of_unity=8065159656716812877374967518403273466521432693661810619979959746626482506078,
+    mult_gen=22,
+)
+
+BW6_761 = CurveParams(
+    name="bw6-761", curve_id=3,
+    p=0x122e824fb83ce0ad187c94004faff3eb926186a81d14688528275ef8087be41707ba638e584e91903cebaff25b423048689c8ed12f9fd9071dcd3dc73ebff2e98a116c25667a8f8160cf8aeeaf0a437e6913e6870000082f49d00000000008b,
+    r=0x1ae3a4617c510eac63b05c06ca1493b1a22d9f300f5138f1ef3622fba094800170b5d44300000008508c00000000001,
+    fp_limbs=12, fr_limbs=6, b=-1,
+    g1=None,   # filled by oracle/derive.py (cofactor-cleared point; gnark-crypto's constant not recalled)
+    fp2_nonresidue=None,
+    g2=None,
+    two_adicity=46,
+    root_of_unity=32863578547254505029601261939868325669770508939375122462904745766352256812585773382134936404344547323199885654433,
+    mult_gen=15,
+)
+
+CURVES = {c.name: c for c in (BN254, BLS12_381, BLS12_377, BW6_761)}
+CURVES_BY_ID = {c.curve_id: c for c in CURVES.values()}
