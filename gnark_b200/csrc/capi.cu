@@ -1,0 +1,419 @@
+// C ABI of libgnark_b200.so (declared in include/gnark_b200.h): runtime, memory,
+// MSM base tables, MSM, NTT, vector ops.  The Groth16 host layer lives in
+// groth16_host.cu.  Requires a CUDA device: there is no CPU fallback.
+#include "capi_common.h"
+
+namespace gb200 {
+
+// ---- registries ------------------------------------------------------------
+static const MsmOps* g_msm_ops[4][3];
+static const NttOps* g_ntt_ops[4];
+static const HostGroupOps* g_host_ops[4][3];
+void register_msm_ops(int curve, int group, const MsmOps* ops) { g_msm_ops[curve][group] = ops; }
+void register_ntt_ops(int curve, const NttOps* ops) { g_ntt_ops[curve] = ops; }
+void register_host_group_ops(int curve, int group, const HostGroupOps* ops) { g_host_ops[curve][group] = ops; }
+const MsmOps* get_msm_ops(int curve, int group) {
+  if (curve < 0 || curve > 3 || group < 1 || group > 2) return nullptr;
+  return g_msm_ops[curve][group];
+}
+const NttOps* get_ntt_ops(int curve) { return (curve < 0 || curve > 3) ? nullptr : g_ntt_ops[curve]; }
+const HostGroupOps* get_host_group_ops(int curve, int group) {
+  if (curve < 0 || curve > 3 || group < 1 || group > 2) return nullptr;
+  return g_host_ops[curve][group];
+}
+
+// ---- error + device context --------------------------------------------------
+thread_local std::string g_last_error;
+int32_t set_error(const std::string& msg) { g_last_error = msg; return 1; }
+int32_t cuda_fail(const char* what, cudaError_t e) {
+  g_last_error = std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
+  return 2;
+}
+
+static std::mutex g_ctx_mu;
+static DeviceCtx g_ctx[GB200_MAX_DEVICES];
+
+int32_t device_ctx(int dev, DeviceCtx** out) {
+  if (dev < 0 || dev >= GB200_MAX_DEVICES) return set_error("invalid device id " + std::to_string(dev));
+  std::lock_guard<std::mutex> lk(g_ctx_mu);
+  DeviceCtx& c = g_ctx[dev];
+  if (!c.ready) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess) return cuda_fail("cudaGetDeviceCount (a CUDA device is required; no CPU fallback)", e);
+    if (dev >= count) return set_error("device " + std::to_string(dev) + " not present (" + std::to_string(count) + " visible)");
+    CK(cudaSetDevice(dev));
+    CK(cudaStreamCreateWithFlags(&c.own_stream, cudaStreamNonBlocking));
+    c.stream = c.own_stream;
+    cudaMemPool_t pool;
+    CK(cudaDeviceGetDefaultMemPool(&pool, dev));
+    uint64_t thr = UINT64_MAX;  // keep freed workspace cached in the pool
+    CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    c.dev = dev;
+    c.ready = true;
+  }
+  cudaError_t e = cudaSetDevice(dev);
+  if (e != cudaSuccess) return cuda_fail("cudaSetDevice", e);
+  *out = &c;
+  return 0;
+}
+
+// MSM tuning (mirrors the reference's env knob ICICLE_MSM_MAX_WINDOW, icicle.go:586-598)
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+int msm_window_for(size_t n) {
+  int c = env_int("GB200_MSM_WINDOW", 0);
+  if (c > 0) return c < 2 ? 2 : (c > 24 ? 24 : c);
+  int lg = 0;
+  while ((1ull << (lg + 1)) <= n) lg++;
+  c = lg - 4;
+  if (c < 4) c = 4;
+  if (c > 16) c = 16;
+  return c;
+}
+void msm_tuning(size_t n, int nwin, int c, uint32_t* task_len, uint32_t* chunk) {
+  const size_t m = n * (size_t)nwin;
+  size_t tl = m / 150000;
+  if (tl < 8) tl = 8;
+  if (tl > 64) tl = 64;
+  *task_len = (uint32_t)env_int("GB200_MSM_TASK_LEN", (int)tl);
+  *chunk = (uint32_t)env_int("GB200_MSM_CHUNK", c >= 12 ? 8 : 4);
+}
+
+int32_t msm_on_stream(DeviceCtx* ctx, b200_table_s* t, size_t off, size_t n, const void* d_scalars, void* d_out) {
+  if (off + n > t->n) return set_error("msm: range [off, off+n) exceeds the table");
+  uint32_t task_len, chunk;
+  msm_tuning(n, t->nwin, t->c, &task_len, &chunk);
+  size_t ws_bytes = 0;
+  CK(t->ops->ws_bytes((uint32_t)n, (uint32_t)t->n, t->c, t->precomp, task_len, chunk, &ws_bytes));
+  void* ws = nullptr;
+  CK(cudaMallocAsync(&ws, ws_bytes, ctx->stream));
+  cudaError_t e = t->ops->run(ctx->stream, (uint32_t)n, (uint32_t)t->n, (uint32_t)off, t->c, t->precomp, task_len, chunk,
+                              t->d_points, d_scalars, d_out, ws);
+  cudaError_t e2 = cudaFreeAsync(ws, ctx->stream);
+  if (e != cudaSuccess) return cuda_fail("msm enqueue", e);
+  if (e2 != cudaSuccess) return cuda_fail("cudaFreeAsync", e2);
+  return 0;
+}
+
+}  // namespace gb200
+
+using namespace gb200;
+
+extern "C" {
+
+const char* b200_version(void) { return "gnark_b200 0.1.0 (sm_100a)"; }
+const char* b200_last_error(void) { return g_last_error.c_str(); }
+
+int32_t b200_device_count(int32_t* out) {
+  GUARD_BEGIN
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess) return cuda_fail("cudaGetDeviceCount", e);
+  *out = count;
+  return 0;
+  GUARD_END
+}
+
+int32_t b200_init(int32_t n_dev, const int32_t* dev_ids) {
+  GUARD_BEGIN
+  if (n_dev <= 0 || !dev_ids) { DeviceCtx* c; return device_ctx(0, &c); }
+  for (int i = 0; i < n_dev; i++) { DeviceCtx* c; int32_t rc = device_ctx(dev_ids[i], &c); if (rc) return rc; }
+  return 0;
+  GUARD_END
+}
+
+int32_t b200_shutdown(void) {
+  GUARD_BEGIN
+  std::lock_guard<std::mutex> lk(g_ctx_mu);
+  for (int d = 0; d < GB200_MAX_DEVICES; d++) {
+    DeviceCtx& c = g_ctx[d];
+    if (!c.ready) continue;
+    cudaSetDevice(d);
+    cudaStreamSynchronize(c.stream);
+    cudaStreamDestroy(c.own_stream);
+    c = DeviceCtx();
+  }
+  return 0;
+  GUARD_END
+}
+
+int32_t b200_set_stream(int32_t dev, void* stream) {
+  GUARD_BEGIN
+  DeviceCtx* c; int32_t rc = device_ctx(dev, &c); if (rc) return rc;
+  c->stream = stream ? reinterpret_cast<cudaStream_t>(stream) : c->own_stream;
+  return 0;
+  GUARD_END
+}
+
+int32_t b200_sync(int32_t dev) {
+  GUARD_BEGIN
+  DeviceCtx* c; int32_t rc = device_ctx(dev, &c); if (rc) return rc;
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+  GUARD_END
+}
+
+int32_t b200_alloc(int32_t dev, size_t bytes, void** out) {
+  GUARD_BEGIN
+  DeviceCtx* c; int32_t rc = device_ctx(dev, &c); if (rc) return rc;
+  CK(cudaMalloc(out, bytes ? bytes : 1));
+  return 0;
+  GUARD_END
+}
+int32_t b200_free(int32_t dev, void* p) {
+  GUARD_BEGIN
+  DeviceCtx* c; int32_t rc = device_ctx(dev, &c); if (rc) return rc;
+  CK(cudaStreamSynchronize(c->stream));
+  CK(cudaFree(p));
+  return 0;
+  GUARD_END
+}
+int32_t b200_h2d(int32_t dev, void* dst, const void* src, size_t bytes) {
+  GUARD_BEGIN
+  DeviceCtx* c; int32_t rc = device_ctx(dev, &c); if (rc) return rc;
+  CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaStreamSynchronize(c->stream));  // host pointer is only borrowed for the call
+  return 0;
+  GUARD_END
+}
+int32_t b200_d2h(int32_t dev, void* dst, const void* src, size_t bytes) {
+  GUARD_BEGIN
+  DeviceCtx* c; int32_t rc = device_ctx(dev, &c); if (rc) return rc;
+  CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+  GUARD_END
+}
+int32_t b200_host_alloc(size_t bytes, void** out) {
+  GUARD_BEGIN
+  CK(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+  return 0;
+  GUARD_END
+}
+int32_t b200_host_free(void* p) {
+  GUARD_BEGIN
+  CK(cudaFreeHost(p));
+  return 0;
+  GUARD_END
+}
+
+// ---- tables ------------------------------------------------------------------
+int32_t b200_table_upload(int32_t dev, int32_t curve, int32_t group, const void* points, size_t n, int32_t flags,
+                          b200_table_t* out) {
+  GUARD_BEGIN
+  DeviceCtx* ctx; int32_t rc = device_ctx(dev, &ctx); if (rc) return rc;
+  const MsmOps* ops = get_msm_ops(curve, group);
+  if (!ops) return set_error("table_upload: unsupported curve/group");
+  if (n && !points) return set_error("table_upload: null points");
+  std::unique_ptr<b200_table_s> t(new b200_table_s());
+  t->dev = dev; t->curve = curve; t->group = group; t->n = n; t->ops = ops;
+  t->c = msm_window_for(n ? n : 1);
+  t->nwin = msm_num_windows(ops->scalar_bits, t->c);
+  t->precomp = (flags & B200_TABLE_PRECOMP) ? 1 : 0;
+  if (env_int("GB200_MSM_PRECOMP", -1) >= 0) t->precomp = env_int("GB200_MSM_PRECOMP", 0) ? 1 : 0;
+  const size_t slabs = t->precomp ? (size_t)t->nwin : 1;
+  if (slabs * n >= (1ull << 31)) return set_error("table_upload: table too large for 31-bit point indices; shard it");
+  t->bytes = slabs * (n ? n : 1) * ops->affine_bytes;
+  CK(cudaMalloc(&t->d_points, t->bytes));
+  const cudaMemcpyKind kind = (flags & B200_TABLE_SRC_ON_DEVICE) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  if (n) CK(cudaMemcpyAsync(t->d_points, points, n * ops->affine_bytes, kind, ctx->stream));
+  if (t->precomp) CK(ops->precompute(ctx->stream, (uint32_t)n, t->nwin, t->c, t->d_points));
+  CK(cudaStreamSynchronize(ctx->stream));
+  *out = t.release();
+  return 0;
+  GUARD_END
+}
+
+int32_t b200_table_free(b200_table_t t) {
+  GUARD_BEGIN
+  if (!t) return 0;
+  DeviceCtx* ctx; int32_t rc = device_ctx(t->dev, &ctx); if (rc) return rc;
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaFree(t->d_points));
+  delete t;
+  return 0;
+  GUARD_END
+}
+
+int32_t b200_table_info(b200_table_t t, size_t* n, int32_t* c, int32_t* nwin, int32_t* precomp, size_t* bytes) {
+  GUARD_BEGIN
+  if (!t) return set_error("table_info: null table");
+  if (n) *n = t->n;
+  if (c) *c = t->c;
+  if (nwin) *nwin = t->nwin;
+  if (precomp) *precomp = t->precomp;
+  if (bytes) *bytes = t->bytes;
+  return 0;
+  GUARD_END
+}
+
+// ---- MSM -----------------------------------------------------------------------
+int32_t b200_msm_async(b200_table_t t, size_t off, size_t n, const void* d_scalars, void* d_out) {
+  GUARD_BEGIN
+  if (!t) return set_error("msm: null table");
+  DeviceCtx* ctx; int32_t rc = device_ctx(t->dev, &ctx); if (rc) return rc;
+  return msm_on_stream(ctx, t, off, n, d_scalars, d_out);
+  GUARD_END
+}
+
+int32_t b200_msm(b200_table_t t, size_t off, size_t n, const void* scalars, int32_t on_dev, void* out_host) {
+  GUARD_BEGIN
+  if (!t) return set_error("msm: null table");
+  if (n && !scalars) return set_error("msm: null scalars");
+  DeviceCtx* ctx; int32_t rc = device_ctx(t->dev, &ctx); if (rc) return rc;
+  void* d_sc = nullptr;
+  void* d_out = nullptr;
+  CK(cudaMallocAsync(&d_out, t->ops->jac_bytes, ctx->stream));
+  const void* sc = scalars;
+  if (!on_dev && n) {
+    CK(cudaMallocAsync(&d_sc, n * t->ops->fr_bytes, ctx->stream));
+    CK(cudaMemcpyAsync(d_sc, scalars, n * t->ops->fr_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    sc = d_sc;
+  }
+  rc = msm_on_stream(ctx, t, off, n, sc, d_out);
+  if (rc == 0) {
+    cudaError_t e = cudaMemcpyAsync(out_host, d_out, t->ops->jac_bytes, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e != cudaSuccess) rc = cuda_fail("msm result copy", e);
+  }
+  if (d_sc) cudaFreeAsync(d_sc, ctx->stream);
+  cudaFreeAsync(d_out, ctx->stream);
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  if (rc) return rc;
+  if (e != cudaSuccess) return cuda_fail("msm", e);
+  return 0;
+  GUARD_END
+}
+
+int32_t b200_msm_g1(b200_table_t t, size_t off, size_t n, const void* s, int32_t on_dev, void* out) {
+  if (t && t->group != 1) return set_error("msm_g1: table holds G2 points");
+  return b200_msm(t, off, n, s, on_dev, out);
+}
+int32_t b200_msm_g2(b200_table_t t, size_t off, size_t n, const void* s, int32_t on_dev, void* out) {
+  if (t && t->group != 2) return set_error("msm_g2: table holds G1 points");
+  return b200_msm(t, off, n, s, on_dev, out);
+}
+
+// ---- NTT -----------------------------------------------------------------------
+int32_t b200_ntt_domain_new(int32_t dev, int32_t curve, uint32_t log2n, const void* gen, const void* coset,
+                            b200_domain_t* out) {
+  GUARD_BEGIN
+  DeviceCtx* ctx; int32_t rc = device_ctx(dev, &ctx); if (rc) return rc;
+  const NttOps* ops = get_ntt_ops(curve);
+  if (!ops) return set_error("ntt_domain_new: unsupported curve");
+  if ((int)log2n > ops->two_adicity || log2n > 30)
+    return set_error("ntt_domain_new: log2n exceeds the field's 2-adicity / supported size");
+  cudaError_t e = cudaSuccess;
+  void* impl = ops->domain_new(ctx->stream, (int)log2n, gen, coset, &e);
+  if (!impl) return cuda_fail("ntt_domain_new", e);
+  b200_domain_s* d = new b200_domain_s();
+  d->dev = dev; d->curve = curve; d->logn = (int)log2n; d->ops = ops; d->impl = impl;
+  *out = d;
+  return 0;
+  GUARD_END
+}
+
+int32_t b200_ntt_domain_free(b200_domain_t d) {
+  GUARD_BEGIN
+  if (!d) return 0;
+  DeviceCtx* ctx; int32_t rc = device_ctx(d->dev, &ctx); if (rc) return rc;
+  CK(cudaStreamSynchronize(ctx->stream));
+  d->ops->domain_free(d->impl);
+  delete d;
+  return 0;
+  GUARD_END
+}
+
+int32_t b200_ntt_async(b200_domain_t d, void* d_data, int32_t inverse, int32_t decimation, int32_t on_coset) {
+  GUARD_BEGIN
+  if (!d) return set_error("ntt: null domain");
+  if (decimation != B200_DIF && decimation != B200_DIT) return set_error("ntt: decimation must be DIF or DIT");
+  DeviceCtx* ctx; int32_t rc = device_ctx(d->dev, &ctx); if (rc) return rc;
+  CK(d->ops->ntt(ctx->stream, d->impl, d_data, inverse, decimation, on_coset));
+  return 0;
+  GUARD_END
+}
+
+int32_t b200_ntt(b200_domain_t d, void* data, int32_t on_dev, int32_t inverse, int32_t decimation, int32_t on_coset) {
+  GUARD_BEGIN
+  if (!d) return set_error("ntt: null domain");
+  if (decimation != B200_DIF && decimation != B200_DIT) return set_error("ntt: decimation must be DIF or DIT");
+  DeviceCtx* ctx; int32_t rc = device_ctx(d->dev, &ctx); if (rc) return rc;
+  const size_t bytes = ((size_t)1 << d->logn) * d->ops->fr_bytes;
+  void* buf = data;
+  if (!on_dev) {
+    CK(cudaMallocAsync(&buf, bytes, ctx->stream));
+    CK(cudaMemcpyAsync(buf, data, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  cudaError_t e = d->ops->ntt(ctx->stream, d->impl, buf, inverse, decimation, on_coset);
+  if (!on_dev) {
+    if (e == cudaSuccess) e = cudaMemcpyAsync(data, buf, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaFreeAsync(buf, ctx->stream);
+  }
+  cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) return cuda_fail("ntt", e);
+  if (e2 != cudaSuccess) return cuda_fail("ntt", e2);
+  return 0;
+  GUARD_END
+}
+
+int32_t b200_groth16_compute_h(b200_domain_t d, const void* a, const void* b, const void* c, size_t len,
+                               int32_t in_dev, void* h_out, int32_t out_dev) {
+  GUARD_BEGIN
+  if (!d) return set_error("compute_h: null domain");
+  DeviceCtx* ctx; int32_t rc = device_ctx(d->dev, &ctx); if (rc) return rc;
+  const size_t n = (size_t)1 << d->logn;
+  if (len > n) return set_error("compute_h: len exceeds the domain");
+  const size_t fb = d->ops->fr_bytes;
+  void* v[3] = {nullptr, nullptr, nullptr};
+  const void* src[3] = {a, b, c};
+  const cudaMemcpyKind kind = in_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  for (int k = 0; k < 3; k++) {
+    CK(cudaMallocAsync(&v[k], n * fb, ctx->stream));
+    if (len) CK(cudaMemcpyAsync(v[k], src[k], len * fb, kind, ctx->stream));
+    if (len < n) CK(cudaMemsetAsync((char*)v[k] + len * fb, 0, (n - len) * fb, ctx->stream));
+  }
+  cudaError_t e = d->ops->compute_h(ctx->stream, d->impl, v[0], v[1], v[2]);
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(h_out, v[0], n * fb, out_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->stream);
+  for (int k = 0; k < 3; k++) cudaFreeAsync(v[k], ctx->stream);
+  cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) return cuda_fail("compute_h", e);
+  if (e2 != cudaSuccess) return cuda_fail("compute_h", e2);
+  return 0;
+  GUARD_END
+}
+
+// ---- vector ops -----------------------------------------------------------------
+int32_t b200_vec_op(int32_t dev, int32_t curve, int32_t op, void* out, const void* a, const void* b, size_t n) {
+  GUARD_BEGIN
+  DeviceCtx* ctx; int32_t rc = device_ctx(dev, &ctx); if (rc) return rc;
+  const NttOps* ops = get_ntt_ops(curve);
+  if (!ops) return set_error("vec_op: unsupported curve");
+  if (op < 0 || op > 2) return set_error("vec_op: unknown op");
+  CK(ops->vec_op(ctx->stream, op, out, a, b, n));
+  return 0;
+  GUARD_END
+}
+int32_t b200_vec_bit_reverse(int32_t dev, int32_t curve, void* data, uint32_t log2n) {
+  GUARD_BEGIN
+  DeviceCtx* ctx; int32_t rc = device_ctx(dev, &ctx); if (rc) return rc;
+  const NttOps* ops = get_ntt_ops(curve);
+  if (!ops) return set_error("vec_bit_reverse: unsupported curve");
+  CK(ops->bit_reverse(ctx->stream, data, log2n));
+  return 0;
+  GUARD_END
+}
+int32_t b200_vec_scale_powers(int32_t dev, int32_t curve, void* data, size_t n, const void* s, const void* g) {
+  GUARD_BEGIN
+  DeviceCtx* ctx; int32_t rc = device_ctx(dev, &ctx); if (rc) return rc;
+  const NttOps* ops = get_ntt_ops(curve);
+  if (!ops) return set_error("vec_scale_powers: unsupported curve");
+  CK(ops->scale_powers(ctx->stream, data, n, s, g));
+  return 0;
+  GUARD_END
+}
+
+}  // extern "C"

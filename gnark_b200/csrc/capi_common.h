@@ -1,0 +1,65 @@
+// shared between capi.cu and groth16_host.cu
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdlib>
+#include <cstring>
+#include <exception>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/gnark_b200.h"
+#include "internal.h"
+#include "msm.cuh"
+
+#define GB200_MAX_DEVICES 16
+
+namespace gb200 {
+
+struct DeviceCtx {
+  bool ready = false;
+  int dev = 0;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;  // own_stream or the caller's (b200_set_stream)
+};
+
+int32_t set_error(const std::string& msg);
+int32_t cuda_fail(const char* what, cudaError_t e);
+int32_t device_ctx(int dev, DeviceCtx** out);
+int msm_window_for(size_t n);
+void msm_tuning(size_t n, int nwin, int c, uint32_t* task_len, uint32_t* chunk);
+
+}  // namespace gb200
+
+struct b200_table_s {
+  int dev, curve, group;
+  size_t n;          // bases
+  int c, nwin, precomp;
+  size_t bytes;
+  void* d_points = nullptr;
+  const gb200::MsmOps* ops;
+};
+
+struct b200_domain_s {
+  int dev, curve, logn;
+  const gb200::NttOps* ops;
+  void* impl;
+};
+
+namespace gb200 {
+int32_t msm_on_stream(DeviceCtx* ctx, b200_table_s* t, size_t off, size_t n, const void* d_scalars, void* d_out);
+}
+
+#define CK(x)                                                        \
+  do {                                                               \
+    cudaError_t e_ = (x);                                            \
+    if (e_ != cudaSuccess) return gb200::cuda_fail(#x, e_);          \
+  } while (0)
+
+#define GUARD_BEGIN try {
+#define GUARD_END                                                               \
+  }                                                                             \
+  catch (const std::exception& ex) { return gb200::set_error(std::string("exception: ") + ex.what()); } \
+  catch (...) { return gb200::set_error("unknown exception"); }

@@ -1,0 +1,209 @@
+// Groth16 prover host layer: the B200 twin of
+// backend/accelerated/icicle/groth16/bn254/icicle.go (setupDevicePointers :88-264,
+// Prove :784-1360, computeH :1391-1488) and of the CPU prover
+// backend/groth16/bn254/prove.go:52-315, from "solved witness" to "proof points".
+// The R1CS solver (constraint/bn254/solver.go) stays in Go and is out of scope.
+#include "capi_common.h"
+
+using namespace gb200;
+
+struct b200_pk_s {
+  int dev = 0, curve = 0;
+  int logn = 0;
+  size_t n = 0;  // domain cardinality
+  b200_domain_t dom = nullptr;
+  b200_table_t A = nullptr, B1 = nullptr, Z = nullptr, K = nullptr, B2 = nullptr;
+  std::vector<uint8_t> alpha, beta, delta, beta2, delta2;
+  uint32_t* d_idx_a = nullptr;
+  uint32_t* d_idx_b = nullptr;
+  size_t n_a = 0, n_b = 0, nb_wires = 0, nb_public = 0;
+  const HostGroupOps* h1 = nullptr;
+  const HostGroupOps* h2 = nullptr;
+  const NttOps* fr = nullptr;
+  std::mutex mu;  // one proof at a time per key (device buffers are per call, tables are read-only)
+};
+
+static std::vector<uint8_t> copy_bytes(const void* p, size_t n) {
+  const uint8_t* b = reinterpret_cast<const uint8_t*>(p);
+  return std::vector<uint8_t>(b, b + n);
+}
+
+extern "C" {
+
+int32_t b200_point_add_jac(int32_t curve, int32_t group, void* acc, const void* q) {
+  GUARD_BEGIN
+  const HostGroupOps* h = get_host_group_ops(curve, group);
+  if (!h) return set_error("point_add_jac: unsupported curve/group");
+  h->add_jac(acc, q);
+  return 0;
+  GUARD_END
+}
+int32_t b200_point_to_affine(int32_t curve, int32_t group, const void* p, void* out) {
+  GUARD_BEGIN
+  const HostGroupOps* h = get_host_group_ops(curve, group);
+  if (!h) return set_error("point_to_affine: unsupported curve/group");
+  h->to_affine(p, out);
+  return 0;
+  GUARD_END
+}
+
+int32_t b200_groth16_pk_free(b200_pk_t pk);
+
+int32_t b200_groth16_pk_load(int32_t dev, const b200_groth16_pk_desc* d, b200_pk_t* out) {
+  GUARD_BEGIN
+  if (!d || !out) return set_error("pk_load: null argument");
+  DeviceCtx* ctx; int32_t rc = device_ctx(dev, &ctx); if (rc) return rc;
+  const HostGroupOps* h1 = get_host_group_ops(d->curve, 1);
+  const HostGroupOps* h2 = get_host_group_ops(d->curve, 2);
+  const NttOps* fr = get_ntt_ops(d->curve);
+  if (!h1 || !h2 || !fr) return set_error("pk_load: unsupported curve");
+  if (d->domain_size == 0 || (d->domain_size & (d->domain_size - 1))) return set_error("pk_load: domain size must be a power of two");
+  if (d->n_z + 1 != d->domain_size) return set_error("pk_load: len(G1.Z) must be domain size - 1");
+  if (d->n_b2 != d->n_b) return set_error("pk_load: len(G2.B) != len(G1.B)");
+  if (d->nb_public > d->nb_wires || d->n_k != d->nb_wires - d->nb_public)
+    return set_error("pk_load: len(G1.K) must equal nb_wires - nb_public (BSB22 commitments are not supported by this entry point)");
+  std::unique_ptr<b200_pk_s> pk(new b200_pk_s());
+  pk->dev = dev; pk->curve = d->curve; pk->n = d->domain_size;
+  while ((1ull << pk->logn) < pk->n) pk->logn++;
+  pk->h1 = h1; pk->h2 = h2; pk->fr = fr;
+  pk->nb_wires = d->nb_wires; pk->nb_public = d->nb_public;
+  pk->alpha = copy_bytes(d->g1_alpha, h1->affine_bytes);
+  pk->beta = copy_bytes(d->g1_beta, h1->affine_bytes);
+  pk->delta = copy_bytes(d->g1_delta, h1->affine_bytes);
+  pk->beta2 = copy_bytes(d->g2_beta, h2->affine_bytes);
+  pk->delta2 = copy_bytes(d->g2_delta, h2->affine_bytes);
+  // wire filters (prove.go:147-168): indices of wires whose A / B base is not infinity
+  std::vector<uint32_t> ia, ib;
+  for (size_t i = 0; i < d->nb_wires; i++) {
+    if (!d->infinity_a[i]) ia.push_back((uint32_t)i);
+    if (!d->infinity_b[i]) ib.push_back((uint32_t)i);
+  }
+  if (ia.size() != d->n_a || ib.size() != d->n_b) return set_error("pk_load: infinity flags inconsistent with len(G1.A)/len(G1.B)");
+  pk->n_a = ia.size(); pk->n_b = ib.size();
+  b200_pk_t raw = pk.get();
+#define PK_TRY(x) do { int32_t rc_ = (x); if (rc_) { std::string m = b200_last_error(); b200_groth16_pk_free(pk.release()); set_error(m); return rc_; } } while (0)
+  PK_TRY(b200_ntt_domain_new(dev, d->curve, (uint32_t)pk->logn, d->domain_gen, d->coset_gen, &raw->dom));
+  PK_TRY(b200_table_upload(dev, d->curve, 1, d->g1_a, d->n_a, d->flags, &raw->A));
+  PK_TRY(b200_table_upload(dev, d->curve, 1, d->g1_b, d->n_b, d->flags, &raw->B1));
+  PK_TRY(b200_table_upload(dev, d->curve, 1, d->g1_z, d->n_z, d->flags, &raw->Z));
+  PK_TRY(b200_table_upload(dev, d->curve, 1, d->g1_k, d->n_k, d->flags, &raw->K));
+  PK_TRY(b200_table_upload(dev, d->curve, 2, d->g2_b, d->n_b2, d->flags, &raw->B2));
+  auto up = [&](const std::vector<uint32_t>& v, uint32_t** dptr) -> int32_t {
+    CK(cudaMalloc(dptr, (v.size() ? v.size() : 1) * sizeof(uint32_t)));
+    if (!v.empty()) CK(cudaMemcpy(*dptr, v.data(), v.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    return 0;
+  };
+  PK_TRY(up(ia, &raw->d_idx_a));
+  PK_TRY(up(ib, &raw->d_idx_b));
+#undef PK_TRY
+  *out = pk.release();
+  return 0;
+  GUARD_END
+}
+
+int32_t b200_groth16_pk_free(b200_pk_t pk) {
+  GUARD_BEGIN
+  if (!pk) return 0;
+  DeviceCtx* ctx; int32_t rc = device_ctx(pk->dev, &ctx); if (rc) return rc;
+  cudaStreamSynchronize(ctx->stream);
+  b200_table_free(pk->A); b200_table_free(pk->B1); b200_table_free(pk->Z); b200_table_free(pk->K); b200_table_free(pk->B2);
+  b200_ntt_domain_free(pk->dom);
+  cudaFree(pk->d_idx_a); cudaFree(pk->d_idx_b);
+  delete pk;
+  return 0;
+  GUARD_END
+}
+
+int32_t b200_groth16_prove(b200_pk_t pk, const void* wires, const void* a, const void* b, const void* c,
+                           size_t n_constraints, const void* r, const void* s, void* ar_out, void* bs_out,
+                           void* krs_out, void* msm_out) {
+  GUARD_BEGIN
+  if (!pk) return set_error("prove: null proving key");
+  if (!wires || !a || !b || !c || !r || !s || !ar_out || !bs_out || !krs_out) return set_error("prove: null argument");
+  if (n_constraints > pk->n) return set_error("prove: more constraints than the domain holds");
+  std::lock_guard<std::mutex> lk(pk->mu);
+  DeviceCtx* ctx; int32_t rc = device_ctx(pk->dev, &ctx); if (rc) return rc;
+  cudaStream_t st = ctx->stream;
+  const size_t fb = pk->fr->fr_bytes;
+  const size_t n = pk->n;
+  const size_t j1 = pk->h1->jac_bytes, j2 = pk->h2->jac_bytes;
+
+  struct Bufs {
+    cudaStream_t st; std::vector<void*> p;
+    ~Bufs() { for (void* q : p) cudaFreeAsync(q, st); }
+    cudaError_t get(void** out, size_t bytes) { cudaError_t e = cudaMallocAsync(out, bytes ? bytes : 1, st); if (e == cudaSuccess) p.push_back(*out); return e; }
+  } bufs{st, {}};
+  void *d_w, *d_a, *d_b, *d_c, *d_wa, *d_wb, *d_res;
+  CK(bufs.get(&d_w, pk->nb_wires * fb));
+  CK(bufs.get(&d_a, n * fb)); CK(bufs.get(&d_b, n * fb)); CK(bufs.get(&d_c, n * fb));
+  CK(bufs.get(&d_wa, pk->n_a * fb)); CK(bufs.get(&d_wb, pk->n_b * fb));
+  CK(bufs.get(&d_res, 4 * j1 + j2));
+
+  // upload the solution (R1CSSolution{W,A,B,C}); pad A,B,C to the domain (prove.go:356-359)
+  CK(cudaMemcpyAsync(d_w, wires, pk->nb_wires * fb, cudaMemcpyHostToDevice, st));
+  const void* src[3] = {a, b, c};
+  void* dst[3] = {d_a, d_b, d_c};
+  for (int k = 0; k < 3; k++) {
+    if (n_constraints) CK(cudaMemcpyAsync(dst[k], src[k], n_constraints * fb, cudaMemcpyHostToDevice, st));
+    if (n_constraints < n) CK(cudaMemsetAsync((char*)dst[k] + n_constraints * fb, 0, (n - n_constraints) * fb, st));
+  }
+  // h (bit-reversed, Montgomery) - prove.go:134,346-389
+  CK(pk->fr->compute_h(st, pk->dom->impl, d_a, d_b, d_c));
+  // wire filtering - prove.go:147-168
+  CK(pk->fr->gather(st, d_wa, d_w, pk->d_idx_a, pk->n_a));
+  CK(pk->fr->gather(st, d_wb, d_w, pk->d_idx_b, pk->n_b));
+  // the five MSMs - prove.go:207 (Ar), :194 (Bs1), :227 (Krs2 over h), :237 (Krs), :283 (Bs2)
+  char* res = reinterpret_cast<char*>(d_res);
+  rc = msm_on_stream(ctx, pk->A, 0, pk->n_a, d_wa, res + 0 * j1); if (rc) return rc;
+  rc = msm_on_stream(ctx, pk->B1, 0, pk->n_b, d_wb, res + 1 * j1); if (rc) return rc;
+  rc = msm_on_stream(ctx, pk->Z, 0, n - 1, d_a, res + 2 * j1); if (rc) return rc;
+  rc = msm_on_stream(ctx, pk->K, 0, pk->nb_wires - pk->nb_public, (char*)d_w + pk->nb_public * fb, res + 3 * j1); if (rc) return rc;
+  rc = msm_on_stream(ctx, pk->B2, 0, pk->n_b, d_wb, res + 4 * j1); if (rc) return rc;
+  std::vector<uint8_t> host(4 * j1 + j2);
+  CK(cudaMemcpyAsync(host.data(), d_res, host.size(), cudaMemcpyDeviceToHost, st));
+
+  // host work that does not depend on the MSMs overlaps with them: deltas = [r, s, -rs] * delta (prove.go:185)
+  const HostGroupOps* h1 = pk->h1;
+  const HostGroupOps* h2 = pk->h2;
+  std::vector<uint8_t> kr(fb), rd(j1), sd(j1), krd(j1), sd2(j2);
+  h1->fr_neg_mul(r, s, kr.data());
+  h1->scalar_mul_affine(pk->delta.data(), r, rd.data());
+  h1->scalar_mul_affine(pk->delta.data(), s, sd.data());
+  h1->scalar_mul_affine(pk->delta.data(), kr.data(), krd.data());
+  h2->scalar_mul_affine(pk->delta2.data(), s, sd2.data());
+
+  CK(cudaStreamSynchronize(st));
+  if (msm_out) memcpy(msm_out, host.data(), host.size());
+  uint8_t* mA = host.data();
+  uint8_t* mB1 = host.data() + j1;
+  uint8_t* mZ = host.data() + 2 * j1;
+  uint8_t* mK = host.data() + 3 * j1;
+  uint8_t* mB2 = host.data() + 4 * j1;
+  // ar = A + alpha + r*delta (prove.go:207-214)
+  std::vector<uint8_t> ar(mA, mA + j1);
+  h1->add_mixed(ar.data(), pk->alpha.data());
+  h1->add_jac(ar.data(), rd.data());
+  // bs1 = B + beta + s*delta (prove.go:194-200)
+  std::vector<uint8_t> bs1(mB1, mB1 + j1);
+  h1->add_mixed(bs1.data(), pk->beta.data());
+  h1->add_jac(bs1.data(), sd.data());
+  // krs = K + Z.h + (-rs)*delta + s*ar + r*bs1 (prove.go:227-269)
+  std::vector<uint8_t> krs(mK, mK + j1), tmp(j1);
+  h1->add_jac(krs.data(), krd.data());
+  h1->add_jac(krs.data(), mZ);
+  h1->scalar_mul_jac(ar.data(), s, tmp.data());
+  h1->add_jac(krs.data(), tmp.data());
+  h1->scalar_mul_jac(bs1.data(), r, tmp.data());
+  h1->add_jac(krs.data(), tmp.data());
+  // bs2 = B2 + s*delta2 + beta2 (prove.go:283-292)
+  std::vector<uint8_t> bs2(mB2, mB2 + j2);
+  h2->add_jac(bs2.data(), sd2.data());
+  h2->add_mixed(bs2.data(), pk->beta2.data());
+  h1->to_affine(ar.data(), ar_out);
+  h1->to_affine(krs.data(), krs_out);
+  h2->to_affine(bs2.data(), bs_out);
+  return 0;
+  GUARD_END
+}
+
+}  // extern "C"

@@ -1,0 +1,199 @@
+// Per-curve instantiation of the kernel templates behind the type-erased tables of
+// internal.h.  Included by inst_<curve>.cu only.
+#pragma once
+#include "host_field.h"
+#include "internal.h"
+#include "msm_impl.cuh"
+#include "ntt_impl.cuh"
+
+namespace gb200 {
+
+// ---------------------------------------------------------------------------
+// MSM
+// ---------------------------------------------------------------------------
+template <class Fr, class F>
+struct MsmInst {
+  static MsmPlan plan(uint32_t n, uint32_t stride, uint32_t off, int c, int precomp, uint32_t task_len,
+                      uint32_t chunk) {
+    return msm_make_plan(n, stride, off, Fr::Params::BITS, c, precomp, task_len, chunk);
+  }
+  static cudaError_t ws_bytes(uint32_t n, uint32_t stride, int c, int precomp, uint32_t task_len, uint32_t chunk,
+                              size_t* out) {
+    MsmLayout<F> L;
+    GB_CUDA_TRY(msm_layout<F>(plan(n, stride, 0, c, precomp, task_len, chunk), L));
+    *out = L.total;
+    return cudaSuccess;
+  }
+  static cudaError_t run(cudaStream_t st, uint32_t n, uint32_t stride, uint32_t off, int c, int precomp,
+                         uint32_t task_len, uint32_t chunk, const void* d_table, const void* d_scalars,
+                         void* d_out_jac, void* ws) {
+    MsmPlan pl = plan(n, stride, off, c, precomp, task_len, chunk);
+    MsmLayout<F> L;
+    GB_CUDA_TRY(msm_layout<F>(pl, L));
+    return msm_enqueue<Fr, F>(st, pl, reinterpret_cast<const Affine<F>*>(d_table),
+                              reinterpret_cast<const Fr*>(d_scalars), reinterpret_cast<Jacobian<F>*>(d_out_jac), ws, L);
+  }
+  static cudaError_t precompute(cudaStream_t st, uint32_t n, int nwin, int c, void* d_table) {
+    if (n == 0 || nwin <= 1) return cudaSuccess;
+    k_msm_precompute<F><<<(n + 127) / 128, 128, 0, st>>>(n, nwin, c, reinterpret_cast<Affine<F>*>(d_table));
+    return cudaGetLastError();
+  }
+  static const MsmOps* ops() {
+    static const MsmOps o = {Fr::Params::BITS, sizeof(Fr), sizeof(Affine<F>), sizeof(Jacobian<F>), &ws_bytes, &run,
+                             &precompute};
+    return &o;
+  }
+};
+
+// ---------------------------------------------------------------------------
+// vector kernels
+// ---------------------------------------------------------------------------
+template <class Fr>
+__global__ void __launch_bounds__(256) k_vec_op(int op, Fr* __restrict__ out, const Fr* __restrict__ a,
+                                                const Fr* __restrict__ b, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const Fr x = a[i], y = b[i];
+  out[i] = op == 0 ? x * y : (op == 1 ? x + y : x - y);
+}
+template <class Fr>
+__global__ void __launch_bounds__(256) k_bit_reverse(Fr* __restrict__ d, uint32_t logn) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (1u << logn)) return;
+  const uint32_t j = ntt_bitrev(i, (int)logn);
+  if (j > i) { Fr t = d[i]; d[i] = d[j]; d[j] = t; }
+}
+template <class Fr>
+__global__ void __launch_bounds__(256) k_scale_powers(const Fr* __restrict__ pw, Fr s, size_t n, Fr* __restrict__ d) {
+  const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  Fr acc = s;
+  size_t e = k;
+  for (int j = 0; e; j++, e >>= 1)
+    if (e & 1) acc = acc * pw[j];
+  d[k] = d[k] * acc;
+}
+template <class Fr>
+__global__ void __launch_bounds__(256) k_gather(Fr* __restrict__ out, const Fr* __restrict__ src,
+                                                const uint32_t* __restrict__ idx, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = src[idx[i]];
+}
+
+// ---------------------------------------------------------------------------
+// NTT
+// ---------------------------------------------------------------------------
+template <class Fr>
+struct NttInst {
+  using Dom = NttDomainDev<Fr>;
+  static void* domain_new(cudaStream_t st, int logn, const void* gen, const void* coset, cudaError_t* err) {
+    Dom* d = new Dom();
+    *err = d->init(st, logn, reinterpret_cast<const Fr*>(gen), reinterpret_cast<const Fr*>(coset));
+    if (*err != cudaSuccess) { d->destroy(); delete d; return nullptr; }
+    return d;
+  }
+  static void domain_free(void* p) { Dom* d = reinterpret_cast<Dom*>(p); d->destroy(); delete d; }
+  static size_t domain_bytes(void* p) { return reinterpret_cast<Dom*>(p)->table_bytes(); }
+  static cudaError_t ntt(cudaStream_t st, void* dom, void* data, int inverse, int decimation, int on_coset) {
+    return ntt_enqueue<Fr>(st, *reinterpret_cast<Dom*>(dom), reinterpret_cast<Fr*>(data), inverse != 0, decimation,
+                           on_coset != 0);
+  }
+  static cudaError_t compute_h(cudaStream_t st, void* dom, void* a, void* b, void* c) {
+    return compute_h_enqueue<Fr>(st, *reinterpret_cast<Dom*>(dom), reinterpret_cast<Fr*>(a), reinterpret_cast<Fr*>(b),
+                                 reinterpret_cast<Fr*>(c));
+  }
+  static cudaError_t vec_op(cudaStream_t st, int op, void* out, const void* a, const void* b, size_t n) {
+    if (!n) return cudaSuccess;
+    k_vec_op<Fr><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(op, (Fr*)out, (const Fr*)a, (const Fr*)b, n);
+    return cudaGetLastError();
+  }
+  static cudaError_t bit_reverse(cudaStream_t st, void* d, uint32_t logn) {
+    k_bit_reverse<Fr><<<((1u << logn) + 255) / 256, 256, 0, st>>>((Fr*)d, logn);
+    return cudaGetLastError();
+  }
+  static cudaError_t scale_powers(cudaStream_t st, void* d, size_t n, const void* s, const void* g) {
+    if (!n) return cudaSuccess;
+    Fr pw[64];
+    Fr b = *reinterpret_cast<const Fr*>(g);
+    for (int j = 0; j < 64; j++) { pw[j] = b; b = b.sqr(); }
+    Fr* d_pw = nullptr;
+    GB_CUDA_TRY(cudaMallocAsync(&d_pw, sizeof(pw), st));
+    GB_CUDA_TRY(cudaMemcpyAsync(d_pw, pw, sizeof(pw), cudaMemcpyHostToDevice, st));
+    k_scale_powers<Fr><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_pw, *reinterpret_cast<const Fr*>(s), n, (Fr*)d);
+    GB_CUDA_TRY(cudaGetLastError());
+    GB_CUDA_TRY(cudaFreeAsync(d_pw, st));
+    return cudaStreamSynchronize(st);
+  }
+  static cudaError_t gather(cudaStream_t st, void* out, const void* src, const uint32_t* idx, size_t n) {
+    if (!n) return cudaSuccess;
+    k_gather<Fr><<<(unsigned)((n + 255) / 256), 256, 0, st>>>((Fr*)out, (const Fr*)src, idx, n);
+    return cudaGetLastError();
+  }
+  static const NttOps* ops() {
+    static const NttOps o = {sizeof(Fr), Fr::Params::TWO_ADICITY, &domain_new, &domain_free, &domain_bytes, &ntt,
+                             &compute_h, &vec_op, &bit_reverse, &scale_powers, &gather};
+    return &o;
+  }
+};
+
+// ---------------------------------------------------------------------------
+// host group arithmetic (proof assembly)
+// ---------------------------------------------------------------------------
+template <class HFr, class HF>
+struct HostGroupInst {
+  using A = Affine<HF>;
+  using J = Jacobian<HF>;
+  using X = XYZZ<HF>;
+  static X mul(const X& p, const HFr& k_mont) {
+    HFr k = k_mont.from_mont();
+    X acc = X::inf();
+    for (int i = HFr::M - 1; i >= 0; i--)
+      for (int b = 63; b >= 0; b--) {
+        acc.dbl();
+        if ((k.l[i] >> b) & 1) acc.add(p);
+      }
+    return acc;
+  }
+  static void scalar_mul_affine(const void* p, const void* k, void* out) {
+    *reinterpret_cast<J*>(out) = mul(X::from_affine(*reinterpret_cast<const A*>(p)), *reinterpret_cast<const HFr*>(k)).to_jacobian();
+  }
+  static void scalar_mul_jac(const void* p, const void* k, void* out) {
+    *reinterpret_cast<J*>(out) = mul(X::from_jacobian(*reinterpret_cast<const J*>(p)), *reinterpret_cast<const HFr*>(k)).to_jacobian();
+  }
+  static void add_jac(void* acc, const void* q) {
+    X a = X::from_jacobian(*reinterpret_cast<J*>(acc));
+    a.add(X::from_jacobian(*reinterpret_cast<const J*>(q)));
+    *reinterpret_cast<J*>(acc) = a.to_jacobian();
+  }
+  static void add_mixed(void* acc, const void* q) {
+    X a = X::from_jacobian(*reinterpret_cast<J*>(acc));
+    a.add_mixed(*reinterpret_cast<const A*>(q));
+    *reinterpret_cast<J*>(acc) = a.to_jacobian();
+  }
+  static void to_affine(const void* p, void* out) {
+    *reinterpret_cast<A*>(out) = X::from_jacobian(*reinterpret_cast<const J*>(p)).to_affine();
+  }
+  static void fr_neg_mul(const void* a, const void* b, void* out) {
+    *reinterpret_cast<HFr*>(out) = ((*reinterpret_cast<const HFr*>(a)) * (*reinterpret_cast<const HFr*>(b))).neg();
+  }
+  static const HostGroupOps* ops() {
+    static const HostGroupOps o = {sizeof(A), sizeof(J), sizeof(HFr), &scalar_mul_affine, &scalar_mul_jac, &add_jac,
+                                   &add_mixed, &to_affine, &fr_neg_mul};
+    return &o;
+  }
+};
+
+#define GB200_REGISTER_CURVE(ID, FR, FP, G2F, HFR, HFP, HG2F)                      \
+  namespace {                                                                       \
+  struct Registrar_##ID {                                                           \
+    Registrar_##ID() {                                                              \
+      register_msm_ops(ID, 1, MsmInst<FR, FP>::ops());                              \
+      register_msm_ops(ID, 2, MsmInst<FR, G2F>::ops());                             \
+      register_ntt_ops(ID, NttInst<FR>::ops());                                     \
+      register_host_group_ops(ID, 1, HostGroupInst<HFR, HFP>::ops());               \
+      register_host_group_ops(ID, 2, HostGroupInst<HFR, HG2F>::ops());              \
+    }                                                                               \
+  } registrar_##ID;                                                                 \
+  }
+
+}  // namespace gb200

@@ -1,0 +1,66 @@
+// Type-erased per-(curve, group) operation tables.  Each inst_<curve>.cu translation
+// unit instantiates the templates for its field types and registers the function
+// pointers here; capi.cu / groth16_host.cu dispatch through them.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstddef>
+#include <cstdint>
+
+namespace gb200 {
+
+struct MsmOps {
+  int scalar_bits;      // Fr bit length
+  size_t fr_bytes;      // sizeof(fr.Element)
+  size_t affine_bytes;  // sizeof(G?Affine)
+  size_t jac_bytes;     // sizeof(G?Jac)
+  // workspace bytes for an MSM of n scalars with the given parameters
+  cudaError_t (*ws_bytes)(uint32_t n, uint32_t stride, int c, int precomp, uint32_t task_len, uint32_t chunk,
+                          size_t* out);
+  // enqueue a full MSM (all pointers on device)
+  cudaError_t (*run)(cudaStream_t st, uint32_t n, uint32_t stride, uint32_t off, int c, int precomp,
+                     uint32_t task_len, uint32_t chunk, const void* d_table, const void* d_scalars, void* d_out_jac,
+                     void* ws);
+  // fill slabs 1..nwin-1 of a [nwin][n] table whose slab 0 holds the bases
+  cudaError_t (*precompute)(cudaStream_t st, uint32_t n, int nwin, int c, void* d_table);
+};
+
+struct NttOps {
+  size_t fr_bytes;
+  int two_adicity;
+  void* (*domain_new)(cudaStream_t st, int logn, const void* gen_mont, const void* coset_mont, cudaError_t* err);
+  void (*domain_free)(void* dom);
+  size_t (*domain_bytes)(void* dom);
+  cudaError_t (*ntt)(cudaStream_t st, void* dom, void* d_data, int inverse, int decimation, int on_coset);
+  cudaError_t (*compute_h)(cudaStream_t st, void* dom, void* d_a, void* d_b, void* d_c);
+  cudaError_t (*vec_op)(cudaStream_t st, int op, void* d_out, const void* d_a, const void* d_b, size_t n);
+  cudaError_t (*bit_reverse)(cudaStream_t st, void* d_data, uint32_t logn);
+  cudaError_t (*scale_powers)(cudaStream_t st, void* d_data, size_t n, const void* s_mont, const void* g_mont);
+  // out[j] = src[idx[j]] (wire filtering, backend/groth16/bn254/prove.go:147-168)
+  cudaError_t (*gather)(cudaStream_t st, void* d_out, const void* d_src, const uint32_t* d_idx, size_t n);
+};
+
+// Host-side group arithmetic for proof assembly (backend/groth16/bn254/prove.go:
+// 185,199-200,212-214,241-269,287-292): a handful of scalar multiplications and
+// additions that the reference also keeps on the CPU (in Go).
+struct HostGroupOps {
+  size_t affine_bytes, jac_bytes, fr_bytes;
+  // out_jac = k * p_affine   (k: fr.Element Montgomery)
+  void (*scalar_mul_affine)(const void* p_affine, const void* k_mont, void* out_jac);
+  void (*scalar_mul_jac)(const void* p_jac, const void* k_mont, void* out_jac);
+  void (*add_jac)(void* acc_jac, const void* q_jac);            // acc += q
+  void (*add_mixed)(void* acc_jac, const void* q_affine);       // acc += q
+  void (*to_affine)(const void* p_jac, void* out_affine);
+  // fr helpers: out = -(a*b)
+  void (*fr_neg_mul)(const void* a_mont, const void* b_mont, void* out_mont);
+};
+
+const MsmOps* get_msm_ops(int curve, int group);
+const NttOps* get_ntt_ops(int curve);
+const HostGroupOps* get_host_group_ops(int curve, int group);
+
+// registration (called from static initialisers in inst_*.cu)
+void register_msm_ops(int curve, int group, const MsmOps* ops);
+void register_ntt_ops(int curve, const NttOps* ops);
+void register_host_group_ops(int curve, int group, const HostGroupOps* ops);
+
+}  // namespace gb200

@@ -1,0 +1,252 @@
+// sm_100a kernels + stream-ordered host driver for the bucket MSM (see msm.cuh for
+// the algorithm and the reference call sites it replaces).
+#pragma once
+#include <cub/cub.cuh>
+#include <cuda_runtime.h>
+
+#include "msm.cuh"
+
+namespace gb200 {
+
+#define GB_CUDA_TRY(x)                                   \
+  do {                                                   \
+    cudaError_t e_ = (x);                                \
+    if (e_ != cudaSuccess) return e_;                    \
+  } while (0)
+
+// ---------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------
+template <class Fr>
+__global__ void __launch_bounds__(256) k_msm_decompose(MsmPlan pl, const Fr* __restrict__ scalars,
+                                                       uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < pl.n) msm_decompose_one<Fr>(pl, i, scalars, keys, vals);
+}
+
+// off[b] = first sorted position with key >= b, for b in [0, nb]
+static __global__ void k_msm_bucket_offsets(const uint32_t* __restrict__ skeys, uint32_t m, uint32_t nb,
+                                     uint32_t* __restrict__ off) {
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b > nb) return;
+  uint32_t lo = 0, hi = m;
+  while (lo < hi) {
+    const uint32_t mid = lo + ((hi - lo) >> 1);
+    if (__ldg(skeys + mid) < b) lo = mid + 1; else hi = mid;
+  }
+  off[b] = lo;
+}
+
+static __global__ void k_msm_task_counts(const uint32_t* __restrict__ off, uint32_t nb, uint32_t task_len,
+                                  uint32_t* __restrict__ ntasks) {
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b > nb) return;
+  ntasks[b] = b == nb ? 0u : (off[b + 1] - off[b] + task_len - 1) / task_len;
+}
+
+// one thread per task: partial[t] = sum of <= task_len consecutive entries of one bucket
+template <class F>
+__global__ void __launch_bounds__(128) k_msm_accumulate(MsmPlan pl, const Affine<F>* __restrict__ table,
+                                                        const uint32_t* __restrict__ svals,
+                                                        const uint32_t* __restrict__ off,
+                                                        const uint32_t* __restrict__ task_off,
+                                                        XYZZ<F>* __restrict__ partial) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t nb = pl.total_buckets;
+  if (t >= __ldg(task_off + nb)) return;
+  // bucket of task t: largest b with task_off[b] <= t
+  uint32_t lo = 0, hi = nb;
+  while (lo < hi) {
+    const uint32_t mid = lo + ((hi - lo + 1) >> 1);
+    if (__ldg(task_off + mid) <= t) lo = mid; else hi = mid - 1;
+  }
+  const uint32_t b = lo;
+  const uint32_t j = t - __ldg(task_off + b);
+  const uint32_t begin = __ldg(off + b) + j * pl.task_len;
+  uint32_t end = begin + pl.task_len;
+  const uint32_t bend = __ldg(off + b + 1);
+  if (end > bend) end = bend;
+  partial[t] = msm_accumulate_range<F>(table, svals, begin, end);
+}
+
+// one thread per bucket: sum of its task partials
+template <class F>
+__global__ void __launch_bounds__(128) k_msm_combine(MsmPlan pl, const uint32_t* __restrict__ task_off,
+                                                     const XYZZ<F>* __restrict__ partial,
+                                                     XYZZ<F>* __restrict__ buckets) {
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= pl.total_buckets) return;
+  const uint32_t t0 = task_off[b], t1 = task_off[b + 1];
+  XYZZ<F> acc = XYZZ<F>::inf();
+  if (t0 < t1) acc = partial[t0];
+  for (uint32_t t = t0 + 1; t < t1; t++) acc.add(partial[t]);
+  buckets[b] = acc;
+}
+
+// one thread per (set, chunk): weighted running sum of `chunk` buckets
+template <class F>
+__global__ void __launch_bounds__(128) k_msm_reduce_chunks(MsmPlan pl, uint32_t chunks_per_set,
+                                                           const XYZZ<F>* __restrict__ buckets,
+                                                           XYZZ<F>* __restrict__ chunk_sums) {
+  const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= chunks_per_set * (uint32_t)pl.nsets) return;
+  const uint32_t s = g / chunks_per_set, t = g % chunks_per_set;
+  const uint32_t lo = t * pl.chunk;
+  uint32_t hi = lo + pl.chunk;
+  if (hi > pl.set_size) hi = pl.set_size;
+  chunk_sums[g] = msm_reduce_chunk<F>(buckets + (size_t)s * pl.set_size, lo, hi);
+}
+
+// one block per set: tree sum of that set's chunk sums (dynamic shared memory)
+template <class F>
+__global__ void k_msm_set_sum(uint32_t chunks_per_set, const XYZZ<F>* __restrict__ chunk_sums,
+                              XYZZ<F>* __restrict__ set_sums) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  XYZZ<F>* sm = reinterpret_cast<XYZZ<F>*>(smem_raw);
+  const uint32_t s = blockIdx.x;
+  const XYZZ<F>* src = chunk_sums + (size_t)s * chunks_per_set;
+  XYZZ<F> acc = XYZZ<F>::inf();
+  for (uint32_t k = threadIdx.x; k < chunks_per_set; k += blockDim.x) acc.add(src[k]);
+  sm[threadIdx.x] = acc;
+  __syncthreads();
+  for (uint32_t w = blockDim.x >> 1; w > 0; w >>= 1) {
+    if (threadIdx.x < w) {
+      XYZZ<F> a = sm[threadIdx.x];
+      a.add(sm[threadIdx.x + w]);
+      sm[threadIdx.x] = a;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) set_sums[s] = sm[0];
+}
+
+// Horner over sets, result in gnark Jacobian layout
+template <class F>
+__global__ void k_msm_finish(int nsets, int c, const XYZZ<F>* __restrict__ set_sums, Jacobian<F>* __restrict__ out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    XYZZ<F> r = nsets > 0 ? msm_horner<F>(set_sums, nsets, c) : XYZZ<F>::inf();
+    *out = r.to_jacobian();
+  }
+}
+
+// table precompute: slab w holds 2^(c*w) * P_i   (built once per table upload)
+template <class F>
+__global__ void __launch_bounds__(128) k_msm_precompute(uint32_t n, int nwin, int c, Affine<F>* __restrict__ table) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  XYZZ<F> q = XYZZ<F>::from_affine(table[i]);
+  for (int w = 1; w < nwin; w++) {
+    for (int k = 0; k < c; k++) q.dbl();
+    table[(size_t)w * n + i] = q.to_affine();
+  }
+}
+
+// ---------------------------------------------------------------------------
+// workspace + driver
+// ---------------------------------------------------------------------------
+struct MsmWorkspace {
+  void* base = nullptr;
+  size_t bytes = 0;
+};
+
+template <class F>
+struct MsmLayout {
+  size_t m;            // entries
+  size_t max_tasks;
+  uint32_t chunks_per_set;
+  size_t cub_bytes;
+  // offsets into the workspace
+  size_t o_keys0, o_keys1, o_vals0, o_vals1, o_off, o_ntasks, o_task_off, o_partial, o_buckets, o_chunks, o_sets, o_cub,
+      total;
+};
+
+inline size_t gb_align(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+template <class F>
+cudaError_t msm_layout(const MsmPlan& pl, MsmLayout<F>& L) {
+  L.m = (size_t)pl.n * pl.nwin;
+  L.max_tasks = L.m / pl.task_len + pl.total_buckets + 1;
+  L.chunks_per_set = (pl.set_size + pl.chunk - 1) / pl.chunk;
+  size_t sort_bytes = 0, scan_bytes = 0;
+  int end_bit = 1;
+  while ((1ull << end_bit) <= pl.total_buckets) end_bit++;
+  GB_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr,
+                                              (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)L.m, 0, end_bit));
+  GB_CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr,
+                                            (int)pl.total_buckets + 1));
+  L.cub_bytes = sort_bytes > scan_bytes ? sort_bytes : scan_bytes;
+  size_t o = 0;
+  L.o_keys0 = o; o += gb_align(L.m * 4);
+  L.o_keys1 = o; o += gb_align(L.m * 4);
+  L.o_vals0 = o; o += gb_align(L.m * 4);
+  L.o_vals1 = o; o += gb_align(L.m * 4);
+  L.o_off = o; o += gb_align(((size_t)pl.total_buckets + 2) * 4);
+  L.o_ntasks = o; o += gb_align(((size_t)pl.total_buckets + 2) * 4);
+  L.o_task_off = o; o += gb_align(((size_t)pl.total_buckets + 2) * 4);
+  L.o_partial = o; o += gb_align(L.max_tasks * sizeof(XYZZ<F>));
+  L.o_buckets = o; o += gb_align((size_t)pl.total_buckets * sizeof(XYZZ<F>));
+  L.o_chunks = o; o += gb_align((size_t)L.chunks_per_set * pl.nsets * sizeof(XYZZ<F>));
+  L.o_sets = o; o += gb_align((size_t)pl.nsets * sizeof(XYZZ<F>));
+  L.o_cub = o; o += gb_align(L.cub_bytes);
+  L.total = o;
+  return cudaSuccess;
+}
+
+// largest power-of-two block that fits `budget` bytes of XYZZ<F> in shared memory
+template <class F>
+inline int msm_set_sum_threads(size_t budget = 160 * 1024) {
+  int t = 1024;
+  while ((size_t)t * sizeof(XYZZ<F>) > budget) t >>= 1;
+  return t;
+}
+
+// Enqueue a full MSM on `stream`.  d_scalars: n Fr elements (Montgomery) on device.
+// d_out: one Jacobian<F> on device.  ws must hold msm_layout().total bytes.
+template <class Fr, class F>
+cudaError_t msm_enqueue(cudaStream_t stream, const MsmPlan& pl, const Affine<F>* d_table, const Fr* d_scalars,
+                        Jacobian<F>* d_out, void* ws, const MsmLayout<F>& L) {
+  unsigned char* w = reinterpret_cast<unsigned char*>(ws);
+  uint32_t* keys0 = (uint32_t*)(w + L.o_keys0);
+  uint32_t* keys1 = (uint32_t*)(w + L.o_keys1);
+  uint32_t* vals0 = (uint32_t*)(w + L.o_vals0);
+  uint32_t* vals1 = (uint32_t*)(w + L.o_vals1);
+  uint32_t* off = (uint32_t*)(w + L.o_off);
+  uint32_t* ntasks = (uint32_t*)(w + L.o_ntasks);
+  uint32_t* task_off = (uint32_t*)(w + L.o_task_off);
+  XYZZ<F>* partial = (XYZZ<F>*)(w + L.o_partial);
+  XYZZ<F>* buckets = (XYZZ<F>*)(w + L.o_buckets);
+  XYZZ<F>* chunks = (XYZZ<F>*)(w + L.o_chunks);
+  XYZZ<F>* sets = (XYZZ<F>*)(w + L.o_sets);
+  void* cub_tmp = w + L.o_cub;
+  size_t cub_bytes = L.cub_bytes;
+  const uint32_t nb = pl.total_buckets;
+
+  if (pl.n == 0) {
+    // empty sum = infinity
+    k_msm_finish<F><<<1, 1, 0, stream>>>(0, pl.c, sets, d_out);  // nsets=0 handled below
+    return cudaGetLastError();
+  }
+  k_msm_decompose<Fr><<<(pl.n + 255) / 256, 256, 0, stream>>>(pl, d_scalars, keys0, vals0);
+  int end_bit = 1;
+  while ((1ull << end_bit) <= nb) end_bit++;
+  GB_CUDA_TRY(cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, keys0, keys1, vals0, vals1, (int)L.m, 0, end_bit,
+                                              stream));
+  k_msm_bucket_offsets<<<(nb + 1 + 255) / 256, 256, 0, stream>>>(keys1, (uint32_t)L.m, nb, off);
+  k_msm_task_counts<<<(nb + 1 + 255) / 256, 256, 0, stream>>>(off, nb, pl.task_len, ntasks);
+  cub_bytes = L.cub_bytes;
+  GB_CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, ntasks, task_off, (int)nb + 1, stream));
+  k_msm_accumulate<F><<<(unsigned)((L.max_tasks + 127) / 128), 128, 0, stream>>>(pl, d_table, vals1, off, task_off,
+                                                                                 partial);
+  k_msm_combine<F><<<(nb + 127) / 128, 128, 0, stream>>>(pl, task_off, partial, buckets);
+  const uint32_t nchunks = L.chunks_per_set * (uint32_t)pl.nsets;
+  k_msm_reduce_chunks<F><<<(nchunks + 127) / 128, 128, 0, stream>>>(pl, L.chunks_per_set, buckets, chunks);
+  int st = msm_set_sum_threads<F>();
+  while (st > 32 && (uint32_t)st > L.chunks_per_set) st >>= 1;
+  const size_t smem = (size_t)st * sizeof(XYZZ<F>);
+  GB_CUDA_TRY(cudaFuncSetAttribute(k_msm_set_sum<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_msm_set_sum<F><<<pl.nsets, st, smem, stream>>>(L.chunks_per_set, chunks, sets);
+  k_msm_finish<F><<<1, 1, 0, stream>>>(pl.nsets, pl.c, sets, d_out);
+  return cudaGetLastError();
+}
+
+}  // namespace gb200

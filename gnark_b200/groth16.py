@@ -1,0 +1,227 @@
+"""Host-side mirror of the reference's accelerated Groth16 package
+(backend/accelerated/icicle/groth16/groth16_icicle.go:79-194 and
+backend/accelerated/icicle/opts.go:10-124): same function set and option names,
+on top of libgnark_b200.so.  Python stands in for the Go shim of INTEGRATION.md
+because this image has no Go toolchain; the arithmetic all happens in the C ABI.
+
+    pk = NewProvingKey(ecc_id); pk.load(...)           # or ProvingKey.from_arrays
+    proof = Prove(r1cs, pk, full_witness, WithDeviceID(0), WithPinToGPU(True))
+
+Out of scope here, as in the reference's accelerated package: the R1CS solver
+(`r1cs.Solve`, constraint/bn254/solver.go) - any object with a
+``Solve(witness) -> R1CSSolution`` method plugs in - Setup / Verify (CPU, pairing).
+"""
+
+import ctypes
+import secrets
+from dataclasses import dataclass, field
+from typing import Callable, List, Optional
+
+import numpy as np
+
+from . import lib as _lib
+
+# ecc.ID values used across the ABI
+BN254, BLS12_381, BLS12_377, BW6_761 = _lib.BN254, _lib.BLS12_381, _lib.BLS12_377, _lib.BW6_761
+
+_FR_MODULUS = {
+    BN254: 0x30644e72e131a029b85045b68181585d2833e84879b9709143e1f593f0000001,
+    BLS12_381: 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001,
+    BLS12_377: 0x12ab655e9a2ca55660b44d1e5c37b00159aa76fed00000010a11800000000001,
+    BW6_761: 0x1ae3a4617c510eac63b05c06ca1493b1a22d9f300f5138f1ef3622fba094800170b5d44300000008508c00000000001,
+}
+
+
+# ---- options (backend/accelerated/icicle/opts.go) -----------------------------------
+@dataclass
+class Config:
+    DeviceID: int = 0
+    PinToGPU: bool = True        # tables are always device resident here; kept for API parity
+    Precompute: bool = True      # build the per-window table slabs (B200_TABLE_PRECOMP)
+    ProverOpts: list = field(default_factory=list)
+    Randomness: Optional[Callable[[int], int]] = None   # test hook: r,s injection
+
+
+Option = Callable[[Config], None]
+
+
+def NewConfig(*opts: Option) -> Config:
+    cfg = Config()
+    for o in opts:
+        if o is not None:
+            o(cfg)
+    return cfg
+
+
+def WithDeviceID(dev: int) -> Option:
+    def f(c: Config):
+        if dev < 0:
+            raise ValueError(f"invalid device id {dev}")
+        c.DeviceID = dev
+    return f
+
+
+def WithPinToGPU(pin: bool) -> Option:
+    def f(c: Config):
+        c.PinToGPU = pin
+    return f
+
+
+def WithPrecompute(on: bool) -> Option:
+    def f(c: Config):
+        c.Precompute = on
+    return f
+
+
+def WithProverOptions(*opts) -> Option:
+    def f(c: Config):
+        if not opts:
+            raise ValueError("no prover options provided")
+        c.ProverOpts = list(opts)
+    return f
+
+
+def WithRandomness(fn: Callable[[int], int]) -> Option:
+    """Deterministic r, s for parity tests (the reference samples crypto/rand, prove.go:170-182)."""
+    def f(c: Config):
+        c.Randomness = fn
+    return f
+
+
+# ---- data carried across the boundary ------------------------------------------------
+@dataclass
+class R1CSSolution:
+    """constraint/bn254/system.go:162-165: fr.Vectors in gnark memory layout (uint64, Montgomery)."""
+    W: np.ndarray
+    A: np.ndarray
+    B: np.ndarray
+    C: np.ndarray
+
+
+@dataclass
+class Proof:
+    """backend/groth16/bn254/prove.go:38-43: Ar, Krs in G1, Bs in G2 (affine, gnark layout)."""
+    Ar: np.ndarray
+    Bs: np.ndarray
+    Krs: np.ndarray
+    msm: Optional[np.ndarray] = None   # the five raw MSM results (A, B1, Z, K | B2), for parity tests
+
+
+class ProvingKey:
+    """Accelerated proving key: the native key's fields (backend/groth16/bn254/setup.go:25-48)
+    plus the device handle, as backend/accelerated/icicle/groth16/bn254/provingkey.go:37-42."""
+
+    def __init__(self, curve: int):
+        self.curve = curve
+        self.domain_size = 0
+        self.domain_gen = None       # fr.Element or None (defaults as fft.NewDomain)
+        self.coset_gen = None
+        self.G1_Alpha = self.G1_Beta = self.G1_Delta = None
+        self.G1_A = self.G1_B = self.G1_Z = self.G1_K = None
+        self.G2_Beta = self.G2_Delta = self.G2_B = None
+        self.InfinityA = self.InfinityB = None
+        self.nb_wires = 0
+        self.nb_public = 0
+        self._handle = None
+        self._dev = None
+
+    @classmethod
+    def from_arrays(cls, curve, domain_size, alpha, beta, delta, A, B, Z, K, beta2, delta2, B2, inf_a, inf_b,
+                    nb_public, domain_gen=None, coset_gen=None):
+        pk = cls(curve)
+        pk.domain_size = int(domain_size)
+        pk.domain_gen, pk.coset_gen = domain_gen, coset_gen
+        c = np.ascontiguousarray
+        pk.G1_Alpha, pk.G1_Beta, pk.G1_Delta = c(alpha), c(beta), c(delta)
+        pk.G1_A, pk.G1_B, pk.G1_Z, pk.G1_K = c(A), c(B), c(Z), c(K)
+        pk.G2_Beta, pk.G2_Delta, pk.G2_B = c(beta2), c(delta2), c(B2)
+        pk.InfinityA = np.ascontiguousarray(inf_a, dtype=np.uint8)
+        pk.InfinityB = np.ascontiguousarray(inf_b, dtype=np.uint8)
+        pk.nb_wires = len(pk.InfinityA)
+        pk.nb_public = int(nb_public)
+        return pk
+
+    def _count(self, arr, group):
+        frl, fpl, deg = _lib.CURVE_SHAPES[self.curve]
+        per = 2 * fpl * (deg if group == 2 else 1)
+        return arr.size // per
+
+    def setup_device_pointers(self, cfg: Config):
+        """icicle.go:88-264 setupDevicePointers: once per key and device."""
+        if self._handle is not None and self._dev == cfg.DeviceID:
+            return
+        self.free_gpu_resources()
+        d = _lib.Groth16PkDesc()
+        d.curve = self.curve
+        d.domain_size = self.domain_size
+        p = _lib.ptr
+        d.domain_gen, d.coset_gen = p(self.domain_gen), p(self.coset_gen)
+        d.g1_alpha, d.g1_beta, d.g1_delta = p(self.G1_Alpha), p(self.G1_Beta), p(self.G1_Delta)
+        d.g2_beta, d.g2_delta = p(self.G2_Beta), p(self.G2_Delta)
+        d.g1_a, d.n_a = p(self.G1_A), self._count(self.G1_A, 1)
+        d.g1_b, d.n_b = p(self.G1_B), self._count(self.G1_B, 1)
+        d.g1_z, d.n_z = p(self.G1_Z), self._count(self.G1_Z, 1)
+        d.g1_k, d.n_k = p(self.G1_K), self._count(self.G1_K, 1)
+        d.g2_b, d.n_b2 = p(self.G2_B), self._count(self.G2_B, 2)
+        d.infinity_a, d.infinity_b = p(self.InfinityA), p(self.InfinityB)
+        d.nb_wires, d.nb_public = self.nb_wires, self.nb_public
+        d.flags = _lib.TABLE_PRECOMP if cfg.Precompute else 0
+        h = ctypes.c_void_p(0)
+        _lib.check(_lib.load().b200_groth16_pk_load(cfg.DeviceID, ctypes.byref(d), ctypes.byref(h)))
+        self._handle, self._dev = h, cfg.DeviceID
+
+    def free_gpu_resources(self):
+        """icicle.go:1493-1549 FreeGPUResources; safe to call repeatedly."""
+        if self._handle is not None:
+            _lib.check(_lib.load().b200_groth16_pk_free(self._handle))
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.free_gpu_resources()
+        except Exception:
+            pass
+
+
+def NewProvingKey(curve_id: int) -> ProvingKey:
+    """groth16_icicle.go:179-194."""
+    if curve_id not in _lib.CURVE_SHAPES:
+        raise ValueError("b200 backend requested but curve is not supported")
+    return ProvingKey(curve_id)
+
+
+def _fr_to_mont_limbs(x: int, curve: int) -> np.ndarray:
+    frl = _lib.CURVE_SHAPES[curve][0]
+    q = _FR_MODULUS[curve]
+    v = (x % q) * (1 << (64 * frl)) % q
+    return np.frombuffer(v.to_bytes(8 * frl, "little"), dtype=np.uint64).copy()
+
+
+def ProveSolution(pk: ProvingKey, sol: R1CSSolution, *opts: Option, keep_msm: bool = False) -> Proof:
+    """The hot path proper: from the solver's output to the three proof points
+    (backend/groth16/bn254/prove.go:131-315; icicle.go:981-1360)."""
+    cfg = NewConfig(*opts)
+    pk.setup_device_pointers(cfg)
+    frl, fpl, deg = _lib.CURVE_SHAPES[pk.curve]
+    q = _FR_MODULUS[pk.curve]
+    rnd = cfg.Randomness or (lambda modulus: secrets.randbelow(modulus))
+    r = _fr_to_mont_limbs(rnd(q), pk.curve)
+    s = _fr_to_mont_limbs(rnd(q), pk.curve)
+    n_constraints = sol.A.size // frl
+    if sol.W.size // frl != pk.nb_wires:
+        raise ValueError("witness size does not match the proving key")
+    ar = np.zeros(2 * fpl, dtype=np.uint64)
+    krs = np.zeros(2 * fpl, dtype=np.uint64)
+    bs = np.zeros(2 * fpl * deg, dtype=np.uint64)
+    msm = np.zeros(4 * 3 * fpl + 3 * fpl * deg, dtype=np.uint64) if keep_msm else None
+    p = _lib.ptr
+    _lib.check(_lib.load().b200_groth16_prove(pk._handle, p(sol.W), p(sol.A), p(sol.B), p(sol.C), n_constraints,
+                                              p(r), p(s), p(ar), p(bs), p(krs), p(msm)))
+    return Proof(Ar=ar, Bs=bs, Krs=krs, msm=msm)
+
+
+def Prove(r1cs, pk: ProvingKey, full_witness, *opts: Option) -> Proof:
+    """groth16_icicle.go:79-98.  `r1cs.Solve(full_witness)` must return an R1CSSolution
+    (the solver itself is CPU code outside this backend, as in the reference)."""
+    sol = r1cs.Solve(full_witness)
+    return ProveSolution(pk, sol, *opts)

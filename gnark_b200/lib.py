@@ -1,0 +1,258 @@
+"""ctypes binding of libgnark_b200.so (include/gnark_b200.h).
+
+This is the Python twin of the cgo shim shown in INTEGRATION.md.  It loads the
+in-tree CUDA library ONLY: there is no CPU fallback, and nothing here imports
+``oracle/``.  A missing library or a missing CUDA device raises.
+"""
+
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libgnark_b200.so")
+
+BN254, BLS12_381, BLS12_377, BW6_761 = 0, 1, 2, 3
+DIF, DIT = 0, 1
+TABLE_PRECOMP = 1
+TABLE_SRC_ON_DEVICE = 2
+VEC_MUL, VEC_ADD, VEC_SUB = 0, 1, 2
+
+CURVE_IDS = {"bn254": BN254, "bls12-381": BLS12_381, "bls12-377": BLS12_377, "bw6-761": BW6_761}
+# (fr limbs64, fp limbs64, g2 extension degree)
+CURVE_SHAPES = {BN254: (4, 4, 2), BLS12_381: (4, 6, 2), BLS12_377: (4, 6, 2), BW6_761: (6, 12, 1)}
+
+EXPORTS = [
+    "b200_version", "b200_last_error", "b200_device_count", "b200_init", "b200_shutdown", "b200_set_stream",
+    "b200_sync", "b200_alloc", "b200_free", "b200_h2d", "b200_d2h", "b200_host_alloc", "b200_host_free",
+    "b200_table_upload", "b200_table_free", "b200_table_info", "b200_msm", "b200_msm_g1", "b200_msm_g2",
+    "b200_msm_async", "b200_ntt_domain_new", "b200_ntt_domain_free", "b200_ntt", "b200_ntt_async",
+    "b200_groth16_compute_h", "b200_vec_op", "b200_vec_bit_reverse", "b200_vec_scale_powers",
+    "b200_point_add_jac", "b200_point_to_affine", "b200_groth16_pk_load", "b200_groth16_pk_free", "b200_groth16_prove",
+]
+
+
+class B200Error(RuntimeError):
+    pass
+
+
+class Groth16PkDesc(ctypes.Structure):
+    _fields_ = [
+        ("curve", ctypes.c_int32),
+        ("domain_size", ctypes.c_uint64),
+        ("domain_gen", ctypes.c_void_p),
+        ("coset_gen", ctypes.c_void_p),
+        ("g1_alpha", ctypes.c_void_p),
+        ("g1_beta", ctypes.c_void_p),
+        ("g1_delta", ctypes.c_void_p),
+        ("g2_beta", ctypes.c_void_p),
+        ("g2_delta", ctypes.c_void_p),
+        ("g1_a", ctypes.c_void_p), ("n_a", ctypes.c_size_t),
+        ("g1_b", ctypes.c_void_p), ("n_b", ctypes.c_size_t),
+        ("g1_z", ctypes.c_void_p), ("n_z", ctypes.c_size_t),
+        ("g1_k", ctypes.c_void_p), ("n_k", ctypes.c_size_t),
+        ("g2_b", ctypes.c_void_p), ("n_b2", ctypes.c_size_t),
+        ("infinity_a", ctypes.c_void_p),
+        ("infinity_b", ctypes.c_void_p),
+        ("nb_wires", ctypes.c_size_t),
+        ("nb_public", ctypes.c_size_t),
+        ("flags", ctypes.c_int32),
+    ]
+
+
+_lib = None
+
+
+def load(path: str = None):
+    """Load the shared library (no CUDA call is made here)."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise B200Error(
+            f"{p} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is no CPU fallback)")
+    lib = ctypes.CDLL(p)
+    lib.b200_version.restype = ctypes.c_char_p
+    lib.b200_last_error.restype = ctypes.c_char_p
+    for name in EXPORTS:
+        fn = getattr(lib, name)
+        if name not in ("b200_version", "b200_last_error"):
+            fn.restype = ctypes.c_int32
+    vp, sz, i32, u32 = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int32, ctypes.c_uint32
+    lib.b200_device_count.argtypes = [ctypes.POINTER(i32)]
+    lib.b200_init.argtypes = [i32, ctypes.POINTER(i32)]
+    lib.b200_set_stream.argtypes = [i32, vp]
+    lib.b200_sync.argtypes = [i32]
+    lib.b200_alloc.argtypes = [i32, sz, ctypes.POINTER(vp)]
+    lib.b200_free.argtypes = [i32, vp]
+    lib.b200_h2d.argtypes = [i32, vp, vp, sz]
+    lib.b200_d2h.argtypes = [i32, vp, vp, sz]
+    lib.b200_host_alloc.argtypes = [sz, ctypes.POINTER(vp)]
+    lib.b200_host_free.argtypes = [vp]
+    lib.b200_table_upload.argtypes = [i32, i32, i32, vp, sz, i32, ctypes.POINTER(vp)]
+    lib.b200_table_free.argtypes = [vp]
+    lib.b200_table_info.argtypes = [vp, ctypes.POINTER(sz), ctypes.POINTER(i32), ctypes.POINTER(i32),
+                                    ctypes.POINTER(i32), ctypes.POINTER(sz)]
+    for n in ("b200_msm", "b200_msm_g1", "b200_msm_g2"):
+        getattr(lib, n).argtypes = [vp, sz, sz, vp, i32, vp]
+    lib.b200_msm_async.argtypes = [vp, sz, sz, vp, vp]
+    lib.b200_ntt_domain_new.argtypes = [i32, i32, u32, vp, vp, ctypes.POINTER(vp)]
+    lib.b200_ntt_domain_free.argtypes = [vp]
+    lib.b200_ntt.argtypes = [vp, vp, i32, i32, i32, i32]
+    lib.b200_ntt_async.argtypes = [vp, vp, i32, i32, i32]
+    lib.b200_groth16_compute_h.argtypes = [vp, vp, vp, vp, sz, i32, vp, i32]
+    lib.b200_vec_op.argtypes = [i32, i32, i32, vp, vp, vp, sz]
+    lib.b200_vec_bit_reverse.argtypes = [i32, i32, vp, u32]
+    lib.b200_vec_scale_powers.argtypes = [i32, i32, vp, sz, vp, vp]
+    lib.b200_point_add_jac.argtypes = [i32, i32, vp, vp]
+    lib.b200_point_to_affine.argtypes = [i32, i32, vp, vp]
+    lib.b200_groth16_pk_load.argtypes = [i32, ctypes.POINTER(Groth16PkDesc), ctypes.POINTER(vp)]
+    lib.b200_groth16_pk_free.argtypes = [vp]
+    lib.b200_groth16_prove.argtypes = [vp, vp, vp, vp, vp, sz, vp, vp, vp, vp, vp, vp]
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def check(rc: int):
+    if rc != 0:
+        raise B200Error(load().b200_last_error().decode())
+
+
+def ptr(a) -> ctypes.c_void_p:
+    """Host pointer of a numpy array / device pointer of a torch CUDA tensor / raw int."""
+    if a is None:
+        return ctypes.c_void_p(0)
+    if isinstance(a, np.ndarray):
+        assert a.flags["C_CONTIGUOUS"]
+        return ctypes.c_void_p(a.ctypes.data)
+    if hasattr(a, "data_ptr"):
+        return ctypes.c_void_p(a.data_ptr())
+    return ctypes.c_void_p(int(a))
+
+
+def device_count() -> int:
+    n = ctypes.c_int32(0)
+    check(load().b200_device_count(ctypes.byref(n)))
+    return n.value
+
+
+def init(dev_ids=None):
+    lib = load()
+    if not dev_ids:
+        check(lib.b200_init(0, None))
+    else:
+        arr = (ctypes.c_int32 * len(dev_ids))(*dev_ids)
+        check(lib.b200_init(len(dev_ids), arr))
+
+
+def set_stream(dev: int, cuda_stream: int):
+    check(load().b200_set_stream(dev, ctypes.c_void_p(cuda_stream)))
+
+
+def sync(dev: int = 0):
+    check(load().b200_sync(dev))
+
+
+class Table:
+    """Device-resident MSM base table (the reference's pinned G1Device / G2Device slices,
+    backend/accelerated/icicle/groth16/bn254/provingkey.go)."""
+
+    def __init__(self, curve: int, group: int, points, dev: int = 0, precomp: bool = True, n: int = None,
+                 on_device: bool = False):
+        self.curve, self.group, self.dev = curve, group, dev
+        frl, fpl, deg = CURVE_SHAPES[curve]
+        self.fr_limbs = frl
+        self.coord_limbs = fpl * (deg if group == 2 else 1)
+        if n is None:
+            n = points.size // (2 * self.coord_limbs)
+        self.n = n
+        flags = (TABLE_PRECOMP if precomp else 0) | (TABLE_SRC_ON_DEVICE if on_device else 0)
+        h = ctypes.c_void_p(0)
+        check(load().b200_table_upload(dev, curve, group, ptr(points), n, flags, ctypes.byref(h)))
+        self.handle = h
+
+    def info(self):
+        n, c, w, p, b = ctypes.c_size_t(), ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32(), ctypes.c_size_t()
+        check(load().b200_table_info(self.handle, ctypes.byref(n), ctypes.byref(c), ctypes.byref(w), ctypes.byref(p),
+                                     ctypes.byref(b)))
+        return {"n": n.value, "window_bits": c.value, "n_windows": w.value, "precomp": p.value,
+                "device_bytes": b.value}
+
+    def msm(self, scalars, off: int = 0, n: int = None, on_device: bool = False) -> np.ndarray:
+        """sum scalars[i] * bases[off+i] -> Jacobian {X,Y,Z} (gnark layout, uint64 limbs)."""
+        if n is None:
+            n = (scalars.size if isinstance(scalars, np.ndarray) else scalars.numel()) // self.fr_limbs
+        out = np.zeros(3 * self.coord_limbs, dtype=np.uint64)
+        fn = load().b200_msm_g1 if self.group == 1 else load().b200_msm_g2
+        check(fn(self.handle, off, n, ptr(scalars), 1 if on_device else 0, ptr(out)))
+        return out
+
+    def msm_async(self, d_scalars, d_out, off: int = 0, n: int = None):
+        check(load().b200_msm_async(self.handle, off, n, ptr(d_scalars), ptr(d_out)))
+
+    def free(self):
+        if self.handle:
+            check(load().b200_table_free(self.handle))
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Domain:
+    """Device-resident fft.Domain."""
+
+    def __init__(self, curve: int, log2n: int, dev: int = 0, generator=None, coset_gen=None):
+        self.curve, self.log2n, self.dev = curve, log2n, dev
+        self.n = 1 << log2n
+        self.fr_limbs = CURVE_SHAPES[curve][0]
+        h = ctypes.c_void_p(0)
+        check(load().b200_ntt_domain_new(dev, curve, log2n, ptr(generator), ptr(coset_gen), ctypes.byref(h)))
+        self.handle = h
+
+    def ntt(self, data, inverse=False, decimation=DIF, on_coset=False, on_device=False):
+        check(load().b200_ntt(self.handle, ptr(data), 1 if on_device else 0, 1 if inverse else 0, decimation,
+                              1 if on_coset else 0))
+        return data
+
+    def ntt_async(self, d_data, inverse=False, decimation=DIF, on_coset=False):
+        check(load().b200_ntt_async(self.handle, ptr(d_data), 1 if inverse else 0, decimation, 1 if on_coset else 0))
+
+    def compute_h(self, a, b, c, length=None, on_device=False, out=None, out_on_device=False):
+        if length is None:
+            length = a.size // self.fr_limbs
+        if out is None:
+            out = np.zeros((self.n, self.fr_limbs), dtype=np.uint64)
+        check(load().b200_groth16_compute_h(self.handle, ptr(a), ptr(b), ptr(c), length, 1 if on_device else 0,
+                                            ptr(out), 1 if out_on_device else 0))
+        return out
+
+    def free(self):
+        if self.handle:
+            check(load().b200_ntt_domain_free(self.handle))
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def point_add_jac(curve: int, group: int, acc: np.ndarray, q: np.ndarray) -> np.ndarray:
+    """acc += q on Jacobian points in gnark layout (host CPU; no device needed)."""
+    check(load().b200_point_add_jac(curve, group, ptr(acc), ptr(q)))
+    return acc
+
+
+def point_to_affine(curve: int, group: int, p: np.ndarray) -> np.ndarray:
+    out = np.zeros(p.size // 3 * 2, dtype=np.uint64)
+    check(load().b200_point_to_affine(curve, group, ptr(p), ptr(out)))
+    return out

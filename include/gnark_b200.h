@@ -1,0 +1,175 @@
+/* libgnark_b200.so - C ABI of the B200 (sm_100a) prover-arithmetic backend for gnark.
+ *
+ * This is the drop-in boundary for the Groth16 / PLONK prover hot path: every
+ * entry point below is what a cgo shim package backend/accelerated/b200/... would
+ * bind, in place of the icicle-gnark cgo calls the reference makes from
+ * backend/accelerated/icicle/groth16/<curve>/icicle.go (cited per function).
+ * The Go-side binding is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *  - Every function returns int32_t: 0 = success, non-zero = failure with a
+ *    thread-local message available from b200_last_error().  Nothing aborts or
+ *    throws across the ABI (reference: EIcicleError.AsString(), panics in
+ *    RunOnDevice closures icicle.go:122,164,200).
+ *  - All field elements / points use gnark-crypto's in-memory layout, unchanged:
+ *    fr.Element / fp.Element = [Limbs]uint64 little-endian, Montgomery form
+ *    (R = 2^(64*Limbs)); G1Affine {X,Y}; G2Affine {X{A0,A1},Y{A0,A1}}; affine
+ *    infinity = (0,0); G1Jac/G2Jac {X,Y,Z} with x = X/Z^2, y = Y/Z^3.
+ *    No Montgomery conversion is ever required of the caller
+ *    (reference: FromMontgomery/AffineFromMontgomery icicle.go:121,322,350,1008).
+ *  - Host pointers are borrowed only for the duration of the call (cgo pointer
+ *    rule); device pointers come from b200_alloc.
+ *  - Every call takes a device id or a handle bound to one and selects the device
+ *    itself (thread-local), so callers need not pin OS threads
+ *    (reference: icicle_runtime.RunOnDevice).
+ */
+#ifndef GNARK_B200_H
+#define GNARK_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* curve ids (ecc.ID order used by backend/accelerated/icicle/groth16/groth16_icicle.go:85-96) */
+enum {
+  B200_BN254 = 0,
+  B200_BLS12_381 = 1,
+  B200_BLS12_377 = 2,
+  B200_BW6_761 = 3
+};
+
+enum { B200_DIF = 0, B200_DIT = 1 }; /* fft.DIF / fft.DIT */
+
+/* b200_table_upload flags */
+enum {
+  B200_TABLE_PRECOMP = 1,      /* also build 2^(c*w)*P slabs on device (one bucket set per MSM) */
+  B200_TABLE_SRC_ON_DEVICE = 2 /* `points` is a device pointer */
+};
+
+typedef struct b200_table_s* b200_table_t;   /* device-resident MSM base table  */
+typedef struct b200_domain_s* b200_domain_t; /* device-resident fft.Domain      */
+typedef struct b200_pk_s* b200_pk_t;         /* device-resident Groth16 proving key */
+
+/* ---- runtime (replaces warmUpDevice, groth16_icicle.go:38-72) ---------------- */
+const char* b200_version(void);
+const char* b200_last_error(void);
+int32_t b200_device_count(int32_t* out_count);
+int32_t b200_init(int32_t n_dev, const int32_t* dev_ids); /* idempotent; NULL/0 = device 0 */
+int32_t b200_shutdown(void);
+/* run subsequent work of `dev` on the caller's CUDA stream (cudaStream_t), NULL = library stream */
+int32_t b200_set_stream(int32_t dev, void* cuda_stream);
+int32_t b200_sync(int32_t dev);
+
+/* ---- memory (replaces HostSlice.CopyToDevice / DeviceSlice.Free, ~70 sites) -- */
+int32_t b200_alloc(int32_t dev, size_t bytes, void** out_dev_ptr);
+int32_t b200_free(int32_t dev, void* dev_ptr);
+int32_t b200_h2d(int32_t dev, void* dst_dev, const void* src_host, size_t bytes);
+int32_t b200_d2h(int32_t dev, void* dst_host, const void* src_dev, size_t bytes);
+int32_t b200_host_alloc(size_t bytes, void** out_pinned); /* C-owned pinned staging buffers */
+int32_t b200_host_free(void* pinned);
+
+/* ---- MSM base tables (replaces loadG1/loadG1Raw/loadG2 icicle.go:319-359,
+ *      PinToGPU uploads :185-261, FreeGPUResources :1493-1549) ---------------- */
+int32_t b200_table_upload(int32_t dev, int32_t curve, int32_t group /*1|2*/, const void* points_affine_mont,
+                          size_t n, int32_t flags, b200_table_t* out);
+int32_t b200_table_free(b200_table_t t);
+int32_t b200_table_info(b200_table_t t, size_t* n, int32_t* window_bits, int32_t* n_windows, int32_t* precomp,
+                        size_t* device_bytes);
+
+/* ---- MSM (replaces msmChunkedG1/G2 icicle.go:362-467 + projectiveToGnarkAffine
+ *      :266-315; CPU twin G1Jac/G2Jac.MultiExp prove.go:194,207,227,237,283) ---
+ * out = sum_{i<n} scalars[i] * bases[off+i] as ONE Jacobian point (gnark layout).
+ * Handles n = 0, zero scalars, (0,0) bases, repeated and opposite points. */
+int32_t b200_msm(b200_table_t bases, size_t off, size_t n, const void* scalars_mont, int32_t scalars_on_dev,
+                 void* out_jac_host);
+int32_t b200_msm_g1(b200_table_t bases, size_t off, size_t n, const void* scalars_mont, int32_t scalars_on_dev,
+                    void* out_g1jac_host);
+int32_t b200_msm_g2(b200_table_t bases, size_t off, size_t n, const void* scalars_mont, int32_t scalars_on_dev,
+                    void* out_g2jac_host);
+/* stream-ordered variant: all pointers on device, no synchronisation */
+int32_t b200_msm_async(b200_table_t bases, size_t off, size_t n, const void* d_scalars_mont, void* d_out_jac);
+
+/* host-side group helpers for combining partial results (the reference sums its
+ * per-chunk MSM results on the host in Go, icicle.go:383-411; multi-GPU shards are
+ * combined the same way).  Pure CPU, no device needed. */
+int32_t b200_point_add_jac(int32_t curve, int32_t group, void* acc_jac, const void* q_jac);
+int32_t b200_point_to_affine(int32_t curve, int32_t group, const void* p_jac, void* out_affine);
+
+/* ---- NTT (replaces icicle_ntt.InitDomain/ReleaseDomain icicle.go:151,163 and
+ *      Ntt :1425,1428,1474; CPU twin fft.Domain.FFT/FFTInverse prove.go:362-386) -
+ * generator / coset_gen: one fr.Element (Montgomery) each, NULL = gnark-crypto's
+ * fft.NewDomain defaults (Generator of order 2^log2n, FrMultiplicativeGen).
+ * One domain per handle: no process-global NTT state (the reference serialises all
+ * proofs on nttDomainMu / deviceProveMu, icicle.go:53-60). */
+int32_t b200_ntt_domain_new(int32_t dev, int32_t curve, uint32_t log2n, const void* generator_mont,
+                            const void* coset_gen_mont, b200_domain_t* out);
+int32_t b200_ntt_domain_free(b200_domain_t d);
+/* in place on `data` (2^log2n fr.Elements).  DIF: natural -> bit-reversed; DIT:
+ * bit-reversed -> natural; inverse scales by 1/n; on_coset as fft.OnCoset(). */
+int32_t b200_ntt(b200_domain_t d, void* data, int32_t data_on_dev, int32_t inverse, int32_t decimation,
+                 int32_t on_coset);
+int32_t b200_ntt_async(b200_domain_t d, void* d_data, int32_t inverse, int32_t decimation, int32_t on_coset);
+
+/* ---- Groth16 quotient (replaces computeH icicle.go:1391-1488; CPU twin
+ *      prove.go:346-389).  a,b,c: `len` fr.Elements each (len <= n, zero padded
+ *      internally); h_out: n elements, BIT-REVERSED order, Montgomery - directly
+ *      usable as the scalars of MSM(G1.Z, h[:n-1]). */
+int32_t b200_groth16_compute_h(b200_domain_t d, const void* a, const void* b, const void* c, size_t len,
+                               int32_t inputs_on_dev, void* h_out, int32_t out_on_dev);
+
+/* ---- element-wise vector ops on device vectors (replaces icicle_vecops.VecOp
+ *      icicle.go:1455-1461 and the PLONK pointwise loops plonk/bn254/prove.go:
+ *      953-1076,1312-1317) ---------------------------------------------------- */
+enum { B200_VEC_MUL = 0, B200_VEC_ADD = 1, B200_VEC_SUB = 2 };
+int32_t b200_vec_op(int32_t dev, int32_t curve, int32_t op, void* d_out, const void* d_a, const void* d_b, size_t n);
+int32_t b200_vec_bit_reverse(int32_t dev, int32_t curve, void* d_data, uint32_t log2n);
+/* out[i] = a[i] * s * g^i */
+int32_t b200_vec_scale_powers(int32_t dev, int32_t curve, void* d_data, size_t n, const void* s_mont,
+                              const void* g_mont);
+
+/* ---- Groth16 prover (host layer mirroring backend/accelerated/icicle/groth16/
+ *      bn254/icicle.go:784-1360 Prove + setupDevicePointers :88-264) ------------
+ * Builds the device-resident key from the gnark ProvingKey fields
+ * (backend/groth16/bn254/setup.go:25-48).  infinity_a/b: one byte per wire. */
+typedef struct {
+  int32_t curve;
+  uint64_t domain_size;       /* pk.Domain.Cardinality */
+  const void* domain_gen;     /* pk.Domain.Generator (fr, Montgomery) or NULL */
+  const void* coset_gen;      /* pk.Domain.FrMultiplicativeGen or NULL */
+  const void* g1_alpha;       /* G1Affine */
+  const void* g1_beta;
+  const void* g1_delta;
+  const void* g2_beta;        /* G2Affine */
+  const void* g2_delta;
+  const void* g1_a; size_t n_a;   /* []G1Affine, infinities already removed */
+  const void* g1_b; size_t n_b;
+  const void* g1_z; size_t n_z;   /* n-1 entries, bit-reversed order */
+  const void* g1_k; size_t n_k;   /* private wires */
+  const void* g2_b; size_t n_b2;
+  const uint8_t* infinity_a;  /* nb_wires flags */
+  const uint8_t* infinity_b;
+  size_t nb_wires;
+  size_t nb_public;           /* r1cs.GetNbPublicVariables() (K covers wires[nb_public:]) */
+  int32_t flags;              /* B200_TABLE_PRECOMP */
+} b200_groth16_pk_desc;
+
+int32_t b200_groth16_pk_load(int32_t dev, const b200_groth16_pk_desc* desc, b200_pk_t* out);
+int32_t b200_groth16_pk_free(b200_pk_t pk);
+
+/* One proof from a solved witness (R1CSSolution{W,A,B,C}, constraint/bn254/system.go:162-165).
+ * r, s: the prover's randomness as fr.Elements (Montgomery); the Go shim samples
+ * them exactly as prove.go:170-182 does.  Outputs are gnark affine points:
+ * ar, krs: G1Affine; bs: G2Affine.  msm_out (optional, may be NULL): the five raw
+ * MSM results as Jacobian points in the order A, B1, Z(h), K, B2 - the
+ * deterministic sub-results parity tests pin. */
+int32_t b200_groth16_prove(b200_pk_t pk, const void* wires, const void* a, const void* b, const void* c,
+                           size_t n_constraints, const void* r, const void* s, void* ar_out, void* bs_out,
+                           void* krs_out, void* msm_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GNARK_B200_H */

@@ -1,0 +1,100 @@
+"""The device templates (field.cuh / curve.cuh / msm.cuh / ntt.cuh), compiled for the
+host with the PTX carry chains emulated, against the oracle.  This checks the
+kernels' per-thread logic on a box without a GPU; the -m gpu tests check the real
+thing through the C ABI."""
+import ctypes
+import random
+
+import numpy as np
+import pytest
+
+from oracle import ec, ff, ntt
+from oracle.params import CURVES
+from util import pick_base
+
+ALL = list(CURVES.values())
+
+
+def P(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+@pytest.mark.parametrize("c", ALL, ids=lambda c: c.name)
+def test_field_ops(hostemu, c):
+    rng = random.Random(5)
+    for which, (q, L) in enumerate(((c.p, c.fp_limbs), (c.r, c.fr_limbs))):
+        fid = c.curve_id * 2 + which
+        for trial in range(40):
+            a, b = rng.randrange(q), rng.randrange(q)
+            if trial == 0: a, b = 0, 0
+            if trial == 1: a, b = q - 1, q - 1
+            if trial == 2: a, b = 1, q - 1
+            if trial == 3: a, b = (1 << (64 * L)) % q, q - 2      # R mod q
+            A, B = ff.pack_elements([a], q, L), ff.pack_elements([b], q, L)
+            O = np.zeros_like(A)
+            for op, exp in ((0, (a + b) % q), (1, (a - b) % q), (2, a * b % q), (4, (-a) % q), (5, a * a % q), (6, 2 * a % q)):
+                assert hostemu.emu_field_op(fid, op, P(A), P(B), P(O)) == 0
+                assert ff.unpack_elements(O, q, L)[0] == exp, (c.name, which, op)
+            if a and trial < 6:
+                hostemu.emu_field_op(fid, 3, P(A), P(B), P(O))
+                assert ff.unpack_elements(O, q, L)[0] == pow(a, -1, q)
+
+
+@pytest.mark.parametrize("c", [c for c in ALL if c.fp2_nonresidue is not None], ids=lambda c: c.name)
+def test_fp2_ops(hostemu, c):
+    rng = random.Random(6)
+    F2 = ff.Fp2(c.p, c.fp2_nonresidue)
+    L = c.fp_limbs
+    for _ in range(20):
+        a = (rng.randrange(c.p), rng.randrange(c.p))
+        b = (rng.randrange(c.p), rng.randrange(c.p))
+        A = ff.pack_elements(list(a), c.p, L).reshape(-1)
+        B = ff.pack_elements(list(b), c.p, L).reshape(-1)
+        O = np.zeros_like(A)
+        for op, exp in ((2, F2.mul(a, b)), (5, F2.sqr(a)), (3, F2.inv(a)), (0, F2.add(a, b)), (1, F2.sub(a, b))):
+            assert hostemu.emu_field_op(100 + c.curve_id * 2, op, P(A), P(B), P(O)) == 0
+            assert tuple(ff.unpack_elements(O, c.p, L)) == exp
+
+
+@pytest.mark.parametrize("c", ALL, ids=lambda c: c.name)
+@pytest.mark.parametrize("group", (1, 2))
+def test_msm_logic(hostemu, c, group):
+    rng = random.Random(9 + group)
+    F, base = pick_base(c, group, rng)
+    n = 37
+    pts = [ec.scalar_mul(F, rng.randrange(1, 1 << 40), base) for _ in range(n)]
+    pts[3] = ec.INF
+    pts[5] = pts[4]
+    pts[7] = ec.affine_neg(F, pts[6])
+    sc = [rng.randrange(c.r) for _ in range(n)]
+    sc[0], sc[1], sc[2] = 0, c.r - 1, 1
+    sc[6] = sc[7] = 12345
+    sc[8], sc[9] = 1 << 15, (1 << 16) - 1
+    exp = ec.msm_naive(F, pts, sc)
+    PA, SA = ec.pack_points(c, group, pts), ff.pack_elements(sc, c.r, c.fr_limbs)
+    for (cw, pre, tl, ch) in ((4, 0, 3, 4), (7, 1, 2, 16), (16, 0, 64, 512), (13, 1, 5, 100)):
+        if cw >= 13 and c.fp_limbs > 6:
+            continue
+        out = np.zeros(3 * F.degree * c.fp_limbs, dtype=np.uint64)
+        assert hostemu.emu_msm(c.curve_id, group, P(PA), P(SA), n, cw, pre, tl, ch, P(out)) == 0
+        got = ec.from_jac(F, ec.unpack_points(c, group, out, ncoords=3)[0])
+        assert got == exp, (c.name, group, cw, pre)
+
+
+@pytest.mark.parametrize("c", ALL, ids=lambda c: c.name)
+def test_ntt_logic(hostemu, c):
+    rng = random.Random(4)
+    for logn in (1, 3, 6, 12, 13):
+        n = 1 << logn
+        dom = ntt.Domain(c, n)
+        a = [rng.randrange(c.r) for _ in range(n)]
+        A0 = ff.pack_elements(a, c.r, c.fr_limbs)
+        for inv in (0, 1):
+            for dec in (0, 1):
+                for cos in (0, 1):
+                    if logn >= 12 and (cos == 0 and dec == 1):
+                        continue
+                    A = A0.copy()
+                    assert hostemu.emu_ntt(c.curve_id, P(A), logn, inv, dec, cos, None, None) == 0
+                    exp = (dom.fft_inverse if inv else dom.fft)(a, dec, on_coset=bool(cos))
+                    assert ff.unpack_elements(A, c.r, c.fr_limbs) == exp, (c.name, logn, inv, dec, cos)

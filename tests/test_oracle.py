@@ -1,0 +1,115 @@
+"""Oracle self-checks (CPU).  The reference pins nothing at the bit level for this
+path ('parity unpinned'), so the oracle is anchored on properties:
+published constants property-checked, NTT against the O(n^2) definition, the
+Groth16 pipeline against the pairing equation evaluated in the exponent (the
+reference's own test is prove -> Verify, test/assert_checkcircuit.go:140-144)."""
+import random
+
+import pytest
+
+from oracle import ec, ff, groth16 as g16, ntt
+from oracle.params import CURVES
+
+ALL = list(CURVES.values())
+
+
+@pytest.mark.parametrize("c", ALL, ids=lambda c: c.name)
+def test_constants(c):
+    r, p, s = c.r, c.p, c.two_adicity
+    assert (r - 1) % (1 << s) == 0 and ((r - 1) >> s) % 2 == 1
+    w = c.root_of_unity
+    assert pow(w, 1 << s, r) == 1 and pow(w, 1 << (s - 1), r) == r - 1
+    assert pow(c.mult_gen, (r - 1) // 2, r) == r - 1          # non-residue => g^n != 1 for n | 2^s
+    assert p.bit_length() <= 64 * c.fp_limbs and r.bit_length() <= 64 * c.fr_limbs
+    if c.g1 is not None:
+        F = ff.Fp(p)
+        assert ec.is_on_curve(F, c.g1, c.b % p)
+        assert ec.scalar_mul(F, r, c.g1) is ec.INF
+    if c.g2 is not None:
+        F2 = ff.Fp2(p, c.fp2_nonresidue)
+        assert ec.scalar_mul(F2, r, c.g2) is ec.INF
+
+
+@pytest.mark.parametrize("c", ALL, ids=lambda c: c.name)
+def test_ntt_conventions(c):
+    rng = random.Random(3)
+    for logn in (0, 1, 4, 6):
+        n = 1 << logn
+        dom = ntt.Domain(c, n)
+        a = [rng.randrange(c.r) for _ in range(n)]
+        ev = ntt.dft_naive(c, a, dom.generator)
+        evc = ntt.dft_naive(c, a, dom.generator, dom.coset_gen)
+        assert ntt.bit_reverse(dom.fft(a, ntt.DIF)) == ev            # DIF: natural -> bit-reversed
+        assert dom.fft(ntt.bit_reverse(a), ntt.DIT) == ev            # DIT: bit-reversed -> natural
+        assert ntt.bit_reverse(dom.fft_inverse(ev, ntt.DIF)) == a
+        assert dom.fft_inverse(ntt.bit_reverse(ev), ntt.DIT) == a
+        assert dom.fft(ntt.bit_reverse(a), ntt.DIT, on_coset=True) == evc
+        assert ntt.bit_reverse(dom.fft(a, ntt.DIF, on_coset=True)) == evc
+        assert ntt.bit_reverse(dom.fft_inverse(evc, ntt.DIF, on_coset=True)) == a
+        assert dom.fft_inverse(ntt.bit_reverse(evc), ntt.DIT, on_coset=True) == a
+
+
+def test_lagrange_srs_convention():
+    """test/unsafekzg/kzgsrs.go:186-194: iFFT-DIF of (1,tau,tau^2,...) + BitReverse = L_i(tau)."""
+    c = CURVES["bn254"]
+    n = 8
+    dom = ntt.Domain(c, n)
+    tau = 123456789
+    pows = [pow(tau, i, c.r) for i in range(n)]
+    lag = ntt.bit_reverse(dom.fft_inverse(pows, ntt.DIF))
+    # L_i(tau) = prod_{j != i} (tau - w^j) / (w^i - w^j)
+    w = [pow(dom.generator, i, c.r) for i in range(n)]
+    for i in range(n):
+        num = den = 1
+        for j in range(n):
+            if j != i:
+                num = num * (tau - w[j]) % c.r
+                den = den * (w[i] - w[j]) % c.r
+        assert lag[i] == num * pow(den, -1, c.r) % c.r
+
+
+@pytest.mark.parametrize("c", ALL, ids=lambda c: c.name)
+def test_groth16_cubic_and_chain(c):
+    """config 1 (examples/cubic, x=3 y=35: examples/cubic/cubic_test.go:47-50) restated."""
+    for make, wit in ((g16.cubic_r1cs, lambda: g16.cubic_witness(c.r)),
+                      (lambda: g16.square_chain_r1cs(13), lambda: g16.square_chain_witness(c.r, 13))):
+        cs, W = make(), wit()
+        A, B, C = g16.solve_abc(cs, W, c.r)
+        assert all((x * y - z) % c.r == 0 for x, y, z in zip(A, B, C))
+        pk = g16.setup_dlog(c, cs, g16.random_toxic(c, 7))
+        pr = g16.prove_dlog(c, cs, pk, W, 0x1234567, 0x7654321)
+        assert g16.verify_dlog(c, cs, pk, pr, W)
+        assert pr.h[pk.domain.n - 1] == 0                 # deg h <= n-2 (prove.go:225)
+        W2 = list(W); W2[2] = (W2[2] + 1) % c.r
+        assert not g16.verify_dlog(c, cs, pk, g16.prove_dlog(c, cs, pk, W2, 1, 2), W2)
+
+
+def test_compute_h_identity():
+    """h(X) (X^n - 1) = A(X)B(X) - C(X) at a random point."""
+    c = CURVES["bn254"]
+    cs = g16.square_chain_r1cs(29)
+    W = g16.square_chain_witness(c.r, 29)
+    A, B, C = g16.solve_abc(cs, W, c.r)
+    dom = ntt.Domain(c, cs.nb_constraints)
+    n = dom.n
+    h = ntt.bit_reverse(g16.compute_h(dom, A, B, C))
+    pad = [0] * (n - len(A))
+    ca = ntt.bit_reverse(dom.fft_inverse(A + pad, ntt.DIF))
+    cb = ntt.bit_reverse(dom.fft_inverse(B + pad, ntt.DIF))
+    cc = ntt.bit_reverse(dom.fft_inverse(C + pad, ntt.DIF))
+    x = 0xabcdef1234567
+    r = c.r
+    lhs = ntt.poly_eval(r, h, x) * (pow(x, n, r) - 1) % r
+    rhs = (ntt.poly_eval(r, ca, x) * ntt.poly_eval(r, cb, x) - ntt.poly_eval(r, cc, x)) % r
+    assert lhs == rhs
+
+
+def test_filter_semantics():
+    """backend/groth16/bn254/utils_test.go:17-38 (filterHeap) - the only exact-value test on
+    the reference's prove path; our K scalars are W[nb_public:] minus removed wires."""
+    def filter_heap(slice_, first, to_remove):
+        rm = set(to_remove)
+        return [v for i, v in enumerate(slice_) if (i + first) not in rm]
+    elems = [1, 2, 3, 4, 5, 6, 7, 8, 9, 10]
+    assert filter_heap(elems, 2, [2, 3, 5]) == [3, 5, 6, 7, 8, 9, 10]   # indices 2,3,5 -> drop 1,2,4
+    assert filter_heap(elems, 0, []) == elems
