@@ -1,0 +1,314 @@
+#!/usr/bin/env python3
+"""bench.py - BN254 G1 MSM throughput (BASELINE.json metric, config 2) on N B200s.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]          # this repo's CUDA path
+  python bench.py --impl reference [...]                        # CPU arm (oracle port, all host cores)
+  torchrun --nproc-per-node N bench.py --gpus N ...             # one rank per GPU
+
+One "step" = one full MSM (decompose -> sort -> bucket accumulate -> reduce) over
+2^20 random scalars per GPU against a device-resident base table (PinToGPU
+semantics of the reference, backend/accelerated/icicle/groth16/bn254/icicle.go:185-261).
+N > 1: the (scalar, base) index range is sharded over ranks (weak scaling: 2^20 per
+GPU), each rank produces one partial point, one NCCL all_gather of N Jacobian
+points, host-side group adds (the reference sums its chunk results the same way,
+icicle.go:383-411).  Prints ONE JSON line on rank 0.
+"""
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "bn254_g1_msm_scalar_muls_per_sec"
+UNIT = "scalar-muls/s"
+LOG_N = 20
+SEED = 0x6E61726B00000002  # config 2 seed
+
+
+# --------------------------------------------------------------------------------------
+# workload (synthetic, seeded).  Uses the oracle ONLY to materialise known-discrete-log
+# bases and to check the result before timing (checker role) and for the CPU arm.
+# --------------------------------------------------------------------------------------
+def make_workload(n, seed, rank=0):
+    import random
+    from oracle import corelib, ec, ff
+    from oracle.params import BN254 as C
+    rng = random.Random(seed + 7919 * rank)
+    rs = np.random.RandomState((seed + rank) & 0x7FFFFFFF)
+
+    def rand_fr(count):
+        # uniform in [0, r) by rejection on 254-bit draws, canonical -> Montgomery via the oracle
+        a = rs.randint(0, 1 << 62, size=(count, 4), dtype=np.int64).astype(np.uint64)
+        a[:, 3] &= np.uint64((1 << 61) - 1)          # < 2^253 < r  (r ~ 2^253.6): uniform on a 2^253 subset
+        return a
+    # Montgomery residues are themselves uniform field elements: use the raw limbs as the
+    # Montgomery representation (value = limbs * R^-1), no conversion needed.
+    ks_m = rand_fr(n)
+    sc_m = rand_fr(n)
+    pts = corelib.fixed_base(C, 1, ec.pack_points(C, 1, [C.g1]), ks_m)
+    dot = corelib.fr_dot(C, ks_m, sc_m)               # sum k_i s_i mod r
+    expected = ec.scalar_mul(ff.Fp(C.p), dot, C.g1)   # known-dlog oracle
+    return C, pts, sc_m, expected
+
+
+def jac_to_affine(C, jac):
+    from oracle import ec, ff
+    return ec.from_jac(ff.Fp(C.p), ec.unpack_points(C, 1, jac, ncoords=3)[0])
+
+
+# --------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.idx = gpu_index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+                for k, nme in enumerate(names):
+                    if r[3 + k].lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# --------------------------------------------------------------------------------------
+def cpu_msm_rate(C, pts, sc, sample_n, reps, threads):
+    """oracle port (restatement of gnark-crypto's MultiExp algorithm, NOT gnark-crypto) on host cores."""
+    from oracle import corelib
+    p, s = pts[:sample_n], sc[:sample_n]
+    corelib.msm(C, 1, p, s, nthreads=threads)         # warm
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        corelib.msm(C, 1, p, s, nthreads=threads)
+    dt = (time.perf_counter() - t0) / reps
+    return sample_n / dt, dt
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of this path.  gnark (Go) cannot be
+    built here and its arithmetic lives in the absent gnark-crypto module, so this arm times the
+    C++ restatement of the same algorithm (oracle/c/oracle.cpp) on all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = 1 << LOG_N
+    threads = os.cpu_count() or 1
+    sample_n = n if threads >= 16 else n >> 2
+    C, pts, sc, expected = make_workload(sample_n, SEED)
+    from oracle import corelib
+    assert jac_to_affine(C, corelib.msm(C, 1, pts, sc, nthreads=threads)) == expected
+    for _ in range(args.warmup):
+        corelib.msm(C, 1, pts, sc, nthreads=threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        corelib.msm(C, 1, pts, sc, nthreads=threads)
+    dt = time.perf_counter() - t0
+    value = sample_n * args.steps / dt
+    sample = f"{args.steps} x BN254 G1 MSM of 2^{int(np.log2(sample_n))} points per step on {threads} host threads"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32x8 (254-bit Montgomery)",
+        "data": "synthetic",
+        "config": {"workload": f"BN254 G1 MSM 2^{LOG_N} random scalars/bases (BASELINE configs[1]); CPU arm sample 2^{int(np.log2(sample_n))}"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# --------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from gnark_b200 import lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torchrun --nproc-per-node N for --gpus N")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib.load()
+    lib.init([local])
+    lib.set_stream(local, torch.cuda.current_stream().cuda_stream)
+
+    n = 1 << LOG_N
+    C, pts, sc, expected = make_workload(n, SEED, rank)
+    table = lib.Table(lib.BN254, 1, pts, dev=local, precomp=True)
+    info = table.info()
+    d_sc = torch.from_numpy(sc.view(np.int64)).cuda()
+    d_out = torch.zeros(12, dtype=torch.int64, device="cuda")
+    h_sc = torch.from_numpy(sc.view(np.int64)).pin_memory()
+    h_out = np.zeros(12, dtype=np.uint64)
+
+    # correctness on the timed input before timing (known-dlog oracle)
+    table.msm_async(d_sc, d_out, n=n)
+    torch.cuda.synchronize()
+    got = jac_to_affine(C, d_out.cpu().numpy().view(np.uint64))
+    assert got == expected, "GPU MSM does not match the known-discrete-log oracle"
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def combine(d_partial):
+        """N partial points -> one (all_gather over NCCL, host adds); returns on every rank."""
+        if world == 1:
+            return d_partial
+        parts = [torch.empty_like(d_partial) for _ in range(world)]
+        dist.all_gather(parts, d_partial)
+        acc = parts[0].cpu().numpy().view(np.uint64).copy()
+        for p in parts[1:]:
+            lib.point_add_jac(lib.BN254, 1, acc, p.cpu().numpy().view(np.uint64))
+        return acc
+
+    # ---- device-resident throughput (value) ------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        table.msm_async(d_sc, d_out, n=n)
+        combine(d_out)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        table.msm_async(d_sc, d_out, n=n)
+        combine(d_out)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end to end through the C ABI with host buffers (e2e) --------------------------
+    for _ in range(2):
+        table.msm(h_sc, n=n)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        part = table.msm(h_sc, n=n)      # H2D scalars (pinned) + MSM + D2H result, synchronous
+        if world > 1:
+            combine(torch.from_numpy(part.view(np.int64)).cuda())
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+
+    # ---- stage profile of the dominant kernel (accumulate) ------------------------------
+    prof = []
+    for _ in range(5):
+        prof.append(table.msm_profile(d_sc, d_out, n=n))
+    stage_ms = {k: float(np.median([p[k] for p in prof])) for k in prof[0]}
+
+    if world > 1:
+        t = torch.tensor([ms, e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_s = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    total = n * world
+    value = total * args.steps / (ms / 1e3)
+    e2e_value = total * args.steps / e2e_s
+    peak, peak_src = measured_peak_gbs()
+    W = info["n_windows"]
+    alg_bytes = n * W * (64 + 4)           # W x (sizeof(affine) + 4 B index) per scalar-mul
+    acc_ms = stage_ms["accumulate"]
+    achieved = alg_bytes / (acc_ms / 1e3) / 1e9
+    threads = os.cpu_count() or 1
+    sample_n = 1 << 18
+    cpu_rate, cpu_dt = cpu_msm_rate(C, pts, sc, sample_n, 3, threads)
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u32x8 (254-bit Montgomery integers)", "data": "synthetic",
+        "config": {
+            "workload": f"BN254 G1 MSM 2^{LOG_N} random scalars/bases per GPU (BASELINE configs[1]), bases device-resident",
+            "points_per_gpu": n, "window_bits": info["window_bits"], "windows": W, "precomputed_table": bool(info["precomp"]),
+            "table_bytes": info["device_bytes"], "parallelism": f"point-range shard x{world}" if world > 1 else "single GPU",
+            "l2": "no flush: per-step working set (table %.2f GiB + scalars 32 MiB + 256 MiB sort buffers) exceeds the 126 MB L2" % (info["device_bytes"] / 2**30),
+        },
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * 32 * world, "d2h_bytes_per_step": 96 * world,
+                "ms_per_step": 1e3 * e2e_s / args.steps,
+                "note": "b200_msm_g1 with pinned host scalars; bases resident (PinToGPU)"},
+        "gpu_launches": 8 * args.steps,
+        "roofline": {"bound": "hbm", "kernel": "k_msm_accumulate", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": acc_ms,
+                     "note": "integer-ALU (IMAD) bound, not HBM bound: ~10 Fp-mul per gathered 68 B (DESIGN.md)"},
+        "stage_ms": stage_ms,
+        "cpu_baseline": {"value": cpu_rate, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"3 x BN254 G1 MSM of 2^18 points of the same workload ({cpu_dt:.2f} s each)"},
+        "clocks": clocks,
+    }
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -82,7 +82,8 @@ void msm_tuning(size_t n, int nwin, int c, uint32_t* task_len, uint32_t* chunk) 
   *chunk = (uint32_t)env_int("GB200_MSM_CHUNK", c >= 12 ? 8 : 4);
 }
 
-int32_t msm_on_stream(DeviceCtx* ctx, b200_table_s* t, size_t off, size_t n, const void* d_scalars, void* d_out) {
+int32_t msm_on_stream(DeviceCtx* ctx, b200_table_s* t, size_t off, size_t n, const void* d_scalars, void* d_out,
+                      cudaEvent_t* stage_events) {
   if (off + n > t->n) return set_error("msm: range [off, off+n) exceeds the table");
   uint32_t task_len, chunk;
   msm_tuning(n, t->nwin, t->c, &task_len, &chunk);
@@ -91,7 +92,7 @@ int32_t msm_on_stream(DeviceCtx* ctx, b200_table_s* t, size_t off, size_t n, con
   void* ws = nullptr;
   CK(cudaMallocAsync(&ws, ws_bytes, ctx->stream));
   cudaError_t e = t->ops->run(ctx->stream, (uint32_t)n, (uint32_t)t->n, (uint32_t)off, t->c, t->precomp, task_len, chunk,
-                              t->d_points, d_scalars, d_out, ws);
+                              t->d_points, d_scalars, d_out, ws, stage_events);
   cudaError_t e2 = cudaFreeAsync(ws, ctx->stream);
   if (e != cudaSuccess) return cuda_fail("msm enqueue", e);
   if (e2 != cudaSuccess) return cuda_fail("cudaFreeAsync", e2);
@@ -256,6 +257,25 @@ int32_t b200_msm_async(b200_table_t t, size_t off, size_t n, const void* d_scala
   if (!t) return set_error("msm: null table");
   DeviceCtx* ctx; int32_t rc = device_ctx(t->dev, &ctx); if (rc) return rc;
   return msm_on_stream(ctx, t, off, n, d_scalars, d_out);
+  GUARD_END
+}
+
+// step profile: device time of each pipeline stage of one MSM (ms), stages =
+// {decompose, sort, offsets+task scan, accumulate, combine, reduce chunks, set sum+finish}
+int32_t b200_msm_profile(b200_table_t t, size_t off, size_t n, const void* d_scalars, void* d_out, float* stage_ms) {
+  GUARD_BEGIN
+  if (!t || !stage_ms) return set_error("msm_profile: null argument");
+  DeviceCtx* ctx; int32_t rc = device_ctx(t->dev, &ctx); if (rc) return rc;
+  cudaEvent_t ev[8];
+  for (int k = 0; k < 8; k++) CK(cudaEventCreate(&ev[k]));
+  rc = msm_on_stream(ctx, t, off, n, d_scalars, d_out, ev);
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  if (rc == 0 && e == cudaSuccess && n > 0)
+    for (int k = 0; k < 7; k++) cudaEventElapsedTime(&stage_ms[k], ev[k], ev[k + 1]);
+  for (int k = 0; k < 8; k++) cudaEventDestroy(ev[k]);
+  if (rc) return rc;
+  if (e != cudaSuccess) return cuda_fail("msm_profile", e);
+  return 0;
   GUARD_END
 }
 

@@ -49,7 +49,8 @@ struct b200_domain_s {
 };
 
 namespace gb200 {
-int32_t msm_on_stream(DeviceCtx* ctx, b200_table_s* t, size_t off, size_t n, const void* d_scalars, void* d_out);
+int32_t msm_on_stream(DeviceCtx* ctx, b200_table_s* t, size_t off, size_t n, const void* d_scalars, void* d_out,
+                      cudaEvent_t* stage_events = nullptr);
 }
 
 #define CK(x)                                                        \

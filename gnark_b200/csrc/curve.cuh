@@ -42,7 +42,7 @@ struct alignas(16) XYZZ {
   HD XYZZ neg() const { XYZZ p = *this; p.y = y.neg(); return p; }
 
   // this = 2 * a (a affine, not infinity)             mdbl-2008-s
-  HD void set_double_affine(const Affine<F>& a) {
+  HDNI void set_double_affine(const Affine<F>& a) {
     if (a.y.is_zero()) { *this = inf(); return; }
     F U = a.y.dbl();
     F V = U.sqr();
@@ -57,7 +57,7 @@ struct alignas(16) XYZZ {
   }
 
   // this *= 2                                           dbl-2008-s-1
-  HD void dbl() {
+  HDNI void dbl() {
     if (is_inf()) return;
     if (y.is_zero()) { *this = inf(); return; }
     F U = y.dbl();
@@ -98,7 +98,7 @@ struct alignas(16) XYZZ {
   }
 
   // this += q                                           add-2008-s
-  HD void add(const XYZZ& q) {
+  HDNI void add(const XYZZ& q) {
     if (q.is_inf()) return;
     if (is_inf()) { *this = q; return; }
     F U1 = x * q.zz;

@@ -208,7 +208,8 @@ struct alignas(16) Fp2 {
   HD friend Fp2 operator+(const Fp2& x, const Fp2& y) { Fp2 r; r.a0 = x.a0 + y.a0; r.a1 = x.a1 + y.a1; return r; }
   HD friend Fp2 operator-(const Fp2& x, const Fp2& y) { Fp2 r; r.a0 = x.a0 - y.a0; r.a1 = x.a1 - y.a1; return r; }
   HD static F mul_beta(const F& t) { return BETA == 1 ? t : t.mul_small(BETA); }
-  HD friend Fp2 operator*(const Fp2& x, const Fp2& y) {
+  // not inlined on device: one copy of the 3-multiplication body per kernel
+  HDNI static Fp2 mul(const Fp2& x, const Fp2& y) {
     // Karatsuba: 3 base multiplications
     F v0 = x.a0 * y.a0;
     F v1 = x.a1 * y.a1;
@@ -218,7 +219,8 @@ struct alignas(16) Fp2 {
     r.a1 = s - v0 - v1;
     return r;
   }
-  HD Fp2 sqr() const {
+  HD friend Fp2 operator*(const Fp2& x, const Fp2& y) { return mul(x, y); }
+  HDNI Fp2 sqr() const {
     if (BETA == 1) {  // (a0+a1)(a0-a1), 2 a0 a1
       Fp2 r;
       F t = a0 * a1;
@@ -226,7 +228,7 @@ struct alignas(16) Fp2 {
       r.a1 = t + t;
       return r;
     }
-    return (*this) * (*this);
+    return mul(*this, *this);
   }
   HD Fp2 neg() const { Fp2 r; r.a0 = a0.neg(); r.a1 = a1.neg(); return r; }
   HD Fp2 dbl() const { Fp2 r; r.a0 = a0.dbl(); r.a1 = a1.dbl(); return r; }

@@ -26,12 +26,12 @@ struct MsmInst {
   }
   static cudaError_t run(cudaStream_t st, uint32_t n, uint32_t stride, uint32_t off, int c, int precomp,
                          uint32_t task_len, uint32_t chunk, const void* d_table, const void* d_scalars,
-                         void* d_out_jac, void* ws) {
+                         void* d_out_jac, void* ws, cudaEvent_t* ev) {
     MsmPlan pl = plan(n, stride, off, c, precomp, task_len, chunk);
     MsmLayout<F> L;
     GB_CUDA_TRY(msm_layout<F>(pl, L));
     return msm_enqueue<Fr, F>(st, pl, reinterpret_cast<const Affine<F>*>(d_table),
-                              reinterpret_cast<const Fr*>(d_scalars), reinterpret_cast<Jacobian<F>*>(d_out_jac), ws, L);
+                              reinterpret_cast<const Fr*>(d_scalars), reinterpret_cast<Jacobian<F>*>(d_out_jac), ws, L, ev);
   }
   static cudaError_t precompute(cudaStream_t st, uint32_t n, int nwin, int c, void* d_table) {
     if (n == 0 || nwin <= 1) return cudaSuccess;
@@ -183,17 +183,21 @@ struct HostGroupInst {
   }
 };
 
-#define GB200_REGISTER_CURVE(ID, FR, FP, G2F, HFR, HFP, HG2F)                      \
+#define GB200_REGISTER_MSM(TAG, ID, GROUP, FR, F)                                  \
   namespace {                                                                       \
-  struct Registrar_##ID {                                                           \
-    Registrar_##ID() {                                                              \
-      register_msm_ops(ID, 1, MsmInst<FR, FP>::ops());                              \
-      register_msm_ops(ID, 2, MsmInst<FR, G2F>::ops());                             \
+  struct RegistrarMsm_##TAG {                                                       \
+    RegistrarMsm_##TAG() { register_msm_ops(ID, GROUP, MsmInst<FR, F>::ops()); }    \
+  } registrar_msm_##TAG;                                                            \
+  }
+#define GB200_REGISTER_FR(TAG, ID, FR, HFR, HFP, HG2F)                             \
+  namespace {                                                                       \
+  struct RegistrarFr_##TAG {                                                        \
+    RegistrarFr_##TAG() {                                                           \
       register_ntt_ops(ID, NttInst<FR>::ops());                                     \
       register_host_group_ops(ID, 1, HostGroupInst<HFR, HFP>::ops());               \
       register_host_group_ops(ID, 2, HostGroupInst<HFR, HG2F>::ops());              \
     }                                                                               \
-  } registrar_##ID;                                                                 \
+  } registrar_fr_##TAG;                                                             \
   }
 
 }  // namespace gb200

@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(128) k_msm_reduce_chunks(MsmPlan pl, uint32_t 
 
 // one block per set: tree sum of that set's chunk sums (dynamic shared memory)
 template <class F>
-__global__ void k_msm_set_sum(uint32_t chunks_per_set, const XYZZ<F>* __restrict__ chunk_sums,
+__global__ void __launch_bounds__(256) k_msm_set_sum(uint32_t chunks_per_set, const XYZZ<F>* __restrict__ chunk_sums,
                               XYZZ<F>* __restrict__ set_sums) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   XYZZ<F>* sm = reinterpret_cast<XYZZ<F>*>(smem_raw);
@@ -144,6 +144,7 @@ __global__ void __launch_bounds__(128) k_msm_precompute(uint32_t n, int nwin, in
 // ---------------------------------------------------------------------------
 // workspace + driver
 // ---------------------------------------------------------------------------
+constexpr int MSM_NUM_EVENTS = 8;
 struct MsmWorkspace {
   void* base = nullptr;
   size_t bytes = 0;
@@ -195,7 +196,7 @@ cudaError_t msm_layout(const MsmPlan& pl, MsmLayout<F>& L) {
 // largest power-of-two block that fits `budget` bytes of XYZZ<F> in shared memory
 template <class F>
 inline int msm_set_sum_threads(size_t budget = 160 * 1024) {
-  int t = 1024;
+  int t = 256;  // __launch_bounds__ of k_msm_set_sum (register budget: up to 255 regs/thread)
   while ((size_t)t * sizeof(XYZZ<F>) > budget) t >>= 1;
   return t;
 }
@@ -204,7 +205,10 @@ inline int msm_set_sum_threads(size_t budget = 160 * 1024) {
 // d_out: one Jacobian<F> on device.  ws must hold msm_layout().total bytes.
 template <class Fr, class F>
 cudaError_t msm_enqueue(cudaStream_t stream, const MsmPlan& pl, const Affine<F>* d_table, const Fr* d_scalars,
-                        Jacobian<F>* d_out, void* ws, const MsmLayout<F>& L) {
+                        Jacobian<F>* d_out, void* ws, const MsmLayout<F>& L, cudaEvent_t* ev = nullptr) {
+  // ev (optional, MSM_NUM_EVENTS entries): stage boundaries for the step profile
+  // (the reference's ICICLE_STEP_PROFILE timers, icicle.go:72-75,1088-1094)
+#define GB_EV(k) do { if (ev) GB_CUDA_TRY(cudaEventRecord(ev[k], stream)); } while (0)
   unsigned char* w = reinterpret_cast<unsigned char*>(ws);
   uint32_t* keys0 = (uint32_t*)(w + L.o_keys0);
   uint32_t* keys1 = (uint32_t*)(w + L.o_keys1);
@@ -226,26 +230,35 @@ cudaError_t msm_enqueue(cudaStream_t stream, const MsmPlan& pl, const Affine<F>*
     k_msm_finish<F><<<1, 1, 0, stream>>>(0, pl.c, sets, d_out);  // nsets=0 handled below
     return cudaGetLastError();
   }
+  GB_EV(0);
   k_msm_decompose<Fr><<<(pl.n + 255) / 256, 256, 0, stream>>>(pl, d_scalars, keys0, vals0);
+  GB_EV(1);
   int end_bit = 1;
   while ((1ull << end_bit) <= nb) end_bit++;
   GB_CUDA_TRY(cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, keys0, keys1, vals0, vals1, (int)L.m, 0, end_bit,
                                               stream));
+  GB_EV(2);
   k_msm_bucket_offsets<<<(nb + 1 + 255) / 256, 256, 0, stream>>>(keys1, (uint32_t)L.m, nb, off);
   k_msm_task_counts<<<(nb + 1 + 255) / 256, 256, 0, stream>>>(off, nb, pl.task_len, ntasks);
   cub_bytes = L.cub_bytes;
   GB_CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, ntasks, task_off, (int)nb + 1, stream));
+  GB_EV(3);
   k_msm_accumulate<F><<<(unsigned)((L.max_tasks + 127) / 128), 128, 0, stream>>>(pl, d_table, vals1, off, task_off,
                                                                                  partial);
+  GB_EV(4);
   k_msm_combine<F><<<(nb + 127) / 128, 128, 0, stream>>>(pl, task_off, partial, buckets);
+  GB_EV(5);
   const uint32_t nchunks = L.chunks_per_set * (uint32_t)pl.nsets;
   k_msm_reduce_chunks<F><<<(nchunks + 127) / 128, 128, 0, stream>>>(pl, L.chunks_per_set, buckets, chunks);
+  GB_EV(6);
   int st = msm_set_sum_threads<F>();
   while (st > 32 && (uint32_t)st > L.chunks_per_set) st >>= 1;
   const size_t smem = (size_t)st * sizeof(XYZZ<F>);
   GB_CUDA_TRY(cudaFuncSetAttribute(k_msm_set_sum<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_msm_set_sum<F><<<pl.nsets, st, smem, stream>>>(L.chunks_per_set, chunks, sets);
   k_msm_finish<F><<<1, 1, 0, stream>>>(pl.nsets, pl.c, sets, d_out);
+  GB_EV(7);
+#undef GB_EV
   return cudaGetLastError();
 }
 

@@ -92,6 +92,12 @@ int32_t b200_msm_g2(b200_table_t bases, size_t off, size_t n, const void* scalar
 /* stream-ordered variant: all pointers on device, no synchronisation */
 int32_t b200_msm_async(b200_table_t bases, size_t off, size_t n, const void* d_scalars_mont, void* d_out_jac);
 
+/* step profile (the reference's ICICLE_STEP_PROFILE timers, icicle.go:72-75,1088-1094):
+ * device milliseconds of the 7 pipeline stages of one MSM - decompose, sort,
+ * offsets+task scan, accumulate, combine, reduce chunks, set sum+finish. */
+int32_t b200_msm_profile(b200_table_t bases, size_t off, size_t n, const void* d_scalars_mont, void* d_out_jac,
+                         float* stage_ms /* [7] */);
+
 /* host-side group helpers for combining partial results (the reference sums its
  * per-chunk MSM results on the host in Go, icicle.go:383-411; multi-GPU shards are
  * combined the same way).  Pure CPU, no device needed. */

@@ -1,0 +1,83 @@
+"""Groth16 prove through the reference-shaped API (gnark_b200.groth16 mirrors
+backend/accelerated/icicle/groth16) on the GPU.  The reference's own test is
+prove -> Verify (backend/accelerated/icicle/groth16/marshal_test.go:50-57); here the
+trapdoor is known, so each of the five MSM results AND the three proof points are
+compared bit-exactly with dlog * base, and the pairing equation is checked in the
+exponent.  r, s are injected."""
+import random
+
+import numpy as np
+import pytest
+
+from oracle import ec, ff
+from oracle import groth16 as g16
+from oracle.params import CURVES
+from util import build_groth16_pk, pack_solution
+
+pytestmark = pytest.mark.gpu
+ALL = list(CURVES.values())
+
+
+def run_case(gpu, c, cs, W, precomp, seed):
+    from gnark_b200 import groth16 as b200
+    pk, pkd, (F1, g1), (F2, g2) = build_groth16_pk(c, cs, g16.random_toxic(c, seed), seed)
+    rng = random.Random(seed)
+    rs = [rng.randrange(c.r), rng.randrange(c.r)]
+    it = iter(rs)
+    sol = pack_solution(c, cs, W)
+    proof = b200.ProveSolution(pk, sol, b200.WithDeviceID(0), b200.WithPrecompute(precomp),
+                               b200.WithRandomness(lambda q: next(it)), keep_msm=True)
+    want = g16.prove_dlog(c, cs, pkd, W, rs[0], rs[1])
+    assert g16.verify_dlog(c, cs, pkd, want, W)
+    # five raw MSM results (A, B1, Z, K in G1; B2 in G2)
+    L = 3 * c.fp_limbs
+    m = proof.msm
+    for k, dlog in enumerate((want.msm_a, want.msm_b, want.msm_z, want.msm_k)):
+        got = ec.from_jac(F1, ec.unpack_points(c, 1, m[k * L:(k + 1) * L], ncoords=3)[0])
+        assert got == ec.scalar_mul(F1, dlog, g1), ("msm", k)
+    got = ec.from_jac(F2, ec.unpack_points(c, 2, m[4 * L:], ncoords=3)[0])
+    assert got == ec.scalar_mul(F2, want.msm_b, g2)
+    # proof points
+    assert ec.unpack_points(c, 1, proof.Ar)[0] == ec.scalar_mul(F1, want.ar, g1)
+    assert ec.unpack_points(c, 2, proof.Bs)[0] == ec.scalar_mul(F2, want.bs, g2)
+    assert ec.unpack_points(c, 1, proof.Krs)[0] == ec.scalar_mul(F1, want.krs, g1)
+    pk.free_gpu_resources()
+
+
+@pytest.mark.parametrize("c", ALL, ids=lambda c: c.name)
+def test_cubic(gpu, c):
+    """BASELINE config 1: examples/cubic (x^3 + x + 5 = y, x = 3, y = 35), n = 4."""
+    run_case(gpu, c, g16.cubic_r1cs(), g16.cubic_witness(c.r), precomp=False, seed=11)
+    run_case(gpu, c, g16.cubic_r1cs(), g16.cubic_witness(c.r), precomp=True, seed=12)
+
+
+@pytest.mark.parametrize("c", ALL, ids=lambda c: c.name)
+def test_square_chain(gpu, c):
+    """x -> x^2 chain, the shape of backend/groth16/groth16_test.go:126-156 (domain 2^10; not a power of two)."""
+    m = 1000 if c.fp_limbs <= 6 else 200
+    run_case(gpu, c, g16.square_chain_r1cs(m), g16.square_chain_witness(c.r, m), precomp=True, seed=5)
+
+
+def test_api_surface(gpu):
+    from gnark_b200 import groth16 as b200
+    with pytest.raises(ValueError):
+        b200.NewConfig(b200.WithDeviceID(-1))
+    with pytest.raises(ValueError):
+        b200.NewConfig(b200.WithProverOptions())
+    with pytest.raises(ValueError):
+        b200.NewProvingKey(99)
+    assert b200.NewProvingKey(b200.BN254).curve == b200.BN254
+
+    class Solver:                      # stand-in for r1cs.Solve (CPU, out of scope)
+        def __init__(self, c, cs): self.c, self.cs = c, cs
+        def Solve(self, W): return pack_solution(self.c, self.cs, W)
+    c = CURVES["bn254"]
+    cs = g16.cubic_r1cs()
+    pk, pkd, (F1, g1), _ = build_groth16_pk(c, cs, g16.random_toxic(c, 3), 3)
+    proof = b200.Prove(Solver(c, cs), pk, g16.cubic_witness(c.r))       # crypto-random r, s
+    assert ec.is_on_curve(F1, ec.unpack_points(c, 1, proof.Ar)[0], c.b)
+    # wrong witness size is an error, not a crash
+    bad = pack_solution(c, cs, g16.cubic_witness(c.r))
+    bad.W = bad.W[:-1]
+    with pytest.raises(ValueError):
+        b200.ProveSolution(pk, bad)
