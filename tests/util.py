@@ -11,17 +11,12 @@ def rng_for(*key):
     return random.Random(hash(key) & 0xFFFFFFFF)
 
 
-def pick_base(curve, group, rng):
-    """A base point for known-dlog tests.  a = 0 formulas never use b, so any
-    (x, y) with y != 0 generates a valid group on its own curve y^2 = x^3 + b'."""
-    F = ff.base_field(curve, group)
-    if group == 1 and curve.g1 is not None:
-        return F, curve.g1
-    if group == 2 and curve.g2 is not None:
-        return F, curve.g2
-    x = F.from_coords([rng.randrange(curve.p) for _ in range(F.degree)])
-    y = F.from_coords([rng.randrange(1, curve.p) for _ in range(F.degree)])
-    return F, (x, y)
+def pick_base(curve, group, rng=None):
+    """A base point of prime order r: gnark-crypto's public generator where recalled, else a
+    derived order-r point on an a = 0 curve over the same field (oracle/derive.py) - the group
+    law never uses b, so the arithmetic exercised is identical."""
+    from oracle import derive
+    return ff.base_field(curve, group), derive.subgroup_point(curve, group)
 
 
 def known_dlog_instance(curve, group, n, seed, skew=False):
