@@ -29,7 +29,8 @@ struct NttScale {
 
 // One pass: tile of 2^(S+cb) elements in shared memory (limb-major), blockDim = tile/2.
 template <class Fr>
-__global__ void k_ntt_pass(NttPass p, int logn, int dit, const Fr* __restrict__ tw, Fr* __restrict__ data,
+__global__ void __launch_bounds__(1 << (NTT_MAX_TILE_LOG - 1))
+k_ntt_pass(NttPass p, int logn, int dit, const Fr* __restrict__ tw, Fr* __restrict__ data,
                            const Fr* __restrict__ pre, int pre_bitrev, const Fr* __restrict__ post, int post_bitrev,
                            int use_const, Fr post_const) {
   constexpr int N = Fr::N;
