@@ -283,7 +283,7 @@ def run_b200(args):
     acc_ms = stage_ms["accumulate"]
     achieved = alg_bytes / (acc_ms / 1e3) / 1e9
     threads = os.cpu_count() or 1
-    sample_n = 1 << 18
+    sample_n = n if threads >= 32 else 1 << 18   # many-core hosts need the full problem to scale
     cpu_rate, cpu_dt = cpu_msm_rate(C, pts, sc, sample_n, 3, threads)
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -305,12 +305,60 @@ def run_b200(args):
                      "note": "integer-ALU (IMAD) bound, not HBM bound: ~10 Fp-mul per gathered 68 B (DESIGN.md)"},
         "stage_ms": stage_ms,
         "cpu_baseline": {"value": cpu_rate, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"3 x BN254 G1 MSM of 2^18 points of the same workload ({cpu_dt:.2f} s each)"},
+                         "sample": f"3 x BN254 G1 MSM of 2^{int(np.log2(sample_n))} points of the same workload "
+                                   f"({cpu_dt:.2f} s each, window picked by a sweep)"},
         "clocks": clocks,
     }
+    if world == 1 and not args.no_groth16:
+        try:
+            table.free()
+            out["groth16"] = groth16_leg(local, pts, n)
+        except Exception as e:  # the headline metric must still be printed
+            out["groth16"] = {"error": repr(e)}
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def groth16_leg(dev, g1_pts, n):
+    """Secondary BASELINE metric: Groth16 prove ms at 2^20 R1CS (configs[2]), BN254, 1 GPU.
+    From "A,B,C,W on the host" to "3 proof points on the host" (solver excluded, as in
+    SURVEY.md §8d config 3): 7 NTT(2^20) + 4 G1 MSM + 1 G2 MSM + host-side assembly.
+    Synthetic key: G1 tables reuse the benchmark's 2^20 known-dlog points, G2.B tiles 2^16
+    oracle-generated points; synthetic (unsatisfied) solution vectors - timing only, the
+    pipeline's parity is pinned by tests/test_gpu_groth16.py at small sizes."""
+    from gnark_b200 import groth16 as g16
+    from oracle import corelib, ec, ff
+    from oracle.params import BN254 as C
+    rs = np.random.RandomState(5)
+
+    def rand_fr(count):
+        a = rs.randint(0, 1 << 62, size=(count, 4), dtype=np.int64).astype(np.uint64)
+        a[:, 3] &= np.uint64((1 << 61) - 1)
+        return a
+    nb_wires, nb_public = n + 2, 2
+    g2_small = corelib.fixed_base(C, 2, ec.pack_points(C, 2, [C.g2]), rand_fr(1 << 16))
+    g2_b = np.tile(g2_small, (n // (1 << 16) + 1, 1))[:nb_wires].copy()
+    g1 = np.concatenate([g1_pts, g1_pts[:2]])
+    pk = g16.ProvingKey.from_arrays(
+        g16.BN254, n, g1[0], g1[1], g1[2], g1[:nb_wires], g1[:nb_wires], g1[:n - 1], g1[:nb_wires - nb_public],
+        g2_small[0], g2_small[1], g2_b, np.zeros(nb_wires, dtype=np.uint8), np.zeros(nb_wires, dtype=np.uint8),
+        nb_public)
+    t0 = time.perf_counter()
+    pk.setup_device_pointers(g16.NewConfig(g16.WithDeviceID(dev)))
+    setup_s = time.perf_counter() - t0
+    sol = g16.R1CSSolution(W=rand_fr(nb_wires), A=rand_fr(n - 1), B=rand_fr(n - 1), C=rand_fr(n - 1))
+    times = []
+    for i in range(6):
+        t0 = time.perf_counter()
+        g16.ProveSolution(pk, sol, g16.WithDeviceID(dev))
+        times.append(1e3 * (time.perf_counter() - t0))
+    pk.free_gpu_resources()
+    return {"metric": "groth16_prove_ms", "n_constraints": n - 1, "curve": "bn254", "n_gpus": 1,
+            "prove_ms_median": float(np.median(times[1:])), "prove_ms_min": float(min(times[1:])),
+            "first_call_ms": times[0], "key_load_s": setup_s,
+            "includes": "H2D of W,A,B,C (4 x 32 MiB, pageable host memory), computeH (7 NTT), 5 MSM, D2H, host assembly",
+            "excludes": "R1CS solver (CPU, out of scope)"}
 
 
 def main():
@@ -319,6 +367,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-groth16", action="store_true", help="skip the secondary Groth16 2^20 prove-time leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
