@@ -230,22 +230,43 @@ def run_b200(args):
         return acc
 
     # ---- device-resident throughput (value) ------------------------------------------
-    for _ in range(max(args.warmup, 3)):
-        table.msm_async(d_sc, d_out, n=n)
-        combine(d_out)
+    # K independent MSMs issued back to back; the latency-bound reduction tail of MSM i overlaps
+    # the sort/accumulate of MSM i+1 (b200_msm_pipelined), results joined before the end event.
+    K = args.steps
+    d_outs = torch.zeros((K, 12), dtype=torch.int64, device="cuda")
+
+    def run_steps(k):
+        for i in range(k):
+            table.msm_pipelined(d_sc, d_outs[i], n=n)
+        table.join()
+        if world == 1:
+            return d_outs[:k]
+        parts = [torch.empty_like(d_outs) for _ in range(world)]
+        dist.all_gather(parts, d_outs)          # one exchange of world x K x 96 B over NVLink
+        return parts
+
+    def fold(parts, i):
+        acc = parts[0][i].cpu().numpy().view(np.uint64).copy()
+        for p in parts[1:]:
+            lib.point_add_jac(lib.BN254, 1, acc, p[i].cpu().numpy().view(np.uint64))
+        return acc
+
+    run_steps(max(args.warmup, 3))
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    for _ in range(args.steps):
-        table.msm_async(d_sc, d_out, n=n)
-        combine(d_out)
+    res = run_steps(K)
+    if world > 1:
+        totals = [fold(res, i) for i in range(K)]   # host-side group adds inside the timed region
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if rank == 0 else None
+    if world == 1:
+        assert jac_to_affine(C, res[K - 1].cpu().numpy().view(np.uint64)) == expected
 
     # ---- end to end through the C ABI with host buffers (e2e) --------------------------
     for _ in range(2):

@@ -45,6 +45,11 @@ int32_t device_ctx(int dev, DeviceCtx** out) {
     CK(cudaSetDevice(dev));
     CK(cudaStreamCreateWithFlags(&c.own_stream, cudaStreamNonBlocking));
     c.stream = c.own_stream;
+    int lo_prio = 0, hi_prio = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));
+    CK(cudaStreamCreateWithPriority(&c.tail_stream, cudaStreamNonBlocking, hi_prio));
+    CK(cudaEventCreateWithFlags(&c.fork_ev, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c.tail_ev, cudaEventDisableTiming));
     cudaMemPool_t pool;
     CK(cudaDeviceGetDefaultMemPool(&pool, dev));
     uint64_t thr = UINT64_MAX;  // keep freed workspace cached in the pool
@@ -82,9 +87,19 @@ void msm_tuning(size_t n, int nwin, int c, uint32_t* task_len, uint32_t* chunk) 
   *chunk = (uint32_t)env_int("GB200_MSM_CHUNK", c >= 12 ? 8 : 4);
 }
 
+int32_t msm_join(DeviceCtx* ctx) {
+  if (ctx->tail_pending) {
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->tail_ev, 0));
+    ctx->tail_pending = false;
+  }
+  return 0;
+}
+
 int32_t msm_on_stream(DeviceCtx* ctx, b200_table_s* t, size_t off, size_t n, const void* d_scalars, void* d_out,
-                      cudaEvent_t* stage_events) {
+                      cudaEvent_t* stage_events, bool pipelined) {
   if (off + n > t->n) return set_error("msm: range [off, off+n) exceeds the table");
+  if (stage_events || n == 0) pipelined = false;
+  if (!pipelined) { int32_t rc = msm_join(ctx); if (rc) return rc; }
   uint32_t task_len, chunk;
   msm_tuning(n, t->nwin, t->c, &task_len, &chunk);
   size_t ws_bytes = 0;
@@ -92,8 +107,15 @@ int32_t msm_on_stream(DeviceCtx* ctx, b200_table_s* t, size_t off, size_t n, con
   void* ws = nullptr;
   CK(cudaMallocAsync(&ws, ws_bytes, ctx->stream));
   cudaError_t e = t->ops->run(ctx->stream, (uint32_t)n, (uint32_t)t->n, (uint32_t)off, t->c, t->precomp, task_len, chunk,
-                              t->d_points, d_scalars, d_out, ws, stage_events);
-  cudaError_t e2 = cudaFreeAsync(ws, ctx->stream);
+                              t->d_points, d_scalars, d_out, ws, stage_events, pipelined ? ctx->tail_stream : nullptr,
+                              ctx->fork_ev);
+  // the workspace is last used by the tail kernels
+  cudaError_t e2 = cudaFreeAsync(ws, pipelined ? ctx->tail_stream : ctx->stream);
+  if (pipelined && e == cudaSuccess) {
+    cudaError_t e3 = cudaEventRecord(ctx->tail_ev, ctx->tail_stream);
+    if (e3 != cudaSuccess) return cuda_fail("cudaEventRecord", e3);
+    ctx->tail_pending = true;
+  }
   if (e != cudaSuccess) return cuda_fail("msm enqueue", e);
   if (e2 != cudaSuccess) return cuda_fail("cudaFreeAsync", e2);
   return 0;
@@ -134,7 +156,11 @@ int32_t b200_shutdown(void) {
     if (!c.ready) continue;
     cudaSetDevice(d);
     cudaStreamSynchronize(c.stream);
+    cudaStreamSynchronize(c.tail_stream);
     cudaStreamDestroy(c.own_stream);
+    cudaStreamDestroy(c.tail_stream);
+    cudaEventDestroy(c.fork_ev);
+    cudaEventDestroy(c.tail_ev);
     c = DeviceCtx();
   }
   return 0;
@@ -152,6 +178,7 @@ int32_t b200_set_stream(int32_t dev, void* stream) {
 int32_t b200_sync(int32_t dev) {
   GUARD_BEGIN
   DeviceCtx* c; int32_t rc = device_ctx(dev, &c); if (rc) return rc;
+  rc = msm_join(c); if (rc) return rc;
   CK(cudaStreamSynchronize(c->stream));
   return 0;
   GUARD_END
@@ -183,6 +210,7 @@ int32_t b200_h2d(int32_t dev, void* dst, const void* src, size_t bytes) {
 int32_t b200_d2h(int32_t dev, void* dst, const void* src, size_t bytes) {
   GUARD_BEGIN
   DeviceCtx* c; int32_t rc = device_ctx(dev, &c); if (rc) return rc;
+  rc = msm_join(c); if (rc) return rc;
   CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   return 0;
@@ -276,6 +304,20 @@ int32_t b200_msm_profile(b200_table_t t, size_t off, size_t n, const void* d_sca
   if (rc) return rc;
   if (e != cudaSuccess) return cuda_fail("msm_profile", e);
   return 0;
+  GUARD_END
+}
+
+int32_t b200_msm_pipelined(b200_table_t t, size_t off, size_t n, const void* d_scalars, void* d_out) {
+  GUARD_BEGIN
+  if (!t) return set_error("msm: null table");
+  DeviceCtx* ctx; int32_t rc = device_ctx(t->dev, &ctx); if (rc) return rc;
+  return msm_on_stream(ctx, t, off, n, d_scalars, d_out, nullptr, true);
+  GUARD_END
+}
+int32_t b200_msm_join(int32_t dev) {
+  GUARD_BEGIN
+  DeviceCtx* ctx; int32_t rc = device_ctx(dev, &ctx); if (rc) return rc;
+  return msm_join(ctx);
   GUARD_END
 }
 

@@ -23,6 +23,11 @@ struct DeviceCtx {
   int dev = 0;
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;  // own_stream or the caller's (b200_set_stream)
+  // pipelined MSMs: reduction tail of MSM i runs here while MSM i+1 sorts/accumulates on `stream`
+  cudaStream_t tail_stream = nullptr;
+  cudaEvent_t fork_ev = nullptr;   // accumulate done (recorded on stream)
+  cudaEvent_t tail_ev = nullptr;   // tail done (recorded on tail_stream)
+  bool tail_pending = false;
 };
 
 int32_t set_error(const std::string& msg);
@@ -50,7 +55,8 @@ struct b200_domain_s {
 
 namespace gb200 {
 int32_t msm_on_stream(DeviceCtx* ctx, b200_table_s* t, size_t off, size_t n, const void* d_scalars, void* d_out,
-                      cudaEvent_t* stage_events = nullptr);
+                      cudaEvent_t* stage_events = nullptr, bool pipelined = false);
+int32_t msm_join(DeviceCtx* ctx);  // make ctx->stream wait for the pipelined tails
 }
 
 #define CK(x)                                                        \

@@ -154,11 +154,12 @@ int32_t b200_groth16_prove(b200_pk_t pk, const void* wires, const void* a, const
   CK(pk->fr->gather(st, d_wb, d_w, pk->d_idx_b, pk->n_b));
   // the five MSMs - prove.go:207 (Ar), :194 (Bs1), :227 (Krs2 over h), :237 (Krs), :283 (Bs2)
   char* res = reinterpret_cast<char*>(d_res);
-  rc = msm_on_stream(ctx, pk->A, 0, pk->n_a, d_wa, res + 0 * j1); if (rc) return rc;
-  rc = msm_on_stream(ctx, pk->B1, 0, pk->n_b, d_wb, res + 1 * j1); if (rc) return rc;
-  rc = msm_on_stream(ctx, pk->Z, 0, n - 1, d_a, res + 2 * j1); if (rc) return rc;
-  rc = msm_on_stream(ctx, pk->K, 0, pk->nb_wires - pk->nb_public, (char*)d_w + pk->nb_public * fb, res + 3 * j1); if (rc) return rc;
-  rc = msm_on_stream(ctx, pk->B2, 0, pk->n_b, d_wb, res + 4 * j1); if (rc) return rc;
+  rc = msm_on_stream(ctx, pk->A, 0, pk->n_a, d_wa, res + 0 * j1, nullptr, true); if (rc) return rc;
+  rc = msm_on_stream(ctx, pk->B1, 0, pk->n_b, d_wb, res + 1 * j1, nullptr, true); if (rc) return rc;
+  rc = msm_on_stream(ctx, pk->Z, 0, n - 1, d_a, res + 2 * j1, nullptr, true); if (rc) return rc;
+  rc = msm_on_stream(ctx, pk->K, 0, pk->nb_wires - pk->nb_public, (char*)d_w + pk->nb_public * fb, res + 3 * j1, nullptr, true); if (rc) return rc;
+  rc = msm_on_stream(ctx, pk->B2, 0, pk->n_b, d_wb, res + 4 * j1, nullptr, true); if (rc) return rc;
+  rc = msm_join(ctx); if (rc) return rc;
   std::vector<uint8_t> host(4 * j1 + j2);
   CK(cudaMemcpyAsync(host.data(), d_res, host.size(), cudaMemcpyDeviceToHost, st));
 

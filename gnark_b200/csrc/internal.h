@@ -19,7 +19,8 @@ struct MsmOps {
   // enqueue a full MSM (all pointers on device)
   cudaError_t (*run)(cudaStream_t st, uint32_t n, uint32_t stride, uint32_t off, int c, int precomp,
                      uint32_t task_len, uint32_t chunk, const void* d_table, const void* d_scalars, void* d_out_jac,
-                     void* ws, cudaEvent_t* stage_events /* nullable, 8 entries */);
+                     void* ws, cudaEvent_t* stage_events /* nullable, 8 entries */,
+                     cudaStream_t tail /* nullable */, cudaEvent_t fork_ev);
   // fill slabs 1..nwin-1 of a [nwin][n] table whose slab 0 holds the bases
   cudaError_t (*precompute)(cudaStream_t st, uint32_t n, int nwin, int c, void* d_table);
 };

@@ -205,7 +205,11 @@ inline int msm_set_sum_threads(size_t budget = 160 * 1024) {
 // d_out: one Jacobian<F> on device.  ws must hold msm_layout().total bytes.
 template <class Fr, class F>
 cudaError_t msm_enqueue(cudaStream_t stream, const MsmPlan& pl, const Affine<F>* d_table, const Fr* d_scalars,
-                        Jacobian<F>* d_out, void* ws, const MsmLayout<F>& L, cudaEvent_t* ev = nullptr) {
+                        Jacobian<F>* d_out, void* ws, const MsmLayout<F>& L, cudaEvent_t* ev = nullptr,
+                        cudaStream_t tail = nullptr, cudaEvent_t fork_ev = nullptr) {
+  // tail (optional): the latency-bound reduction kernels that follow the accumulate kernel are
+  // enqueued on this second stream (forked with fork_ev), so that in a pipeline of MSMs they
+  // overlap the next MSM's sort/accumulate instead of idling 140+ SMs.
   // ev (optional, MSM_NUM_EVENTS entries): stage boundaries for the step profile
   // (the reference's ICICLE_STEP_PROFILE timers, icicle.go:72-75,1088-1094)
 #define GB_EV(k) do { if (ev) GB_CUDA_TRY(cudaEventRecord(ev[k], stream)); } while (0)
@@ -246,6 +250,11 @@ cudaError_t msm_enqueue(cudaStream_t stream, const MsmPlan& pl, const Affine<F>*
   k_msm_accumulate<F><<<(unsigned)((L.max_tasks + 127) / 128), 128, 0, stream>>>(pl, d_table, vals1, off, task_off,
                                                                                  partial);
   GB_EV(4);
+  if (tail) {
+    GB_CUDA_TRY(cudaEventRecord(fork_ev, stream));
+    GB_CUDA_TRY(cudaStreamWaitEvent(tail, fork_ev, 0));
+    stream = tail;
+  }
   k_msm_combine<F><<<(nb + 127) / 128, 128, 0, stream>>>(pl, task_off, partial, buckets);
   GB_EV(5);
   const uint32_t nchunks = L.chunks_per_set * (uint32_t)pl.nsets;

@@ -27,7 +27,7 @@ EXPORTS = [
     "b200_version", "b200_last_error", "b200_device_count", "b200_init", "b200_shutdown", "b200_set_stream",
     "b200_sync", "b200_alloc", "b200_free", "b200_h2d", "b200_d2h", "b200_host_alloc", "b200_host_free",
     "b200_table_upload", "b200_table_free", "b200_table_info", "b200_msm", "b200_msm_g1", "b200_msm_g2",
-    "b200_msm_async", "b200_msm_profile", "b200_ntt_domain_new", "b200_ntt_domain_free", "b200_ntt", "b200_ntt_async",
+    "b200_msm_async", "b200_msm_pipelined", "b200_msm_join", "b200_msm_profile", "b200_ntt_domain_new", "b200_ntt_domain_free", "b200_ntt", "b200_ntt_async",
     "b200_groth16_compute_h", "b200_vec_op", "b200_vec_bit_reverse", "b200_vec_scale_powers",
     "b200_point_add_jac", "b200_point_to_affine", "b200_groth16_pk_load", "b200_groth16_pk_free", "b200_groth16_prove",
 ]
@@ -99,6 +99,8 @@ def load(path: str = None):
     for n in ("b200_msm", "b200_msm_g1", "b200_msm_g2"):
         getattr(lib, n).argtypes = [vp, sz, sz, vp, i32, vp]
     lib.b200_msm_async.argtypes = [vp, sz, sz, vp, vp]
+    lib.b200_msm_pipelined.argtypes = [vp, sz, sz, vp, vp]
+    lib.b200_msm_join.argtypes = [i32]
     lib.b200_msm_profile.argtypes = [vp, sz, sz, vp, vp, ctypes.POINTER(ctypes.c_float)]
     lib.b200_ntt_domain_new.argtypes = [i32, i32, u32, vp, vp, ctypes.POINTER(vp)]
     lib.b200_ntt_domain_free.argtypes = [vp]
@@ -194,6 +196,13 @@ class Table:
 
     def msm_async(self, d_scalars, d_out, off: int = 0, n: int = None):
         check(load().b200_msm_async(self.handle, off, n, ptr(d_scalars), ptr(d_out)))
+
+    def msm_pipelined(self, d_scalars, d_out, off: int = 0, n: int = None):
+        """stream-ordered, tail overlapped with the next call; results valid after join()."""
+        check(load().b200_msm_pipelined(self.handle, off, n, ptr(d_scalars), ptr(d_out)))
+
+    def join(self):
+        check(load().b200_msm_join(self.dev))
 
     MSM_STAGES = ("decompose", "sort", "offsets_scan", "accumulate", "combine", "reduce_chunks", "set_sum_finish")
 

@@ -92,6 +92,13 @@ int32_t b200_msm_g2(b200_table_t bases, size_t off, size_t n, const void* scalar
 /* stream-ordered variant: all pointers on device, no synchronisation */
 int32_t b200_msm_async(b200_table_t bases, size_t off, size_t n, const void* d_scalars_mont, void* d_out_jac);
 
+/* pipelined variant: as b200_msm_async, but the reduction tail of this MSM is placed on a second
+ * stream so it overlaps the NEXT b200_msm_pipelined call (a Groth16 proof issues five MSMs back
+ * to back; the reference overlaps its four G1 MSMs on CPU cores, prove.go:296-304).  d_out_jac is
+ * valid on the device stream only after b200_msm_join (or b200_sync). */
+int32_t b200_msm_pipelined(b200_table_t bases, size_t off, size_t n, const void* d_scalars_mont, void* d_out_jac);
+int32_t b200_msm_join(int32_t dev);
+
 /* step profile (the reference's ICICLE_STEP_PROFILE timers, icicle.go:72-75,1088-1094):
  * device milliseconds of the 7 pipeline stages of one MSM - decompose, sort,
  * offsets+task scan, accumulate, combine, reduce chunks, set sum+finish. */
