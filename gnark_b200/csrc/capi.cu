@@ -478,4 +478,37 @@ int32_t b200_vec_scale_powers(int32_t dev, int32_t curve, void* data, size_t n, 
   GUARD_END
 }
 
+int32_t b200_vec_batch_invert(int32_t dev, int32_t curve, void* data, size_t n) {
+  GUARD_BEGIN
+  DeviceCtx* ctx; int32_t rc = device_ctx(dev, &ctx); if (rc) return rc;
+  const NttOps* ops = get_ntt_ops(curve);
+  if (!ops) return set_error("vec_batch_invert: unsupported curve");
+  CK(ops->batch_invert(ctx->stream, data, n));
+  return 0;
+  GUARD_END
+}
+
+// ---- PLONK ------------------------------------------------------------------------
+int32_t b200_plonk_constraints_coset(b200_domain_t d0, const void* big_coset_gen, const void* big_gen,
+                                     const b200_plonk_coset_args* args) {
+  GUARD_BEGIN
+  if (!d0 || !big_coset_gen || !big_gen || !args) return set_error("plonk_constraints_coset: null argument");
+  DeviceCtx* ctx; int32_t rc = device_ctx(d0->dev, &ctx); if (rc) return rc;
+  cudaError_t e = d0->ops->plonk_coset(ctx->stream, d0->impl, big_coset_gen, big_gen, args);
+  if (e == cudaErrorInvalidValue) return set_error("plonk_constraints_coset: invalid rho / coset index / blinding length");
+  if (e != cudaSuccess) return cuda_fail("plonk_constraints_coset", e);
+  return 0;
+  GUARD_END
+}
+int32_t b200_plonk_divide_by_zh(b200_domain_t d1, uint32_t log_n0, void* d_data) {
+  GUARD_BEGIN
+  if (!d1 || !d_data) return set_error("plonk_divide_by_zh: null argument");
+  DeviceCtx* ctx; int32_t rc = device_ctx(d1->dev, &ctx); if (rc) return rc;
+  cudaError_t e = d1->ops->plonk_divide_by_zh(ctx->stream, d1->impl, log_n0, d_data);
+  if (e == cudaErrorInvalidValue) return set_error("plonk_divide_by_zh: invalid domain ratio");
+  if (e != cudaSuccess) return cuda_fail("plonk_divide_by_zh", e);
+  return 0;
+  GUARD_END
+}
+
 }  // extern "C"

@@ -5,6 +5,8 @@
 #include "internal.h"
 #include "msm_impl.cuh"
 #include "ntt_impl.cuh"
+#include "plonk.cuh"
+#include "../../include/gnark_b200.h"
 
 namespace gb200 {
 
@@ -124,6 +126,70 @@ struct NttInst {
     GB_CUDA_TRY(cudaFreeAsync(d_pw, st));
     return cudaStreamSynchronize(st);
   }
+  static cudaError_t batch_invert(cudaStream_t st, void* d, size_t n) {
+    if (!n) return cudaSuccess;
+    const size_t threads = (n + BI_CHUNK - 1) / BI_CHUNK;
+    k_batch_invert<Fr><<<(unsigned)((threads + 127) / 128), 128, 0, st>>>((Fr*)d, n);
+    return cudaGetLastError();
+  }
+  static cudaError_t plonk_coset(cudaStream_t st, void* dom0, const void* big_coset_gen, const void* big_gen,
+                                 const void* args_) {
+    const Dom& d = *reinterpret_cast<Dom*>(dom0);
+    const b200_plonk_coset_args& c = *reinterpret_cast<const b200_plonk_coset_args*>(args_);
+    PlonkCosetArgs<Fr> a;
+    a.l = (const Fr*)c.l; a.r = (const Fr*)c.r; a.o = (const Fr*)c.o; a.z = (const Fr*)c.z;
+    a.s1 = (const Fr*)c.s1; a.s2 = (const Fr*)c.s2; a.s3 = (const Fr*)c.s3;
+    a.ql = (const Fr*)c.ql; a.qr = (const Fr*)c.qr; a.qm = (const Fr*)c.qm; a.qo = (const Fr*)c.qo; a.qk = (const Fr*)c.qk;
+    a.tw = d.tw; a.out = (Fr*)c.out;
+    a.alpha = *(const Fr*)c.alpha; a.beta = *(const Fr*)c.beta; a.gamma = *(const Fr*)c.gamma;
+    const Fr g = *(const Fr*)big_coset_gen, w4 = *(const Fr*)big_gen;
+    Fr coset = g;
+    for (uint32_t k = 0; k < c.coset_index; k++) coset = coset * w4;   // shifters (:943-948)
+    a.coset = coset; a.cs = g; a.css = g.sqr();
+    Fr cn = coset;
+    for (int k = 0; k < d.logn; k++) cn = cn.sqr();
+    a.coset_n_minus_one = cn - Fr::one();
+    a.lone_scale = a.coset_n_minus_one * d.ninv;
+    const void* bsrc[4] = {c.bl, c.br, c.bo, c.bz};
+    const int bn[4] = {c.nbl, c.nbr, c.nbo, c.nbz};
+    Fr* bdst[4] = {a.bl, a.br, a.bo, a.bz};
+    for (int q = 0; q < 4; q++) {
+      if (bn[q] < 0 || bn[q] > PLONK_MAX_BLIND) return cudaErrorInvalidValue;
+      for (int k = 0; k < PLONK_MAX_BLIND; k++) bdst[q][k] = k < bn[q] ? ((const Fr*)bsrc[q])[k] : Fr::zero();
+    }
+    a.nbl = c.nbl; a.nbr = c.nbr; a.nbo = c.nbo; a.nbz = c.nbz;
+    a.n = d.n; a.logn = (uint32_t)d.logn; a.rho = c.rho; a.coset_index = c.coset_index;
+    a.log_rho = 0;
+    while ((1u << a.log_rho) < c.rho) a.log_rho++;
+    if ((1u << a.log_rho) != c.rho || c.coset_index >= c.rho) return cudaErrorInvalidValue;
+    Fr* den = nullptr;
+    GB_CUDA_TRY(cudaMallocAsync(&den, (size_t)d.n * sizeof(Fr), st));
+    k_plonk_denominators<Fr><<<(d.n + 255) / 256, 256, 0, st>>>(den, d.n, d.tw, coset);
+    GB_CUDA_TRY(batch_invert(st, den, d.n));
+    a.den_inv = den;
+    k_plonk_constraints<Fr><<<(d.n + 255) / 256, 256, 0, st>>>(a);
+    GB_CUDA_TRY(cudaGetLastError());
+    return cudaFreeAsync(den, st);
+  }
+  static cudaError_t plonk_divide_by_zh(cudaStream_t st, void* dom1, uint32_t log_n0, void* data) {
+    const Dom& d = *reinterpret_cast<Dom*>(dom1);
+    if ((int)log_n0 > d.logn || d.logn - (int)log_n0 > 6) return cudaErrorInvalidValue;
+    const uint32_t rho = 1u << (d.logn - (int)log_n0);
+    // evaluateXnMinusOneDomainBigCoset (:1327-1350): 1 / (g^n * (w^n)^i - 1), i < rho
+    Fr tab[64];
+    Fr gn = d.coset, wn = d.gen;
+    for (uint32_t k = 0; k < log_n0; k++) { gn = gn.sqr(); wn = wn.sqr(); }
+    Fr cur = gn;
+    for (uint32_t i = 0; i < rho; i++) { tab[i] = (cur - Fr::one()).inverse(); cur = cur * wn; }
+    Fr* d_tab = nullptr;
+    GB_CUDA_TRY(cudaMallocAsync(&d_tab, sizeof(tab), st));
+    GB_CUDA_TRY(cudaMemcpyAsync(d_tab, tab, sizeof(Fr) * rho, cudaMemcpyHostToDevice, st));
+    k_plonk_zh_scale<Fr><<<(d.n + 255) / 256, 256, 0, st>>>((Fr*)data, (uint32_t)d.logn, rho, d_tab);
+    GB_CUDA_TRY(cudaGetLastError());
+    GB_CUDA_TRY(ntt_enqueue<Fr>(st, d, (Fr*)data, true, NTT_DIT, true));
+    GB_CUDA_TRY(cudaFreeAsync(d_tab, st));
+    return cudaStreamSynchronize(st);  // tab is a stack buffer
+  }
   static cudaError_t gather(cudaStream_t st, void* out, const void* src, const uint32_t* idx, size_t n) {
     if (!n) return cudaSuccess;
     k_gather<Fr><<<(unsigned)((n + 255) / 256), 256, 0, st>>>((Fr*)out, (const Fr*)src, idx, n);
@@ -131,7 +197,8 @@ struct NttInst {
   }
   static const NttOps* ops() {
     static const NttOps o = {sizeof(Fr), Fr::Params::TWO_ADICITY, &domain_new, &domain_free, &domain_bytes, &ntt,
-                             &compute_h, &vec_op, &bit_reverse, &scale_powers, &gather};
+                             &compute_h, &vec_op, &bit_reverse, &scale_powers, &batch_invert, &plonk_coset,
+                             &plonk_divide_by_zh, &gather};
     return &o;
   }
 };

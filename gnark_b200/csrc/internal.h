@@ -36,6 +36,11 @@ struct NttOps {
   cudaError_t (*vec_op)(cudaStream_t st, int op, void* d_out, const void* d_a, const void* d_b, size_t n);
   cudaError_t (*bit_reverse)(cudaStream_t st, void* d_data, uint32_t logn);
   cudaError_t (*scale_powers)(cudaStream_t st, void* d_data, size_t n, const void* s_mont, const void* g_mont);
+  cudaError_t (*batch_invert)(cudaStream_t st, void* d_data, size_t n);
+  // PLONK (see plonk.cuh); `args` is a const b200_plonk_coset_args*
+  cudaError_t (*plonk_coset)(cudaStream_t st, void* dom0, const void* big_coset_gen, const void* big_gen,
+                             const void* args);
+  cudaError_t (*plonk_divide_by_zh)(cudaStream_t st, void* dom1, uint32_t log_n0, void* d_data);
   // out[j] = src[idx[j]] (wire filtering, backend/groth16/bn254/prove.go:147-168)
   cudaError_t (*gather)(cudaStream_t st, void* d_out, const void* d_src, const uint32_t* d_idx, size_t n);
 };

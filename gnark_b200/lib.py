@@ -29,6 +29,7 @@ EXPORTS = [
     "b200_table_upload", "b200_table_free", "b200_table_info", "b200_msm", "b200_msm_g1", "b200_msm_g2",
     "b200_msm_async", "b200_msm_pipelined", "b200_msm_join", "b200_msm_profile", "b200_ntt_domain_new", "b200_ntt_domain_free", "b200_ntt", "b200_ntt_async",
     "b200_groth16_compute_h", "b200_vec_op", "b200_vec_bit_reverse", "b200_vec_scale_powers",
+    "b200_vec_batch_invert", "b200_plonk_constraints_coset", "b200_plonk_divide_by_zh",
     "b200_point_add_jac", "b200_point_to_affine", "b200_groth16_pk_load", "b200_groth16_pk_free", "b200_groth16_prove",
 ]
 
@@ -110,6 +111,9 @@ def load(path: str = None):
     lib.b200_vec_op.argtypes = [i32, i32, i32, vp, vp, vp, sz]
     lib.b200_vec_bit_reverse.argtypes = [i32, i32, vp, u32]
     lib.b200_vec_scale_powers.argtypes = [i32, i32, vp, sz, vp, vp]
+    lib.b200_vec_batch_invert.argtypes = [i32, i32, vp, sz]
+    lib.b200_plonk_constraints_coset.argtypes = [vp, vp, vp, vp]
+    lib.b200_plonk_divide_by_zh.argtypes = [vp, u32, vp]
     lib.b200_point_add_jac.argtypes = [i32, i32, vp, vp]
     lib.b200_point_to_affine.argtypes = [i32, i32, vp, vp]
     lib.b200_groth16_pk_load.argtypes = [i32, ctypes.POINTER(Groth16PkDesc), ctypes.POINTER(vp)]
@@ -273,3 +277,54 @@ def point_to_affine(curve: int, group: int, p: np.ndarray) -> np.ndarray:
     out = np.zeros(p.size // 3 * 2, dtype=np.uint64)
     check(load().b200_point_to_affine(curve, group, ptr(p), ptr(out)))
     return out
+
+
+# ---- vector ops / PLONK building blocks ----------------------------------------------------------
+def vec_op(dev, curve, op, d_out, d_a, d_b, n):
+    check(load().b200_vec_op(dev, curve, op, ptr(d_out), ptr(d_a), ptr(d_b), n))
+
+
+def vec_bit_reverse(dev, curve, d_data, log2n):
+    check(load().b200_vec_bit_reverse(dev, curve, ptr(d_data), log2n))
+
+
+def vec_scale_powers(dev, curve, d_data, n, s_mont, g_mont):
+    check(load().b200_vec_scale_powers(dev, curve, ptr(d_data), n, ptr(s_mont), ptr(g_mont)))
+
+
+def vec_batch_invert(dev, curve, d_data, n):
+    check(load().b200_vec_batch_invert(dev, curve, ptr(d_data), n))
+
+
+class PlonkCosetArgs(ctypes.Structure):
+    _fields_ = ([(k, ctypes.c_void_p) for k in ("l", "r", "o", "z", "s1", "s2", "s3", "ql", "qr", "qm", "qo", "qk",
+                                                "alpha", "beta", "gamma", "bl", "br", "bo", "bz")]
+                + [(k, ctypes.c_int32) for k in ("nbl", "nbr", "nbo", "nbz")]
+                + [("coset_index", ctypes.c_uint32), ("rho", ctypes.c_uint32), ("out", ctypes.c_void_p)])
+
+
+def plonk_constraints_coset(domain0: "Domain", big_coset_gen, big_gen, polys: dict, alpha, beta, gamma, blind: dict,
+                            coset_index: int, rho: int, d_out):
+    """polys: name -> device tensor (n fr.Elements on the current coset); blind: name -> host array or None."""
+    a = PlonkCosetArgs()
+    keep = []
+    for k in ("l", "r", "o", "z", "s1", "s2", "s3", "ql", "qr", "qm", "qo", "qk"):
+        setattr(a, k, ptr(polys[k]).value)
+    for k, v in (("alpha", alpha), ("beta", beta), ("gamma", gamma)):
+        setattr(a, k, ptr(v).value)
+    frl = domain0.fr_limbs
+    for k in ("l", "r", "o", "z"):
+        b = blind.get(k)
+        if b is None or b.size == 0:
+            setattr(a, "b" + k, None)
+            setattr(a, "nb" + k, 0)
+        else:
+            keep.append(b)
+            setattr(a, "b" + k, ptr(b).value)
+            setattr(a, "nb" + k, b.size // frl)
+    a.coset_index, a.rho, a.out = coset_index, rho, ptr(d_out).value
+    check(load().b200_plonk_constraints_coset(domain0.handle, ptr(big_coset_gen), ptr(big_gen), ctypes.byref(a)))
+
+
+def plonk_divide_by_zh(domain1: "Domain", domain0_log2n: int, d_data):
+    check(load().b200_plonk_divide_by_zh(domain1.handle, domain0_log2n, ptr(d_data)))

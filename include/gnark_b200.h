@@ -143,6 +143,30 @@ int32_t b200_vec_bit_reverse(int32_t dev, int32_t curve, void* d_data, uint32_t 
 int32_t b200_vec_scale_powers(int32_t dev, int32_t curve, void* d_data, size_t n, const void* s_mont,
                               const void* g_mont);
 
+int32_t b200_vec_batch_invert(int32_t dev, int32_t curve, void* d_data, size_t n); /* 0 stays 0 */
+
+/* ---- PLONK quotient building blocks (no accelerated PLONK exists in the reference; these are
+ *      the device twins of backend/plonk/bn254/prove.go computeNumerator :841-1123 and
+ *      divideByZH :1287-1324).  One call evaluates gate + alpha*permutation + alpha^2*L1
+ *      constraints on ONE coset of the small domain and scatters the n values into the
+ *      bit-reversed rho*n result vector (cres[bitrev(rho*j+i)], :1070-1076).
+ *      Inputs are the 12 polynomials already evaluated on that coset (iFFT-DIF, then FFT-DIT
+ *      on the coset through b200_ntt with the matching coset generator, as :1035-1057). */
+typedef struct {
+  const void *l, *r, *o, *z, *s1, *s2, *s3, *ql, *qr, *qm, *qo, *qk; /* device, n fr.Elements each */
+  const void *alpha, *beta, *gamma;                                  /* host, one fr.Element each */
+  const void *bl, *br, *bo, *bz;                                     /* host, blinding poly coeffs */
+  int32_t nbl, nbr, nbo, nbz;                                        /* their lengths (<= 4)       */
+  uint32_t coset_index;                                              /* i in [0, rho)              */
+  uint32_t rho;                                                      /* |domain1| / |domain0|      */
+  void* out;                                                         /* device, rho*n elements     */
+} b200_plonk_coset_args;
+int32_t b200_plonk_constraints_coset(b200_domain_t domain0, const void* domain1_coset_gen_mont,
+                                     const void* domain1_gen_mont, const b200_plonk_coset_args* args);
+/* r[i] *= 1/(X^n-1) on the big coset (indexing rule of :1312-1317), then
+ * FFTInverse(DIT, OnCoset) on domain1: LagrangeCoset/BitReverse -> Canonical/Regular, in place. */
+int32_t b200_plonk_divide_by_zh(b200_domain_t domain1, uint32_t domain0_log2n, void* d_data);
+
 /* ---- Groth16 prover (host layer mirroring backend/accelerated/icicle/groth16/
  *      bn254/icicle.go:784-1360 Prove + setupDevicePointers :88-264) ------------
  * Builds the device-resident key from the gnark ProvingKey fields

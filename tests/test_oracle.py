@@ -113,3 +113,40 @@ def test_filter_semantics():
     elems = [1, 2, 3, 4, 5, 6, 7, 8, 9, 10]
     assert filter_heap(elems, 2, [2, 3, 5]) == [3, 5, 6, 7, 8, 9, 10]   # indices 2,3,5 -> drop 1,2,4
     assert filter_heap(elems, 0, []) == elems
+
+
+def test_plonk_quotient_identity():
+    """A satisfying trace (sigma = identity => Z = 1) makes the numerator vanish on H, so the
+    quotient h from numerator/divide_by_zh satisfies h(x)(x^n - 1) = N(x) at a random point
+    (independent of the coset machinery)."""
+    from oracle import plonk
+    c = CURVES["bn254"]
+    r = c.r
+    n, rho = 8, 4
+    rng = random.Random(12)
+    dom0 = ntt.Domain(c, n)
+    dom1 = ntt.Domain(c, rho * n)
+    g = dom1.coset_gen
+    w = [pow(dom0.generator, j, r) for j in range(n)]
+    l = [rng.randrange(r) for _ in range(n)]
+    rr = [rng.randrange(r) for _ in range(n)]
+    qm = [rng.randrange(r) for _ in range(n)]
+    ql = [rng.randrange(r) for _ in range(n)]
+    qr = [rng.randrange(r) for _ in range(n)]
+    qk = [rng.randrange(r) for _ in range(n)]
+    qo = [r - 1] * n
+    o = [(ql[j] * l[j] + qr[j] * rr[j] + qm[j] * l[j] * rr[j] + qk[j]) % r for j in range(n)]   # gate holds
+    polys = {"l": l, "r": rr, "o": o, "z": [1] * n, "ql": ql, "qr": qr, "qm": qm, "qo": qo, "qk": qk,
+             "s1": w, "s2": [g * x % r for x in w], "s3": [g * g * x % r for x in w]}
+    alpha, beta, gamma = (rng.randrange(r) for _ in range(3))
+    cres = plonk.numerator(c, n, rho, polys, alpha, beta, gamma, {})
+    h = plonk.divide_by_zh(c, n, rho, cres)
+    assert all(v == 0 for v in h[3 * n:])                       # deg h < 3n
+    # independent evaluation of the numerator at a random point
+    x = rng.randrange(r)
+    can = {k: ntt.bit_reverse(dom0.fft_inverse(v, ntt.DIF)) for k, v in polys.items()}
+    u = {k: ntt.poly_eval(r, can[k], x) for k in plonk.POLYS}
+    u["zs"] = ntt.poly_eval(r, can["z"], x * dom0.generator % r)
+    N = plonk.all_constraints(r, n, dom0.cardinality_inv, u, x, x * dom0.generator % r, alpha, beta, gamma, g, {},
+                              (pow(x, n, r) - 1) % r)
+    assert ntt.poly_eval(r, h, x) * (pow(x, n, r) - 1) % r == N
