@@ -5,6 +5,9 @@
 // The R1CS solver (constraint/bn254/solver.go) stays in Go and is out of scope.
 #include "capi_common.h"
 
+#include <chrono>
+#include <cstdio>
+
 using namespace gb200;
 
 struct b200_pk_s {
@@ -16,7 +19,9 @@ struct b200_pk_s {
   std::vector<uint8_t> alpha, beta, delta, beta2, delta2;
   uint32_t* d_idx_a = nullptr;
   uint32_t* d_idx_b = nullptr;
-  size_t n_a = 0, n_b = 0, nb_wires = 0, nb_public = 0;
+  size_t n_a = 0, n_b = 0, nb_wires = 0, nb_public = 0;   // n_a/n_b: THIS shard's counts
+  size_t off_z = 0, cnt_z = 0, off_k = 0, cnt_k = 0;       // this shard's slice of Z and K
+  int shard_rank = 0, shard_world = 1;
   const HostGroupOps* h1 = nullptr;
   const HostGroupOps* h2 = nullptr;
   const NttOps* fr = nullptr;
@@ -79,15 +84,34 @@ int32_t b200_groth16_pk_load(int32_t dev, const b200_groth16_pk_desc* d, b200_pk
     if (!d->infinity_b[i]) ib.push_back((uint32_t)i);
   }
   if (ia.size() != d->n_a || ib.size() != d->n_b) return set_error("pk_load: infinity flags inconsistent with len(G1.A)/len(G1.B)");
-  pk->n_a = ia.size(); pk->n_b = ib.size();
+  // point-range sharding: contiguous, balanced slices of every table
+  const int world = d->shard_world > 1 ? d->shard_world : 1;
+  const int rank = world > 1 ? d->shard_rank : 0;
+  if (rank < 0 || rank >= world) return set_error("pk_load: shard_rank out of range");
+  pk->shard_rank = rank; pk->shard_world = world;
+  auto shard = [&](size_t n, size_t* off, size_t* cnt) {
+    const size_t base = n / world, rem = n % world;
+    *cnt = base + ((size_t)rank < rem ? 1 : 0);
+    *off = (size_t)rank * base + ((size_t)rank < rem ? (size_t)rank : rem);
+  };
+  size_t off_a, cnt_a, off_b, cnt_b;
+  shard(d->n_a, &off_a, &cnt_a);
+  shard(d->n_b, &off_b, &cnt_b);
+  shard(d->n_z, &pk->off_z, &pk->cnt_z);
+  shard(d->n_k, &pk->off_k, &pk->cnt_k);
+  ia = std::vector<uint32_t>(ia.begin() + off_a, ia.begin() + off_a + cnt_a);
+  ib = std::vector<uint32_t>(ib.begin() + off_b, ib.begin() + off_b + cnt_b);
+  pk->n_a = cnt_a; pk->n_b = cnt_b;
+  const size_t ab1 = h1->affine_bytes, ab2 = h2->affine_bytes;
+  auto at = [](const void* p, size_t bytes) { return (const void*)((const char*)p + bytes); };
   b200_pk_t raw = pk.get();
 #define PK_TRY(x) do { int32_t rc_ = (x); if (rc_) { std::string m = b200_last_error(); b200_groth16_pk_free(pk.release()); set_error(m); return rc_; } } while (0)
   PK_TRY(b200_ntt_domain_new(dev, d->curve, (uint32_t)pk->logn, d->domain_gen, d->coset_gen, &raw->dom));
-  PK_TRY(b200_table_upload(dev, d->curve, 1, d->g1_a, d->n_a, d->flags, &raw->A));
-  PK_TRY(b200_table_upload(dev, d->curve, 1, d->g1_b, d->n_b, d->flags, &raw->B1));
-  PK_TRY(b200_table_upload(dev, d->curve, 1, d->g1_z, d->n_z, d->flags, &raw->Z));
-  PK_TRY(b200_table_upload(dev, d->curve, 1, d->g1_k, d->n_k, d->flags, &raw->K));
-  PK_TRY(b200_table_upload(dev, d->curve, 2, d->g2_b, d->n_b2, d->flags, &raw->B2));
+  PK_TRY(b200_table_upload(dev, d->curve, 1, at(d->g1_a, off_a * ab1), cnt_a, d->flags, &raw->A));
+  PK_TRY(b200_table_upload(dev, d->curve, 1, at(d->g1_b, off_b * ab1), cnt_b, d->flags, &raw->B1));
+  PK_TRY(b200_table_upload(dev, d->curve, 1, at(d->g1_z, pk->off_z * ab1), pk->cnt_z, d->flags, &raw->Z));
+  PK_TRY(b200_table_upload(dev, d->curve, 1, at(d->g1_k, pk->off_k * ab1), pk->cnt_k, d->flags, &raw->K));
+  PK_TRY(b200_table_upload(dev, d->curve, 2, at(d->g2_b, off_b * ab2), cnt_b, d->flags, &raw->B2));
   auto up = [&](const std::vector<uint32_t>& v, uint32_t** dptr) -> int32_t {
     CK(cudaMalloc(dptr, (v.size() ? v.size() : 1) * sizeof(uint32_t)));
     if (!v.empty()) CK(cudaMemcpy(*dptr, v.data(), v.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
@@ -114,12 +138,16 @@ int32_t b200_groth16_pk_free(b200_pk_t pk) {
   GUARD_END
 }
 
-int32_t b200_groth16_prove(b200_pk_t pk, const void* wires, const void* a, const void* b, const void* c,
-                           size_t n_constraints, const void* r, const void* s, void* ar_out, void* bs_out,
-                           void* krs_out, void* msm_out) {
+static double now_ms() {
+  using namespace std::chrono;
+  return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+int32_t b200_groth16_msms(b200_pk_t pk, const void* wires, const void* a, const void* b, const void* c,
+                          size_t n_constraints, void* msm_out) {
   GUARD_BEGIN
   if (!pk) return set_error("prove: null proving key");
-  if (!wires || !a || !b || !c || !r || !s || !ar_out || !bs_out || !krs_out) return set_error("prove: null argument");
+  if (!wires || !a || !b || !c || !msm_out) return set_error("prove: null argument");
   if (n_constraints > pk->n) return set_error("prove: more constraints than the domain holds");
   std::lock_guard<std::mutex> lk(pk->mu);
   DeviceCtx* ctx; int32_t rc = device_ctx(pk->dev, &ctx); if (rc) return rc;
@@ -127,6 +155,18 @@ int32_t b200_groth16_prove(b200_pk_t pk, const void* wires, const void* a, const
   const size_t fb = pk->fr->fr_bytes;
   const size_t n = pk->n;
   const size_t j1 = pk->h1->jac_bytes, j2 = pk->h2->jac_bytes;
+  // step profile, the twin of the reference's ICICLE_STEP_PROFILE (icicle.go:72-75): serialises the stages
+  const bool profile = getenv("GB200_STEP_PROFILE") != nullptr;
+  double t_prev = now_ms();
+  auto lap = [&](const char* what) -> int32_t {
+    if (!profile) return 0;
+    int32_t r_ = msm_join(ctx); if (r_) return r_;
+    CK(cudaStreamSynchronize(st));
+    const double t = now_ms();
+    fprintf(stderr, "[gb200 step] %-14s %8.3f ms\n", what, t - t_prev);
+    t_prev = t;
+    return 0;
+  };
 
   struct Bufs {
     cudaStream_t st; std::vector<void*> p;
@@ -141,45 +181,60 @@ int32_t b200_groth16_prove(b200_pk_t pk, const void* wires, const void* a, const
 
   // upload the solution (R1CSSolution{W,A,B,C}); pad A,B,C to the domain (prove.go:356-359)
   CK(cudaMemcpyAsync(d_w, wires, pk->nb_wires * fb, cudaMemcpyHostToDevice, st));
+  // wire filtering (prove.go:147-168) and the three MSMs that do not need h start right after W lands
+  CK(pk->fr->gather(st, d_wa, d_w, pk->d_idx_a, pk->n_a));
+  CK(pk->fr->gather(st, d_wb, d_w, pk->d_idx_b, pk->n_b));
+  rc = lap("h2d W+filter"); if (rc) return rc;
+  char* res = reinterpret_cast<char*>(d_res);
+  // prove.go:207 (Ar), :194 (Bs1), :237 (Krs), :283 (Bs2), :227 (Krs2 over h)
+  rc = msm_on_stream(ctx, pk->A, 0, pk->n_a, d_wa, res + 0 * j1, nullptr, true); if (rc) return rc;
+  rc = lap("msm A"); if (rc) return rc;
+  rc = msm_on_stream(ctx, pk->B1, 0, pk->n_b, d_wb, res + 1 * j1, nullptr, true); if (rc) return rc;
+  rc = lap("msm B1"); if (rc) return rc;
+  rc = msm_on_stream(ctx, pk->K, 0, pk->cnt_k, (char*)d_w + (pk->nb_public + pk->off_k) * fb, res + 3 * j1, nullptr, true); if (rc) return rc;
+  rc = lap("msm K"); if (rc) return rc;
+  rc = msm_on_stream(ctx, pk->B2, 0, pk->n_b, d_wb, res + 4 * j1, nullptr, true); if (rc) return rc;
+  rc = lap("msm B2 (G2)"); if (rc) return rc;
   const void* src[3] = {a, b, c};
   void* dst[3] = {d_a, d_b, d_c};
   for (int k = 0; k < 3; k++) {
     if (n_constraints) CK(cudaMemcpyAsync(dst[k], src[k], n_constraints * fb, cudaMemcpyHostToDevice, st));
     if (n_constraints < n) CK(cudaMemsetAsync((char*)dst[k] + n_constraints * fb, 0, (n - n_constraints) * fb, st));
   }
+  rc = lap("h2d A,B,C"); if (rc) return rc;
   // h (bit-reversed, Montgomery) - prove.go:134,346-389
   CK(pk->fr->compute_h(st, pk->dom->impl, d_a, d_b, d_c));
-  // wire filtering - prove.go:147-168
-  CK(pk->fr->gather(st, d_wa, d_w, pk->d_idx_a, pk->n_a));
-  CK(pk->fr->gather(st, d_wb, d_w, pk->d_idx_b, pk->n_b));
-  // the five MSMs - prove.go:207 (Ar), :194 (Bs1), :227 (Krs2 over h), :237 (Krs), :283 (Bs2)
-  char* res = reinterpret_cast<char*>(d_res);
-  rc = msm_on_stream(ctx, pk->A, 0, pk->n_a, d_wa, res + 0 * j1, nullptr, true); if (rc) return rc;
-  rc = msm_on_stream(ctx, pk->B1, 0, pk->n_b, d_wb, res + 1 * j1, nullptr, true); if (rc) return rc;
-  rc = msm_on_stream(ctx, pk->Z, 0, n - 1, d_a, res + 2 * j1, nullptr, true); if (rc) return rc;
-  rc = msm_on_stream(ctx, pk->K, 0, pk->nb_wires - pk->nb_public, (char*)d_w + pk->nb_public * fb, res + 3 * j1, nullptr, true); if (rc) return rc;
-  rc = msm_on_stream(ctx, pk->B2, 0, pk->n_b, d_wb, res + 4 * j1, nullptr, true); if (rc) return rc;
+  rc = lap("computeH"); if (rc) return rc;
+  rc = msm_on_stream(ctx, pk->Z, 0, pk->cnt_z, (char*)d_a + pk->off_z * fb, res + 2 * j1, nullptr, true); if (rc) return rc;
   rc = msm_join(ctx); if (rc) return rc;
-  std::vector<uint8_t> host(4 * j1 + j2);
-  CK(cudaMemcpyAsync(host.data(), d_res, host.size(), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(msm_out, d_res, 4 * j1 + j2, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  rc = lap("msm Z + d2h"); if (rc) return rc;
+  return 0;
+  GUARD_END
+}
 
-  // host work that does not depend on the MSMs overlaps with them: deltas = [r, s, -rs] * delta (prove.go:185)
+int32_t b200_groth16_assemble(b200_pk_t pk, const void* msm5, const void* r, const void* s, void* ar_out,
+                              void* bs_out, void* krs_out) {
+  GUARD_BEGIN
+  if (!pk || !msm5 || !r || !s || !ar_out || !bs_out || !krs_out) return set_error("assemble: null argument");
   const HostGroupOps* h1 = pk->h1;
   const HostGroupOps* h2 = pk->h2;
+  const size_t fb = pk->fr->fr_bytes;
+  const size_t j1 = h1->jac_bytes, j2 = h2->jac_bytes;
+  // deltas = [r, s, -rs] * delta (prove.go:185)
   std::vector<uint8_t> kr(fb), rd(j1), sd(j1), krd(j1), sd2(j2);
   h1->fr_neg_mul(r, s, kr.data());
   h1->scalar_mul_affine(pk->delta.data(), r, rd.data());
   h1->scalar_mul_affine(pk->delta.data(), s, sd.data());
   h1->scalar_mul_affine(pk->delta.data(), kr.data(), krd.data());
   h2->scalar_mul_affine(pk->delta2.data(), s, sd2.data());
-
-  CK(cudaStreamSynchronize(st));
-  if (msm_out) memcpy(msm_out, host.data(), host.size());
-  uint8_t* mA = host.data();
-  uint8_t* mB1 = host.data() + j1;
-  uint8_t* mZ = host.data() + 2 * j1;
-  uint8_t* mK = host.data() + 3 * j1;
-  uint8_t* mB2 = host.data() + 4 * j1;
+  const uint8_t* m = reinterpret_cast<const uint8_t*>(msm5);
+  const uint8_t* mA = m;
+  const uint8_t* mB1 = m + j1;
+  const uint8_t* mZ = m + 2 * j1;
+  const uint8_t* mK = m + 3 * j1;
+  const uint8_t* mB2 = m + 4 * j1;
   // ar = A + alpha + r*delta (prove.go:207-214)
   std::vector<uint8_t> ar(mA, mA + j1);
   h1->add_mixed(ar.data(), pk->alpha.data());
@@ -204,6 +259,25 @@ int32_t b200_groth16_prove(b200_pk_t pk, const void* wires, const void* a, const
   h1->to_affine(krs.data(), krs_out);
   h2->to_affine(bs2.data(), bs_out);
   return 0;
+  GUARD_END
+}
+
+int32_t b200_groth16_prove(b200_pk_t pk, const void* wires, const void* a, const void* b, const void* c,
+                           size_t n_constraints, const void* r, const void* s, void* ar_out, void* bs_out,
+                           void* krs_out, void* msm_out) {
+  GUARD_BEGIN
+  if (!pk) return set_error("prove: null proving key");
+  if (pk->shard_world > 1) return set_error("prove: sharded key - use b200_groth16_msms + all_gather + b200_groth16_assemble");
+  if (!r || !s || !ar_out || !bs_out || !krs_out) return set_error("prove: null argument");
+  std::vector<uint8_t> msm(4 * pk->h1->jac_bytes + pk->h2->jac_bytes);
+  const double t0 = now_ms();
+  int32_t rc = b200_groth16_msms(pk, wires, a, b, c, n_constraints, msm.data());
+  if (rc) return rc;
+  const double t1 = now_ms();
+  if (msm_out) memcpy(msm_out, msm.data(), msm.size());
+  rc = b200_groth16_assemble(pk, msm.data(), r, s, ar_out, bs_out, krs_out);
+  if (getenv("GB200_STEP_PROFILE")) fprintf(stderr, "[gb200 step] %-14s %8.3f ms (device part %.3f ms)\n", "host assembly", now_ms() - t1, t1 - t0);
+  return rc;
   GUARD_END
 }
 

@@ -40,6 +40,9 @@ class Config:
     Precompute: bool = True      # build the per-window table slabs (B200_TABLE_PRECOMP)
     ProverOpts: list = field(default_factory=list)
     Randomness: Optional[Callable[[int], int]] = None   # test hook: r,s injection
+    ShardRank: int = 0           # multi-GPU (one process per GPU): this process's point-range shard
+    ShardWorld: int = 1
+    ProcessGroup: object = None  # torch.distributed group used to gather the partial MSM results
 
 
 Option = Callable[[Config], None]
@@ -78,6 +81,17 @@ def WithProverOptions(*opts) -> Option:
         if not opts:
             raise ValueError("no prover options provided")
         c.ProverOpts = list(opts)
+    return f
+
+
+def WithSharding(rank: int, world: int, process_group=None) -> Option:
+    """One process per GPU: every MSM table is cut into `world` contiguous point ranges
+    (SURVEY.md §8e); partial results are all-gathered over `process_group` and summed on the host
+    (the shape of the reference's chunk loop, icicle.go:383-411)."""
+    def f(c: Config):
+        if world < 1 or not (0 <= rank < world):
+            raise ValueError(f"invalid shard {rank}/{world}")
+        c.ShardRank, c.ShardWorld, c.ProcessGroup = rank, world, process_group
     return f
 
 
@@ -148,7 +162,8 @@ class ProvingKey:
 
     def setup_device_pointers(self, cfg: Config):
         """icicle.go:88-264 setupDevicePointers: once per key and device."""
-        if self._handle is not None and self._dev == cfg.DeviceID:
+        key = (cfg.DeviceID, cfg.ShardRank, cfg.ShardWorld)
+        if self._handle is not None and self._dev == key:
             return
         self.free_gpu_resources()
         d = _lib.Groth16PkDesc()
@@ -166,9 +181,10 @@ class ProvingKey:
         d.infinity_a, d.infinity_b = p(self.InfinityA), p(self.InfinityB)
         d.nb_wires, d.nb_public = self.nb_wires, self.nb_public
         d.flags = _lib.TABLE_PRECOMP if cfg.Precompute else 0
+        d.shard_rank, d.shard_world = cfg.ShardRank, cfg.ShardWorld
         h = ctypes.c_void_p(0)
         _lib.check(_lib.load().b200_groth16_pk_load(cfg.DeviceID, ctypes.byref(d), ctypes.byref(h)))
-        self._handle, self._dev = h, cfg.DeviceID
+        self._handle, self._dev = h, key
 
     def free_gpu_resources(self):
         """icicle.go:1493-1549 FreeGPUResources; safe to call repeatedly."""
@@ -213,11 +229,34 @@ def ProveSolution(pk: ProvingKey, sol: R1CSSolution, *opts: Option, keep_msm: bo
     ar = np.zeros(2 * fpl, dtype=np.uint64)
     krs = np.zeros(2 * fpl, dtype=np.uint64)
     bs = np.zeros(2 * fpl * deg, dtype=np.uint64)
-    msm = np.zeros(4 * 3 * fpl + 3 * fpl * deg, dtype=np.uint64) if keep_msm else None
     p = _lib.ptr
-    _lib.check(_lib.load().b200_groth16_prove(pk._handle, p(sol.W), p(sol.A), p(sol.B), p(sol.C), n_constraints,
-                                              p(r), p(s), p(ar), p(bs), p(krs), p(msm)))
-    return Proof(Ar=ar, Bs=bs, Krs=krs, msm=msm)
+    L = _lib.load()
+    if cfg.ShardWorld <= 1:
+        msm = np.zeros(4 * 3 * fpl + 3 * fpl * deg, dtype=np.uint64) if keep_msm else None
+        _lib.check(L.b200_groth16_prove(pk._handle, p(sol.W), p(sol.A), p(sol.B), p(sol.C), n_constraints,
+                                        p(r), p(s), p(ar), p(bs), p(krs), p(msm)))
+        return Proof(Ar=ar, Bs=bs, Krs=krs, msm=msm)
+    # sharded: device part on every rank, one all_gather of 5 partial points, host-side sums
+    import torch
+    import torch.distributed as dist
+    part = np.zeros(4 * 3 * fpl + 3 * fpl * deg, dtype=np.uint64)
+    _lib.check(L.b200_groth16_msms(pk._handle, p(sol.W), p(sol.A), p(sol.B), p(sol.C), n_constraints, p(part)))
+    t = torch.from_numpy(part.view(np.int64))
+    if dist.get_backend(cfg.ProcessGroup) == "nccl":
+        t = t.cuda(cfg.DeviceID)
+    parts = [torch.empty_like(t) for _ in range(cfg.ShardWorld)]
+    dist.all_gather(parts, t, group=cfg.ProcessGroup)
+    parts = [x.cpu().numpy().view(np.uint64) for x in parts]
+    msm = parts[0].copy()
+    j1 = 3 * fpl
+    spans = [(k * j1, (k + 1) * j1, 1) for k in range(4)] + [(4 * j1, 4 * j1 + 3 * fpl * deg, 2)]
+    for q in parts[1:]:
+        for lo, hi, grp in spans:
+            seg = np.ascontiguousarray(msm[lo:hi])
+            _lib.point_add_jac(pk.curve, grp, seg, np.ascontiguousarray(q[lo:hi]))
+            msm[lo:hi] = seg
+    _lib.check(L.b200_groth16_assemble(pk._handle, p(msm), p(r), p(s), p(ar), p(bs), p(krs)))
+    return Proof(Ar=ar, Bs=bs, Krs=krs, msm=msm if keep_msm else None)
 
 
 def Prove(r1cs, pk: ProvingKey, full_witness, *opts: Option) -> Proof:

@@ -30,7 +30,8 @@ EXPORTS = [
     "b200_msm_async", "b200_msm_pipelined", "b200_msm_join", "b200_msm_profile", "b200_ntt_domain_new", "b200_ntt_domain_free", "b200_ntt", "b200_ntt_async",
     "b200_groth16_compute_h", "b200_vec_op", "b200_vec_bit_reverse", "b200_vec_scale_powers",
     "b200_vec_batch_invert", "b200_plonk_constraints_coset", "b200_plonk_divide_by_zh",
-    "b200_point_add_jac", "b200_point_to_affine", "b200_groth16_pk_load", "b200_groth16_pk_free", "b200_groth16_prove",
+    "b200_point_add_jac", "b200_point_to_affine", "b200_groth16_pk_load", "b200_groth16_pk_free", "b200_groth16_prove", "b200_groth16_msms",
+    "b200_groth16_assemble",
 ]
 
 
@@ -59,6 +60,8 @@ class Groth16PkDesc(ctypes.Structure):
         ("nb_wires", ctypes.c_size_t),
         ("nb_public", ctypes.c_size_t),
         ("flags", ctypes.c_int32),
+        ("shard_rank", ctypes.c_int32),
+        ("shard_world", ctypes.c_int32),
     ]
 
 
@@ -119,6 +122,8 @@ def load(path: str = None):
     lib.b200_groth16_pk_load.argtypes = [i32, ctypes.POINTER(Groth16PkDesc), ctypes.POINTER(vp)]
     lib.b200_groth16_pk_free.argtypes = [vp]
     lib.b200_groth16_prove.argtypes = [vp, vp, vp, vp, vp, sz, vp, vp, vp, vp, vp, vp]
+    lib.b200_groth16_msms.argtypes = [vp, vp, vp, vp, vp, sz, vp]
+    lib.b200_groth16_assemble.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     if path is None:
         _lib = lib
     return lib

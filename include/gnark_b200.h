@@ -191,6 +191,10 @@ typedef struct {
   size_t nb_wires;
   size_t nb_public;           /* r1cs.GetNbPublicVariables() (K covers wires[nb_public:]) */
   int32_t flags;              /* B200_TABLE_PRECOMP */
+  /* multi-GPU: this process keeps only shard `shard_rank` of `shard_world` contiguous point-range
+   * shards of every table; 0/0 or world <= 1 = the whole key. */
+  int32_t shard_rank;
+  int32_t shard_world;
 } b200_groth16_pk_desc;
 
 int32_t b200_groth16_pk_load(int32_t dev, const b200_groth16_pk_desc* desc, b200_pk_t* out);
@@ -205,6 +209,16 @@ int32_t b200_groth16_pk_free(b200_pk_t pk);
 int32_t b200_groth16_prove(b200_pk_t pk, const void* wires, const void* a, const void* b, const void* c,
                            size_t n_constraints, const void* r, const void* s, void* ar_out, void* bs_out,
                            void* krs_out, void* msm_out);
+/* The two halves of b200_groth16_prove, for sharded keys (one process per GPU):
+ *  - b200_groth16_msms: device part.  computeH + this shard's slice of the five MSMs; msm_out
+ *    receives 4 G1Jac + 1 G2Jac partial sums (order A, B1, Z(h), K, B2).  Partial sums of all
+ *    shards are added with b200_point_add_jac after one all_gather.
+ *  - b200_groth16_assemble: host part (prove.go:185,199-214,241-269,287-292) from the five
+ *    complete MSM results. */
+int32_t b200_groth16_msms(b200_pk_t pk, const void* wires, const void* a, const void* b, const void* c,
+                          size_t n_constraints, void* msm_out);
+int32_t b200_groth16_assemble(b200_pk_t pk, const void* msm5, const void* r, const void* s, void* ar_out,
+                              void* bs_out, void* krs_out);
 
 #ifdef __cplusplus
 }
