@@ -50,6 +50,8 @@ int32_t device_ctx(int dev, DeviceCtx** out) {
     CK(cudaStreamCreateWithPriority(&c.tail_stream, cudaStreamNonBlocking, hi_prio));
     CK(cudaEventCreateWithFlags(&c.fork_ev, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c.tail_ev, cudaEventDisableTiming));
+    CK(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&c.copy_ev, cudaEventDisableTiming));
     cudaMemPool_t pool;
     CK(cudaDeviceGetDefaultMemPool(&pool, dev));
     uint64_t thr = UINT64_MAX;  // keep freed workspace cached in the pool
@@ -159,6 +161,8 @@ int32_t b200_shutdown(void) {
     cudaStreamSynchronize(c.tail_stream);
     cudaStreamDestroy(c.own_stream);
     cudaStreamDestroy(c.tail_stream);
+    cudaStreamDestroy(c.copy_stream);
+    cudaEventDestroy(c.copy_ev);
     cudaEventDestroy(c.fork_ev);
     cudaEventDestroy(c.tail_ev);
     c = DeviceCtx();

@@ -25,6 +25,8 @@ struct DeviceCtx {
   cudaStream_t stream = nullptr;  // own_stream or the caller's (b200_set_stream)
   // pipelined MSMs: reduction tail of MSM i runs here while MSM i+1 sorts/accumulates on `stream`
   cudaStream_t tail_stream = nullptr;
+  cudaStream_t copy_stream = nullptr;  // H2D of later-needed inputs overlaps compute on `stream`
+  cudaEvent_t copy_ev = nullptr;
   cudaEvent_t fork_ev = nullptr;   // accumulate done (recorded on stream)
   cudaEvent_t tail_ev = nullptr;   // tail done (recorded on tail_stream)
   bool tail_pending = false;

@@ -195,11 +195,22 @@ int32_t b200_groth16_msms(b200_pk_t pk, const void* wires, const void* a, const 
   rc = lap("msm K"); if (rc) return rc;
   rc = msm_on_stream(ctx, pk->B2, 0, pk->n_b, d_wb, res + 4 * j1, nullptr, true); if (rc) return rc;
   rc = lap("msm B2 (G2)"); if (rc) return rc;
+  // A, B, C go up on the copy stream while the four h-independent MSMs run (the copy engine is
+  // idle otherwise); with pageable host memory the copies block this host thread, not the GPU
+  cudaStream_t cs = profile ? st : ctx->copy_stream;
+  if (!profile) {
+    CK(cudaEventRecord(ctx->copy_ev, st));          // d_a/d_b/d_c were allocated in st's order
+    CK(cudaStreamWaitEvent(cs, ctx->copy_ev, 0));
+  }
   const void* src[3] = {a, b, c};
   void* dst[3] = {d_a, d_b, d_c};
   for (int k = 0; k < 3; k++) {
-    if (n_constraints) CK(cudaMemcpyAsync(dst[k], src[k], n_constraints * fb, cudaMemcpyHostToDevice, st));
-    if (n_constraints < n) CK(cudaMemsetAsync((char*)dst[k] + n_constraints * fb, 0, (n - n_constraints) * fb, st));
+    if (n_constraints) CK(cudaMemcpyAsync(dst[k], src[k], n_constraints * fb, cudaMemcpyHostToDevice, cs));
+    if (n_constraints < n) CK(cudaMemsetAsync((char*)dst[k] + n_constraints * fb, 0, (n - n_constraints) * fb, cs));
+  }
+  if (!profile) {
+    CK(cudaEventRecord(ctx->copy_ev, cs));
+    CK(cudaStreamWaitEvent(st, ctx->copy_ev, 0));
   }
   rc = lap("h2d A,B,C"); if (rc) return rc;
   // h (bit-reversed, Montgomery) - prove.go:134,346-389
