@@ -69,18 +69,56 @@ __global__ void __launch_bounds__(128) k_msm_accumulate(MsmPlan pl, const Affine
   partial[t] = msm_accumulate_range<F>(table, svals, begin, end);
 }
 
-// one thread per bucket: sum of its task partials
+// one thread per bucket: sum of its task partials.  Buckets with more than MSM_HEAVY partials
+// (skewed witnesses: many equal small scalars; a short top window) are queued for the
+// block-cooperative kernel below instead of being summed serially.
+constexpr uint32_t MSM_HEAVY = 16;
 template <class F>
 __global__ void __launch_bounds__(128) k_msm_combine(MsmPlan pl, const uint32_t* __restrict__ task_off,
                                                      const XYZZ<F>* __restrict__ partial,
-                                                     XYZZ<F>* __restrict__ buckets) {
+                                                     XYZZ<F>* __restrict__ buckets, uint32_t* __restrict__ heavy_count,
+                                                     uint32_t* __restrict__ heavy_list) {
   const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= pl.total_buckets) return;
   const uint32_t t0 = task_off[b], t1 = task_off[b + 1];
+  if (t1 - t0 > MSM_HEAVY) {
+    heavy_list[atomicAdd(heavy_count, 1u)] = b;
+    return;
+  }
   XYZZ<F> acc = XYZZ<F>::inf();
   if (t0 < t1) acc = partial[t0];
   for (uint32_t t = t0 + 1; t < t1; t++) acc.add(partial[t]);
   buckets[b] = acc;
+}
+
+// one block per heavy bucket (grid-stride over the queue): strided partial sums, shared-memory tree
+template <class F>
+__global__ void __launch_bounds__(256) k_msm_combine_heavy(const uint32_t* __restrict__ task_off,
+                                                           const XYZZ<F>* __restrict__ partial,
+                                                           XYZZ<F>* __restrict__ buckets,
+                                                           const uint32_t* __restrict__ heavy_count,
+                                                           const uint32_t* __restrict__ heavy_list) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  XYZZ<F>* sm = reinterpret_cast<XYZZ<F>*>(smem_raw);
+  const uint32_t nh = *heavy_count;
+  for (uint32_t i = blockIdx.x; i < nh; i += gridDim.x) {
+    const uint32_t b = heavy_list[i];
+    const uint32_t t0 = task_off[b], t1 = task_off[b + 1];
+    XYZZ<F> acc = XYZZ<F>::inf();
+    for (uint32_t t = t0 + threadIdx.x; t < t1; t += blockDim.x) acc.add(partial[t]);
+    sm[threadIdx.x] = acc;
+    __syncthreads();
+    for (uint32_t w = blockDim.x >> 1; w > 0; w >>= 1) {
+      if (threadIdx.x < w) {
+        XYZZ<F> a = sm[threadIdx.x];
+        a.add(sm[threadIdx.x + w]);
+        sm[threadIdx.x] = a;
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) buckets[b] = sm[0];
+    __syncthreads();
+  }
 }
 
 // one thread per (set, chunk): weighted running sum of `chunk` buckets
@@ -157,7 +195,7 @@ struct MsmLayout {
   uint32_t chunks_per_set;
   size_t cub_bytes;
   // offsets into the workspace
-  size_t o_keys0, o_keys1, o_vals0, o_vals1, o_off, o_ntasks, o_task_off, o_partial, o_buckets, o_chunks, o_sets, o_cub,
+  size_t o_keys0, o_keys1, o_vals0, o_vals1, o_off, o_ntasks, o_task_off, o_partial, o_buckets, o_chunks, o_sets, o_heavy, o_cub,
       total;
 };
 
@@ -188,6 +226,7 @@ cudaError_t msm_layout(const MsmPlan& pl, MsmLayout<F>& L) {
   L.o_buckets = o; o += gb_align((size_t)pl.total_buckets * sizeof(XYZZ<F>));
   L.o_chunks = o; o += gb_align((size_t)L.chunks_per_set * pl.nsets * sizeof(XYZZ<F>));
   L.o_sets = o; o += gb_align((size_t)pl.nsets * sizeof(XYZZ<F>));
+  L.o_heavy = o; o += gb_align((L.max_tasks / MSM_HEAVY + 2) * 4);  // [0] = count, [1..] = bucket ids
   L.o_cub = o; o += gb_align(L.cub_bytes);
   L.total = o;
   return cudaSuccess;
@@ -255,7 +294,15 @@ cudaError_t msm_enqueue(cudaStream_t stream, const MsmPlan& pl, const Affine<F>*
     GB_CUDA_TRY(cudaStreamWaitEvent(tail, fork_ev, 0));
     stream = tail;
   }
-  k_msm_combine<F><<<(nb + 127) / 128, 128, 0, stream>>>(pl, task_off, partial, buckets);
+  uint32_t* heavy = (uint32_t*)(w + L.o_heavy);
+  GB_CUDA_TRY(cudaMemsetAsync(heavy, 0, 4, stream));
+  k_msm_combine<F><<<(nb + 127) / 128, 128, 0, stream>>>(pl, task_off, partial, buckets, heavy, heavy + 1);
+  {
+    int ht = msm_set_sum_threads<F>();
+    const size_t hsmem = (size_t)ht * sizeof(XYZZ<F>);
+    GB_CUDA_TRY(cudaFuncSetAttribute(k_msm_combine_heavy<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsmem));
+    k_msm_combine_heavy<F><<<148, ht, hsmem, stream>>>(task_off, partial, buckets, heavy, heavy + 1);
+  }
   GB_EV(5);
   const uint32_t nchunks = L.chunks_per_set * (uint32_t)pl.nsets;
   k_msm_reduce_chunks<F><<<(nchunks + 127) / 128, 128, 0, stream>>>(pl, L.chunks_per_set, buckets, chunks);
