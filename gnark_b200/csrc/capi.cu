@@ -110,7 +110,7 @@ int32_t msm_on_stream(DeviceCtx* ctx, b200_table_s* t, size_t off, size_t n, con
   CK(cudaMallocAsync(&ws, ws_bytes, ctx->stream));
   cudaError_t e = t->ops->run(ctx->stream, (uint32_t)n, (uint32_t)t->n, (uint32_t)off, t->c, t->precomp, task_len, chunk,
                               t->d_points, d_scalars, d_out, ws, stage_events, pipelined ? ctx->tail_stream : nullptr,
-                              ctx->fork_ev);
+                              ctx->fork_ev, t->fmt52);
   // the workspace is last used by the tail kernels
   cudaError_t e2 = cudaFreeAsync(ws, pipelined ? ctx->tail_stream : ctx->stream);
   if (pipelined && e == cudaSuccess) {
@@ -249,11 +249,23 @@ int32_t b200_table_upload(int32_t dev, int32_t curve, int32_t group, const void*
   if (env_int("GB200_MSM_PRECOMP", -1) >= 0) t->precomp = env_int("GB200_MSM_PRECOMP", 0) ? 1 : 0;
   const size_t slabs = t->precomp ? (size_t)t->nwin : 1;
   if (slabs * n >= (1ull << 31)) return set_error("table_upload: table too large for 31-bit point indices; shard it");
-  t->bytes = slabs * (n ? n : 1) * ops->affine_bytes;
-  CK(cudaMalloc(&t->d_points, t->bytes));
   const cudaMemcpyKind kind = (flags & B200_TABLE_SRC_ON_DEVICE) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-  if (n) CK(cudaMemcpyAsync(t->d_points, points, n * ops->affine_bytes, kind, ctx->stream));
-  if (t->precomp) CK(ops->precompute(ctx->stream, (uint32_t)n, t->nwin, t->c, t->d_points));
+  // FP64-pipe accumulate (field52.cuh) for precomputed G1 tables unless GB200_MSM_FP64=0
+  t->fmt52 = (t->precomp && ops->affine52_bytes && env_int("GB200_MSM_FP64", 1) && n > 0) ? 1 : 0;
+  if (t->fmt52) {
+    t->bytes = slabs * n * ops->affine52_bytes;
+    CK(cudaMalloc(&t->d_points, t->bytes));
+    void* d_src = nullptr;
+    CK(cudaMallocAsync(&d_src, n * ops->affine_bytes, ctx->stream));
+    CK(cudaMemcpyAsync(d_src, points, n * ops->affine_bytes, kind, ctx->stream));
+    CK(ops->precompute52(ctx->stream, (uint32_t)n, t->nwin, t->c, d_src, t->d_points));
+    CK(cudaFreeAsync(d_src, ctx->stream));
+  } else {
+    t->bytes = slabs * (n ? n : 1) * ops->affine_bytes;
+    CK(cudaMalloc(&t->d_points, t->bytes));
+    if (n) CK(cudaMemcpyAsync(t->d_points, points, n * ops->affine_bytes, kind, ctx->stream));
+    if (t->precomp) CK(ops->precompute(ctx->stream, (uint32_t)n, t->nwin, t->c, t->d_points));
+  }
   CK(cudaStreamSynchronize(ctx->stream));
   *out = t.release();
   return 0;

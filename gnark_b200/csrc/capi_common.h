@@ -44,6 +44,7 @@ struct b200_table_s {
   int dev, curve, group;
   size_t n;          // bases
   int c, nwin, precomp;
+  int fmt52 = 0;     // entries are Affine52 (FP64-pipe accumulate)
   size_t bytes;
   void* d_points = nullptr;
   const gb200::MsmOps* ops;

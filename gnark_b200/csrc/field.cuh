@@ -240,6 +240,13 @@ struct alignas(16) Fp2 {
   }
 };
 
+// 52-bit-limb (FP64 pipe) parameter pack of a base field, when one exists (field52.cuh)
+template <class F> struct F52Traits { static constexpr bool ok = false; using P52 = void; };
+template <> struct F52Traits<Fp<bn254_fp_params>> { static constexpr bool ok = true; using P52 = bn254_fp_params52; };
+template <> struct F52Traits<Fp<bls12_381_fp_params>> { static constexpr bool ok = true; using P52 = bls12_381_fp_params52; };
+template <> struct F52Traits<Fp<bls12_377_fp_params>> { static constexpr bool ok = true; using P52 = bls12_377_fp_params52; };
+template <> struct F52Traits<Fp<bw6_761_fp_params>> { static constexpr bool ok = true; using P52 = bw6_761_fp_params52; };
+
 // concrete fields
 using bn254_fp = Fp<bn254_fp_params>;
 using bn254_fr = Fp<bn254_fr_params>;

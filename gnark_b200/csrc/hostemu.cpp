@@ -10,6 +10,9 @@
 #include <numeric>
 #include <vector>
 
+#include <cfenv>
+
+#include "curve52.cuh"
 #include "msm.cuh"
 #include "ntt.cuh"
 
@@ -98,7 +101,116 @@ int ntt_emu(void* data_, unsigned logn, int inverse, int decimation, int on_cose
 
 }  // namespace
 
+template <class P52>
+int f52_mul(const uint64_t* a, const uint64_t* b, uint64_t* out) {
+  const int old = fegetround();
+  fesetround(FE_TOWARDZERO);   // __fma_rz on the device
+  F52<P52> x, y;
+  for (int i = 0; i < P52::L; i++) { x.l[i] = (int64_t)a[i]; y.l[i] = (int64_t)b[i]; }
+  F52<P52> r = mul52<P52>(x, y);
+  for (int i = 0; i < P52::L; i++) out[i] = (uint64_t)r.l[i];
+  fesetround(old);
+  return P52::L;
+}
+
+// gnark element (Montgomery R32) -> 52-bit form -> back; must be the identity
+template <class P52>
+int f52_roundtrip(const uint32_t* in, uint32_t* out) {
+  const int old = fegetround();
+  fesetround(FE_TOWARDZERO);
+  F52<P52> x = from_mont32<P52>(in);
+  to_mont32<P52>(x, out);
+  fesetround(old);
+  return 0;
+}
+
+// bucket accumulation through the FP64-pipe path (XYZZ52), checked against the 32-bit path
+template <class Fr, class F, class P52>
+int msm_emu52(const void* points_, const void* scalars_, uint32_t n, int c, uint32_t task_len, uint32_t chunk,
+              void* out_jac) {
+  const int old = fegetround();
+  fesetround(FE_TOWARDZERO);
+  const Affine<F>* points = reinterpret_cast<const Affine<F>*>(points_);
+  const Fr* scalars = reinterpret_cast<const Fr*>(scalars_);
+  MsmPlan pl = msm_make_plan(n, n, 0, Fr::Params::BITS, c, 1, task_len, chunk);
+  std::vector<Affine<F>> table(points, points + n);
+  table.resize((size_t)n * pl.nwin);
+  for (int w = 1; w < pl.nwin; w++)
+    for (uint32_t i = 0; i < n; i++) table[(size_t)w * n + i] = msm_shift_point(table[(size_t)(w - 1) * n + i], c);
+  std::vector<Affine52<P52>> table52(table.size());
+  for (size_t i = 0; i < table.size(); i++) table52[i] = affine_to_52<P52, F>(table[i]);
+  const size_t m = (size_t)n * pl.nwin;
+  std::vector<uint32_t> keys(m), vals(m);
+  for (uint32_t i = 0; i < n; i++) msm_decompose_one<Fr>(pl, i, scalars, keys.data(), vals.data());
+  std::vector<uint32_t> order(m);
+  std::iota(order.begin(), order.end(), 0u);
+  std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return keys[x] < keys[y]; });
+  std::vector<uint32_t> skeys(m), svals(m);
+  for (size_t k = 0; k < m; k++) { skeys[k] = keys[order[k]]; svals[k] = vals[order[k]]; }
+  std::vector<uint32_t> off(pl.total_buckets + 1);
+  for (uint32_t b = 0; b <= pl.total_buckets; b++)
+    off[b] = (uint32_t)(std::lower_bound(skeys.begin(), skeys.end(), b) - skeys.begin());
+  std::vector<XYZZ<F>> buckets(pl.total_buckets);
+  for (uint32_t b = 0; b < pl.total_buckets; b++) {
+    XYZZ<F> acc = XYZZ<F>::inf();
+    for (uint32_t s = off[b]; s < off[b + 1]; s += pl.task_len) {
+      uint32_t e = std::min(off[b + 1], s + pl.task_len);
+      acc.add(msm_accumulate_range52<P52, F>(table52.data(), svals.data(), s, e));
+    }
+    buckets[b] = acc;
+  }
+  XYZZ<F> tot = XYZZ<F>::inf();
+  for (uint32_t lo = 0; lo < pl.set_size; lo += pl.chunk) {
+    uint32_t hi = std::min(pl.set_size, lo + pl.chunk);
+    tot.add(msm_reduce_chunk<F>(buckets.data(), lo, hi));
+  }
+  *reinterpret_cast<Jacobian<F>*>(out_jac) = tot.to_jacobian();
+  fesetround(old);
+  return 0;
+}
+
 extern "C" {
+
+// 52-bit-limb Montgomery product on the (emulated) FP64 path; limbs as uint64 < 2^52
+int emu_f52_mul(int field_id, const uint64_t* a, const uint64_t* b, uint64_t* out) {
+  switch (field_id) {
+    case 0: return f52_mul<bn254_fp_params52>(a, b, out);
+    case 1: return f52_mul<bn254_fr_params52>(a, b, out);
+    case 2: return f52_mul<bls12_381_fp_params52>(a, b, out);
+    case 3: return f52_mul<bls12_381_fr_params52>(a, b, out);
+    case 4: return f52_mul<bls12_377_fp_params52>(a, b, out);
+    case 5: return f52_mul<bls12_377_fr_params52>(a, b, out);
+    case 6: return f52_mul<bw6_761_fp_params52>(a, b, out);
+    case 7: return f52_mul<bw6_761_fr_params52>(a, b, out);
+  }
+  return -1;
+}
+
+int emu_f52_roundtrip(int field_id, const uint32_t* in, uint32_t* out) {
+  switch (field_id) {
+    case 0: return f52_roundtrip<bn254_fp_params52>(in, out);
+    case 1: return f52_roundtrip<bn254_fr_params52>(in, out);
+    case 2: return f52_roundtrip<bls12_381_fp_params52>(in, out);
+    case 3: return f52_roundtrip<bls12_381_fr_params52>(in, out);
+    case 4: return f52_roundtrip<bls12_377_fp_params52>(in, out);
+    case 5: return f52_roundtrip<bls12_377_fr_params52>(in, out);
+    case 6: return f52_roundtrip<bw6_761_fp_params52>(in, out);
+    case 7: return f52_roundtrip<bw6_761_fr_params52>(in, out);
+  }
+  return -1;
+}
+
+// G1 MSM with the FP64-pipe accumulate (precomputed table mode)
+int emu_msm52(int curve, const void* points, const void* scalars, uint32_t n, int c, uint32_t task_len, uint32_t chunk,
+              void* out_jac) {
+  switch (curve) {
+    case 0: return msm_emu52<bn254_fr, bn254_fp, bn254_fp_params52>(points, scalars, n, c, task_len, chunk, out_jac);
+    case 1: return msm_emu52<bls12_381_fr, bls12_381_fp, bls12_381_fp_params52>(points, scalars, n, c, task_len, chunk, out_jac);
+    case 2: return msm_emu52<bls12_377_fr, bls12_377_fp, bls12_377_fp_params52>(points, scalars, n, c, task_len, chunk, out_jac);
+    case 3: return msm_emu52<bw6_761_fr, bw6_761_fp, bw6_761_fp_params52>(points, scalars, n, c, task_len, chunk, out_jac);
+  }
+  return -1;
+}
 
 // field_id = curve*2 + (0: fp, 1: fr)
 int emu_field_op(int field_id, int op, const void* a, const void* b, void* out) {

@@ -28,21 +28,36 @@ struct MsmInst {
   }
   static cudaError_t run(cudaStream_t st, uint32_t n, uint32_t stride, uint32_t off, int c, int precomp,
                          uint32_t task_len, uint32_t chunk, const void* d_table, const void* d_scalars,
-                         void* d_out_jac, void* ws, cudaEvent_t* ev, cudaStream_t tail, cudaEvent_t fork_ev) {
+                         void* d_out_jac, void* ws, cudaEvent_t* ev, cudaStream_t tail, cudaEvent_t fork_ev, int fmt52) {
     MsmPlan pl = plan(n, stride, off, c, precomp, task_len, chunk);
     MsmLayout<F> L;
     GB_CUDA_TRY(msm_layout<F>(pl, L));
     return msm_enqueue<Fr, F>(st, pl, reinterpret_cast<const Affine<F>*>(d_table),
-                              reinterpret_cast<const Fr*>(d_scalars), reinterpret_cast<Jacobian<F>*>(d_out_jac), ws, L, ev, tail, fork_ev);
+                              reinterpret_cast<const Fr*>(d_scalars), reinterpret_cast<Jacobian<F>*>(d_out_jac), ws, L, ev, tail, fork_ev, fmt52);
   }
   static cudaError_t precompute(cudaStream_t st, uint32_t n, int nwin, int c, void* d_table) {
     if (n == 0 || nwin <= 1) return cudaSuccess;
     k_msm_precompute<F><<<(n + 127) / 128, 128, 0, st>>>(n, nwin, c, reinterpret_cast<Affine<F>*>(d_table));
     return cudaGetLastError();
   }
+  static size_t affine52_bytes() {
+    if constexpr (F52Traits<F>::ok) return sizeof(Affine52<typename F52Traits<F>::P52>);
+    else return 0;
+  }
+  static cudaError_t precompute52(cudaStream_t st, uint32_t n, int nwin, int c, const void* d_src, void* d_table52) {
+    if constexpr (F52Traits<F>::ok) {
+      using P52 = typename F52Traits<F>::P52;
+      if (n == 0) return cudaSuccess;
+      k_msm_precompute52<F, P52><<<(n + 127) / 128, 128, 0, st>>>(n, nwin, c, reinterpret_cast<const Affine<F>*>(d_src),
+                                                                  reinterpret_cast<Affine52<P52>*>(d_table52));
+      return cudaGetLastError();
+    } else {
+      return cudaErrorNotSupported;
+    }
+  }
   static const MsmOps* ops() {
     static const MsmOps o = {Fr::Params::BITS, sizeof(Fr), sizeof(Affine<F>), sizeof(Jacobian<F>), &ws_bytes, &run,
-                             &precompute};
+                             &precompute, affine52_bytes(), &precompute52};
     return &o;
   }
 };

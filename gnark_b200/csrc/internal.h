@@ -20,9 +20,12 @@ struct MsmOps {
   cudaError_t (*run)(cudaStream_t st, uint32_t n, uint32_t stride, uint32_t off, int c, int precomp,
                      uint32_t task_len, uint32_t chunk, const void* d_table, const void* d_scalars, void* d_out_jac,
                      void* ws, cudaEvent_t* stage_events /* nullable, 8 entries */,
-                     cudaStream_t tail /* nullable */, cudaEvent_t fork_ev);
+                     cudaStream_t tail /* nullable */, cudaEvent_t fork_ev, int fmt52);
   // fill slabs 1..nwin-1 of a [nwin][n] table whose slab 0 holds the bases
   cudaError_t (*precompute)(cudaStream_t st, uint32_t n, int nwin, int c, void* d_table);
+  // FP64-pipe table format (field52.cuh): bytes per entry, 0 when the group has no such path
+  size_t affine52_bytes;
+  cudaError_t (*precompute52)(cudaStream_t st, uint32_t n, int nwin, int c, const void* d_src, void* d_table52);
 };
 
 struct NttOps {

@@ -23,6 +23,7 @@
 // all windows share ONE bucket set.  PLAIN: table = the n points; W bucket sets.
 #pragma once
 #include "curve.cuh"
+#include "curve52.cuh"
 
 namespace gb200 {
 
@@ -107,6 +108,22 @@ HD XYZZ<F> msm_accumulate_range(const Affine<F>* table, const uint32_t* vals, ui
   XYZZ<F> acc = XYZZ<F>::inf();
   for (uint32_t e = begin; e < end; e++) acc.add_mixed(msm_load_point(table, vals[e]));
   return acc;
+}
+
+// FP64-pipe variant (field52.cuh / curve52.cuh): table entries are Affine52, the accumulator is
+// XYZZ52, the task result is converted once to the 32-bit representation of the reduction kernels
+template <class P52, class F>
+HD XYZZ<F> msm_accumulate_range52(const Affine52<P52>* table, const uint32_t* vals, uint32_t begin, uint32_t end) {
+  XYZZ52<P52> acc = XYZZ52<P52>::inf();
+  for (uint32_t e = begin; e < end; e++) {
+    const uint32_t v = vals[e];
+    const Affine52<P52>& a = table[v & 0x7fffffffu];
+    D52<P52> ax, ay;
+#pragma unroll
+    for (int i = 0; i < P52::L; i++) { ax.d[i] = a.x[i]; ay.d[i] = a.y[i]; }
+    acc.add_mixed(ax, ay, (v >> 31) != 0);
+  }
+  return acc.template to_xyzz32<F>();
 }
 
 // ---- 5. reduce -------------------------------------------------------------

@@ -69,10 +69,50 @@ __global__ void __launch_bounds__(128) k_msm_accumulate(MsmPlan pl, const Affine
   partial[t] = msm_accumulate_range<F>(table, svals, begin, end);
 }
 
+// FP64-pipe twin of k_msm_accumulate (field52.cuh / curve52.cuh): same task decomposition, table
+// entries are Affine52 (Montgomery R52, doubles), the accumulator lives in 52-bit limbs
+template <class F, class P52>
+__global__ void __launch_bounds__(128) k_msm_accumulate52(MsmPlan pl, const Affine52<P52>* __restrict__ table,
+                                                          const uint32_t* __restrict__ svals,
+                                                          const uint32_t* __restrict__ off,
+                                                          const uint32_t* __restrict__ task_off,
+                                                          XYZZ<F>* __restrict__ partial) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t nb = pl.total_buckets;
+  if (t >= __ldg(task_off + nb)) return;
+  uint32_t lo = 0, hi = nb;
+  while (lo < hi) {
+    const uint32_t mid = lo + ((hi - lo + 1) >> 1);
+    if (__ldg(task_off + mid) <= t) lo = mid; else hi = mid - 1;
+  }
+  const uint32_t b = lo;
+  const uint32_t j = t - __ldg(task_off + b);
+  const uint32_t begin = __ldg(off + b) + j * pl.task_len;
+  uint32_t end = begin + pl.task_len;
+  const uint32_t bend = __ldg(off + b + 1);
+  if (end > bend) end = bend;
+  partial[t] = msm_accumulate_range52<P52, F>(table, svals, begin, end);
+}
+
+// table build for the FP64-pipe path: slab w holds 2^(c*w) * P_i as Affine52
+template <class F, class P52>
+__global__ void __launch_bounds__(128) k_msm_precompute52(uint32_t n, int nwin, int c, const Affine<F>* __restrict__ src,
+                                                          Affine52<P52>* __restrict__ table) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const Affine<F> p0 = src[i];
+  table[i] = affine_to_52<P52, F>(p0);
+  XYZZ<F> q = XYZZ<F>::from_affine(p0);
+  for (int w = 1; w < nwin; w++) {
+    for (int k = 0; k < c; k++) q.dbl();
+    table[(size_t)w * n + i] = affine_to_52<P52, F>(q.to_affine());
+  }
+}
+
 // one thread per bucket: sum of its task partials.  Buckets with more than MSM_HEAVY partials
 // (skewed witnesses: many equal small scalars; a short top window) are queued for the
 // block-cooperative kernel below instead of being summed serially.
-constexpr uint32_t MSM_HEAVY = 16;
+constexpr uint32_t MSM_HEAVY = 8;
 template <class F>
 __global__ void __launch_bounds__(128) k_msm_combine(MsmPlan pl, const uint32_t* __restrict__ task_off,
                                                      const XYZZ<F>* __restrict__ partial,
@@ -91,33 +131,38 @@ __global__ void __launch_bounds__(128) k_msm_combine(MsmPlan pl, const uint32_t*
   buckets[b] = acc;
 }
 
-// one block per heavy bucket (grid-stride over the queue): strided partial sums, shared-memory tree
+// one WARP per heavy bucket (grid-stride over the queue): lanes stride the partials, then a
+// 5-level tree through shared memory
 template <class F>
-__global__ void __launch_bounds__(256) k_msm_combine_heavy(const uint32_t* __restrict__ task_off,
+__global__ void __launch_bounds__(128) k_msm_combine_heavy(const uint32_t* __restrict__ task_off,
                                                            const XYZZ<F>* __restrict__ partial,
                                                            XYZZ<F>* __restrict__ buckets,
                                                            const uint32_t* __restrict__ heavy_count,
                                                            const uint32_t* __restrict__ heavy_list) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  XYZZ<F>* sm = reinterpret_cast<XYZZ<F>*>(smem_raw);
+  XYZZ<F>* sm = reinterpret_cast<XYZZ<F>*>(smem_raw) + (threadIdx.x & ~31u);
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t warps_per_block = blockDim.x >> 5;
+  const uint32_t warp = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+  const uint32_t nwarps = gridDim.x * warps_per_block;
   const uint32_t nh = *heavy_count;
-  for (uint32_t i = blockIdx.x; i < nh; i += gridDim.x) {
+  for (uint32_t i = warp; i < nh; i += nwarps) {
     const uint32_t b = heavy_list[i];
     const uint32_t t0 = task_off[b], t1 = task_off[b + 1];
     XYZZ<F> acc = XYZZ<F>::inf();
-    for (uint32_t t = t0 + threadIdx.x; t < t1; t += blockDim.x) acc.add(partial[t]);
-    sm[threadIdx.x] = acc;
-    __syncthreads();
-    for (uint32_t w = blockDim.x >> 1; w > 0; w >>= 1) {
-      if (threadIdx.x < w) {
-        XYZZ<F> a = sm[threadIdx.x];
-        a.add(sm[threadIdx.x + w]);
-        sm[threadIdx.x] = a;
+    for (uint32_t t = t0 + lane; t < t1; t += 32) acc.add(partial[t]);
+    sm[lane] = acc;
+    __syncwarp();
+    for (uint32_t w = 16; w > 0; w >>= 1) {
+      if (lane < w) {
+        XYZZ<F> a = sm[lane];
+        a.add(sm[lane + w]);
+        sm[lane] = a;
       }
-      __syncthreads();
+      __syncwarp();
     }
-    if (threadIdx.x == 0) buckets[b] = sm[0];
-    __syncthreads();
+    if (lane == 0) buckets[b] = sm[0];
+    __syncwarp();
   }
 }
 
@@ -245,7 +290,7 @@ inline int msm_set_sum_threads(size_t budget = 160 * 1024) {
 template <class Fr, class F>
 cudaError_t msm_enqueue(cudaStream_t stream, const MsmPlan& pl, const Affine<F>* d_table, const Fr* d_scalars,
                         Jacobian<F>* d_out, void* ws, const MsmLayout<F>& L, cudaEvent_t* ev = nullptr,
-                        cudaStream_t tail = nullptr, cudaEvent_t fork_ev = nullptr) {
+                        cudaStream_t tail = nullptr, cudaEvent_t fork_ev = nullptr, int fmt52 = 0) {
   // tail (optional): the latency-bound reduction kernels that follow the accumulate kernel are
   // enqueued on this second stream (forked with fork_ev), so that in a pipeline of MSMs they
   // overlap the next MSM's sort/accumulate instead of idling 140+ SMs.
@@ -286,8 +331,19 @@ cudaError_t msm_enqueue(cudaStream_t stream, const MsmPlan& pl, const Affine<F>*
   cub_bytes = L.cub_bytes;
   GB_CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, ntasks, task_off, (int)nb + 1, stream));
   GB_EV(3);
-  k_msm_accumulate<F><<<(unsigned)((L.max_tasks + 127) / 128), 128, 0, stream>>>(pl, d_table, vals1, off, task_off,
-                                                                                 partial);
+  if constexpr (F52Traits<F>::ok) {
+    if (fmt52) {
+      using P52 = typename F52Traits<F>::P52;
+      k_msm_accumulate52<F, P52><<<(unsigned)((L.max_tasks + 127) / 128), 128, 0, stream>>>(
+          pl, reinterpret_cast<const Affine52<P52>*>(d_table), vals1, off, task_off, partial);
+    } else {
+      k_msm_accumulate<F><<<(unsigned)((L.max_tasks + 127) / 128), 128, 0, stream>>>(pl, d_table, vals1, off,
+                                                                                     task_off, partial);
+    }
+  } else {
+    k_msm_accumulate<F><<<(unsigned)((L.max_tasks + 127) / 128), 128, 0, stream>>>(pl, d_table, vals1, off, task_off,
+                                                                                   partial);
+  }
   GB_EV(4);
   if (tail) {
     GB_CUDA_TRY(cudaEventRecord(fork_ev, stream));
@@ -298,10 +354,10 @@ cudaError_t msm_enqueue(cudaStream_t stream, const MsmPlan& pl, const Affine<F>*
   GB_CUDA_TRY(cudaMemsetAsync(heavy, 0, 4, stream));
   k_msm_combine<F><<<(nb + 127) / 128, 128, 0, stream>>>(pl, task_off, partial, buckets, heavy, heavy + 1);
   {
-    int ht = msm_set_sum_threads<F>();
+    const int ht = 128;  // 4 warps = 4 buckets in flight per block
     const size_t hsmem = (size_t)ht * sizeof(XYZZ<F>);
     GB_CUDA_TRY(cudaFuncSetAttribute(k_msm_combine_heavy<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsmem));
-    k_msm_combine_heavy<F><<<148, ht, hsmem, stream>>>(task_off, partial, buckets, heavy, heavy + 1);
+    k_msm_combine_heavy<F><<<148 * 2, ht, hsmem, stream>>>(task_off, partial, buckets, heavy, heavy + 1);
   }
   GB_EV(5);
   const uint32_t nchunks = L.chunks_per_set * (uint32_t)pl.nsets;

@@ -98,3 +98,67 @@ def test_ntt_logic(hostemu, c):
                     assert hostemu.emu_ntt(c.curve_id, P(A), logn, inv, dec, cos, None, None) == 0
                     exp = (dom.fft_inverse if inv else dom.fft)(a, dec, on_coset=bool(cos))
                     assert ff.unpack_elements(A, c.r, c.fr_limbs) == exp, (c.name, logn, inv, dec, cos)
+
+
+# ---- FP64-pipe path (field52.cuh / curve52.cuh): 52-bit limbs, DFMA round-toward-zero products ----
+def _limbs52(v, L):
+    return np.array([(v >> (52 * i)) & ((1 << 52) - 1) for i in range(L)], dtype=np.uint64)
+
+
+def _l52(q):
+    bits = q.bit_length()
+    L = (bits + 51) // 52
+    if 52 * L - bits < 5:
+        L += 1
+    return L
+
+
+@pytest.mark.parametrize("c", ALL, ids=lambda c: c.name)
+def test_f52_mul_lazy_bounds_and_roundtrip(hostemu, c):
+    rng = random.Random(1)
+    for which, (q, L64) in enumerate(((c.p, c.fp_limbs), (c.r, c.fr_limbs))):
+        fid = c.curve_id * 2 + which
+        L = _l52(q)
+        R = 1 << (52 * L)
+        bound = 8 * q if 52 * L - q.bit_length() >= 6 else 4 * q     # lazy-reduction input bound
+        for t in range(100):
+            a, b = rng.randrange(bound), rng.randrange(bound)
+            if t == 0: a = b = 0
+            if t == 1: a = b = bound - 1
+            if t == 2: a, b = q, q - 1
+            out = np.zeros(L, dtype=np.uint64)
+            assert hostemu.emu_f52_mul(fid, P(_limbs52(a, L)), P(_limbs52(b, L)), P(out)) == L
+            got = sum(int(out[i]) << (52 * i) for i in range(L))
+            assert all(int(x) < (1 << 52) for x in out)                 # normalised limbs
+            assert got % q == a * b * pow(R, -1, q) % q and got < 2 * q   # value and output bound
+        for t in range(40):                                             # gnark layout <-> 52-bit form
+            v = [0, q - 1, 1][t] if t < 3 else rng.randrange(q)
+            A = ff.pack_elements([v], q, L64)
+            O = np.zeros_like(A)
+            hostemu.emu_f52_roundtrip(fid, P(A), P(O))
+            assert np.array_equal(A, O)
+
+
+@pytest.mark.parametrize("c", ALL, ids=lambda c: c.name)
+def test_msm_fp64_path_logic(hostemu, c):
+    """same edge cases as test_msm_logic, bucket accumulation through XYZZ52 (precomputed-table mode)"""
+    rng = random.Random(19)
+    F, base = pick_base(c, 1, rng)
+    n = 37
+    pts = [ec.scalar_mul(F, rng.randrange(1, 1 << 40), base) for _ in range(n)]
+    pts[3] = ec.INF
+    pts[5] = pts[4]
+    pts[7] = ec.affine_neg(F, pts[6])
+    sc = [rng.randrange(c.r) for _ in range(n)]
+    sc[0], sc[1], sc[2] = 0, c.r - 1, 1
+    sc[4] = sc[5]
+    sc[6] = sc[7] = 12345
+    sc[8], sc[9] = 1 << 15, (1 << 16) - 1
+    exp = ec.msm_naive(F, pts, sc)
+    PA, SA = ec.pack_points(c, 1, pts), ff.pack_elements(sc, c.r, c.fr_limbs)
+    for (cw, tl, ch) in ((7, 2, 16), (13, 5, 100), (4, 3, 4)):
+        if cw >= 13 and c.fp_limbs > 6:
+            continue
+        out = np.zeros(3 * c.fp_limbs, dtype=np.uint64)
+        assert hostemu.emu_msm52(c.curve_id, P(PA), P(SA), n, cw, tl, ch, P(out)) == 0
+        assert ec.from_jac(F, ec.unpack_points(c, 1, out, ncoords=3)[0]) == exp, (c.name, cw)
