@@ -80,11 +80,16 @@ int msm_window_for(size_t n) {
   if (c > 16) c = 16;
   return c;
 }
-void msm_tuning(size_t n, int nwin, int c, uint32_t* task_len, uint32_t* chunk) {
+void msm_tuning(size_t n, int nwin, int c, int precomp, uint32_t* task_len, uint32_t* chunk) {
   const size_t m = n * (size_t)nwin;
+  // enough tasks to fill the GPU (~150k), but no more than ~8 partial sums per bucket on average
+  // (each partial costs the combine kernel one serial XYZZ addition)
+  const size_t buckets = (precomp ? (size_t)1 : (size_t)nwin) << (c - 1);
   size_t tl = m / 150000;
+  const size_t per_bucket = (m / buckets + 7) / 8;
+  if (per_bucket > tl) tl = per_bucket;
   if (tl < 8) tl = 8;
-  if (tl > 64) tl = 64;
+  if (tl > 128) tl = 128;
   *task_len = (uint32_t)env_int("GB200_MSM_TASK_LEN", (int)tl);
   *chunk = (uint32_t)env_int("GB200_MSM_CHUNK", c >= 12 ? 8 : 4);
 }
@@ -103,7 +108,7 @@ int32_t msm_on_stream(DeviceCtx* ctx, b200_table_s* t, size_t off, size_t n, con
   if (stage_events || n == 0) pipelined = false;
   if (!pipelined) { int32_t rc = msm_join(ctx); if (rc) return rc; }
   uint32_t task_len, chunk;
-  msm_tuning(n, t->nwin, t->c, &task_len, &chunk);
+  msm_tuning(n, t->nwin, t->c, t->precomp, &task_len, &chunk);
   size_t ws_bytes = 0;
   CK(t->ops->ws_bytes((uint32_t)n, (uint32_t)t->n, t->c, t->precomp, task_len, chunk, &ws_bytes));
   void* ws = nullptr;
@@ -250,8 +255,9 @@ int32_t b200_table_upload(int32_t dev, int32_t curve, int32_t group, const void*
   const size_t slabs = t->precomp ? (size_t)t->nwin : 1;
   if (slabs * n >= (1ull << 31)) return set_error("table_upload: table too large for 31-bit point indices; shard it");
   const cudaMemcpyKind kind = (flags & B200_TABLE_SRC_ON_DEVICE) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-  // FP64-pipe accumulate (field52.cuh) for precomputed G1 tables unless GB200_MSM_FP64=0
-  t->fmt52 = (t->precomp && ops->affine52_bytes && env_int("GB200_MSM_FP64", 1) && n > 0) ? 1 : 0;
+  // FP64-pipe accumulate (field52.cuh) for precomputed G1 tables: opt-in (GB200_MSM_FP64=1).  Measured on
+  // B200 it is SLOWER than the IMAD.WIDE path (profiles/r01_fp64_pipe_experiment.md), so it is off by default.
+  t->fmt52 = (t->precomp && ops->affine52_bytes && env_int("GB200_MSM_FP64", 0) && n > 0) ? 1 : 0;
   if (t->fmt52) {
     t->bytes = slabs * n * ops->affine52_bytes;
     CK(cudaMalloc(&t->d_points, t->bytes));

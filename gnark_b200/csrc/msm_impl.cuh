@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(128) k_msm_precompute52(uint32_t n, int nwin, 
 // one thread per bucket: sum of its task partials.  Buckets with more than MSM_HEAVY partials
 // (skewed witnesses: many equal small scalars; a short top window) are queued for the
 // block-cooperative kernel below instead of being summed serially.
-constexpr uint32_t MSM_HEAVY = 8;
+constexpr uint32_t MSM_HEAVY = 48;   // below this a single thread's serial sum beats the warp tree (measured)
 template <class F>
 __global__ void __launch_bounds__(128) k_msm_combine(MsmPlan pl, const uint32_t* __restrict__ task_off,
                                                      const XYZZ<F>* __restrict__ partial,
