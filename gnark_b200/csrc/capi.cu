@@ -510,6 +510,46 @@ int32_t b200_vec_batch_invert(int32_t dev, int32_t curve, void* data, size_t n) 
   GUARD_END
 }
 
+int32_t b200_vec_scan(int32_t dev, int32_t curve, int32_t op, void* data, size_t n, int32_t exclusive) {
+  GUARD_BEGIN
+  DeviceCtx* ctx; int32_t rc = device_ctx(dev, &ctx); if (rc) return rc;
+  const NttOps* ops = get_ntt_ops(curve);
+  if (!ops) return set_error("vec_scan: unsupported curve");
+  if (op != B200_SCAN_PRODUCT && op != B200_SCAN_SUM) return set_error("vec_scan: unknown op");
+  CK(ops->scan(ctx->stream, op, data, n, exclusive));
+  return 0;
+  GUARD_END
+}
+int32_t b200_plonk_build_z(b200_domain_t d0, const void* l, const void* r, const void* o, const int64_t* perm,
+                           const void* beta, const void* gamma, void* z) {
+  GUARD_BEGIN
+  if (!d0 || !l || !r || !o || !perm || !beta || !gamma || !z) return set_error("plonk_build_z: null argument");
+  DeviceCtx* ctx; int32_t rc = device_ctx(d0->dev, &ctx); if (rc) return rc;
+  CK(d0->ops->plonk_build_z(ctx->stream, d0->impl, l, r, o, perm, beta, gamma, z));
+  return 0;
+  GUARD_END
+}
+int32_t b200_poly_eval(int32_t dev, int32_t curve, const void* c, size_t n, const void* x, void* out) {
+  GUARD_BEGIN
+  DeviceCtx* ctx; int32_t rc = device_ctx(dev, &ctx); if (rc) return rc;
+  const NttOps* ops = get_ntt_ops(curve);
+  if (!ops) return set_error("poly_eval: unsupported curve");
+  if (!x || !out || (n && !c)) return set_error("poly_eval: null argument");
+  CK(ops->poly_eval(ctx->stream, c, n, x, out));
+  return 0;
+  GUARD_END
+}
+int32_t b200_poly_div_by_linear(int32_t dev, int32_t curve, void* c, size_t n, const void* z, void* rem) {
+  GUARD_BEGIN
+  DeviceCtx* ctx; int32_t rc = device_ctx(dev, &ctx); if (rc) return rc;
+  const NttOps* ops = get_ntt_ops(curve);
+  if (!ops) return set_error("poly_div_by_linear: unsupported curve");
+  if (!z || !rem || (n && !c)) return set_error("poly_div_by_linear: null argument");
+  CK(ops->poly_div_linear(ctx->stream, c, n, z, rem));
+  return 0;
+  GUARD_END
+}
+
 // ---- PLONK ------------------------------------------------------------------------
 int32_t b200_plonk_constraints_coset(b200_domain_t d0, const void* big_coset_gen, const void* big_gen,
                                      const b200_plonk_coset_args* args) {

@@ -205,6 +205,82 @@ struct NttInst {
     GB_CUDA_TRY(cudaFreeAsync(d_tab, st));
     return cudaStreamSynchronize(st);  // tab is a stack buffer
   }
+  static cudaError_t scan(cudaStream_t st, int op, void* d, size_t n, int exclusive) {
+    return op == 0 ? scan_enqueue<Fr, 0>(st, (Fr*)d, n, exclusive != 0) : scan_enqueue<Fr, 1>(st, (Fr*)d, n, exclusive != 0);
+  }
+  // iop.BuildRatioCopyConstraint: Z[0] = 1, Z[i+1] = Z[i] * num_i / den_i  (Lagrange, regular layout)
+  static cudaError_t plonk_build_z(cudaStream_t st, void* dom0, const void* l, const void* r, const void* o,
+                                   const int64_t* perm, const void* beta, const void* gamma, void* z) {
+    const Dom& d = *reinterpret_cast<Dom*>(dom0);
+    Fr *num = nullptr, *den = nullptr;
+    GB_CUDA_TRY(cudaMallocAsync(&num, (size_t)d.n * sizeof(Fr), st));
+    GB_CUDA_TRY(cudaMallocAsync(&den, (size_t)d.n * sizeof(Fr), st));
+    k_plonk_ratio_terms<Fr><<<(d.n + 255) / 256, 256, 0, st>>>(d.n, (const Fr*)l, (const Fr*)r, (const Fr*)o, perm, d.tw,
+                                                            *(const Fr*)beta, *(const Fr*)gamma, d.coset, num, den);
+    GB_CUDA_TRY(cudaGetLastError());
+    GB_CUDA_TRY(batch_invert(st, den, d.n));
+    k_plonk_shift_ratio<Fr><<<(d.n + 255) / 256, 256, 0, st>>>(d.n, num, den, (Fr*)z);
+    GB_CUDA_TRY(cudaGetLastError());
+    GB_CUDA_TRY((scan_enqueue<Fr, 0>(st, (Fr*)z, d.n, false)));
+    GB_CUDA_TRY(cudaFreeAsync(num, st));
+    return cudaFreeAsync(den, st);
+  }
+  static cudaError_t upload_pow_table(cudaStream_t st, const Fr& x, Fr** d_pw) {
+    Fr pw[64];
+    Fr b = x;
+    for (int j = 0; j < 64; j++) { pw[j] = b; b = b.sqr(); }
+    GB_CUDA_TRY(cudaMallocAsync(d_pw, sizeof(pw), st));
+    GB_CUDA_TRY(cudaMemcpyAsync(*d_pw, pw, sizeof(pw), cudaMemcpyHostToDevice, st));
+    return cudaStreamSynchronize(st);  // pw is a stack buffer
+  }
+  static cudaError_t poly_eval(cudaStream_t st, const void* c, size_t n, const void* x_, void* out_host) {
+    const Fr x = *(const Fr*)x_;
+    if (n == 0) { *(Fr*)out_host = Fr::zero(); return cudaSuccess; }
+    Fr* d_pw = nullptr;
+    GB_CUDA_TRY(upload_pow_table(st, x, &d_pw));
+    const size_t nblocks = (n + 256 * EVAL_E - 1) / (256 * EVAL_E);
+    Fr* sums = nullptr;
+    GB_CUDA_TRY(cudaMallocAsync(&sums, (nblocks + 1) * sizeof(Fr), st));
+    k_poly_eval_partial<Fr><<<(unsigned)nblocks, 256, 0, st>>>((const Fr*)c, n, d_pw, x, sums);
+    k_sum_reduce<Fr><<<1, 256, 0, st>>>(sums, nblocks, sums + nblocks);
+    GB_CUDA_TRY(cudaGetLastError());
+    GB_CUDA_TRY(cudaMemcpyAsync(out_host, sums + nblocks, sizeof(Fr), cudaMemcpyDeviceToHost, st));
+    GB_CUDA_TRY(cudaFreeAsync(sums, st));
+    GB_CUDA_TRY(cudaFreeAsync(d_pw, st));
+    return cudaStreamSynchronize(st);
+  }
+  // in place: coeffs[0..n-2] <- (p(X) - p(z)) / (X - z), coeffs[n-1] <- 0; remainder p(z) to the host
+  static cudaError_t poly_div_linear(cudaStream_t st, void* c_, size_t n, const void* z_, void* rem_host) {
+    Fr* c = (Fr*)c_;
+    const Fr z = *(const Fr*)z_;
+    if (n == 0) { *(Fr*)rem_host = Fr::zero(); return cudaSuccess; }
+    if (z.is_zero()) {
+      // q_i = c_{i+1}, remainder c_0
+      GB_CUDA_TRY(cudaMemcpyAsync(rem_host, c, sizeof(Fr), cudaMemcpyDeviceToHost, st));
+      Fr* tmp = nullptr;
+      GB_CUDA_TRY(cudaMallocAsync(&tmp, n * sizeof(Fr), st));
+      GB_CUDA_TRY(cudaMemcpyAsync(tmp, c, n * sizeof(Fr), cudaMemcpyDeviceToDevice, st));
+      if (n > 1) GB_CUDA_TRY(cudaMemcpyAsync(c, tmp + 1, (n - 1) * sizeof(Fr), cudaMemcpyDeviceToDevice, st));
+      GB_CUDA_TRY(cudaMemsetAsync(c + (n - 1), 0, sizeof(Fr), st));
+      GB_CUDA_TRY(cudaFreeAsync(tmp, st));
+      return cudaStreamSynchronize(st);
+    }
+    const Fr zinv = z.inverse();
+    Fr *d_pw = nullptr, *d_pwi = nullptr, *t = nullptr, *d_rem = nullptr;
+    GB_CUDA_TRY(upload_pow_table(st, z, &d_pw));
+    GB_CUDA_TRY(upload_pow_table(st, zinv, &d_pwi));
+    GB_CUDA_TRY(cudaMallocAsync(&t, n * sizeof(Fr), st));
+    GB_CUDA_TRY(cudaMallocAsync(&d_rem, sizeof(Fr), st));
+    const unsigned nb = (unsigned)((n + 256 * EVAL_E - 1) / (256 * EVAL_E));
+    k_syndiv_pre<Fr><<<nb, 256, 0, st>>>(c, n, d_pwi, zinv, t);
+    GB_CUDA_TRY((scan_enqueue<Fr, 1>(st, t, n, false)));
+    k_syndiv_post<Fr><<<nb, 256, 0, st>>>(t, n, d_pw, z, c, d_rem);
+    GB_CUDA_TRY(cudaGetLastError());
+    GB_CUDA_TRY(cudaMemcpyAsync(rem_host, d_rem, sizeof(Fr), cudaMemcpyDeviceToHost, st));
+    GB_CUDA_TRY(cudaFreeAsync(t, st)); GB_CUDA_TRY(cudaFreeAsync(d_rem, st));
+    GB_CUDA_TRY(cudaFreeAsync(d_pw, st)); GB_CUDA_TRY(cudaFreeAsync(d_pwi, st));
+    return cudaStreamSynchronize(st);
+  }
   static cudaError_t gather(cudaStream_t st, void* out, const void* src, const uint32_t* idx, size_t n) {
     if (!n) return cudaSuccess;
     k_gather<Fr><<<(unsigned)((n + 255) / 256), 256, 0, st>>>((Fr*)out, (const Fr*)src, idx, n);
@@ -213,7 +289,7 @@ struct NttInst {
   static const NttOps* ops() {
     static const NttOps o = {sizeof(Fr), Fr::Params::TWO_ADICITY, &domain_new, &domain_free, &domain_bytes, &ntt,
                              &compute_h, &vec_op, &bit_reverse, &scale_powers, &batch_invert, &plonk_coset,
-                             &plonk_divide_by_zh, &gather};
+                             &plonk_divide_by_zh, &scan, &plonk_build_z, &poly_eval, &poly_div_linear, &gather};
     return &o;
   }
 };

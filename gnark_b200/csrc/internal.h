@@ -44,6 +44,12 @@ struct NttOps {
   cudaError_t (*plonk_coset)(cudaStream_t st, void* dom0, const void* big_coset_gen, const void* big_gen,
                              const void* args);
   cudaError_t (*plonk_divide_by_zh)(cudaStream_t st, void* dom1, uint32_t log_n0, void* d_data);
+  // O(n) scans (plonk.cuh)
+  cudaError_t (*scan)(cudaStream_t st, int op /*0 product, 1 sum*/, void* d_data, size_t n, int exclusive);
+  cudaError_t (*plonk_build_z)(cudaStream_t st, void* dom0, const void* d_l, const void* d_r, const void* d_o,
+                               const int64_t* d_perm, const void* beta, const void* gamma, void* d_z);
+  cudaError_t (*poly_eval)(cudaStream_t st, const void* d_coeffs, size_t n, const void* x_mont, void* out_host);
+  cudaError_t (*poly_div_linear)(cudaStream_t st, void* d_coeffs, size_t n, const void* z_mont, void* rem_host);
   // out[j] = src[idx[j]] (wire filtering, backend/groth16/bn254/prove.go:147-168)
   cudaError_t (*gather)(cudaStream_t st, void* d_out, const void* d_src, const uint32_t* d_idx, size_t n);
 };

@@ -131,3 +131,200 @@ __global__ void __launch_bounds__(256) k_plonk_denominators(Fr* __restrict__ d, 
 #endif
 
 }  // namespace gb200
+
+// ---------------------------------------------------------------------------------------------
+// O(n) scans of the PLONK prover on device: prefix scans over Fr,
+// the permutation grand product Z (iop.BuildRatioCopyConstraint, plonk/bn254/prove.go:645-656),
+// polynomial evaluation (Polynomial.Evaluate :742,1191,1382) and division by (X - z)
+// (the quotient inside kzg.Open / BatchOpenSinglePoint :681,827).
+// ---------------------------------------------------------------------------------------------
+namespace gb200 {
+
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_E = 4;   // elements per thread
+
+template <class Fr, int OP>   // OP 0: product, 1: sum
+HD Fr scan_op(const Fr& a, const Fr& b) { return OP == 0 ? a * b : a + b; }
+template <class Fr, int OP>
+HD Fr scan_identity() { return OP == 0 ? Fr::one() : Fr::zero(); }
+
+#ifdef __CUDACC__
+// block-local scan of SCAN_THREADS*SCAN_E elements; block totals to block_sums (nullable)
+template <class Fr, int OP>
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_block(Fr* __restrict__ data, size_t n, Fr* __restrict__ block_sums,
+                                                             int exclusive) {
+  __shared__ Fr sm[SCAN_THREADS];
+  const size_t base = ((size_t)blockIdx.x * SCAN_THREADS + threadIdx.x) * SCAN_E;
+  Fr v[SCAN_E];
+#pragma unroll
+  for (int k = 0; k < SCAN_E; k++) v[k] = base + k < n ? data[base + k] : scan_identity<Fr, OP>();
+#pragma unroll
+  for (int k = 1; k < SCAN_E; k++) v[k] = scan_op<Fr, OP>(v[k - 1], v[k]);
+  sm[threadIdx.x] = v[SCAN_E - 1];
+  __syncthreads();
+  for (int off = 1; off < SCAN_THREADS; off <<= 1) {
+    Fr x = sm[threadIdx.x];
+    if ((int)threadIdx.x >= off) x = scan_op<Fr, OP>(sm[threadIdx.x - off], x);
+    __syncthreads();
+    sm[threadIdx.x] = x;
+    __syncthreads();
+  }
+  const Fr prefix = threadIdx.x == 0 ? scan_identity<Fr, OP>() : sm[threadIdx.x - 1];
+  if (block_sums && threadIdx.x == SCAN_THREADS - 1) block_sums[blockIdx.x] = sm[SCAN_THREADS - 1];
+#pragma unroll
+  for (int k = 0; k < SCAN_E; k++) {
+    if (base + k >= n) break;
+    if (exclusive) data[base + k] = k == 0 ? prefix : scan_op<Fr, OP>(prefix, v[k - 1]);
+    else data[base + k] = scan_op<Fr, OP>(prefix, v[k]);
+  }
+}
+template <class Fr, int OP>
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_fix(Fr* __restrict__ data, size_t n,
+                                                           const Fr* __restrict__ block_prefix) {
+  if (blockIdx.x == 0) return;
+  const Fr p = block_prefix[blockIdx.x];
+  const size_t base = ((size_t)blockIdx.x * SCAN_THREADS + threadIdx.x) * SCAN_E;
+#pragma unroll
+  for (int k = 0; k < SCAN_E; k++)
+    if (base + k < n) data[base + k] = scan_op<Fr, OP>(p, data[base + k]);
+}
+
+// in-place scan of n elements on `st` (recursive over block totals)
+template <class Fr, int OP>
+cudaError_t scan_enqueue(cudaStream_t st, Fr* data, size_t n, bool exclusive) {
+  if (n == 0) return cudaSuccess;
+  const size_t per_block = (size_t)SCAN_THREADS * SCAN_E;
+  const size_t nblocks = (n + per_block - 1) / per_block;
+  if (nblocks == 1) {
+    k_scan_block<Fr, OP><<<1, SCAN_THREADS, 0, st>>>(data, n, nullptr, exclusive ? 1 : 0);
+    return cudaGetLastError();
+  }
+  Fr* sums = nullptr;
+  cudaError_t e = cudaMallocAsync(&sums, nblocks * sizeof(Fr), st);
+  if (e != cudaSuccess) return e;
+  k_scan_block<Fr, OP><<<(unsigned)nblocks, SCAN_THREADS, 0, st>>>(data, n, sums, exclusive ? 1 : 0);
+  e = scan_enqueue<Fr, OP>(st, sums, nblocks, true);
+  if (e == cudaSuccess) {
+    k_scan_fix<Fr, OP><<<(unsigned)nblocks, SCAN_THREADS, 0, st>>>(data, n, sums);
+    e = cudaGetLastError();
+  }
+  cudaError_t e2 = cudaFreeAsync(sums, st);
+  return e != cudaSuccess ? e : e2;
+}
+
+// x^k by square-and-multiply from pw[j] = x^(2^j)
+template <class Fr>
+DEV Fr pow_from_table(const Fr* __restrict__ pw, size_t k) {
+  Fr acc = Fr::one();
+  for (int j = 0; k; j++, k >>= 1)
+    if (k & 1) acc = acc * pw[j];
+  return acc;
+}
+
+// permutation ratios: num[i] = prod_j (f_j[i] + beta*id_j(i) + gamma), den[i] = prod_j (f_j[i] + beta*supp[S[j n+i]] + gamma)
+// supp[k] = g^(k / n) * w^(k % n)   (getSupportPermutation, plonk/bn254/setup.go:377-392)
+template <class Fr>
+__global__ void __launch_bounds__(256) k_plonk_ratio_terms(uint32_t n, const Fr* __restrict__ l, const Fr* __restrict__ r,
+                                                           const Fr* __restrict__ o, const int64_t* __restrict__ S,
+                                                           const Fr* __restrict__ tw, Fr beta, Fr gamma, Fr g,
+                                                           Fr* __restrict__ num, Fr* __restrict__ den) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t half = n >> 1;
+  auto w_at = [&](uint32_t k) -> Fr { return n == 1 ? Fr::one() : (k < half ? tw[k] : tw[k - half].neg()); };
+  const Fr g2 = g * g;
+  auto supp = [&](int64_t k) -> Fr {
+    const uint32_t blk = (uint32_t)(k / n), idx = (uint32_t)(k % n);
+    const Fr w = w_at(idx);
+    return blk == 0 ? w : (blk == 1 ? g * w : g2 * w);
+  };
+  const Fr f[3] = {l[i], r[i], o[i]};
+  const Fr wi = w_at(i);
+  const Fr id[3] = {wi, g * wi, g2 * wi};
+  Fr a = Fr::one(), b = Fr::one();
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    a = a * (f[j] + beta * id[j] + gamma);
+    b = b * (f[j] + beta * supp(S[(size_t)j * n + i]) + gamma);
+  }
+  num[i] = a;
+  den[i] = b;
+}
+// z[0] = 1, z[i+1] = ratio[i] for i < n-1 (then an inclusive product scan yields Z)
+template <class Fr>
+__global__ void __launch_bounds__(256) k_plonk_shift_ratio(uint32_t n, const Fr* __restrict__ num,
+                                                           const Fr* __restrict__ den_inv, Fr* __restrict__ z) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  z[i] = i == 0 ? Fr::one() : num[i - 1] * den_inv[i - 1];
+}
+
+// polynomial evaluation: block partial sums of c_i x^i
+constexpr int EVAL_E = 8;
+template <class Fr>
+__global__ void __launch_bounds__(256) k_poly_eval_partial(const Fr* __restrict__ c, size_t n, const Fr* __restrict__ pw,
+                                                           Fr x, Fr* __restrict__ block_sums) {
+  __shared__ Fr sm[256];
+  const size_t base = ((size_t)blockIdx.x * 256 + threadIdx.x) * EVAL_E;
+  Fr acc = Fr::zero();
+  if (base < n) {
+#pragma unroll
+    for (int k = EVAL_E - 1; k >= 0; k--) acc = acc * x + (base + k < n ? c[base + k] : Fr::zero());
+    acc = acc * pow_from_table<Fr>(pw, base);
+  }
+  sm[threadIdx.x] = acc;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if ((int)threadIdx.x < w) sm[threadIdx.x] = sm[threadIdx.x] + sm[threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) block_sums[blockIdx.x] = sm[0];
+}
+template <class Fr>
+__global__ void __launch_bounds__(256) k_sum_reduce(const Fr* __restrict__ v, size_t n, Fr* __restrict__ out) {
+  __shared__ Fr sm[256];
+  Fr acc = Fr::zero();
+  for (size_t i = threadIdx.x; i < n; i += 256) acc = acc + v[i];
+  sm[threadIdx.x] = acc;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if ((int)threadIdx.x < w) sm[threadIdx.x] = sm[threadIdx.x] + sm[threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = sm[0];
+}
+
+// synthetic division by (X - z), z != 0:  t_k = c_{n-1-k} z^-k ; s = inclusive sum scan(t) ;
+// q_{n-2-k} = s_k z^k (k <= n-2) ; remainder = s_{n-1} z^(n-1) = p(z)
+template <class Fr>
+__global__ void __launch_bounds__(256) k_syndiv_pre(const Fr* __restrict__ c, size_t n, const Fr* __restrict__ pw_inv,
+                                                    Fr zinv, Fr* __restrict__ t) {
+  const size_t base = ((size_t)blockIdx.x * 256 + threadIdx.x) * EVAL_E;
+  if (base >= n) return;
+  Fr p = pow_from_table<Fr>(pw_inv, base);
+#pragma unroll
+  for (int k = 0; k < EVAL_E; k++) {
+    if (base + k >= n) break;
+    t[base + k] = c[n - 1 - (base + k)] * p;
+    p = p * zinv;
+  }
+}
+template <class Fr>
+__global__ void __launch_bounds__(256) k_syndiv_post(const Fr* __restrict__ s, size_t n, const Fr* __restrict__ pw, Fr z,
+                                                     Fr* __restrict__ q, Fr* __restrict__ rem) {
+  const size_t base = ((size_t)blockIdx.x * 256 + threadIdx.x) * EVAL_E;
+  if (base >= n) return;
+  Fr p = pow_from_table<Fr>(pw, base);
+#pragma unroll
+  for (int k = 0; k < EVAL_E; k++) {
+    const size_t kk = base + k;
+    if (kk >= n) break;
+    const Fr v = s[kk] * p;
+    if (kk == n - 1) { *rem = v; q[n - 1] = Fr::zero(); }
+    else q[n - 2 - kk] = v;
+    p = p * z;
+  }
+}
+#endif
+
+}  // namespace gb200

@@ -30,6 +30,7 @@ EXPORTS = [
     "b200_msm_async", "b200_msm_pipelined", "b200_msm_join", "b200_msm_profile", "b200_ntt_domain_new", "b200_ntt_domain_free", "b200_ntt", "b200_ntt_async",
     "b200_groth16_compute_h", "b200_vec_op", "b200_vec_bit_reverse", "b200_vec_scale_powers",
     "b200_vec_batch_invert", "b200_plonk_constraints_coset", "b200_plonk_divide_by_zh",
+    "b200_vec_scan", "b200_plonk_build_z", "b200_poly_eval", "b200_poly_div_by_linear",
     "b200_point_add_jac", "b200_point_to_affine", "b200_groth16_pk_load", "b200_groth16_pk_free", "b200_groth16_prove", "b200_groth16_msms",
     "b200_groth16_assemble",
 ]
@@ -117,6 +118,10 @@ def load(path: str = None):
     lib.b200_vec_batch_invert.argtypes = [i32, i32, vp, sz]
     lib.b200_plonk_constraints_coset.argtypes = [vp, vp, vp, vp]
     lib.b200_plonk_divide_by_zh.argtypes = [vp, u32, vp]
+    lib.b200_vec_scan.argtypes = [i32, i32, i32, vp, sz, i32]
+    lib.b200_plonk_build_z.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.b200_poly_eval.argtypes = [i32, i32, vp, sz, vp, vp]
+    lib.b200_poly_div_by_linear.argtypes = [i32, i32, vp, sz, vp, vp]
     lib.b200_point_add_jac.argtypes = [i32, i32, vp, vp]
     lib.b200_point_to_affine.argtypes = [i32, i32, vp, vp]
     lib.b200_groth16_pk_load.argtypes = [i32, ctypes.POINTER(Groth16PkDesc), ctypes.POINTER(vp)]
@@ -333,3 +338,28 @@ def plonk_constraints_coset(domain0: "Domain", big_coset_gen, big_gen, polys: di
 
 def plonk_divide_by_zh(domain1: "Domain", domain0_log2n: int, d_data):
     check(load().b200_plonk_divide_by_zh(domain1.handle, domain0_log2n, ptr(d_data)))
+
+
+SCAN_PRODUCT, SCAN_SUM = 0, 1
+
+
+def vec_scan(dev, curve, op, d_data, n, exclusive=False):
+    check(load().b200_vec_scan(dev, curve, op, ptr(d_data), n, 1 if exclusive else 0))
+
+
+def plonk_build_z(domain0: "Domain", d_l, d_r, d_o, d_perm, beta, gamma, d_z):
+    check(load().b200_plonk_build_z(domain0.handle, ptr(d_l), ptr(d_r), ptr(d_o), ptr(d_perm), ptr(beta), ptr(gamma),
+                                    ptr(d_z)))
+
+
+def poly_eval(dev, curve, d_coeffs, n, x) -> np.ndarray:
+    out = np.zeros(CURVE_SHAPES[curve][0], dtype=np.uint64)
+    check(load().b200_poly_eval(dev, curve, ptr(d_coeffs), n, ptr(x), ptr(out)))
+    return out
+
+
+def poly_div_by_linear(dev, curve, d_coeffs, n, z) -> np.ndarray:
+    """in place quotient; returns the claimed value p(z)"""
+    out = np.zeros(CURVE_SHAPES[curve][0], dtype=np.uint64)
+    check(load().b200_poly_div_by_linear(dev, curve, ptr(d_coeffs), n, ptr(z), ptr(out)))
+    return out

@@ -167,6 +167,23 @@ int32_t b200_plonk_constraints_coset(b200_domain_t domain0, const void* domain1_
  * FFTInverse(DIT, OnCoset) on domain1: LagrangeCoset/BitReverse -> Canonical/Regular, in place. */
 int32_t b200_plonk_divide_by_zh(b200_domain_t domain1, uint32_t domain0_log2n, void* d_data);
 
+/* ---- O(n) scans of the PLONK prover: keep every polynomial device-resident
+ *      between the MSM / NTT stages.  */
+enum { B200_SCAN_PRODUCT = 0, B200_SCAN_SUM = 1 };
+int32_t b200_vec_scan(int32_t dev, int32_t curve, int32_t op, void* d_data, size_t n, int32_t exclusive);
+/* iop.BuildRatioCopyConstraint (plonk/bn254/prove.go:645-656): Z[0] = 1,
+ * Z[i+1] = Z[i] * prod_j (f_j[i] + beta*id_j[i] + gamma) / (f_j[i] + beta*supp[S[j*n+i]] + gamma), f = (L, R, O)
+ * in Lagrange/regular form on domain0; S = the trace permutation (int64[3n], plonk/bn254/setup.go:289-392);
+ * supp = <w> || g<w> || g^2<w> (getSupportPermutation :377-392), g = domain0's coset generator. */
+int32_t b200_plonk_build_z(b200_domain_t domain0, const void* d_l, const void* d_r, const void* d_o,
+                           const int64_t* d_perm, const void* beta_mont, const void* gamma_mont, void* d_z_out);
+/* Polynomial.Evaluate (Horner) of n canonical coefficients at x; result (one fr.Element) on the host */
+int32_t b200_poly_eval(int32_t dev, int32_t curve, const void* d_coeffs, size_t n, const void* x_mont, void* out_host);
+/* kzg.Open's quotient: coeffs <- (p(X) - p(z)) / (X - z) in place (degree n-2, top coefficient zeroed);
+ * the claimed value p(z) is returned on the host */
+int32_t b200_poly_div_by_linear(int32_t dev, int32_t curve, void* d_coeffs, size_t n, const void* z_mont,
+                                void* claimed_value_host);
+
 /* ---- Groth16 prover (host layer mirroring backend/accelerated/icicle/groth16/
  *      bn254/icicle.go:784-1360 Prove + setupDevicePointers :88-264) ------------
  * Builds the device-resident key from the gnark ProvingKey fields

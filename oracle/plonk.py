@@ -85,3 +85,38 @@ def divide_by_zh(curve, n, rho, cres):
     tab = [pow((gn * pow(wn, i, r) - 1) % r, -1, r) for i in range(rho)]
     scaled = [cres[i] * tab[bitrev(i, logm) % rho] % r for i in range(m)]
     return dom1.fft_inverse(scaled, DIT, on_coset=True)
+
+
+def support_permutation(curve, dom0: Domain):
+    """getSupportPermutation (backend/plonk/bn254/setup.go:377-392): <w> || g<w> || g^2<w>."""
+    r, n, g = curve.r, dom0.n, dom0.coset_gen
+    w = [pow(dom0.generator, i, r) for i in range(n)]
+    return w + [g * x % r for x in w] + [g * g * x % r for x in w]
+
+
+def build_ratio_copy_constraint(curve, dom0: Domain, l, rr, o, perm, beta, gamma):
+    """iop.BuildRatioCopyConstraint as relied upon at plonk/bn254/prove.go:645-656:
+    Z[0] = 1, Z[i+1] = Z[i] * prod_j (f_j[i] + beta*id_j[i] + gamma) / (f_j[i] + beta*supp[S[j n + i]] + gamma)."""
+    r, n = curve.r, dom0.n
+    supp = support_permutation(curve, dom0)
+    f = (l, rr, o)
+    z = [1] * n
+    for i in range(n - 1):
+        num = den = 1
+        for j in range(3):
+            num = num * ((f[j][i] + beta * supp[j * n + i] + gamma) % r) % r
+            den = den * ((f[j][i] + beta * supp[perm[j * n + i]] + gamma) % r) % r
+        z[i + 1] = z[i] * num % r * pow(den, -1, r) % r
+    return z
+
+
+def div_by_linear(r, coeffs, z):
+    """(p(X) - p(z)) / (X - z) by synthetic division; returns (quotient (len n-1), p(z))."""
+    n = len(coeffs)
+    q = [0] * max(n - 1, 0)
+    acc = 0
+    for i in range(n - 1, 0, -1):
+        acc = (coeffs[i] + z * acc) % r
+        q[i - 1] = acc
+    rem = (coeffs[0] + z * acc) % r if n else 0
+    return q, rem

@@ -109,3 +109,79 @@ def test_kzg_commit_trapdoor_srs(gpu):
     digest = jac_to_affine(c, 1, t.msm(ff.pack_elements(p, c.r, c.fr_limbs)))
     assert digest == ec.scalar_mul(ff.Fp(c.p), ntt.poly_eval(c.r, p, tau), c.g1)
     t.free()
+
+
+@pytest.mark.parametrize("c", [CURVES["bn254"], CURVES["bls12-381"], CURVES["bw6-761"]], ids=lambda c: c.name)
+def test_scans_eval_division(gpu, c):
+    rng = random.Random(41)
+    r, L = c.r, c.fr_limbs
+    pe = lambda v: ff.pack_elements(v, r, L)
+    for n in (1, 5, 1024, 1025, 5000):          # below / at / across block boundaries (1024 per block)
+        v = [rng.randrange(1, r) for _ in range(n)]
+        for op, f, ident in ((gpu.SCAN_PRODUCT, lambda a, b: a * b % r, 1), (gpu.SCAN_SUM, lambda a, b: (a + b) % r, 0)):
+            for excl in (False, True):
+                d = dev(pe(v))
+                gpu.vec_scan(0, c.curve_id, op, d, n, exclusive=excl)
+                gpu.sync(0)
+                acc, want = ident, []
+                for x in v:
+                    if excl:
+                        want.append(acc)
+                    acc = f(acc, x)
+                    if not excl:
+                        want.append(acc)
+                assert ff.unpack_elements(host(d, L), r, L) == want, (c.name, n, op, excl)
+        # Horner evaluation and division by (X - z)
+        x = rng.randrange(r)
+        d = dev(pe(v))
+        assert ff.unpack_elements(gpu.poly_eval(0, c.curve_id, d, n, pe([x])), r, L)[0] == ntt.poly_eval(r, v, x)
+        for z in (x, 0):
+            d = dev(pe(v))
+            rem = ff.unpack_elements(gpu.poly_div_by_linear(0, c.curve_id, d, n, pe([z])), r, L)[0]
+            q, want_rem = plonk.div_by_linear(r, v, z)
+            assert rem == want_rem
+            assert ff.unpack_elements(host(d, L), r, L) == q + [0]
+
+
+@pytest.mark.parametrize("c", [CURVES["bn254"], CURVES["bls12-381"]], ids=lambda c: c.name)
+def test_build_z_grand_product(gpu, c):
+    """iop.BuildRatioCopyConstraint on device vs the oracle; for a permutation that really links equal
+    wires the product telescopes back to 1 (Z[n-1] * ratio[n-1] = 1)."""
+    rng = random.Random(43)
+    r, L = c.r, c.fr_limbs
+    logn = 7
+    n = 1 << logn
+    dom0 = ntt.Domain(c, n)
+    pe = lambda v: ff.pack_elements(v, r, L)
+    # wires: 3n slots; build a random permutation made of cycles and assign equal values along each cycle
+    slots = list(range(3 * n))
+    rng.shuffle(slots)
+    perm = list(range(3 * n))
+    vals = [0] * (3 * n)
+    i = 0
+    while i < 3 * n:
+        k = min(rng.choice((1, 1, 2, 3, 5)), 3 * n - i)
+        cyc = slots[i:i + k]
+        v = rng.randrange(r)
+        for a, b in zip(cyc, cyc[1:] + cyc[:1]):
+            perm[a] = b
+            vals[a] = v
+        i += k
+    l, rr, o = vals[:n], vals[n:2 * n], vals[2 * n:]
+    beta, gamma = rng.randrange(r), rng.randrange(r)
+    want = plonk.build_ratio_copy_constraint(c, dom0, l, rr, o, perm, beta, gamma)
+    d0 = gpu.Domain(c.curve_id, logn)
+    dz = torch.zeros(n * L, dtype=torch.int64, device="cuda")
+    dperm = torch.tensor(perm, dtype=torch.int64, device="cuda")
+    gpu.plonk_build_z(d0, dev(pe(l)), dev(pe(rr)), dev(pe(o)), dperm, pe([beta]), pe([gamma]), dz)
+    gpu.sync(0)
+    got = ff.unpack_elements(host(dz, L), r, L)
+    assert got == want
+    # telescoping: the last ratio brings the product back to one
+    supp = plonk.support_permutation(c, dom0)
+    num = den = 1
+    for j, f in enumerate((l, rr, o)):
+        num = num * ((f[n - 1] + beta * supp[j * n + n - 1] + gamma) % r) % r
+        den = den * ((f[n - 1] + beta * supp[perm[j * n + n - 1]] + gamma) % r) % r
+    assert got[n - 1] * num % r * pow(den, -1, r) % r == 1
+    d0.free()
