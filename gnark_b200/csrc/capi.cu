@@ -85,11 +85,11 @@ void msm_tuning(size_t n, int nwin, int c, int precomp, uint32_t* task_len, uint
   // enough tasks to fill the GPU (~150k), but no more than ~8 partial sums per bucket on average
   // (each partial costs the combine kernel one serial XYZZ addition)
   const size_t buckets = (precomp ? (size_t)1 : (size_t)nwin) << (c - 1);
-  size_t tl = m / 150000;
+  size_t tl = m / 300000;
   const size_t per_bucket = (m / buckets + 7) / 8;
   if (per_bucket > tl) tl = per_bucket;
   if (tl < 8) tl = 8;
-  if (tl > 128) tl = 128;
+  if (tl > 64) tl = 64;   // 128 measured slower at 2^20 (fewer, longer tasks: wave quantisation)
   *task_len = (uint32_t)env_int("GB200_MSM_TASK_LEN", (int)tl);
   *chunk = (uint32_t)env_int("GB200_MSM_CHUNK", c >= 12 ? 8 : 4);
 }

@@ -35,10 +35,11 @@ struct MsmInst {
     return msm_enqueue<Fr, F>(st, pl, reinterpret_cast<const Affine<F>*>(d_table),
                               reinterpret_cast<const Fr*>(d_scalars), reinterpret_cast<Jacobian<F>*>(d_out_jac), ws, L, ev, tail, fork_ev, fmt52);
   }
+  // d_table holds the n bases in slab 0 already; slabs 1.. are filled in place
   static cudaError_t precompute(cudaStream_t st, uint32_t n, int nwin, int c, void* d_table) {
     if (n == 0 || nwin <= 1) return cudaSuccess;
-    k_msm_precompute<F><<<(n + 127) / 128, 128, 0, st>>>(n, nwin, c, reinterpret_cast<Affine<F>*>(d_table));
-    return cudaGetLastError();
+    Affine<F>* t = reinterpret_cast<Affine<F>*>(d_table);
+    return msm_precompute_enqueue<F, Affine<F>, ConvIdentity<F>>(st, n, nwin, c, t, t);
   }
   static size_t affine52_bytes() {
     if constexpr (F52Traits<F>::ok) return sizeof(Affine52<typename F52Traits<F>::P52>);
@@ -47,10 +48,8 @@ struct MsmInst {
   static cudaError_t precompute52(cudaStream_t st, uint32_t n, int nwin, int c, const void* d_src, void* d_table52) {
     if constexpr (F52Traits<F>::ok) {
       using P52 = typename F52Traits<F>::P52;
-      if (n == 0) return cudaSuccess;
-      k_msm_precompute52<F, P52><<<(n + 127) / 128, 128, 0, st>>>(n, nwin, c, reinterpret_cast<const Affine<F>*>(d_src),
-                                                                  reinterpret_cast<Affine52<P52>*>(d_table52));
-      return cudaGetLastError();
+      return msm_precompute_enqueue<F, Affine52<P52>, ConvTo52<F, P52>>(st, n, nwin, c, reinterpret_cast<const Affine<F>*>(d_src),
+                                                                      reinterpret_cast<Affine52<P52>*>(d_table52));
     } else {
       return cudaErrorNotSupported;
     }

@@ -94,21 +94,6 @@ __global__ void __launch_bounds__(128) k_msm_accumulate52(MsmPlan pl, const Affi
   partial[t] = msm_accumulate_range52<P52, F>(table, svals, begin, end);
 }
 
-// table build for the FP64-pipe path: slab w holds 2^(c*w) * P_i as Affine52
-template <class F, class P52>
-__global__ void __launch_bounds__(128) k_msm_precompute52(uint32_t n, int nwin, int c, const Affine<F>* __restrict__ src,
-                                                          Affine52<P52>* __restrict__ table) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const Affine<F> p0 = src[i];
-  table[i] = affine_to_52<P52, F>(p0);
-  XYZZ<F> q = XYZZ<F>::from_affine(p0);
-  for (int w = 1; w < nwin; w++) {
-    for (int k = 0; k < c; k++) q.dbl();
-    table[(size_t)w * n + i] = affine_to_52<P52, F>(q.to_affine());
-  }
-}
-
 // one thread per bucket: sum of its task partials.  Buckets with more than MSM_HEAVY partials
 // (skewed witnesses: many equal small scalars; a short top window) are queued for the
 // block-cooperative kernel below instead of being summed serially.
@@ -212,16 +197,71 @@ __global__ void k_msm_finish(int nsets, int c, const XYZZ<F>* __restrict__ set_s
   }
 }
 
-// table precompute: slab w holds 2^(c*w) * P_i   (built once per table upload)
+// table precompute (built once per table upload): slab w holds 2^(c*w) * P_i.
+// pass 1: doubling chains, XYZZ results to a scratch buffer [w-1][chunk];
+// pass 2: one inversion per point (Montgomery's trick over its nwin-1 outputs), affine results.
+constexpr int MSM_MAX_WINDOWS = 64;
 template <class F>
-__global__ void __launch_bounds__(128) k_msm_precompute(uint32_t n, int nwin, int c, Affine<F>* __restrict__ table) {
+__global__ void __launch_bounds__(128) k_msm_precompute_dbl(uint32_t cnt, int nwin, int c, const Affine<F>* __restrict__ src,
+                                                            XYZZ<F>* __restrict__ tmp) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  XYZZ<F> q = XYZZ<F>::from_affine(table[i]);
+  if (i >= cnt) return;
+  XYZZ<F> q = XYZZ<F>::from_affine(src[i]);
   for (int w = 1; w < nwin; w++) {
     for (int k = 0; k < c; k++) q.dbl();
-    table[(size_t)w * n + i] = q.to_affine();
+    tmp[(size_t)(w - 1) * cnt + i] = q;
   }
+}
+// OUT = Affine<F> (32-bit layout) or Affine52<P52>; conv(affine) -> OUT
+template <class F, class OUT, class CONV>
+__global__ void __launch_bounds__(128) k_msm_precompute_affine(uint32_t cnt, uint32_t n, uint32_t first, int nwin,
+                                                               const Affine<F>* __restrict__ src,
+                                                               const XYZZ<F>* __restrict__ tmp, OUT* __restrict__ table,
+                                                               CONV conv) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= cnt) return;
+  table[first + i] = conv(src[i]);
+  F pre[MSM_MAX_WINDOWS];
+  F acc = F::one();
+  for (int w = 1; w < nwin; w++) {
+    pre[w] = acc;
+    const F zzz = tmp[(size_t)(w - 1) * cnt + i].zzz;
+    if (!zzz.is_zero()) acc = acc * zzz;
+  }
+  F inv = acc.inverse();
+  for (int w = nwin - 1; w >= 1; w--) {
+    const XYZZ<F> q = tmp[(size_t)(w - 1) * cnt + i];
+    Affine<F> a = Affine<F>::inf();
+    if (!q.zzz.is_zero()) {
+      const F zi3 = inv * pre[w];       // 1 / zzz_w
+      inv = inv * q.zzz;
+      const F zi2 = (zi3 * q.zz).sqr(); // (zz/zzz)^2 = 1 / zz
+      a.x = q.x * zi2;
+      a.y = q.y * zi3;
+    }
+    table[(size_t)w * n + first + i] = conv(a);
+  }
+}
+template <class F> struct ConvIdentity { __device__ Affine<F> operator()(const Affine<F>& a) const { return a; } };
+template <class F, class P52> struct ConvTo52 { __device__ Affine52<P52> operator()(const Affine<F>& a) const { return affine_to_52<P52, F>(a); } };
+
+// d_src: n affine points; d_table: [nwin][n] entries of OUT
+template <class F, class OUT, class CONV>
+cudaError_t msm_precompute_enqueue(cudaStream_t st, uint32_t n, int nwin, int c, const Affine<F>* d_src, OUT* d_table) {
+  if (n == 0) return cudaSuccess;
+  if (nwin > MSM_MAX_WINDOWS) return cudaErrorInvalidValue;
+  const uint32_t chunk = n < (1u << 18) ? n : (1u << 18);
+  XYZZ<F>* tmp = nullptr;
+  if (nwin > 1) GB_CUDA_TRY(cudaMallocAsync(&tmp, (size_t)(nwin - 1) * chunk * sizeof(XYZZ<F>), st));
+  for (uint32_t first = 0; first < n; first += chunk) {
+    const uint32_t cnt = n - first < chunk ? n - first : chunk;
+    if (nwin > 1) k_msm_precompute_dbl<F><<<(cnt + 127) / 128, 128, 0, st>>>(cnt, nwin, c, d_src + first, tmp);
+    k_msm_precompute_affine<F, OUT, CONV><<<(cnt + 127) / 128, 128, 0, st>>>(cnt, n, first, nwin, d_src + first, tmp,
+                                                                          d_table, CONV());
+  }
+  GB_CUDA_TRY(cudaGetLastError());
+  if (tmp) GB_CUDA_TRY(cudaFreeAsync(tmp, st));
+  return cudaSuccess;
 }
 
 // ---------------------------------------------------------------------------
