@@ -249,6 +249,7 @@ int32_t b200_table_upload(int32_t dev, int32_t curve, int32_t group, const void*
   std::unique_ptr<b200_table_s> t(new b200_table_s());
   t->dev = dev; t->curve = curve; t->group = group; t->n = n; t->ops = ops;
   t->c = msm_window_for(n ? n : 1);
+  while (msm_num_windows(ops->scalar_bits, t->c) > 64) t->c++;   // MSM_MAX_WINDOWS of the table precompute
   t->nwin = msm_num_windows(ops->scalar_bits, t->c);
   t->precomp = (flags & B200_TABLE_PRECOMP) ? 1 : 0;
   if (env_int("GB200_MSM_PRECOMP", -1) >= 0) t->precomp = env_int("GB200_MSM_PRECOMP", 0) ? 1 : 0;
