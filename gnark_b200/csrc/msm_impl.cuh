@@ -46,7 +46,7 @@ static __global__ void k_msm_task_counts(const uint32_t* __restrict__ off, uint3
 
 // one thread per task: partial[t] = sum of <= task_len consecutive entries of one bucket
 template <class F>
-__global__ void __launch_bounds__(128, 4) k_msm_accumulate(MsmPlan pl, const Affine<F>* __restrict__ table,
+__global__ void __launch_bounds__(128) k_msm_accumulate(MsmPlan pl, const Affine<F>* __restrict__ table,
                                                         const uint32_t* __restrict__ svals,
                                                         const uint32_t* __restrict__ off,
                                                         const uint32_t* __restrict__ task_off,
