@@ -511,6 +511,16 @@ int32_t b200_vec_batch_invert(int32_t dev, int32_t curve, void* data, size_t n) 
   GUARD_END
 }
 
+int32_t b200_vec_axpy(int32_t dev, int32_t curve, void* y, const void* a, const void* x, size_t n) {
+  GUARD_BEGIN
+  DeviceCtx* ctx; int32_t rc = device_ctx(dev, &ctx); if (rc) return rc;
+  const NttOps* ops = get_ntt_ops(curve);
+  if (!ops) return set_error("vec_axpy: unsupported curve");
+  if (!a || (n && (!y || !x))) return set_error("vec_axpy: null argument");
+  CK(ops->axpy(ctx->stream, y, a, x, n));
+  return 0;
+  GUARD_END
+}
 int32_t b200_vec_scan(int32_t dev, int32_t curve, int32_t op, void* data, size_t n, int32_t exclusive) {
   GUARD_BEGIN
   DeviceCtx* ctx; int32_t rc = device_ctx(dev, &ctx); if (rc) return rc;

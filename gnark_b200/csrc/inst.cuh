@@ -90,6 +90,11 @@ __global__ void __launch_bounds__(256) k_scale_powers(const Fr* __restrict__ pw,
   d[k] = d[k] * acc;
 }
 template <class Fr>
+__global__ void __launch_bounds__(256) k_axpy(Fr* __restrict__ y, Fr a, const Fr* __restrict__ x, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = y[i] + a * x[i];
+}
+template <class Fr>
 __global__ void __launch_bounds__(256) k_gather(Fr* __restrict__ out, const Fr* __restrict__ src,
                                                 const uint32_t* __restrict__ idx, size_t n) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -204,6 +209,11 @@ struct NttInst {
     GB_CUDA_TRY(cudaFreeAsync(d_tab, st));
     return cudaStreamSynchronize(st);  // tab is a stack buffer
   }
+  static cudaError_t axpy(cudaStream_t st, void* y, const void* a, const void* x, size_t n) {
+    if (!n) return cudaSuccess;
+    k_axpy<Fr><<<(unsigned)((n + 255) / 256), 256, 0, st>>>((Fr*)y, *(const Fr*)a, (const Fr*)x, n);
+    return cudaGetLastError();
+  }
   static cudaError_t scan(cudaStream_t st, int op, void* d, size_t n, int exclusive) {
     return op == 0 ? scan_enqueue<Fr, 0>(st, (Fr*)d, n, exclusive != 0) : scan_enqueue<Fr, 1>(st, (Fr*)d, n, exclusive != 0);
   }
@@ -288,7 +298,7 @@ struct NttInst {
   static const NttOps* ops() {
     static const NttOps o = {sizeof(Fr), Fr::Params::TWO_ADICITY, &domain_new, &domain_free, &domain_bytes, &ntt,
                              &compute_h, &vec_op, &bit_reverse, &scale_powers, &batch_invert, &plonk_coset,
-                             &plonk_divide_by_zh, &scan, &plonk_build_z, &poly_eval, &poly_div_linear, &gather};
+                             &plonk_divide_by_zh, &axpy, &scan, &plonk_build_z, &poly_eval, &poly_div_linear, &gather};
     return &o;
   }
 };

@@ -44,6 +44,7 @@ struct NttOps {
   cudaError_t (*plonk_coset)(cudaStream_t st, void* dom0, const void* big_coset_gen, const void* big_gen,
                              const void* args);
   cudaError_t (*plonk_divide_by_zh)(cudaStream_t st, void* dom1, uint32_t log_n0, void* d_data);
+  cudaError_t (*axpy)(cudaStream_t st, void* d_y, const void* a_mont, const void* d_x, size_t n);   // y += a*x
   // O(n) scans (plonk.cuh)
   cudaError_t (*scan)(cudaStream_t st, int op /*0 product, 1 sum*/, void* d_data, size_t n, int exclusive);
   cudaError_t (*plonk_build_z)(cudaStream_t st, void* dom0, const void* d_l, const void* d_r, const void* d_o,

@@ -30,7 +30,7 @@ EXPORTS = [
     "b200_msm_async", "b200_msm_pipelined", "b200_msm_join", "b200_msm_profile", "b200_ntt_domain_new", "b200_ntt_domain_free", "b200_ntt", "b200_ntt_async",
     "b200_groth16_compute_h", "b200_vec_op", "b200_vec_bit_reverse", "b200_vec_scale_powers",
     "b200_vec_batch_invert", "b200_plonk_constraints_coset", "b200_plonk_divide_by_zh",
-    "b200_vec_scan", "b200_plonk_build_z", "b200_poly_eval", "b200_poly_div_by_linear",
+    "b200_vec_axpy", "b200_vec_scan", "b200_plonk_build_z", "b200_poly_eval", "b200_poly_div_by_linear",
     "b200_point_add_jac", "b200_point_to_affine", "b200_groth16_pk_load", "b200_groth16_pk_free", "b200_groth16_prove", "b200_groth16_msms",
     "b200_groth16_assemble",
 ]
@@ -118,6 +118,7 @@ def load(path: str = None):
     lib.b200_vec_batch_invert.argtypes = [i32, i32, vp, sz]
     lib.b200_plonk_constraints_coset.argtypes = [vp, vp, vp, vp]
     lib.b200_plonk_divide_by_zh.argtypes = [vp, u32, vp]
+    lib.b200_vec_axpy.argtypes = [i32, i32, vp, vp, vp, sz]
     lib.b200_vec_scan.argtypes = [i32, i32, i32, vp, sz, i32]
     lib.b200_plonk_build_z.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
     lib.b200_poly_eval.argtypes = [i32, i32, vp, sz, vp, vp]
@@ -363,3 +364,8 @@ def poly_div_by_linear(dev, curve, d_coeffs, n, z) -> np.ndarray:
     out = np.zeros(CURVE_SHAPES[curve][0], dtype=np.uint64)
     check(load().b200_poly_div_by_linear(dev, curve, ptr(d_coeffs), n, ptr(z), ptr(out)))
     return out
+
+
+def vec_axpy(dev, curve, d_y, a_mont, d_x, n):
+    """y += a * x on device vectors"""
+    check(load().b200_vec_axpy(dev, curve, ptr(d_y), ptr(a_mont), ptr(d_x), n))

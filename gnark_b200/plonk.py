@@ -1,0 +1,275 @@
+"""Device-resident PLONK prover: host orchestration over the C ABI (include/gnark_b200.h).
+
+The reference has no accelerated PLONK; this is the twin of the CPU prover
+backend/plonk/bn254/prove.go, stage by stage, with every polynomial kept in HBM between the
+MSM / NTT stages and only digests, challenges and opened values crossing to the host - the four
+mandatory sync points of the Fiat-Shamir transcript.
+
+    pk = ProvingKey.from_trace(curve, log2n, ql, qr, qm, qo, qk, perm, srs_canonical)   # setupDevicePointers
+    proof = Prove(pk, l, r, o, challenges)
+
+Stages (reference line numbers in backend/plonk/bn254/prove.go):
+  commitToLRO :404-489           canonical forms (iNTT), blinding :1211-1220, 3 MSMs on the SRS
+  buildRatioCopyConstraint :635  b200_plonk_build_z, commit Z
+  computeQuotient :558-633       48 coset NTTs + fused constraint kernel x4 :841-1123, divideByZH :1287,
+                                 commitToQuotient :1263-1282 (3 MSMs of n+2)
+  openZ :670-687, computeLinearizedPolynomial :724-794 (+ :1366-1487), batchOpening :796-837
+
+Digests are computed from canonical coefficients against the canonical SRS: [p + b(X^n - 1)] is one MSM of
+n + deg(b) + 1 points, the same group element the reference obtains from its Lagrange-SRS MSM plus
+commitBlindingFactor (:1223-1236).  BSB22 commitments and StatisticalZK are not supported.
+
+Challenges and blinding coefficients are taken from the caller (`Challenges`): the Fiat-Shamir transcript
+encoding is gnark-crypto's (absent here); a Go shim derives them exactly as prove.go:492-555 does and passes
+them in, which also makes every intermediate result reproducible (parity tests).
+Host language note: the reference's prover is Go orchestrating gnark-crypto calls; with no Go toolchain in this
+image the orchestration is Python over the same C ABI a Go shim would call.
+"""
+
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+import numpy as np
+
+from . import lib as _lib
+
+_FR_MODULUS = {
+    _lib.BN254: 0x30644e72e131a029b85045b68181585d2833e84879b9709143e1f593f0000001,
+    _lib.BLS12_381: 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001,
+    _lib.BLS12_377: 0x12ab655e9a2ca55660b44d1e5c37b00159aa76fed00000010a11800000000001,
+    _lib.BW6_761: 0x1ae3a4617c510eac63b05c06ca1493b1a22d9f300f5138f1ef3622fba094800170b5d44300000008508c00000000001,
+}
+# gnark-crypto fft.Domain constants (2-adicity, root of unity, FrMultiplicativeGen) - as params_gen.cuh
+_FR_DOMAIN = {
+    _lib.BN254: (28, 19103219067921713944291392827692070036145651957329286315305642004821462161904, 5),
+    _lib.BLS12_381: (32, 10238227357739495823651030575849232062558860180284477541189508159991286009131, 7),
+    _lib.BLS12_377: (47, 8065159656716812877374967518403273466521432693661810619979959746626482506078, 22),
+    _lib.BW6_761: (46, 32863578547254505029601261939868325669770508939375122462904745766352256812585773382134936404344547323199885654433, 15),
+}
+
+
+@dataclass
+class Challenges:
+    gamma: int
+    beta: int
+    alpha: int
+    zeta: int
+    v: int
+    bl: List[int] = field(default_factory=lambda: [0, 0])
+    br: List[int] = field(default_factory=lambda: [0, 0])
+    bo: List[int] = field(default_factory=lambda: [0, 0])
+    bz: List[int] = field(default_factory=lambda: [0, 0, 0])
+
+
+@dataclass
+class Proof:
+    """backend/plonk/bn254/prove.go:77-96.  Digests are Jacobian points in gnark layout (uint64 limbs)."""
+    LRO: List[np.ndarray]
+    Z: np.ndarray
+    H: List[np.ndarray]
+    LinearizedDigest: np.ndarray
+    BatchedProofH: np.ndarray
+    BatchedClaimedValues: List[int]
+    ZShiftedOpeningH: np.ndarray
+    ZShiftedClaimedValue: int
+    timings_ms: dict = field(default_factory=dict)
+
+
+class _Fr:
+    """tiny host-side helper: canonical int <-> fr.Element limbs (Montgomery)"""
+
+    def __init__(self, curve):
+        self.q = _FR_MODULUS[curve]
+        self.limbs = _lib.CURVE_SHAPES[curve][0]
+        self.R = 1 << (64 * self.limbs)
+        self.Rinv = pow(self.R, -1, self.q)
+
+    def enc(self, x: int) -> np.ndarray:
+        v = (x % self.q) * self.R % self.q
+        return np.frombuffer(v.to_bytes(8 * self.limbs, "little"), dtype=np.uint64).copy()
+
+    def enc_many(self, xs) -> np.ndarray:
+        return np.concatenate([self.enc(x) for x in xs]) if len(xs) else np.zeros(0, dtype=np.uint64)
+
+    def dec(self, a) -> int:
+        return int.from_bytes(np.ascontiguousarray(a, dtype=np.uint64).tobytes(), "little") * self.Rinv % self.q
+
+
+class ProvingKey:
+    """Device-resident PLONK proving key (backend/plonk/bn254/setup.go:88-93 ProvingKey + Trace :67-86)."""
+
+    def __init__(self, curve: int, log2n: int, dev: int = 0):
+        import torch
+        self.torch = torch
+        self.curve, self.log2n, self.dev = curve, log2n, dev
+        self.n = 1 << log2n
+        self.fr = _Fr(curve)
+        s, root, g = _FR_DOMAIN[curve]
+        q = self.fr.q
+        self.g = g
+        self.w = pow(root, 1 << (s - log2n), q)                 # domain0.Generator
+        self.w4 = pow(root, 1 << (s - log2n - 2), q)            # domain1.Generator
+        # domain0 handles for the four cosets g * w4^i (computeNumerator :943-948) and the big domain
+        self.dom0 = [_lib.Domain(curve, log2n, dev=dev, coset_gen=self.fr.enc(g * pow(self.w4, i, q) % q)) for i in range(4)]
+        self.dom1 = _lib.Domain(curve, log2n + 2, dev=dev)
+        self.polys = {}        # name -> device tensor, CANONICAL coefficients in BIT-REVERSED layout (n)
+        self.canon = {}        # name -> canonical, regular layout (for evaluations / linearised polynomial)
+        self.perm = None
+        self.srs = None
+
+    def _dev(self, arr):
+        return self.torch.from_numpy(np.ascontiguousarray(arr).view(np.int64)).to(f"cuda:{self.dev}")
+
+    @classmethod
+    def from_trace(cls, curve, log2n, ql, qr, qm, qo, qk, perm, srs_canonical, dev=0):
+        """ql..qk: (n, limbs) uint64 Lagrange/regular (Montgomery); perm: int64[3n]; srs_canonical: (n+3) G1Affine."""
+        pk = cls(curve, log2n, dev)
+        t = pk.torch
+        n, L, q = pk.n, pk.fr.limbs, pk.fr.q
+        pk.perm = t.from_numpy(np.ascontiguousarray(perm, dtype=np.int64)).to(f"cuda:{dev}")
+        # sigma polynomials from the permutation: s_j[i] = supp[perm[j n + i]] (setup.go:289-392)
+        w_pows = [1] * n
+        for i in range(1, n):
+            w_pows[i] = w_pows[i - 1] * pk.w % q
+        supp = w_pows + [pk.g * x % q for x in w_pows] + [pk.g * pk.g * x % q for x in w_pows]
+        perm_l = [int(x) for x in perm]
+        lag = {"ql": ql, "qr": qr, "qm": qm, "qo": qo, "qk": qk}
+        for j, name in enumerate(("s1", "s2", "s3")):
+            lag[name] = pk.fr.enc_many([supp[perm_l[j * n + i]] for i in range(n)]).reshape(n, L)
+        for name, v in lag.items():
+            d = pk._dev(v)
+            pk.dom0[0].ntt_async(d, inverse=True, decimation=_lib.DIF)       # Lagrange/regular -> canonical/bit-reversed
+            pk.polys[name] = d
+            c = d.clone()
+            _lib.vec_bit_reverse(dev, curve, c, log2n)
+            pk.canon[name] = c
+        pk.srs = _lib.Table(curve, 1, srs_canonical, dev=dev, precomp=True)
+        _lib.sync(dev)
+        return pk
+
+    def free(self):
+        for d in self.dom0:
+            d.free()
+        self.dom1.free()
+        if self.srs is not None:
+            self.srs.free()
+
+
+def Prove(pk: ProvingKey, l, r, o, ch: Challenges) -> Proof:
+    """l, r, o: (n, limbs) uint64 Lagrange/regular solution vectors (SparseR1CSSolution{L,R,O},
+    constraint/bn254/system.go:208-210) on the host."""
+    import time
+    t = pk.torch
+    curve, dev, n, logn = pk.curve, pk.dev, pk.n, pk.log2n
+    fr = pk.fr
+    q, L = fr.q, fr.limbs
+    E = fr.enc
+    tm = {}
+    t_start = time.perf_counter()
+
+    def lap(name):
+        _lib.sync(dev)
+        nonlocal t_start
+        now = time.perf_counter()
+        tm[name] = tm.get(name, 0.0) + 1e3 * (now - t_start)
+        t_start = now
+
+    def commit(d_coeffs, count):
+        return pk.srs.msm(d_coeffs, n=count, on_device=True)
+
+    def canonical_blinded(d_lagrange, b):
+        """Lagrange/regular -> (canonical bit-reversed copy for the coset NTTs, blinded canonical regular [n+len(b)])"""
+        cb = d_lagrange.clone()
+        pk.dom0[0].ntt_async(cb, inverse=True, decimation=_lib.DIF)
+        reg = t.zeros((n + len(b)) * L, dtype=t.int64, device=cb.device)
+        reg[:n * L] = cb
+        _lib.vec_bit_reverse(dev, curve, reg, logn)
+        # p + b (X^n - 1): low coefficients minus b, then b on top (getBlindedCoefficients :1211-1220)
+        low = reg[:len(b) * L].cpu().numpy().view(np.uint64).reshape(len(b), L)
+        patched = fr.enc_many([(fr.dec(low[i]) - b[i]) % q for i in range(len(b))])
+        reg[:len(b) * L] = t.from_numpy(patched.view(np.int64)).to(reg.device)
+        reg[n * L:] = t.from_numpy(fr.enc_many(b).view(np.int64)).to(reg.device)
+        return cb, reg
+
+    # ---- commitToLRO ----------------------------------------------------------------------------
+    d_l, d_r, d_o = (pk._dev(v) for v in (l, r, o))
+    cb, blinded = {}, {}
+    for name, d, b in (("l", d_l, ch.bl), ("r", d_r, ch.br), ("o", d_o, ch.bo)):
+        cb[name], blinded[name] = canonical_blinded(d, b)
+    lro = [commit(blinded[k], n + 2) for k in ("l", "r", "o")]
+    lap("commit LRO")
+
+    # ---- buildRatioCopyConstraint + commit Z ------------------------------------------------------
+    d_z = t.zeros(n * L, dtype=t.int64, device=d_l.device)
+    _lib.plonk_build_z(pk.dom0[0], d_l, d_r, d_o, pk.perm, E(ch.beta), E(ch.gamma), d_z)
+    cb["z"], blinded["z"] = canonical_blinded(d_z, ch.bz)
+    z_digest = commit(blinded["z"], n + 3)
+    lap("build + commit Z")
+
+    # ---- computeQuotient: numerator on the 4 cosets, divide by Z_H, commit h1, h2, h3 --------------
+    cres = t.zeros(4 * n * L, dtype=t.int64, device=d_l.device)
+    names = ("l", "r", "o", "z", "s1", "s2", "s3", "ql", "qr", "qm", "qo", "qk")
+    blind = {"l": fr.enc_many(ch.bl), "r": fr.enc_many(ch.br), "o": fr.enc_many(ch.bo), "z": fr.enc_many(ch.bz)}
+    g_m, w4_m = E(pk.g), E(pk.w4)
+    a_m, b_m, c_m = E(ch.alpha), E(ch.beta), E(ch.gamma)
+    for i in range(4):
+        on_coset = {}
+        for name in names:
+            src = cb[name] if name in cb else pk.polys[name]
+            d = src.clone()
+            pk.dom0[i].ntt_async(d, inverse=False, decimation=_lib.DIT, on_coset=True)   # canonical/bit-rev -> coset i, regular
+            on_coset[name] = d
+        _lib.plonk_constraints_coset(pk.dom0[i], g_m, w4_m, on_coset, a_m, b_m, c_m, blind, i, 4, cres)
+        _lib.sync(dev)
+        del on_coset
+    _lib.plonk_divide_by_zh(pk.dom1, logn, cres)       # -> h canonical regular (4n)
+    h = cres
+    H = [commit(h[k * (n + 2) * L:(k + 1) * (n + 2) * L], n + 2) for k in range(3)]
+    lap("quotient + commit H")
+
+    # ---- openZ, evaluations at zeta ------------------------------------------------------------
+    zeta = ch.zeta % q
+    wz = zeta * pk.w % q
+    ev = lambda d, cnt, x: fr.dec(_lib.poly_eval(dev, curve, d, cnt, E(x)))
+    zu = ev(blinded["z"], n + 3, wz)
+    lz, rz, oz = (ev(blinded[k], n + 2, zeta) for k in ("l", "r", "o"))
+    s1z, s2z = ev(pk.canon["s1"], n, zeta), ev(pk.canon["s2"], n, zeta)
+
+    # ---- innerComputeLinearizedPoly :1366-1487 ------------------------------------------------------
+    alpha, beta, gamma = ch.alpha % q, ch.beta % q, ch.gamma % q
+    rl = rz * lz % q
+    c1 = (lz + beta * s1z + gamma) % q * ((rz + beta * s2z + gamma) % q) % q * zu % q * beta % q * alpha % q
+    uz, uuz = zeta * pk.g % q, zeta * pk.g % q * pk.g % q
+    c2 = (-(lz + beta * zeta + gamma) % q * ((rz + beta * uz + gamma) % q) % q * ((oz + beta * uuz + gamma) % q) % q * alpha) % q
+    zn = pow(zeta, n, q)
+    zn2 = zn * zeta % q * zeta % q
+    zh = (zn - 1) % q
+    a2l1 = zh * pow((zeta - 1) % q, -1, q) % q * alpha % q * alpha % q * pow(n, -1, q) % q
+    lin = t.zeros((n + 3) * L, dtype=t.int64, device=d_l.device)
+    axpy = lambda y, a, x, cnt: _lib.vec_axpy(dev, curve, y, E(a), x, cnt)
+    axpy(lin, (c2 + a2l1) % q, blinded["z"], n + 3)
+    for coef, name in ((c1, "s3"), (rl, "qm"), (lz, "ql"), (rz, "qr"), (oz, "qo"), (1, "qk")):
+        axpy(lin, coef, pk.canon[name], n)
+    for k, coef in enumerate((zh, zh * zn2 % q, zh * zn2 % q * zn2 % q)):
+        axpy(lin, (-coef) % q, h[k * (n + 2) * L:(k + 1) * (n + 2) * L], n + 2)
+    lin_digest = commit(lin, n + 3)
+    lap("linearised polynomial")
+
+    # ---- batchOpening :796-837 (fold with powers of v, divide by X - zeta) and the Z opening ---------
+    to_open = [(lin, n + 3), (blinded["l"], n + 2), (blinded["r"], n + 2), (blinded["o"], n + 2),
+               (pk.canon["s1"], n), (pk.canon["s2"], n)]
+    claimed = [ev(d, cnt, zeta) for d, cnt in to_open]
+    fold = t.zeros((n + 3) * L, dtype=t.int64, device=d_l.device)
+    vp = 1
+    for d, cnt in to_open:
+        axpy(fold, vp, d, cnt)
+        vp = vp * ch.v % q
+    _lib.poly_div_by_linear(dev, curve, fold, n + 3, E(zeta))
+    batch_h = commit(fold, n + 2)
+    zq = blinded["z"].clone()
+    zu_check = fr.dec(_lib.poly_div_by_linear(dev, curve, zq, n + 3, E(wz)))
+    assert zu_check == zu
+    z_open_h = commit(zq, n + 2)
+    lap("openings")
+    return Proof(LRO=lro, Z=z_digest, H=H, LinearizedDigest=lin_digest, BatchedProofH=batch_h,
+                 BatchedClaimedValues=claimed, ZShiftedOpeningH=z_open_h, ZShiftedClaimedValue=zu, timings_ms=tm)

@@ -144,6 +144,8 @@ int32_t b200_vec_scale_powers(int32_t dev, int32_t curve, void* d_data, size_t n
                               const void* g_mont);
 
 int32_t b200_vec_batch_invert(int32_t dev, int32_t curve, void* d_data, size_t n); /* 0 stays 0 */
+/* y[i] += a * x[i]  (linear combinations: linearised polynomial plonk/bn254/prove.go:1431-1480, opening folds) */
+int32_t b200_vec_axpy(int32_t dev, int32_t curve, void* d_y, const void* a_mont, const void* d_x, size_t n);
 
 /* ---- PLONK quotient building blocks (no accelerated PLONK exists in the reference; these are
  *      the device twins of backend/plonk/bn254/prove.go computeNumerator :841-1123 and

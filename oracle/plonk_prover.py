@@ -1,0 +1,227 @@
+"""PLONK prover restated on big ints, with a trapdoor SRS.  TEST INFRASTRUCTURE ONLY
+(see oracle/params.py header; parity unpinned by the reference).
+
+Follows backend/plonk/bn254/prove.go (no BSB22 commitments, StatisticalZK off):
+  Prove :98-153; blinding polynomials :259-266,1239-1253 (orders 1,1,1,2 :72-75);
+  commitToLRO :404-489 + commitBlindingFactor :1223-1236 (digest of p + b*(X^n - 1));
+  buildRatioCopyConstraint :635-667; computeQuotient :558-633 -> computeNumerator :841-1123,
+  divideByZH :1287-1324, h split h1,h2,h3 of n+2 coefficients :689-722, commitToQuotient :1263-1282;
+  openZ :670-687 (blinded Z at w*zeta); computeLinearizedPolynomial :724-794 +
+  innerComputeLinearizedPoly :1366-1487; batchOpening :796-837.
+
+Randomness (blinding coefficients) and the Fiat-Shamir challenges (gamma, beta, alpha, zeta and the
+KZG folding challenge) are INJECTED: the transcript encoding lives in gnark-crypto (absent), and
+injected values make every intermediate result comparable bit for bit.
+With a known tau every KZG digest is p(tau) * G, so digests are carried as discrete logs and the
+verifier's pairing checks become equalities in Fr (test/unsafekzg pattern).
+The batched opening folds with powers of the challenge: f = sum_i v^i p_i (kzg.BatchOpenSinglePoint
+semantics as relied upon at :827-834).
+"""
+
+from dataclasses import dataclass, field
+from typing import List
+
+from . import plonk
+from .ntt import DIF, Domain, bit_reverse, poly_eval
+
+
+@dataclass
+class Circuit:
+    """Lagrange-form (regular layout) trace on domain0 and the wire permutation
+    (Trace / NewTrace, backend/plonk/bn254/setup.go:67-231,289-392)."""
+    n: int
+    ql: List[int]
+    qr: List[int]
+    qm: List[int]
+    qo: List[int]
+    qk: List[int]           # complete Qk (public inputs folded in, prove.go:349-373)
+    perm: List[int]         # 3n entries
+
+
+@dataclass
+class Challenges:
+    gamma: int
+    beta: int
+    alpha: int
+    zeta: int
+    v: int                  # KZG folding challenge
+    bl: List[int] = field(default_factory=lambda: [0, 0])
+    br: List[int] = field(default_factory=lambda: [0, 0])
+    bo: List[int] = field(default_factory=lambda: [0, 0])
+    bz: List[int] = field(default_factory=lambda: [0, 0, 0])
+
+
+@dataclass
+class Proof:
+    # digests as discrete logs (p(tau))
+    L: int
+    R: int
+    O: int
+    Z: int
+    H: List[int]
+    lin: int
+    batch_opening: int       # [ (f - f(zeta)) / (X - zeta) ]
+    z_opening: int           # [ (Z_b - Z_b(w zeta)) / (X - w zeta) ]
+    claimed: List[int]       # lin(zeta), l(zeta), r(zeta), o(zeta), s1(zeta), s2(zeta)
+    zu: int                  # Z_b(w zeta)
+    # intermediates kept for parity tests
+    h: List[int] = field(default_factory=list)
+    lin_poly: List[int] = field(default_factory=list)
+    z_lagrange: List[int] = field(default_factory=list)
+
+
+def canonical(curve, dom: Domain, lagrange):
+    return bit_reverse(dom.fft_inverse(lagrange, DIF))
+
+
+def blinded(r, n, coeffs, b):
+    """getBlindedCoefficients :1211-1220: p + b*(X^n - 1)."""
+    out = list(coeffs) + list(b)
+    for i, bi in enumerate(b):
+        out[i] = (out[i] - bi) % r
+    return out
+
+
+def sigma_polys(curve, dom0: Domain, perm):
+    supp = plonk.support_permutation(curve, dom0)
+    n = dom0.n
+    return [[supp[perm[j * n + i]] for i in range(n)] for j in range(3)]
+
+
+def prove(curve, circ: Circuit, l, rr, o, ch: Challenges, tau: int) -> Proof:
+    r, n = curve.r, circ.n
+    dom0 = Domain(curve, n)
+    g, w = dom0.coset_gen, dom0.generator
+    ev = lambda p, x: poly_eval(r, p, x)
+    s1, s2, s3 = sigma_polys(curve, dom0, circ.perm)
+    # --- L, R, O
+    cl, cr, co = (canonical(curve, dom0, v) for v in (l, rr, o))
+    lb, rb, ob = blinded(r, n, cl, ch.bl), blinded(r, n, cr, ch.br), blinded(r, n, co, ch.bo)
+    # --- Z
+    z = plonk.build_ratio_copy_constraint(curve, dom0, l, rr, o, circ.perm, ch.beta, ch.gamma)
+    zb = blinded(r, n, canonical(curve, dom0, z), ch.bz)
+    # --- quotient
+    polys = {"l": l, "r": rr, "o": o, "z": z, "s1": s1, "s2": s2, "s3": s3,
+             "ql": circ.ql, "qr": circ.qr, "qm": circ.qm, "qo": circ.qo, "qk": circ.qk}
+    blind = {"l": ch.bl, "r": ch.br, "o": ch.bo, "z": ch.bz}
+    cres = plonk.numerator(curve, n, 4, polys, ch.alpha, ch.beta, ch.gamma, blind)
+    h = plonk.divide_by_zh(curve, n, 4, cres)
+    assert all(x == 0 for x in h[3 * (n + 2):]), "numerator not divisible by X^n - 1: unsatisfied trace"
+    h1, h2, h3 = h[:n + 2], h[n + 2:2 * (n + 2)], h[2 * (n + 2):3 * (n + 2)]
+    # --- openings at zeta
+    zeta = ch.zeta
+    zu = ev(zb, zeta * w % r)
+    lz, rz, oz = ev(lb, zeta), ev(rb, zeta), ev(ob, zeta)
+    cs1, cs2, cs3 = (canonical(curve, dom0, v) for v in (s1, s2, s3))
+    cql, cqr, cqm, cqo, cqk = (canonical(curve, dom0, v) for v in (circ.ql, circ.qr, circ.qm, circ.qo, circ.qk))
+    s1z, s2z = ev(cs1, zeta), ev(cs2, zeta)
+    # innerComputeLinearizedPoly :1366-1487
+    alpha, beta, gamma = ch.alpha, ch.beta, ch.gamma
+    rl = rz * lz % r
+    c1 = (lz + beta * s1z + gamma) % r * ((rz + beta * s2z + gamma) % r) % r * zu % r * beta % r * alpha % r
+    uz, uuz = zeta * g % r, zeta * g % r * g % r
+    c2 = (lz + beta * zeta + gamma) % r * ((rz + beta * uz + gamma) % r) % r * ((oz + beta * uuz + gamma) % r) % r
+    c2 = (-c2 * alpha) % r
+    zn = pow(zeta, n, r)
+    zn2 = zn * zeta % r * zeta % r
+    zh = (zn - 1) % r
+    a2l1 = zh * pow((zeta - 1) % r, -1, r) % r * alpha % r * alpha % r * dom0.cardinality_inv % r
+    lin = []
+    for i in range(len(zb)):
+        t = zb[i] * c2 % r
+        if i < n:
+            t = (t + cs3[i] * c1 + cqm[i] * rl + cql[i] * lz + cqr[i] * rz + cqo[i] * oz + cqk[i]) % r
+        t = (t + zb[i] * a2l1) % r
+        if i < n + 2:
+            t = (t - zh * ((h3[i] * zn2 + h2[i]) % r * zn2 % r + h1[i])) % r
+        lin.append(t)
+    # batchOpening :796-837
+    to_open = [lin, lb, rb, ob, cs1, cs2]
+    claimed = [ev(p, zeta) for p in to_open]
+    size = max(len(p) for p in to_open)
+    f = [0] * size
+    vp = 1
+    for p in to_open:
+        for i, c in enumerate(p):
+            f[i] = (f[i] + vp * c) % r
+        vp = vp * ch.v % r
+    qf, _ = plonk.div_by_linear(r, f, zeta)
+    qz, zu2 = plonk.div_by_linear(r, zb, zeta * w % r)
+    assert zu2 == zu
+    com = lambda p: ev(p, tau)
+    return Proof(L=com(lb), R=com(rb), O=com(ob), Z=com(zb), H=[com(h1), com(h2), com(h3)], lin=com(lin),
+                 batch_opening=com(qf), z_opening=com(qz), claimed=claimed, zu=zu, h=h, lin_poly=lin, z_lagrange=z)
+
+
+def verify(curve, circ: Circuit, proof: Proof, ch: Challenges, tau: int) -> bool:
+    """The verifier's checks (backend/plonk/bn254/verify.go:38-320) in the exponent: the linearised
+    identity at zeta and the two KZG openings, with every digest replaced by its discrete log."""
+    r, n = curve.r, circ.n
+    dom0 = Domain(curve, n)
+    g, w = dom0.coset_gen, dom0.generator
+    zeta, alpha, beta, gamma = ch.zeta, ch.alpha, ch.beta, ch.gamma
+    lin_z, lz, rz, oz, s1z, s2z = proof.claimed
+    zn = pow(zeta, n, r)
+    zh = (zn - 1) % r
+    l1 = zh * pow((zeta - 1) % r, -1, r) % r * dom0.cardinality_inv % r
+    # lin(zeta) = alpha^2 L1(zeta) - alpha (l + beta s1 + gamma)(r + beta s2 + gamma)(o + gamma) zu
+    want = (alpha * alpha % r * l1
+            - alpha * ((lz + beta * s1z + gamma) % r) % r * ((rz + beta * s2z + gamma) % r) % r * ((oz + gamma) % r) % r * proof.zu) % r
+    if lin_z != want:
+        return False
+    # the verifier rebuilds [lin] from the verifying key digests and the claimed values
+    s1, s2, s3 = sigma_polys(curve, dom0, circ.perm)
+    com_l = lambda lag: poly_eval(r, canonical(curve, dom0, lag), tau)
+    c1 = (lz + beta * s1z + gamma) % r * ((rz + beta * s2z + gamma) % r) % r * proof.zu % r * beta % r * alpha % r
+    uz, uuz = zeta * g % r, zeta * g % r * g % r
+    c2 = (-(lz + beta * zeta + gamma) % r * ((rz + beta * uz + gamma) % r) % r * ((oz + beta * uuz + gamma) % r) % r * alpha) % r
+    zn2 = zn * zeta % r * zeta % r
+    lin_digest = (proof.Z * ((c2 + alpha * alpha % r * l1) % r) + com_l(s3) * c1 + com_l(circ.qm) * (rz * lz % r)
+                  + com_l(circ.ql) * lz + com_l(circ.qr) * rz + com_l(circ.qo) * oz + com_l(circ.qk)
+                  - zh * ((proof.H[2] * zn2 + proof.H[1]) % r * zn2 % r + proof.H[0])) % r
+    if lin_digest != proof.lin:
+        return False
+    # batched KZG opening at zeta: e([f] - f(zeta)[1], [1]) = e([H], [tau - zeta])
+    digests = [proof.lin, proof.L, proof.R, proof.O, com_l(s1), com_l(s2)]
+    f_tau = f_z = 0
+    vp = 1
+    for d, c in zip(digests, proof.claimed):
+        f_tau = (f_tau + vp * d) % r
+        f_z = (f_z + vp * c) % r
+        vp = vp * ch.v % r
+    if proof.batch_opening * ((tau - zeta) % r) % r != (f_tau - f_z) % r:
+        return False
+    # opening of Z at w*zeta
+    if proof.z_opening * ((tau - zeta * w) % r) % r != (proof.Z - proof.zu) % r:
+        return False
+    return True
+
+
+def random_satisfied_instance(curve, n, seed):
+    """A random satisfied trace: random gates L*R-style with O solved, and a permutation built from
+    cycles over slots that are FORCED to carry equal values (so the copy constraints hold)."""
+    import random
+    rng = random.Random(seed)
+    r = curve.r
+    # pick wire values with repeated values so that non-trivial cycles exist
+    pool = [rng.randrange(r) for _ in range(max(4, n // 2))]
+    l = [rng.choice(pool) for _ in range(n)]
+    rr = [rng.choice(pool) for _ in range(n)]
+    ql = [rng.randrange(r) for _ in range(n)]
+    qr = [rng.randrange(r) for _ in range(n)]
+    qm = [rng.randrange(r) for _ in range(n)]
+    qk = [rng.randrange(r) for _ in range(n)]
+    qo = [r - 1] * n
+    o = [(ql[i] * l[i] + qr[i] * rr[i] + qm[i] * l[i] * rr[i] + qk[i]) % r for i in range(n)]
+    vals = l + rr + o
+    # permutation: link all slots holding the same value into one cycle
+    groups = {}
+    for idx, v in enumerate(vals):
+        groups.setdefault(v, []).append(idx)
+    perm = list(range(3 * n))
+    for idxs in groups.values():
+        if len(idxs) > 1:
+            rng.shuffle(idxs)
+            for a, b in zip(idxs, idxs[1:] + idxs[:1]):
+                perm[a] = b
+    return Circuit(n=n, ql=ql, qr=qr, qm=qm, qo=qo, qk=qk, perm=perm), l, rr, o
