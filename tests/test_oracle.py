@@ -150,3 +150,28 @@ def test_plonk_quotient_identity():
     N = plonk.all_constraints(r, n, dom0.cardinality_inv, u, x, x * dom0.generator % r, alpha, beta, gamma, g, {},
                               (pow(x, n, r) - 1) % r)
     assert ntt.poly_eval(r, h, x) * (pow(x, n, r) - 1) % r == N
+
+
+@pytest.mark.parametrize("cname", ("bn254", "bls12-381", "bw6-761"))
+def test_plonk_prover_oracle_verifies(cname):
+    """oracle/plonk_prover.py (restating backend/plonk/bn254/prove.go with injected challenges) produces
+    proofs that satisfy the verifier's equations in the exponent; a tampered witness is rejected."""
+    from oracle import plonk_prover as pp
+    c = CURVES[cname]
+    rng = random.Random(5)
+    rnd = lambda: rng.randrange(c.r)
+    for n in (8, 16):
+        circ, l, rr, o = pp.random_satisfied_instance(c, n, seed=n)
+        ch = pp.Challenges(gamma=rnd(), beta=rnd(), alpha=rnd(), zeta=rnd(), v=rnd(), bl=[rnd(), rnd()],
+                           br=[rnd(), rnd()], bo=[rnd(), rnd()], bz=[rnd(), rnd(), rnd()])
+        tau = rnd()
+        pr = pp.prove(c, circ, l, rr, o, ch, tau)
+        assert pp.verify(c, circ, pr, ch, tau)
+        assert len(pr.lin_poly) == n + 3 and pr.z_lagrange[0] == 1
+        bad = pp.prove(c, circ, l, rr, o, ch, tau)
+        bad.claimed[1] = (bad.claimed[1] + 1) % c.r            # a wrong opened value
+        assert not pp.verify(c, circ, bad, ch, tau)
+        l2 = list(l)
+        l2[1] = (l2[1] + 1) % c.r                                # an unsatisfied trace does not divide
+        with pytest.raises(AssertionError):
+            pp.prove(c, circ, l2, rr, o, ch, tau)
