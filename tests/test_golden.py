@@ -1,0 +1,84 @@
+"""Committed known-answer vectors (tests/golden/kat_v1.json, made by tests/golden/make_golden.py from the
+big-int oracle): the oracle and the C++ oracle must reproduce them on the CPU, the CUDA path on the GPU."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import corelib, ec, ff, groth16 as g16, ntt
+from oracle.params import CURVES
+
+KAT = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "kat_v1.json")))
+ALL = list(CURVES.values())
+H = lambda s: int(s, 16)
+
+
+def pt(F, v):
+    if v is None:
+        return None
+    conv = (lambda x: (H(x[0]), H(x[1]))) if F.degree == 2 else H
+    return (conv(v[0]), conv(v[1]))
+
+
+@pytest.mark.parametrize("c", ALL, ids=lambda c: c.name)
+def test_oracles_reproduce_golden(c):
+    e = KAT["curves"][c.name]
+    for a, b, ab in e["fp_mul"]:
+        assert H(a) * H(b) % c.p == H(ab)
+    for group in (1, 2):
+        F = ff.base_field(c, group)
+        m = e[f"msm_g{group}"]
+        pts = [pt(F, p) for p in m["points"]]
+        sc = [H(s) for s in m["scalars"]]
+        want = pt(F, m["result"])
+        assert ec.msm_naive(F, pts, sc) == want
+        got = corelib.msm(c, group, ec.pack_points(c, group, pts), ff.pack_elements(sc, c.r, c.fr_limbs), c=4)
+        assert ec.from_jac(F, ec.unpack_points(c, group, got, ncoords=3)[0]) == want
+    n8 = e["ntt8"]
+    dom = ntt.Domain(c, 8)
+    assert dom.generator == H(n8["generator"]) and dom.coset_gen == H(n8["coset_gen"])
+    a = [H(x) for x in n8["input"]]
+    for key, out in n8["out"].items():
+        inv, dec, cos = int(key[3]), int(key[8]), int(key[-1])
+        assert (dom.fft_inverse if inv else dom.fft)(a, dec, on_coset=bool(cos)) == [H(x) for x in out]
+        A = ff.pack_elements(a, c.r, c.fr_limbs)
+        corelib.ntt(c, A, 3, inv, dec, cos)
+        assert ff.unpack_elements(A, c.r, c.fr_limbs) == [H(x) for x in out]
+    gc = e["groth16_cubic"]
+    cs, W = g16.cubic_r1cs(), g16.cubic_witness(c.r)
+    pk = g16.setup_dlog(c, cs, g16.Toxic(*[H(v) for v in gc["toxic"]]))
+    pr = g16.prove_dlog(c, cs, pk, W, H(gc["r"]), H(gc["s"]))
+    assert [pr.ar, pr.bs, pr.krs] == [H(gc["ar"]), H(gc["bs"]), H(gc["krs"])]
+    assert pr.h == [H(v) for v in gc["h_bitreversed"]]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("c", ALL, ids=lambda c: c.name)
+def test_cuda_reproduces_golden(gpu, c):
+    e = KAT["curves"][c.name]
+    for group in (1, 2):
+        F = ff.base_field(c, group)
+        m = e[f"msm_g{group}"]
+        pts = [pt(F, p) for p in m["points"]]
+        sc = [H(s) for s in m["scalars"]]
+        for precomp in (False, True):
+            t = gpu.Table(c.curve_id, group, ec.pack_points(c, group, pts), precomp=precomp)
+            got = t.msm(ff.pack_elements(sc, c.r, c.fr_limbs))
+            assert ec.from_jac(F, ec.unpack_points(c, group, got, ncoords=3)[0]) == pt(F, m["result"])
+            t.free()
+    n8 = e["ntt8"]
+    a = [H(x) for x in n8["input"]]
+    d = gpu.Domain(c.curve_id, 3)
+    for key, out in n8["out"].items():
+        inv, dec, cos = int(key[3]), int(key[8]), int(key[-1])
+        A = d.ntt(ff.pack_elements(a, c.r, c.fr_limbs), inverse=bool(inv), decimation=dec, on_coset=bool(cos))
+        assert ff.unpack_elements(A, c.r, c.fr_limbs) == [H(x) for x in out]
+    # computeH of the cubic circuit
+    gc = e["groth16_cubic"]
+    cs, W = g16.cubic_r1cs(), g16.cubic_witness(c.r)
+    A_, B_, C_ = g16.solve_abc(cs, W, c.r)
+    d2 = gpu.Domain(c.curve_id, 2)
+    got = d2.compute_h(*(ff.pack_elements(v, c.r, c.fr_limbs) for v in (A_, B_, C_)))
+    assert ff.unpack_elements(got, c.r, c.fr_limbs) == [H(v) for v in gc["h_bitreversed"]]
+    d.free(); d2.free()
