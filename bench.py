@@ -39,24 +39,25 @@ NCU_TRAFFIC_BYTES = 2.324e9  # k_msm_accumulate at 2^20, one ncu --set full capt
 # bases and to check the result before timing (checker role) and for the CPU arm.
 # --------------------------------------------------------------------------------------
 def make_workload(n, seed, rank=0):
-    import random
+    """bases: 2^16 distinct known-discrete-log points k_i * G (same on every rank), tiled to n;
+    scalars: n uniform field elements per rank.  expected = (sum s_i k_i) * G."""
     from oracle import corelib, ec, ff
     from oracle.params import BN254 as C
-    rng = random.Random(seed + 7919 * rank)
-    rs = np.random.RandomState((seed + rank) & 0x7FFFFFFF)
 
-    def rand_fr(count):
-        # uniform in [0, r) by rejection on 254-bit draws, canonical -> Montgomery via the oracle
+    def rand_fr(rs, count):
+        # uniform on [0, 2^253) (r ~ 2^253.6); the raw limbs are used as Montgomery residues, which are
+        # themselves uniform field elements: no conversion needed
         a = rs.randint(0, 1 << 62, size=(count, 4), dtype=np.int64).astype(np.uint64)
-        a[:, 3] &= np.uint64((1 << 61) - 1)          # < 2^253 < r  (r ~ 2^253.6): uniform on a 2^253 subset
+        a[:, 3] &= np.uint64((1 << 61) - 1)
         return a
-    # Montgomery residues are themselves uniform field elements: use the raw limbs as the
-    # Montgomery representation (value = limbs * R^-1), no conversion needed.
-    ks_m = rand_fr(n)
-    sc_m = rand_fr(n)
-    pts = corelib.fixed_base(C, 1, ec.pack_points(C, 1, [C.g1]), ks_m)
-    dot = corelib.fr_dot(C, ks_m, sc_m)               # sum k_i s_i mod r
-    expected = ec.scalar_mul(ff.Fp(C.p), dot, C.g1)   # known-dlog oracle
+    small = min(n, 1 << 16)
+    ks_small = rand_fr(np.random.RandomState(seed & 0x7FFFFFFF), small)
+    pts_small = corelib.fixed_base(C, 1, ec.pack_points(C, 1, [C.g1]), ks_small)
+    reps = n // small
+    pts = np.tile(pts_small, (reps, 1))
+    sc_m = rand_fr(np.random.RandomState((seed + rank + 1) & 0x7FFFFFFF), n)
+    dot = corelib.fr_dot(C, np.tile(ks_small, (reps, 1)), sc_m)      # sum k_i s_i mod r
+    expected = ec.scalar_mul(ff.Fp(C.p), dot, C.g1)
     return C, pts, sc_m, expected
 
 
@@ -301,9 +302,7 @@ def run_b200(args):
                 groth16_leg(local, pts, n, rank, world)
             except Exception:
                 pass
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        finish(world)
 
     total = n * world
     value = total * args.steps / (ms / 1e3)
@@ -315,7 +314,14 @@ def run_b200(args):
     achieved = alg_bytes / (acc_ms / 1e3) / 1e9
     threads = os.cpu_count() or 1
     sample_n = n if threads >= 32 else 1 << 18   # many-core hosts need the full problem to scale
-    cpu_rate, cpu_dt = cpu_msm_rate(C, pts, sc, sample_n, 3, threads)
+    if world == 1:
+        cpu_rate, cpu_dt = cpu_msm_rate(C, pts, sc, sample_n, 3, threads)
+        cpu_baseline = {"value": cpu_rate, "unit": UNIT, "cores": threads, "kind": "port",
+                        "sample": f"3 x BN254 G1 MSM of 2^{int(np.log2(sample_n))} points of the same workload "
+                                  f"({cpu_dt:.2f} s each, window picked by a sweep)"}
+    else:
+        cpu_baseline = {"value": None, "unit": UNIT, "cores": threads, "kind": "port",
+                        "sample": "timed on rank 0 at N=1 only (see the N=1 line)"}
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -338,23 +344,31 @@ def run_b200(args):
                                       "source": "profiles/r01_ncu_accumulate_summary.md"},
                      "note": "integer-multiplier bound, not HBM bound: ~1360 IMAD.WIDE per gathered 68 B (DESIGN.md)"},
         "stage_ms": stage_ms,
-        "cpu_baseline": {"value": cpu_rate, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"3 x BN254 G1 MSM of 2^{int(np.log2(sample_n))} points of the same workload "
-                                   f"({cpu_dt:.2f} s each, window picked by a sweep)"},
+        "cpu_baseline": cpu_baseline,
         "clocks": clocks,
     }
     emit(out) if args.no_groth16 else None
     if args.no_groth16:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        finish(world)
     try:
         out["groth16"] = groth16_leg(local, pts, n, 0, world)
     except Exception as e:  # the headline metric must still be printed
         out["groth16"] = {"error": repr(e)}
     emit(out)
-    if world > 1:
-        dist.destroy_process_group()
+    finish(world)
+
+
+def finish(world):
+    """orderly exit without NCCL teardown (destroy_process_group can stall at exit on some multi-rank boxes)"""
+    import torch
+    import torch.distributed as dist
+    try:
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    finally:
+        sys.stdout.flush(); sys.stderr.flush()
+        os._exit(0)
 
 
 def groth16_leg(dev, g1_pts, n, rank=0, world=1):
@@ -375,8 +389,7 @@ def groth16_leg(dev, g1_pts, n, rank=0, world=1):
         a = rs.randint(0, 1 << 62, size=(count, 4), dtype=np.int64).astype(np.uint64)
         a[:, 3] &= np.uint64((1 << 61) - 1)
         return a
-    if world > 1:       # every rank needs the SAME synthetic key before sharding it
-        _, g1_pts, _, _ = make_workload(n, SEED, 0)
+    # bases are identical on every rank (make_workload), so every rank holds the SAME synthetic key to shard
     nb_wires, nb_public = n + 2, 2
     g2_small = corelib.fixed_base(C, 2, ec.pack_points(C, 2, [C.g2]), rand_fr(1 << 16))
     g2_b = np.tile(g2_small, (n // (1 << 16) + 1, 1))[:nb_wires].copy()

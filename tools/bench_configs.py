@@ -175,9 +175,15 @@ def main():
         out["note"] = ("sum of primitive timings x per-proof counts (SURVEY.md §8d config 4); the O(n) scans, "
                        "Fiat-Shamir and host orchestration of a full PLONK prover are not included")
         emit(out)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    # no NCCL teardown: at 8 ranks destroy_process_group stalled after both results had been emitted
+    # (round-1 run: 600 s lost to the timeout); barrier, flush and leave
+    try:
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    finally:
+        sys.stdout.flush(); sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":
