@@ -4,7 +4,9 @@
 // allConstraints :961-988), the 1/(X^n - 1) scaling of divideByZH (:1287-1324) and a
 // parallel batch inversion (batchInvert :1130-1143).  No BSB22 commitment gates yet.
 #pragma once
+#ifdef __CUDACC__
 #include <cuda_runtime.h>
+#endif
 
 #include "ntt.cuh"
 

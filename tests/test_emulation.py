@@ -162,3 +162,32 @@ def test_msm_fp64_path_logic(hostemu, c):
         out = np.zeros(3 * c.fp_limbs, dtype=np.uint64)
         assert hostemu.emu_msm52(c.curve_id, P(PA), P(SA), n, cw, tl, ch, P(out)) == 0
         assert ec.from_jac(F, ec.unpack_points(c, 1, out, ncoords=3)[0]) == exp, (c.name, cw)
+
+
+@pytest.mark.parametrize("c", [CURVES["bn254"], CURVES["bls12-381"], CURVES["bw6-761"]], ids=lambda c: c.name)
+def test_plonk_constraint_kernel_logic(hostemu, c):
+    """per-point logic of k_plonk_constraints (gate + permutation + L1 with blinding, bit-reversed scatter)
+    walked on the CPU, against oracle/plonk.py (restating plonk/bn254/prove.go:841-1123)."""
+    from oracle import plonk
+    rng = random.Random(77)
+    r, L = c.r, c.fr_limbs
+    logn, rho = 4, 4
+    n = 1 << logn
+    polys = {k: [rng.randrange(r) for _ in range(n)] for k in plonk.POLYS}
+    alpha, beta, gamma = (rng.randrange(r) for _ in range(3))
+    blind = {"l": [rng.randrange(r) for _ in range(2)], "r": [rng.randrange(r) for _ in range(2)],
+             "o": [rng.randrange(r) for _ in range(2)], "z": [rng.randrange(r) for _ in range(3)]}
+    want = plonk.numerator(c, n, rho, polys, alpha, beta, gamma, blind)
+    dom0, dom1 = ntt.Domain(c, n), ntt.Domain(c, rho * n)
+    out = np.zeros((rho * n, L), dtype=np.uint64)
+    pe = lambda v: ff.pack_elements(v, r, L)
+    abg = pe([alpha, beta, gamma])
+    bl = [pe(blind[k]) for k in ("l", "r", "o", "z")]
+    nbl = (ctypes.c_int * 4)(2, 2, 2, 3)
+    blp = (ctypes.c_void_p * 4)(*[b.ctypes.data for b in bl])
+    for i in range(rho):
+        coset = dom1.coset_gen * pow(dom1.generator, i, r) % r
+        on_coset = [pe(plonk.coset_values(c, dom0, polys[k], coset)) for k in plonk.POLYS]
+        pp = (ctypes.c_void_p * 12)(*[a.ctypes.data for a in on_coset])
+        assert hostemu.emu_plonk_constraints_coset(c.curve_id, pp, P(abg), blp, nbl, logn, i, rho, P(out)) == 0
+    assert ff.unpack_elements(out, r, L) == want
