@@ -182,7 +182,7 @@ def Prove(pk: ProvingKey, l, r, o, ch: Challenges) -> Proof:
         cb = d_lagrange.clone()
         pk.dom0[0].ntt_async(cb, inverse=True, decimation=_lib.DIF)
         reg = t.zeros((n + len(b)) * L, dtype=t.int64, device=cb.device)
-        reg[:n * L] = cb
+        reg[:n * L] = cb.reshape(-1)
         _lib.vec_bit_reverse(dev, curve, reg, logn)
         # p + b (X^n - 1): low coefficients minus b, then b on top (getBlindedCoefficients :1211-1220)
         low = reg[:len(b) * L].cpu().numpy().view(np.uint64).reshape(len(b), L)
