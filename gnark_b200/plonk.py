@@ -112,6 +112,10 @@ class ProvingKey:
         # domain0 handles for the four cosets g * w4^i (computeNumerator :943-948) and the big domain
         self.dom0 = [_lib.Domain(curve, log2n, dev=dev, coset_gen=self.fr.enc(g * pow(self.w4, i, q) % q)) for i in range(4)]
         self.dom1 = _lib.Domain(curve, log2n + 2, dev=dev)
+        # ONE stream for everything: torch tensor ops (clone, slice copies, H2D/D2H) and the library's kernels
+        # must be ordered with respect to each other, so the library is pointed at this torch stream while a
+        # key method / Prove runs (the library's own stream is non-blocking and would race with torch's)
+        self.stream = torch.cuda.Stream(device=dev)
         self.polys = {}        # name -> device tensor, CANONICAL coefficients in BIT-REVERSED layout (n)
         self.canon = {}        # name -> canonical, regular layout (for evaluations / linearised polynomial)
         self.perm = None
@@ -120,10 +124,33 @@ class ProvingKey:
     def _dev(self, arr):
         return self.torch.from_numpy(np.ascontiguousarray(arr).view(np.int64)).to(f"cuda:{self.dev}")
 
+    def on_stream(self):
+        """context manager: torch's current stream and the library's stream are both self.stream"""
+        pk = self
+
+        class _Ctx:
+            def __enter__(self_inner):
+                self_inner.cm = pk.torch.cuda.stream(pk.stream)
+                self_inner.cm.__enter__()
+                _lib.set_stream(pk.dev, pk.stream.cuda_stream)
+                return pk
+
+            def __exit__(self_inner, *exc):
+                pk.stream.synchronize()
+                _lib.set_stream(pk.dev, 0)          # back to the library's own stream
+                return self_inner.cm.__exit__(*exc)
+        return _Ctx()
+
     @classmethod
     def from_trace(cls, curve, log2n, ql, qr, qm, qo, qk, perm, srs_canonical, dev=0):
         """ql..qk: (n, limbs) uint64 Lagrange/regular (Montgomery); perm: int64[3n]; srs_canonical: (n+3) G1Affine."""
         pk = cls(curve, log2n, dev)
+        with pk.on_stream():
+            pk._load(ql, qr, qm, qo, qk, perm, srs_canonical)
+        return pk
+
+    def _load(self, ql, qr, qm, qo, qk, perm, srs_canonical):
+        pk, curve, log2n, dev = self, self.curve, self.log2n, self.dev
         t = pk.torch
         n, L, q = pk.n, pk.fr.limbs, pk.fr.q
         pk.perm = t.from_numpy(np.ascontiguousarray(perm, dtype=np.int64)).to(f"cuda:{dev}")
@@ -145,7 +172,6 @@ class ProvingKey:
             pk.canon[name] = c
         pk.srs = _lib.Table(curve, 1, srs_canonical, dev=dev, precomp=True)
         _lib.sync(dev)
-        return pk
 
     def free(self):
         for d in self.dom0:
@@ -158,6 +184,11 @@ class ProvingKey:
 def Prove(pk: ProvingKey, l, r, o, ch: Challenges) -> Proof:
     """l, r, o: (n, limbs) uint64 Lagrange/regular solution vectors (SparseR1CSSolution{L,R,O},
     constraint/bn254/system.go:208-210) on the host."""
+    with pk.on_stream():
+        return _prove(pk, l, r, o, ch)
+
+
+def _prove(pk: ProvingKey, l, r, o, ch: Challenges) -> Proof:
     import time
     t = pk.torch
     curve, dev, n, logn = pk.curve, pk.dev, pk.n, pk.log2n
