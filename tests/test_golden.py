@@ -51,34 +51,3 @@ def test_oracles_reproduce_golden(c):
     pr = g16.prove_dlog(c, cs, pk, W, H(gc["r"]), H(gc["s"]))
     assert [pr.ar, pr.bs, pr.krs] == [H(gc["ar"]), H(gc["bs"]), H(gc["krs"])]
     assert pr.h == [H(v) for v in gc["h_bitreversed"]]
-
-
-@pytest.mark.gpu
-@pytest.mark.parametrize("c", ALL, ids=lambda c: c.name)
-def test_cuda_reproduces_golden(gpu, c):
-    e = KAT["curves"][c.name]
-    for group in (1, 2):
-        F = ff.base_field(c, group)
-        m = e[f"msm_g{group}"]
-        pts = [pt(F, p) for p in m["points"]]
-        sc = [H(s) for s in m["scalars"]]
-        for precomp in (False, True):
-            t = gpu.Table(c.curve_id, group, ec.pack_points(c, group, pts), precomp=precomp)
-            got = t.msm(ff.pack_elements(sc, c.r, c.fr_limbs))
-            assert ec.from_jac(F, ec.unpack_points(c, group, got, ncoords=3)[0]) == pt(F, m["result"])
-            t.free()
-    n8 = e["ntt8"]
-    a = [H(x) for x in n8["input"]]
-    d = gpu.Domain(c.curve_id, 3)
-    for key, out in n8["out"].items():
-        inv, dec, cos = int(key[3]), int(key[8]), int(key[-1])
-        A = d.ntt(ff.pack_elements(a, c.r, c.fr_limbs), inverse=bool(inv), decimation=dec, on_coset=bool(cos))
-        assert ff.unpack_elements(A, c.r, c.fr_limbs) == [H(x) for x in out]
-    # computeH of the cubic circuit
-    gc = e["groth16_cubic"]
-    cs, W = g16.cubic_r1cs(), g16.cubic_witness(c.r)
-    A_, B_, C_ = g16.solve_abc(cs, W, c.r)
-    d2 = gpu.Domain(c.curve_id, 2)
-    got = d2.compute_h(*(ff.pack_elements(v, c.r, c.fr_limbs) for v in (A_, B_, C_)))
-    assert ff.unpack_elements(got, c.r, c.fr_limbs) == [H(v) for v in gc["h_bitreversed"]]
-    d.free(); d2.free()

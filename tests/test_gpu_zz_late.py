@@ -1,0 +1,100 @@
+"""GPU tests written AFTER round 1's GPU budget was spent (hardware-unvalidated at commit time).  They live in a
+file that sorts last so that, under `pytest -x`, the hardware-validated parity suite (test_gpu_groth16/msm/ntt/
+plonk) has already reported before these run.
+
+  * test_cuda_reproduces_golden   - the CUDA path on the committed known-answer vectors (tests/golden)
+  * test_full_prover_vs_oracle    - the device PLONK prover (gnark_b200/plonk.py) against the big-int oracle
+                                    prover, same injected challenges (xfail-guarded until run on hardware)
+"""
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+from oracle import ec, ff, groth16 as g16
+from oracle.params import CURVES
+from util import jac_to_affine
+
+pytestmark = pytest.mark.gpu
+KAT = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "kat_v1.json")))
+ALL = list(CURVES.values())
+H = lambda s: int(s, 16)
+
+
+def pt(F, v):
+    if v is None:
+        return None
+    conv = (lambda x: (H(x[0]), H(x[1]))) if F.degree == 2 else H
+    return (conv(v[0]), conv(v[1]))
+
+
+@pytest.mark.parametrize("c", ALL, ids=lambda c: c.name)
+def test_cuda_reproduces_golden(gpu, c):
+    e = KAT["curves"][c.name]
+    for group in (1, 2):
+        F = ff.base_field(c, group)
+        m = e[f"msm_g{group}"]
+        pts = [pt(F, p) for p in m["points"]]
+        sc = [H(s) for s in m["scalars"]]
+        for precomp in (False, True):
+            t = gpu.Table(c.curve_id, group, ec.pack_points(c, group, pts), precomp=precomp)
+            got = t.msm(ff.pack_elements(sc, c.r, c.fr_limbs))
+            assert ec.from_jac(F, ec.unpack_points(c, group, got, ncoords=3)[0]) == pt(F, m["result"])
+            t.free()
+    n8 = e["ntt8"]
+    a = [H(x) for x in n8["input"]]
+    d = gpu.Domain(c.curve_id, 3)
+    for key, out in n8["out"].items():
+        inv, dec, cos = int(key[3]), int(key[8]), int(key[-1])
+        A = d.ntt(ff.pack_elements(a, c.r, c.fr_limbs), inverse=bool(inv), decimation=dec, on_coset=bool(cos))
+        assert ff.unpack_elements(A, c.r, c.fr_limbs) == [H(x) for x in out]
+    # computeH of the cubic circuit
+    gc = e["groth16_cubic"]
+    cs, W = g16.cubic_r1cs(), g16.cubic_witness(c.r)
+    A_, B_, C_ = g16.solve_abc(cs, W, c.r)
+    d2 = gpu.Domain(c.curve_id, 2)
+    got = d2.compute_h(*(ff.pack_elements(v, c.r, c.fr_limbs) for v in (A_, B_, C_)))
+    assert ff.unpack_elements(got, c.r, c.fr_limbs) == [H(v) for v in gc["h_bitreversed"]]
+    d.free(); d2.free()
+
+
+@pytest.mark.xfail(strict=False, reason="orchestrator written after this round's GPU budget was spent: every C-ABI "
+                   "building block it calls is validated above, the end-to-end sequence has not run on hardware yet")
+@pytest.mark.parametrize("c", [CURVES["bn254"], CURVES["bls12-381"]], ids=lambda c: c.name)
+@pytest.mark.parametrize("logn", (4, 6))
+def test_full_prover_vs_oracle(gpu, c, logn):
+    """The device PLONK prover (gnark_b200/plonk.py, twin of backend/plonk/bn254/prove.go) against the
+    big-int oracle prover with the same injected challenges / blinding: every digest (as dlog * G with a
+    trapdoor SRS), every opened value; the oracle proof itself passes the verifier's equations."""
+    from gnark_b200 import plonk as b200_plonk
+    from oracle import corelib, plonk_prover as pp
+    rng = random.Random(1000 + logn)
+    r, L = c.r, c.fr_limbs
+    n = 1 << logn
+    circ, l, rr, o = pp.random_satisfied_instance(c, n, seed=logn)
+    rnd = lambda: rng.randrange(r)
+    ch = pp.Challenges(gamma=rnd(), beta=rnd(), alpha=rnd(), zeta=rnd(), v=rnd(), bl=[rnd(), rnd()], br=[rnd(), rnd()],
+                       bo=[rnd(), rnd()], bz=[rnd(), rnd(), rnd()])
+    tau = rnd()
+    want = pp.prove(c, circ, l, rr, o, ch, tau)
+    assert pp.verify(c, circ, want, ch, tau)
+    # trapdoor SRS: [tau^i] G, i < n + 3  (test/unsafekzg/kzgsrs.go:142-172)
+    pe = lambda v: ff.pack_elements(v, r, L)
+    srs = corelib.fixed_base(c, 1, ec.pack_points(c, 1, [c.g1]), pe([pow(tau, i, r) for i in range(n + 3)]))
+    pk = b200_plonk.ProvingKey.from_trace(c.curve_id, logn, pe(circ.ql), pe(circ.qr), pe(circ.qm), pe(circ.qo),
+                                         pe(circ.qk), np.array(circ.perm, dtype=np.int64), srs)
+    got = b200_plonk.Prove(pk, pe(l), pe(rr), pe(o),
+                           b200_plonk.Challenges(gamma=ch.gamma, beta=ch.beta, alpha=ch.alpha, zeta=ch.zeta, v=ch.v,
+                                                 bl=ch.bl, br=ch.br, bo=ch.bo, bz=ch.bz))
+    F = ff.Fp(c.p)
+    pt = lambda dlog: ec.scalar_mul(F, dlog, c.g1)
+    for name, g_, w_ in (("L", got.LRO[0], want.L), ("R", got.LRO[1], want.R), ("O", got.LRO[2], want.O),
+                         ("Z", got.Z, want.Z), ("H1", got.H[0], want.H[0]), ("H2", got.H[1], want.H[1]),
+                         ("H3", got.H[2], want.H[2]), ("lin", got.LinearizedDigest, want.lin),
+                         ("batch", got.BatchedProofH, want.batch_opening), ("zopen", got.ZShiftedOpeningH, want.z_opening)):
+        assert jac_to_affine(c, 1, g_) == pt(w_), name
+    assert got.BatchedClaimedValues == want.claimed
+    assert got.ZShiftedClaimedValue == want.zu
+    pk.free()
