@@ -48,6 +48,21 @@ _FR_DOMAIN = {
 }
 
 
+# device plumbing, gathered here so that tests/test_plonk_orchestration.py can run the ORCHESTRATION (ordering,
+# layouts, blinding, index conventions) on host tensors against a mock of the C ABI; the product always
+# runs on CUDA and there is no CPU implementation of any library call
+def _device(dev: int) -> str:
+    return f"cuda:{dev}"
+
+
+def _new_stream(torch, dev: int):
+    return torch.cuda.Stream(device=dev)
+
+
+def _stream_ctx(torch, stream):
+    return torch.cuda.stream(stream)
+
+
 @dataclass
 class Challenges:
     gamma: int
@@ -115,14 +130,14 @@ class ProvingKey:
         # ONE stream for everything: torch tensor ops (clone, slice copies, H2D/D2H) and the library's kernels
         # must be ordered with respect to each other, so the library is pointed at this torch stream while a
         # key method / Prove runs (the library's own stream is non-blocking and would race with torch's)
-        self.stream = torch.cuda.Stream(device=dev)
+        self.stream = _new_stream(torch, dev)
         self.polys = {}        # name -> device tensor, CANONICAL coefficients in BIT-REVERSED layout (n)
         self.canon = {}        # name -> canonical, regular layout (for evaluations / linearised polynomial)
         self.perm = None
         self.srs = None
 
     def _dev(self, arr):
-        return self.torch.from_numpy(np.ascontiguousarray(arr).view(np.int64)).to(f"cuda:{self.dev}")
+        return self.torch.from_numpy(np.ascontiguousarray(arr).view(np.int64)).to(_device(self.dev))
 
     def on_stream(self):
         """context manager: torch's current stream and the library's stream are both self.stream"""
@@ -130,7 +145,7 @@ class ProvingKey:
 
         class _Ctx:
             def __enter__(self_inner):
-                self_inner.cm = pk.torch.cuda.stream(pk.stream)
+                self_inner.cm = _stream_ctx(pk.torch, pk.stream)
                 self_inner.cm.__enter__()
                 _lib.set_stream(pk.dev, pk.stream.cuda_stream)
                 return pk
@@ -153,7 +168,7 @@ class ProvingKey:
         pk, curve, log2n, dev = self, self.curve, self.log2n, self.dev
         t = pk.torch
         n, L, q = pk.n, pk.fr.limbs, pk.fr.q
-        pk.perm = t.from_numpy(np.ascontiguousarray(perm, dtype=np.int64)).to(f"cuda:{dev}")
+        pk.perm = t.from_numpy(np.ascontiguousarray(perm, dtype=np.int64)).to(_device(dev))
         # sigma polynomials from the permutation: s_j[i] = supp[perm[j n + i]] (setup.go:289-392)
         w_pows = [1] * n
         for i in range(1, n):
