@@ -31,6 +31,8 @@ METRIC = "bn254_g1_msm_scalar_muls_per_sec"
 UNIT = "scalar-muls/s"
 LOG_N = 20
 SEED = 0x6E61726B00000002  # config 2 seed
+GROTH16_LEG_LIMIT_S = 420
+WHOLE_RUN_LIMIT_S = 1500
 NCU_TRAFFIC_BYTES = 2.324e9  # k_msm_accumulate at 2^20, one ncu --set full capture (profiles/r01_ncu_accumulate_summary.md)
 
 
@@ -298,6 +300,7 @@ def run_b200(args):
     table.free()
     if rank != 0:
         if not args.no_groth16:
+            arm_watchdog(GROTH16_LEG_LIMIT_S)
             try:
                 groth16_leg(local, pts, n, rank, world)
             except Exception:
@@ -350,12 +353,35 @@ def run_b200(args):
     emit(out) if args.no_groth16 else None
     if args.no_groth16:
         finish(world)
+    def headline_only():
+        out["groth16"] = {"error": "secondary leg did not finish within %d s" % GROTH16_LEG_LIMIT_S}
+        emit(out)
+    dog = arm_watchdog(GROTH16_LEG_LIMIT_S, headline_only)
     try:
         out["groth16"] = groth16_leg(local, pts, n, 0, world)
     except Exception as e:  # the headline metric must still be printed
         out["groth16"] = {"error": repr(e)}
+    dog.cancel()
     emit(out)
+    arm_watchdog(60)          # the line is out; never hang in the closing barrier
     finish(world)
+
+
+def arm_watchdog(seconds, last_words=None, code=0):
+    """a stuck secondary leg (a rank lost inside a collective) must not cost the headline line: after
+    `seconds` run last_words() (rank 0: print what is already measured) and leave"""
+    def fire():
+        try:
+            if last_words is not None:
+                last_words()
+        finally:
+            sys.stderr.write("bench.py: watchdog fired after %d s\n" % seconds)
+            sys.stderr.flush()
+            os._exit(code)
+    t = threading.Timer(seconds, fire)
+    t.daemon = True
+    t.start()
+    return t
 
 
 def finish(world):
@@ -453,6 +479,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-groth16", action="store_true", help="skip the secondary Groth16 2^20 prove-time leg")
     args = ap.parse_args()
+    arm_watchdog(WHOLE_RUN_LIMIT_S, code=1)
     if args.impl == "reference":
         run_reference(args)
     else:
