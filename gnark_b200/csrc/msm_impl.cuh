@@ -268,11 +268,6 @@ cudaError_t msm_precompute_enqueue(cudaStream_t st, uint32_t n, int nwin, int c,
 // workspace + driver
 // ---------------------------------------------------------------------------
 constexpr int MSM_NUM_EVENTS = 8;
-struct MsmWorkspace {
-  void* base = nullptr;
-  size_t bytes = 0;
-};
-
 template <class F>
 struct MsmLayout {
   size_t m;            // entries

@@ -22,11 +22,6 @@ __global__ void __launch_bounds__(256) k_powers(const Fr* __restrict__ pw, Fr sc
   out[k] = acc;
 }
 
-struct NttScale {
-  const void* table;  // nullptr: none
-  int bitrev;         // index the table by bitrev(i)
-};
-
 // One pass: tile of 2^(S+cb) elements in shared memory (limb-major), blockDim = tile/2.
 template <class Fr>
 __global__ void __launch_bounds__(1 << (NTT_MAX_TILE_LOG - 1))

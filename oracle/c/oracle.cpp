@@ -21,6 +21,8 @@
 #include <atomic>
 #include <functional>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <thread>
 #include <vector>
@@ -38,6 +40,7 @@ struct Ctx {
 template <int N>
 void ctx_init(Ctx<N>& c, const u64* mod) {
   for (int i = 0; i < N; i++) c.p[i] = mod[i];
+  if (mod[N - 1] >> 63) { fprintf(stderr, "oracle: modulus with the top bit set is not supported by mul()\n"); abort(); }
   u64 x = 1;
   for (int i = 0; i < 6; i++) x *= 2 - mod[0] * x;  // p^-1 mod 2^64
   c.ninv = 0 - x;
@@ -90,20 +93,24 @@ struct Fp {
   }
   Fp neg() const { return is_zero() ? *this : zero().sub(*this); }
   Fp dbl() const { return add(*this); }
+  // CIOS Montgomery product; every modulus here leaves the top bit of the top word clear, so the
+  // two carry words of the textbook CIOS collapse into one ("no-carry" variant: t stays < 2p)
   Fp mul(const Fp& o) const {
-    u64 t[N + 2];
-    memset(t, 0, sizeof(t));
+    u64 t[N];
     for (int i = 0; i < N; i++) {
-      u128 c = 0;
-      for (int j = 0; j < N; j++) { c += (u128)v[j] * o.v[i] + t[j]; t[j] = (u64)c; c >>= 64; }
-      c += t[N]; t[N] = (u64)c; t[N + 1] = (u64)(c >> 64);
-      u64 m = t[0] * C.ninv;
-      c = ((u128)m * C.p[0] + t[0]) >> 64;
-      for (int j = 1; j < N; j++) { c += (u128)m * C.p[j] + t[j]; t[j - 1] = (u64)c; c >>= 64; }
-      c += t[N]; t[N - 1] = (u64)c; t[N] = t[N + 1] + (u64)(c >> 64);
+      u128 A = (u128)v[0] * o.v[i] + (i ? t[0] : 0);
+      const u64 t0 = (u64)A; A >>= 64;
+      const u64 m = t0 * C.ninv;
+      u128 Cc = ((u128)m * C.p[0] + t0) >> 64;
+      for (int j = 1; j < N; j++) {
+        A += (u128)v[j] * o.v[i] + (i ? t[j] : 0);
+        Cc += (u128)m * C.p[j] + (u64)A; A >>= 64;
+        t[j - 1] = (u64)Cc; Cc >>= 64;
+      }
+      t[N - 1] = (u64)Cc + (u64)A;
     }
     Fp r; memcpy(r.v, t, sizeof(r.v));
-    if (t[N] || ge_p(r.v)) sub_p(r.v);
+    if (ge_p(r.v)) sub_p(r.v);
     return r;
   }
   Fp sqr() const { return mul(*this); }
@@ -227,15 +234,94 @@ void run_threads(int nt, const std::function<void(int)>& f) {
 }
 
 // ---- Pippenger ----------------------------------------------------------------
+// ---- batch-affine bucket accumulation ------------------------------------------------
+// gnark-crypto's MultiExp switches from extended-Jacobian buckets to AFFINE buckets with batched
+// additions for large windows (Montgomery's simultaneous-inversion trick: one field inversion per batch,
+// 3 multiplications per element; an affine addition then costs 2M + 1S instead of 8M + 2S).  Additions in
+// one batch must touch distinct buckets; a point whose bucket is already in the batch waits in a queue.
+template <class K>
+struct BatchAffine {
+  static const int MAX_BATCH = 512;
+  std::vector<Aff<K>>& bk;          // affine buckets, (0,0) = empty
+  std::vector<uint8_t> busy;        // bucket is the target of an operation in the current batch
+  int batch;                        // operations per inversion (scaled to the bucket count, as gnark-crypto does)
+  uint32_t idx[MAX_BATCH];
+  Aff<K> rhs[MAX_BATCH];
+  K num[MAX_BATCH], den[MAX_BATCH]; // slope = num / den
+  K pre[MAX_BATCH];
+  int cnt = 0;
+  struct Pending { uint32_t b; Aff<K> p; };
+  std::vector<Pending> queue, tmp;
+
+  explicit BatchAffine(std::vector<Aff<K>>& buckets) : bk(buckets), busy(buckets.size(), 0) {
+    size_t b = buckets.size() / 16;
+    batch = (int)(b < 32 ? 32 : (b > (size_t)MAX_BATCH ? (size_t)MAX_BATCH : b));
+  }
+
+  // stage one addition; false when the bucket is already a target in this batch or the batch is full
+  bool push(uint32_t b, const Aff<K>& p) {
+    if (busy[b]) return false;
+    Aff<K>& B = bk[b];
+    if (B.is_inf()) { B = p; return true; }
+    if (cnt == batch) return false;
+    if (B.x.eq(p.x)) {
+      if (!B.y.eq(p.y) || p.y.is_zero()) { B = Aff<K>{K::zero(), K::zero()}; return true; }   // P + (-P)
+      K xx = p.x.sqr();
+      num[cnt] = xx.dbl().add(xx);                                                // doubling: 3x^2 / 2y
+      den[cnt] = p.y.dbl();
+    } else {
+      num[cnt] = p.y.sub(B.y);
+      den[cnt] = p.x.sub(B.x);
+    }
+    idx[cnt] = b; rhs[cnt] = p; busy[b] = 1;
+    cnt++;
+    return true;
+  }
+  void flush() {
+    if (!cnt) return;
+    K acc = K::one();
+    for (int i = 0; i < cnt; i++) { pre[i] = acc; acc = acc.mul(den[i]); }
+    K inv = acc.inv();
+    for (int i = cnt - 1; i >= 0; i--) {
+      K dinv = inv.mul(pre[i]);
+      inv = inv.mul(den[i]);
+      Aff<K>& B = bk[idx[i]];
+      K lam = num[i].mul(dinv);
+      K x3 = lam.sqr().sub(B.x).sub(rhs[i].x);
+      K y3 = lam.mul(B.x.sub(x3)).sub(B.y);
+      B.x = x3; B.y = y3;
+      busy[idx[i]] = 0;
+    }
+    cnt = 0;
+  }
+  // execute the staged batch, then stage whatever queued points have become possible
+  void flush_and_requeue() {
+    flush();
+    tmp.swap(queue);
+    queue.clear();
+    for (auto& q : tmp) if (!push(q.b, q.p)) queue.push_back(q);
+    tmp.clear();
+  }
+  void add(uint32_t b, const Aff<K>& p) {
+    if (p.is_inf()) return;
+    if (!push(b, p)) queue.push_back(Pending{b, p});
+    if (cnt == batch || queue.size() >= (size_t)(2 * batch)) flush_and_requeue();
+  }
+  void finish() {
+    while (cnt || !queue.empty()) flush_and_requeue();
+  }
+};
+
 template <class K, class S>
-Ext<K> msm_pippenger(const Aff<K>* pts, const S* sc_mont, size_t n, int c, int nthreads, int scalar_bits) {
+Ext<K> msm_pippenger(const Aff<K>* pts, const S* sc_mont, size_t n, int c, int nthreads, int scalar_bits,
+                     bool batch_affine = false) {
   if (n == 0) return Ext<K>::inf();
   const int NS = sizeof(S) / 8;
   const int nwin = scalar_bits / c + 1;
   // signed digits
   std::vector<int32_t> digits((size_t)nwin * n);
   run_threads(nthreads, [&](int t) {
-    for (size_t i = t; i < n; i += nthreads) {
+    for (size_t i = n * t / nthreads, end = n * (t + 1) / nthreads; i < end; i++) {   // contiguous: no false sharing
       S s = sc_mont[i].from_mont();
       int carry = 0;
       for (int w = 0; w < nwin; w++) {
@@ -258,22 +344,38 @@ Ext<K> msm_pippenger(const Aff<K>* pts, const S* sc_mont, size_t n, int c, int n
   std::vector<int> next_task(1, 0);
   std::atomic<int> counter(0);
   const size_t nb = (size_t)1 << (c - 1);
+  // the top window holds only scalar_bits - (nwin-1)*c bits: with a handful of live buckets a batch cannot
+  // fill, so (as gnark-crypto does for its last chunk) it keeps extended-Jacobian buckets
+  const int top_bits = scalar_bits - (nwin - 1) * c;
   run_threads(nthreads, [&](int) {
-    std::vector<Ext<K>> buckets(nb);
+    std::vector<Ext<K>> buckets;
+    std::vector<Aff<K>> abuckets;
     for (;;) {
       int task = counter.fetch_add(1);
       if (task >= ntasks) break;
       int w = task / split, part = task % split;
       size_t lo = n * part / split, hi = n * (part + 1) / split;
-      for (auto& b : buckets) b = Ext<K>::inf();
       const int32_t* dg = &digits[(size_t)w * n];
-      for (size_t i = lo; i < hi; i++) {
-        int32_t d = dg[i];
-        if (d > 0) buckets[d - 1].add_aff(pts[i], false);
-        else if (d < 0) buckets[-d - 1].add_aff(pts[i], true);
-      }
       Ext<K> run = Ext<K>::inf(), acc = Ext<K>::inf();
-      for (size_t k = nb; k-- > 0;) { run.add_ext(buckets[k]); acc.add_ext(run); }
+      if (batch_affine && !(w == nwin - 1 && top_bits < 10)) {
+        abuckets.assign(nb, Aff<K>{K::zero(), K::zero()});
+        BatchAffine<K> ba(abuckets);
+        for (size_t i = lo; i < hi; i++) {
+          int32_t d = dg[i];
+          if (d > 0) ba.add((uint32_t)(d - 1), pts[i]);
+          else if (d < 0) ba.add((uint32_t)(-d - 1), Aff<K>{pts[i].x, pts[i].y.neg()});
+        }
+        ba.finish();
+        for (size_t k = nb; k-- > 0;) { run.add_aff(abuckets[k]); acc.add_ext(run); }
+      } else {
+        buckets.assign(nb, Ext<K>::inf());
+        for (size_t i = lo; i < hi; i++) {
+          int32_t d = dg[i];
+          if (d > 0) buckets[d - 1].add_aff(pts[i], false);
+          else if (d < 0) buckets[-d - 1].add_aff(pts[i], true);
+        }
+        for (size_t k = nb; k-- > 0;) { run.add_ext(buckets[k]); acc.add_ext(run); }
+      }
       partial[task] = acc;
     }
   });
@@ -454,8 +556,9 @@ struct Curve {
 };
 
 template <class K, class S>
-int do_msm(const void* pts, const void* sc, size_t n, int c, int nthreads, int scalar_bits, void* out_jac) {
-  Ext<K> r = msm_pippenger<K, S>((const Aff<K>*)pts, (const S*)sc, n, c, nthreads, scalar_bits);
+int do_msm(const void* pts, const void* sc, size_t n, int c, int nthreads, int scalar_bits, void* out_jac,
+           bool batch_affine = false) {
+  Ext<K> r = msm_pippenger<K, S>((const Aff<K>*)pts, (const S*)sc, n, c, nthreads, scalar_bits, batch_affine);
   *(Jac<K>*)out_jac = r.to_jac();
   return 0;
 }
@@ -495,6 +598,15 @@ int orc_msm(const u64* p_mod, int np, const u64* r_mod, int nr, int deg, int bet
   DISPATCH(4, 4, (do_msm<K, S>(pts, sc, n, c, nthreads, sb, out_jac)), (do_msm<K, S>(pts, sc, n, c, nthreads, sb, out_jac)))
   DISPATCH(6, 4, (do_msm<K, S>(pts, sc, n, c, nthreads, sb, out_jac)), (do_msm<K, S>(pts, sc, n, c, nthreads, sb, out_jac)))
   DISPATCH(12, 6, (do_msm<K, S>(pts, sc, n, c, nthreads, sb, out_jac)), (do_msm<K, S>(pts, sc, n, c, nthreads, sb, out_jac)))
+  return -1;
+}
+// same result, buckets kept affine with batched additions (gnark-crypto's choice for large windows)
+int orc_msm_batch_affine(const u64* p_mod, int np, const u64* r_mod, int nr, int deg, int beta, const void* pts,
+                         const void* sc, size_t n, int c, int nthreads, void* out_jac) {
+  int sb = bitlen(r_mod, nr);
+  DISPATCH(4, 4, (do_msm<K, S>(pts, sc, n, c, nthreads, sb, out_jac, true)), (do_msm<K, S>(pts, sc, n, c, nthreads, sb, out_jac, true)))
+  DISPATCH(6, 4, (do_msm<K, S>(pts, sc, n, c, nthreads, sb, out_jac, true)), (do_msm<K, S>(pts, sc, n, c, nthreads, sb, out_jac, true)))
+  DISPATCH(12, 6, (do_msm<K, S>(pts, sc, n, c, nthreads, sb, out_jac, true)), (do_msm<K, S>(pts, sc, n, c, nthreads, sb, out_jac, true)))
   return -1;
 }
 int orc_msm_naive(const u64* p_mod, int np, const u64* r_mod, int nr, int deg, int beta, const void* pts,

@@ -34,6 +34,37 @@ def test_msm_and_fixed_base(c, group):
 
 
 @pytest.mark.parametrize("c", ALL, ids=lambda c: c.name)
+@pytest.mark.parametrize("group", (1, 2))
+def test_msm_batch_affine_variant(c, group):
+    """the CPU arm's batch-affine buckets (gnark-crypto's large-window path) against the big-int oracle, on inputs
+    that hit every special case of an affine addition: repeated points (doubling), P and -P in one bucket
+    (cancellation), points at infinity, zero scalars, more operations than one batch, bucket collisions."""
+    rng = random.Random(21 + group)
+    F, base = pick_base(c, group, rng)
+    n = 700
+    ks = [rng.randrange(1, c.r) for _ in range(n)]
+    for i in range(0, 60, 3):            # same base three times in a row ...
+        ks[i + 1] = ks[i]
+        ks[i + 2] = c.r - ks[i]          # ... and its negative
+    KS = ff.pack_elements(ks, c.r, c.fr_limbs)
+    PTS = corelib.fixed_base(c, group, ec.pack_points(c, group, [base]), KS)
+    PTS[100] = 0                          # (0,0) = infinity
+    ks[100] = 0
+    sc = [rng.randrange(c.r) for _ in range(n)]
+    for i in range(0, 60, 3):            # identical digits -> identical buckets in every window
+        sc[i + 1] = sc[i + 2] = sc[i]
+    sc[200], sc[201], sc[202] = 0, c.r - 1, 1
+    for i in range(300, 400):             # tiny scalars: one hot bucket in the lowest window only
+        sc[i] = 1 + (i & 1)
+    SC = ff.pack_elements(sc, c.r, c.fr_limbs)
+    exp = ec.scalar_mul(F, sum(s * k for s, k in zip(sc, ks)) % c.r, base)
+    for cw in (4, 10, 13):
+        for threads in (1, 3):
+            got = corelib.msm(c, group, PTS, SC, c=cw, nthreads=threads, batch_affine=True)
+            assert ec.from_jac(F, ec.unpack_points(c, group, got, ncoords=3)[0]) == exp, (cw, threads)
+
+
+@pytest.mark.parametrize("c", ALL, ids=lambda c: c.name)
 def test_ntt(c):
     rng = random.Random(5)
     for logn in (0, 1, 5, 9):
