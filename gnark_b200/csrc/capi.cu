@@ -52,6 +52,9 @@ int32_t device_ctx(int dev, DeviceCtx** out) {
     CK(cudaEventCreateWithFlags(&c.tail_ev, cudaEventDisableTiming));
     CK(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&c.copy_ev, cudaEventDisableTiming));
+    CK(cudaStreamCreateWithFlags(&c.aux_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&c.aux_fork_ev, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c.aux_join_ev, cudaEventDisableTiming));
     cudaMemPool_t pool;
     CK(cudaDeviceGetDefaultMemPool(&pool, dev));
     uint64_t thr = UINT64_MAX;  // keep freed workspace cached in the pool
@@ -113,9 +116,10 @@ int32_t msm_on_stream(DeviceCtx* ctx, b200_table_s* t, size_t off, size_t n, con
   CK(t->ops->ws_bytes((uint32_t)n, (uint32_t)t->n, t->c, t->precomp, task_len, chunk, &ws_bytes));
   void* ws = nullptr;
   CK(cudaMallocAsync(&ws, ws_bytes, ctx->stream));
+  MsmHybrid hy{t->d_points52, t->hybrid52_of_16, ctx->aux_stream, ctx->aux_fork_ev, ctx->aux_join_ev};
   cudaError_t e = t->ops->run(ctx->stream, (uint32_t)n, (uint32_t)t->n, (uint32_t)off, t->c, t->precomp, task_len, chunk,
                               t->d_points, d_scalars, d_out, ws, stage_events, pipelined ? ctx->tail_stream : nullptr,
-                              ctx->fork_ev, t->fmt52);
+                              ctx->fork_ev, t->fmt52, t->hybrid52_of_16 > 0 ? &hy : nullptr);
   // the workspace is last used by the tail kernels
   cudaError_t e2 = cudaFreeAsync(ws, pipelined ? ctx->tail_stream : ctx->stream);
   if (pipelined && e == cudaSuccess) {
@@ -272,6 +276,17 @@ int32_t b200_table_upload(int32_t dev, int32_t curve, int32_t group, const void*
     CK(cudaMalloc(&t->d_points, t->bytes));
     if (n) CK(cudaMemcpyAsync(t->d_points, points, n * ops->affine_bytes, kind, ctx->stream));
     if (t->precomp) CK(ops->precompute(ctx->stream, (uint32_t)n, t->nwin, t->c, t->d_points));
+    // opt-in hybrid accumulate: GB200_MSM_HYBRID = percentage of the accumulate work given to the FP64-pipe
+    // kernel running concurrently with the IMAD.WIDE kernel; needs the table in both formats
+    const int pct = env_int("GB200_MSM_HYBRID", 0);
+    if (pct > 0 && pct < 100 && t->precomp && ops->affine52_bytes && n > 0) {
+      int k = (pct * 16 + 50) / 100;
+      t->hybrid52_of_16 = k < 1 ? 1 : (k > 15 ? 15 : k);
+      const size_t bytes52 = slabs * n * ops->affine52_bytes;
+      CK(cudaMalloc(&t->d_points52, bytes52));
+      CK(ops->precompute52(ctx->stream, (uint32_t)n, t->nwin, t->c, t->d_points, t->d_points52));
+      t->bytes += bytes52;
+    }
   }
   CK(cudaStreamSynchronize(ctx->stream));
   *out = t.release();
@@ -285,6 +300,7 @@ int32_t b200_table_free(b200_table_t t) {
   DeviceCtx* ctx; int32_t rc = device_ctx(t->dev, &ctx); if (rc) return rc;
   CK(cudaStreamSynchronize(ctx->stream));
   CK(cudaFree(t->d_points));
+  if (t->d_points52) CK(cudaFree(t->d_points52));
   delete t;
   return 0;
   GUARD_END

@@ -30,6 +30,9 @@ struct DeviceCtx {
   cudaEvent_t fork_ev = nullptr;   // accumulate done (recorded on stream)
   cudaEvent_t tail_ev = nullptr;   // tail done (recorded on tail_stream)
   bool tail_pending = false;
+  // opt-in hybrid accumulate (MsmHybrid): second stream for the FP64-pipe kernel
+  cudaStream_t aux_stream = nullptr;
+  cudaEvent_t aux_fork_ev = nullptr, aux_join_ev = nullptr;
 };
 
 int32_t set_error(const std::string& msg);
@@ -47,6 +50,8 @@ struct b200_table_s {
   int fmt52 = 0;     // entries are Affine52 (FP64-pipe accumulate)
   size_t bytes;
   void* d_points = nullptr;
+  void* d_points52 = nullptr;   // hybrid accumulate only: the same table in Affine52 format
+  int hybrid52_of_16 = 0;       // 0 = off
   const gb200::MsmOps* ops;
 };
 

@@ -170,6 +170,72 @@ int msm_emu52(const void* points_, const void* scalars_, uint32_t n, int c, uint
   return 0;
 }
 
+// the opt-in hybrid accumulate (MsmHybrid): the launch geometry of k_msm_accumulate_split and
+// k_msm_accumulate52_split walked block by block; every task must be produced exactly once
+template <class Fr, class F, class P52>
+int msm_emu_hybrid(const void* points_, const void* scalars_, uint32_t n, int c, uint32_t task_len, uint32_t chunk,
+                   int blocks52_of_16, void* out_jac) {
+  const int old = fegetround();
+  fesetround(FE_TOWARDZERO);
+  const Affine<F>* points = reinterpret_cast<const Affine<F>*>(points_);
+  const Fr* scalars = reinterpret_cast<const Fr*>(scalars_);
+  MsmPlan pl = msm_make_plan(n, n, 0, Fr::Params::BITS, c, 1, task_len, chunk);
+  std::vector<Affine<F>> table(points, points + n);
+  table.resize((size_t)n * pl.nwin);
+  for (int w = 1; w < pl.nwin; w++)
+    for (uint32_t i = 0; i < n; i++) table[(size_t)w * n + i] = msm_shift_point(table[(size_t)(w - 1) * n + i], c);
+  std::vector<Affine52<P52>> table52(table.size());
+  for (size_t i = 0; i < table.size(); i++) table52[i] = affine_to_52<P52, F>(table[i]);
+  const size_t m = (size_t)n * pl.nwin;
+  std::vector<uint32_t> keys(m), vals(m);
+  for (uint32_t i = 0; i < n; i++) msm_decompose_one<Fr>(pl, i, scalars, keys.data(), vals.data());
+  std::vector<uint32_t> order(m);
+  std::iota(order.begin(), order.end(), 0u);
+  std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return keys[x] < keys[y]; });
+  std::vector<uint32_t> skeys(m), svals(m);
+  for (size_t k = 0; k < m; k++) { skeys[k] = keys[order[k]]; svals[k] = vals[order[k]]; }
+  const uint32_t nb = pl.total_buckets;
+  std::vector<uint32_t> off(nb + 1), task_off(nb + 1);
+  for (uint32_t b = 0; b <= nb; b++) off[b] = (uint32_t)(std::lower_bound(skeys.begin(), skeys.end(), b) - skeys.begin());
+  uint32_t acc_t = 0;
+  for (uint32_t b = 0; b < nb; b++) { task_off[b] = acc_t; acc_t += (off[b + 1] - off[b] + pl.task_len - 1) / pl.task_len; }
+  task_off[nb] = acc_t;
+  const size_t max_tasks = m / pl.task_len + nb + 1;      // msm_layout
+  if (acc_t > max_tasks) return -2;
+  std::vector<XYZZ<F>> partial(max_tasks);
+  std::vector<int> produced(max_tasks, 0);
+  const uint32_t period = 16, n52 = (uint32_t)blocks52_of_16, n32 = period - n52;
+  const uint32_t total_blocks = (uint32_t)((max_tasks + 127) / 128);
+  for (int pass = 0; pass < 2; pass++) {
+    const uint32_t first = pass ? n32 : 0, count = pass ? n52 : n32;
+    const uint32_t grid = msm_split_grid(total_blocks, period, count);
+    for (uint32_t blk = 0; blk < grid; blk++)
+      for (uint32_t tid = 0; tid < 128; tid++) {
+        const uint32_t t = msm_virtual_block(blk, period, first, count) * 128 + tid;
+        uint32_t begin, end;
+        if (!msm_task_bounds(pl, off.data(), task_off.data(), t, begin, end)) continue;
+        produced[t]++;
+        partial[t] = pass ? msm_accumulate_range52<P52, F>(table52.data(), svals.data(), begin, end)
+                          : msm_accumulate_range<F>(table.data(), svals.data(), begin, end);
+      }
+  }
+  for (uint32_t t = 0; t < acc_t; t++) if (produced[t] != 1) return -3;
+  std::vector<XYZZ<F>> buckets(nb);
+  for (uint32_t b = 0; b < nb; b++) {
+    XYZZ<F> acc = XYZZ<F>::inf();
+    for (uint32_t t = task_off[b]; t < task_off[b + 1]; t++) acc.add(partial[t]);
+    buckets[b] = acc;
+  }
+  XYZZ<F> tot = XYZZ<F>::inf();
+  for (uint32_t lo = 0; lo < pl.set_size; lo += pl.chunk) {
+    uint32_t hi = std::min(pl.set_size, lo + pl.chunk);
+    tot.add(msm_reduce_chunk<F>(buckets.data(), lo, hi));
+  }
+  *reinterpret_cast<Jacobian<F>*>(out_jac) = tot.to_jacobian();
+  fesetround(old);
+  return 0;
+}
+
 // the per-point logic of k_plonk_constraints (plonk.cuh) walked sequentially for one coset
 template <class Fr>
 int plonk_coset_emu(const void* const* polys, const void* abg, const void* const* blind, const int* nblind, uint32_t logn,
@@ -266,6 +332,18 @@ int emu_msm52(int curve, const void* points, const void* scalars, uint32_t n, in
     case 1: return msm_emu52<bls12_381_fr, bls12_381_fp, bls12_381_fp_params52>(points, scalars, n, c, task_len, chunk, out_jac);
     case 2: return msm_emu52<bls12_377_fr, bls12_377_fp, bls12_377_fp_params52>(points, scalars, n, c, task_len, chunk, out_jac);
     case 3: return msm_emu52<bw6_761_fr, bw6_761_fp, bw6_761_fp_params52>(points, scalars, n, c, task_len, chunk, out_jac);
+  }
+  return -1;
+}
+
+int emu_msm_hybrid(int curve, const void* points, const void* scalars, uint32_t n, int c, uint32_t task_len,
+                   uint32_t chunk, int blocks52_of_16, void* out_jac) {
+  if (blocks52_of_16 < 1 || blocks52_of_16 > 15) return -1;
+  switch (curve) {
+    case 0: return msm_emu_hybrid<bn254_fr, bn254_fp, bn254_fp_params52>(points, scalars, n, c, task_len, chunk, blocks52_of_16, out_jac);
+    case 1: return msm_emu_hybrid<bls12_381_fr, bls12_381_fp, bls12_381_fp_params52>(points, scalars, n, c, task_len, chunk, blocks52_of_16, out_jac);
+    case 2: return msm_emu_hybrid<bls12_377_fr, bls12_377_fp, bls12_377_fp_params52>(points, scalars, n, c, task_len, chunk, blocks52_of_16, out_jac);
+    case 3: return msm_emu_hybrid<bw6_761_fr, bw6_761_fp, bw6_761_fp_params52>(points, scalars, n, c, task_len, chunk, blocks52_of_16, out_jac);
   }
   return -1;
 }

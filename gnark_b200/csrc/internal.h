@@ -8,6 +8,16 @@
 
 namespace gb200 {
 
+// Opt-in experiment (GB200_MSM_HYBRID=<percent>): the bucket-accumulate tasks are split between the
+// IMAD.WIDE kernel and its FP64-pipe twin, launched concurrently on two streams so that both multiplier
+// pipes of an SM are busy at once (the pipes are independent: profiles/r01_microbench_pipes.txt).
+struct MsmHybrid {
+  const void* d_table52;   // same table in Affine52 format
+  int blocks52_of_16;      // of every 16 consecutive 128-task blocks, this many go to the FP64 kernel (1..15)
+  cudaStream_t aux;        // second stream
+  cudaEvent_t fork_ev, join_ev;
+};
+
 struct MsmOps {
   int scalar_bits;      // Fr bit length
   size_t fr_bytes;      // sizeof(fr.Element)
@@ -20,7 +30,8 @@ struct MsmOps {
   cudaError_t (*run)(cudaStream_t st, uint32_t n, uint32_t stride, uint32_t off, int c, int precomp,
                      uint32_t task_len, uint32_t chunk, const void* d_table, const void* d_scalars, void* d_out_jac,
                      void* ws, cudaEvent_t* stage_events /* nullable, 8 entries */,
-                     cudaStream_t tail /* nullable */, cudaEvent_t fork_ev, int fmt52);
+                     cudaStream_t tail /* nullable */, cudaEvent_t fork_ev, int fmt52,
+                     const MsmHybrid* hybrid /* nullable */);
   // fill slabs 1..nwin-1 of a [nwin][n] table whose slab 0 holds the bases
   cudaError_t (*precompute)(cudaStream_t st, uint32_t n, int nwin, int c, void* d_table);
   // FP64-pipe table format (field52.cuh): bytes per entry, 0 when the group has no such path

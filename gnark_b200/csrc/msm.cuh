@@ -126,6 +126,33 @@ HD XYZZ<F> msm_accumulate_range52(const Affine52<P52>* table, const uint32_t* va
   return acc.template to_xyzz32<F>();
 }
 
+// ---- 4b. hybrid split of the accumulate tasks ---------------------------------
+// Hybrid split (opt-in, MsmHybrid): the same two kernels over a SUBSET of the 128-task blocks.  Of every
+// `period` consecutive virtual blocks, `count` starting at `first` belong to this launch:
+//   virtual block = (blockIdx / count) * period + first + blockIdx % count
+HD uint32_t msm_virtual_block(uint32_t block, uint32_t period, uint32_t first, uint32_t count) {
+  return (block / count) * period + first + block % count;
+}
+HD uint32_t msm_split_grid(uint32_t total_blocks, uint32_t period, uint32_t count) {
+  return ((total_blocks + period - 1) / period) * count;
+}
+// entries [begin, end) of task t (false: t is past the last task); the same arithmetic as k_msm_accumulate
+HD bool msm_task_bounds(const MsmPlan& pl, const uint32_t* off, const uint32_t* task_off, uint32_t t, uint32_t& begin,
+                        uint32_t& end) {
+  const uint32_t nb = pl.total_buckets;
+  if (t >= task_off[nb]) return false;
+  uint32_t lo = 0, hi = nb;
+  while (lo < hi) {     // bucket of task t: largest b with task_off[b] <= t
+    const uint32_t mid = lo + ((hi - lo + 1) >> 1);
+    if (task_off[mid] <= t) lo = mid; else hi = mid - 1;
+  }
+  const uint32_t j = t - task_off[lo];
+  begin = off[lo] + j * pl.task_len;
+  end = begin + pl.task_len;
+  if (end > off[lo + 1]) end = off[lo + 1];
+  return true;
+}
+
 // ---- 5. reduce -------------------------------------------------------------
 // chunk t of a set covers buckets [lo, hi) (set-local, weight of bucket k is k+1):
 // returns sum_k (k+1) * B_k over the chunk.

@@ -4,6 +4,7 @@
 #include <cub/cub.cuh>
 #include <cuda_runtime.h>
 
+#include "internal.h"
 #include "msm.cuh"
 
 namespace gb200 {
@@ -91,6 +92,32 @@ __global__ void __launch_bounds__(128) k_msm_accumulate52(MsmPlan pl, const Affi
   uint32_t end = begin + pl.task_len;
   const uint32_t bend = __ldg(off + b + 1);
   if (end > bend) end = bend;
+  partial[t] = msm_accumulate_range52<P52, F>(table, svals, begin, end);
+}
+
+// Hybrid split (opt-in, MsmHybrid; index helpers in msm.cuh)
+template <class F>
+__global__ void __launch_bounds__(128) k_msm_accumulate_split(MsmPlan pl, const Affine<F>* __restrict__ table,
+                                                              const uint32_t* __restrict__ svals,
+                                                              const uint32_t* __restrict__ off,
+                                                              const uint32_t* __restrict__ task_off,
+                                                              XYZZ<F>* __restrict__ partial, uint32_t period,
+                                                              uint32_t first, uint32_t count) {
+  const uint32_t t = msm_virtual_block(blockIdx.x, period, first, count) * blockDim.x + threadIdx.x;
+  uint32_t begin, end;
+  if (!msm_task_bounds(pl, off, task_off, t, begin, end)) return;
+  partial[t] = msm_accumulate_range<F>(table, svals, begin, end);
+}
+template <class F, class P52>
+__global__ void __launch_bounds__(128) k_msm_accumulate52_split(MsmPlan pl, const Affine52<P52>* __restrict__ table,
+                                                                const uint32_t* __restrict__ svals,
+                                                                const uint32_t* __restrict__ off,
+                                                                const uint32_t* __restrict__ task_off,
+                                                                XYZZ<F>* __restrict__ partial, uint32_t period,
+                                                                uint32_t first, uint32_t count) {
+  const uint32_t t = msm_virtual_block(blockIdx.x, period, first, count) * blockDim.x + threadIdx.x;
+  uint32_t begin, end;
+  if (!msm_task_bounds(pl, off, task_off, t, begin, end)) return;
   partial[t] = msm_accumulate_range52<P52, F>(table, svals, begin, end);
 }
 
@@ -325,7 +352,8 @@ inline int msm_set_sum_threads(size_t budget = 160 * 1024) {
 template <class Fr, class F>
 cudaError_t msm_enqueue(cudaStream_t stream, const MsmPlan& pl, const Affine<F>* d_table, const Fr* d_scalars,
                         Jacobian<F>* d_out, void* ws, const MsmLayout<F>& L, cudaEvent_t* ev = nullptr,
-                        cudaStream_t tail = nullptr, cudaEvent_t fork_ev = nullptr, int fmt52 = 0) {
+                        cudaStream_t tail = nullptr, cudaEvent_t fork_ev = nullptr, int fmt52 = 0,
+                        const MsmHybrid* hybrid = nullptr) {
   // tail (optional): the latency-bound reduction kernels that follow the accumulate kernel are
   // enqueued on this second stream (forked with fork_ev), so that in a pipeline of MSMs they
   // overlap the next MSM's sort/accumulate instead of idling 140+ SMs.
@@ -366,7 +394,25 @@ cudaError_t msm_enqueue(cudaStream_t stream, const MsmPlan& pl, const Affine<F>*
   cub_bytes = L.cub_bytes;
   GB_CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, ntasks, task_off, (int)nb + 1, stream));
   GB_EV(3);
+  bool done = false;
   if constexpr (F52Traits<F>::ok) {
+    if (hybrid && !fmt52 && hybrid->d_table52 && hybrid->blocks52_of_16 > 0 && hybrid->blocks52_of_16 < 16) {
+      using P52 = typename F52Traits<F>::P52;
+      const uint32_t period = 16, n52 = (uint32_t)hybrid->blocks52_of_16, n32 = period - n52;
+      const uint32_t total_blocks = (uint32_t)((L.max_tasks + 127) / 128);
+      GB_CUDA_TRY(cudaEventRecord(hybrid->fork_ev, stream));
+      GB_CUDA_TRY(cudaStreamWaitEvent(hybrid->aux, hybrid->fork_ev, 0));
+      k_msm_accumulate52_split<F, P52><<<msm_split_grid(total_blocks, period, n52), 128, 0, hybrid->aux>>>(
+          pl, reinterpret_cast<const Affine52<P52>*>(hybrid->d_table52), vals1, off, task_off, partial, period, n32, n52);
+      GB_CUDA_TRY(cudaEventRecord(hybrid->join_ev, hybrid->aux));
+      k_msm_accumulate_split<F><<<msm_split_grid(total_blocks, period, n32), 128, 0, stream>>>(
+          pl, d_table, vals1, off, task_off, partial, period, 0, n32);
+      GB_CUDA_TRY(cudaStreamWaitEvent(stream, hybrid->join_ev, 0));
+      done = true;
+    }
+  }
+  if (done) {
+  } else if constexpr (F52Traits<F>::ok) {
     if (fmt52) {
       using P52 = typename F52Traits<F>::P52;
       k_msm_accumulate52<F, P52><<<(unsigned)((L.max_tasks + 127) / 128), 128, 0, stream>>>(

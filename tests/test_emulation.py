@@ -164,6 +164,28 @@ def test_msm_fp64_path_logic(hostemu, c):
         assert ec.from_jac(F, ec.unpack_points(c, 1, out, ncoords=3)[0]) == exp, (c.name, cw)
 
 
+@pytest.mark.parametrize("c", [CURVES["bn254"], CURVES["bls12-381"]], ids=lambda c: c.name)
+def test_msm_hybrid_split_logic(hostemu, c):
+    """opt-in hybrid accumulate (GB200_MSM_HYBRID): the launch geometry of the two split kernels walked block by
+    block - every task produced exactly once, by the 32-bit-limb path or the FP64-pipe path according to its
+    block, same result as the oracle.  Enough entries for several 128-task blocks."""
+    rng = random.Random(29)
+    F, base = pick_base(c, 1, rng)
+    n = 300
+    ks = [rng.randrange(1, 1 << 48) for _ in range(n)]
+    KS = ff.pack_elements(ks, c.r, c.fr_limbs)
+    from oracle import corelib
+    PA = corelib.fixed_base(c, 1, ec.pack_points(c, 1, [base]), KS)
+    sc = [rng.randrange(c.r) for _ in range(n)]
+    sc[0], sc[1], sc[2] = 0, c.r - 1, 1
+    SA = ff.pack_elements(sc, c.r, c.fr_limbs)
+    exp = ec.scalar_mul(F, sum(s * k for s, k in zip(sc, ks)) % c.r, base)
+    for (cw, tl, ch, k52) in ((5, 2, 4, 5), (6, 3, 8, 15)):
+        out = np.zeros(3 * c.fp_limbs, dtype=np.uint64)
+        assert hostemu.emu_msm_hybrid(c.curve_id, P(PA), P(SA), n, cw, tl, ch, k52, P(out)) == 0
+        assert ec.from_jac(F, ec.unpack_points(c, 1, out, ncoords=3)[0]) == exp, (c.name, cw, k52)
+
+
 @pytest.mark.parametrize("c", [CURVES["bn254"], CURVES["bls12-381"], CURVES["bw6-761"]], ids=lambda c: c.name)
 def test_plonk_constraint_kernel_logic(hostemu, c):
     """per-point logic of k_plonk_constraints (gate + permutation + L1 with blinding, bit-reversed scatter)

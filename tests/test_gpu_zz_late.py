@@ -5,6 +5,7 @@ plonk) has already reported before these run.
   * test_cuda_reproduces_golden   - the CUDA path on the committed known-answer vectors (tests/golden)
   * test_full_prover_vs_oracle    - the device PLONK prover (gnark_b200/plonk.py) against the big-int oracle
                                     prover, same injected challenges (xfail-guarded until run on hardware)
+  * test_msm_hybrid_accumulate    - opt-in experiment GB200_MSM_HYBRID (both multiplier pipes at once)
 """
 import json
 import os
@@ -98,3 +99,24 @@ def test_full_prover_vs_oracle(gpu, c, logn):
     assert got.BatchedClaimedValues == want.claimed
     assert got.ZShiftedClaimedValue == want.zu
     pk.free()
+
+
+@pytest.mark.xfail(strict=False, reason="opt-in experiment written after this round's GPU budget was spent; both kernels "
+                   "and the split geometry are validated separately, the concurrent launch is not yet")
+@pytest.mark.parametrize("cname", ["bn254", "bls12-381"])
+@pytest.mark.parametrize("pct", [30, 70])
+def test_msm_hybrid_accumulate(gpu, monkeypatch, cname, pct):
+    """opt-in GB200_MSM_HYBRID: accumulate tasks split between the IMAD.WIDE kernel and the FP64-pipe kernel on
+    two concurrent streams (CPU twin: tests/test_emulation.py::test_msm_hybrid_split_logic); known-dlog oracle"""
+    from util import known_dlog_instance
+    c = CURVES[cname]
+    monkeypatch.setenv("GB200_MSM_HYBRID", str(pct))
+    _, _, pts, sc, expected = known_dlog_instance(c, 1, 20000, seed=pct)
+    t = gpu.Table(c.curve_id, 1, pts, precomp=True)
+    for _ in range(3):      # repeated: the fork/join events are reused across calls
+        assert jac_to_affine(c, 1, t.msm(sc)) == expected
+    t.free()
+    monkeypatch.delenv("GB200_MSM_HYBRID")
+    t = gpu.Table(c.curve_id, 1, pts, precomp=True)
+    assert jac_to_affine(c, 1, t.msm(sc)) == expected
+    t.free()
