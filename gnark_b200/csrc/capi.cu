@@ -2,6 +2,7 @@
 // MSM base tables, MSM, NTT, vector ops.  The Groth16 host layer lives in
 // groth16_host.cu.  Requires a CUDA device: there is no CPU fallback.
 #include "capi_common.h"
+#include "fixed_base.cuh"
 
 namespace gb200 {
 
@@ -324,6 +325,37 @@ int32_t b200_msm_async(b200_table_t t, size_t off, size_t n, const void* d_scala
   if (!t) return set_error("msm: null table");
   DeviceCtx* ctx; int32_t rc = device_ctx(t->dev, &ctx); if (rc) return rc;
   return msm_on_stream(ctx, t, off, n, d_scalars, d_out);
+  GUARD_END
+}
+
+int32_t b200_fixed_base_batch(int32_t dev, int32_t curve, int32_t group, const void* base_affine,
+                              const void* scalars, int32_t scalars_on_device, size_t n, void* out_affine,
+                              int32_t out_on_device) {
+  GUARD_BEGIN
+  DeviceCtx* ctx; int32_t rc = device_ctx(dev, &ctx); if (rc) return rc;
+  const MsmOps* ops = get_msm_ops(curve, group);
+  if (!ops) return set_error("fixed_base_batch: unsupported curve/group");
+  if (!base_affine || (n && (!scalars || !out_affine))) return set_error("fixed_base_batch: null argument");
+  if (n == 0) return 0;
+  rc = msm_join(ctx); if (rc) return rc;
+  void* d_sc = const_cast<void*>(scalars);
+  void* d_out = out_affine;
+  if (!scalars_on_device) {
+    CK(cudaMallocAsync(&d_sc, n * ops->fr_bytes, ctx->stream));
+    CK(cudaMemcpyAsync(d_sc, scalars, n * ops->fr_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  if (!out_on_device) CK(cudaMallocAsync(&d_out, n * ops->affine_bytes, ctx->stream));
+  int c = env_int("GB200_FIXED_BASE_WINDOW", 0);
+  if (c < 2 || c > 16) c = fixed_base_window_for(n);
+  cudaError_t e = ops->fixed_base(ctx->stream, base_affine, d_sc, n, c, d_out);
+  if (e == cudaSuccess && !out_on_device)
+    e = cudaMemcpyAsync(out_affine, d_out, n * ops->affine_bytes, cudaMemcpyDeviceToHost, ctx->stream);
+  if (!scalars_on_device) cudaFreeAsync(d_sc, ctx->stream);
+  if (!out_on_device) cudaFreeAsync(d_out, ctx->stream);
+  cudaError_t e2 = cudaStreamSynchronize(ctx->stream);   // host pointers are only borrowed for the call
+  if (e != cudaSuccess) return cuda_fail("fixed_base_batch", e);
+  if (e2 != cudaSuccess) return cuda_fail("fixed_base_batch", e2);
+  return 0;
   GUARD_END
 }
 

@@ -13,6 +13,7 @@
 #include <cfenv>
 
 #include "curve52.cuh"
+#include "fixed_base.cuh"
 #include "msm.cuh"
 #include "ntt.cuh"
 #include "plonk.cuh"
@@ -236,6 +237,28 @@ int msm_emu_hybrid(const void* points_, const void* scalars_, uint32_t n, int c,
   return 0;
 }
 
+// fixed-base batch (fixed_base.cuh): the kernels' per-thread functions walked sequentially
+template <class Fr, class F>
+int fixed_base_emu(const void* base_, const void* scalars_, uint32_t n, int c, void* out_) {
+  const Affine<F> base = *reinterpret_cast<const Affine<F>*>(base_);
+  const Fr* scalars = reinterpret_cast<const Fr*>(scalars_);
+  Affine<F>* out = reinterpret_cast<Affine<F>*>(out_);
+  const FixedBasePlan pl = fixed_base_plan(Fr::Params::BITS, c);
+  if (pl.nwin > FB_MAX_WINDOWS) return -2;
+  std::vector<Affine<F>> Pw(pl.nwin);
+  for (int w = 0; w < pl.nwin; w++) Pw[w] = fixed_base_window_base<F>(base, c, w).to_affine();        // k_fb_window_bases
+  const size_t entries = (size_t)pl.nwin * pl.half;
+  std::vector<XYZZ<F>> tmp(std::max(entries, (size_t)n));
+  for (size_t t = 0; t < entries; t++) tmp[t] = fixed_base_entry<F>(Pw[t / pl.half], (uint32_t)(t % pl.half));  // k_fb_table
+  std::vector<Affine<F>> table(entries);
+  for (size_t first = 0; first < entries; first += FB_CHUNK)                                            // k_fb_to_affine
+    xyzz_batch_to_affine<F>(tmp.data() + first, table.data() + first, (uint32_t)std::min((size_t)FB_CHUNK, entries - first));
+  for (uint32_t i = 0; i < n; i++) tmp[i] = fixed_base_eval<Fr, F>(pl, table.data(), scalars[i]);      // k_fb_eval
+  for (size_t first = 0; first < n; first += FB_CHUNK)
+    xyzz_batch_to_affine<F>(tmp.data() + first, out + first, (uint32_t)std::min((size_t)FB_CHUNK, (size_t)n - first));
+  return 0;
+}
+
 // the per-point logic of k_plonk_constraints (plonk.cuh) walked sequentially for one coset
 template <class Fr>
 int plonk_coset_emu(const void* const* polys, const void* abg, const void* const* blind, const int* nblind, uint32_t logn,
@@ -344,6 +367,20 @@ int emu_msm_hybrid(int curve, const void* points, const void* scalars, uint32_t 
     case 1: return msm_emu_hybrid<bls12_381_fr, bls12_381_fp, bls12_381_fp_params52>(points, scalars, n, c, task_len, chunk, blocks52_of_16, out_jac);
     case 2: return msm_emu_hybrid<bls12_377_fr, bls12_377_fp, bls12_377_fp_params52>(points, scalars, n, c, task_len, chunk, blocks52_of_16, out_jac);
     case 3: return msm_emu_hybrid<bw6_761_fr, bw6_761_fp, bw6_761_fp_params52>(points, scalars, n, c, task_len, chunk, blocks52_of_16, out_jac);
+  }
+  return -1;
+}
+
+int emu_fixed_base(int curve, int group, const void* base, const void* scalars, uint32_t n, int c, void* out_affine) {
+  switch (curve * 2 + (group - 1)) {
+    case 0: return fixed_base_emu<bn254_fr, bn254_fp>(base, scalars, n, c, out_affine);
+    case 1: return fixed_base_emu<bn254_fr, bn254_fp2>(base, scalars, n, c, out_affine);
+    case 2: return fixed_base_emu<bls12_381_fr, bls12_381_fp>(base, scalars, n, c, out_affine);
+    case 3: return fixed_base_emu<bls12_381_fr, bls12_381_fp2>(base, scalars, n, c, out_affine);
+    case 4: return fixed_base_emu<bls12_377_fr, bls12_377_fp>(base, scalars, n, c, out_affine);
+    case 5: return fixed_base_emu<bls12_377_fr, bls12_377_fp2>(base, scalars, n, c, out_affine);
+    case 6:
+    case 7: return fixed_base_emu<bw6_761_fr, bw6_761_fp>(base, scalars, n, c, out_affine);
   }
   return -1;
 }

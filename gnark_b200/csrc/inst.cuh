@@ -3,6 +3,7 @@
 #pragma once
 #include "host_field.h"
 #include "internal.h"
+#include "fixed_base.cuh"
 #include "msm_impl.cuh"
 #include "ntt_impl.cuh"
 #include "plonk.cuh"
@@ -55,9 +56,16 @@ struct MsmInst {
       return cudaErrorNotSupported;
     }
   }
+  static cudaError_t fixed_base(cudaStream_t st, const void* h_base, const void* d_scalars, size_t n, int c,
+                                void* d_out_affine) {
+    Affine<F> base;
+    memcpy(&base, h_base, sizeof(base));
+    return fixed_base_enqueue<Fr, F>(st, base, reinterpret_cast<const Fr*>(d_scalars), n, c,
+                                     reinterpret_cast<Affine<F>*>(d_out_affine));
+  }
   static const MsmOps* ops() {
     static const MsmOps o = {Fr::Params::BITS, sizeof(Fr), sizeof(Affine<F>), sizeof(Jacobian<F>), &ws_bytes, &run,
-                             &precompute, affine52_bytes(), &precompute52};
+                             &precompute, affine52_bytes(), &precompute52, &fixed_base};
     return &o;
   }
 };

@@ -37,6 +37,8 @@ struct MsmOps {
   // FP64-pipe table format (field52.cuh): bytes per entry, 0 when the group has no such path
   size_t affine52_bytes;
   cudaError_t (*precompute52)(cudaStream_t st, uint32_t n, int nwin, int c, const void* d_src, void* d_table52);
+  // fixed-base batch (fixed_base.cuh): d_out[i] = scalars[i] * base; h_base is ONE affine point on the host
+  cudaError_t (*fixed_base)(cudaStream_t st, const void* h_base, const void* d_scalars, size_t n, int c, void* d_out_affine);
 };
 
 struct NttOps {

@@ -32,7 +32,7 @@ EXPORTS = [
     "b200_vec_batch_invert", "b200_plonk_constraints_coset", "b200_plonk_divide_by_zh",
     "b200_vec_axpy", "b200_vec_scan", "b200_plonk_build_z", "b200_poly_eval", "b200_poly_div_by_linear",
     "b200_point_add_jac", "b200_point_to_affine", "b200_groth16_pk_load", "b200_groth16_pk_free", "b200_groth16_prove", "b200_groth16_msms",
-    "b200_groth16_assemble",
+    "b200_groth16_assemble", "b200_fixed_base_batch",
 ]
 
 
@@ -106,6 +106,7 @@ def load(path: str = None):
     lib.b200_msm_async.argtypes = [vp, sz, sz, vp, vp]
     lib.b200_msm_pipelined.argtypes = [vp, sz, sz, vp, vp]
     lib.b200_msm_join.argtypes = [i32]
+    lib.b200_fixed_base_batch.argtypes = [i32, i32, i32, vp, vp, i32, sz, vp, i32]
     lib.b200_msm_profile.argtypes = [vp, sz, sz, vp, vp, ctypes.POINTER(ctypes.c_float)]
     lib.b200_ntt_domain_new.argtypes = [i32, i32, u32, vp, vp, ctypes.POINTER(vp)]
     lib.b200_ntt_domain_free.argtypes = [vp]
@@ -276,6 +277,22 @@ class Domain:
             self.free()
         except Exception:
             pass
+
+
+def fixed_base_batch(curve: int, group: int, base_affine: np.ndarray, scalars, n: int = None, dev: int = 0,
+                     out=None) -> np.ndarray:
+    """[k_i * base] as affine points (curve.BatchScalarMultiplicationG1/G2).  scalars / out: host numpy arrays or
+    device tensors (anything with data_ptr()); returns out."""
+    frl, fpl, deg = CURVE_SHAPES[curve]
+    cl = fpl * (deg if group == 2 else 1)
+    on_dev = hasattr(scalars, "data_ptr")
+    if n is None:
+        n = (scalars.numel() if on_dev else scalars.size) // frl
+    if out is None:
+        out = np.zeros((n, 2 * cl), dtype=np.uint64)
+    check(load().b200_fixed_base_batch(dev, curve, group, ptr(base_affine), ptr(scalars), 1 if on_dev else 0, n,
+                                       ptr(out), 1 if hasattr(out, "data_ptr") else 0))
+    return out
 
 
 def point_add_jac(curve: int, group: int, acc: np.ndarray, q: np.ndarray) -> np.ndarray:

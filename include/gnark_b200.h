@@ -111,6 +111,16 @@ int32_t b200_msm_profile(b200_table_t bases, size_t off, size_t n, const void* d
 int32_t b200_point_add_jac(int32_t curve, int32_t group, void* acc_jac, const void* q_jac);
 int32_t b200_point_to_affine(int32_t curve, int32_t group, const void* p_jac, void* out_affine);
 
+/* fixed-base batch: out[i] = scalars[i] * base, n affine points in gnark layout (replaces gnark-crypto's
+ * curve.BatchScalarMultiplicationG1/G2 as called by Groth16 Setup, backend/groth16/bn254/setup.go:233,302,
+ * and by the SRS generators test/unsafekzg/kzgsrs.go:198 - SURVEY.md §8(f)-3).  base_affine: ONE point on the
+ * host; scalars: n fr.Elements (Montgomery), host or device; out: n G?Affine, host or device.  Windowed table
+ * of the base built on the device per call (window by batch size), results converted to affine with batched
+ * inversions. */
+int32_t b200_fixed_base_batch(int32_t dev, int32_t curve, int32_t group, const void* base_affine,
+                              const void* scalars_mont, int32_t scalars_on_device, size_t n, void* out_affine,
+                              int32_t out_on_device);
+
 /* ---- NTT (replaces icicle_ntt.InitDomain/ReleaseDomain icicle.go:151,163 and
  *      Ntt :1425,1428,1474; CPU twin fft.Domain.FFT/FFTInverse prove.go:362-386) -
  * generator / coset_gen: one fr.Element (Montgomery) each, NULL = gnark-crypto's

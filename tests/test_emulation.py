@@ -164,6 +164,28 @@ def test_msm_fp64_path_logic(hostemu, c):
         assert ec.from_jac(F, ec.unpack_points(c, 1, out, ncoords=3)[0]) == exp, (c.name, cw)
 
 
+@pytest.mark.parametrize("c", ALL, ids=lambda c: c.name)
+@pytest.mark.parametrize("group", (1, 2))
+def test_fixed_base_batch_logic(hostemu, c, group):
+    """fixed_base.cuh (windowed table of one base, signed digits, batched XYZZ -> affine conversion) walked on the
+    CPU, against big-int scalar multiplication; scalars 0, 1, r-1, all-ones digits, a chunk boundary"""
+    if group == 2 and c.fp_limbs > 6:
+        pytest.skip("BW6-761 G2 shares the Fp instantiation with G1")
+    rng = random.Random(31 + group)
+    F, base = pick_base(c, group, rng)
+    n = 19                                   # one full chunk of 16 + a ragged one
+    ks = [rng.randrange(c.r) for _ in range(n)]
+    ks[0], ks[1], ks[2], ks[3] = 0, 1, c.r - 1, (1 << (c.r.bit_length() - 1)) - 1
+    KS = ff.pack_elements(ks, c.r, c.fr_limbs)
+    BA = ec.pack_points(c, group, [base])
+    for cw in (2, 5, 8):
+        out = np.zeros((n, 2 * c.fp_limbs * (2 if (group == 2 and c.fp2_nonresidue is not None) else 1)), dtype=np.uint64)
+        assert hostemu.emu_fixed_base(c.curve_id, group, P(BA), P(KS), n, cw, P(out)) == 0
+        got = ec.unpack_points(c, group, out)
+        for i in (0, 1, 2, 3, 7, 15, 16, 18):
+            assert got[i] == ec.scalar_mul(F, ks[i], base), (c.name, group, cw, i)
+
+
 @pytest.mark.parametrize("c", [CURVES["bn254"], CURVES["bls12-381"]], ids=lambda c: c.name)
 def test_msm_hybrid_split_logic(hostemu, c):
     """opt-in hybrid accumulate (GB200_MSM_HYBRID): the launch geometry of the two split kernels walked block by

@@ -120,3 +120,30 @@ def test_msm_hybrid_accumulate(gpu, monkeypatch, cname, pct):
     t = gpu.Table(c.curve_id, 1, pts, precomp=True)
     assert jac_to_affine(c, 1, t.msm(sc)) == expected
     t.free()
+
+
+@pytest.mark.xfail(strict=False, reason="entry point written after this round's GPU budget was spent; the per-thread "
+                   "functions are pinned on the CPU by tests/test_emulation.py::test_fixed_base_batch_logic")
+@pytest.mark.parametrize("c", ALL, ids=lambda c: c.name)
+@pytest.mark.parametrize("group", (1, 2))
+def test_fixed_base_batch(gpu, c, group):
+    """b200_fixed_base_batch (curve.BatchScalarMultiplicationG1/G2, setup.go:233,302) against the C++ oracle's
+    fixed-base batch, bit-exact affine points; host and device I/O; edge scalars"""
+    import torch
+    from oracle import corelib
+    from util import pick_base
+    rng = random.Random(61 + group)
+    F, base = pick_base(c, group, rng)
+    n = 3001
+    ks = [rng.randrange(c.r) for _ in range(n)]
+    ks[0], ks[1], ks[2] = 0, 1, c.r - 1
+    KS = ff.pack_elements(ks, c.r, c.fr_limbs)
+    BA = ec.pack_points(c, group, [base])
+    want = corelib.fixed_base(c, group, BA, KS)
+    got = gpu.fixed_base_batch(c.curve_id, group, BA, KS)
+    assert np.array_equal(got.reshape(want.shape), want)
+    d_ks = torch.from_numpy(KS.view(np.int64)).cuda()
+    d_out = torch.zeros(want.size, dtype=torch.int64, device="cuda")
+    gpu.fixed_base_batch(c.curve_id, group, BA, d_ks, n=n, out=d_out)
+    assert np.array_equal(d_out.cpu().numpy().view(np.uint64).reshape(want.shape), want)
+    assert ec.unpack_points(c, group, got)[2] == ec.scalar_mul(F, c.r - 1, base)
