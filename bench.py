@@ -291,6 +291,25 @@ def run_b200(args):
             combine(torch.from_numpy(part.view(np.int64)).cuda())
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    # optional (not yet hardware-validated, off by default): the same K MSMs submitted back to back through
+    # b200_msm_submit - upload of step i+1, compute of step i and tail/download of step i-1 overlap
+    e2e_submit = None
+    if args.e2e_submit and world == 1:
+        try:
+            h_outs = torch.zeros((args.steps, 12), dtype=torch.int64).pin_memory()
+            for _ in range(2):
+                table.msm_submit(h_sc, h_outs[0], n=n)
+            lib.sync(local)
+            t0 = time.perf_counter()
+            for i in range(args.steps):
+                table.msm_submit(h_sc, h_outs[i], n=n)
+            lib.sync(local)
+            dt = time.perf_counter() - t0
+            ok = jac_to_affine(C, h_outs[args.steps - 1].numpy().view(np.uint64)) == expected
+            e2e_submit = {"value": n * args.steps / dt, "unit": UNIT, "ms_per_step": 1e3 * dt / args.steps, "correct": bool(ok),
+                          "note": "b200_msm_submit: K MSMs from pinned host scalars, H2D / compute / tail+D2H overlapped"}
+        except Exception as e:
+            e2e_submit = {"error": repr(e)}
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- stage profile of the dominant kernel (accumulate) ------------------------------
@@ -353,6 +372,7 @@ def run_b200(args):
                                       "source": "profiles/r01_ncu_accumulate_summary.md"},
                      "note": "integer-multiplier bound, not HBM bound: ~1360 IMAD.WIDE per gathered 68 B (DESIGN.md)"},
         "stage_ms": stage_ms,
+        "e2e_submit": e2e_submit,
         "cpu_baseline": cpu_baseline,
         "clocks": clocks,
     }
@@ -484,6 +504,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-groth16", action="store_true", help="skip the secondary Groth16 2^20 prove-time leg")
+    ap.add_argument("--e2e-submit", action="store_true", help="also time the asynchronous host-buffer path (b200_msm_submit)")
     args = ap.parse_args()
     arm_watchdog(WHOLE_RUN_LIMIT_S, code=1)
     if args.impl == "reference":

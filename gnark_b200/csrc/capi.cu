@@ -420,6 +420,41 @@ int32_t b200_msm(b200_table_t t, size_t off, size_t n, const void* scalars, int3
   GUARD_END
 }
 
+// Asynchronous twin of b200_msm for a STREAM of MSMs from host buffers: the scalar upload of call i+1 (copy
+// stream) and the reduction tail + result download of call i (tail stream) overlap the sort/accumulate of the
+// calls around them.  Both host buffers must stay valid until b200_sync(dev) returns - use b200_host_alloc
+// memory (pinned, C-owned: legal to hold across cgo calls), never Go memory.
+int32_t b200_msm_submit(b200_table_t t, size_t off, size_t n, const void* scalars_host, void* out_host) {
+  GUARD_BEGIN
+  if (!t) return set_error("msm_submit: null table");
+  if (!out_host || (n && !scalars_host)) return set_error("msm_submit: null argument");
+  DeviceCtx* ctx; int32_t rc = device_ctx(t->dev, &ctx); if (rc) return rc;
+  void* d_sc = nullptr;
+  void* d_out = nullptr;
+  CK(cudaMallocAsync(&d_out, t->ops->jac_bytes, ctx->stream));
+  if (n) {
+    CK(cudaMallocAsync(&d_sc, n * t->ops->fr_bytes, ctx->copy_stream));
+    CK(cudaMemcpyAsync(d_sc, scalars_host, n * t->ops->fr_bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+    CK(cudaEventRecord(ctx->copy_ev, ctx->copy_stream));
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->copy_ev, 0));
+  }
+  rc = msm_on_stream(ctx, t, off, n, d_sc, d_out, nullptr, /*pipelined=*/true);
+  // the result is produced on the tail stream when the call was pipelined (n > 0), else on the main stream
+  cudaStream_t res_stream = (n > 0) ? ctx->tail_stream : ctx->stream;
+  if (rc == 0) {
+    cudaError_t e = cudaMemcpyAsync(out_host, d_out, t->ops->jac_bytes, cudaMemcpyDeviceToHost, res_stream);
+    if (e != cudaSuccess) rc = cuda_fail("msm_submit result copy", e);
+    if (rc == 0 && n > 0) {   // the join point must cover the download too
+      e = cudaEventRecord(ctx->tail_ev, ctx->tail_stream);
+      if (e != cudaSuccess) rc = cuda_fail("cudaEventRecord", e);
+    }
+  }
+  if (d_sc) cudaFreeAsync(d_sc, ctx->stream);
+  cudaFreeAsync(d_out, res_stream);
+  return rc;
+  GUARD_END
+}
+
 int32_t b200_msm_g1(b200_table_t t, size_t off, size_t n, const void* s, int32_t on_dev, void* out) {
   if (t && t->group != 1) return set_error("msm_g1: table holds G2 points");
   return b200_msm(t, off, n, s, on_dev, out);

@@ -32,7 +32,7 @@ EXPORTS = [
     "b200_vec_batch_invert", "b200_plonk_constraints_coset", "b200_plonk_divide_by_zh",
     "b200_vec_axpy", "b200_vec_scan", "b200_plonk_build_z", "b200_poly_eval", "b200_poly_div_by_linear",
     "b200_point_add_jac", "b200_point_to_affine", "b200_groth16_pk_load", "b200_groth16_pk_free", "b200_groth16_prove", "b200_groth16_msms",
-    "b200_groth16_assemble", "b200_fixed_base_batch",
+    "b200_groth16_assemble", "b200_fixed_base_batch", "b200_msm_submit",
 ]
 
 
@@ -106,6 +106,7 @@ def load(path: str = None):
     lib.b200_msm_async.argtypes = [vp, sz, sz, vp, vp]
     lib.b200_msm_pipelined.argtypes = [vp, sz, sz, vp, vp]
     lib.b200_msm_join.argtypes = [i32]
+    lib.b200_msm_submit.argtypes = [vp, sz, sz, vp, vp]
     lib.b200_fixed_base_batch.argtypes = [i32, i32, i32, vp, vp, i32, sz, vp, i32]
     lib.b200_msm_profile.argtypes = [vp, sz, sz, vp, vp, ctypes.POINTER(ctypes.c_float)]
     lib.b200_ntt_domain_new.argtypes = [i32, i32, u32, vp, vp, ctypes.POINTER(vp)]
@@ -216,6 +217,13 @@ class Table:
     def msm_pipelined(self, d_scalars, d_out, off: int = 0, n: int = None):
         """stream-ordered, tail overlapped with the next call; results valid after join()."""
         check(load().b200_msm_pipelined(self.handle, off, n, ptr(d_scalars), ptr(d_out)))
+
+    def msm_submit(self, h_scalars, h_out, off: int = 0, n: int = None):
+        """asynchronous MSM from PINNED host buffers (torch pinned tensors / b200_host_alloc memory); the result
+        lands in h_out after sync(dev).  Consecutive submissions overlap upload, compute, tail and download."""
+        if n is None:
+            n = h_scalars.numel() // self.fr_limbs
+        check(load().b200_msm_submit(self.handle, off, n, ptr(h_scalars), ptr(h_out)))
 
     def join(self):
         check(load().b200_msm_join(self.dev))

@@ -99,6 +99,12 @@ int32_t b200_msm_async(b200_table_t bases, size_t off, size_t n, const void* d_s
 int32_t b200_msm_pipelined(b200_table_t bases, size_t off, size_t n, const void* d_scalars_mont, void* d_out_jac);
 int32_t b200_msm_join(int32_t dev);
 
+/* Asynchronous MSM from HOST buffers, for a stream of MSMs (the reference issues its MSMs from concurrent
+ * goroutines, prove.go:186-292): scalar upload, compute, reduction tail and result download of consecutive
+ * calls overlap.  scalars_host (n fr.Elements) and out_jac_host (one G?Jac) must be b200_host_alloc memory
+ * and stay untouched until b200_sync(dev) returns; results are valid after b200_sync. */
+int32_t b200_msm_submit(b200_table_t bases, size_t off, size_t n, const void* scalars_host, void* out_jac_host);
+
 /* step profile (the reference's ICICLE_STEP_PROFILE timers, icicle.go:72-75,1088-1094):
  * device milliseconds of the 7 pipeline stages of one MSM - decompose, sort,
  * offsets+task scan, accumulate, combine, reduce chunks, set sum+finish. */
