@@ -1,0 +1,39 @@
+#!/usr/bin/env bash
+# One gpurun call that validates everything written without a GPU and A/B-tests the opt-in kernels:
+#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/gpu_session.sh'
+# Outputs land in gpurun_out/ (copy what is worth keeping into profiles/).
+set -u
+OUT=gpurun_out
+mkdir -p $OUT
+export PYTHONUNBUFFERED=1
+
+echo "== 1. parity suite (validated part first, then the late file)" | tee $OUT/session.log
+timeout 900 python -m pytest tests -q -m gpu -x --deselect tests/test_gpu_zz_late.py 2>&1 | tail -5 | tee -a $OUT/session.log
+timeout 600 python -m pytest tests/test_gpu_zz_late.py -q -m gpu -rxX 2>&1 | tail -40 | tee -a $OUT/session.log
+
+echo "== 2. bench, 1 GPU (with the asynchronous host path)" | tee -a $OUT/session.log
+timeout 600 python bench.py --steps 20 --warmup 3 --e2e-submit > $OUT/bench_n1.json 2> $OUT/bench_n1.err
+tail -c 2000 $OUT/bench_n1.json | tee -a $OUT/session.log
+
+echo "== 3. MSM knob sweeps (every configuration is checked against the known-dlog oracle)" | tee -a $OUT/session.log
+timeout 600 python tools/sweep_msm.py bn254 1 20 --set GB200_MSM_WINDOW=16,17,18,19,20,22 > $OUT/sweep_bn254_window.jsonl 2>> $OUT/session.err
+timeout 600 python tools/sweep_msm.py bn254 1 20 --set GB200_MSM_HYBRID=0,12,25,38,50,62 > $OUT/sweep_bn254_hybrid.jsonl 2>> $OUT/session.err
+timeout 600 python tools/sweep_msm.py bls12-381 1 20 --set GB200_MSM_HYBRID=0,25,38,50,62,75 > $OUT/sweep_bls381_hybrid.jsonl 2>> $OUT/session.err
+timeout 600 python tools/sweep_msm.py bn254 2 20 --set GB200_MSM_WINDOW=14,16,18 > $OUT/sweep_bn254_g2_window.jsonl 2>> $OUT/session.err
+cat $OUT/sweep_*.jsonl | cut -c1-400 | tee -a $OUT/session.log
+
+echo "== 4. ncu: launch list of one Groth16-sized step and full captures of the NTT pass and the G2 accumulate" | tee -a $OUT/session.log
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_g2.csv \
+    python tools/run_msm.py bn254 2 20 1 > $OUT/ncu_g2.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_msm_accumulate -c 1 -o $OUT/ncu_g2_accumulate \
+    python tools/run_msm.py bn254 2 20 1 >> $OUT/ncu_g2.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_ntt_pass -c 2 -o $OUT/ncu_ntt_pass \
+    python -c "
+import numpy as np, torch
+from gnark_b200 import lib
+lib.load(); lib.init([0])
+d = lib.Domain(lib.BN254, 22)
+x = torch.randint(0, 1 << 60, ((1 << 22) * 4,), dtype=torch.int64, device='cuda')
+d.ntt_async(x); lib.sync(0)
+" > $OUT/ncu_ntt.log 2>&1
+ls -la $OUT | tee -a $OUT/session.log
