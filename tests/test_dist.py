@@ -46,3 +46,59 @@ def test_sharded_msm_gloo(b200lib):
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, port, n, ret), nprocs=world, join=True)
     assert all(ret[r] for r in range(world))
+
+
+def _ntt_worker(rank, world, port, cname, logn, ret):
+    """sharded NTT (gnark_b200/parallel_ntt.py) over gloo: the exchange, layouts, twiddles and the DFT over the rank
+    index are the product code; each single-GPU C-ABI call is replaced by its oracle twin (no GPU here)."""
+    import contextlib
+    import types
+    import torch
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from gnark_b200 import lib as real_lib, parallel_ntt as pn, plonk as b200_plonk
+    from oracle import ff, ntt
+    from oracle.params import CURVES
+    from test_plonk_orchestration import make_mock_lib
+    c = CURVES[cname]
+    pn._lib = make_mock_lib(real_lib, [])
+    b200_plonk._new_stream = lambda torch_, dev: types.SimpleNamespace(cuda_stream=1, synchronize=lambda: None)
+    b200_plonk._stream_ctx = lambda torch_, s: contextlib.nullcontext()
+    n = 1 << logn
+    rng = random.Random(4242)                      # same data on every rank
+    x = [rng.randrange(c.r) for _ in range(n)]
+    X = ff.pack_elements(x, c.r, c.fr_limbs).reshape(n, c.fr_limbs)
+    dom = ntt.Domain(c, n)
+    ok = True
+    sd = pn.ShardedDomain(c.curve_id, logn, rank, world)
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.int64).reshape(-1).copy())
+    H = lambda t: t.numpy().view(np.uint64).reshape(-1, c.fr_limbs)
+    for on_coset in (False, True):
+        # forward: natural-order coefficients, CYCLIC shard in -> natural-order evaluations, SLICED shard out
+        want = ntt.bit_reverse(dom.fft(list(x), ntt.DIF, on_coset=on_coset))        # DIF output is bit-reversed
+        W = ff.pack_elements(want, c.r, c.fr_limbs).reshape(n, c.fr_limbs)
+        got = H(sd.forward(T(pn.cyclic_shard(X, world, rank)), on_coset=on_coset))
+        ok &= np.array_equal(got, pn.sliced_shard(W, world, rank))
+        # inverse: SLICED evaluations in -> CYCLIC coefficients out
+        want_i = ntt.bit_reverse(dom.fft_inverse(list(x), ntt.DIF, on_coset=on_coset))
+        WI = ff.pack_elements(want_i, c.r, c.fr_limbs).reshape(n, c.fr_limbs)
+        got_i = H(sd.inverse(T(pn.sliced_shard(X, world, rank)), on_coset=on_coset))
+        ok &= np.array_equal(got_i, pn.cyclic_shard(WI, world, rank))
+        # round trip through the exchange
+        back = H(sd.inverse(sd.forward(T(pn.cyclic_shard(X, world, rank)), on_coset=on_coset), on_coset=on_coset))
+        ok &= np.array_equal(back, pn.cyclic_shard(X, world, rank))
+    # shard helpers are inverse to each other
+    ok &= np.array_equal(pn.cyclic_unshard([pn.cyclic_shard(X, world, r) for r in range(world)]), X)
+    ok &= np.array_equal(pn.sliced_unshard([pn.sliced_shard(X, world, r) for r in range(world)]), X)
+    ret[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,cname,logn", [(2, "bn254", 5), (4, "bls12-381", 6)])
+def test_sharded_ntt_gloo(b200lib, world, cname, logn):
+    port = 31500 + random.randrange(2000)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_ntt_worker, args=(world, port, cname, logn, ret), nprocs=world, join=True)
+    assert all(ret[r] for r in range(world))

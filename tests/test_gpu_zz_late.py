@@ -177,3 +177,30 @@ def test_msm_submit_stream_of_msms(gpu):
     assert jac_to_affine(c, 1, h2[0].numpy().view(np.uint64)) == want_half
     assert jac_to_affine(c, 1, h2[1].numpy().view(np.uint64)) is None
     t.free()
+
+
+@pytest.mark.xfail(strict=False, reason="written after this round's GPU budget was spent; the decomposition is pinned on the "
+                   "CPU over gloo (tests/test_dist.py::test_sharded_ntt_gloo)")
+def test_sharded_ntt_single_rank(gpu):
+    """gnark_b200/parallel_ntt.py with world = 1 on the GPU: no exchange, but the stream scoping, the local
+    transform + bit reversal and the coset scaling are the ones every rank runs (multi-rank: tools/bench_sharded_ntt.py)"""
+    import torch
+    from gnark_b200 import parallel_ntt as pn
+    from oracle import ntt
+    c = CURVES["bn254"]
+    logn = 10
+    n = 1 << logn
+    rng = random.Random(5)
+    x = [rng.randrange(c.r) for _ in range(n)]
+    X = ff.pack_elements(x, c.r, c.fr_limbs).reshape(n, c.fr_limbs)
+    dom = ntt.Domain(c, n)
+    sd = pn.ShardedDomain(c.curve_id, logn, 0, 1)
+    for on_coset in (False, True):
+        d = torch.from_numpy(X.view(np.int64).reshape(-1).copy()).cuda()
+        got = sd.forward(d, on_coset=on_coset).cpu().numpy().view(np.uint64)
+        want = ntt.bit_reverse(dom.fft(list(x), ntt.DIF, on_coset=on_coset))
+        assert ff.unpack_elements(got, c.r, c.fr_limbs) == want
+        back = sd.inverse(sd.forward(torch.from_numpy(X.view(np.int64).reshape(-1).copy()).cuda(), on_coset=on_coset),
+                          on_coset=on_coset).cpu().numpy().view(np.uint64)
+        assert ff.unpack_elements(back, c.r, c.fr_limbs) == x
+    sd.free()

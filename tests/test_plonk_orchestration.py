@@ -127,6 +127,18 @@ def make_mock_lib(real_lib, calls):
         y, x = _ints(c, d_y, n), _ints(c, d_x, n)
         _store(c, d_y, [(yy + s * xx) % c.r for yy, xx in zip(y, x)])
 
+    def vec_scale_powers(dev, curve, d, n, s_mont, g_mont):
+        c = BY_ID[curve]
+        s_, g_ = _scalar(c, s_mont), _scalar(c, g_mont)
+        _store(c, d, [x * s_ * pow(g_, i, c.r) % c.r for i, x in enumerate(_ints(c, d, n))])
+
+    def vec_op(dev, curve, op, d_out, d_a, d_b, n):
+        c = BY_ID[curve]
+        a, b = _ints(c, d_a, n), _ints(c, d_b, n)
+        f = (lambda x, y: x * y, lambda x, y: x + y, lambda x, y: x - y)[op]
+        _store(c, d_out, [f(x, y) % c.r for x, y in zip(a, b)])
+
+    m.vec_scale_powers, m.vec_op = vec_scale_powers, vec_op
     m.Domain, m.Table = Domain, Table
     m.vec_bit_reverse, m.plonk_build_z, m.plonk_constraints_coset = vec_bit_reverse, plonk_build_z, plonk_constraints_coset
     m.plonk_divide_by_zh, m.poly_eval, m.poly_div_by_linear, m.vec_axpy = plonk_divide_by_zh, poly_eval, poly_div_by_linear, vec_axpy
