@@ -36,4 +36,14 @@ d = lib.Domain(lib.BN254, 22)
 x = torch.randint(0, 1 << 60, ((1 << 22) * 4,), dtype=torch.int64, device='cuda')
 d.ntt_async(x); lib.sync(0)
 " > $OUT/ncu_ntt.log 2>&1
+echo "== 5. (only under gpurun --gpus 2/4/8) sharded NTT and the sharded configs" | tee -a $OUT/session.log
+NG=$(python -c "import torch; print(torch.cuda.device_count())")
+if [ "$NG" -gt 1 ]; then
+  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29611 \
+      tools/bench_sharded_ntt.py --log2n 24 > $OUT/sharded_ntt_n$NG.json 2>> $OUT/session.err
+  cat $OUT/sharded_ntt_n$NG.json | tee -a $OUT/session.log
+  timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29612 \
+      bench.py --gpus $NG --steps 20 --warmup 3 > $OUT/bench_n$NG.json 2>> $OUT/session.err
+  tail -c 1500 $OUT/bench_n$NG.json | tee -a $OUT/session.log
+fi
 ls -la $OUT | tee -a $OUT/session.log
