@@ -114,13 +114,17 @@ int32_t msm_on_stream(DeviceCtx* ctx, b200_table_s* t, size_t off, size_t n, con
   uint32_t task_len, chunk;
   msm_tuning(n, t->nwin, t->c, t->precomp, &task_len, &chunk);
   size_t ws_bytes = 0;
-  CK(t->ops->ws_bytes((uint32_t)n, (uint32_t)t->n, t->c, t->precomp, task_len, chunk, &ws_bytes));
+  // opt-in: batched-affine tree levels before the XYZZ accumulate (msm_batch.cuh); 0 = off (default)
+  int ba_levels = env_int("GB200_MSM_BATCH_AFFINE", 0);
+  if (ba_levels < 0 || t->fmt52) ba_levels = 0;
+  if (ba_levels > 12) ba_levels = 12;
+  CK(t->ops->ws_bytes((uint32_t)n, (uint32_t)t->n, t->c, t->precomp, task_len, chunk, ba_levels, &ws_bytes));
   void* ws = nullptr;
   CK(cudaMallocAsync(&ws, ws_bytes, ctx->stream));
-  MsmHybrid hy{t->d_points52, t->hybrid52_of_16, ctx->aux_stream, ctx->aux_fork_ev, ctx->aux_join_ev};
+  MsmHybrid hy{t->d_points52, t->hybrid52_of_16, ctx->aux_stream, ctx->aux_fork_ev, ctx->aux_join_ev, ba_levels};
   cudaError_t e = t->ops->run(ctx->stream, (uint32_t)n, (uint32_t)t->n, (uint32_t)off, t->c, t->precomp, task_len, chunk,
                               t->d_points, d_scalars, d_out, ws, stage_events, pipelined ? ctx->tail_stream : nullptr,
-                              ctx->fork_ev, t->fmt52, t->hybrid52_of_16 > 0 ? &hy : nullptr);
+                              ctx->fork_ev, t->fmt52, (t->hybrid52_of_16 > 0 || ba_levels > 0) ? &hy : nullptr);
   // the workspace is last used by the tail kernels
   cudaError_t e2 = cudaFreeAsync(ws, pipelined ? ctx->tail_stream : ctx->stream);
   if (pipelined && e == cudaSuccess) {

@@ -15,6 +15,7 @@
 #include "curve52.cuh"
 #include "fixed_base.cuh"
 #include "msm.cuh"
+#include "msm_batch.cuh"
 #include "ntt.cuh"
 #include "plonk.cuh"
 
@@ -34,6 +35,7 @@ int field_op(int op, const void* a_, const void* b_, void* out_) {
     case 4: r = a.neg(); break;
     case 5: r = a.sqr(); break;
     case 6: r = a.dbl(); break;
+    case 7: r = a.inverse_gcd(); break;
     default: return -1;
   }
   *reinterpret_cast<F*>(out_) = r;
@@ -237,6 +239,86 @@ int msm_emu_hybrid(const void* points_, const void* scalars_, uint32_t n, int c,
   return 0;
 }
 
+// batched-affine tree levels (msm_batch.cuh) in front of the XYZZ accumulate: the per-thread function of
+// k_msm_ba_level walked over the launch geometry of msm_enqueue
+template <class Fr, class F>
+int msm_emu_ba(const void* points_, const void* scalars_, uint32_t n, int c, int precomp, uint32_t task_len,
+               uint32_t chunk, int levels, void* out_jac) {
+  const Affine<F>* points = reinterpret_cast<const Affine<F>*>(points_);
+  const Fr* scalars = reinterpret_cast<const Fr*>(scalars_);
+  MsmPlan pl = msm_make_plan(n, n, 0, Fr::Params::BITS, c, precomp, task_len, chunk);
+  std::vector<Affine<F>> table(points, points + n);
+  if (precomp) {
+    table.resize((size_t)n * pl.nwin);
+    for (int w = 1; w < pl.nwin; w++)
+      for (uint32_t i = 0; i < n; i++) table[(size_t)w * n + i] = msm_shift_point(table[(size_t)(w - 1) * n + i], c);
+  }
+  const size_t m = (size_t)n * pl.nwin;
+  std::vector<uint32_t> keys(m), vals(m);
+  for (uint32_t i = 0; i < n; i++) msm_decompose_one<Fr>(pl, i, scalars, keys.data(), vals.data());
+  std::vector<uint32_t> order(m);
+  std::iota(order.begin(), order.end(), 0u);
+  std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return keys[x] < keys[y]; });
+  std::vector<uint32_t> skeys(m), svals(m);
+  for (size_t k = 0; k < m; k++) { skeys[k] = keys[order[k]]; svals[k] = vals[order[k]]; }
+  const uint32_t nb = pl.total_buckets;
+  std::vector<uint32_t> off(nb + 1);
+  for (uint32_t b = 0; b <= nb; b++) off[b] = (uint32_t)(std::lower_bound(skeys.begin(), skeys.end(), b) - skeys.begin());
+  // levels
+  std::vector<Affine<F>> bufs[2];
+  std::vector<uint32_t> offs[2];
+  const size_t cap[2] = {m / 2 + nb + 1, m / 4 + nb + 1};
+  bufs[0].resize(cap[0]); bufs[1].resize(cap[1]);
+  const uint32_t* off_in = off.data();
+  size_t bound = m;
+  for (int lvl = 0; lvl < levels; lvl++) {
+    std::vector<uint32_t>& off_out = offs[lvl & 1];
+    off_out.assign(nb + 1, 0);
+    uint32_t run = 0;
+    for (uint32_t b = 0; b < nb; b++) { off_out[b] = run; run += msm_ba_next_count(off_in[b + 1] - off_in[b]); }
+    off_out[nb] = run;
+    bound = bound / 2 + nb + 1;
+    if (bound > cap[lvl & 1]) bound = cap[lvl & 1];
+    if (run > bound) return -2;                                  // the grid would not cover the level
+    const size_t threads = (bound + MSM_BA_BATCH - 1) / MSM_BA_BATCH;
+    for (size_t t = 0; t < threads; t++) {
+      const uint64_t o_begin = (uint64_t)t * MSM_BA_BATCH;
+      if (o_begin >= run) continue;
+      const uint32_t o_end = (uint32_t)std::min<uint64_t>(o_begin + MSM_BA_BATCH, run);
+      if (lvl == 0) {
+        BaSrcTable<F> src{table.data(), svals.data()};
+        msm_ba_level_thread<F, BaSrcTable<F>>(src, off_in, off_out.data(), nb, (uint32_t)o_begin, o_end, bufs[0].data());
+      } else {
+        BaSrcPoints<F> src{bufs[(lvl - 1) & 1].data()};
+        msm_ba_level_thread<F, BaSrcPoints<F>>(src, off_in, off_out.data(), nb, (uint32_t)o_begin, o_end, bufs[lvl & 1].data());
+      }
+    }
+    off_in = off_out.data();
+  }
+  if (bound > m) bound = m;
+  std::vector<uint32_t> ident(bound);
+  std::iota(ident.begin(), ident.end(), 0u);
+  const Affine<F>* acc_table = levels ? bufs[(levels - 1) & 1].data() : table.data();
+  const uint32_t* acc_vals = levels ? ident.data() : svals.data();
+  if (levels && off_in[nb] > bound) return -3;
+  std::vector<XYZZ<F>> buckets(nb);
+  for (uint32_t b = 0; b < nb; b++) {
+    XYZZ<F> acc = XYZZ<F>::inf();
+    for (uint32_t s0 = off_in[b]; s0 < off_in[b + 1]; s0 += pl.task_len)
+      acc.add(msm_accumulate_range<F>(acc_table, acc_vals, s0, std::min(off_in[b + 1], s0 + pl.task_len)));
+    buckets[b] = acc;
+  }
+  std::vector<XYZZ<F>> sets(pl.nsets);
+  for (int st = 0; st < pl.nsets; st++) {
+    XYZZ<F> tot = XYZZ<F>::inf();
+    for (uint32_t lo = 0; lo < pl.set_size; lo += pl.chunk)
+      tot.add(msm_reduce_chunk<F>(buckets.data() + (size_t)st * pl.set_size, lo, std::min(pl.set_size, lo + pl.chunk)));
+    sets[st] = tot;
+  }
+  *reinterpret_cast<Jacobian<F>*>(out_jac) = msm_horner<F>(sets.data(), pl.nsets, pl.c).to_jacobian();
+  return 0;
+}
+
 // fixed-base batch (fixed_base.cuh): the kernels' per-thread functions walked sequentially
 template <class Fr, class F>
 int fixed_base_emu(const void* base_, const void* scalars_, uint32_t n, int c, void* out_) {
@@ -367,6 +449,21 @@ int emu_msm_hybrid(int curve, const void* points, const void* scalars, uint32_t 
     case 1: return msm_emu_hybrid<bls12_381_fr, bls12_381_fp, bls12_381_fp_params52>(points, scalars, n, c, task_len, chunk, blocks52_of_16, out_jac);
     case 2: return msm_emu_hybrid<bls12_377_fr, bls12_377_fp, bls12_377_fp_params52>(points, scalars, n, c, task_len, chunk, blocks52_of_16, out_jac);
     case 3: return msm_emu_hybrid<bw6_761_fr, bw6_761_fp, bw6_761_fp_params52>(points, scalars, n, c, task_len, chunk, blocks52_of_16, out_jac);
+  }
+  return -1;
+}
+
+int emu_msm_ba(int curve, int group, const void* points, const void* scalars, uint32_t n, int c, int precomp,
+               uint32_t task_len, uint32_t chunk, int levels, void* out_jac) {
+  switch (curve * 2 + (group - 1)) {
+    case 0: return msm_emu_ba<bn254_fr, bn254_fp>(points, scalars, n, c, precomp, task_len, chunk, levels, out_jac);
+    case 1: return msm_emu_ba<bn254_fr, bn254_fp2>(points, scalars, n, c, precomp, task_len, chunk, levels, out_jac);
+    case 2: return msm_emu_ba<bls12_381_fr, bls12_381_fp>(points, scalars, n, c, precomp, task_len, chunk, levels, out_jac);
+    case 3: return msm_emu_ba<bls12_381_fr, bls12_381_fp2>(points, scalars, n, c, precomp, task_len, chunk, levels, out_jac);
+    case 4: return msm_emu_ba<bls12_377_fr, bls12_377_fp>(points, scalars, n, c, precomp, task_len, chunk, levels, out_jac);
+    case 5: return msm_emu_ba<bls12_377_fr, bls12_377_fp2>(points, scalars, n, c, precomp, task_len, chunk, levels, out_jac);
+    case 6:
+    case 7: return msm_emu_ba<bw6_761_fr, bw6_761_fp>(points, scalars, n, c, precomp, task_len, chunk, levels, out_jac);
   }
   return -1;
 }

@@ -21,9 +21,11 @@ struct MsmInst {
     return msm_make_plan(n, stride, off, Fr::Params::BITS, c, precomp, task_len, chunk);
   }
   static cudaError_t ws_bytes(uint32_t n, uint32_t stride, int c, int precomp, uint32_t task_len, uint32_t chunk,
-                              size_t* out) {
+                              int ba_levels, size_t* out) {
     MsmLayout<F> L;
-    GB_CUDA_TRY(msm_layout<F>(plan(n, stride, 0, c, precomp, task_len, chunk), L));
+    MsmPlan pl = plan(n, stride, 0, c, precomp, task_len, chunk);
+    pl.ba_levels = ba_levels;
+    GB_CUDA_TRY(msm_layout<F>(pl, L));
     *out = L.total;
     return cudaSuccess;
   }
@@ -32,6 +34,7 @@ struct MsmInst {
                          void* d_out_jac, void* ws, cudaEvent_t* ev, cudaStream_t tail, cudaEvent_t fork_ev, int fmt52,
                          const MsmHybrid* hybrid) {
     MsmPlan pl = plan(n, stride, off, c, precomp, task_len, chunk);
+    pl.ba_levels = (hybrid && !fmt52) ? hybrid->ba_levels : 0;
     MsmLayout<F> L;
     GB_CUDA_TRY(msm_layout<F>(pl, L));
     return msm_enqueue<Fr, F>(st, pl, reinterpret_cast<const Affine<F>*>(d_table),

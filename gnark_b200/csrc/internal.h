@@ -16,6 +16,8 @@ struct MsmHybrid {
   int blocks52_of_16;      // of every 16 consecutive 128-task blocks, this many go to the FP64 kernel (1..15)
   cudaStream_t aux;        // second stream
   cudaEvent_t fork_ev, join_ev;
+  // second opt-in experiment (GB200_MSM_BATCH_AFFINE=<levels>, msm_batch.cuh): batched-affine tree levels
+  int ba_levels;
 };
 
 struct MsmOps {
@@ -25,7 +27,7 @@ struct MsmOps {
   size_t jac_bytes;     // sizeof(G?Jac)
   // workspace bytes for an MSM of n scalars with the given parameters
   cudaError_t (*ws_bytes)(uint32_t n, uint32_t stride, int c, int precomp, uint32_t task_len, uint32_t chunk,
-                          size_t* out);
+                          int ba_levels, size_t* out);
   // enqueue a full MSM (all pointers on device)
   cudaError_t (*run)(cudaStream_t st, uint32_t n, uint32_t stride, uint32_t off, int c, int precomp,
                      uint32_t task_len, uint32_t chunk, const void* d_table, const void* d_scalars, void* d_out_jac,

@@ -39,6 +39,7 @@ struct MsmPlan {
   uint32_t total_buckets; // nsets * set_size ; also the "no entry" key
   uint32_t task_len;      // max entries per accumulate task
   uint32_t chunk;         // buckets per level-1 reduction chunk
+  int ba_levels;          // batched-affine tree levels before the XYZZ accumulate (msm_batch.cuh), 0 = off
 };
 
 HD int msm_num_windows(int scalar_bits, int c) { return scalar_bits / c + 1; }
@@ -53,6 +54,7 @@ HD MsmPlan msm_make_plan(uint32_t n, uint32_t table_stride, uint32_t table_off, 
   p.set_size = 1u << (c - 1);
   p.total_buckets = (uint32_t)p.nsets * p.set_size;
   p.task_len = task_len;
+  p.ba_levels = 0;
   p.chunk = chunk;
   return p;
 }

@@ -6,6 +6,7 @@
 
 #include "internal.h"
 #include "msm.cuh"
+#include "msm_batch.cuh"
 
 namespace gb200 {
 
@@ -119,6 +120,28 @@ __global__ void __launch_bounds__(128) k_msm_accumulate52_split(MsmPlan pl, cons
   uint32_t begin, end;
   if (!msm_task_bounds(pl, off, task_off, t, begin, end)) return;
   partial[t] = msm_accumulate_range52<P52, F>(table, svals, begin, end);
+}
+
+// ---- batched-affine tree levels (opt-in, msm_batch.cuh) ----------------------------------
+// cnt[b] = ceil(k_b / 2) for b < nb, cnt[nb] = 0 (so that the exclusive scan yields nb + 1 offsets)
+static __global__ void k_msm_ba_next_counts(const uint32_t* __restrict__ off_in, uint32_t nb, uint32_t* __restrict__ cnt) {
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b > nb) return;
+  cnt[b] = b < nb ? msm_ba_next_count(off_in[b + 1] - off_in[b]) : 0u;
+}
+template <class F, class SRC>
+__global__ void __launch_bounds__(128) k_msm_ba_level(SRC src, const uint32_t* __restrict__ off_in,
+                                                      const uint32_t* __restrict__ off_out, uint32_t nb,
+                                                      Affine<F>* __restrict__ out) {
+  const uint32_t total = off_out[nb];
+  const uint64_t o_begin = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * MSM_BA_BATCH;
+  if (o_begin >= total) return;
+  const uint32_t o_end = (uint32_t)(o_begin + MSM_BA_BATCH < total ? o_begin + MSM_BA_BATCH : total);
+  msm_ba_level_thread<F, SRC>(src, off_in, off_out, nb, (uint32_t)o_begin, o_end, out);
+}
+static __global__ void k_msm_iota(uint32_t* __restrict__ v, uint32_t n) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) v[i] = i;
 }
 
 // one thread per bucket: sum of its task partials.  Buckets with more than MSM_HEAVY partials
@@ -304,6 +327,9 @@ struct MsmLayout {
   // offsets into the workspace
   size_t o_keys0, o_keys1, o_vals0, o_vals1, o_off, o_ntasks, o_task_off, o_partial, o_buckets, o_chunks, o_sets, o_heavy, o_cub,
       total;
+  // batched-affine levels (pl.ba_levels > 0): two ping-pong point buffers, two offset arrays, counts
+  size_t ba_cap_a, ba_cap_b;   // capacities in points
+  size_t o_ba_a, o_ba_b, o_ba_off_a, o_ba_off_b, o_ba_cnt;
 };
 
 inline size_t gb_align(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
@@ -335,6 +361,18 @@ cudaError_t msm_layout(const MsmPlan& pl, MsmLayout<F>& L) {
   L.o_sets = o; o += gb_align((size_t)pl.nsets * sizeof(XYZZ<F>));
   L.o_heavy = o; o += gb_align((L.max_tasks / MSM_HEAVY + 2) * 4);  // [0] = count, [1..] = bucket ids
   L.o_cub = o; o += gb_align(L.cub_bytes);
+  L.ba_cap_a = L.ba_cap_b = 0;
+  L.o_ba_a = L.o_ba_b = L.o_ba_off_a = L.o_ba_off_b = L.o_ba_cnt = 0;
+  if (pl.ba_levels > 0) {
+    // level l holds at most m / 2^l + nb entries (every bucket rounds up once per level)
+    L.ba_cap_a = L.m / 2 + pl.total_buckets + 1;
+    L.ba_cap_b = L.m / 4 + pl.total_buckets + 1;
+    L.o_ba_a = o; o += gb_align(L.ba_cap_a * sizeof(Affine<F>));
+    L.o_ba_b = o; o += gb_align(L.ba_cap_b * sizeof(Affine<F>));
+    L.o_ba_off_a = o; o += gb_align(((size_t)pl.total_buckets + 2) * 4);
+    L.o_ba_off_b = o; o += gb_align(((size_t)pl.total_buckets + 2) * 4);
+    L.o_ba_cnt = o; o += gb_align(((size_t)pl.total_buckets + 2) * 4);
+  }
   L.total = o;
   return cudaSuccess;
 }
@@ -390,13 +428,50 @@ cudaError_t msm_enqueue(cudaStream_t stream, const MsmPlan& pl, const Affine<F>*
                                               stream));
   GB_EV(2);
   k_msm_bucket_offsets<<<(nb + 1 + 255) / 256, 256, 0, stream>>>(keys1, (uint32_t)L.m, nb, off);
+  // what the XYZZ accumulate reads: the table through the sorted values, or (batched-affine levels on) the last
+  // level's points through identity values
+  const Affine<F>* acc_table = d_table;
+  const uint32_t* acc_vals = vals1;
+  if (pl.ba_levels > 0 && !fmt52) {
+    Affine<F>* bufs[2] = {(Affine<F>*)(w + L.o_ba_a), (Affine<F>*)(w + L.o_ba_b)};
+    uint32_t* offs[2] = {(uint32_t*)(w + L.o_ba_off_a), (uint32_t*)(w + L.o_ba_off_b)};
+    uint32_t* cnt = (uint32_t*)(w + L.o_ba_cnt);
+    const uint32_t* off_in = off;
+    size_t bound = L.m;                       // upper bound of the entries of the current level
+    for (int lvl = 0; lvl < pl.ba_levels; lvl++) {
+      uint32_t* off_out = offs[lvl & 1];
+      Affine<F>* out_pts = bufs[lvl & 1];
+      k_msm_ba_next_counts<<<(nb + 1 + 255) / 256, 256, 0, stream>>>(off_in, nb, cnt);
+      cub_bytes = L.cub_bytes;
+      GB_CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, cnt, off_out, (int)nb + 1, stream));
+      bound = bound / 2 + nb + 1;
+      if (bound > ((lvl & 1) ? L.ba_cap_b : L.ba_cap_a)) bound = (lvl & 1) ? L.ba_cap_b : L.ba_cap_a;
+      const size_t threads = (bound + MSM_BA_BATCH - 1) / MSM_BA_BATCH;
+      const unsigned grid = (unsigned)((threads + 127) / 128);
+      if (lvl == 0) {
+        BaSrcTable<F> src{d_table, vals1};
+        k_msm_ba_level<F, BaSrcTable<F>><<<grid, 128, 0, stream>>>(src, off_in, off_out, nb, out_pts);
+      } else {
+        BaSrcPoints<F> src{bufs[(lvl - 1) & 1]};
+        k_msm_ba_level<F, BaSrcPoints<F>><<<grid, 128, 0, stream>>>(src, off_in, off_out, nb, out_pts);
+      }
+      off_in = off_out;
+    }
+    // identity values over the surviving entries (vals0 is free after the sort)
+    if (bound > L.m) bound = L.m;             // entries never increase: the true count is <= m (vals0 holds m)
+    k_msm_iota<<<(unsigned)((bound + 255) / 256), 256, 0, stream>>>(vals0, (uint32_t)bound);
+    acc_table = bufs[(pl.ba_levels - 1) & 1];
+    acc_vals = vals0;
+    off = const_cast<uint32_t*>(off_in);
+  }
   k_msm_task_counts<<<(nb + 1 + 255) / 256, 256, 0, stream>>>(off, nb, pl.task_len, ntasks);
   cub_bytes = L.cub_bytes;
   GB_CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, ntasks, task_off, (int)nb + 1, stream));
   GB_EV(3);
   bool done = false;
   if constexpr (F52Traits<F>::ok) {
-    if (hybrid && !fmt52 && hybrid->d_table52 && hybrid->blocks52_of_16 > 0 && hybrid->blocks52_of_16 < 16) {
+    if (hybrid && !fmt52 && pl.ba_levels == 0 && hybrid->d_table52 && hybrid->blocks52_of_16 > 0 &&
+        hybrid->blocks52_of_16 < 16) {
       using P52 = typename F52Traits<F>::P52;
       const uint32_t period = 16, n52 = (uint32_t)hybrid->blocks52_of_16, n32 = period - n52;
       const uint32_t total_blocks = (uint32_t)((L.max_tasks + 127) / 128);
@@ -418,12 +493,12 @@ cudaError_t msm_enqueue(cudaStream_t stream, const MsmPlan& pl, const Affine<F>*
       k_msm_accumulate52<F, P52><<<(unsigned)((L.max_tasks + 127) / 128), 128, 0, stream>>>(
           pl, reinterpret_cast<const Affine52<P52>*>(d_table), vals1, off, task_off, partial);
     } else {
-      k_msm_accumulate<F><<<(unsigned)((L.max_tasks + 127) / 128), 128, 0, stream>>>(pl, d_table, vals1, off,
+      k_msm_accumulate<F><<<(unsigned)((L.max_tasks + 127) / 128), 128, 0, stream>>>(pl, acc_table, acc_vals, off,
                                                                                      task_off, partial);
     }
   } else {
-    k_msm_accumulate<F><<<(unsigned)((L.max_tasks + 127) / 128), 128, 0, stream>>>(pl, d_table, vals1, off, task_off,
-                                                                                   partial);
+    k_msm_accumulate<F><<<(unsigned)((L.max_tasks + 127) / 128), 128, 0, stream>>>(pl, acc_table, acc_vals, off,
+                                                                                   task_off, partial);
   }
   GB_EV(4);
   if (tail) {

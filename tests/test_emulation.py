@@ -38,6 +38,9 @@ def test_field_ops(hostemu, c):
             if a and trial < 6:
                 hostemu.emu_field_op(fid, 3, P(A), P(B), P(O))
                 assert ff.unpack_elements(O, q, L)[0] == pow(a, -1, q)
+            if a:       # binary-GCD inversion (shift/add only): every trial incl. 1, q-1, R mod q, powers of two
+                hostemu.emu_field_op(fid, 7, P(A), P(B), P(O))
+                assert ff.unpack_elements(O, q, L)[0] == pow(a, -1, q), (c.name, which, "inverse_gcd", trial)
 
 
 @pytest.mark.parametrize("c", [c for c in ALL if c.fp2_nonresidue is not None], ids=lambda c: c.name)
@@ -51,7 +54,7 @@ def test_fp2_ops(hostemu, c):
         A = ff.pack_elements(list(a), c.p, L).reshape(-1)
         B = ff.pack_elements(list(b), c.p, L).reshape(-1)
         O = np.zeros_like(A)
-        for op, exp in ((2, F2.mul(a, b)), (5, F2.sqr(a)), (3, F2.inv(a)), (0, F2.add(a, b)), (1, F2.sub(a, b))):
+        for op, exp in ((2, F2.mul(a, b)), (5, F2.sqr(a)), (3, F2.inv(a)), (7, F2.inv(a)), (0, F2.add(a, b)), (1, F2.sub(a, b))):
             assert hostemu.emu_field_op(100 + c.curve_id * 2, op, P(A), P(B), P(O)) == 0
             assert tuple(ff.unpack_elements(O, c.p, L)) == exp
 
@@ -162,6 +165,38 @@ def test_msm_fp64_path_logic(hostemu, c):
         out = np.zeros(3 * c.fp_limbs, dtype=np.uint64)
         assert hostemu.emu_msm52(c.curve_id, P(PA), P(SA), n, cw, tl, ch, P(out)) == 0
         assert ec.from_jac(F, ec.unpack_points(c, 1, out, ncoords=3)[0]) == exp, (c.name, cw)
+
+
+@pytest.mark.parametrize("c", ALL, ids=lambda c: c.name)
+@pytest.mark.parametrize("group", (1, 2))
+def test_msm_batched_affine_levels_logic(hostemu, c, group):
+    """opt-in GB200_MSM_BATCH_AFFINE: batched-affine tree levels (msm_batch.cuh) in front of the XYZZ accumulate,
+    walked over the launch geometry on the CPU.  Inputs hit every branch of the affine addition: equal points in
+    one bucket (tangent), P and -P (infinity, then infinity + point at the next level), (0,0) bases, odd bucket
+    sizes, empty buckets, more levels than any bucket needs, batches that straddle buckets."""
+    if group == 2 and c.fp_limbs > 6:
+        pytest.skip("BW6-761 G2 shares the Fp instantiation with G1")
+    rng = random.Random(41 + group)
+    F, base = pick_base(c, group, rng)
+    n = 90
+    pts = [ec.scalar_mul(F, rng.randrange(1, 1 << 40), base) for _ in range(12)]
+    pts = [pts[i % 12] for i in range(n)]                 # heavy repetition: equal points meet in buckets
+    pts[3] = ec.INF
+    pts[7] = ec.affine_neg(F, pts[6])
+    sc = [rng.randrange(c.r) for _ in range(n)]
+    for i in range(12, 60):                                 # same scalar for the copies of a base -> P + P, then 2P + 2P
+        sc[i] = sc[i % 12]
+    sc[0], sc[1], sc[2] = 0, c.r - 1, 1
+    sc[6] = sc[7] = 12345                                   # P and -P with the same digits
+    sc[18] = sc[19] = 12345                                 # ... twice: (P - P) + (P - P)
+    exp = ec.msm_naive(F, pts, sc)
+    PA, SA = ec.pack_points(c, group, pts), ff.pack_elements(sc, c.r, c.fr_limbs)
+    for (cw, pre, tl, ch, levels) in ((4, 0, 3, 4, 1), (4, 1, 2, 4, 3), (6, 1, 4, 8, 12), (3, 0, 64, 2, 2)):
+        if pre and c.fp_limbs > 6 and cw < 6:
+            continue                                        # table build by repeated inversion: slow for BW6
+        out = np.zeros(3 * c.fp_limbs * (2 if (group == 2 and c.fp2_nonresidue is not None) else 1), dtype=np.uint64)
+        assert hostemu.emu_msm_ba(c.curve_id, group, P(PA), P(SA), n, cw, pre, tl, ch, levels, P(out)) == 0
+        assert ec.from_jac(F, ec.unpack_points(c, group, out, ncoords=3)[0]) == exp, (c.name, group, cw, pre, levels)
 
 
 @pytest.mark.parametrize("c", ALL, ids=lambda c: c.name)

@@ -204,3 +204,21 @@ def test_sharded_ntt_single_rank(gpu):
                           on_coset=on_coset).cpu().numpy().view(np.uint64)
         assert ff.unpack_elements(back, c.r, c.fr_limbs) == x
     sd.free()
+
+
+@pytest.mark.xfail(strict=False, reason="opt-in experiment written after this round's GPU budget was spent; per-thread logic "
+                   "pinned by tests/test_emulation.py::test_msm_batched_affine_levels_logic")
+@pytest.mark.parametrize("cname,group", [("bn254", 1), ("bn254", 2), ("bls12-381", 1), ("bw6-761", 1)])
+@pytest.mark.parametrize("levels", [1, 4])
+def test_msm_batched_affine_levels(gpu, monkeypatch, cname, group, levels):
+    """opt-in GB200_MSM_BATCH_AFFINE: affine tree levels (one binary-GCD inversion per 32 additions) in front of the
+    XYZZ accumulate; known-dlog oracle, uniform and skewed scalars, precomputed and plain tables"""
+    from util import known_dlog_instance
+    c = CURVES[cname]
+    monkeypatch.setenv("GB200_MSM_BATCH_AFFINE", str(levels))
+    for skew in (False, True):
+        _, _, pts, sc, expected = known_dlog_instance(c, group, 9000, seed=levels + 10 * group, skew=skew)
+        for precomp in (True, False):
+            t = gpu.Table(c.curve_id, group, pts, precomp=precomp)
+            assert jac_to_affine(c, group, t.msm(sc)) == expected
+            t.free()

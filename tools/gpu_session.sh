@@ -20,6 +20,9 @@ timeout 600 python tools/sweep_msm.py bn254 1 20 --set GB200_MSM_WINDOW=16,17,18
 timeout 600 python tools/sweep_msm.py bn254 1 20 --set GB200_MSM_HYBRID=0,12,25,38,50,62 > $OUT/sweep_bn254_hybrid.jsonl 2>> $OUT/session.err
 timeout 600 python tools/sweep_msm.py bls12-381 1 20 --set GB200_MSM_HYBRID=0,25,38,50,62,75 > $OUT/sweep_bls381_hybrid.jsonl 2>> $OUT/session.err
 timeout 600 python tools/sweep_msm.py bn254 2 20 --set GB200_MSM_WINDOW=14,16,18 > $OUT/sweep_bn254_g2_window.jsonl 2>> $OUT/session.err
+timeout 600 python tools/sweep_msm.py bn254 1 20 --set GB200_MSM_BATCH_AFFINE=0,2,4,5,6 > $OUT/sweep_bn254_ba.jsonl 2>> $OUT/session.err
+timeout 600 python tools/sweep_msm.py bn254 2 20 --set GB200_MSM_BATCH_AFFINE=0,3,5 > $OUT/sweep_bn254_g2_ba.jsonl 2>> $OUT/session.err
+timeout 600 python tools/sweep_msm.py bls12-381 1 20 --set GB200_MSM_BATCH_AFFINE=0,3,5 > $OUT/sweep_bls381_ba.jsonl 2>> $OUT/session.err
 cat $OUT/sweep_*.jsonl | cut -c1-400 | tee -a $OUT/session.log
 
 echo "== 4. ncu: launch list of one Groth16-sized step and full captures of the NTT pass and the G2 accumulate" | tee -a $OUT/session.log

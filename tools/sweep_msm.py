@@ -8,6 +8,7 @@ known-discrete-log oracle for every configuration before it is timed):
 
 Knobs (read by the library at table upload / MSM time): GB200_MSM_WINDOW (window bits c), GB200_MSM_HYBRID
 (percent of accumulate blocks on the FP64-pipe kernel, 0 = off), GB200_MSM_FP64 (1 = FP64-pipe kernel only),
+GB200_MSM_BATCH_AFFINE (batched-affine tree levels before the XYZZ accumulate, 0 = off),
 GB200_MSM_TASK_LEN, GB200_MSM_CHUNK, GB200_MSM_PRECOMP.  The cartesian product of all --set lists is run.
 """
 import argparse
