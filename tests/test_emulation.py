@@ -176,6 +176,8 @@ def test_msm_batched_affine_levels_logic(hostemu, c, group):
     sizes, empty buckets, more levels than any bucket needs, batches that straddle buckets."""
     if group == 2 and c.fp_limbs > 6:
         pytest.skip("BW6-761 G2 shares the Fp instantiation with G1")
+    if group == 1 and c.name == "bls12-377":
+        pytest.skip("same limb shape as BLS12-381 G1")
     rng = random.Random(41 + group)
     F, base = pick_base(c, group, rng)
     n = 90
@@ -237,7 +239,7 @@ def test_msm_hybrid_split_logic(hostemu, c):
     sc[0], sc[1], sc[2] = 0, c.r - 1, 1
     SA = ff.pack_elements(sc, c.r, c.fr_limbs)
     exp = ec.scalar_mul(F, sum(s * k for s, k in zip(sc, ks)) % c.r, base)
-    for (cw, tl, ch, k52) in ((5, 2, 4, 5), (6, 3, 8, 15)):
+    for (cw, tl, ch, k52) in (((5, 2, 4, 5), (6, 3, 8, 15)) if c.fp_limbs == 4 else ((6, 3, 8, 11),)):
         out = np.zeros(3 * c.fp_limbs, dtype=np.uint64)
         assert hostemu.emu_msm_hybrid(c.curve_id, P(PA), P(SA), n, cw, tl, ch, k52, P(out)) == 0
         assert ec.from_jac(F, ec.unpack_points(c, 1, out, ncoords=3)[0]) == exp, (c.name, cw, k52)
