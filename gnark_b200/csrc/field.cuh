@@ -175,25 +175,45 @@ struct alignas(16) Fp {
     return result;
   }
   // Same result as inverse() by the binary extended Euclidean algorithm (Kaliski's "almost Montgomery inverse"):
-  // shifts, additions and subtractions only - about 2*BITS iterations on the ALU pipe instead of ~1.5*BITS
-  // Montgomery products on the multiplier pipe.  Phase 1 gives x^-1 * 2^k mod p (BITS <= k <= 2*BITS) for the stored
-  // value x = a*R; a^-1 * R = x^-1 * R^2 = x^-1 * 2^(64N), so phase 2 is 64N - k modular doublings.  Needs the top
-  // bit of the top limb of p clear (r, s < 2p must fit N limbs): true for every modulus here.
+  // shifts, additions and subtractions only, on the ALU pipe instead of ~1.5*BITS Montgomery products on the
+  // multiplier pipe.  Phase 1 gives x^-1 * 2^k mod p (BITS <= k <= 2*BITS) for the stored value x = a*R;
+  // a^-1 * R = x^-1 * R^2 = x^-1 * 2^(64N), so phase 2 is 64N - k modular doublings.  Needs the top bit of the top
+  // limb of p clear (r, s < 2p must fit N limbs): true for every modulus here.
+  // Kaliski's single-bit cases are merged so that a warp does not diverge: with u, v both odd and (u, r) kept as
+  // the larger pair (conditional swap), one iteration is  u -= v; r += s; t = ctz(u); u >>= t; s <<= t; k += t
+  // (his "u > v" step followed by t-1 "u even" steps), about 0.8*BITS iterations in all.
   HD Fp inverse_gcd() const {
     if (is_zero()) return zero();
     uint32_t u[N], v[N], r[N], s[N];
 #pragma unroll
     for (int i = 0; i < N; i++) { u[i] = P::mod(i); v[i] = l[i]; r[i] = 0; s[i] = 0; }
     s[0] = 1;
-    auto shr1 = [](uint32_t* a) {
-#pragma unroll
-      for (int i = 0; i < N - 1; i++) a[i] = (a[i] >> 1) | (a[i + 1] << 31);
-      a[N - 1] >>= 1;
+    auto ctz32 = [](uint32_t x) -> int {
+#if defined(__CUDA_ARCH__)
+      return __ffs((int)x) - 1;
+#else
+      return __builtin_ctz(x);
+#endif
     };
-    auto shl1 = [](uint32_t* a) {
+    auto shr = [](uint32_t* a, int t) {       // 0 < t < 32
 #pragma unroll
-      for (int i = N - 1; i > 0; i--) a[i] = (a[i] << 1) | (a[i - 1] >> 31);
-      a[0] <<= 1;
+      for (int i = 0; i < N - 1; i++) a[i] = (a[i] >> t) | (a[i + 1] << (32 - t));
+      a[N - 1] >>= t;
+    };
+    auto shl = [](uint32_t* a, int t) {       // 0 < t < 32
+#pragma unroll
+      for (int i = N - 1; i > 0; i--) a[i] = (a[i] << t) | (a[i - 1] >> (32 - t));
+      a[0] <<= t;
+    };
+    auto shr_limb = [](uint32_t* a) {
+#pragma unroll
+      for (int i = 0; i < N - 1; i++) a[i] = a[i + 1];
+      a[N - 1] = 0;
+    };
+    auto shl_limb = [](uint32_t* a) {
+#pragma unroll
+      for (int i = N - 1; i > 0; i--) a[i] = a[i - 1];
+      a[0] = 0;
     };
     auto add = [](uint32_t* a, const uint32_t* b) {
       uint64_t c = 0;
@@ -205,26 +225,44 @@ struct alignas(16) Fp {
 #pragma unroll
       for (int i = 0; i < N; i++) { const uint64_t d = (uint64_t)a[i] - b[i] - br; a[i] = (uint32_t)d; br = (d >> 32) & 1; }
     };
-    auto gt = [](const uint32_t* a, const uint32_t* b) {    // a > b
-      for (int i = N - 1; i >= 0; i--) { if (a[i] != b[i]) return a[i] > b[i]; }
-      return false;
-    };
-    auto nonzero = [](const uint32_t* a) { uint32_t t = 0;
+    // -1 / 0 / +1 for a < b / a == b / a > b, without data-dependent branches
+    auto cmp = [](const uint32_t* a, const uint32_t* b) -> int {
+      int res = 0;
 #pragma unroll
-      for (int i = 0; i < N; i++) t |= a[i]; return t != 0; };
+      for (int i = 0; i < N; i++) res = a[i] != b[i] ? (a[i] > b[i] ? 1 : -1) : res;
+      return res;
+    };
     int k = 0;
-    while (nonzero(v)) {
-      if (!(u[0] & 1)) { shr1(u); shl1(s); }
-      else if (!(v[0] & 1)) { shr1(v); shl1(r); }
-      else if (gt(u, v)) { sub(u, v); shr1(u); add(r, s); shl1(s); }
-      else { sub(v, u); shr1(v); add(s, r); shl1(r); }
-      k++;
+    // x is non-zero: strip its trailing zeros (Kaliski's "v even" steps; r = 0 so r <<= t is a no-op)
+    while (v[0] == 0) { shr_limb(v); k += 32; }
+    { const int t = ctz32(v[0]); if (t) { shr(v, t); k += t; } }
+    bool swapped = false;                    // false: (u, r) / (v, s) are Kaliski's pairs; true: exchanged
+    for (;;) {
+      const int c = cmp(u, v);
+      if (c == 0) break;
+      if (c < 0) {                           // keep u > v
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+          const uint32_t tu = u[i]; u[i] = v[i]; v[i] = tu;
+          const uint32_t tr = r[i]; r[i] = s[i]; s[i] = tr;
+        }
+        swapped = !swapped;
+      }
+      sub(u, v);
+      add(r, s);
+      while (u[0] == 0) { shr_limb(u); shl_limb(s); k += 32; }
+      const int t = ctz32(u[0]);             // u - v is even and non-zero: t >= 1 unless whole limbs were stripped
+      if (t) { shr(u, t); shl(s, t); k += t; }
     }
+    // u == v (== gcd = 1): Kaliski's last step  v = 0, s += r, r = 2r, k++  ->  result r
+    uint32_t* rr = swapped ? s : r;
+    shl(rr, 1);
+    k++;
     uint32_t pm[N];
 #pragma unroll
     for (int i = 0; i < N; i++) pm[i] = P::mod(i);
-    if (!gt(pm, r)) sub(r, pm);          // r >= p
-    sub(pm, r);                          // p - r = x^-1 * 2^k mod p
+    if (cmp(rr, pm) >= 0) sub(rr, pm);
+    sub(pm, rr);                             // p - r = x^-1 * 2^k mod p
     Fp out;
 #pragma unroll
     for (int i = 0; i < N; i++) out.l[i] = pm[i];

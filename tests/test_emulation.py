@@ -43,6 +43,28 @@ def test_field_ops(hostemu, c):
                 assert ff.unpack_elements(O, q, L)[0] == pow(a, -1, q), (c.name, which, "inverse_gcd", trial)
 
 
+@pytest.mark.parametrize("c", ALL, ids=lambda c: c.name)
+def test_inverse_gcd_many(hostemu, c):
+    """Fp::inverse_gcd (shift-and-add binary GCD, used by the batched-affine levels) against big-int inversion:
+    random values, values with long runs of zero bits (whole-limb shifts), small values, p - small"""
+    rng = random.Random(1234)
+    for which, (q, L) in enumerate(((c.p, c.fp_limbs), (c.r, c.fr_limbs))):
+        fid = c.curve_id * 2 + which
+        vals = [rng.randrange(1, q) for _ in range(200)]
+        vals += [1 << k for k in (1, 31, 32, 33, 63, 64, 65, 96, 127, 128, 200) if (1 << k) < q]
+        vals += [(rng.randrange(1, 1 << 40) << 96) % q or 1 for _ in range(20)]
+        vals += [k for k in range(1, 20)] + [q - k for k in range(1, 20)]
+        R = 1 << (64 * L)
+        for a in vals:
+            # the stored limbs are a*R mod q; choose a so that the STORED value has the special shape too
+            for stored in (a * R % q, a):
+                val = stored * pow(R, -1, q) % q
+                A = ff.pack_elements([val], q, L)
+                O = np.zeros_like(A)
+                assert hostemu.emu_field_op(fid, 7, P(A), P(A), P(O)) == 0
+                assert ff.unpack_elements(O, q, L)[0] == pow(val, -1, q), (c.name, which, hex(a))
+
+
 @pytest.mark.parametrize("c", [c for c in ALL if c.fp2_nonresidue is not None], ids=lambda c: c.name)
 def test_fp2_ops(hostemu, c):
     rng = random.Random(6)
