@@ -14,6 +14,7 @@
 
 #include "curve52.cuh"
 #include "fixed_base.cuh"
+#include "host_fr.h"
 #include "msm.cuh"
 #include "msm_batch.cuh"
 #include "ntt.cuh"
@@ -480,6 +481,35 @@ int emu_fixed_base(int curve, int group, const void* base, const void* scalars, 
     case 7: return fixed_base_emu<bw6_761_fr, bw6_761_fp>(base, scalars, n, c, out_affine);
   }
   return -1;
+}
+
+// host_fr.h (run-time limb count, used by plonk_host.cu): op 0 add, 1 sub, 2 mul, 3 inv, 4 neg, 5 from_u64(a[0]),
+// 6 domain_generator(log2n = a[0]), 7 mult_gen, 8 pow_u64(a, b[0])
+int emu_hostfr_op(int curve, int op, const void* a_, const void* b_, void* out) {
+  HostFrCtx c;
+  switch (curve) {
+    case 0: c = HostFrCtx::make<bn254_fr_params>(); break;
+    case 1: c = HostFrCtx::make<bls12_381_fr_params>(); break;
+    case 2: c = HostFrCtx::make<bls12_377_fr_params>(); break;
+    case 3: c = HostFrCtx::make<bw6_761_fr_params>(); break;
+    default: return -1;
+  }
+  const HostFr a = c.load(a_), b = c.load(b_);
+  HostFr r;
+  switch (op) {
+    case 0: r = c.add(a, b); break;
+    case 1: r = c.sub(a, b); break;
+    case 2: r = c.mul(a, b); break;
+    case 3: r = c.inv(a); break;
+    case 4: r = c.neg(a); break;
+    case 5: r = c.from_u64(*reinterpret_cast<const uint64_t*>(a_)); break;
+    case 6: r = c.domain_generator((int)*reinterpret_cast<const uint64_t*>(a_)); break;
+    case 7: r = c.mult_gen; break;
+    case 8: r = c.pow_u64(a, *reinterpret_cast<const uint64_t*>(b_)); break;
+    default: return -1;
+  }
+  c.store(out, r);
+  return 0;
 }
 
 // field_id = curve*2 + (0: fp, 1: fr)

@@ -307,10 +307,15 @@ struct NttInst {
     k_gather<Fr><<<(unsigned)((n + 255) / 256), 256, 0, st>>>((Fr*)out, (const Fr*)src, idx, n);
     return cudaGetLastError();
   }
+  static const HostFrCtx* host_fr() {
+    static const HostFrCtx c = HostFrCtx::make<typename Fr::Params>();
+    return &c;
+  }
   static const NttOps* ops() {
     static const NttOps o = {sizeof(Fr), Fr::Params::TWO_ADICITY, &domain_new, &domain_free, &domain_bytes, &ntt,
                              &compute_h, &vec_op, &bit_reverse, &scale_powers, &batch_invert, &plonk_coset,
-                             &plonk_divide_by_zh, &axpy, &scan, &plonk_build_z, &poly_eval, &poly_div_linear, &gather};
+                             &plonk_divide_by_zh, &axpy, &scan, &plonk_build_z, &poly_eval, &poly_div_linear, &gather,
+                             &host_fr};
     return &o;
   }
 };

@@ -6,6 +6,8 @@
 #include <cstddef>
 #include <cstdint>
 
+#include "host_fr.h"
+
 namespace gb200 {
 
 // Opt-in experiment (GB200_MSM_HYBRID=<percent>): the bucket-accumulate tasks are split between the
@@ -68,6 +70,8 @@ struct NttOps {
   cudaError_t (*poly_div_linear)(cudaStream_t st, void* d_coeffs, size_t n, const void* z_mont, void* rem_host);
   // out[j] = src[idx[j]] (wire filtering, backend/groth16/bn254/prove.go:147-168)
   cudaError_t (*gather)(cudaStream_t st, void* d_out, const void* d_src, const uint32_t* d_idx, size_t n);
+  // host-side Fr constants and arithmetic (host_fr.h) for the scalar work between device stages
+  const HostFrCtx* (*host_fr)();
 };
 
 // Host-side group arithmetic for proof assembly (backend/groth16/bn254/prove.go:

@@ -1,0 +1,333 @@
+// PLONK prover orchestration on the host, over the C ABI's own device entry points - the compiled twin of
+// gnark_b200/plonk.py and, stage by stage, of the CPU prover backend/plonk/bn254/prove.go:
+//
+//   commitToLRO :404-489           canonical forms (iNTT), blinding :1211-1220, 3 MSMs on the canonical SRS
+//   buildRatioCopyConstraint :635  b200_plonk_build_z, commit Z
+//   computeQuotient :558-633       48 coset NTTs + fused constraint kernel x4 :841-1123, divideByZH :1287,
+//                                  commitToQuotient :1263-1282
+//   openZ :670-687, computeLinearizedPolynomial :724-794 (+ :1366-1487), batchOpening :796-837
+//
+// Every polynomial stays in HBM between the MSM / NTT stages; only blinding patches (<= 3 elements), opened
+// values and digests cross to the host.  Challenges and blinding coefficients are INPUTS (the Fiat-Shamir
+// transcript encoding is gnark-crypto's; a Go shim derives them exactly as prove.go:492-555 does).  BSB22
+// commitments and StatisticalZK are not supported.  Host-side scalar work uses host_fr.h.
+#include <memory>
+#include <vector>
+
+#include "capi_common.h"
+
+using namespace gb200;
+
+struct b200_plonk_pk_s {
+  int dev = 0, curve = 0;
+  uint32_t logn = 0;
+  size_t n = 0;
+  size_t fb = 0;                      // sizeof(fr.Element)
+  const HostFrCtx* fr = nullptr;
+  HostFr g, w, w4;                    // FrMultiplicativeGen, domain0 generator, domain1 generator (Montgomery)
+  b200_domain_t dom0[4] = {nullptr, nullptr, nullptr, nullptr};   // domain0 with coset generator g * w4^i
+  b200_domain_t dom1 = nullptr;
+  // ql, qr, qm, qo, qk, s1, s2, s3
+  void* br[8] = {nullptr};            // canonical coefficients, bit-reversed layout (inputs of the coset NTTs)
+  void* canon[8] = {nullptr};         // canonical coefficients, regular layout
+  int64_t* d_perm = nullptr;
+  b200_table_t srs = nullptr;         // canonical SRS, n + 3 points
+};
+
+namespace {
+
+enum { QL = 0, QR, QM, QO, QK, S1, S2, S3 };
+
+#define RC(x)                        \
+  do {                               \
+    int32_t rc__ = (x);              \
+    if (rc__) return rc__;           \
+  } while (0)
+
+// device buffers freed on scope exit (after the stream has drained)
+struct Scratch {
+  int dev;
+  std::vector<void*> bufs;
+  explicit Scratch(int d) : dev(d) {}
+  ~Scratch() { for (void* p : bufs) if (p) b200_free(dev, p); }
+  int32_t alloc(size_t bytes, void** out) {
+    RC(b200_alloc(dev, bytes, out));
+    bufs.push_back(*out);
+    return 0;
+  }
+};
+
+int32_t d2d(int dev, void* dst, const void* src, size_t bytes) {
+  DeviceCtx* ctx; RC(device_ctx(dev, &ctx));
+  CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+  return 0;
+}
+int32_t dzero(int dev, void* dst, size_t bytes) {
+  DeviceCtx* ctx; RC(device_ctx(dev, &ctx));
+  CK(cudaMemsetAsync(dst, 0, bytes, ctx->stream));
+  return 0;
+}
+
+// Lagrange/regular values (device, n elements) -> cb: canonical, bit-reversed (n) ; reg: canonical, regular,
+// blinded p + b(X)(X^n - 1) with nb blinding coefficients (n + nb elements)     (getBlindedCoefficients :1211-1220)
+int32_t canonical_blinded(b200_plonk_pk_s* pk, const void* d_lagrange, const uint8_t* b_mont, int nb, void* cb, void* reg) {
+  const size_t n = pk->n, fb = pk->fb;
+  RC(d2d(pk->dev, cb, d_lagrange, n * fb));
+  RC(b200_ntt_async(pk->dom0[0], cb, 1, B200_DIF, 0));
+  RC(d2d(pk->dev, reg, cb, n * fb));
+  RC(b200_vec_bit_reverse(pk->dev, pk->curve, reg, pk->logn));
+  std::vector<uint8_t> low((size_t)nb * fb);
+  RC(b200_d2h(pk->dev, low.data(), reg, (size_t)nb * fb));
+  for (int i = 0; i < nb; i++) {       // low coefficients minus b_i (Montgomery form subtracts as is)
+    const HostFr v = pk->fr->sub(pk->fr->load(low.data() + (size_t)i * fb), pk->fr->load(b_mont + (size_t)i * fb));
+    pk->fr->store(low.data() + (size_t)i * fb, v);
+  }
+  RC(b200_h2d(pk->dev, reg, low.data(), (size_t)nb * fb));
+  RC(b200_h2d(pk->dev, (uint8_t*)reg + n * fb, b_mont, (size_t)nb * fb));   // b on top
+  return 0;
+}
+
+int32_t commit(b200_plonk_pk_s* pk, const void* d_coeffs, size_t count, void* out_jac) {
+  return b200_msm_g1(pk->srs, 0, count, d_coeffs, 1, out_jac);
+}
+
+int32_t eval_at(b200_plonk_pk_s* pk, const void* d_coeffs, size_t count, const HostFr& x, HostFr* out) {
+  uint8_t xb[8 * HOSTFR_MAX_LIMBS], ob[8 * HOSTFR_MAX_LIMBS];
+  pk->fr->store(xb, x);
+  RC(b200_poly_eval(pk->dev, pk->curve, d_coeffs, count, xb, ob));
+  *out = pk->fr->load(ob);
+  return 0;
+}
+int32_t axpy(b200_plonk_pk_s* pk, void* d_y, const HostFr& a, const void* d_x, size_t count) {
+  uint8_t ab[8 * HOSTFR_MAX_LIMBS];
+  pk->fr->store(ab, a);
+  return b200_vec_axpy(pk->dev, pk->curve, d_y, ab, d_x, count);
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t b200_plonk_pk_free(b200_plonk_pk_t pk) {
+  GUARD_BEGIN
+  if (!pk) return 0;
+  b200_sync(pk->dev);
+  for (int i = 0; i < 4; i++) if (pk->dom0[i]) b200_ntt_domain_free(pk->dom0[i]);
+  if (pk->dom1) b200_ntt_domain_free(pk->dom1);
+  for (int k = 0; k < 8; k++) { if (pk->br[k]) b200_free(pk->dev, pk->br[k]); if (pk->canon[k]) b200_free(pk->dev, pk->canon[k]); }
+  if (pk->d_perm) b200_free(pk->dev, pk->d_perm);
+  if (pk->srs) b200_table_free(pk->srs);
+  delete pk;
+  return 0;
+  GUARD_END
+}
+
+int32_t b200_plonk_pk_load(int32_t dev, int32_t curve, const b200_plonk_pk_desc* d, b200_plonk_pk_t* out) {
+  GUARD_BEGIN
+  if (!d || !out) return set_error("plonk_pk_load: null argument");
+  if (!d->ql || !d->qr || !d->qm || !d->qo || !d->qk || !d->perm || !d->srs_canonical)
+    return set_error("plonk_pk_load: null field in the descriptor");
+  const NttOps* ops = get_ntt_ops(curve);
+  if (!ops) return set_error("plonk_pk_load: unsupported curve");
+  if ((int)d->log2n + 2 > ops->two_adicity || d->log2n > 28) return set_error("plonk_pk_load: domain too large");
+  DeviceCtx* ctx; RC(device_ctx(dev, &ctx));
+  std::unique_ptr<b200_plonk_pk_s, int32_t (*)(b200_plonk_pk_t)> pk(new b200_plonk_pk_s(), &b200_plonk_pk_free);
+  pk->dev = dev; pk->curve = curve; pk->logn = d->log2n; pk->n = (size_t)1 << d->log2n;
+  pk->fb = ops->fr_bytes;
+  const HostFrCtx* fr = pk->fr = ops->host_fr();
+  const size_t n = pk->n, fb = pk->fb;
+  pk->g = fr->mult_gen;
+  pk->w = fr->domain_generator((int)d->log2n);
+  pk->w4 = fr->domain_generator((int)d->log2n + 2);
+  // domain0 handles for the four cosets g * w4^i (computeNumerator :943-948) and the big domain
+  HostFr coset = pk->g;
+  for (int i = 0; i < 4; i++) {
+    uint8_t cb[8 * HOSTFR_MAX_LIMBS];
+    fr->store(cb, coset);
+    RC(b200_ntt_domain_new(dev, curve, d->log2n, nullptr, cb, &pk->dom0[i]));
+    coset = fr->mul(coset, pk->w4);
+  }
+  RC(b200_ntt_domain_new(dev, curve, d->log2n + 2, nullptr, nullptr, &pk->dom1));
+  RC(b200_alloc(dev, 3 * n * sizeof(int64_t), (void**)&pk->d_perm));
+  RC(b200_h2d(dev, pk->d_perm, d->perm, 3 * n * sizeof(int64_t)));
+  for (size_t i = 0; i < 3 * n; i++)
+    if (d->perm[i] < 0 || (uint64_t)d->perm[i] >= 3 * n) return set_error("plonk_pk_load: permutation entry out of range");
+  // sigma polynomials from the permutation: s_j[i] = supp[perm[j n + i]], supp = <w> || g<w> || g^2<w>
+  // (setup.go:289-392); host side, once per key
+  std::vector<uint8_t> wpow(n * fb), sj(n * fb);
+  {
+    HostFr acc = fr->one_();
+    for (size_t i = 0; i < n; i++) { fr->store(wpow.data() + i * fb, acc); acc = fr->mul(acc, pk->w); }
+  }
+  const HostFr g2 = fr->mul(pk->g, pk->g);
+  const void* lag[8] = {d->ql, d->qr, d->qm, d->qo, d->qk, nullptr, nullptr, nullptr};
+  for (int k = 0; k < 8; k++) {
+    const void* src = lag[k];
+    if (k >= S1) {
+      const int j = k - S1;
+      for (size_t i = 0; i < n; i++) {
+        const uint64_t idx = (uint64_t)d->perm[(size_t)j * n + i];
+        HostFr v = fr->load(wpow.data() + (idx % n) * fb);
+        if (idx / n == 1) v = fr->mul(v, pk->g);
+        else if (idx / n == 2) v = fr->mul(v, g2);
+        fr->store(sj.data() + i * fb, v);
+      }
+      src = sj.data();
+    }
+    RC(b200_alloc(dev, n * fb, &pk->br[k]));
+    RC(b200_alloc(dev, n * fb, &pk->canon[k]));
+    RC(b200_h2d(dev, pk->br[k], src, n * fb));
+    RC(b200_ntt_async(pk->dom0[0], pk->br[k], 1, B200_DIF, 0));      // Lagrange/regular -> canonical/bit-reversed
+    RC(d2d(dev, pk->canon[k], pk->br[k], n * fb));
+    RC(b200_vec_bit_reverse(dev, curve, pk->canon[k], d->log2n));
+  }
+  RC(b200_table_upload(dev, curve, 1, d->srs_canonical, n + 3, B200_TABLE_PRECOMP, &pk->srs));
+  RC(b200_sync(dev));
+  *out = pk.release();
+  return 0;
+  GUARD_END
+}
+
+int32_t b200_plonk_prove(b200_plonk_pk_t pk, const void* l, const void* r, const void* o,
+                         const b200_plonk_challenges* ch, void* out_points, void* out_values) {
+  GUARD_BEGIN
+  if (!pk || !l || !r || !o || !ch || !out_points || !out_values) return set_error("plonk_prove: null argument");
+  if (!ch->gamma || !ch->beta || !ch->alpha || !ch->zeta || !ch->v || !ch->bl || !ch->br || !ch->bo || !ch->bz)
+    return set_error("plonk_prove: null challenge / blinding pointer");
+  const HostFrCtx* fr = pk->fr;
+  const int dev = pk->dev, curve = pk->curve;
+  const size_t n = pk->n, fb = pk->fb;
+  const MsmOps* mops = get_msm_ops(curve, 1);
+  const size_t jb = mops->jac_bytes;
+  uint8_t* pts = (uint8_t*)out_points;          // L, R, O, Z, H1, H2, H3, linearised, batch opening, Z opening
+  uint8_t* vals = (uint8_t*)out_values;         // p(zeta) of {linearised, l, r, o, s1, s2}, then Z(w zeta)
+  Scratch S(dev);
+
+  // ---- commitToLRO -------------------------------------------------------------------------------
+  void *d_l, *d_r, *d_o;
+  RC(S.alloc(n * fb, &d_l)); RC(S.alloc(n * fb, &d_r)); RC(S.alloc(n * fb, &d_o));
+  RC(b200_h2d(dev, d_l, l, n * fb)); RC(b200_h2d(dev, d_r, r, n * fb)); RC(b200_h2d(dev, d_o, o, n * fb));
+  void* cb[4];        // l, r, o, z: canonical bit-reversed (n)
+  void* bl[4];        // blinded canonical regular (n + 2, n + 2, n + 2, n + 3)
+  const int nbl[4] = {2, 2, 2, 3};
+  const uint8_t* bcoef[4] = {(const uint8_t*)ch->bl, (const uint8_t*)ch->br, (const uint8_t*)ch->bo, (const uint8_t*)ch->bz};
+  const void* lag[3] = {d_l, d_r, d_o};
+  for (int k = 0; k < 4; k++) { RC(S.alloc(n * fb, &cb[k])); RC(S.alloc((n + nbl[k]) * fb, &bl[k])); }
+  for (int k = 0; k < 3; k++) RC(canonical_blinded(pk, lag[k], bcoef[k], nbl[k], cb[k], bl[k]));
+  for (int k = 0; k < 3; k++) RC(commit(pk, bl[k], n + 2, pts + (size_t)k * jb));
+
+  // ---- buildRatioCopyConstraint + commit Z ---------------------------------------------------------
+  void* d_z;
+  RC(S.alloc(n * fb, &d_z));
+  RC(b200_plonk_build_z(pk->dom0[0], d_l, d_r, d_o, pk->d_perm, ch->beta, ch->gamma, d_z));
+  RC(canonical_blinded(pk, d_z, bcoef[3], 3, cb[3], bl[3]));
+  RC(commit(pk, bl[3], n + 3, pts + 3 * jb));
+
+  // ---- computeQuotient: numerator on the 4 cosets, divide by Z_H, commit h1, h2, h3 -----------------
+  void* cres;
+  RC(S.alloc(4 * n * fb, &cres));
+  RC(dzero(dev, cres, 4 * n * fb));
+  void* onc[12];      // the 12 polynomials on the current coset
+  for (int k = 0; k < 12; k++) RC(S.alloc(n * fb, &onc[k]));
+  uint8_t gb[8 * HOSTFR_MAX_LIMBS], w4b[8 * HOSTFR_MAX_LIMBS];
+  fr->store(gb, pk->g); fr->store(w4b, pk->w4);
+  // argument order of b200_plonk_coset_args: l r o z s1 s2 s3 ql qr qm qo qk
+  const void* srcs[12] = {cb[0], cb[1], cb[2], cb[3], pk->br[S1], pk->br[S2], pk->br[S3],
+                          pk->br[QL], pk->br[QR], pk->br[QM], pk->br[QO], pk->br[QK]};
+  for (uint32_t i = 0; i < 4; i++) {
+    for (int k = 0; k < 12; k++) {
+      RC(d2d(dev, onc[k], srcs[k], n * fb));
+      RC(b200_ntt_async(pk->dom0[i], onc[k], 0, B200_DIT, 1));     // canonical/bit-reversed -> coset i, regular
+    }
+    b200_plonk_coset_args a;
+    memset(&a, 0, sizeof(a));
+    a.l = onc[0]; a.r = onc[1]; a.o = onc[2]; a.z = onc[3]; a.s1 = onc[4]; a.s2 = onc[5]; a.s3 = onc[6];
+    a.ql = onc[7]; a.qr = onc[8]; a.qm = onc[9]; a.qo = onc[10]; a.qk = onc[11];
+    a.alpha = ch->alpha; a.beta = ch->beta; a.gamma = ch->gamma;
+    a.bl = ch->bl; a.br = ch->br; a.bo = ch->bo; a.bz = ch->bz;
+    a.nbl = 2; a.nbr = 2; a.nbo = 2; a.nbz = 3;
+    a.coset_index = i; a.rho = 4; a.out = cres;
+    RC(b200_plonk_constraints_coset(pk->dom0[i], gb, w4b, &a));
+  }
+  RC(b200_plonk_divide_by_zh(pk->dom1, pk->logn, cres));      // -> h canonical regular (4n)
+  uint8_t* h = (uint8_t*)cres;
+  for (int k = 0; k < 3; k++) RC(commit(pk, h + (size_t)k * (n + 2) * fb, n + 2, pts + (size_t)(4 + k) * jb));
+
+  // ---- openZ, evaluations at zeta ---------------------------------------------------------------------
+  const HostFr zeta = fr->load(ch->zeta), alpha = fr->load(ch->alpha), beta = fr->load(ch->beta),
+               gamma = fr->load(ch->gamma), v = fr->load(ch->v);
+  const HostFr wz = fr->mul(zeta, pk->w);
+  HostFr zu, lz, rz, oz, s1z, s2z;
+  RC(eval_at(pk, bl[3], n + 3, wz, &zu));
+  RC(eval_at(pk, bl[0], n + 2, zeta, &lz));
+  RC(eval_at(pk, bl[1], n + 2, zeta, &rz));
+  RC(eval_at(pk, bl[2], n + 2, zeta, &oz));
+  RC(eval_at(pk, pk->canon[S1], n, zeta, &s1z));
+  RC(eval_at(pk, pk->canon[S2], n, zeta, &s2z));
+
+  // ---- innerComputeLinearizedPoly :1366-1487 ----------------------------------------------------------
+  auto M = [&](const HostFr& a, const HostFr& b) { return fr->mul(a, b); };
+  auto A = [&](const HostFr& a, const HostFr& b) { return fr->add(a, b); };
+  const HostFr rl = M(rz, lz);
+  // c1 = (lz + beta s1z + gamma)(rz + beta s2z + gamma) zu beta alpha
+  const HostFr c1 = M(M(M(M(A(A(lz, M(beta, s1z)), gamma), A(A(rz, M(beta, s2z)), gamma)), zu), beta), alpha);
+  const HostFr uz = M(zeta, pk->g), uuz = M(uz, pk->g);
+  // c2 = -(lz + beta zeta + gamma)(rz + beta uz + gamma)(oz + beta uuz + gamma) alpha
+  const HostFr c2 = fr->neg(M(M(M(A(A(lz, M(beta, zeta)), gamma), A(A(rz, M(beta, uz)), gamma)),
+                                A(A(oz, M(beta, uuz)), gamma)), alpha));
+  const HostFr zn = fr->pow2k(zeta, (int)pk->logn);
+  const HostFr zn2 = M(M(zn, zeta), zeta);
+  const HostFr zh = fr->sub(zn, fr->one_());
+  const HostFr zm1 = fr->sub(zeta, fr->one_());
+  if (fr->is_zero(zm1)) return set_error("plonk_prove: zeta = 1");
+  // alpha^2 L1(zeta) = alpha^2 (zeta^n - 1) / (n (zeta - 1))
+  const HostFr a2l1 = M(M(M(zh, fr->inv(zm1)), M(alpha, alpha)), fr->inv(fr->from_u64((uint64_t)n)));
+  void* lin;
+  RC(S.alloc((n + 3) * fb, &lin));
+  RC(dzero(dev, lin, (n + 3) * fb));
+  RC(axpy(pk, lin, A(c2, a2l1), bl[3], n + 3));
+  RC(axpy(pk, lin, c1, pk->canon[S3], n));
+  RC(axpy(pk, lin, rl, pk->canon[QM], n));
+  RC(axpy(pk, lin, lz, pk->canon[QL], n));
+  RC(axpy(pk, lin, rz, pk->canon[QR], n));
+  RC(axpy(pk, lin, oz, pk->canon[QO], n));
+  RC(axpy(pk, lin, fr->one_(), pk->canon[QK], n));
+  HostFr hc = zh;     // zh, zh zn2, zh zn2^2
+  for (int k = 0; k < 3; k++) {
+    RC(axpy(pk, lin, fr->neg(hc), h + (size_t)k * (n + 2) * fb, n + 2));
+    hc = M(hc, zn2);
+  }
+  RC(commit(pk, lin, n + 3, pts + 7 * jb));
+
+  // ---- batchOpening :796-837 (fold with powers of v, divide by X - zeta) and the Z opening -----------------
+  const void* open_p[6] = {lin, bl[0], bl[1], bl[2], pk->canon[S1], pk->canon[S2]};
+  const size_t open_n[6] = {n + 3, n + 2, n + 2, n + 2, n, n};
+  void* fold;
+  RC(S.alloc((n + 3) * fb, &fold));
+  RC(dzero(dev, fold, (n + 3) * fb));
+  HostFr vp = fr->one_();
+  for (int k = 0; k < 6; k++) {
+    HostFr e;
+    RC(eval_at(pk, open_p[k], open_n[k], zeta, &e));
+    fr->store(vals + (size_t)k * fb, e);
+    RC(axpy(pk, fold, vp, open_p[k], open_n[k]));
+    vp = M(vp, v);
+  }
+  uint8_t zb[8 * HOSTFR_MAX_LIMBS], rem[8 * HOSTFR_MAX_LIMBS];
+  fr->store(zb, zeta);
+  RC(b200_poly_div_by_linear(dev, curve, fold, n + 3, zb, rem));
+  RC(commit(pk, fold, n + 2, pts + 8 * jb));
+  void* zq;
+  RC(S.alloc((n + 3) * fb, &zq));
+  RC(d2d(dev, zq, bl[3], (n + 3) * fb));
+  fr->store(zb, wz);
+  RC(b200_poly_div_by_linear(dev, curve, zq, n + 3, zb, rem));
+  if (!fr->eq(fr->load(rem), zu)) return set_error("plonk_prove: Z(w zeta) from the division differs from the evaluation");
+  RC(commit(pk, zq, n + 2, pts + 9 * jb));
+  fr->store(vals + 6 * fb, zu);
+  RC(b200_sync(dev));
+  return 0;
+  GUARD_END
+}
+
+}  // extern "C"

@@ -33,11 +33,21 @@ EXPORTS = [
     "b200_vec_axpy", "b200_vec_scan", "b200_plonk_build_z", "b200_poly_eval", "b200_poly_div_by_linear",
     "b200_point_add_jac", "b200_point_to_affine", "b200_groth16_pk_load", "b200_groth16_pk_free", "b200_groth16_prove", "b200_groth16_msms",
     "b200_groth16_assemble", "b200_fixed_base_batch", "b200_msm_submit",
+    "b200_plonk_pk_load", "b200_plonk_pk_free", "b200_plonk_prove",
 ]
 
 
 class B200Error(RuntimeError):
     pass
+
+
+class PlonkPkDesc(ctypes.Structure):
+    _fields_ = [("log2n", ctypes.c_uint32)] + [(k, ctypes.c_void_p) for k in ("ql", "qr", "qm", "qo", "qk", "perm",
+                                                                                "srs_canonical")]
+
+
+class PlonkChallenges(ctypes.Structure):
+    _fields_ = [(k, ctypes.c_void_p) for k in ("gamma", "beta", "alpha", "zeta", "v", "bl", "br", "bo", "bz")]
 
 
 class Groth16PkDesc(ctypes.Structure):
@@ -107,6 +117,9 @@ def load(path: str = None):
     lib.b200_msm_pipelined.argtypes = [vp, sz, sz, vp, vp]
     lib.b200_msm_join.argtypes = [i32]
     lib.b200_msm_submit.argtypes = [vp, sz, sz, vp, vp]
+    lib.b200_plonk_pk_load.argtypes = [i32, i32, ctypes.POINTER(PlonkPkDesc), ctypes.POINTER(vp)]
+    lib.b200_plonk_pk_free.argtypes = [vp]
+    lib.b200_plonk_prove.argtypes = [vp, vp, vp, vp, ctypes.POINTER(PlonkChallenges), vp, vp]
     lib.b200_fixed_base_batch.argtypes = [i32, i32, i32, vp, vp, i32, sz, vp, i32]
     lib.b200_msm_profile.argtypes = [vp, sz, sz, vp, vp, ctypes.POINTER(ctypes.c_float)]
     lib.b200_ntt_domain_new.argtypes = [i32, i32, u32, vp, vp, ctypes.POINTER(vp)]
@@ -301,6 +314,50 @@ def fixed_base_batch(curve: int, group: int, base_affine: np.ndarray, scalars, n
     check(load().b200_fixed_base_batch(dev, curve, group, ptr(base_affine), ptr(scalars), 1 if on_dev else 0, n,
                                        ptr(out), 1 if hasattr(out, "data_ptr") else 0))
     return out
+
+
+class PlonkKey:
+    """device-resident PLONK proving key behind b200_plonk_pk_load / b200_plonk_prove (plonk_host.cu)"""
+
+    def __init__(self, curve: int, log2n: int, ql, qr, qm, qo, qk, perm, srs_canonical, dev: int = 0):
+        self.curve, self.log2n, self.dev = curve, log2n, dev
+        frl, fpl, _ = CURVE_SHAPES[curve]
+        self.fr_limbs, self.fp_limbs = frl, fpl
+        keep = [np.ascontiguousarray(a, dtype=np.uint64) for a in (ql, qr, qm, qo, qk)]
+        perm = np.ascontiguousarray(perm, dtype=np.int64)
+        srs = np.ascontiguousarray(srs_canonical, dtype=np.uint64)
+        d = PlonkPkDesc()
+        d.log2n = log2n
+        for k, a in zip(("ql", "qr", "qm", "qo", "qk"), keep):
+            setattr(d, k, ptr(a).value)
+        d.perm, d.srs_canonical = ptr(perm).value, ptr(srs).value
+        h = ctypes.c_void_p(0)
+        check(load().b200_plonk_pk_load(dev, curve, ctypes.byref(d), ctypes.byref(h)))
+        self.handle = h
+
+    def prove(self, l, r, o, gamma, beta, alpha, zeta, v, bl, br, bo, bz):
+        """all scalars: uint64 limb arrays (Montgomery); bl/br/bo: (2, limbs), bz: (3, limbs).
+        Returns (points (10, 3*fp_limbs) Jacobian, values (7, fr_limbs))."""
+        args = [np.ascontiguousarray(a, dtype=np.uint64) for a in (l, r, o, gamma, beta, alpha, zeta, v, bl, br, bo, bz)]
+        ch = PlonkChallenges()
+        for k, a in zip(("gamma", "beta", "alpha", "zeta", "v", "bl", "br", "bo", "bz"), args[3:]):
+            setattr(ch, k, ptr(a).value)
+        pts = np.zeros((10, 3 * self.fp_limbs), dtype=np.uint64)
+        vals = np.zeros((7, self.fr_limbs), dtype=np.uint64)
+        check(load().b200_plonk_prove(self.handle, ptr(args[0]), ptr(args[1]), ptr(args[2]), ctypes.byref(ch), ptr(pts),
+                                      ptr(vals)))
+        return pts, vals
+
+    def free(self):
+        if self.handle:
+            check(load().b200_plonk_pk_free(self.handle))
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
 
 
 def point_add_jac(curve: int, group: int, acc: np.ndarray, q: np.ndarray) -> np.ndarray:

@@ -202,6 +202,36 @@ int32_t b200_poly_eval(int32_t dev, int32_t curve, const void* d_coeffs, size_t 
 int32_t b200_poly_div_by_linear(int32_t dev, int32_t curve, void* d_coeffs, size_t n, const void* z_mont,
                                 void* claimed_value_host);
 
+/* ---- PLONK prover (host orchestration in C++, plonk_host.cu; the reference has no accelerated PLONK - this is
+ *      the device-resident twin of backend/plonk/bn254/prove.go:98-837 behind one call, for a Go package
+ *      backend/accelerated/b200/plonk mirroring backend/plonk/plonk.go:94-135).
+ *      Key = the Trace (setup.go:67-86: Ql, Qr, Qm, Qo, Qk in Lagrange/regular form, the permutation S) and the
+ *      canonical KZG SRS (pk.Kzg.G1, n + 3 points); sigma polynomials are rebuilt from S (setup.go:289-392).
+ *      Challenges and blinding coefficients are INPUTS: the Go shim derives gamma, beta, alpha, zeta, v from its
+ *      Fiat-Shamir transcript exactly as prove.go:492-555 and samples the blinding polynomials (:1211-1220);
+ *      passing them in also makes every intermediate result reproducible.  BSB22 commitments / StatisticalZK are
+ *      not supported.  All scalars are fr.Elements (Montgomery) on the host. */
+typedef struct b200_plonk_pk_s* b200_plonk_pk_t;
+typedef struct {
+  uint32_t log2n;                        /* domain0 = 2^log2n rows */
+  const void *ql, *qr, *qm, *qo, *qk;    /* n fr.Elements each, Lagrange/regular */
+  const int64_t* perm;                   /* trace.S, 3n entries */
+  const void* srs_canonical;             /* n + 3 G1Affine */
+} b200_plonk_pk_desc;
+typedef struct {
+  const void *gamma, *beta, *alpha, *zeta, *v; /* one fr.Element each */
+  const void *bl, *br, *bo;                    /* blinding of L, R, O: 2 coefficients each */
+  const void* bz;                              /* blinding of Z: 3 coefficients */
+} b200_plonk_challenges;
+int32_t b200_plonk_pk_load(int32_t dev, int32_t curve, const b200_plonk_pk_desc* desc, b200_plonk_pk_t* out);
+int32_t b200_plonk_pk_free(b200_plonk_pk_t pk);
+/* l, r, o: the solved wire columns (SparseR1CSSolution{L,R,O}, constraint/bn254/system.go:208-210), n fr.Elements
+ * each on the host.  out_points: 10 G1Jac in gnark layout - [L], [R], [O], [Z], [H1], [H2], [H3], linearised digest,
+ * batched opening quotient, Z-shifted opening quotient (Proof fields, prove.go:77-96).  out_values: 7 fr.Elements -
+ * the claimed values at zeta of {linearised polynomial, l, r, o, s1, s2} (BatchedProof.ClaimedValues) and Z(w*zeta). */
+int32_t b200_plonk_prove(b200_plonk_pk_t pk, const void* l, const void* r, const void* o,
+                         const b200_plonk_challenges* ch, void* out_points, void* out_values);
+
 /* ---- Groth16 prover (host layer mirroring backend/accelerated/icicle/groth16/
  *      bn254/icicle.go:784-1360 Prove + setupDevicePointers :88-264) ------------
  * Builds the device-resident key from the gnark ProvingKey fields

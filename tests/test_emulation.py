@@ -65,6 +65,39 @@ def test_inverse_gcd_many(hostemu, c):
                 assert ff.unpack_elements(O, q, L)[0] == pow(val, -1, q), (c.name, which, hex(a))
 
 
+@pytest.mark.parametrize("c", ALL, ids=lambda c: c.name)
+def test_host_fr(hostemu, c):
+    """host_fr.h: the run-time-limb-count Fr arithmetic the C++ PLONK orchestration uses between device stages"""
+    rng = random.Random(99)
+    q, L = c.r, c.fr_limbs
+    pe = lambda v: ff.pack_elements([v], q, L)
+    un = lambda A: ff.unpack_elements(A, q, L)[0]
+    O = np.zeros(L, dtype=np.uint64)
+    for trial in range(30):
+        a, b = rng.randrange(q), rng.randrange(q)
+        if trial == 0: a, b = 0, 0
+        if trial == 1: a, b = q - 1, q - 1
+        if trial == 2: a, b = 1, q - 1
+        for op, exp in ((0, (a + b) % q), (1, (a - b) % q), (2, a * b % q), (4, (-a) % q)):
+            assert hostemu.emu_hostfr_op(c.curve_id, op, P(pe(a)), P(pe(b)), P(O)) == 0
+            assert un(O) == exp, (c.name, op)
+        if a:
+            hostemu.emu_hostfr_op(c.curve_id, 3, P(pe(a)), P(pe(b)), P(O))
+            assert un(O) == pow(a, -1, q)
+        e = np.array([rng.randrange(1 << 40)] + [0] * (L - 1), dtype=np.uint64)
+        hostemu.emu_hostfr_op(c.curve_id, 8, P(pe(a)), P(e), P(O))
+        assert un(O) == pow(a, int(e[0]), q)
+        hostemu.emu_hostfr_op(c.curve_id, 5, P(e), P(e), P(O))
+        assert un(O) == int(e[0]) % q
+    from oracle import ntt as ontt
+    for logn in (1, 4, 20):
+        k = np.array([logn] + [0] * (L - 1), dtype=np.uint64)
+        hostemu.emu_hostfr_op(c.curve_id, 6, P(k), P(k), P(O))
+        assert un(O) == ontt.Domain(c, 1 << logn).generator
+    hostemu.emu_hostfr_op(c.curve_id, 7, P(O.copy()), P(O.copy()), P(O))
+    assert un(O) == c.mult_gen
+
+
 @pytest.mark.parametrize("c", [c for c in ALL if c.fp2_nonresidue is not None], ids=lambda c: c.name)
 def test_fp2_ops(hostemu, c):
     rng = random.Random(6)
