@@ -222,3 +222,36 @@ def test_msm_batched_affine_levels(gpu, monkeypatch, cname, group, levels):
             t = gpu.Table(c.curve_id, group, pts, precomp=precomp)
             assert jac_to_affine(c, group, t.msm(sc)) == expected
             t.free()
+
+
+@pytest.mark.xfail(strict=False, reason="C++ orchestration (plonk_host.cu) written after this round's GPU budget was spent: a "
+                   "translation of gnark_b200/plonk.py, whose algebra is pinned on the CPU (tests/test_plonk_orchestration.py)")
+@pytest.mark.parametrize("c", [CURVES["bn254"], CURVES["bls12-381"]], ids=lambda c: c.name)
+@pytest.mark.parametrize("logn", (4, 6))
+def test_plonk_prove_c_abi_vs_oracle(gpu, c, logn):
+    """b200_plonk_pk_load / b200_plonk_prove (one C call per proof) against the big-int oracle prover with the same
+    injected challenges / blinding: all ten digests (trapdoor SRS: digest = dlog * G) and the seven opened values"""
+    from oracle import corelib, plonk_prover as pp
+    rng = random.Random(2000 + logn)
+    r, L = c.r, c.fr_limbs
+    n = 1 << logn
+    circ, l, rr, o = pp.random_satisfied_instance(c, n, seed=logn + 50)
+    rnd = lambda: rng.randrange(r)
+    ch = pp.Challenges(gamma=rnd(), beta=rnd(), alpha=rnd(), zeta=rnd(), v=rnd(), bl=[rnd(), rnd()], br=[rnd(), rnd()],
+                       bo=[rnd(), rnd()], bz=[rnd(), rnd(), rnd()])
+    tau = rnd()
+    want = pp.prove(c, circ, l, rr, o, ch, tau)
+    assert pp.verify(c, circ, want, ch, tau)
+    pe = lambda v: ff.pack_elements(v, r, L)
+    srs = corelib.fixed_base(c, 1, ec.pack_points(c, 1, [c.g1]), pe([pow(tau, i, r) for i in range(n + 3)]))
+    key = gpu.PlonkKey(c.curve_id, logn, pe(circ.ql), pe(circ.qr), pe(circ.qm), pe(circ.qo), pe(circ.qk),
+                       np.array(circ.perm, dtype=np.int64), srs)
+    pts, vals = key.prove(pe(l), pe(rr), pe(o), pe([ch.gamma]), pe([ch.beta]), pe([ch.alpha]), pe([ch.zeta]), pe([ch.v]),
+                          pe(ch.bl), pe(ch.br), pe(ch.bo), pe(ch.bz))
+    F = ff.Fp(c.p)
+    dl = [want.L, want.R, want.O, want.Z, want.H[0], want.H[1], want.H[2], want.lin, want.batch_opening, want.z_opening]
+    for k, name in enumerate(("L", "R", "O", "Z", "H1", "H2", "H3", "lin", "batch", "zopen")):
+        assert jac_to_affine(c, 1, pts[k]) == ec.scalar_mul(F, dl[k], c.g1), name
+    got_vals = ff.unpack_elements(vals, r, L)
+    assert got_vals[:6] == want.claimed and got_vals[6] == want.zu
+    key.free()
