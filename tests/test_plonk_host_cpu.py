@@ -1,0 +1,81 @@
+"""The C++ PLONK orchestration (gnark_b200/csrc/plonk_host.cu: b200_plonk_pk_load / b200_plonk_prove) on the CPU.
+plonk_host.cu is compiled as plain C++ against host stand-ins for the device entry points it calls
+(tests/mock/mock_capi.cpp -> libgb200_plonkmock.so; test infrastructure, BN254 only), and its ten digests and
+seven opened values are compared with the big-int oracle prover (oracle/plonk_prover.py) under the same injected
+challenges and blinding.  Together with the hardware parity tests of each entry point (tests/test_gpu_plonk.py)
+this pins everything but the GPU plumbing of tests/test_gpu_zz_late.py::test_plonk_prove_c_abi_vs_oracle."""
+import ctypes
+import os
+import random
+
+import numpy as np
+import pytest
+
+from gnark_b200 import lib as b200
+from oracle import corelib, ec, ff, plonk_prover as pp
+from oracle.params import CURVES
+from util import jac_to_affine
+
+LIB = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gnark_b200", "lib", "libgb200_plonkmock.so")
+
+
+@pytest.fixture(scope="module")
+def mock():
+    if not os.path.exists(LIB):
+        pytest.skip("libgb200_plonkmock.so not built (make -C gnark_b200/csrc)")
+    m = ctypes.CDLL(LIB)
+    vp, i32 = ctypes.c_void_p, ctypes.c_int32
+    m.b200_plonk_pk_load.argtypes = [i32, i32, ctypes.POINTER(b200.PlonkPkDesc), ctypes.POINTER(vp)]
+    m.b200_plonk_pk_free.argtypes = [vp]
+    m.b200_plonk_prove.argtypes = [vp, vp, vp, vp, ctypes.POINTER(b200.PlonkChallenges), vp, vp]
+    m.b200_last_error.restype = ctypes.c_char_p
+    return m
+
+
+@pytest.mark.parametrize("logn", (3, 5))
+def test_plonk_host_orchestration_vs_oracle(mock, logn):
+    c = CURVES["bn254"]
+    rng = random.Random(3000 + logn)
+    r, L = c.r, c.fr_limbs
+    n = 1 << logn
+    circ, l, rr, o = pp.random_satisfied_instance(c, n, seed=logn + 7)
+    rnd = lambda: rng.randrange(r)
+    ch = pp.Challenges(gamma=rnd(), beta=rnd(), alpha=rnd(), zeta=rnd(), v=rnd(), bl=[rnd(), rnd()], br=[rnd(), rnd()],
+                       bo=[rnd(), rnd()], bz=[rnd(), rnd(), rnd()])
+    tau = rnd()
+    want = pp.prove(c, circ, l, rr, o, ch, tau)
+    assert pp.verify(c, circ, want, ch, tau)
+    pe = lambda v: np.ascontiguousarray(ff.pack_elements(v, r, L))
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    srs = np.ascontiguousarray(corelib.fixed_base(c, 1, ec.pack_points(c, 1, [c.g1]), pe([pow(tau, i, r) for i in range(n + 3)])))
+    keep = {k: pe(getattr(circ, k)) for k in ("ql", "qr", "qm", "qo", "qk")}
+    perm = np.ascontiguousarray(np.array(circ.perm, dtype=np.int64))
+    d = b200.PlonkPkDesc()
+    d.log2n = logn
+    for k, a in keep.items():
+        setattr(d, k, P(a).value)
+    d.perm, d.srs_canonical = P(perm).value, P(srs).value
+    h = ctypes.c_void_p(0)
+    assert mock.b200_plonk_pk_load(0, c.curve_id, ctypes.byref(d), ctypes.byref(h)) == 0, mock.b200_last_error()
+    sc = {k: pe(v) for k, v in (("gamma", [ch.gamma]), ("beta", [ch.beta]), ("alpha", [ch.alpha]), ("zeta", [ch.zeta]),
+                                ("v", [ch.v]), ("bl", ch.bl), ("br", ch.br), ("bo", ch.bo), ("bz", ch.bz))}
+    cs = b200.PlonkChallenges()
+    for k, a in sc.items():
+        setattr(cs, k, P(a).value)
+    pts = np.zeros((10, 3 * c.fp_limbs), dtype=np.uint64)
+    vals = np.zeros((7, L), dtype=np.uint64)
+    L_, R_, O_ = pe(l), pe(rr), pe(o)
+    assert mock.b200_plonk_prove(h, P(L_), P(R_), P(O_), ctypes.byref(cs), P(pts), P(vals)) == 0, mock.b200_last_error()
+    F = ff.Fp(c.p)
+    dl = [want.L, want.R, want.O, want.Z, want.H[0], want.H[1], want.H[2], want.lin, want.batch_opening, want.z_opening]
+    for k, name in enumerate(("L", "R", "O", "Z", "H1", "H2", "H3", "lin", "batch", "zopen")):
+        assert jac_to_affine(c, 1, pts[k]) == ec.scalar_mul(F, dl[k], c.g1), name
+    got = ff.unpack_elements(vals, r, L)
+    assert got[:6] == want.claimed and got[6] == want.zu
+    # a permutation entry out of range is refused, not dereferenced
+    bad = perm.copy(); bad[1] = 3 * n
+    d.perm = P(bad).value
+    h2 = ctypes.c_void_p(0)
+    assert mock.b200_plonk_pk_load(0, c.curve_id, ctypes.byref(d), ctypes.byref(h2)) != 0
+    assert b"out of range" in mock.b200_last_error()
+    assert mock.b200_plonk_pk_free(h) == 0
