@@ -15,6 +15,10 @@ echo "== 2. bench, 1 GPU (with the asynchronous host path)" | tee -a $OUT/sessio
 timeout 600 python bench.py --steps 20 --warmup 3 --e2e-submit > $OUT/bench_n1.json 2> $OUT/bench_n1.err
 tail -c 2000 $OUT/bench_n1.json | tee -a $OUT/session.log
 
+echo "== 2b. other configs on this GPU count: sharded MSMs (2^22 total), PLONK building blocks and the end-to-end PLONK prove" | tee -a $OUT/session.log
+timeout 900 python tools/bench_configs.py --total-log 22 --steps 3 > $OUT/configs.jsonl 2>> $OUT/session.err
+cut -c1-600 $OUT/configs.jsonl | tee -a $OUT/session.log
+
 echo "== 3. MSM knob sweeps (every configuration is checked against the known-dlog oracle)" | tee -a $OUT/session.log
 timeout 600 python tools/sweep_msm.py bn254 1 20 --set GB200_MSM_WINDOW=16,17,18,19,20,22 > $OUT/sweep_bn254_window.jsonl 2>> $OUT/session.err
 timeout 600 python tools/sweep_msm.py bn254 1 20 --set GB200_MSM_HYBRID=0,12,25,38,50,62 > $OUT/sweep_bn254_hybrid.jsonl 2>> $OUT/session.err
