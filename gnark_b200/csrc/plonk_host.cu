@@ -34,7 +34,7 @@ struct b200_plonk_pk_s {
   b200_table_t srs = nullptr;         // canonical SRS, n + 3 points
 };
 
-namespace {
+namespace gb200_plonk {
 
 enum { QL = 0, QR, QM, QO, QK, S1, S2, S3 };
 
@@ -56,6 +56,27 @@ struct Scratch {
     return 0;
   }
 };
+
+}  // namespace gb200_plonk
+using namespace gb200_plonk;
+
+// one proof in flight: what the later Fiat-Shamir rounds need from the earlier ones
+struct b200_plonk_session_s {
+  b200_plonk_pk_s* pk;
+  Scratch S;
+  int stage = 0;
+  size_t jb = 0;
+  void *d_l = nullptr, *d_r = nullptr, *d_o = nullptr;
+  void* cb[4] = {nullptr};        // l, r, o, z: canonical, bit-reversed (n)
+  void* bl[4] = {nullptr};        // blinded canonical regular (n + 2, n + 2, n + 2, n + 3)
+  void* h = nullptr;              // quotient, canonical regular (4n)
+  void* lin = nullptr;            // linearised polynomial (n + 3)
+  uint8_t blind[4][3 * 8 * HOSTFR_MAX_LIMBS];   // bl, br, bo (2 each), bz (3)
+  uint8_t beta[8 * HOSTFR_MAX_LIMBS], gamma[8 * HOSTFR_MAX_LIMBS], alpha[8 * HOSTFR_MAX_LIMBS], zeta[8 * HOSTFR_MAX_LIMBS];
+  explicit b200_plonk_session_s(b200_plonk_pk_s* p) : pk(p), S(p->dev) {}
+};
+
+namespace {
 
 int32_t d2d(int dev, void* dst, const void* src, size_t bytes) {
   DeviceCtx* ctx; RC(device_ctx(dev, &ctx));
@@ -188,51 +209,77 @@ int32_t b200_plonk_pk_load(int32_t dev, int32_t curve, const b200_plonk_pk_desc*
   GUARD_END
 }
 
-int32_t b200_plonk_prove(b200_plonk_pk_t pk, const void* l, const void* r, const void* o,
-                         const b200_plonk_challenges* ch, void* out_points, void* out_values) {
+// ---- staged prover: one entry point per Fiat-Shamir round (prove.go:492-555 derives gamma, beta from [L],[R],[O];
+//      alpha from [Z]; zeta from [H]; the folding challenge v from the linearised digest and the opened values) ---
+int32_t b200_plonk_end(b200_plonk_session_t s) {
   GUARD_BEGIN
-  if (!pk || !l || !r || !o || !ch || !out_points || !out_values) return set_error("plonk_prove: null argument");
-  if (!ch->gamma || !ch->beta || !ch->alpha || !ch->zeta || !ch->v || !ch->bl || !ch->br || !ch->bo || !ch->bz)
-    return set_error("plonk_prove: null challenge / blinding pointer");
-  const HostFrCtx* fr = pk->fr;
-  const int dev = pk->dev, curve = pk->curve;
+  if (!s) return 0;
+  b200_sync(s->pk->dev);
+  delete s;       // Scratch frees the device buffers
+  return 0;
+  GUARD_END
+}
+
+int32_t b200_plonk_begin(b200_plonk_pk_t pk, const void* l, const void* r, const void* o, const void* bl,
+                         const void* br, const void* bo, b200_plonk_session_t* out, void* out_lro) {
+  GUARD_BEGIN
+  if (!pk || !l || !r || !o || !bl || !br || !bo || !out || !out_lro) return set_error("plonk_begin: null argument");
+  const int dev = pk->dev;
   const size_t n = pk->n, fb = pk->fb;
-  const MsmOps* mops = get_msm_ops(curve, 1);
-  const size_t jb = mops->jac_bytes;
-  uint8_t* pts = (uint8_t*)out_points;          // L, R, O, Z, H1, H2, H3, linearised, batch opening, Z opening
-  uint8_t* vals = (uint8_t*)out_values;         // p(zeta) of {linearised, l, r, o, s1, s2}, then Z(w zeta)
-  Scratch S(dev);
-
-  // ---- commitToLRO -------------------------------------------------------------------------------
-  void *d_l, *d_r, *d_o;
-  RC(S.alloc(n * fb, &d_l)); RC(S.alloc(n * fb, &d_r)); RC(S.alloc(n * fb, &d_o));
-  RC(b200_h2d(dev, d_l, l, n * fb)); RC(b200_h2d(dev, d_r, r, n * fb)); RC(b200_h2d(dev, d_o, o, n * fb));
-  void* cb[4];        // l, r, o, z: canonical bit-reversed (n)
-  void* bl[4];        // blinded canonical regular (n + 2, n + 2, n + 2, n + 3)
+  std::unique_ptr<b200_plonk_session_s> s(new b200_plonk_session_s(pk));
+  s->jb = get_msm_ops(pk->curve, 1)->jac_bytes;
+  memcpy(s->blind[0], bl, 2 * fb); memcpy(s->blind[1], br, 2 * fb); memcpy(s->blind[2], bo, 2 * fb);
+  // ---- commitToLRO :404-489
+  RC(s->S.alloc(n * fb, &s->d_l)); RC(s->S.alloc(n * fb, &s->d_r)); RC(s->S.alloc(n * fb, &s->d_o));
+  RC(b200_h2d(dev, s->d_l, l, n * fb)); RC(b200_h2d(dev, s->d_r, r, n * fb)); RC(b200_h2d(dev, s->d_o, o, n * fb));
   const int nbl[4] = {2, 2, 2, 3};
-  const uint8_t* bcoef[4] = {(const uint8_t*)ch->bl, (const uint8_t*)ch->br, (const uint8_t*)ch->bo, (const uint8_t*)ch->bz};
-  const void* lag[3] = {d_l, d_r, d_o};
-  for (int k = 0; k < 4; k++) { RC(S.alloc(n * fb, &cb[k])); RC(S.alloc((n + nbl[k]) * fb, &bl[k])); }
-  for (int k = 0; k < 3; k++) RC(canonical_blinded(pk, lag[k], bcoef[k], nbl[k], cb[k], bl[k]));
-  for (int k = 0; k < 3; k++) RC(commit(pk, bl[k], n + 2, pts + (size_t)k * jb));
+  for (int k = 0; k < 4; k++) { RC(s->S.alloc(n * fb, &s->cb[k])); RC(s->S.alloc((n + nbl[k]) * fb, &s->bl[k])); }
+  const void* lag[3] = {s->d_l, s->d_r, s->d_o};
+  for (int k = 0; k < 3; k++) RC(canonical_blinded(pk, lag[k], s->blind[k], 2, s->cb[k], s->bl[k]));
+  for (int k = 0; k < 3; k++) RC(commit(pk, s->bl[k], n + 2, (uint8_t*)out_lro + (size_t)k * s->jb));
+  s->stage = 1;
+  *out = s.release();
+  return 0;
+  GUARD_END
+}
 
-  // ---- buildRatioCopyConstraint + commit Z ---------------------------------------------------------
+// buildRatioCopyConstraint :635-668 + commit Z
+int32_t b200_plonk_commit_z(b200_plonk_session_t s, const void* beta, const void* gamma, const void* bz, void* out_z) {
+  GUARD_BEGIN
+  if (!s || !beta || !gamma || !bz || !out_z) return set_error("plonk_commit_z: null argument");
+  if (s->stage != 1) return set_error("plonk_commit_z: call after plonk_begin");
+  b200_plonk_pk_s* pk = s->pk;
+  const size_t n = pk->n, fb = pk->fb;
+  memcpy(s->beta, beta, fb); memcpy(s->gamma, gamma, fb); memcpy(s->blind[3], bz, 3 * fb);
   void* d_z;
-  RC(S.alloc(n * fb, &d_z));
-  RC(b200_plonk_build_z(pk->dom0[0], d_l, d_r, d_o, pk->d_perm, ch->beta, ch->gamma, d_z));
-  RC(canonical_blinded(pk, d_z, bcoef[3], 3, cb[3], bl[3]));
-  RC(commit(pk, bl[3], n + 3, pts + 3 * jb));
+  RC(s->S.alloc(n * fb, &d_z));
+  RC(b200_plonk_build_z(pk->dom0[0], s->d_l, s->d_r, s->d_o, pk->d_perm, s->beta, s->gamma, d_z));
+  RC(canonical_blinded(pk, d_z, s->blind[3], 3, s->cb[3], s->bl[3]));
+  RC(commit(pk, s->bl[3], n + 3, out_z));
+  s->stage = 2;
+  return 0;
+  GUARD_END
+}
 
-  // ---- computeQuotient: numerator on the 4 cosets, divide by Z_H, commit h1, h2, h3 -----------------
-  void* cres;
-  RC(S.alloc(4 * n * fb, &cres));
-  RC(dzero(dev, cres, 4 * n * fb));
-  void* onc[12];      // the 12 polynomials on the current coset
-  for (int k = 0; k < 12; k++) RC(S.alloc(n * fb, &onc[k]));
+// computeQuotient :558-633: numerator on the 4 cosets, divide by Z_H, commit h1, h2, h3
+int32_t b200_plonk_quotient(b200_plonk_session_t s, const void* alpha, void* out_h) {
+  GUARD_BEGIN
+  if (!s || !alpha || !out_h) return set_error("plonk_quotient: null argument");
+  if (s->stage != 2) return set_error("plonk_quotient: call after plonk_commit_z");
+  b200_plonk_pk_s* pk = s->pk;
+  const HostFrCtx* fr = pk->fr;
+  const int dev = pk->dev;
+  const size_t n = pk->n, fb = pk->fb;
+  memcpy(s->alpha, alpha, fb);
+  RC(s->S.alloc(4 * n * fb, &s->h));
+  RC(dzero(dev, s->h, 4 * n * fb));
+  Scratch T(dev);     // the 12 polynomials on the current coset: released when this stage ends
+  void* onc[12];
+  for (int k = 0; k < 12; k++) RC(T.alloc(n * fb, &onc[k]));
   uint8_t gb[8 * HOSTFR_MAX_LIMBS], w4b[8 * HOSTFR_MAX_LIMBS];
   fr->store(gb, pk->g); fr->store(w4b, pk->w4);
   // argument order of b200_plonk_coset_args: l r o z s1 s2 s3 ql qr qm qo qk
-  const void* srcs[12] = {cb[0], cb[1], cb[2], cb[3], pk->br[S1], pk->br[S2], pk->br[S3],
+  const void* srcs[12] = {s->cb[0], s->cb[1], s->cb[2], s->cb[3], pk->br[S1], pk->br[S2], pk->br[S3],
                           pk->br[QL], pk->br[QR], pk->br[QM], pk->br[QO], pk->br[QK]};
   for (uint32_t i = 0; i < 4; i++) {
     for (int k = 0; k < 12; k++) {
@@ -243,29 +290,44 @@ int32_t b200_plonk_prove(b200_plonk_pk_t pk, const void* l, const void* r, const
     memset(&a, 0, sizeof(a));
     a.l = onc[0]; a.r = onc[1]; a.o = onc[2]; a.z = onc[3]; a.s1 = onc[4]; a.s2 = onc[5]; a.s3 = onc[6];
     a.ql = onc[7]; a.qr = onc[8]; a.qm = onc[9]; a.qo = onc[10]; a.qk = onc[11];
-    a.alpha = ch->alpha; a.beta = ch->beta; a.gamma = ch->gamma;
-    a.bl = ch->bl; a.br = ch->br; a.bo = ch->bo; a.bz = ch->bz;
+    a.alpha = s->alpha; a.beta = s->beta; a.gamma = s->gamma;
+    a.bl = s->blind[0]; a.br = s->blind[1]; a.bo = s->blind[2]; a.bz = s->blind[3];
     a.nbl = 2; a.nbr = 2; a.nbo = 2; a.nbz = 3;
-    a.coset_index = i; a.rho = 4; a.out = cres;
+    a.coset_index = i; a.rho = 4; a.out = s->h;
     RC(b200_plonk_constraints_coset(pk->dom0[i], gb, w4b, &a));
   }
-  RC(b200_plonk_divide_by_zh(pk->dom1, pk->logn, cres));      // -> h canonical regular (4n)
-  uint8_t* h = (uint8_t*)cres;
-  for (int k = 0; k < 3; k++) RC(commit(pk, h + (size_t)k * (n + 2) * fb, n + 2, pts + (size_t)(4 + k) * jb));
+  RC(b200_plonk_divide_by_zh(pk->dom1, pk->logn, s->h));      // -> h canonical regular (4n)
+  for (int k = 0; k < 3; k++)
+    RC(commit(pk, (uint8_t*)s->h + (size_t)k * (n + 2) * fb, n + 2, (uint8_t*)out_h + (size_t)k * s->jb));
+  RC(b200_sync(dev));   // T's buffers are in use until here
+  s->stage = 3;
+  return 0;
+  GUARD_END
+}
 
-  // ---- openZ, evaluations at zeta ---------------------------------------------------------------------
-  const HostFr zeta = fr->load(ch->zeta), alpha = fr->load(ch->alpha), beta = fr->load(ch->beta),
-               gamma = fr->load(ch->gamma), v = fr->load(ch->v);
+// openZ :670-687, evaluations at zeta, innerComputeLinearizedPoly :1366-1487 and its commitment :788
+//   out_points: linearised digest, Z-shifted opening quotient (2 G1Jac)
+//   out_values: p(zeta) of {linearised, l, r, o, s1, s2}, then Z(w zeta)   (7 fr.Elements)
+int32_t b200_plonk_linearise(b200_plonk_session_t s, const void* zeta_, void* out_points, void* out_values) {
+  GUARD_BEGIN
+  if (!s || !zeta_ || !out_points || !out_values) return set_error("plonk_linearise: null argument");
+  if (s->stage != 3) return set_error("plonk_linearise: call after plonk_quotient");
+  b200_plonk_pk_s* pk = s->pk;
+  const HostFrCtx* fr = pk->fr;
+  const int dev = pk->dev, curve = pk->curve;
+  const size_t n = pk->n, fb = pk->fb;
+  uint8_t* vals = (uint8_t*)out_values;
+  uint8_t* h = (uint8_t*)s->h;
+  memcpy(s->zeta, zeta_, fb);
+  const HostFr zeta = fr->load(s->zeta), alpha = fr->load(s->alpha), beta = fr->load(s->beta), gamma = fr->load(s->gamma);
   const HostFr wz = fr->mul(zeta, pk->w);
   HostFr zu, lz, rz, oz, s1z, s2z;
-  RC(eval_at(pk, bl[3], n + 3, wz, &zu));
-  RC(eval_at(pk, bl[0], n + 2, zeta, &lz));
-  RC(eval_at(pk, bl[1], n + 2, zeta, &rz));
-  RC(eval_at(pk, bl[2], n + 2, zeta, &oz));
+  RC(eval_at(pk, s->bl[3], n + 3, wz, &zu));
+  RC(eval_at(pk, s->bl[0], n + 2, zeta, &lz));
+  RC(eval_at(pk, s->bl[1], n + 2, zeta, &rz));
+  RC(eval_at(pk, s->bl[2], n + 2, zeta, &oz));
   RC(eval_at(pk, pk->canon[S1], n, zeta, &s1z));
   RC(eval_at(pk, pk->canon[S2], n, zeta, &s2z));
-
-  // ---- innerComputeLinearizedPoly :1366-1487 ----------------------------------------------------------
   auto M = [&](const HostFr& a, const HostFr& b) { return fr->mul(a, b); };
   auto A = [&](const HostFr& a, const HostFr& b) { return fr->add(a, b); };
   const HostFr rl = M(rz, lz);
@@ -279,13 +341,13 @@ int32_t b200_plonk_prove(b200_plonk_pk_t pk, const void* l, const void* r, const
   const HostFr zn2 = M(M(zn, zeta), zeta);
   const HostFr zh = fr->sub(zn, fr->one_());
   const HostFr zm1 = fr->sub(zeta, fr->one_());
-  if (fr->is_zero(zm1)) return set_error("plonk_prove: zeta = 1");
+  if (fr->is_zero(zm1)) return set_error("plonk_linearise: zeta = 1");
   // alpha^2 L1(zeta) = alpha^2 (zeta^n - 1) / (n (zeta - 1))
   const HostFr a2l1 = M(M(M(zh, fr->inv(zm1)), M(alpha, alpha)), fr->inv(fr->from_u64((uint64_t)n)));
-  void* lin;
-  RC(S.alloc((n + 3) * fb, &lin));
+  RC(s->S.alloc((n + 3) * fb, &s->lin));
+  void* lin = s->lin;
   RC(dzero(dev, lin, (n + 3) * fb));
-  RC(axpy(pk, lin, A(c2, a2l1), bl[3], n + 3));
+  RC(axpy(pk, lin, A(c2, a2l1), s->bl[3], n + 3));
   RC(axpy(pk, lin, c1, pk->canon[S3], n));
   RC(axpy(pk, lin, rl, pk->canon[QM], n));
   RC(axpy(pk, lin, lz, pk->canon[QL], n));
@@ -297,36 +359,85 @@ int32_t b200_plonk_prove(b200_plonk_pk_t pk, const void* l, const void* r, const
     RC(axpy(pk, lin, fr->neg(hc), h + (size_t)k * (n + 2) * fb, n + 2));
     hc = M(hc, zn2);
   }
-  RC(commit(pk, lin, n + 3, pts + 7 * jb));
-
-  // ---- batchOpening :796-837 (fold with powers of v, divide by X - zeta) and the Z opening -----------------
-  const void* open_p[6] = {lin, bl[0], bl[1], bl[2], pk->canon[S1], pk->canon[S2]};
+  RC(commit(pk, lin, n + 3, out_points));
+  // claimed values of the batch opening (BatchedProof.ClaimedValues) - needed by the caller to derive v
+  const void* open_p[6] = {lin, s->bl[0], s->bl[1], s->bl[2], pk->canon[S1], pk->canon[S2]};
   const size_t open_n[6] = {n + 3, n + 2, n + 2, n + 2, n, n};
-  void* fold;
-  RC(S.alloc((n + 3) * fb, &fold));
-  RC(dzero(dev, fold, (n + 3) * fb));
-  HostFr vp = fr->one_();
   for (int k = 0; k < 6; k++) {
     HostFr e;
     RC(eval_at(pk, open_p[k], open_n[k], zeta, &e));
     fr->store(vals + (size_t)k * fb, e);
-    RC(axpy(pk, fold, vp, open_p[k], open_n[k]));
-    vp = M(vp, v);
   }
+  // Z-shifted opening: (Z(X) - Z(w zeta)) / (X - w zeta)
   uint8_t zb[8 * HOSTFR_MAX_LIMBS], rem[8 * HOSTFR_MAX_LIMBS];
-  fr->store(zb, zeta);
-  RC(b200_poly_div_by_linear(dev, curve, fold, n + 3, zb, rem));
-  RC(commit(pk, fold, n + 2, pts + 8 * jb));
+  Scratch T(dev);
   void* zq;
-  RC(S.alloc((n + 3) * fb, &zq));
-  RC(d2d(dev, zq, bl[3], (n + 3) * fb));
+  RC(T.alloc((n + 3) * fb, &zq));
+  RC(d2d(dev, zq, s->bl[3], (n + 3) * fb));
   fr->store(zb, wz);
   RC(b200_poly_div_by_linear(dev, curve, zq, n + 3, zb, rem));
-  if (!fr->eq(fr->load(rem), zu)) return set_error("plonk_prove: Z(w zeta) from the division differs from the evaluation");
-  RC(commit(pk, zq, n + 2, pts + 9 * jb));
+  if (!fr->eq(fr->load(rem), zu)) return set_error("plonk_linearise: Z(w zeta) from the division differs from the evaluation");
+  RC(commit(pk, zq, n + 2, (uint8_t*)out_points + s->jb));
   fr->store(vals + 6 * fb, zu);
   RC(b200_sync(dev));
+  s->stage = 4;
   return 0;
+  GUARD_END
+}
+
+// batchOpening :796-837: fold {linearised, l, r, o, s1, s2} with powers of v, divide by X - zeta, commit
+int32_t b200_plonk_batch_open(b200_plonk_session_t s, const void* v_, void* out_point) {
+  GUARD_BEGIN
+  if (!s || !v_ || !out_point) return set_error("plonk_batch_open: null argument");
+  if (s->stage != 4) return set_error("plonk_batch_open: call after plonk_linearise");
+  b200_plonk_pk_s* pk = s->pk;
+  const HostFrCtx* fr = pk->fr;
+  const int dev = pk->dev, curve = pk->curve;
+  const size_t n = pk->n, fb = pk->fb;
+  const HostFr v = fr->load(v_);
+  const void* open_p[6] = {s->lin, s->bl[0], s->bl[1], s->bl[2], pk->canon[S1], pk->canon[S2]};
+  const size_t open_n[6] = {n + 3, n + 2, n + 2, n + 2, n, n};
+  Scratch T(dev);
+  void* fold;
+  RC(T.alloc((n + 3) * fb, &fold));
+  RC(dzero(dev, fold, (n + 3) * fb));
+  HostFr vp = fr->one_();
+  for (int k = 0; k < 6; k++) {
+    RC(axpy(pk, fold, vp, open_p[k], open_n[k]));
+    vp = fr->mul(vp, v);
+  }
+  uint8_t rem[8 * HOSTFR_MAX_LIMBS];
+  RC(b200_poly_div_by_linear(dev, curve, fold, n + 3, s->zeta, rem));
+  RC(commit(pk, fold, n + 2, out_point));
+  RC(b200_sync(dev));
+  s->stage = 5;
+  return 0;
+  GUARD_END
+}
+
+// the five stages behind one call, for callers that already hold every challenge
+int32_t b200_plonk_prove(b200_plonk_pk_t pk, const void* l, const void* r, const void* o,
+                         const b200_plonk_challenges* ch, void* out_points, void* out_values) {
+  GUARD_BEGIN
+  if (!pk || !l || !r || !o || !ch || !out_points || !out_values) return set_error("plonk_prove: null argument");
+  if (!ch->gamma || !ch->beta || !ch->alpha || !ch->zeta || !ch->v || !ch->bl || !ch->br || !ch->bo || !ch->bz)
+    return set_error("plonk_prove: null challenge / blinding pointer");
+  const size_t jb = get_msm_ops(pk->curve, 1)->jac_bytes;
+  uint8_t* pts = (uint8_t*)out_points;          // L, R, O, Z, H1, H2, H3, linearised, batch opening, Z opening
+  b200_plonk_session_t s = nullptr;
+  int32_t rc = b200_plonk_begin(pk, l, r, o, ch->bl, ch->br, ch->bo, &s, pts);
+  if (!rc) rc = b200_plonk_commit_z(s, ch->beta, ch->gamma, ch->bz, pts + 3 * jb);
+  if (!rc) rc = b200_plonk_quotient(s, ch->alpha, pts + 4 * jb);
+  uint8_t two[2 * 288];     // linearised digest, Z opening; 288 B = G1Jac of the largest curve (BW6-761: 3 x 96 B)
+  if (jb > 288) return set_error("plonk_prove: unexpected point size");
+  if (!rc) rc = b200_plonk_linearise(s, ch->zeta, two, out_values);
+  if (!rc) {
+    memcpy(pts + 7 * jb, two, jb);
+    memcpy(pts + 9 * jb, two + jb, jb);
+    rc = b200_plonk_batch_open(s, ch->v, pts + 8 * jb);
+  }
+  b200_plonk_end(s);
+  return rc;
   GUARD_END
 }
 

@@ -33,7 +33,8 @@ EXPORTS = [
     "b200_vec_axpy", "b200_vec_scan", "b200_plonk_build_z", "b200_poly_eval", "b200_poly_div_by_linear",
     "b200_point_add_jac", "b200_point_to_affine", "b200_groth16_pk_load", "b200_groth16_pk_free", "b200_groth16_prove", "b200_groth16_msms",
     "b200_groth16_assemble", "b200_fixed_base_batch", "b200_msm_submit",
-    "b200_plonk_pk_load", "b200_plonk_pk_free", "b200_plonk_prove",
+    "b200_plonk_pk_load", "b200_plonk_pk_free", "b200_plonk_prove", "b200_plonk_begin", "b200_plonk_commit_z",
+    "b200_plonk_quotient", "b200_plonk_linearise", "b200_plonk_batch_open", "b200_plonk_end",
 ]
 
 
@@ -120,6 +121,12 @@ def load(path: str = None):
     lib.b200_plonk_pk_load.argtypes = [i32, i32, ctypes.POINTER(PlonkPkDesc), ctypes.POINTER(vp)]
     lib.b200_plonk_pk_free.argtypes = [vp]
     lib.b200_plonk_prove.argtypes = [vp, vp, vp, vp, ctypes.POINTER(PlonkChallenges), vp, vp]
+    lib.b200_plonk_begin.argtypes = [vp, vp, vp, vp, vp, vp, vp, ctypes.POINTER(vp), vp]
+    lib.b200_plonk_commit_z.argtypes = [vp, vp, vp, vp, vp]
+    lib.b200_plonk_quotient.argtypes = [vp, vp, vp]
+    lib.b200_plonk_linearise.argtypes = [vp, vp, vp, vp]
+    lib.b200_plonk_batch_open.argtypes = [vp, vp, vp]
+    lib.b200_plonk_end.argtypes = [vp]
     lib.b200_fixed_base_batch.argtypes = [i32, i32, i32, vp, vp, i32, sz, vp, i32]
     lib.b200_msm_profile.argtypes = [vp, sz, sz, vp, vp, ctypes.POINTER(ctypes.c_float)]
     lib.b200_ntt_domain_new.argtypes = [i32, i32, u32, vp, vp, ctypes.POINTER(vp)]

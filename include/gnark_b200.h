@@ -231,6 +231,26 @@ int32_t b200_plonk_pk_free(b200_plonk_pk_t pk);
  * the claimed values at zeta of {linearised polynomial, l, r, o, s1, s2} (BatchedProof.ClaimedValues) and Z(w*zeta). */
 int32_t b200_plonk_prove(b200_plonk_pk_t pk, const void* l, const void* r, const void* o,
                          const b200_plonk_challenges* ch, void* out_points, void* out_values);
+/* The same proof, one entry point per Fiat-Shamir round, so that a caller can derive each challenge from the digests
+ * of the previous round exactly as prove.go:492-555 (gamma, beta <- [L],[R],[O]; alpha <- [Z]; zeta <- [H1..3];
+ * v <- linearised digest + opened values).  Stages must be called in this order; b200_plonk_end releases the
+ * session at any point.
+ *   begin       commitToLRO :404-489            out_lro: [L], [R], [O]                         (3 G1Jac)
+ *   commit_z    buildRatioCopyConstraint :635   out_z: [Z]
+ *   quotient    computeQuotient :558-633        out_h: [H1], [H2], [H3]
+ *   linearise   openZ :670-687 + computeLinearizedPolynomial :724-794
+ *               out_points: linearised digest, Z-shifted opening quotient (2 G1Jac);
+ *               out_values: p(zeta) of {linearised, l, r, o, s1, s2}, then Z(w*zeta)              (7 fr.Elements)
+ *   batch_open  batchOpening :796-837           out_point: BatchedProof.H */
+typedef struct b200_plonk_session_s* b200_plonk_session_t;
+int32_t b200_plonk_begin(b200_plonk_pk_t pk, const void* l, const void* r, const void* o, const void* bl /*2*/,
+                         const void* br /*2*/, const void* bo /*2*/, b200_plonk_session_t* out, void* out_lro);
+int32_t b200_plonk_commit_z(b200_plonk_session_t s, const void* beta, const void* gamma, const void* bz /*3*/,
+                            void* out_z);
+int32_t b200_plonk_quotient(b200_plonk_session_t s, const void* alpha, void* out_h);
+int32_t b200_plonk_linearise(b200_plonk_session_t s, const void* zeta, void* out_points, void* out_values);
+int32_t b200_plonk_batch_open(b200_plonk_session_t s, const void* v, void* out_point);
+int32_t b200_plonk_end(b200_plonk_session_t s);
 
 /* ---- Groth16 prover (host layer mirroring backend/accelerated/icicle/groth16/
  *      bn254/icicle.go:784-1360 Prove + setupDevicePointers :88-264) ------------

@@ -28,6 +28,12 @@ def mock():
     m.b200_plonk_pk_load.argtypes = [i32, i32, ctypes.POINTER(b200.PlonkPkDesc), ctypes.POINTER(vp)]
     m.b200_plonk_pk_free.argtypes = [vp]
     m.b200_plonk_prove.argtypes = [vp, vp, vp, vp, ctypes.POINTER(b200.PlonkChallenges), vp, vp]
+    m.b200_plonk_begin.argtypes = [vp, vp, vp, vp, vp, vp, vp, ctypes.POINTER(vp), vp]
+    m.b200_plonk_commit_z.argtypes = [vp, vp, vp, vp, vp]
+    m.b200_plonk_quotient.argtypes = [vp, vp, vp]
+    m.b200_plonk_linearise.argtypes = [vp, vp, vp, vp]
+    m.b200_plonk_batch_open.argtypes = [vp, vp, vp]
+    m.b200_plonk_end.argtypes = [vp]
     m.b200_last_error.restype = ctypes.c_char_p
     return m
 
@@ -72,6 +78,21 @@ def test_plonk_host_orchestration_vs_oracle(mock, logn):
         assert jac_to_affine(c, 1, pts[k]) == ec.scalar_mul(F, dl[k], c.g1), name
     got = ff.unpack_elements(vals, r, L)
     assert got[:6] == want.claimed and got[6] == want.zu
+    # the same proof round by round (the way a Fiat-Shamir transcript drives it), and the stage order is enforced
+    jl = 3 * c.fp_limbs
+    s_ = ctypes.c_void_p(0)
+    lro, zpt, hpts = np.zeros((3, jl), dtype=np.uint64), np.zeros(jl, dtype=np.uint64), np.zeros((3, jl), dtype=np.uint64)
+    two, vals2, bpt = np.zeros((2, jl), dtype=np.uint64), np.zeros((7, L), dtype=np.uint64), np.zeros(jl, dtype=np.uint64)
+    assert mock.b200_plonk_begin(h, P(L_), P(R_), P(O_), P(sc["bl"]), P(sc["br"]), P(sc["bo"]), ctypes.byref(s_), P(lro)) == 0
+    assert mock.b200_plonk_quotient(s_, P(sc["alpha"]), P(hpts)) != 0 and b"after plonk_commit_z" in mock.b200_last_error()
+    assert mock.b200_plonk_commit_z(s_, P(sc["beta"]), P(sc["gamma"]), P(sc["bz"]), P(zpt)) == 0
+    assert mock.b200_plonk_batch_open(s_, P(sc["v"]), P(bpt)) != 0
+    assert mock.b200_plonk_quotient(s_, P(sc["alpha"]), P(hpts)) == 0
+    assert mock.b200_plonk_linearise(s_, P(sc["zeta"]), P(two), P(vals2)) == 0
+    assert mock.b200_plonk_batch_open(s_, P(sc["v"]), P(bpt)) == 0
+    assert mock.b200_plonk_end(s_) == 0
+    staged = np.concatenate([lro, zpt[None], hpts, two[0:1], bpt[None], two[1:2]])
+    assert np.array_equal(staged, pts) and np.array_equal(vals2, vals)
     # a permutation entry out of range is refused, not dereferenced
     bad = perm.copy(); bad[1] = 3 * n
     d.perm = P(bad).value
