@@ -84,6 +84,119 @@ HD void mont_mul_raw(uint32_t* r, const uint32_t* a, const uint32_t* b) {
   for (int k = 0; k < N; k++) r[k] = borrow ? s[k] : d[k];
 }
 
+// ---------------------------------------------------------------------------
+// Wide (unreduced) products and a separate Montgomery reduction: the building blocks of the dedicated squaring
+// (GB200_MONT_SQR) and of the lazily reduced Fp2 product (GB200_FP2_LAZY).  Compile-time options, off by default;
+// bit-exact against the fused product (tests/test_emulation.py::test_wide_arithmetic and the *_opt emulation runs).
+// ---------------------------------------------------------------------------
+
+// t[0..2N) = a * b for ANY N-limb a, b (no reduction).  Same even/odd carry chains as mont_mul_raw without the m*p rows.
+template <int N>
+HD void wide_mul_raw(uint32_t* t, const uint32_t* a, const uint32_t* b) {
+  uint32_t acc[2][2 * N + 3];
+#pragma unroll
+  for (int k = 0; k < 2 * N + 3; k++) { acc[0][k] = 0; acc[1][k] = 0; }
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    mad_chain<N, 0, false>(acc[i & 1], i, a, b[i]);          // products starting at even+i positions
+    mad_chain<N, 1, false>(acc[(i & 1) ^ 1], i, a, b[i]);
+  }
+  t[0] = ptx::add_cc(acc[0][0], acc[1][0]);
+#pragma unroll
+  for (int k = 1; k < 2 * N; k++) t[k] = ptx::addc_cc(acc[0][k], acc[1][k]);
+  (void)ptx::addc(0, 0);
+}
+
+// cross terms of a square: chains of a_i * a_j, j > i, all j of one parity
+template <int N, int I>
+struct SqrCross {
+  HD static void run(uint32_t (*acc)[2 * N + 3], const uint32_t* a) {
+    if constexpr (I + 1 < N) mad_chain<N, I + 1, false>(acc[1], I, a, a[I]);   // positions 2I+1, 2I+3, ... (odd)
+    if constexpr (I + 2 < N) mad_chain<N, I + 2, false>(acc[0], I, a, a[I]);   // positions 2I+2, 2I+4, ... (even)
+    if constexpr (I + 2 < N) SqrCross<N, I + 1>::run(acc, a);
+  }
+};
+
+// t[0..2N) = a * a:  2 * sum_{i<j} a_i a_j 2^(32(i+j)) + sum_i a_i^2 2^(64 i)   (N(N-1)/2 + N products instead of N^2)
+template <int N>
+HD void wide_sqr_raw(uint32_t* t, const uint32_t* a) {
+  uint32_t acc[2][2 * N + 3];
+#pragma unroll
+  for (int k = 0; k < 2 * N + 3; k++) { acc[0][k] = 0; acc[1][k] = 0; }
+  SqrCross<N, 0>::run(acc, a);
+  uint32_t c[2 * N];
+  c[0] = ptx::add_cc(acc[0][0], acc[1][0]);
+#pragma unroll
+  for (int k = 1; k < 2 * N; k++) c[k] = ptx::addc_cc(acc[0][k], acc[1][k]);
+  (void)ptx::addc(0, 0);
+  // double (the cross sum is < 2^(64N - 1))
+#pragma unroll
+  for (int k = 2 * N - 1; k > 0; k--) c[k] = (c[k] << 1) | (c[k - 1] >> 31);
+  c[0] <<= 1;
+  // add the diagonal a_i^2 at words 2i, 2i+1
+  t[0] = ptx::mad_lo_cc(a[0], a[0], c[0]);
+  t[1] = ptx::madc_hi_cc(a[0], a[0], c[1]);
+#pragma unroll
+  for (int i = 1; i < N; i++) {
+    t[2 * i] = ptx::madc_lo_cc(a[i], a[i], c[2 * i]);
+    t[2 * i + 1] = ptx::madc_hi_cc(a[i], a[i], c[2 * i + 1]);
+  }
+  (void)ptx::addc(0, 0);
+}
+
+// r = T * R^-1 mod p for a 2N-limb T < p * R; output < p.  The m*p rows of mont_mul_raw on their own.
+template <class P>
+HD void mont_reduce_wide(uint32_t* r, const uint32_t* T) {
+  constexpr int N = P::N;
+  uint32_t acc[2][2 * N + 3];
+  uint32_t p[N];
+#pragma unroll
+  for (int k = 0; k < N; k++) p[k] = P::mod(k);
+#pragma unroll
+  for (int k = 0; k < 2 * N + 3; k++) { acc[0][k] = k < 2 * N ? T[k] : 0; acc[1][k] = 0; }
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    uint32_t* X = acc[i & 1];
+    uint32_t* Y = acc[(i & 1) ^ 1];
+    // m from the folded low word, computed before the fold so that no carry is live across plain code
+    const uint32_t m = (X[i] + Y[i]) * P::INV;
+    if (i > 0) {
+      X[i] = ptx::add_cc(X[i], Y[i]);             // fold; the carry goes into the Y chain
+      mad_chain<N, 1, true>(Y, i, p, m);
+    } else {
+      mad_chain<N, 1, false>(Y, i, p, m);
+    }
+    mad_chain<N, 0, false>(X, i, p, m);           // X[i] becomes 0
+  }
+  uint32_t s[N];
+  s[0] = ptx::add_cc(acc[0][N], acc[1][N]);
+#pragma unroll
+  for (int k = 1; k < N; k++) s[k] = ptx::addc_cc(acc[0][N + k], acc[1][N + k]);
+  uint32_t d[N];
+  d[0] = ptx::sub_cc(s[0], p[0]);
+#pragma unroll
+  for (int k = 1; k < N; k++) d[k] = ptx::subc_cc(s[k], p[k]);
+  const uint32_t borrow = ptx::subc(0, 0);
+#pragma unroll
+  for (int k = 0; k < N; k++) r[k] = borrow ? s[k] : d[k];
+}
+
+// multi-limb helpers without reduction (K limbs)
+template <int K>
+HD void limbs_add(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+  r[0] = ptx::add_cc(a[0], b[0]);
+#pragma unroll
+  for (int k = 1; k < K; k++) r[k] = ptx::addc_cc(a[k], b[k]);
+  (void)ptx::addc(0, 0);
+}
+template <int K>
+HD void limbs_sub(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+  r[0] = ptx::sub_cc(a[0], b[0]);
+#pragma unroll
+  for (int k = 1; k < K; k++) r[k] = ptx::subc_cc(a[k], b[k]);
+  (void)ptx::subc(0, 0);
+}
+
 template <class P>
 HD void mod_add_raw(uint32_t* r, const uint32_t* a, const uint32_t* b) {
   constexpr int N = P::N;
@@ -153,7 +266,15 @@ struct alignas(16) Fp {
 #else
   HD friend Fp operator*(const Fp& a, const Fp& b) { Fp r; mont_mul_raw<P>(r.l, a.l, b.l); return r; }
 #endif
+#if defined(GB200_MONT_SQR)
+  HD Fp sqr() const {
+    uint32_t t[2 * N];
+    wide_sqr_raw<N>(t, l);
+    Fp r; mont_reduce_wide<P>(r.l, t); return r;
+  }
+#else
   HD Fp sqr() const { return (*this) * (*this); }
+#endif
   HD Fp neg() const { return is_zero() ? *this : (zero() - *this); }
   HD Fp dbl() const { return *this + *this; }
   // Montgomery -> canonical (multiply by 1) and back
@@ -290,6 +411,9 @@ struct alignas(16) Fp {
 // rule restated from std/algebra/emulated/fields_bn254/e2.go:203-213 and
 // std/algebra/native/fields_bls12377/e2.go:134.  Memory = gnark E2{A0, A1}.
 // ---------------------------------------------------------------------------
+template <class T> struct is_device_fp { static constexpr bool value = false; };
+template <class P> struct is_device_fp<Fp<P>> { static constexpr bool value = true; };
+
 template <class F, unsigned BETA>
 struct alignas(16) Fp2 {
   static constexpr int DEGREE = 2;
@@ -304,7 +428,36 @@ struct alignas(16) Fp2 {
   HD friend Fp2 operator-(const Fp2& x, const Fp2& y) { Fp2 r; r.a0 = x.a0 - y.a0; r.a1 = x.a1 - y.a1; return r; }
   HD static F mul_beta(const F& t) { return BETA == 1 ? t : t.mul_small(BETA); }
   // not inlined on device: one copy of the 3-multiplication body per kernel
+  // Karatsuba on UNREDUCED double-width products: 3 wide products and 2 Montgomery reductions instead of 3 of each.
+  //   c1 = (a0+a1)(b0+b1) - a0b0 - a1b1   (>= 0, < 2p^2)
+  //   c0 = a0b0 + BETA (p^2 - a1b1)       (>= 0, < (1+BETA) p^2 < pR for every modulus here)
+  template <class FF = F>
+  HD static Fp2 mul_lazy(const Fp2& x, const Fp2& y) {
+    constexpr int N = FF::N;
+    using P = typename FF::Params;
+    uint32_t t0[2 * N], t1[2 * N], t2[2 * N], sa[N], sb[N];
+    wide_mul_raw<N>(t0, x.a0.l, y.a0.l);
+    wide_mul_raw<N>(t1, x.a1.l, y.a1.l);
+    limbs_add<N>(sa, x.a0.l, x.a1.l);           // < 2p: fits N limbs (top bit of p clear)
+    limbs_add<N>(sb, y.a0.l, y.a1.l);
+    wide_mul_raw<N>(t2, sa, sb);
+    limbs_sub<2 * N>(t2, t2, t0);
+    limbs_sub<2 * N>(t2, t2, t1);
+    uint32_t q[2 * N];
+#pragma unroll
+    for (int k = 0; k < 2 * N; k++) q[k] = P::psq(k);
+    limbs_sub<2 * N>(q, q, t1);                 // p^2 - a1 b1
+#pragma unroll
+    for (unsigned k = 0; k < BETA; k++) limbs_add<2 * N>(t0, t0, q);
+    Fp2 r;
+    mont_reduce_wide<P>(r.a0.l, t0);
+    mont_reduce_wide<P>(r.a1.l, t2);
+    return r;
+  }
   HDNI static Fp2 mul(const Fp2& x, const Fp2& y) {
+#if defined(GB200_FP2_LAZY)
+    if constexpr (is_device_fp<F>::value) return mul_lazy<F>(x, y);
+#endif
     // Karatsuba: 3 base multiplications
     F v0 = x.a0 * y.a0;
     F v1 = x.a1 * y.a1;

@@ -44,6 +44,21 @@ int field_op(int op, const void* a_, const void* b_, void* out_) {
   return 0;
 }
 
+// raw wide routines (field.cuh): op 0 wide_mul (a, b: N limbs -> 2N), 1 wide_sqr (a -> 2N), 2 mont_reduce_wide (a: 2N -> N)
+template <class F>
+int wide_op(int op, const void* a_, const void* b_, void* out_) {
+  constexpr int N = F::N;
+  const uint32_t* a = reinterpret_cast<const uint32_t*>(a_);
+  const uint32_t* b = reinterpret_cast<const uint32_t*>(b_);
+  uint32_t* out = reinterpret_cast<uint32_t*>(out_);
+  switch (op) {
+    case 0: wide_mul_raw<N>(out, a, b); return 0;
+    case 1: wide_sqr_raw<N>(out, a); return 0;
+    case 2: mont_reduce_wide<typename F::Params>(out, a); return 0;
+  }
+  return -1;
+}
+
 template <class Fr, class F>
 int msm_emu(const void* points_, const void* scalars_, uint32_t n, int c, int precomp, uint32_t task_len,
             uint32_t chunk, void* out_jac) {
@@ -467,6 +482,31 @@ int emu_hostfr_op(int curve, int op, const void* a_, const void* b_, void* out) 
   }
   c.store(out, r);
   return 0;
+}
+
+int emu_wide_op(int field_id, int op, const void* a, const void* b, void* out) {
+  switch (field_id) {
+    case 0: return wide_op<bn254_fp>(op, a, b, out);
+    case 1: return wide_op<bn254_fr>(op, a, b, out);
+    case 2: return wide_op<bls12_381_fp>(op, a, b, out);
+    case 3: return wide_op<bls12_381_fr>(op, a, b, out);
+    case 4: return wide_op<bls12_377_fp>(op, a, b, out);
+    case 5: return wide_op<bls12_377_fr>(op, a, b, out);
+    case 6: return wide_op<bw6_761_fp>(op, a, b, out);
+    case 7: return wide_op<bw6_761_fr>(op, a, b, out);
+  }
+  return -1;
+}
+// 1 when this library was compiled with the optional squaring / lazy-Fp2 paths
+int emu_build_options(void) {
+  int v = 0;
+#if defined(GB200_MONT_SQR)
+  v |= 1;
+#endif
+#if defined(GB200_FP2_LAZY)
+  v |= 2;
+#endif
+  return v;
 }
 
 // field_id = curve*2 + (0: fp, 1: fr)

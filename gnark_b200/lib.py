@@ -85,7 +85,9 @@ def load(path: str = None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = path or LIB_PATH
+    # GB200_LIB: load another build of the same library (e.g. libgnark_b200_opt.so, `make -C gnark_b200/csrc opt`:
+    # dedicated Montgomery squaring + lazily reduced Fp2 product) for A/B runs on hardware
+    p = path or os.environ.get("GB200_LIB") or LIB_PATH
     if not os.path.exists(p):
         raise B200Error(
             f"{p} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "

@@ -66,6 +66,72 @@ def test_inverse_gcd_many(hostemu, c):
 
 
 @pytest.mark.parametrize("c", ALL, ids=lambda c: c.name)
+def test_wide_arithmetic(hostemu, c):
+    """wide_mul_raw / wide_sqr_raw / mont_reduce_wide (building blocks of the optional squaring and lazy Fp2 paths)
+    against big-int arithmetic: ANY N-limb operands for the products (all-ones limbs included), T < p*R for the
+    reduction (largest admissible values included)"""
+    rng = random.Random(77)
+    for which, (q, L) in enumerate(((c.p, c.fp_limbs), (c.r, c.fr_limbs))):
+        fid = c.curve_id * 2 + which
+        top = 1 << (64 * L)
+        R = top
+        def arr(x, limbs):
+            return np.frombuffer(int(x).to_bytes(8 * limbs, "little"), dtype=np.uint64).copy()
+        def val(a):
+            return int.from_bytes(a.tobytes(), "little")
+        cases = [(0, 0), (top - 1, top - 1), (1, top - 1), (q - 1, q - 1), (2 * q - 1, 2 * q - 1)]
+        cases += [(rng.randrange(top), rng.randrange(top)) for _ in range(60)]
+        for a, b in cases:
+            O = np.zeros(2 * L, dtype=np.uint64)
+            assert hostemu.emu_wide_op(fid, 0, P(arr(a, L)), P(arr(b, L)), P(O)) == 0
+            assert val(O) == a * b, (c.name, which, "wide_mul")
+            assert hostemu.emu_wide_op(fid, 1, P(arr(a, L)), P(arr(a, L)), P(O)) == 0
+            assert val(O) == a * a, (c.name, which, "wide_sqr")
+        Rinv = pow(R, -1, q)
+        ts = [0, q * R - 1, q * q, (q - 1) * (q - 1), 6 * q * q if 6 * q < R else q * q]
+        ts += [rng.randrange(q * R) for _ in range(60)]
+        for t in ts:
+            O = np.zeros(L, dtype=np.uint64)
+            assert hostemu.emu_wide_op(fid, 2, P(arr(t, 2 * L)), P(arr(0, L)), P(O)) == 0
+            assert val(O) == t * Rinv % q, (c.name, which, "mont_reduce_wide")
+
+
+@pytest.mark.parametrize("c", ALL, ids=lambda c: c.name)
+def test_optional_paths_field_ops(hostemu_opt, c):
+    """field / Fp2 operations of the library compiled with GB200_MONT_SQR + GB200_FP2_LAZY against big-int"""
+    test_field_ops.__wrapped__(hostemu_opt, c) if hasattr(test_field_ops, "__wrapped__") else test_field_ops(hostemu_opt, c)
+    if c.fp2_nonresidue is not None:
+        test_fp2_ops(hostemu_opt, c)
+
+
+@pytest.mark.parametrize("c", [CURVES["bn254"], CURVES["bls12-377"]], ids=lambda c: c.name)
+@pytest.mark.parametrize("group", (1, 2))
+def test_optional_paths_msm(hostemu_opt, c, group):
+    """one MSM per group through the optional arithmetic paths (G2 of BLS12-377 exercises BETA = 5 in the lazy product)"""
+    rng = random.Random(9 + group)
+    F, base = pick_base(c, group, rng)
+    n = 23
+    pts = [ec.scalar_mul(F, rng.randrange(1, 1 << 40), base) for _ in range(n)]
+    pts[3] = ec.INF
+    pts[5] = pts[4]
+    pts[7] = ec.affine_neg(F, pts[6])
+    sc = [rng.randrange(c.r) for _ in range(n)]
+    sc[0], sc[1], sc[2] = 0, c.r - 1, 1
+    sc[4] = sc[5]
+    sc[6] = sc[7] = 12345
+    exp = ec.msm_naive(F, pts, sc)
+    PA, SA = ec.pack_points(c, group, pts), ff.pack_elements(sc, c.r, c.fr_limbs)
+    deg = 2 if (group == 2 and c.fp2_nonresidue is not None) else 1
+    for (cw, pre, tl, ch) in ((7, 1, 2, 16), (5, 0, 3, 4)):
+        out = np.zeros(3 * c.fp_limbs * deg, dtype=np.uint64)
+        assert hostemu_opt.emu_msm(c.curve_id, group, P(PA), P(SA), n, cw, pre, tl, ch, P(out)) == 0
+        assert ec.from_jac(F, ec.unpack_points(c, group, out, ncoords=3)[0]) == exp
+    out = np.zeros(3 * c.fp_limbs * deg, dtype=np.uint64)
+    assert hostemu_opt.emu_msm_ba(c.curve_id, group, P(PA), P(SA), n, 5, 1, 4, 8, 3, P(out)) == 0
+    assert ec.from_jac(F, ec.unpack_points(c, group, out, ncoords=3)[0]) == exp
+
+
+@pytest.mark.parametrize("c", ALL, ids=lambda c: c.name)
 def test_host_fr(hostemu, c):
     """host_fr.h: the run-time-limb-count Fr arithmetic the C++ PLONK orchestration uses between device stages"""
     rng = random.Random(99)

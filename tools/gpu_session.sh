@@ -27,6 +27,14 @@ timeout 600 python tools/sweep_msm.py bn254 2 20 --set GB200_MSM_WINDOW=14,16,18
 timeout 600 python tools/sweep_msm.py bn254 1 20 --set GB200_MSM_BATCH_AFFINE=0,2,4,5,6 > $OUT/sweep_bn254_ba.jsonl 2>> $OUT/session.err
 timeout 600 python tools/sweep_msm.py bn254 2 20 --set GB200_MSM_BATCH_AFFINE=0,3,5 > $OUT/sweep_bn254_g2_ba.jsonl 2>> $OUT/session.err
 timeout 600 python tools/sweep_msm.py bls12-381 1 20 --set GB200_MSM_BATCH_AFFINE=0,3,5 > $OUT/sweep_bls381_ba.jsonl 2>> $OUT/session.err
+# compile-time variant: dedicated squaring + lazily reduced Fp2 product (built by `make -C gnark_b200/csrc opt`)
+if [ -f gnark_b200/lib/libgnark_b200_opt.so ]; then
+  for cfg in "bn254 1" "bn254 2" "bls12-381 1"; do
+    set -- $cfg
+    GB200_LIB=$PWD/gnark_b200/lib/libgnark_b200_opt.so timeout 600 python tools/sweep_msm.py $1 $2 20 --set GB200_MSM_BATCH_AFFINE=0,5 \
+        | sed 's/^{/{"lib": "opt", /' >> $OUT/sweep_optlib.jsonl 2>> $OUT/session.err
+  done
+fi
 cat $OUT/sweep_*.jsonl | cut -c1-400 | tee -a $OUT/session.log
 
 echo "== 4. ncu: launch list of one Groth16-sized step and full captures of the NTT pass and the G2 accumulate" | tee -a $OUT/session.log
