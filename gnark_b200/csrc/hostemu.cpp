@@ -297,11 +297,13 @@ int msm_emu_ba(const void* points_, const void* scalars_, uint32_t n, int c, int
     bound = bound / 2 + nb + 1;
     if (bound > cap[lvl & 1]) bound = cap[lvl & 1];
     if (run > bound) return -2;                                  // the grid would not cover the level
-    const size_t threads = (bound + MSM_BA_BATCH - 1) / MSM_BA_BATCH;
+    // small emulated problems would always get the minimum batch: alternate so that every size is walked
+    const uint32_t batch = (lvl % 3 == 0) ? (uint32_t)MSM_BA_BATCH : (lvl % 3 == 1 ? msm_ba_batch_for(bound) : 13u);
+    const size_t threads = (bound + batch - 1) / batch;
     for (size_t t = 0; t < threads; t++) {
-      const uint64_t o_begin = (uint64_t)t * MSM_BA_BATCH;
+      const uint64_t o_begin = (uint64_t)t * batch;
       if (o_begin >= run) continue;
-      const uint32_t o_end = (uint32_t)std::min<uint64_t>(o_begin + MSM_BA_BATCH, run);
+      const uint32_t o_end = (uint32_t)std::min<uint64_t>(o_begin + batch, run);
       if (lvl == 0) {
         BaSrcTable<F> src{table.data(), svals.data()};
         msm_ba_level_thread<F, BaSrcTable<F>>(src, off_in, off_out.data(), nb, (uint32_t)o_begin, o_end, bufs[0].data());

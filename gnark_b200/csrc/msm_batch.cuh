@@ -59,7 +59,7 @@ HD int msm_ba_classify(const Affine<F>& P, const Affine<F>& Q, bool has_q, F& nu
   return BA_ADD;
 }
 
-// One thread: output entries [o_begin, o_end) (at most MSM_BA_BATCH) of a level.
+// One thread: output entries [o_begin, o_end) (at most MSM_BA_BATCH; msm_ba_batch_for) of a level.
 //   off_in / off_out: bucket offsets of the input / output level (nb + 1 entries each)
 template <class F, class SRC>
 HD void msm_ba_level_thread(const SRC& src, const uint32_t* off_in, const uint32_t* off_out, uint32_t nb,
@@ -113,6 +113,15 @@ HD void msm_ba_level_thread(const SRC& src, const uint32_t* off_in, const uint32
     }
     out[o] = R;
   }
+}
+
+// outputs per thread (= additions sharing one inversion) for a level with at most `bound` outputs: the full
+// batch while that still leaves >= ~150k threads (148 SMs x 8 blocks x 128), smaller batches for the small deep levels
+HD uint32_t msm_ba_batch_for(size_t bound) {
+  size_t b = bound / 150000;
+  if (b > (size_t)MSM_BA_BATCH) b = MSM_BA_BATCH;
+  if (b < 8) b = 8;
+  return (uint32_t)b;
 }
 
 // next level's per-bucket count

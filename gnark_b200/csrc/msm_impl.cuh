@@ -132,11 +132,11 @@ static __global__ void k_msm_ba_next_counts(const uint32_t* __restrict__ off_in,
 template <class F, class SRC>
 __global__ void __launch_bounds__(128) k_msm_ba_level(SRC src, const uint32_t* __restrict__ off_in,
                                                       const uint32_t* __restrict__ off_out, uint32_t nb,
-                                                      Affine<F>* __restrict__ out) {
+                                                      Affine<F>* __restrict__ out, uint32_t batch) {
   const uint32_t total = off_out[nb];
-  const uint64_t o_begin = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * MSM_BA_BATCH;
+  const uint64_t o_begin = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * batch;
   if (o_begin >= total) return;
-  const uint32_t o_end = (uint32_t)(o_begin + MSM_BA_BATCH < total ? o_begin + MSM_BA_BATCH : total);
+  const uint32_t o_end = (uint32_t)(o_begin + batch < total ? o_begin + batch : total);
   msm_ba_level_thread<F, SRC>(src, off_in, off_out, nb, (uint32_t)o_begin, o_end, out);
 }
 static __global__ void k_msm_iota(uint32_t* __restrict__ v, uint32_t n) {
@@ -446,14 +446,15 @@ cudaError_t msm_enqueue(cudaStream_t stream, const MsmPlan& pl, const Affine<F>*
       GB_CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, cnt, off_out, (int)nb + 1, stream));
       bound = bound / 2 + nb + 1;
       if (bound > ((lvl & 1) ? L.ba_cap_b : L.ba_cap_a)) bound = (lvl & 1) ? L.ba_cap_b : L.ba_cap_a;
-      const size_t threads = (bound + MSM_BA_BATCH - 1) / MSM_BA_BATCH;
+      const uint32_t batch = msm_ba_batch_for(bound);
+      const size_t threads = (bound + batch - 1) / batch;
       const unsigned grid = (unsigned)((threads + 127) / 128);
       if (lvl == 0) {
         BaSrcTable<F> src{d_table, vals1};
-        k_msm_ba_level<F, BaSrcTable<F>><<<grid, 128, 0, stream>>>(src, off_in, off_out, nb, out_pts);
+        k_msm_ba_level<F, BaSrcTable<F>><<<grid, 128, 0, stream>>>(src, off_in, off_out, nb, out_pts, batch);
       } else {
         BaSrcPoints<F> src{bufs[(lvl - 1) & 1]};
-        k_msm_ba_level<F, BaSrcPoints<F>><<<grid, 128, 0, stream>>>(src, off_in, off_out, nb, out_pts);
+        k_msm_ba_level<F, BaSrcPoints<F>><<<grid, 128, 0, stream>>>(src, off_in, off_out, nb, out_pts, batch);
       }
       off_in = off_out;
     }
