@@ -363,7 +363,9 @@ def run_b200(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * 32 * world, "d2h_bytes_per_step": 96 * world,
                 "ms_per_step": 1e3 * e2e_s / args.steps,
                 "note": "b200_msm_g1 with pinned host scalars; bases resident (PinToGPU)"},
-        "gpu_launches": 8 * args.steps,
+        # own kernels per MSM: decompose, bucket_offsets, task_counts, accumulate, combine, combine_heavy,
+        # reduce_chunks, set_sum, finish (the radix sort and the scan are CUB launches on top of these)
+        "gpu_launches": 9 * args.steps,
         "roofline": {"bound": "hbm", "kernel": "k_msm_accumulate", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": acc_ms,
