@@ -109,11 +109,13 @@ int msm_emu(const void* points_, const void* scalars_, uint32_t n, int c, int pr
   return 0;
 }
 
+int g_ntt_tile_log = NTT_MAX_TILE_LOG;
 template <class Fr>
 int ntt_emu(void* data_, unsigned logn, int inverse, int decimation, int on_coset, const void* gen_mont,
             const void* coset_mont) {
   Fr* data = reinterpret_cast<Fr*>(data_);
   NttDomainHost<Fr> dom;
+  dom.tile_log = g_ntt_tile_log;
   dom.init(logn, gen_mont ? reinterpret_cast<const Fr*>(gen_mont) : nullptr,
            coset_mont ? reinterpret_cast<const Fr*>(coset_mont) : nullptr);
   dom.transform(data, inverse != 0, decimation, on_coset != 0);
@@ -543,6 +545,9 @@ int emu_msm(int curve, int group, const void* points, const void* scalars, uint3
   }
   return -1;
 }
+
+// plan tile size used by emu_ntt (GB200_NTT_TILE_LOG on the device)
+int emu_ntt_set_tile_log(int t) { if (t < 2 || t > NTT_MAX_TILE_LOG) return -1; g_ntt_tile_log = t; return 0; }
 
 int emu_ntt(int curve, void* data, unsigned logn, int inverse, int decimation, int on_coset, const void* gen_mont,
             const void* coset_mont) {

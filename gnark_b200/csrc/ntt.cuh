@@ -158,8 +158,9 @@ struct NttDomainHost {
   }
 
   // sequential walk of the kernel structure (emulation)
+  int tile_log = NTT_MAX_TILE_LOG;   // emulation tests lower it to walk multi-pass plans at small sizes
   void transform(Fr* data, bool inverse, int decimation, bool on_coset) const {
-    NttPlan plan = ntt_make_plan(logn);
+    NttPlan plan = ntt_make_plan(logn, tile_log);
     const std::vector<Fr>& T = inverse ? itw : tw;
     // pre-scale (forward coset)
     if (!inverse && on_coset) {

@@ -5,6 +5,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "msm_impl.cuh"  // GB_CUDA_TRY, gb_align
 #include "ntt.cuh"
 
@@ -109,7 +111,11 @@ struct NttDomainDev {
   cudaError_t init(cudaStream_t st, int logn_, const Fr* gen_mont, const Fr* coset_mont) {
     logn = logn_;
     n = 1u << logn;
-    plan = ntt_make_plan(logn);
+    // GB200_NTT_TILE_LOG (opt-in, 6..11): smaller tiles = smaller blocks, so that two blocks share an SM and one
+    // block's loads / barriers overlap the other's butterflies (default 11: one 1024-thread block per SM)
+    int tile_log = NTT_MAX_TILE_LOG;
+    if (const char* e = getenv("GB200_NTT_TILE_LOG")) { const int v = atoi(e); if (v >= 6 && v <= NTT_MAX_TILE_LOG) tile_log = v; }
+    plan = ntt_make_plan(logn, tile_log);
     gen = gen_mont ? *gen_mont : NttDomainHost<Fr>::default_generator(logn);
     coset = coset_mont ? *coset_mont : NttDomainHost<Fr>::default_coset();
     gen_inv = gen.inverse();

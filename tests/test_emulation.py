@@ -224,6 +224,26 @@ def test_ntt_logic(hostemu, c):
                     assert ff.unpack_elements(A, c.r, c.fr_limbs) == exp, (c.name, logn, inv, dec, cos)
 
 
+@pytest.mark.parametrize("c", [CURVES["bn254"], CURVES["bw6-761"]], ids=lambda c: c.name)
+def test_ntt_smaller_tiles(hostemu, c):
+    """GB200_NTT_TILE_LOG: the same pass / tile / stage walk with smaller tiles (more passes, other cb splits)"""
+    rng = random.Random(14)
+    try:
+        for tile_log, logn in ((10, 12), (10, 13), (6, 9), (4, 10), (7, 7)):
+            assert hostemu.emu_ntt_set_tile_log(tile_log) == 0
+            n = 1 << logn
+            dom = ntt.Domain(c, n)
+            a = [rng.randrange(c.r) for _ in range(n)]
+            A0 = ff.pack_elements(a, c.r, c.fr_limbs)
+            for inv, dec, cos in ((0, 0, 0), (1, 0, 1), (0, 1, 1), (1, 1, 0)):
+                A = A0.copy()
+                assert hostemu.emu_ntt(c.curve_id, P(A), logn, inv, dec, cos, None, None) == 0
+                exp = (dom.fft_inverse if inv else dom.fft)(a, dec, on_coset=bool(cos))
+                assert ff.unpack_elements(A, c.r, c.fr_limbs) == exp, (c.name, tile_log, logn, inv, dec, cos)
+    finally:
+        hostemu.emu_ntt_set_tile_log(11)
+
+
 # ---- FP64-pipe path (field52.cuh / curve52.cuh): 52-bit limbs, DFMA round-toward-zero products ----
 def _limbs52(v, L):
     return np.array([(v >> (52 * i)) & ((1 << 52) - 1) for i in range(L)], dtype=np.uint64)

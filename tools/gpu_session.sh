@@ -37,6 +37,11 @@ if [ -f gnark_b200/lib/libgnark_b200_opt.so ]; then
 fi
 cat $OUT/sweep_*.jsonl | cut -c1-400 | tee -a $OUT/session.log
 
+echo "== 3b. NTT tile sizes" | tee -a $OUT/session.log
+timeout 600 python tools/sweep_ntt.py --curve bn254 --logs 20,22,24 > $OUT/sweep_ntt.jsonl 2>> $OUT/session.err
+timeout 600 python tools/sweep_ntt.py --curve bls12-381 --logs 22 >> $OUT/sweep_ntt.jsonl 2>> $OUT/session.err
+cat $OUT/sweep_ntt.jsonl | tee -a $OUT/session.log
+
 echo "== 4. ncu: launch list of one Groth16-sized step and full captures of the NTT pass and the G2 accumulate" | tee -a $OUT/session.log
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_g2.csv \
     python tools/run_msm.py bn254 2 20 1 > $OUT/ncu_g2.log 2>&1
