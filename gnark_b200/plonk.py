@@ -113,10 +113,18 @@ class _Fr:
 class ProvingKey:
     """Device-resident PLONK proving key (backend/plonk/bn254/setup.go:88-93 ProvingKey + Trace :67-86)."""
 
-    def __init__(self, curve: int, log2n: int, dev: int = 0):
+    def __init__(self, curve: int, log2n: int, dev: int = 0, shard=None):
+        """shard = (rank, world, process_group): one process per GPU.  Polynomials and the O(n) stages are
+        replicated; the two things that dominate a proof are split: every KZG commitment is a
+        point-range-sharded MSM (this rank holds SRS points [off, off+cnt), partial digests all-gathered and
+        summed on the host, as parallel.sharded_msm), and coset i of the quotient numerator is evaluated by rank
+        i mod world, the disjoint quarter results merged with one all-reduce."""
         import torch
         self.torch = torch
         self.curve, self.log2n, self.dev = curve, log2n, dev
+        self.rank, self.world, self.pg = (0, 1, None) if shard is None else shard
+        if not (0 <= self.rank < self.world):
+            raise ValueError(f"invalid shard {self.rank}/{self.world}")
         self.n = 1 << log2n
         self.fr = _Fr(curve)
         s, root, g = _FR_DOMAIN[curve]
@@ -157,9 +165,10 @@ class ProvingKey:
         return _Ctx()
 
     @classmethod
-    def from_trace(cls, curve, log2n, ql, qr, qm, qo, qk, perm, srs_canonical, dev=0):
-        """ql..qk: (n, limbs) uint64 Lagrange/regular (Montgomery); perm: int64[3n]; srs_canonical: (n+3) G1Affine."""
-        pk = cls(curve, log2n, dev)
+    def from_trace(cls, curve, log2n, ql, qr, qm, qo, qk, perm, srs_canonical, dev=0, shard=None):
+        """ql..qk: (n, limbs) uint64 Lagrange/regular (Montgomery); perm: int64[3n]; srs_canonical: (n+3) G1Affine
+        (the FULL SRS on every rank; a sharded key uploads only its own point range)."""
+        pk = cls(curve, log2n, dev, shard=shard)
         with pk.on_stream():
             pk._load(ql, qr, qm, qo, qk, perm, srs_canonical)
         return pk
@@ -185,7 +194,11 @@ class ProvingKey:
             c = d.clone()
             _lib.vec_bit_reverse(dev, curve, c, log2n)
             pk.canon[name] = c
-        pk.srs = _lib.Table(curve, 1, srs_canonical, dev=dev, precomp=True)
+        from .parallel import shard_range
+        srs = np.ascontiguousarray(srs_canonical).reshape(n + 3, -1)
+        pk.srs_off, pk.srs_cnt = shard_range(n + 3, pk.world, pk.rank)
+        pk.srs = _lib.Table(curve, 1, np.ascontiguousarray(srs[pk.srs_off:pk.srs_off + pk.srs_cnt]), dev=dev, precomp=True,
+                            n=pk.srs_cnt)
         _lib.sync(dev)
 
     def free(self):
@@ -221,7 +234,22 @@ def _prove(pk: ProvingKey, l, r, o, ch: Challenges) -> Proof:
         t_start = now
 
     def commit(d_coeffs, count):
-        return pk.srs.msm(d_coeffs, n=count, on_device=True)
+        """[sum_i c_i tau^i]: this rank's point range of the first `count` coefficients, then (sharded key) one
+        all_gather of the partial digests and host-side group additions"""
+        lo = min(pk.srs_off, count)
+        hi = min(pk.srs_off + pk.srs_cnt, count)
+        flat = d_coeffs.reshape(-1)
+        part = pk.srs.msm(flat[lo * L:hi * L], n=hi - lo, on_device=True)
+        if pk.world == 1:
+            return part
+        import torch.distributed as dist
+        mine = t.from_numpy(part.view(np.int64).copy()).to(flat.device)
+        parts = [t.empty_like(mine) for _ in range(pk.world)]
+        dist.all_gather(parts, mine, group=pk.pg)
+        acc = parts[0].cpu().numpy().view(np.uint64).copy()
+        for p_ in parts[1:]:
+            _lib.point_add_jac(curve, 1, acc, p_.cpu().numpy().view(np.uint64))
+        return acc
 
     def canonical_blinded(d_lagrange, b):
         """Lagrange/regular -> (canonical bit-reversed copy for the coset NTTs, blinded canonical regular [n+len(b)])"""
@@ -259,6 +287,8 @@ def _prove(pk: ProvingKey, l, r, o, ch: Challenges) -> Proof:
     g_m, w4_m = E(pk.g), E(pk.w4)
     a_m, b_m, c_m = E(ch.alpha), E(ch.beta), E(ch.gamma)
     for i in range(4):
+        if i % pk.world != pk.rank:          # this coset belongs to another rank
+            continue
         on_coset = {}
         for name in names:
             src = cb[name] if name in cb else pk.polys[name]
@@ -268,6 +298,10 @@ def _prove(pk: ProvingKey, l, r, o, ch: Challenges) -> Proof:
         _lib.plonk_constraints_coset(pk.dom0[i], g_m, w4_m, on_coset, a_m, b_m, c_m, blind, i, 4, cres)
         _lib.sync(dev)
         del on_coset
+    if pk.world > 1:
+        # every slot of cres was written by exactly one rank and is zero elsewhere: an integer SUM merges the quarters
+        import torch.distributed as dist
+        dist.all_reduce(cres, op=dist.ReduceOp.SUM, group=pk.pg)
     _lib.plonk_divide_by_zh(pk.dom1, logn, cres)       # -> h canonical regular (4n)
     h = cres
     H = [commit(h[k * (n + 2) * L:(k + 1) * (n + 2) * L], n + 2) for k in range(3)]

@@ -102,3 +102,60 @@ def test_sharded_ntt_gloo(b200lib, world, cname, logn):
     ret = mgr.dict()
     mp.spawn(_ntt_worker, args=(world, port, cname, logn, ret), nprocs=world, join=True)
     assert all(ret[r] for r in range(world))
+
+
+def _plonk_worker(rank, world, port, logn, ret):
+    """sharded PLONK prover (gnark_b200/plonk.py with shard=(rank, world, pg)) over gloo: point-range-sharded KZG
+    commitments (all_gather + host adds) and coset-parallel quotient (all_reduce of disjoint quarters) are the
+    product code; every single-GPU C-ABI call is replaced by its oracle twin (no GPU here)."""
+    import contextlib
+    import types
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from gnark_b200 import lib as real_lib, plonk as b200_plonk
+    from oracle import corelib, ec, ff, plonk_prover as pp
+    from oracle.params import CURVES
+    from test_plonk_orchestration import make_mock_lib
+    from util import jac_to_affine
+    c = CURVES["bn254"]
+    mock = make_mock_lib(real_lib, [])
+    mock.point_add_jac = real_lib.point_add_jac            # host-side group addition: the real (CPU) entry point
+    b200_plonk._lib = mock
+    b200_plonk._device = lambda dev: "cpu"
+    b200_plonk._new_stream = lambda torch_, dev: types.SimpleNamespace(cuda_stream=1, synchronize=lambda: None)
+    b200_plonk._stream_ctx = lambda torch_, s: contextlib.nullcontext()
+    rng = random.Random(777)                               # same instance on every rank
+    r, L = c.r, c.fr_limbs
+    n = 1 << logn
+    circ, l, rr, o = pp.random_satisfied_instance(c, n, seed=logn + 3)
+    rnd = lambda: rng.randrange(r)
+    ch = pp.Challenges(gamma=rnd(), beta=rnd(), alpha=rnd(), zeta=rnd(), v=rnd(), bl=[rnd(), rnd()], br=[rnd(), rnd()],
+                       bo=[rnd(), rnd()], bz=[rnd(), rnd(), rnd()])
+    tau = rnd()
+    want = pp.prove(c, circ, l, rr, o, ch, tau)
+    pe = lambda v: ff.pack_elements(v, r, L)
+    srs = corelib.fixed_base(c, 1, ec.pack_points(c, 1, [c.g1]), pe([pow(tau, i, r) for i in range(n + 3)]))
+    pk = b200_plonk.ProvingKey.from_trace(c.curve_id, logn, pe(circ.ql), pe(circ.qr), pe(circ.qm), pe(circ.qo),
+                                         pe(circ.qk), np.array(circ.perm, dtype=np.int64), srs, shard=(rank, world, None))
+    got = b200_plonk.Prove(pk, pe(l), pe(rr), pe(o),
+                           b200_plonk.Challenges(gamma=ch.gamma, beta=ch.beta, alpha=ch.alpha, zeta=ch.zeta, v=ch.v,
+                                                 bl=ch.bl, br=ch.br, bo=ch.bo, bz=ch.bz))
+    F = ff.Fp(c.p)
+    ok = True
+    for g_, w_ in ((got.LRO[0], want.L), (got.LRO[1], want.R), (got.LRO[2], want.O), (got.Z, want.Z),
+                   (got.H[0], want.H[0]), (got.H[1], want.H[1]), (got.H[2], want.H[2]), (got.LinearizedDigest, want.lin),
+                   (got.BatchedProofH, want.batch_opening), (got.ZShiftedOpeningH, want.z_opening)):
+        ok &= jac_to_affine(c, 1, g_) == ec.scalar_mul(F, w_, c.g1)
+    ok &= got.BatchedClaimedValues == want.claimed and got.ZShiftedClaimedValue == want.zu
+    ret[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,logn", [(2, 4), (3, 3)])
+def test_sharded_plonk_gloo(b200lib, world, logn):
+    port = 33500 + random.randrange(2000)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_plonk_worker, args=(world, port, logn, ret), nprocs=world, join=True)
+    assert all(ret[r] for r in range(world))

@@ -62,6 +62,9 @@ if [ "$NG" -gt 1 ]; then
   timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29611 \
       tools/bench_sharded_ntt.py --log2n 24 > $OUT/sharded_ntt_n$NG.json 2>> $OUT/session.err
   cat $OUT/sharded_ntt_n$NG.json | tee -a $OUT/session.log
+  timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29613 \
+      tools/bench_plonk_multi.py --log2n 22 > $OUT/plonk_n$NG.json 2>> $OUT/session.err
+  cut -c1-800 $OUT/plonk_n$NG.json | tee -a $OUT/session.log
   timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29612 \
       bench.py --gpus $NG --steps 20 --warmup 3 > $OUT/bench_n$NG.json 2>> $OUT/session.err
   tail -c 1500 $OUT/bench_n$NG.json | tee -a $OUT/session.log
