@@ -178,17 +178,23 @@ class ProvingKey:
         t = pk.torch
         n, L, q = pk.n, pk.fr.limbs, pk.fr.q
         pk.perm = t.from_numpy(np.ascontiguousarray(perm, dtype=np.int64)).to(_device(dev))
-        # sigma polynomials from the permutation: s_j[i] = supp[perm[j n + i]] (setup.go:289-392)
-        w_pows = [1] * n
-        for i in range(1, n):
-            w_pows[i] = w_pows[i - 1] * pk.w % q
-        supp = w_pows + [pk.g * x % q for x in w_pows] + [pk.g * pk.g * x % q for x in w_pows]
-        perm_l = [int(x) for x in perm]
+        # sigma polynomials from the permutation: s_j[i] = supp[perm[j n + i]], supp = <w> || g<w> || g^2<w>
+        # (setup.go:289-392, getSupportPermutation :377-392) - built on the device: powers of w by
+        # b200_vec_scale_powers on a vector of ones, the two cosets by a constant scaling, then one gather
+        one = pk.fr.enc(1)
+        d_w = pk._dev(np.tile(one, (n, 1))).reshape(-1)
+        _lib.vec_scale_powers(dev, curve, d_w, n, one, pk.fr.enc(pk.w))
+        supp = t.empty((3 * n, L), dtype=t.int64, device=d_w.device)
+        supp[:n] = d_w.view(n, L)
+        for j in (1, 2):
+            blk = d_w.clone()
+            _lib.vec_scale_powers(dev, curve, blk, n, pk.fr.enc(pow(pk.g, j, q)), one)
+            supp[j * n:(j + 1) * n] = blk.view(n, L)
         lag = {"ql": ql, "qr": qr, "qm": qm, "qo": qo, "qk": qk}
-        for j, name in enumerate(("s1", "s2", "s3")):
-            lag[name] = pk.fr.enc_many([supp[perm_l[j * n + i]] for i in range(n)]).reshape(n, L)
-        for name, v in lag.items():
-            d = pk._dev(v)
+        sigma = {name: supp[pk.perm[j * n:(j + 1) * n]].contiguous() for j, name in enumerate(("s1", "s2", "s3"))}
+        del supp, d_w
+        for name in ("ql", "qr", "qm", "qo", "qk", "s1", "s2", "s3"):
+            d = pk._dev(lag[name]) if name in lag else sigma[name]
             pk.dom0[0].ntt_async(d, inverse=True, decimation=_lib.DIF)       # Lagrange/regular -> canonical/bit-reversed
             pk.polys[name] = d
             c = d.clone()
