@@ -660,6 +660,17 @@ int32_t b200_plonk_constraints_coset(b200_domain_t d0, const void* big_coset_gen
   return 0;
   GUARD_END
 }
+int32_t b200_plonk_bsb22_coset(b200_domain_t d0, const void* d_qcp, const void* d_pi2, uint32_t coset_index, uint32_t rho,
+                               void* d_out) {
+  GUARD_BEGIN
+  if (!d0 || !d_qcp || !d_pi2 || !d_out) return set_error("plonk_bsb22_coset: null argument");
+  DeviceCtx* ctx; int32_t rc = device_ctx(d0->dev, &ctx); if (rc) return rc;
+  cudaError_t e = d0->ops->plonk_bsb22(ctx->stream, d0->impl, d_qcp, d_pi2, coset_index, rho, d_out);
+  if (e == cudaErrorInvalidValue) return set_error("plonk_bsb22_coset: invalid rho / coset index");
+  if (e != cudaSuccess) return cuda_fail("plonk_bsb22_coset", e);
+  return 0;
+  GUARD_END
+}
 int32_t b200_plonk_divide_by_zh(b200_domain_t d1, uint32_t log_n0, void* d_data) {
   GUARD_BEGIN
   if (!d1 || !d_data) return set_error("plonk_divide_by_zh: null argument");

@@ -363,6 +363,16 @@ int fixed_base_emu(const void* base_, const void* scalars_, uint32_t n, int c, v
 }
 
 
+// k_plonk_add_bsb22 walked over the n points of one coset (BN254 / BLS12-381 / BW6 Fr by curve id)
+template <class Fr>
+int bsb22_emu(const void* qcp, const void* pi2, void* out, uint32_t logn, uint32_t coset_index, uint32_t rho) {
+  uint32_t log_rho = 0;
+  while ((1u << log_rho) < rho) log_rho++;
+  for (uint32_t j = 0; j < (1u << logn); j++)
+    plonk_add_bsb22_point<Fr>((const Fr*)qcp, (const Fr*)pi2, (Fr*)out, j, coset_index, rho, logn, log_rho);
+  return 0;
+}
+
 extern "C" {
 
 // polys: 12 pointers (l r o z s1 s2 s3 ql qr qm qo qk), each n fr.Elements ON the coset; abg: alpha, beta, gamma
@@ -542,6 +552,16 @@ int emu_msm(int curve, int group, const void* points, const void* scalars, uint3
     case 5: return msm_emu<bls12_377_fr, bls12_377_fp2>(points, scalars, n, c, precomp, task_len, chunk, out_jac);
     case 6:
     case 7: return msm_emu<bw6_761_fr, bw6_761_fp>(points, scalars, n, c, precomp, task_len, chunk, out_jac);
+  }
+  return -1;
+}
+
+int emu_plonk_bsb22(int curve, const void* qcp, const void* pi2, void* out, uint32_t logn, uint32_t coset_index, uint32_t rho) {
+  switch (curve) {
+    case 0: return bsb22_emu<bn254_fr>(qcp, pi2, out, logn, coset_index, rho);
+    case 1: return bsb22_emu<bls12_381_fr>(qcp, pi2, out, logn, coset_index, rho);
+    case 2: return bsb22_emu<bls12_377_fr>(qcp, pi2, out, logn, coset_index, rho);
+    case 3: return bsb22_emu<bw6_761_fr>(qcp, pi2, out, logn, coset_index, rho);
   }
   return -1;
 }

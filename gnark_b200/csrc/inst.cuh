@@ -202,6 +202,16 @@ struct NttInst {
     GB_CUDA_TRY(cudaGetLastError());
     return cudaFreeAsync(den, st);
   }
+  static cudaError_t plonk_bsb22(cudaStream_t st, void* dom0, const void* qcp, const void* pi2, uint32_t coset_index,
+                                 uint32_t rho, void* out) {
+    const Dom& d = *reinterpret_cast<Dom*>(dom0);
+    uint32_t log_rho = 0;
+    while ((1u << log_rho) < rho) log_rho++;
+    if ((1u << log_rho) != rho || coset_index >= rho) return cudaErrorInvalidValue;
+    k_plonk_add_bsb22<Fr><<<(d.n + 255) / 256, 256, 0, st>>>((const Fr*)qcp, (const Fr*)pi2, (Fr*)out, d.n, coset_index, rho,
+                                                           (uint32_t)d.logn, log_rho);
+    return cudaGetLastError();
+  }
   static cudaError_t plonk_divide_by_zh(cudaStream_t st, void* dom1, uint32_t log_n0, void* data) {
     const Dom& d = *reinterpret_cast<Dom*>(dom1);
     if ((int)log_n0 > d.logn || d.logn - (int)log_n0 > 6) return cudaErrorInvalidValue;
@@ -315,7 +325,7 @@ struct NttInst {
     static const NttOps o = {sizeof(Fr), Fr::Params::TWO_ADICITY, &domain_new, &domain_free, &domain_bytes, &ntt,
                              &compute_h, &vec_op, &bit_reverse, &scale_powers, &batch_invert, &plonk_coset,
                              &plonk_divide_by_zh, &axpy, &scan, &plonk_build_z, &poly_eval, &poly_div_linear, &gather,
-                             &host_fr};
+                             &host_fr, &plonk_bsb22};
     return &o;
   }
 };

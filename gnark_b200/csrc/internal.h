@@ -72,6 +72,9 @@ struct NttOps {
   cudaError_t (*gather)(cudaStream_t st, void* d_out, const void* d_src, const uint32_t* d_idx, size_t n);
   // host-side Fr constants and arithmetic (host_fr.h) for the scalar work between device stages
   const HostFrCtx* (*host_fr)();
+  // BSB22 commitment gate: out[scatter(j)] += qcp[j] * pi2[j] on one coset (plonk.cuh)
+  cudaError_t (*plonk_bsb22)(cudaStream_t st, void* dom0, const void* d_qcp, const void* d_pi2, uint32_t coset_index,
+                             uint32_t rho, void* d_out);
 };
 
 // Host-side group arithmetic for proof assembly (backend/groth16/bn254/prove.go:

@@ -68,7 +68,28 @@ HD Fr plonk_all_constraints(const PlonkCosetArgs<Fr>& a, uint32_t j, const Fr& w
   return (local * a.alpha + ordering) * a.alpha + gate;   // :985
 }
 
+// BSB22 commitment gate (gateConstraint :881-884): the term Qcp_i * PI2_i of one commitment at point j of one coset,
+// added to the slot the fused kernel wrote (the gate enters allConstraints with coefficient 1, so the sum can be
+// completed afterwards, one call per commitment and coset)
+HD uint32_t plonk_scatter_index(uint32_t j, uint32_t coset_index, uint32_t rho, uint32_t logn, uint32_t log_rho) {
+  return ntt_bitrev(rho * j + coset_index, (int)(logn + log_rho));
+}
+template <class Fr>
+HD void plonk_add_bsb22_point(const Fr* qcp, const Fr* pi2, Fr* out, uint32_t j, uint32_t coset_index, uint32_t rho,
+                              uint32_t logn, uint32_t log_rho) {
+  const uint32_t k = plonk_scatter_index(j, coset_index, rho, logn, log_rho);
+  out[k] = out[k] + qcp[j] * pi2[j];
+}
+
 #ifdef __CUDACC__
+template <class Fr>
+__global__ void __launch_bounds__(256) k_plonk_add_bsb22(const Fr* __restrict__ qcp, const Fr* __restrict__ pi2,
+                                                         Fr* __restrict__ out, uint32_t n, uint32_t coset_index,
+                                                         uint32_t rho, uint32_t logn, uint32_t log_rho) {
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n) plonk_add_bsb22_point<Fr>(qcp, pi2, out, j, coset_index, rho, logn, log_rho);
+}
+
 template <class Fr>
 __global__ void __launch_bounds__(256) k_plonk_constraints(PlonkCosetArgs<Fr> a) {
   const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;

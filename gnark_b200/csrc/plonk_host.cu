@@ -9,8 +9,9 @@
 //
 // Every polynomial stays in HBM between the MSM / NTT stages; only blinding patches (<= 3 elements), opened
 // values and digests cross to the host.  Challenges and blinding coefficients are INPUTS (the Fiat-Shamir
-// transcript encoding is gnark-crypto's; a Go shim derives them exactly as prove.go:492-555 does).  BSB22
-// commitments and StatisticalZK are not supported.  Host-side scalar work uses host_fr.h.
+// transcript encoding is gnark-crypto's; a Go shim derives them exactly as prove.go:492-555 does).  BSB22 commitment
+// gates (:867-884) are supported with the committed polynomials PI2_i supplied by the caller (the reference's solver
+// hint :280-318 produces them); StatisticalZK is not.  Host-side scalar work uses host_fr.h.
 #include <memory>
 #include <vector>
 
@@ -32,6 +33,8 @@ struct b200_plonk_pk_s {
   void* canon[8] = {nullptr};         // canonical coefficients, regular layout
   int64_t* d_perm = nullptr;
   b200_table_t srs = nullptr;         // canonical SRS, n + 3 points
+  // BSB22 commitment gates: selectors Qcp_j (trace.Qcp), canonical bit-reversed / regular like the other key polys
+  std::vector<void*> qcp_br, qcp_canon;
 };
 
 namespace gb200_plonk {
@@ -69,6 +72,7 @@ struct b200_plonk_session_s {
   void *d_l = nullptr, *d_r = nullptr, *d_o = nullptr;
   void* cb[4] = {nullptr};        // l, r, o, z: canonical, bit-reversed (n)
   void* bl[4] = {nullptr};        // blinded canonical regular (n + 2, n + 2, n + 2, n + 3)
+  std::vector<void*> pi2_br, pi2_canon;   // BSB22 committed polynomials, canonical (bit-reversed / regular)
   void* h = nullptr;              // quotient, canonical regular (4n)
   void* lin = nullptr;            // linearised polynomial (n + 3)
   uint8_t blind[4][3 * 8 * HOSTFR_MAX_LIMBS];   // bl, br, bo (2 each), bz (3)
@@ -137,6 +141,8 @@ int32_t b200_plonk_pk_free(b200_plonk_pk_t pk) {
   if (pk->dom1) b200_ntt_domain_free(pk->dom1);
   for (int k = 0; k < 8; k++) { if (pk->br[k]) b200_free(pk->dev, pk->br[k]); if (pk->canon[k]) b200_free(pk->dev, pk->canon[k]); }
   if (pk->d_perm) b200_free(pk->dev, pk->d_perm);
+  for (void* q : pk->qcp_br) if (q) b200_free(pk->dev, q);
+  for (void* q : pk->qcp_canon) if (q) b200_free(pk->dev, q);
   if (pk->srs) b200_table_free(pk->srs);
   delete pk;
   return 0;
@@ -202,6 +208,17 @@ int32_t b200_plonk_pk_load(int32_t dev, int32_t curve, const b200_plonk_pk_desc*
     RC(d2d(dev, pk->canon[k], pk->br[k], n * fb));
     RC(b200_vec_bit_reverse(dev, curve, pk->canon[k], d->log2n));
   }
+  if (d->n_qcp > 16 || (d->n_qcp && !d->qcp)) return set_error("plonk_pk_load: invalid BSB22 selector list");
+  for (uint32_t j = 0; j < d->n_qcp; j++) {
+    if (!d->qcp[j]) return set_error("plonk_pk_load: null BSB22 selector");
+    void *b = nullptr, *c = nullptr;
+    RC(b200_alloc(dev, n * fb, &b)); pk->qcp_br.push_back(b);
+    RC(b200_alloc(dev, n * fb, &c)); pk->qcp_canon.push_back(c);
+    RC(b200_h2d(dev, b, d->qcp[j], n * fb));
+    RC(b200_ntt_async(pk->dom0[0], b, 1, B200_DIF, 0));
+    RC(d2d(dev, c, b, n * fb));
+    RC(b200_vec_bit_reverse(dev, curve, c, d->log2n));
+  }
   RC(b200_table_upload(dev, curve, 1, d->srs_canonical, n + 3, B200_TABLE_PRECOMP, &pk->srs));
   RC(b200_sync(dev));
   *out = pk.release();
@@ -221,9 +238,12 @@ int32_t b200_plonk_end(b200_plonk_session_t s) {
 }
 
 int32_t b200_plonk_begin(b200_plonk_pk_t pk, const void* l, const void* r, const void* o, const void* bl,
-                         const void* br, const void* bo, b200_plonk_session_t* out, void* out_lro) {
+                         const void* br, const void* bo, const void* const* pi2, void* out_bsb22,
+                         b200_plonk_session_t* out, void* out_lro) {
   GUARD_BEGIN
   if (!pk || !l || !r || !o || !bl || !br || !bo || !out || !out_lro) return set_error("plonk_begin: null argument");
+  if (!pk->qcp_br.empty() && (!pi2 || !out_bsb22))
+    return set_error("plonk_begin: the key has BSB22 commitment gates - one committed polynomial per gate is required");
   const int dev = pk->dev;
   const size_t n = pk->n, fb = pk->fb;
   std::unique_ptr<b200_plonk_session_s> s(new b200_plonk_session_s(pk));
@@ -237,6 +257,19 @@ int32_t b200_plonk_begin(b200_plonk_pk_t pk, const void* l, const void* r, const
   const void* lag[3] = {s->d_l, s->d_r, s->d_o};
   for (int k = 0; k < 3; k++) RC(canonical_blinded(pk, lag[k], s->blind[k], 2, s->cb[k], s->bl[k]));
   for (int k = 0; k < 3; k++) RC(commit(pk, s->bl[k], n + 2, (uint8_t*)out_lro + (size_t)k * s->jb));
+  // BSB22: committed polynomials -> canonical, and their digests (Bsb22Commitments :300; canonical SRS here, the
+  // same group element as the reference's Lagrange-SRS commitment)
+  for (size_t j = 0; j < pk->qcp_br.size(); j++) {
+    if (!pi2[j]) return set_error("plonk_begin: null committed polynomial");
+    void *b = nullptr, *c = nullptr;
+    RC(s->S.alloc(n * fb, &b)); RC(s->S.alloc(n * fb, &c));
+    s->pi2_br.push_back(b); s->pi2_canon.push_back(c);
+    RC(b200_h2d(dev, b, pi2[j], n * fb));
+    RC(b200_ntt_async(pk->dom0[0], b, 1, B200_DIF, 0));
+    RC(d2d(dev, c, b, n * fb));
+    RC(b200_vec_bit_reverse(dev, pk->curve, c, pk->logn));
+    RC(commit(pk, c, n, (uint8_t*)out_bsb22 + j * s->jb));
+  }
   s->stage = 1;
   *out = s.release();
   return 0;
@@ -295,6 +328,13 @@ int32_t b200_plonk_quotient(b200_plonk_session_t s, const void* alpha, void* out
     a.nbl = 2; a.nbr = 2; a.nbo = 2; a.nbz = 3;
     a.coset_index = i; a.rho = 4; a.out = s->h;
     RC(b200_plonk_constraints_coset(pk->dom0[i], gb, w4b, &a));
+    for (size_t j = 0; j < pk->qcp_br.size(); j++) {   // + Qcp_j * PI2_j on this coset (gateConstraint :881-884)
+      RC(d2d(dev, onc[0], pk->qcp_br[j], n * fb));
+      RC(d2d(dev, onc[1], s->pi2_br[j], n * fb));
+      RC(b200_ntt_async(pk->dom0[i], onc[0], 0, B200_DIT, 1));
+      RC(b200_ntt_async(pk->dom0[i], onc[1], 0, B200_DIT, 1));
+      RC(b200_plonk_bsb22_coset(pk->dom0[i], onc[0], onc[1], i, 4, s->h));
+    }
   }
   RC(b200_plonk_divide_by_zh(pk->dom1, pk->logn, s->h));      // -> h canonical regular (4n)
   for (int k = 0; k < 3; k++)
@@ -354,6 +394,13 @@ int32_t b200_plonk_linearise(b200_plonk_session_t s, const void* zeta_, void* ou
   RC(axpy(pk, lin, rz, pk->canon[QR], n));
   RC(axpy(pk, lin, oz, pk->canon[QO], n));
   RC(axpy(pk, lin, fr->one_(), pk->canon[QK], n));
+  // + sum_j Qcp_j(zeta) PI2_j(X)   (:1457-1460); Qcp_j(zeta) are claimed values 6.. of the batch opening
+  for (size_t j = 0; j < pk->qcp_canon.size(); j++) {
+    HostFr qz;
+    RC(eval_at(pk, pk->qcp_canon[j], n, zeta, &qz));
+    fr->store(vals + (7 + j) * fb, qz);
+    RC(axpy(pk, lin, qz, s->pi2_canon[j], n));
+  }
   HostFr hc = zh;     // zh, zh zn2, zh zn2^2
   for (int k = 0; k < 3; k++) {
     RC(axpy(pk, lin, fr->neg(hc), h + (size_t)k * (n + 2) * fb, n + 2));
@@ -406,6 +453,10 @@ int32_t b200_plonk_batch_open(b200_plonk_session_t s, const void* v_, void* out_
     RC(axpy(pk, fold, vp, open_p[k], open_n[k]));
     vp = fr->mul(vp, v);
   }
+  for (size_t j = 0; j < pk->qcp_canon.size(); j++) {     // polysToOpen[6:] = Qcp (:805-807)
+    RC(axpy(pk, fold, vp, pk->qcp_canon[j], n));
+    vp = fr->mul(vp, v);
+  }
   uint8_t rem[8 * HOSTFR_MAX_LIMBS];
   RC(b200_poly_div_by_linear(dev, curve, fold, n + 3, s->zeta, rem));
   RC(commit(pk, fold, n + 2, out_point));
@@ -425,7 +476,9 @@ int32_t b200_plonk_prove(b200_plonk_pk_t pk, const void* l, const void* r, const
   const size_t jb = get_msm_ops(pk->curve, 1)->jac_bytes;
   uint8_t* pts = (uint8_t*)out_points;          // L, R, O, Z, H1, H2, H3, linearised, batch opening, Z opening
   b200_plonk_session_t s = nullptr;
-  int32_t rc = b200_plonk_begin(pk, l, r, o, ch->bl, ch->br, ch->bo, &s, pts);
+  if (!pk->qcp_br.empty() && (!ch->pi2 || !ch->out_bsb22))
+    return set_error("plonk_prove: the key has BSB22 commitment gates - challenges.pi2 / out_bsb22 are required");
+  int32_t rc = b200_plonk_begin(pk, l, r, o, ch->bl, ch->br, ch->bo, ch->pi2, ch->out_bsb22, &s, pts);
   if (!rc) rc = b200_plonk_commit_z(s, ch->beta, ch->gamma, ch->bz, pts + 3 * jb);
   if (!rc) rc = b200_plonk_quotient(s, ch->alpha, pts + 4 * jb);
   uint8_t two[2 * 288];     // linearised digest, Z opening; 288 B = G1Jac of the largest curve (BW6-761: 3 x 96 B)

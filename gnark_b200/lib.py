@@ -34,7 +34,7 @@ EXPORTS = [
     "b200_point_add_jac", "b200_point_to_affine", "b200_groth16_pk_load", "b200_groth16_pk_free", "b200_groth16_prove", "b200_groth16_msms",
     "b200_groth16_assemble", "b200_fixed_base_batch", "b200_msm_submit",
     "b200_plonk_pk_load", "b200_plonk_pk_free", "b200_plonk_prove", "b200_plonk_begin", "b200_plonk_commit_z",
-    "b200_plonk_quotient", "b200_plonk_linearise", "b200_plonk_batch_open", "b200_plonk_end",
+    "b200_plonk_quotient", "b200_plonk_linearise", "b200_plonk_batch_open", "b200_plonk_end", "b200_plonk_bsb22_coset",
 ]
 
 
@@ -43,12 +43,14 @@ class B200Error(RuntimeError):
 
 
 class PlonkPkDesc(ctypes.Structure):
-    _fields_ = [("log2n", ctypes.c_uint32)] + [(k, ctypes.c_void_p) for k in ("ql", "qr", "qm", "qo", "qk", "perm",
-                                                                                "srs_canonical")]
+    _fields_ = ([("log2n", ctypes.c_uint32)]
+                + [(k, ctypes.c_void_p) for k in ("ql", "qr", "qm", "qo", "qk", "perm", "srs_canonical")]
+                + [("n_qcp", ctypes.c_uint32), ("qcp", ctypes.POINTER(ctypes.c_void_p))])
 
 
 class PlonkChallenges(ctypes.Structure):
-    _fields_ = [(k, ctypes.c_void_p) for k in ("gamma", "beta", "alpha", "zeta", "v", "bl", "br", "bo", "bz")]
+    _fields_ = ([(k, ctypes.c_void_p) for k in ("gamma", "beta", "alpha", "zeta", "v", "bl", "br", "bo", "bz")]
+                + [("pi2", ctypes.POINTER(ctypes.c_void_p)), ("out_bsb22", ctypes.c_void_p)])
 
 
 class Groth16PkDesc(ctypes.Structure):
@@ -123,12 +125,13 @@ def load(path: str = None):
     lib.b200_plonk_pk_load.argtypes = [i32, i32, ctypes.POINTER(PlonkPkDesc), ctypes.POINTER(vp)]
     lib.b200_plonk_pk_free.argtypes = [vp]
     lib.b200_plonk_prove.argtypes = [vp, vp, vp, vp, ctypes.POINTER(PlonkChallenges), vp, vp]
-    lib.b200_plonk_begin.argtypes = [vp, vp, vp, vp, vp, vp, vp, ctypes.POINTER(vp), vp]
+    lib.b200_plonk_begin.argtypes = [vp, vp, vp, vp, vp, vp, vp, ctypes.POINTER(vp), vp, ctypes.POINTER(vp), vp]
     lib.b200_plonk_commit_z.argtypes = [vp, vp, vp, vp, vp]
     lib.b200_plonk_quotient.argtypes = [vp, vp, vp]
     lib.b200_plonk_linearise.argtypes = [vp, vp, vp, vp]
     lib.b200_plonk_batch_open.argtypes = [vp, vp, vp]
     lib.b200_plonk_end.argtypes = [vp]
+    lib.b200_plonk_bsb22_coset.argtypes = [vp, vp, vp, u32, u32, vp]
     lib.b200_fixed_base_batch.argtypes = [i32, i32, i32, vp, vp, i32, sz, vp, i32]
     lib.b200_msm_profile.argtypes = [vp, sz, sz, vp, vp, ctypes.POINTER(ctypes.c_float)]
     lib.b200_ntt_domain_new.argtypes = [i32, i32, u32, vp, vp, ctypes.POINTER(vp)]
@@ -328,8 +331,9 @@ def fixed_base_batch(curve: int, group: int, base_affine: np.ndarray, scalars, n
 class PlonkKey:
     """device-resident PLONK proving key behind b200_plonk_pk_load / b200_plonk_prove (plonk_host.cu)"""
 
-    def __init__(self, curve: int, log2n: int, ql, qr, qm, qo, qk, perm, srs_canonical, dev: int = 0):
+    def __init__(self, curve: int, log2n: int, ql, qr, qm, qo, qk, perm, srs_canonical, dev: int = 0, qcp=()):
         self.curve, self.log2n, self.dev = curve, log2n, dev
+        self.n_qcp = len(qcp)
         frl, fpl, _ = CURVE_SHAPES[curve]
         self.fr_limbs, self.fp_limbs = frl, fpl
         keep = [np.ascontiguousarray(a, dtype=np.uint64) for a in (ql, qr, qm, qo, qk)]
@@ -340,22 +344,33 @@ class PlonkKey:
         for k, a in zip(("ql", "qr", "qm", "qo", "qk"), keep):
             setattr(d, k, ptr(a).value)
         d.perm, d.srs_canonical = ptr(perm).value, ptr(srs).value
+        qk_ = [np.ascontiguousarray(a, dtype=np.uint64) for a in qcp]
+        qarr = (ctypes.c_void_p * max(1, len(qk_)))(*[ptr(a).value for a in qk_])
+        d.n_qcp, d.qcp = len(qk_), ctypes.cast(qarr, ctypes.POINTER(ctypes.c_void_p))
         h = ctypes.c_void_p(0)
         check(load().b200_plonk_pk_load(dev, curve, ctypes.byref(d), ctypes.byref(h)))
         self.handle = h
 
-    def prove(self, l, r, o, gamma, beta, alpha, zeta, v, bl, br, bo, bz):
-        """all scalars: uint64 limb arrays (Montgomery); bl/br/bo: (2, limbs), bz: (3, limbs).
-        Returns (points (10, 3*fp_limbs) Jacobian, values (7, fr_limbs))."""
+    def prove(self, l, r, o, gamma, beta, alpha, zeta, v, bl, br, bo, bz, pi2=()):
+        """all scalars: uint64 limb arrays (Montgomery); bl/br/bo: (2, limbs), bz: (3, limbs); pi2: one committed
+        polynomial per BSB22 gate of the key.  Returns (points (10, 3*fp_limbs) Jacobian, values (7 + n_qcp,
+        fr_limbs)[, bsb22 digests (n_qcp, 3*fp_limbs)])."""
         args = [np.ascontiguousarray(a, dtype=np.uint64) for a in (l, r, o, gamma, beta, alpha, zeta, v, bl, br, bo, bz)]
         ch = PlonkChallenges()
         for k, a in zip(("gamma", "beta", "alpha", "zeta", "v", "bl", "br", "bo", "bz"), args[3:]):
             setattr(ch, k, ptr(a).value)
         pts = np.zeros((10, 3 * self.fp_limbs), dtype=np.uint64)
-        vals = np.zeros((7, self.fr_limbs), dtype=np.uint64)
+        vals = np.zeros((7 + self.n_qcp, self.fr_limbs), dtype=np.uint64)
+        pk_ = [np.ascontiguousarray(a, dtype=np.uint64) for a in pi2]
+        parr = (ctypes.c_void_p * max(1, len(pk_)))(*[ptr(a).value for a in pk_])
+        bsb = np.zeros((max(1, self.n_qcp), 3 * self.fp_limbs), dtype=np.uint64)
+        if self.n_qcp:
+            if len(pk_) != self.n_qcp:
+                raise ValueError("one committed polynomial per BSB22 gate of the key is required")
+            ch.pi2, ch.out_bsb22 = ctypes.cast(parr, ctypes.POINTER(ctypes.c_void_p)), ptr(bsb).value
         check(load().b200_plonk_prove(self.handle, ptr(args[0]), ptr(args[1]), ptr(args[2]), ctypes.byref(ch), ptr(pts),
                                       ptr(vals)))
-        return pts, vals
+        return (pts, vals, bsb[:self.n_qcp]) if self.n_qcp else (pts, vals)
 
     def free(self):
         if self.handle:
@@ -426,6 +441,11 @@ def plonk_constraints_coset(domain0: "Domain", big_coset_gen, big_gen, polys: di
             setattr(a, "nb" + k, b.size // frl)
     a.coset_index, a.rho, a.out = coset_index, rho, ptr(d_out).value
     check(load().b200_plonk_constraints_coset(domain0.handle, ptr(big_coset_gen), ptr(big_gen), ctypes.byref(a)))
+
+
+def plonk_bsb22_coset(domain0: "Domain", d_qcp, d_pi2, coset_index: int, rho: int, d_out):
+    """BSB22 commitment gate: out[slot of point j] += qcp[j] * pi2[j] on one coset"""
+    check(load().b200_plonk_bsb22_coset(domain0.handle, ptr(d_qcp), ptr(d_pi2), coset_index, rho, ptr(d_out)))
 
 
 def plonk_divide_by_zh(domain1: "Domain", domain0_log2n: int, d_data):

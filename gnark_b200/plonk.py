@@ -17,7 +17,10 @@ Stages (reference line numbers in backend/plonk/bn254/prove.go):
 
 Digests are computed from canonical coefficients against the canonical SRS: [p + b(X^n - 1)] is one MSM of
 n + deg(b) + 1 points, the same group element the reference obtains from its Lagrange-SRS MSM plus
-commitBlindingFactor (:1223-1236).  BSB22 commitments and StatisticalZK are not supported.
+commitBlindingFactor (:1223-1236).  BSB22 commitment gates (:867-884) are supported with the committed polynomials
+PI2_i given by the caller (in the reference they come out of the solver hint :280-318): their selectors Qcp_i are
+part of the key, the gate term, the linearised-polynomial term sum_i Qcp_i(zeta) PI2_i(X) (:1457) and the Qcp openings
+(:805-817) are added, and the digests [PI2_i] are returned.  StatisticalZK is not supported.
 
 Challenges and blinding coefficients are taken from the caller (`Challenges`): the Fiat-Shamir transcript
 encoding is gnark-crypto's (absent here); a Go shim derives them exactly as prove.go:492-555 does and passes
@@ -87,6 +90,7 @@ class Proof:
     BatchedClaimedValues: List[int]
     ZShiftedOpeningH: np.ndarray
     ZShiftedClaimedValue: int
+    Bsb22Commitments: List[np.ndarray] = field(default_factory=list)
     timings_ms: dict = field(default_factory=dict)
 
 
@@ -165,15 +169,15 @@ class ProvingKey:
         return _Ctx()
 
     @classmethod
-    def from_trace(cls, curve, log2n, ql, qr, qm, qo, qk, perm, srs_canonical, dev=0, shard=None):
+    def from_trace(cls, curve, log2n, ql, qr, qm, qo, qk, perm, srs_canonical, dev=0, shard=None, qcp=()):
         """ql..qk: (n, limbs) uint64 Lagrange/regular (Montgomery); perm: int64[3n]; srs_canonical: (n+3) G1Affine
         (the FULL SRS on every rank; a sharded key uploads only its own point range)."""
         pk = cls(curve, log2n, dev, shard=shard)
         with pk.on_stream():
-            pk._load(ql, qr, qm, qo, qk, perm, srs_canonical)
+            pk._load(ql, qr, qm, qo, qk, perm, srs_canonical, qcp)
         return pk
 
-    def _load(self, ql, qr, qm, qo, qk, perm, srs_canonical):
+    def _load(self, ql, qr, qm, qo, qk, perm, srs_canonical, qcp=()):
         pk, curve, log2n, dev = self, self.curve, self.log2n, self.dev
         t = pk.torch
         n, L, q = pk.n, pk.fr.limbs, pk.fr.q
@@ -191,9 +195,12 @@ class ProvingKey:
             _lib.vec_scale_powers(dev, curve, blk, n, pk.fr.enc(pow(pk.g, j, q)), one)
             supp[j * n:(j + 1) * n] = blk.view(n, L)
         lag = {"ql": ql, "qr": qr, "qm": qm, "qo": qo, "qk": qk}
+        pk.n_commit = len(qcp)
+        for j, v in enumerate(qcp):                  # trace.Qcp: selectors of the BSB22 commitment gates
+            lag[f"qcp{j}"] = v
         sigma = {name: supp[pk.perm[j * n:(j + 1) * n]].contiguous() for j, name in enumerate(("s1", "s2", "s3"))}
         del supp, d_w
-        for name in ("ql", "qr", "qm", "qo", "qk", "s1", "s2", "s3"):
+        for name in ("ql", "qr", "qm", "qo", "qk", "s1", "s2", "s3") + tuple(f"qcp{j}" for j in range(pk.n_commit)):
             d = pk._dev(lag[name]) if name in lag else sigma[name]
             pk.dom0[0].ntt_async(d, inverse=True, decimation=_lib.DIF)       # Lagrange/regular -> canonical/bit-reversed
             pk.polys[name] = d
@@ -215,14 +222,17 @@ class ProvingKey:
             self.srs.free()
 
 
-def Prove(pk: ProvingKey, l, r, o, ch: Challenges) -> Proof:
+def Prove(pk: ProvingKey, l, r, o, ch: Challenges, pi2=()) -> Proof:
     """l, r, o: (n, limbs) uint64 Lagrange/regular solution vectors (SparseR1CSSolution{L,R,O},
-    constraint/bn254/system.go:208-210) on the host."""
+    constraint/bn254/system.go:208-210) on the host; pi2: one (n, limbs) Lagrange/regular vector per BSB22
+    commitment of the key (the committed polynomials the solver hint produced)."""
+    if len(pi2) != getattr(pk, "n_commit", 0):
+        raise ValueError("one committed polynomial per Qcp selector of the key is required")
     with pk.on_stream():
-        return _prove(pk, l, r, o, ch)
+        return _prove(pk, l, r, o, ch, pi2)
 
 
-def _prove(pk: ProvingKey, l, r, o, ch: Challenges) -> Proof:
+def _prove(pk: ProvingKey, l, r, o, ch: Challenges, pi2=()) -> Proof:
     import time
     t = pk.torch
     curve, dev, n, logn = pk.curve, pk.dev, pk.n, pk.log2n
@@ -277,6 +287,15 @@ def _prove(pk: ProvingKey, l, r, o, ch: Challenges) -> Proof:
     for name, d, b in (("l", d_l, ch.bl), ("r", d_r, ch.br), ("o", d_o, ch.bo)):
         cb[name], blinded[name] = canonical_blinded(d, b)
     lro = [commit(blinded[k], n + 2) for k in ("l", "r", "o")]
+    # BSB22: committed polynomials, canonical (bit-reversed for the coset NTTs, regular for [PI2_j] and the rest)
+    pi2_br, pi2_canon, bsb22 = [], [], []
+    for v in pi2:
+        d = pk._dev(v).reshape(-1)
+        pk.dom0[0].ntt_async(d, inverse=True, decimation=_lib.DIF)
+        c_ = d.clone()
+        _lib.vec_bit_reverse(dev, curve, c_, logn)
+        pi2_br.append(d); pi2_canon.append(c_)
+        bsb22.append(commit(c_, n))
     lap("commit LRO")
 
     # ---- buildRatioCopyConstraint + commit Z ------------------------------------------------------
@@ -302,6 +321,11 @@ def _prove(pk: ProvingKey, l, r, o, ch: Challenges) -> Proof:
             pk.dom0[i].ntt_async(d, inverse=False, decimation=_lib.DIT, on_coset=True)   # canonical/bit-rev -> coset i, regular
             on_coset[name] = d
         _lib.plonk_constraints_coset(pk.dom0[i], g_m, w4_m, on_coset, a_m, b_m, c_m, blind, i, 4, cres)
+        for j in range(len(pi2)):           # + Qcp_j * PI2_j on this coset (gateConstraint :881-884)
+            dq, dp = pk.polys[f"qcp{j}"].clone(), pi2_br[j].clone()
+            pk.dom0[i].ntt_async(dq, inverse=False, decimation=_lib.DIT, on_coset=True)
+            pk.dom0[i].ntt_async(dp, inverse=False, decimation=_lib.DIT, on_coset=True)
+            _lib.plonk_bsb22_coset(pk.dom0[i], dq, dp, i, 4, cres)
         _lib.sync(dev)
         del on_coset
     if pk.world > 1:
@@ -336,6 +360,9 @@ def _prove(pk: ProvingKey, l, r, o, ch: Challenges) -> Proof:
     axpy(lin, (c2 + a2l1) % q, blinded["z"], n + 3)
     for coef, name in ((c1, "s3"), (rl, "qm"), (lz, "ql"), (rz, "qr"), (oz, "qo"), (1, "qk")):
         axpy(lin, coef, pk.canon[name], n)
+    qcpz = [ev(pk.canon[f"qcp{j}"], n, zeta) for j in range(len(pi2))]
+    for j in range(len(pi2)):               # + sum_j Qcp_j(zeta) PI2_j(X)   (:1457-1460)
+        axpy(lin, qcpz[j], pi2_canon[j], n)
     for k, coef in enumerate((zh, zh * zn2 % q, zh * zn2 % q * zn2 % q)):
         axpy(lin, (-coef) % q, h[k * (n + 2) * L:(k + 1) * (n + 2) * L], n + 2)
     lin_digest = commit(lin, n + 3)
@@ -343,7 +370,7 @@ def _prove(pk: ProvingKey, l, r, o, ch: Challenges) -> Proof:
 
     # ---- batchOpening :796-837 (fold with powers of v, divide by X - zeta) and the Z opening ---------
     to_open = [(lin, n + 3), (blinded["l"], n + 2), (blinded["r"], n + 2), (blinded["o"], n + 2),
-               (pk.canon["s1"], n), (pk.canon["s2"], n)]
+               (pk.canon["s1"], n), (pk.canon["s2"], n)] + [(pk.canon[f"qcp{j}"], n) for j in range(len(pi2))]
     claimed = [ev(d, cnt, zeta) for d, cnt in to_open]
     fold = t.zeros((n + 3) * L, dtype=t.int64, device=d_l.device)
     vp = 1
@@ -358,4 +385,5 @@ def _prove(pk: ProvingKey, l, r, o, ch: Challenges) -> Proof:
     z_open_h = commit(zq, n + 2)
     lap("openings")
     return Proof(LRO=lro, Z=z_digest, H=H, LinearizedDigest=lin_digest, BatchedProofH=batch_h,
-                 BatchedClaimedValues=claimed, ZShiftedOpeningH=z_open_h, ZShiftedClaimedValue=zu, timings_ms=tm)
+                 BatchedClaimedValues=claimed, ZShiftedOpeningH=z_open_h, ZShiftedClaimedValue=zu, Bsb22Commitments=bsb22,
+                 timings_ms=tm)

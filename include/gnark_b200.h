@@ -181,6 +181,11 @@ typedef struct {
 } b200_plonk_coset_args;
 int32_t b200_plonk_constraints_coset(b200_domain_t domain0, const void* domain1_coset_gen_mont,
                                      const void* domain1_gen_mont, const b200_plonk_coset_args* args);
+/* BSB22 commitment gates (gateConstraint :881-884: + sum_i Qcp_i * PI2_i): after b200_plonk_constraints_coset has
+ * written coset `coset_index`, one call per commitment adds qcp[j] * pi2[j] (both already ON that coset, regular
+ * layout, n elements) to the slot of point j. */
+int32_t b200_plonk_bsb22_coset(b200_domain_t domain0, const void* d_qcp, const void* d_pi2, uint32_t coset_index,
+                               uint32_t rho, void* d_out);
 /* r[i] *= 1/(X^n-1) on the big coset (indexing rule of :1312-1317), then
  * FFTInverse(DIT, OnCoset) on domain1: LagrangeCoset/BitReverse -> Canonical/Regular, in place. */
 int32_t b200_plonk_divide_by_zh(b200_domain_t domain1, uint32_t domain0_log2n, void* d_data);
@@ -217,18 +222,25 @@ typedef struct {
   const void *ql, *qr, *qm, *qo, *qk;    /* n fr.Elements each, Lagrange/regular */
   const int64_t* perm;                   /* trace.S, 3n entries */
   const void* srs_canonical;             /* n + 3 G1Affine */
+  uint32_t n_qcp;                        /* BSB22 commitment gates (len(trace.Qcp)), 0 = none */
+  const void* const* qcp;                /* n_qcp selectors Qcp_j, n fr.Elements each, Lagrange/regular */
 } b200_plonk_pk_desc;
 typedef struct {
   const void *gamma, *beta, *alpha, *zeta, *v; /* one fr.Element each */
   const void *bl, *br, *bo;                    /* blinding of L, R, O: 2 coefficients each */
   const void* bz;                              /* blinding of Z: 3 coefficients */
+  /* BSB22 (keys with n_qcp > 0, else NULL): the committed polynomials PI2_j produced by the solver hint
+   * (prove.go:280-318), n fr.Elements each, Lagrange/regular; out_bsb22 receives [PI2_j] (n_qcp G1Jac) */
+  const void* const* pi2;
+  void* out_bsb22;
 } b200_plonk_challenges;
 int32_t b200_plonk_pk_load(int32_t dev, int32_t curve, const b200_plonk_pk_desc* desc, b200_plonk_pk_t* out);
 int32_t b200_plonk_pk_free(b200_plonk_pk_t pk);
 /* l, r, o: the solved wire columns (SparseR1CSSolution{L,R,O}, constraint/bn254/system.go:208-210), n fr.Elements
  * each on the host.  out_points: 10 G1Jac in gnark layout - [L], [R], [O], [Z], [H1], [H2], [H3], linearised digest,
- * batched opening quotient, Z-shifted opening quotient (Proof fields, prove.go:77-96).  out_values: 7 fr.Elements -
- * the claimed values at zeta of {linearised polynomial, l, r, o, s1, s2} (BatchedProof.ClaimedValues) and Z(w*zeta). */
+ * batched opening quotient, Z-shifted opening quotient (Proof fields, prove.go:77-96).  out_values: 7 + n_qcp
+ * fr.Elements - the claimed values at zeta of {linearised polynomial, l, r, o, s1, s2}, then Z(w*zeta), then
+ * Qcp_j(zeta) (BatchedProof.ClaimedValues = values 0-5 followed by values 7..). */
 int32_t b200_plonk_prove(b200_plonk_pk_t pk, const void* l, const void* r, const void* o,
                          const b200_plonk_challenges* ch, void* out_points, void* out_values);
 /* The same proof, one entry point per Fiat-Shamir round, so that a caller can derive each challenge from the digests
@@ -240,11 +252,13 @@ int32_t b200_plonk_prove(b200_plonk_pk_t pk, const void* l, const void* r, const
  *   quotient    computeQuotient :558-633        out_h: [H1], [H2], [H3]
  *   linearise   openZ :670-687 + computeLinearizedPolynomial :724-794
  *               out_points: linearised digest, Z-shifted opening quotient (2 G1Jac);
- *               out_values: p(zeta) of {linearised, l, r, o, s1, s2}, then Z(w*zeta)              (7 fr.Elements)
+ *               out_values: p(zeta) of {linearised, l, r, o, s1, s2}, then Z(w*zeta), then Qcp_j(zeta)
+ *                                                                                       (7 + n_qcp fr.Elements)
  *   batch_open  batchOpening :796-837           out_point: BatchedProof.H */
 typedef struct b200_plonk_session_s* b200_plonk_session_t;
 int32_t b200_plonk_begin(b200_plonk_pk_t pk, const void* l, const void* r, const void* o, const void* bl /*2*/,
-                         const void* br /*2*/, const void* bo /*2*/, b200_plonk_session_t* out, void* out_lro);
+                         const void* br /*2*/, const void* bo /*2*/, const void* const* pi2 /* n_qcp or NULL */,
+                         void* out_bsb22 /* n_qcp G1Jac or NULL */, b200_plonk_session_t* out, void* out_lro);
 int32_t b200_plonk_commit_z(b200_plonk_session_t s, const void* beta, const void* gamma, const void* bz /*3*/,
                             void* out_z);
 int32_t b200_plonk_quotient(b200_plonk_session_t s, const void* alpha, void* out_h);

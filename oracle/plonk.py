@@ -6,7 +6,7 @@ Follows backend/plonk/bn254/prove.go:
                                localConstraint :933-941 with computeLagrangeOneOnCoset :380-385,
                                allConstraints :961-988, coset loop :996-1088, scatter :1070-1076)
   divideByZH :1287-1324, evaluateXnMinusOneDomainBigCoset :1327-1350, batchInvert :1130-1143.
-No BSB22 gates (nbBsbGates = 0).
+BSB22 commitment gates (:881-884): gate += sum_i Qcp_i * PI2_i, passed as `bsb22` = [(qcp_lagrange, pi2_lagrange), ...].
 
 The reference moves the 12 polynomials from coset to coset incrementally (iFFT, scale by the
 shifter powers, FFT) and pre-scales the blinding polynomials' coefficients; mathematically every
@@ -52,7 +52,7 @@ def coset_values(curve, dom0: Domain, lagrange, coset):
     return [poly_eval(r, coeffs, coset * pow(dom0.generator, j, r) % r) for j in range(dom0.n)]
 
 
-def numerator(curve, n, rho, polys_lagrange, alpha, beta, gamma, blind):
+def numerator(curve, n, rho, polys_lagrange, alpha, beta, gamma, blind, bsb22=()):
     """cres (LagrangeCoset on the big domain, BitReverse layout), length rho*n."""
     r = curve.r
     dom0 = Domain(curve, n)
@@ -63,6 +63,7 @@ def numerator(curve, n, rho, polys_lagrange, alpha, beta, gamma, blind):
     for i in range(rho):
         coset = g * pow(w4, i, r) % r
         vals = {k: coset_values(curve, dom0, polys_lagrange[k], coset) for k in POLYS}
+        extra = [(coset_values(curve, dom0, qcp, coset), coset_values(curve, dom0, pi2, coset)) for qcp, pi2 in bsb22]
         xn1 = (pow(coset, n, r) - 1) % r
         for j in range(n):
             x = coset * pow(w, j, r) % r
@@ -70,6 +71,8 @@ def numerator(curve, n, rho, polys_lagrange, alpha, beta, gamma, blind):
             u = {k: vals[k][j] for k in POLYS}
             u["zs"] = vals["z"][(j + 1) % n]
             v = all_constraints(r, n, dom0.cardinality_inv, u, x, x1, alpha, beta, gamma, g, blind, xn1)
+            for qv, pv in extra:                      # the gate term enters the sum with coefficient 1
+                v = (v + qv[j] * pv[j]) % r
             cres[bitrev(rho * j + i, logm)] = v
     return cres
 

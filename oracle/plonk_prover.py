@@ -1,7 +1,10 @@
 """PLONK prover restated on big ints, with a trapdoor SRS.  TEST INFRASTRUCTURE ONLY
 (see oracle/params.py header; parity unpinned by the reference).
 
-Follows backend/plonk/bn254/prove.go (no BSB22 commitments, StatisticalZK off):
+Follows backend/plonk/bn254/prove.go (StatisticalZK off; BSB22 commitment gates :867-884 with the committed
+polynomials PI2_i GIVEN - in the reference they come from the solver hint :280-318 - their digests
+Bsb22Commitments :300, the linearised-polynomial term sum_i Qcp_i(zeta) PI2_i(X) :1362,1457 and the Qcp openings
+:805-817):
   Prove :98-153; blinding polynomials :259-266,1239-1253 (orders 1,1,1,2 :72-75);
   commitToLRO :404-489 + commitBlindingFactor :1223-1236 (digest of p + b*(X^n - 1));
   buildRatioCopyConstraint :635-667; computeQuotient :558-633 -> computeNumerator :841-1123,
@@ -36,6 +39,7 @@ class Circuit:
     qo: List[int]
     qk: List[int]           # complete Qk (public inputs folded in, prove.go:349-373)
     perm: List[int]         # 3n entries
+    qcp: List[List[int]] = field(default_factory=list)    # trace.Qcp: one selector per BSB22 commitment
 
 
 @dataclass
@@ -62,12 +66,13 @@ class Proof:
     lin: int
     batch_opening: int       # [ (f - f(zeta)) / (X - zeta) ]
     z_opening: int           # [ (Z_b - Z_b(w zeta)) / (X - w zeta) ]
-    claimed: List[int]       # lin(zeta), l(zeta), r(zeta), o(zeta), s1(zeta), s2(zeta)
+    claimed: List[int]       # lin(zeta), l(zeta), r(zeta), o(zeta), s1(zeta), s2(zeta), then Qcp_j(zeta)
     zu: int                  # Z_b(w zeta)
     # intermediates kept for parity tests
     h: List[int] = field(default_factory=list)
     lin_poly: List[int] = field(default_factory=list)
     z_lagrange: List[int] = field(default_factory=list)
+    bsb22: List[int] = field(default_factory=list)       # Bsb22Commitments: [PI2_j]
 
 
 def canonical(curve, dom: Domain, lagrange):
@@ -88,8 +93,10 @@ def sigma_polys(curve, dom0: Domain, perm):
     return [[supp[perm[j * n + i]] for i in range(n)] for j in range(3)]
 
 
-def prove(curve, circ: Circuit, l, rr, o, ch: Challenges, tau: int) -> Proof:
+def prove(curve, circ: Circuit, l, rr, o, ch: Challenges, tau: int, pi2=()) -> Proof:
+    """pi2: the committed polynomials (Lagrange/regular), one per circ.qcp entry"""
     r, n = curve.r, circ.n
+    assert len(pi2) == len(circ.qcp)
     dom0 = Domain(curve, n)
     g, w = dom0.coset_gen, dom0.generator
     ev = lambda p, x: poly_eval(r, p, x)
@@ -104,7 +111,7 @@ def prove(curve, circ: Circuit, l, rr, o, ch: Challenges, tau: int) -> Proof:
     polys = {"l": l, "r": rr, "o": o, "z": z, "s1": s1, "s2": s2, "s3": s3,
              "ql": circ.ql, "qr": circ.qr, "qm": circ.qm, "qo": circ.qo, "qk": circ.qk}
     blind = {"l": ch.bl, "r": ch.br, "o": ch.bo, "z": ch.bz}
-    cres = plonk.numerator(curve, n, 4, polys, ch.alpha, ch.beta, ch.gamma, blind)
+    cres = plonk.numerator(curve, n, 4, polys, ch.alpha, ch.beta, ch.gamma, blind, bsb22=list(zip(circ.qcp, pi2)))
     h = plonk.divide_by_zh(curve, n, 4, cres)
     assert all(x == 0 for x in h[3 * (n + 2):]), "numerator not divisible by X^n - 1: unsatisfied trace"
     h1, h2, h3 = h[:n + 2], h[n + 2:2 * (n + 2)], h[2 * (n + 2):3 * (n + 2)]
@@ -115,6 +122,9 @@ def prove(curve, circ: Circuit, l, rr, o, ch: Challenges, tau: int) -> Proof:
     cs1, cs2, cs3 = (canonical(curve, dom0, v) for v in (s1, s2, s3))
     cql, cqr, cqm, cqo, cqk = (canonical(curve, dom0, v) for v in (circ.ql, circ.qr, circ.qm, circ.qo, circ.qk))
     s1z, s2z = ev(cs1, zeta), ev(cs2, zeta)
+    cqcp = [canonical(curve, dom0, v) for v in circ.qcp]
+    cpi2 = [canonical(curve, dom0, v) for v in pi2]
+    qcpz = [ev(p, zeta) for p in cqcp]
     # innerComputeLinearizedPoly :1366-1487
     alpha, beta, gamma = ch.alpha, ch.beta, ch.gamma
     rl = rz * lz % r
@@ -131,12 +141,14 @@ def prove(curve, circ: Circuit, l, rr, o, ch: Challenges, tau: int) -> Proof:
         t = zb[i] * c2 % r
         if i < n:
             t = (t + cs3[i] * c1 + cqm[i] * rl + cql[i] * lz + cqr[i] * rz + cqo[i] * oz + cqk[i]) % r
+            for j in range(len(cqcp)):              # + sum_j Qcp_j(zeta) PI2_j(X)   (:1457-1460)
+                t = (t + cpi2[j][i] * qcpz[j]) % r
         t = (t + zb[i] * a2l1) % r
         if i < n + 2:
             t = (t - zh * ((h3[i] * zn2 + h2[i]) % r * zn2 % r + h1[i])) % r
         lin.append(t)
     # batchOpening :796-837
-    to_open = [lin, lb, rb, ob, cs1, cs2]
+    to_open = [lin, lb, rb, ob, cs1, cs2] + cqcp
     claimed = [ev(p, zeta) for p in to_open]
     size = max(len(p) for p in to_open)
     f = [0] * size
@@ -150,7 +162,8 @@ def prove(curve, circ: Circuit, l, rr, o, ch: Challenges, tau: int) -> Proof:
     assert zu2 == zu
     com = lambda p: ev(p, tau)
     return Proof(L=com(lb), R=com(rb), O=com(ob), Z=com(zb), H=[com(h1), com(h2), com(h3)], lin=com(lin),
-                 batch_opening=com(qf), z_opening=com(qz), claimed=claimed, zu=zu, h=h, lin_poly=lin, z_lagrange=z)
+                 batch_opening=com(qf), z_opening=com(qz), claimed=claimed, zu=zu, h=h, lin_poly=lin, z_lagrange=z,
+                 bsb22=[com(p) for p in cpi2])
 
 
 def verify(curve, circ: Circuit, proof: Proof, ch: Challenges, tau: int) -> bool:
@@ -160,7 +173,9 @@ def verify(curve, circ: Circuit, proof: Proof, ch: Challenges, tau: int) -> bool
     dom0 = Domain(curve, n)
     g, w = dom0.coset_gen, dom0.generator
     zeta, alpha, beta, gamma = ch.zeta, ch.alpha, ch.beta, ch.gamma
-    lin_z, lz, rz, oz, s1z, s2z = proof.claimed
+    lin_z, lz, rz, oz, s1z, s2z = proof.claimed[:6]
+    qcpz = proof.claimed[6:]
+    assert len(qcpz) == len(circ.qcp) == len(proof.bsb22)
     zn = pow(zeta, n, r)
     zh = (zn - 1) % r
     l1 = zh * pow((zeta - 1) % r, -1, r) % r * dom0.cardinality_inv % r
@@ -178,11 +193,12 @@ def verify(curve, circ: Circuit, proof: Proof, ch: Challenges, tau: int) -> bool
     zn2 = zn * zeta % r * zeta % r
     lin_digest = (proof.Z * ((c2 + alpha * alpha % r * l1) % r) + com_l(s3) * c1 + com_l(circ.qm) * (rz * lz % r)
                   + com_l(circ.ql) * lz + com_l(circ.qr) * rz + com_l(circ.qo) * oz + com_l(circ.qk)
+                  + sum(q_ * d_ for q_, d_ in zip(qcpz, proof.bsb22))       # sum_j Qcp_j(zeta) [PI2_j]  (verify.go)
                   - zh * ((proof.H[2] * zn2 + proof.H[1]) % r * zn2 % r + proof.H[0])) % r
     if lin_digest != proof.lin:
         return False
     # batched KZG opening at zeta: e([f] - f(zeta)[1], [1]) = e([H], [tau - zeta])
-    digests = [proof.lin, proof.L, proof.R, proof.O, com_l(s1), com_l(s2)]
+    digests = [proof.lin, proof.L, proof.R, proof.O, com_l(s1), com_l(s2)] + [com_l(q_) for q_ in circ.qcp]
     f_tau = f_z = 0
     vp = 1
     for d, c in zip(digests, proof.claimed):
@@ -197,9 +213,11 @@ def verify(curve, circ: Circuit, proof: Proof, ch: Challenges, tau: int) -> bool
     return True
 
 
-def random_satisfied_instance(curve, n, seed):
+def random_satisfied_instance(curve, n, seed, n_commit=0):
     """A random satisfied trace: random gates L*R-style with O solved, and a permutation built from
-    cycles over slots that are FORCED to carry equal values (so the copy constraints hold)."""
+    cycles over slots that are FORCED to carry equal values (so the copy constraints hold).
+    n_commit > 0: also n_commit BSB22 gates (random selectors Qcp_j, random committed polynomials PI2_j entering
+    the gate equation); returns (circuit, l, r, o, pi2)."""
     import random
     rng = random.Random(seed)
     r = curve.r
@@ -212,7 +230,10 @@ def random_satisfied_instance(curve, n, seed):
     qm = [rng.randrange(r) for _ in range(n)]
     qk = [rng.randrange(r) for _ in range(n)]
     qo = [r - 1] * n
-    o = [(ql[i] * l[i] + qr[i] * rr[i] + qm[i] * l[i] * rr[i] + qk[i]) % r for i in range(n)]
+    qcp = [[rng.randrange(r) if rng.random() < 0.5 else 0 for _ in range(n)] for _ in range(n_commit)]
+    pi2 = [[rng.randrange(r) for _ in range(n)] for _ in range(n_commit)]
+    o = [(ql[i] * l[i] + qr[i] * rr[i] + qm[i] * l[i] * rr[i] + qk[i]
+          + sum(qcp[j][i] * pi2[j][i] for j in range(n_commit))) % r for i in range(n)]
     vals = l + rr + o
     # permutation: link all slots holding the same value into one cycle
     groups = {}
@@ -224,4 +245,7 @@ def random_satisfied_instance(curve, n, seed):
             rng.shuffle(idxs)
             for a, b in zip(idxs, idxs[1:] + idxs[:1]):
                 perm[a] = b
-    return Circuit(n=n, ql=ql, qr=qr, qm=qm, qo=qo, qk=qk, perm=perm), l, rr, o
+    circ = Circuit(n=n, ql=ql, qr=qr, qm=qm, qo=qo, qk=qk, perm=perm, qcp=qcp)
+    if n_commit:
+        return circ, l, rr, o, pi2
+    return circ, l, rr, o

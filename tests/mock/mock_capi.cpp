@@ -121,6 +121,17 @@ int32_t b200_plonk_constraints_coset(b200_domain_t d0, const void* big_coset_gen
   const int nb[4] = {a->nbl, a->nbr, a->nbo, a->nbz};
   return plonk_coset_emu<Fr>(polys, abg, blind, nb, (uint32_t)dom->logn, a->coset_index, a->rho, a->out);
 }
+int32_t b200_plonk_bsb22_coset(b200_domain_t d0, const void* qcp, const void* pi2, uint32_t coset_index, uint32_t rho, void* out) {
+  NttDomainHost<Fr>* dom = (NttDomainHost<Fr>*)d0->impl;
+  uint32_t log_rho = 0;
+  while ((1u << log_rho) < rho) log_rho++;
+  const Fr* Q = (const Fr*)qcp; const Fr* PI = (const Fr*)pi2; Fr* O = (Fr*)out;
+  for (uint32_t j = 0; j < dom->n; j++) {
+    const uint32_t k = ntt_bitrev(rho * j + coset_index, dom->logn + (int)log_rho);
+    O[k] = O[k] + Q[j] * PI[j];
+  }
+  return 0;
+}
 // r[i] *= 1/(X^n - 1) on the big coset, then FFTInverse(DIT, OnCoset) on domain1
 int32_t b200_plonk_divide_by_zh(b200_domain_t d1, uint32_t log_n0, void* data) {
   NttDomainHost<Fr>* dom = (NttDomainHost<Fr>*)d1->impl;

@@ -413,3 +413,13 @@ def test_plonk_constraint_kernel_logic(hostemu, c):
         pp = (ctypes.c_void_p * 12)(*[a.ctypes.data for a in on_coset])
         assert hostemu.emu_plonk_constraints_coset(c.curve_id, pp, P(abg), blp, nbl, logn, i, rho, P(out)) == 0
     assert ff.unpack_elements(out, r, L) == want
+    # BSB22 commitment gates: k_plonk_add_bsb22 completes the gate term afterwards, one call per commitment and coset
+    bsb = [([rng.randrange(r) for _ in range(n)], [rng.randrange(r) for _ in range(n)]) for _ in range(2)]
+    want2 = plonk.numerator(c, n, rho, polys, alpha, beta, gamma, blind, bsb22=bsb)
+    assert want2 != want
+    for i in range(rho):
+        coset = dom1.coset_gen * pow(dom1.generator, i, r) % r
+        for qcp, pi2 in bsb:
+            Q, PI = pe(plonk.coset_values(c, dom0, qcp, coset)), pe(plonk.coset_values(c, dom0, pi2, coset))
+            assert hostemu.emu_plonk_bsb22(c.curve_id, P(Q), P(PI), P(out), logn, i, rho) == 0
+    assert ff.unpack_elements(out, r, L) == want2

@@ -255,3 +255,39 @@ def test_plonk_prove_c_abi_vs_oracle(gpu, c, logn):
     got_vals = ff.unpack_elements(vals, r, L)
     assert got_vals[:6] == want.claimed and got_vals[6] == want.zu
     key.free()
+
+
+@pytest.mark.xfail(strict=False, reason="BSB22 commitment gates written after this round's GPU budget was spent; pinned on the "
+                   "CPU by tests/test_plonk_host_cpu.py::test_plonk_host_bsb22_commitments and the emulation tests")
+@pytest.mark.parametrize("n_commit", (1, 2))
+def test_plonk_prove_bsb22(gpu, n_commit):
+    """b200_plonk_prove on a key with BSB22 commitment gates against the oracle prover: digests (incl. [PI2_j]) and the
+    7 + n_commit opened values"""
+    from oracle import corelib, plonk_prover as pp
+    c = CURVES["bn254"]
+    logn = 5
+    rng = random.Random(5000 + n_commit)
+    r, L = c.r, c.fr_limbs
+    n = 1 << logn
+    circ, l, rr, o, pi2 = pp.random_satisfied_instance(c, n, seed=71, n_commit=n_commit)
+    rnd = lambda: rng.randrange(r)
+    ch = pp.Challenges(gamma=rnd(), beta=rnd(), alpha=rnd(), zeta=rnd(), v=rnd(), bl=[rnd(), rnd()], br=[rnd(), rnd()],
+                       bo=[rnd(), rnd()], bz=[rnd(), rnd(), rnd()])
+    tau = rnd()
+    want = pp.prove(c, circ, l, rr, o, ch, tau, pi2=pi2)
+    assert pp.verify(c, circ, want, ch, tau)
+    pe = lambda v: ff.pack_elements(v, r, L)
+    srs = corelib.fixed_base(c, 1, ec.pack_points(c, 1, [c.g1]), pe([pow(tau, i, r) for i in range(n + 3)]))
+    key = gpu.PlonkKey(c.curve_id, logn, pe(circ.ql), pe(circ.qr), pe(circ.qm), pe(circ.qo), pe(circ.qk),
+                       np.array(circ.perm, dtype=np.int64), srs, qcp=[pe(v) for v in circ.qcp])
+    pts, vals, bsb = key.prove(pe(l), pe(rr), pe(o), pe([ch.gamma]), pe([ch.beta]), pe([ch.alpha]), pe([ch.zeta]),
+                               pe([ch.v]), pe(ch.bl), pe(ch.br), pe(ch.bo), pe(ch.bz), pi2=[pe(v) for v in pi2])
+    F = ff.Fp(c.p)
+    dl = [want.L, want.R, want.O, want.Z, want.H[0], want.H[1], want.H[2], want.lin, want.batch_opening, want.z_opening]
+    for k in range(10):
+        assert jac_to_affine(c, 1, pts[k]) == ec.scalar_mul(F, dl[k], c.g1), k
+    for j in range(n_commit):
+        assert jac_to_affine(c, 1, bsb[j]) == ec.scalar_mul(F, want.bsb22[j], c.g1)
+    got = ff.unpack_elements(vals, r, L)
+    assert got[:6] + got[7:] == want.claimed and got[6] == want.zu
+    key.free()

@@ -28,7 +28,7 @@ def mock():
     m.b200_plonk_pk_load.argtypes = [i32, i32, ctypes.POINTER(b200.PlonkPkDesc), ctypes.POINTER(vp)]
     m.b200_plonk_pk_free.argtypes = [vp]
     m.b200_plonk_prove.argtypes = [vp, vp, vp, vp, ctypes.POINTER(b200.PlonkChallenges), vp, vp]
-    m.b200_plonk_begin.argtypes = [vp, vp, vp, vp, vp, vp, vp, ctypes.POINTER(vp), vp]
+    m.b200_plonk_begin.argtypes = [vp, vp, vp, vp, vp, vp, vp, ctypes.POINTER(vp), vp, ctypes.POINTER(vp), vp]
     m.b200_plonk_commit_z.argtypes = [vp, vp, vp, vp, vp]
     m.b200_plonk_quotient.argtypes = [vp, vp, vp]
     m.b200_plonk_linearise.argtypes = [vp, vp, vp, vp]
@@ -83,7 +83,8 @@ def test_plonk_host_orchestration_vs_oracle(mock, logn):
     s_ = ctypes.c_void_p(0)
     lro, zpt, hpts = np.zeros((3, jl), dtype=np.uint64), np.zeros(jl, dtype=np.uint64), np.zeros((3, jl), dtype=np.uint64)
     two, vals2, bpt = np.zeros((2, jl), dtype=np.uint64), np.zeros((7, L), dtype=np.uint64), np.zeros(jl, dtype=np.uint64)
-    assert mock.b200_plonk_begin(h, P(L_), P(R_), P(O_), P(sc["bl"]), P(sc["br"]), P(sc["bo"]), ctypes.byref(s_), P(lro)) == 0
+    assert mock.b200_plonk_begin(h, P(L_), P(R_), P(O_), P(sc["bl"]), P(sc["br"]), P(sc["bo"]), None, None,
+                                 ctypes.byref(s_), P(lro)) == 0
     assert mock.b200_plonk_quotient(s_, P(sc["alpha"]), P(hpts)) != 0 and b"after plonk_commit_z" in mock.b200_last_error()
     assert mock.b200_plonk_commit_z(s_, P(sc["beta"]), P(sc["gamma"]), P(sc["bz"]), P(zpt)) == 0
     assert mock.b200_plonk_batch_open(s_, P(sc["v"]), P(bpt)) != 0
@@ -99,4 +100,61 @@ def test_plonk_host_orchestration_vs_oracle(mock, logn):
     h2 = ctypes.c_void_p(0)
     assert mock.b200_plonk_pk_load(0, c.curve_id, ctypes.byref(d), ctypes.byref(h2)) != 0
     assert b"out of range" in mock.b200_last_error()
+    assert mock.b200_plonk_pk_free(h) == 0
+
+
+@pytest.mark.parametrize("n_commit", (1, 2))
+def test_plonk_host_bsb22_commitments(mock, n_commit):
+    """keys with BSB22 commitment gates: gate term on every coset, [PI2_j], sum_j Qcp_j(zeta) PI2_j(X) in the linearised
+    polynomial, Qcp openings - b200_plonk_prove against the oracle prover (extended verifier equations hold)"""
+    c = CURVES["bn254"]
+    logn = 4
+    rng = random.Random(4000 + n_commit)
+    r, L = c.r, c.fr_limbs
+    n = 1 << logn
+    circ, l, rr, o, pi2 = pp.random_satisfied_instance(c, n, seed=61, n_commit=n_commit)
+    rnd = lambda: rng.randrange(r)
+    ch = pp.Challenges(gamma=rnd(), beta=rnd(), alpha=rnd(), zeta=rnd(), v=rnd(), bl=[rnd(), rnd()], br=[rnd(), rnd()],
+                       bo=[rnd(), rnd()], bz=[rnd(), rnd(), rnd()])
+    tau = rnd()
+    want = pp.prove(c, circ, l, rr, o, ch, tau, pi2=pi2)
+    assert pp.verify(c, circ, want, ch, tau)
+    pe = lambda v: np.ascontiguousarray(ff.pack_elements(v, r, L))
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    srs = np.ascontiguousarray(corelib.fixed_base(c, 1, ec.pack_points(c, 1, [c.g1]), pe([pow(tau, i, r) for i in range(n + 3)])))
+    keep = {k: pe(getattr(circ, k)) for k in ("ql", "qr", "qm", "qo", "qk")}
+    perm = np.ascontiguousarray(np.array(circ.perm, dtype=np.int64))
+    qcp = [pe(v) for v in circ.qcp]
+    qarr = (ctypes.c_void_p * n_commit)(*[a.ctypes.data for a in qcp])
+    d = b200.PlonkPkDesc()
+    d.log2n = logn
+    for k, a in keep.items():
+        setattr(d, k, P(a).value)
+    d.perm, d.srs_canonical = P(perm).value, P(srs).value
+    d.n_qcp, d.qcp = n_commit, ctypes.cast(qarr, ctypes.POINTER(ctypes.c_void_p))
+    h = ctypes.c_void_p(0)
+    assert mock.b200_plonk_pk_load(0, c.curve_id, ctypes.byref(d), ctypes.byref(h)) == 0, mock.b200_last_error()
+    sc = {k: pe(v) for k, v in (("gamma", [ch.gamma]), ("beta", [ch.beta]), ("alpha", [ch.alpha]), ("zeta", [ch.zeta]),
+                                ("v", [ch.v]), ("bl", ch.bl), ("br", ch.br), ("bo", ch.bo), ("bz", ch.bz))}
+    cs = b200.PlonkChallenges()
+    for k, a in sc.items():
+        setattr(cs, k, P(a).value)
+    pts = np.zeros((10, 3 * c.fp_limbs), dtype=np.uint64)
+    vals = np.zeros((7 + n_commit, L), dtype=np.uint64)
+    bsb = np.zeros((n_commit, 3 * c.fp_limbs), dtype=np.uint64)
+    L_, R_, O_ = pe(l), pe(rr), pe(o)
+    # without the committed polynomials the call is refused
+    assert mock.b200_plonk_prove(h, P(L_), P(R_), P(O_), ctypes.byref(cs), P(pts), P(vals)) != 0
+    pi2a = [pe(v) for v in pi2]
+    parr = (ctypes.c_void_p * n_commit)(*[a.ctypes.data for a in pi2a])
+    cs.pi2, cs.out_bsb22 = ctypes.cast(parr, ctypes.POINTER(ctypes.c_void_p)), P(bsb).value
+    assert mock.b200_plonk_prove(h, P(L_), P(R_), P(O_), ctypes.byref(cs), P(pts), P(vals)) == 0, mock.b200_last_error()
+    F = ff.Fp(c.p)
+    dl = [want.L, want.R, want.O, want.Z, want.H[0], want.H[1], want.H[2], want.lin, want.batch_opening, want.z_opening]
+    for k, name in enumerate(("L", "R", "O", "Z", "H1", "H2", "H3", "lin", "batch", "zopen")):
+        assert jac_to_affine(c, 1, pts[k]) == ec.scalar_mul(F, dl[k], c.g1), name
+    for j in range(n_commit):
+        assert jac_to_affine(c, 1, bsb[j]) == ec.scalar_mul(F, want.bsb22[j], c.g1)
+    got = ff.unpack_elements(vals, r, L)
+    assert got[:6] + got[7:] == want.claimed and got[6] == want.zu
     assert mock.b200_plonk_pk_free(h) == 0

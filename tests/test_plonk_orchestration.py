@@ -106,6 +106,17 @@ def make_mock_lib(real_lib, calls):
                                       _scalar(c, gamma), g, bl, xn1)
             _store(c, d_out, [v], offset=ntt.bitrev(rho * j + coset_index, logm))
 
+    def plonk_bsb22_coset(dom0, d_qcp, d_pi2, coset_index, rho, d_out):
+        """documented result of b200_plonk_bsb22_coset: out[slot of point j] += qcp[j] * pi2[j]"""
+        calls.append("bsb22")
+        c, n = dom0.c, dom0.n
+        qv, pv = _ints(c, d_qcp, n), _ints(c, d_pi2, n)
+        logm = (rho * n).bit_length() - 1
+        cur = _ints(c, d_out, rho * n)
+        for j in range(n):
+            k = ntt.bitrev(rho * j + coset_index, logm)
+            _store(c, d_out, [(cur[k] + qv[j] * pv[j]) % c.r], offset=k)
+
     def plonk_divide_by_zh(dom1, domain0_log2n, d):
         c = dom1.c
         n = 1 << domain0_log2n
@@ -139,6 +150,7 @@ def make_mock_lib(real_lib, calls):
         _store(c, d_out, [f(x, y) % c.r for x, y in zip(a, b)])
 
     m.vec_scale_powers, m.vec_op = vec_scale_powers, vec_op
+    m.plonk_bsb22_coset = plonk_bsb22_coset
     m.Domain, m.Table = Domain, Table
     m.vec_bit_reverse, m.plonk_build_z, m.plonk_constraints_coset = vec_bit_reverse, plonk_build_z, plonk_constraints_coset
     m.plonk_divide_by_zh, m.poly_eval, m.poly_div_by_linear, m.vec_axpy = plonk_divide_by_zh, poly_eval, poly_div_by_linear, vec_axpy
@@ -190,3 +202,50 @@ def test_orchestration_against_oracle_prover(monkeypatch, cname, logn):
     # per proof: 12 polys x 4 cosets + 4 canonical conversions (l, r, o, z) NTTs; 4 constraint calls; 10 commitments
     assert calls.count("ntt") == 8 + 48 + 4 and calls.count("constraints") == 4 and calls.count("msm") == 10
     pk.free()
+
+
+@pytest.mark.parametrize("n_commit", (1, 2))
+def test_orchestration_with_bsb22_commitments(monkeypatch, n_commit):
+    """BSB22 commitment gates through the orchestrator: gate term on every coset, [PI2_j], the linearised-polynomial
+    term sum_j Qcp_j(zeta) PI2_j(X) and the extra Qcp openings - against the oracle prover (whose proof passes the
+    extended verifier equations)"""
+    from gnark_b200 import lib as real_lib, plonk as b200_plonk
+    c = CURVES["bn254"]
+    calls = []
+    monkeypatch.setattr(b200_plonk, "_lib", make_mock_lib(real_lib, calls))
+    monkeypatch.setattr(b200_plonk, "_device", lambda dev: "cpu")
+    monkeypatch.setattr(b200_plonk, "_new_stream",
+                        lambda torch, dev: types.SimpleNamespace(cuda_stream=1234, synchronize=lambda: None))
+    monkeypatch.setattr(b200_plonk, "_stream_ctx", lambda torch, s: contextlib.nullcontext())
+    logn = 4
+    rng = random.Random(900 + n_commit)
+    r, L = c.r, c.fr_limbs
+    n = 1 << logn
+    circ, l, rr, o, pi2 = pp.random_satisfied_instance(c, n, seed=31, n_commit=n_commit)
+    rnd = lambda: rng.randrange(r)
+    ch = pp.Challenges(gamma=rnd(), beta=rnd(), alpha=rnd(), zeta=rnd(), v=rnd(), bl=[rnd(), rnd()], br=[rnd(), rnd()],
+                       bo=[rnd(), rnd()], bz=[rnd(), rnd(), rnd()])
+    tau = rnd()
+    want = pp.prove(c, circ, l, rr, o, ch, tau, pi2=pi2)
+    assert pp.verify(c, circ, want, ch, tau)
+    pe = lambda v: ff.pack_elements(v, r, L)
+    srs = corelib.fixed_base(c, 1, ec.pack_points(c, 1, [c.g1]), pe([pow(tau, i, r) for i in range(n + 3)]))
+    pk = b200_plonk.ProvingKey.from_trace(c.curve_id, logn, pe(circ.ql), pe(circ.qr), pe(circ.qm), pe(circ.qo),
+                                         pe(circ.qk), np.array(circ.perm, dtype=np.int64), srs,
+                                         qcp=[pe(v) for v in circ.qcp])
+    got = b200_plonk.Prove(pk, pe(l), pe(rr), pe(o),
+                           b200_plonk.Challenges(gamma=ch.gamma, beta=ch.beta, alpha=ch.alpha, zeta=ch.zeta, v=ch.v,
+                                                 bl=ch.bl, br=ch.br, bo=ch.bo, bz=ch.bz), pi2=[pe(v) for v in pi2])
+    F = ff.Fp(c.p)
+    pt = lambda dlog: ec.scalar_mul(F, dlog, c.g1)
+    for name, g_, w_ in (("L", got.LRO[0], want.L), ("Z", got.Z, want.Z), ("H1", got.H[0], want.H[0]),
+                         ("H3", got.H[2], want.H[2]), ("lin", got.LinearizedDigest, want.lin),
+                         ("batch", got.BatchedProofH, want.batch_opening), ("zopen", got.ZShiftedOpeningH, want.z_opening)):
+        assert jac_to_affine(c, 1, g_) == pt(w_), name
+    for j in range(n_commit):
+        assert jac_to_affine(c, 1, got.Bsb22Commitments[j]) == pt(want.bsb22[j])
+    assert got.BatchedClaimedValues == want.claimed and len(want.claimed) == 6 + n_commit
+    assert got.ZShiftedClaimedValue == want.zu
+    assert calls.count("bsb22") == 4 * n_commit
+    with pytest.raises(ValueError):
+        b200_plonk.Prove(pk, pe(l), pe(rr), pe(o), b200_plonk.Challenges(gamma=1, beta=2, alpha=3, zeta=4, v=5))
