@@ -19,6 +19,7 @@ struct b200_pk_s {
   std::vector<uint8_t> alpha, beta, delta, beta2, delta2;
   uint32_t* d_idx_a = nullptr;
   uint32_t* d_idx_b = nullptr;
+  uint32_t* d_idx_k = nullptr;   // only for keys with BSB22 commitments: private wires minus the committed ones
   size_t n_a = 0, n_b = 0, nb_wires = 0, nb_public = 0;   // n_a/n_b: THIS shard's counts
   size_t off_z = 0, cnt_z = 0, off_k = 0, cnt_k = 0;       // this shard's slice of Z and K
   int shard_rank = 0, shard_world = 1;
@@ -65,8 +66,9 @@ int32_t b200_groth16_pk_load(int32_t dev, const b200_groth16_pk_desc* d, b200_pk
   if (d->domain_size == 0 || (d->domain_size & (d->domain_size - 1))) return set_error("pk_load: domain size must be a power of two");
   if (d->n_z + 1 != d->domain_size) return set_error("pk_load: len(G1.Z) must be domain size - 1");
   if (d->n_b2 != d->n_b) return set_error("pk_load: len(G2.B) != len(G1.B)");
-  if (d->nb_public > d->nb_wires || d->n_k != d->nb_wires - d->nb_public)
-    return set_error("pk_load: len(G1.K) must equal nb_wires - nb_public (BSB22 commitments are not supported by this entry point)");
+  if (d->n_k_removed && !d->k_removed) return set_error("pk_load: null k_removed");
+  if (d->nb_public > d->nb_wires || d->n_k + d->n_k_removed != d->nb_wires - d->nb_public)
+    return set_error("pk_load: len(G1.K) must equal nb_wires - nb_public - (number of committed private wires)");
   std::unique_ptr<b200_pk_s> pk(new b200_pk_s());
   pk->dev = dev; pk->curve = d->curve; pk->n = d->domain_size;
   while ((1ull << pk->logn) < pk->n) pk->logn++;
@@ -99,6 +101,19 @@ int32_t b200_groth16_pk_load(int32_t dev, const b200_groth16_pk_desc* d, b200_pk
   shard(d->n_b, &off_b, &cnt_b);
   shard(d->n_z, &pk->off_z, &pk->cnt_z);
   shard(d->n_k, &pk->off_k, &pk->cnt_k);
+  // Krs scalars: private wires minus the committed ones (filterHeap, prove.go:321-344); only built when needed,
+  // otherwise the K MSM reads the contiguous tail of the wire vector
+  std::vector<uint32_t> ik;
+  if (d->n_k_removed) {
+    size_t r_ = 0;
+    for (size_t i = d->nb_public; i < d->nb_wires; i++) {
+      while (r_ < d->n_k_removed && d->k_removed[r_] < i) r_++;
+      if (r_ < d->n_k_removed && d->k_removed[r_] == i) continue;
+      ik.push_back((uint32_t)i);
+    }
+    if (ik.size() != d->n_k) return set_error("pk_load: k_removed must be sorted, distinct private wire indices");
+    ik = std::vector<uint32_t>(ik.begin() + pk->off_k, ik.begin() + pk->off_k + pk->cnt_k);
+  }
   ia = std::vector<uint32_t>(ia.begin() + off_a, ia.begin() + off_a + cnt_a);
   ib = std::vector<uint32_t>(ib.begin() + off_b, ib.begin() + off_b + cnt_b);
   pk->n_a = cnt_a; pk->n_b = cnt_b;
@@ -119,6 +134,7 @@ int32_t b200_groth16_pk_load(int32_t dev, const b200_groth16_pk_desc* d, b200_pk
   };
   PK_TRY(up(ia, &raw->d_idx_a));
   PK_TRY(up(ib, &raw->d_idx_b));
+  if (d->n_k_removed) PK_TRY(up(ik, &raw->d_idx_k));
 #undef PK_TRY
   *out = pk.release();
   return 0;
@@ -132,7 +148,7 @@ int32_t b200_groth16_pk_free(b200_pk_t pk) {
   cudaStreamSynchronize(ctx->stream);
   b200_table_free(pk->A); b200_table_free(pk->B1); b200_table_free(pk->Z); b200_table_free(pk->K); b200_table_free(pk->B2);
   b200_ntt_domain_free(pk->dom);
-  cudaFree(pk->d_idx_a); cudaFree(pk->d_idx_b);
+  cudaFree(pk->d_idx_a); cudaFree(pk->d_idx_b); cudaFree(pk->d_idx_k);
   delete pk;
   return 0;
   GUARD_END
@@ -191,7 +207,14 @@ int32_t b200_groth16_msms(b200_pk_t pk, const void* wires, const void* a, const 
   rc = lap("msm A"); if (rc) return rc;
   rc = msm_on_stream(ctx, pk->B1, 0, pk->n_b, d_wb, res + 1 * j1, nullptr, true); if (rc) return rc;
   rc = lap("msm B1"); if (rc) return rc;
-  rc = msm_on_stream(ctx, pk->K, 0, pk->cnt_k, (char*)d_w + (pk->nb_public + pk->off_k) * fb, res + 3 * j1, nullptr, true); if (rc) return rc;
+  const void* k_scalars = (char*)d_w + (pk->nb_public + pk->off_k) * fb;
+  if (pk->d_idx_k) {       // committed wires filtered out (BSB22)
+    void* d_wk;
+    CK(bufs.get(&d_wk, pk->cnt_k * fb));
+    CK(pk->fr->gather(st, d_wk, d_w, pk->d_idx_k, pk->cnt_k));
+    k_scalars = d_wk;
+  }
+  rc = msm_on_stream(ctx, pk->K, 0, pk->cnt_k, k_scalars, res + 3 * j1, nullptr, true); if (rc) return rc;
   rc = lap("msm K"); if (rc) return rc;
   rc = msm_on_stream(ctx, pk->B2, 0, pk->n_b, d_wb, res + 4 * j1, nullptr, true); if (rc) return rc;
   rc = lap("msm B2 (G2)"); if (rc) return rc;

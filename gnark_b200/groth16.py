@@ -141,8 +141,11 @@ class ProvingKey:
 
     @classmethod
     def from_arrays(cls, curve, domain_size, alpha, beta, delta, A, B, Z, K, beta2, delta2, B2, inf_a, inf_b,
-                    nb_public, domain_gen=None, coset_gen=None):
+                    nb_public, domain_gen=None, coset_gen=None, committed_private_wires=()):
+        """committed_private_wires: sorted absolute indices of the private wires committed by BSB22 / Pedersen
+        commitments (internal.ConcatAll(commitmentInfo.PrivateCommitted...), prove.go:231-235): K has no base for them"""
         pk = cls(curve)
+        pk.k_removed = np.ascontiguousarray(sorted(int(x) for x in committed_private_wires), dtype=np.uint32)
         pk.domain_size = int(domain_size)
         pk.domain_gen, pk.coset_gen = domain_gen, coset_gen
         c = np.ascontiguousarray
@@ -180,6 +183,9 @@ class ProvingKey:
         d.g2_b, d.n_b2 = p(self.G2_B), self._count(self.G2_B, 2)
         d.infinity_a, d.infinity_b = p(self.InfinityA), p(self.InfinityB)
         d.nb_wires, d.nb_public = self.nb_wires, self.nb_public
+        kr = getattr(self, "k_removed", None)
+        if kr is not None and kr.size:
+            d.k_removed, d.n_k_removed = p(kr), kr.size
         d.flags = _lib.TABLE_PRECOMP if cfg.Precompute else 0
         d.shard_rank, d.shard_world = cfg.ShardRank, cfg.ShardWorld
         h = ctypes.c_void_p(0)

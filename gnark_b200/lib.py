@@ -76,6 +76,8 @@ class Groth16PkDesc(ctypes.Structure):
         ("flags", ctypes.c_int32),
         ("shard_rank", ctypes.c_int32),
         ("shard_world", ctypes.c_int32),
+        ("k_removed", ctypes.c_void_p),
+        ("n_k_removed", ctypes.c_size_t),
     ]
 
 

@@ -294,6 +294,13 @@ typedef struct {
    * shards of every table; 0/0 or world <= 1 = the whole key. */
   int32_t shard_rank;
   int32_t shard_world;
+  /* BSB22 commitments: the private wires committed by Pedersen commitments are excluded from Krs
+   * (filterHeap, backend/groth16/bn254/prove.go:231-239,321-344; pk.G1.K has no base for them):
+   * sorted absolute wire indices, internal.ConcatAll(commitmentInfo.PrivateCommitted...); n_k then equals
+   * nb_wires - nb_public - n_k_removed.  NULL / 0 = no commitments.  The commitment MSMs themselves
+   * (CommitmentKeys[i].Commit / ProveKnowledge, prove.go:84,114) go through b200_table_upload + b200_msm_g1. */
+  const uint32_t* k_removed;
+  size_t n_k_removed;
 } b200_groth16_pk_desc;
 
 int32_t b200_groth16_pk_load(int32_t dev, const b200_groth16_pk_desc* desc, b200_pk_t* out);
