@@ -1,6 +1,6 @@
 """The C++ PLONK orchestration (gnark_b200/csrc/plonk_host.cu: b200_plonk_pk_load / b200_plonk_prove) on the CPU.
 plonk_host.cu is compiled as plain C++ against host stand-ins for the device entry points it calls
-(tests/mock/mock_capi.cpp -> libgb200_plonkmock.so; test infrastructure, BN254 only), and its ten digests and
+(tests/mock/mock_capi.cpp -> libgb200_plonkmock.so; test infrastructure, BN254 and BLS12-381), and its ten digests and
 seven opened values are compared with the big-int oracle prover (oracle/plonk_prover.py) under the same injected
 challenges and blinding.  Together with the hardware parity tests of each entry point (tests/test_gpu_plonk.py)
 this pins everything but the GPU plumbing of tests/test_gpu_zz_late.py::test_plonk_prove_c_abi_vs_oracle."""
@@ -38,9 +38,9 @@ def mock():
     return m
 
 
-@pytest.mark.parametrize("logn", (3, 5))
-def test_plonk_host_orchestration_vs_oracle(mock, logn):
-    c = CURVES["bn254"]
+@pytest.mark.parametrize("cname,logn", [("bn254", 3), ("bn254", 5), ("bls12-381", 4)])
+def test_plonk_host_orchestration_vs_oracle(mock, cname, logn):
+    c = CURVES[cname]
     rng = random.Random(3000 + logn)
     r, L = c.r, c.fr_limbs
     n = 1 << logn
