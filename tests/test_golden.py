@@ -51,3 +51,35 @@ def test_oracles_reproduce_golden(c):
     pr = g16.prove_dlog(c, cs, pk, W, H(gc["r"]), H(gc["s"]))
     assert [pr.ar, pr.bs, pr.krs] == [H(gc["ar"]), H(gc["bs"]), H(gc["krs"])]
     assert pr.h == [H(v) for v in gc["h_bitreversed"]]
+
+
+PLONK_KAT = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "kat_plonk_v1.json")))
+
+
+def _plonk_case(cname):
+    from oracle import plonk_prover as pp
+    c = CURVES[cname]
+    e = PLONK_KAT["curves"][cname]
+    HL = lambda v: [H(x) for x in v]
+    k = e["circuit"]
+    circ = pp.Circuit(n=e["n"], ql=HL(k["ql"]), qr=HL(k["qr"]), qm=HL(k["qm"]), qo=HL(k["qo"]), qk=HL(k["qk"]),
+                      perm=list(k["perm"]), qcp=[HL(v) for v in k["qcp"]])
+    w = e["witness"]
+    x = e["challenges"]
+    ch = pp.Challenges(gamma=H(x["gamma"]), beta=H(x["beta"]), alpha=H(x["alpha"]), zeta=H(x["zeta"]), v=H(x["v"]),
+                       bl=HL(x["bl"]), br=HL(x["br"]), bo=HL(x["bo"]), bz=HL(x["bz"]))
+    return c, circ, HL(w["l"]), HL(w["r"]), HL(w["o"]), [HL(v) for v in w["pi2"]], ch, H(e["tau"]), e["proof"]
+
+
+@pytest.mark.parametrize("cname", ["bn254", "bls12-381"])
+def test_oracle_prover_reproduces_plonk_golden(cname):
+    """the oracle PLONK prover (with one BSB22 commitment gate) on the committed instance: every digest and opened value"""
+    from oracle import plonk_prover as pp
+    c, circ, l, rr, o, pi2, ch, tau, want = _plonk_case(cname)
+    pr = pp.prove(c, circ, l, rr, o, ch, tau, pi2=pi2)
+    assert pp.verify(c, circ, pr, ch, tau)
+    HL = lambda v: [H(x) for x in v]
+    assert [pr.L, pr.R, pr.O, pr.Z] == [H(want[k]) for k in ("L", "R", "O", "Z")]
+    assert pr.H == HL(want["H"]) and pr.lin == H(want["lin"])
+    assert pr.batch_opening == H(want["batch_opening"]) and pr.z_opening == H(want["z_opening"])
+    assert pr.bsb22 == HL(want["bsb22"]) and pr.claimed == HL(want["claimed"]) and pr.zu == H(want["zu"])

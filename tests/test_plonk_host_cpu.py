@@ -158,3 +158,51 @@ def test_plonk_host_bsb22_commitments(mock, n_commit):
     got = ff.unpack_elements(vals, r, L)
     assert got[:6] + got[7:] == want.claimed and got[6] == want.zu
     assert mock.b200_plonk_pk_free(h) == 0
+
+
+@pytest.mark.parametrize("cname", ["bn254", "bls12-381"])
+def test_plonk_host_reproduces_golden(mock, cname):
+    """the committed PLONK known-answer vector (tests/golden/kat_plonk_v1.json: 8 rows, one BSB22 gate) through the C++
+    orchestration on host stand-ins"""
+    from test_golden import _plonk_case
+    c, circ, l, rr, o, pi2, ch, tau, want = _plonk_case(cname)
+    r, L = c.r, c.fr_limbs
+    n, logn = circ.n, circ.n.bit_length() - 1
+    pe = lambda v: np.ascontiguousarray(ff.pack_elements(v, r, L))
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    srs = np.ascontiguousarray(corelib.fixed_base(c, 1, ec.pack_points(c, 1, [c.g1]), pe([pow(tau, i, r) for i in range(n + 3)])))
+    keep = {k: pe(getattr(circ, k)) for k in ("ql", "qr", "qm", "qo", "qk")}
+    perm = np.ascontiguousarray(np.array(circ.perm, dtype=np.int64))
+    qcp = [pe(v) for v in circ.qcp]
+    qarr = (ctypes.c_void_p * len(qcp))(*[a.ctypes.data for a in qcp])
+    d = b200.PlonkPkDesc()
+    d.log2n = logn
+    for k, a in keep.items():
+        setattr(d, k, P(a).value)
+    d.perm, d.srs_canonical = P(perm).value, P(srs).value
+    d.n_qcp, d.qcp = len(qcp), ctypes.cast(qarr, ctypes.POINTER(ctypes.c_void_p))
+    h = ctypes.c_void_p(0)
+    assert mock.b200_plonk_pk_load(0, c.curve_id, ctypes.byref(d), ctypes.byref(h)) == 0, mock.b200_last_error()
+    sc = {k: pe(v) for k, v in (("gamma", [ch.gamma]), ("beta", [ch.beta]), ("alpha", [ch.alpha]), ("zeta", [ch.zeta]),
+                                ("v", [ch.v]), ("bl", ch.bl), ("br", ch.br), ("bo", ch.bo), ("bz", ch.bz))}
+    cs = b200.PlonkChallenges()
+    for k, a in sc.items():
+        setattr(cs, k, P(a).value)
+    pi2a = [pe(v) for v in pi2]
+    parr = (ctypes.c_void_p * len(pi2a))(*[a.ctypes.data for a in pi2a])
+    bsb = np.zeros((len(pi2a), 3 * c.fp_limbs), dtype=np.uint64)
+    cs.pi2, cs.out_bsb22 = ctypes.cast(parr, ctypes.POINTER(ctypes.c_void_p)), P(bsb).value
+    pts = np.zeros((10, 3 * c.fp_limbs), dtype=np.uint64)
+    vals = np.zeros((7 + len(pi2a), L), dtype=np.uint64)
+    L_, R_, O_ = pe(l), pe(rr), pe(o)
+    assert mock.b200_plonk_prove(h, P(L_), P(R_), P(O_), ctypes.byref(cs), P(pts), P(vals)) == 0, mock.b200_last_error()
+    F = ff.Fp(c.p)
+    Hx = lambda s_: int(s_, 16)
+    dl = [Hx(want[k]) for k in ("L", "R", "O", "Z")] + [Hx(x) for x in want["H"]] + [Hx(want["lin"]), Hx(want["batch_opening"]),
+                                                                                    Hx(want["z_opening"])]
+    for k in range(10):
+        assert jac_to_affine(c, 1, pts[k]) == ec.scalar_mul(F, dl[k], c.g1), k
+    assert jac_to_affine(c, 1, bsb[0]) == ec.scalar_mul(F, Hx(want["bsb22"][0]), c.g1)
+    got = ff.unpack_elements(vals, r, L)
+    assert got[:6] + got[7:] == [Hx(x) for x in want["claimed"]] and got[6] == Hx(want["zu"])
+    assert mock.b200_plonk_pk_free(h) == 0
