@@ -159,7 +159,7 @@ int32_t b200_device_count(int32_t* out) {
 int32_t b200_init(int32_t n_dev, const int32_t* dev_ids) {
   GUARD_BEGIN
   if (n_dev <= 0 || !dev_ids) { DeviceCtx* c; return device_ctx(0, &c); }
-  for (int i = 0; i < n_dev; i++) { DeviceCtx* c; int32_t rc = device_ctx(dev_ids[i], &c); if (rc) return rc; }
+  for (int i = 0; i < n_dev; i++) { GB_DEVICE(c, dev_ids[i]); [[maybe_unused]] int32_t rc = 0; }
   return 0;
   GUARD_END
 }
@@ -179,7 +179,13 @@ int32_t b200_shutdown(void) {
     cudaEventDestroy(c.copy_ev);
     cudaEventDestroy(c.fork_ev);
     cudaEventDestroy(c.tail_ev);
-    c = DeviceCtx();
+    cudaStreamDestroy(c.aux_stream);
+    cudaEventDestroy(c.aux_fork_ev);
+    cudaEventDestroy(c.aux_join_ev);
+    // back to the initial state (the lock itself stays)
+    c.ready = false; c.tail_pending = false;
+    c.own_stream = c.stream = c.tail_stream = c.copy_stream = c.aux_stream = nullptr;
+    c.copy_ev = c.fork_ev = c.tail_ev = c.aux_fork_ev = c.aux_join_ev = nullptr;
   }
   return 0;
   GUARD_END
@@ -187,7 +193,7 @@ int32_t b200_shutdown(void) {
 
 int32_t b200_set_stream(int32_t dev, void* stream) {
   GUARD_BEGIN
-  DeviceCtx* c; int32_t rc = device_ctx(dev, &c); if (rc) return rc;
+  GB_DEVICE(c, dev); [[maybe_unused]] int32_t rc = 0;
   c->stream = stream ? reinterpret_cast<cudaStream_t>(stream) : c->own_stream;
   return 0;
   GUARD_END
@@ -195,7 +201,7 @@ int32_t b200_set_stream(int32_t dev, void* stream) {
 
 int32_t b200_sync(int32_t dev) {
   GUARD_BEGIN
-  DeviceCtx* c; int32_t rc = device_ctx(dev, &c); if (rc) return rc;
+  GB_DEVICE(c, dev); [[maybe_unused]] int32_t rc = 0;
   rc = msm_join(c); if (rc) return rc;
   CK(cudaStreamSynchronize(c->stream));
   return 0;
@@ -204,14 +210,14 @@ int32_t b200_sync(int32_t dev) {
 
 int32_t b200_alloc(int32_t dev, size_t bytes, void** out) {
   GUARD_BEGIN
-  DeviceCtx* c; int32_t rc = device_ctx(dev, &c); if (rc) return rc;
+  GB_DEVICE(c, dev); [[maybe_unused]] int32_t rc = 0;
   CK(cudaMalloc(out, bytes ? bytes : 1));
   return 0;
   GUARD_END
 }
 int32_t b200_free(int32_t dev, void* p) {
   GUARD_BEGIN
-  DeviceCtx* c; int32_t rc = device_ctx(dev, &c); if (rc) return rc;
+  GB_DEVICE(c, dev); [[maybe_unused]] int32_t rc = 0;
   CK(cudaStreamSynchronize(c->stream));
   CK(cudaFree(p));
   return 0;
@@ -219,7 +225,7 @@ int32_t b200_free(int32_t dev, void* p) {
 }
 int32_t b200_h2d(int32_t dev, void* dst, const void* src, size_t bytes) {
   GUARD_BEGIN
-  DeviceCtx* c; int32_t rc = device_ctx(dev, &c); if (rc) return rc;
+  GB_DEVICE(c, dev); [[maybe_unused]] int32_t rc = 0;
   CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
   CK(cudaStreamSynchronize(c->stream));  // host pointer is only borrowed for the call
   return 0;
@@ -227,7 +233,7 @@ int32_t b200_h2d(int32_t dev, void* dst, const void* src, size_t bytes) {
 }
 int32_t b200_d2h(int32_t dev, void* dst, const void* src, size_t bytes) {
   GUARD_BEGIN
-  DeviceCtx* c; int32_t rc = device_ctx(dev, &c); if (rc) return rc;
+  GB_DEVICE(c, dev); [[maybe_unused]] int32_t rc = 0;
   rc = msm_join(c); if (rc) return rc;
   CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
@@ -251,7 +257,7 @@ int32_t b200_host_free(void* p) {
 int32_t b200_table_upload(int32_t dev, int32_t curve, int32_t group, const void* points, size_t n, int32_t flags,
                           b200_table_t* out) {
   GUARD_BEGIN
-  DeviceCtx* ctx; int32_t rc = device_ctx(dev, &ctx); if (rc) return rc;
+  GB_DEVICE(ctx, dev); [[maybe_unused]] int32_t rc = 0;
   const MsmOps* ops = get_msm_ops(curve, group);
   if (!ops) return set_error("table_upload: unsupported curve/group");
   if (n && !points) return set_error("table_upload: null points");
@@ -302,7 +308,7 @@ int32_t b200_table_upload(int32_t dev, int32_t curve, int32_t group, const void*
 int32_t b200_table_free(b200_table_t t) {
   GUARD_BEGIN
   if (!t) return 0;
-  DeviceCtx* ctx; int32_t rc = device_ctx(t->dev, &ctx); if (rc) return rc;
+  GB_DEVICE(ctx, t->dev); [[maybe_unused]] int32_t rc = 0;
   CK(cudaStreamSynchronize(ctx->stream));
   CK(cudaFree(t->d_points));
   if (t->d_points52) CK(cudaFree(t->d_points52));
@@ -327,7 +333,7 @@ int32_t b200_table_info(b200_table_t t, size_t* n, int32_t* c, int32_t* nwin, in
 int32_t b200_msm_async(b200_table_t t, size_t off, size_t n, const void* d_scalars, void* d_out) {
   GUARD_BEGIN
   if (!t) return set_error("msm: null table");
-  DeviceCtx* ctx; int32_t rc = device_ctx(t->dev, &ctx); if (rc) return rc;
+  GB_DEVICE(ctx, t->dev); [[maybe_unused]] int32_t rc = 0;
   return msm_on_stream(ctx, t, off, n, d_scalars, d_out);
   GUARD_END
 }
@@ -336,7 +342,7 @@ int32_t b200_fixed_base_batch(int32_t dev, int32_t curve, int32_t group, const v
                               const void* scalars, int32_t scalars_on_device, size_t n, void* out_affine,
                               int32_t out_on_device) {
   GUARD_BEGIN
-  DeviceCtx* ctx; int32_t rc = device_ctx(dev, &ctx); if (rc) return rc;
+  GB_DEVICE(ctx, dev); [[maybe_unused]] int32_t rc = 0;
   const MsmOps* ops = get_msm_ops(curve, group);
   if (!ops) return set_error("fixed_base_batch: unsupported curve/group");
   if (!base_affine || (n && (!scalars || !out_affine))) return set_error("fixed_base_batch: null argument");
@@ -368,7 +374,7 @@ int32_t b200_fixed_base_batch(int32_t dev, int32_t curve, int32_t group, const v
 int32_t b200_msm_profile(b200_table_t t, size_t off, size_t n, const void* d_scalars, void* d_out, float* stage_ms) {
   GUARD_BEGIN
   if (!t || !stage_ms) return set_error("msm_profile: null argument");
-  DeviceCtx* ctx; int32_t rc = device_ctx(t->dev, &ctx); if (rc) return rc;
+  GB_DEVICE(ctx, t->dev); [[maybe_unused]] int32_t rc = 0;
   cudaEvent_t ev[8];
   for (int k = 0; k < 8; k++) CK(cudaEventCreate(&ev[k]));
   rc = msm_on_stream(ctx, t, off, n, d_scalars, d_out, ev);
@@ -385,13 +391,13 @@ int32_t b200_msm_profile(b200_table_t t, size_t off, size_t n, const void* d_sca
 int32_t b200_msm_pipelined(b200_table_t t, size_t off, size_t n, const void* d_scalars, void* d_out) {
   GUARD_BEGIN
   if (!t) return set_error("msm: null table");
-  DeviceCtx* ctx; int32_t rc = device_ctx(t->dev, &ctx); if (rc) return rc;
+  GB_DEVICE(ctx, t->dev); [[maybe_unused]] int32_t rc = 0;
   return msm_on_stream(ctx, t, off, n, d_scalars, d_out, nullptr, true);
   GUARD_END
 }
 int32_t b200_msm_join(int32_t dev) {
   GUARD_BEGIN
-  DeviceCtx* ctx; int32_t rc = device_ctx(dev, &ctx); if (rc) return rc;
+  GB_DEVICE(ctx, dev); [[maybe_unused]] int32_t rc = 0;
   return msm_join(ctx);
   GUARD_END
 }
@@ -400,7 +406,7 @@ int32_t b200_msm(b200_table_t t, size_t off, size_t n, const void* scalars, int3
   GUARD_BEGIN
   if (!t) return set_error("msm: null table");
   if (n && !scalars) return set_error("msm: null scalars");
-  DeviceCtx* ctx; int32_t rc = device_ctx(t->dev, &ctx); if (rc) return rc;
+  GB_DEVICE(ctx, t->dev); [[maybe_unused]] int32_t rc = 0;
   void* d_sc = nullptr;
   void* d_out = nullptr;
   CK(cudaMallocAsync(&d_out, t->ops->jac_bytes, ctx->stream));
@@ -432,7 +438,7 @@ int32_t b200_msm_submit(b200_table_t t, size_t off, size_t n, const void* scalar
   GUARD_BEGIN
   if (!t) return set_error("msm_submit: null table");
   if (!out_host || (n && !scalars_host)) return set_error("msm_submit: null argument");
-  DeviceCtx* ctx; int32_t rc = device_ctx(t->dev, &ctx); if (rc) return rc;
+  GB_DEVICE(ctx, t->dev); [[maybe_unused]] int32_t rc = 0;
   void* d_sc = nullptr;
   void* d_out = nullptr;
   CK(cudaMallocAsync(&d_out, t->ops->jac_bytes, ctx->stream));
@@ -472,7 +478,7 @@ int32_t b200_msm_g2(b200_table_t t, size_t off, size_t n, const void* s, int32_t
 int32_t b200_ntt_domain_new(int32_t dev, int32_t curve, uint32_t log2n, const void* gen, const void* coset,
                             b200_domain_t* out) {
   GUARD_BEGIN
-  DeviceCtx* ctx; int32_t rc = device_ctx(dev, &ctx); if (rc) return rc;
+  GB_DEVICE(ctx, dev); [[maybe_unused]] int32_t rc = 0;
   const NttOps* ops = get_ntt_ops(curve);
   if (!ops) return set_error("ntt_domain_new: unsupported curve");
   if ((int)log2n > ops->two_adicity || log2n > 30)
@@ -490,7 +496,7 @@ int32_t b200_ntt_domain_new(int32_t dev, int32_t curve, uint32_t log2n, const vo
 int32_t b200_ntt_domain_free(b200_domain_t d) {
   GUARD_BEGIN
   if (!d) return 0;
-  DeviceCtx* ctx; int32_t rc = device_ctx(d->dev, &ctx); if (rc) return rc;
+  GB_DEVICE(ctx, d->dev); [[maybe_unused]] int32_t rc = 0;
   CK(cudaStreamSynchronize(ctx->stream));
   d->ops->domain_free(d->impl);
   delete d;
@@ -502,7 +508,7 @@ int32_t b200_ntt_async(b200_domain_t d, void* d_data, int32_t inverse, int32_t d
   GUARD_BEGIN
   if (!d) return set_error("ntt: null domain");
   if (decimation != B200_DIF && decimation != B200_DIT) return set_error("ntt: decimation must be DIF or DIT");
-  DeviceCtx* ctx; int32_t rc = device_ctx(d->dev, &ctx); if (rc) return rc;
+  GB_DEVICE(ctx, d->dev); [[maybe_unused]] int32_t rc = 0;
   CK(d->ops->ntt(ctx->stream, d->impl, d_data, inverse, decimation, on_coset));
   return 0;
   GUARD_END
@@ -512,7 +518,7 @@ int32_t b200_ntt(b200_domain_t d, void* data, int32_t on_dev, int32_t inverse, i
   GUARD_BEGIN
   if (!d) return set_error("ntt: null domain");
   if (decimation != B200_DIF && decimation != B200_DIT) return set_error("ntt: decimation must be DIF or DIT");
-  DeviceCtx* ctx; int32_t rc = device_ctx(d->dev, &ctx); if (rc) return rc;
+  GB_DEVICE(ctx, d->dev); [[maybe_unused]] int32_t rc = 0;
   const size_t bytes = ((size_t)1 << d->logn) * d->ops->fr_bytes;
   void* buf = data;
   if (!on_dev) {
@@ -535,7 +541,7 @@ int32_t b200_groth16_compute_h(b200_domain_t d, const void* a, const void* b, co
                                int32_t in_dev, void* h_out, int32_t out_dev) {
   GUARD_BEGIN
   if (!d) return set_error("compute_h: null domain");
-  DeviceCtx* ctx; int32_t rc = device_ctx(d->dev, &ctx); if (rc) return rc;
+  GB_DEVICE(ctx, d->dev); [[maybe_unused]] int32_t rc = 0;
   const size_t n = (size_t)1 << d->logn;
   if (len > n) return set_error("compute_h: len exceeds the domain");
   const size_t fb = d->ops->fr_bytes;
@@ -561,7 +567,7 @@ int32_t b200_groth16_compute_h(b200_domain_t d, const void* a, const void* b, co
 // ---- vector ops -----------------------------------------------------------------
 int32_t b200_vec_op(int32_t dev, int32_t curve, int32_t op, void* out, const void* a, const void* b, size_t n) {
   GUARD_BEGIN
-  DeviceCtx* ctx; int32_t rc = device_ctx(dev, &ctx); if (rc) return rc;
+  GB_DEVICE(ctx, dev); [[maybe_unused]] int32_t rc = 0;
   const NttOps* ops = get_ntt_ops(curve);
   if (!ops) return set_error("vec_op: unsupported curve");
   if (op < 0 || op > 2) return set_error("vec_op: unknown op");
@@ -571,7 +577,7 @@ int32_t b200_vec_op(int32_t dev, int32_t curve, int32_t op, void* out, const voi
 }
 int32_t b200_vec_bit_reverse(int32_t dev, int32_t curve, void* data, uint32_t log2n) {
   GUARD_BEGIN
-  DeviceCtx* ctx; int32_t rc = device_ctx(dev, &ctx); if (rc) return rc;
+  GB_DEVICE(ctx, dev); [[maybe_unused]] int32_t rc = 0;
   const NttOps* ops = get_ntt_ops(curve);
   if (!ops) return set_error("vec_bit_reverse: unsupported curve");
   CK(ops->bit_reverse(ctx->stream, data, log2n));
@@ -580,7 +586,7 @@ int32_t b200_vec_bit_reverse(int32_t dev, int32_t curve, void* data, uint32_t lo
 }
 int32_t b200_vec_scale_powers(int32_t dev, int32_t curve, void* data, size_t n, const void* s, const void* g) {
   GUARD_BEGIN
-  DeviceCtx* ctx; int32_t rc = device_ctx(dev, &ctx); if (rc) return rc;
+  GB_DEVICE(ctx, dev); [[maybe_unused]] int32_t rc = 0;
   const NttOps* ops = get_ntt_ops(curve);
   if (!ops) return set_error("vec_scale_powers: unsupported curve");
   CK(ops->scale_powers(ctx->stream, data, n, s, g));
@@ -590,7 +596,7 @@ int32_t b200_vec_scale_powers(int32_t dev, int32_t curve, void* data, size_t n, 
 
 int32_t b200_vec_batch_invert(int32_t dev, int32_t curve, void* data, size_t n) {
   GUARD_BEGIN
-  DeviceCtx* ctx; int32_t rc = device_ctx(dev, &ctx); if (rc) return rc;
+  GB_DEVICE(ctx, dev); [[maybe_unused]] int32_t rc = 0;
   const NttOps* ops = get_ntt_ops(curve);
   if (!ops) return set_error("vec_batch_invert: unsupported curve");
   CK(ops->batch_invert(ctx->stream, data, n));
@@ -600,7 +606,7 @@ int32_t b200_vec_batch_invert(int32_t dev, int32_t curve, void* data, size_t n) 
 
 int32_t b200_vec_axpy(int32_t dev, int32_t curve, void* y, const void* a, const void* x, size_t n) {
   GUARD_BEGIN
-  DeviceCtx* ctx; int32_t rc = device_ctx(dev, &ctx); if (rc) return rc;
+  GB_DEVICE(ctx, dev); [[maybe_unused]] int32_t rc = 0;
   const NttOps* ops = get_ntt_ops(curve);
   if (!ops) return set_error("vec_axpy: unsupported curve");
   if (!a || (n && (!y || !x))) return set_error("vec_axpy: null argument");
@@ -610,7 +616,7 @@ int32_t b200_vec_axpy(int32_t dev, int32_t curve, void* y, const void* a, const 
 }
 int32_t b200_vec_scan(int32_t dev, int32_t curve, int32_t op, void* data, size_t n, int32_t exclusive) {
   GUARD_BEGIN
-  DeviceCtx* ctx; int32_t rc = device_ctx(dev, &ctx); if (rc) return rc;
+  GB_DEVICE(ctx, dev); [[maybe_unused]] int32_t rc = 0;
   const NttOps* ops = get_ntt_ops(curve);
   if (!ops) return set_error("vec_scan: unsupported curve");
   if (op != B200_SCAN_PRODUCT && op != B200_SCAN_SUM) return set_error("vec_scan: unknown op");
@@ -622,14 +628,14 @@ int32_t b200_plonk_build_z(b200_domain_t d0, const void* l, const void* r, const
                            const void* beta, const void* gamma, void* z) {
   GUARD_BEGIN
   if (!d0 || !l || !r || !o || !perm || !beta || !gamma || !z) return set_error("plonk_build_z: null argument");
-  DeviceCtx* ctx; int32_t rc = device_ctx(d0->dev, &ctx); if (rc) return rc;
+  GB_DEVICE(ctx, d0->dev); [[maybe_unused]] int32_t rc = 0;
   CK(d0->ops->plonk_build_z(ctx->stream, d0->impl, l, r, o, perm, beta, gamma, z));
   return 0;
   GUARD_END
 }
 int32_t b200_poly_eval(int32_t dev, int32_t curve, const void* c, size_t n, const void* x, void* out) {
   GUARD_BEGIN
-  DeviceCtx* ctx; int32_t rc = device_ctx(dev, &ctx); if (rc) return rc;
+  GB_DEVICE(ctx, dev); [[maybe_unused]] int32_t rc = 0;
   const NttOps* ops = get_ntt_ops(curve);
   if (!ops) return set_error("poly_eval: unsupported curve");
   if (!x || !out || (n && !c)) return set_error("poly_eval: null argument");
@@ -639,7 +645,7 @@ int32_t b200_poly_eval(int32_t dev, int32_t curve, const void* c, size_t n, cons
 }
 int32_t b200_poly_div_by_linear(int32_t dev, int32_t curve, void* c, size_t n, const void* z, void* rem) {
   GUARD_BEGIN
-  DeviceCtx* ctx; int32_t rc = device_ctx(dev, &ctx); if (rc) return rc;
+  GB_DEVICE(ctx, dev); [[maybe_unused]] int32_t rc = 0;
   const NttOps* ops = get_ntt_ops(curve);
   if (!ops) return set_error("poly_div_by_linear: unsupported curve");
   if (!z || !rem || (n && !c)) return set_error("poly_div_by_linear: null argument");
@@ -653,7 +659,7 @@ int32_t b200_plonk_constraints_coset(b200_domain_t d0, const void* big_coset_gen
                                      const b200_plonk_coset_args* args) {
   GUARD_BEGIN
   if (!d0 || !big_coset_gen || !big_gen || !args) return set_error("plonk_constraints_coset: null argument");
-  DeviceCtx* ctx; int32_t rc = device_ctx(d0->dev, &ctx); if (rc) return rc;
+  GB_DEVICE(ctx, d0->dev); [[maybe_unused]] int32_t rc = 0;
   cudaError_t e = d0->ops->plonk_coset(ctx->stream, d0->impl, big_coset_gen, big_gen, args);
   if (e == cudaErrorInvalidValue) return set_error("plonk_constraints_coset: invalid rho / coset index / blinding length");
   if (e != cudaSuccess) return cuda_fail("plonk_constraints_coset", e);
@@ -664,7 +670,7 @@ int32_t b200_plonk_bsb22_coset(b200_domain_t d0, const void* d_qcp, const void* 
                                void* d_out) {
   GUARD_BEGIN
   if (!d0 || !d_qcp || !d_pi2 || !d_out) return set_error("plonk_bsb22_coset: null argument");
-  DeviceCtx* ctx; int32_t rc = device_ctx(d0->dev, &ctx); if (rc) return rc;
+  GB_DEVICE(ctx, d0->dev); [[maybe_unused]] int32_t rc = 0;
   cudaError_t e = d0->ops->plonk_bsb22(ctx->stream, d0->impl, d_qcp, d_pi2, coset_index, rho, d_out);
   if (e == cudaErrorInvalidValue) return set_error("plonk_bsb22_coset: invalid rho / coset index");
   if (e != cudaSuccess) return cuda_fail("plonk_bsb22_coset", e);
@@ -674,7 +680,7 @@ int32_t b200_plonk_bsb22_coset(b200_domain_t d0, const void* d_qcp, const void* 
 int32_t b200_plonk_divide_by_zh(b200_domain_t d1, uint32_t log_n0, void* d_data) {
   GUARD_BEGIN
   if (!d1 || !d_data) return set_error("plonk_divide_by_zh: null argument");
-  DeviceCtx* ctx; int32_t rc = device_ctx(d1->dev, &ctx); if (rc) return rc;
+  GB_DEVICE(ctx, d1->dev); [[maybe_unused]] int32_t rc = 0;
   cudaError_t e = d1->ops->plonk_divide_by_zh(ctx->stream, d1->impl, log_n0, d_data);
   if (e == cudaErrorInvalidValue) return set_error("plonk_divide_by_zh: invalid domain ratio");
   if (e != cudaSuccess) return cuda_fail("plonk_divide_by_zh", e);

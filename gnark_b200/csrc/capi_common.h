@@ -19,6 +19,11 @@
 namespace gb200 {
 
 struct DeviceCtx {
+  // Host-side state of a device (current stream, fork/join events, pending tail) is shared by every entry point:
+  // each extern "C" function holds this lock from its device_ctx() lookup to its return, so concurrent callers
+  // (goroutines) on ONE device are serialised here instead of by a process-global mutex (the reference:
+  // deviceProveMu, icicle.go:53-60); different devices do not contend.  Recursive: entry points call one another.
+  std::recursive_mutex mu;
   bool ready = false;
   int dev = 0;
   cudaStream_t own_stream = nullptr;
@@ -72,6 +77,15 @@ int32_t msm_join(DeviceCtx* ctx);  // make ctx->stream wait for the pipelined ta
     cudaError_t e_ = (x);                                            \
     if (e_ != cudaSuccess) return gb200::cuda_fail(#x, e_);          \
   } while (0)
+
+// device_ctx() + the per-device lock for the rest of the enclosing scope
+#define GB_DEVICE(ctxvar, dev)                                        \
+  gb200::DeviceCtx* ctxvar;                                           \
+  {                                                                   \
+    int32_t rc_dev_ = gb200::device_ctx((dev), &ctxvar);              \
+    if (rc_dev_) return rc_dev_;                                      \
+  }                                                                   \
+  std::lock_guard<std::recursive_mutex> lock_##ctxvar(ctxvar->mu)
 
 #define GUARD_BEGIN try {
 #define GUARD_END                                                               \

@@ -58,7 +58,7 @@ int32_t b200_groth16_pk_free(b200_pk_t pk);
 int32_t b200_groth16_pk_load(int32_t dev, const b200_groth16_pk_desc* d, b200_pk_t* out) {
   GUARD_BEGIN
   if (!d || !out) return set_error("pk_load: null argument");
-  DeviceCtx* ctx; int32_t rc = device_ctx(dev, &ctx); if (rc) return rc;
+  GB_DEVICE(ctx, dev); [[maybe_unused]] int32_t rc = 0;
   const HostGroupOps* h1 = get_host_group_ops(d->curve, 1);
   const HostGroupOps* h2 = get_host_group_ops(d->curve, 2);
   const NttOps* fr = get_ntt_ops(d->curve);
@@ -144,7 +144,7 @@ int32_t b200_groth16_pk_load(int32_t dev, const b200_groth16_pk_desc* d, b200_pk
 int32_t b200_groth16_pk_free(b200_pk_t pk) {
   GUARD_BEGIN
   if (!pk) return 0;
-  DeviceCtx* ctx; int32_t rc = device_ctx(pk->dev, &ctx); if (rc) return rc;
+  GB_DEVICE(ctx, pk->dev); [[maybe_unused]] int32_t rc = 0;
   cudaStreamSynchronize(ctx->stream);
   b200_table_free(pk->A); b200_table_free(pk->B1); b200_table_free(pk->Z); b200_table_free(pk->K); b200_table_free(pk->B2);
   b200_ntt_domain_free(pk->dom);
@@ -166,7 +166,7 @@ int32_t b200_groth16_msms(b200_pk_t pk, const void* wires, const void* a, const 
   if (!wires || !a || !b || !c || !msm_out) return set_error("prove: null argument");
   if (n_constraints > pk->n) return set_error("prove: more constraints than the domain holds");
   std::lock_guard<std::mutex> lk(pk->mu);
-  DeviceCtx* ctx; int32_t rc = device_ctx(pk->dev, &ctx); if (rc) return rc;
+  GB_DEVICE(ctx, pk->dev); [[maybe_unused]] int32_t rc = 0;
   cudaStream_t st = ctx->stream;
   const size_t fb = pk->fr->fr_bytes;
   const size_t n = pk->n;

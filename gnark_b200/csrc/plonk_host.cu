@@ -83,12 +83,12 @@ struct b200_plonk_session_s {
 namespace {
 
 int32_t d2d(int dev, void* dst, const void* src, size_t bytes) {
-  DeviceCtx* ctx; RC(device_ctx(dev, &ctx));
+  GB_DEVICE(ctx, dev);
   CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
   return 0;
 }
 int32_t dzero(int dev, void* dst, size_t bytes) {
-  DeviceCtx* ctx; RC(device_ctx(dev, &ctx));
+  GB_DEVICE(ctx, dev);
   CK(cudaMemsetAsync(dst, 0, bytes, ctx->stream));
   return 0;
 }
@@ -157,7 +157,7 @@ int32_t b200_plonk_pk_load(int32_t dev, int32_t curve, const b200_plonk_pk_desc*
   const NttOps* ops = get_ntt_ops(curve);
   if (!ops) return set_error("plonk_pk_load: unsupported curve");
   if ((int)d->log2n + 2 > ops->two_adicity || d->log2n > 28) return set_error("plonk_pk_load: domain too large");
-  DeviceCtx* ctx; RC(device_ctx(dev, &ctx));
+  GB_DEVICE(ctx, dev);
   std::unique_ptr<b200_plonk_pk_s, int32_t (*)(b200_plonk_pk_t)> pk(new b200_plonk_pk_s(), &b200_plonk_pk_free);
   pk->dev = dev; pk->curve = curve; pk->logn = d->log2n; pk->n = (size_t)1 << d->log2n;
   pk->fb = ops->fr_bytes;
