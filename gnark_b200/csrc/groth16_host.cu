@@ -3,6 +3,8 @@
 // Prove :784-1360, computeH :1391-1488) and of the CPU prover
 // backend/groth16/bn254/prove.go:52-315, from "solved witness" to "proof points".
 // The R1CS solver (constraint/bn254/solver.go) stays in Go and is out of scope.
+#include <thread>
+
 #include "capi_common.h"
 
 #include <chrono>
@@ -154,6 +156,61 @@ int32_t b200_groth16_pk_free(b200_pk_t pk) {
   GUARD_END
 }
 
+// Upload from PAGEABLE host memory (Go heap slices are pageable): cudaMemcpyAsync would stage it through the driver's
+// single bounce buffer at host-memcpy speed of one thread.  With GB200_STAGE_THREADS=T (opt-in, 0 = off) the source is
+// copied by T threads into two pinned 16 MiB slots and each slot is DMA'd while the other is being filled.
+// Pinned / registered sources (b200_host_alloc) take the plain asynchronous copy.
+static cudaError_t upload_async(cudaStream_t st, void* dst, const void* src, size_t bytes) {
+  static const int T = [] { const char* e = getenv("GB200_STAGE_THREADS"); int v = e ? atoi(e) : 0; return v < 0 ? 0 : (v > 16 ? 16 : v); }();
+  if (T == 0 || bytes < ((size_t)4 << 20)) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st);
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, src) != cudaSuccess) { cudaGetLastError(); return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st); }
+  if (attr.type != cudaMemoryTypeUnregistered) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st);
+  constexpr size_t SLOT = (size_t)16 << 20;
+  struct Ring {
+    void* slot[2] = {nullptr, nullptr};
+    cudaEvent_t done[2] = {nullptr, nullptr};
+    bool used[2] = {false, false};
+    std::mutex mu;
+  };
+  static Ring rings[GB200_MAX_DEVICES];               // per device (pinned slots and events belong to its context)
+  int dev_ = 0;
+  if (cudaGetDevice(&dev_) != cudaSuccess || dev_ < 0 || dev_ >= GB200_MAX_DEVICES)
+    return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st);
+  Ring& ring = rings[dev_];
+  std::lock_guard<std::mutex> lk(ring.mu);              // one upload at a time through the ring
+  for (int k = 0; k < 2; k++)
+    if (!ring.slot[k]) {
+      cudaError_t e = cudaHostAlloc(&ring.slot[k], SLOT, cudaHostAllocDefault);
+      if (e != cudaSuccess) return e;
+      e = cudaEventCreateWithFlags(&ring.done[k], cudaEventDisableTiming);
+      if (e != cudaSuccess) return e;
+    }
+  const char* s = static_cast<const char*>(src);
+  char* d = static_cast<char*>(dst);
+  int k = 0;
+  for (size_t off = 0; off < bytes; off += SLOT, k ^= 1) {
+    const size_t len = bytes - off < SLOT ? bytes - off : SLOT;
+    if (ring.used[k]) { cudaError_t e = cudaEventSynchronize(ring.done[k]); if (e != cudaSuccess) return e; }
+    std::vector<std::thread> th;
+    const size_t part = (len + T - 1) / T;
+    for (int t = 0; t < T; t++) {
+      const size_t lo = (size_t)t * part;
+      if (lo >= len) break;
+      const size_t cnt = len - lo < part ? len - lo : part;
+      char* slot = static_cast<char*>(ring.slot[k]);
+      th.emplace_back([=] { memcpy(slot + lo, s + off + lo, cnt); });
+    }
+    for (auto& x : th) x.join();
+    cudaError_t e = cudaMemcpyAsync(d + off, ring.slot[k], len, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return e;
+    e = cudaEventRecord(ring.done[k], st);
+    if (e != cudaSuccess) return e;
+    ring.used[k] = true;
+  }
+  return cudaSuccess;
+}
+
 static double now_ms() {
   using namespace std::chrono;
   return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
@@ -196,7 +253,7 @@ int32_t b200_groth16_msms(b200_pk_t pk, const void* wires, const void* a, const 
   CK(bufs.get(&d_res, 4 * j1 + j2));
 
   // upload the solution (R1CSSolution{W,A,B,C}); pad A,B,C to the domain (prove.go:356-359)
-  CK(cudaMemcpyAsync(d_w, wires, pk->nb_wires * fb, cudaMemcpyHostToDevice, st));
+  CK(upload_async(st, d_w, wires, pk->nb_wires * fb));
   // wire filtering (prove.go:147-168) and the three MSMs that do not need h start right after W lands
   CK(pk->fr->gather(st, d_wa, d_w, pk->d_idx_a, pk->n_a));
   CK(pk->fr->gather(st, d_wb, d_w, pk->d_idx_b, pk->n_b));
@@ -228,7 +285,7 @@ int32_t b200_groth16_msms(b200_pk_t pk, const void* wires, const void* a, const 
   const void* src[3] = {a, b, c};
   void* dst[3] = {d_a, d_b, d_c};
   for (int k = 0; k < 3; k++) {
-    if (n_constraints) CK(cudaMemcpyAsync(dst[k], src[k], n_constraints * fb, cudaMemcpyHostToDevice, cs));
+    if (n_constraints) CK(upload_async(cs, dst[k], src[k], n_constraints * fb));
     if (n_constraints < n) CK(cudaMemsetAsync((char*)dst[k] + n_constraints * fb, 0, (n - n_constraints) * fb, cs));
   }
   if (!profile) {

@@ -355,3 +355,45 @@ def test_plonk_prove_reproduces_golden(gpu, cname):
     got = ff.unpack_elements(vals, r, L)
     assert got[:6] + got[7:] == [H(x) for x in want["claimed"]] and got[6] == H(want["zu"])
     key.free()
+
+
+@pytest.mark.xfail(strict=False, reason="opt-in upload path written after this round's GPU budget was spent")
+def test_groth16_threaded_staging_of_pageable_inputs(gpu):
+    """GB200_STAGE_THREADS: W, A, B, C uploaded from pageable memory through two pinned slots filled by several
+    threads; the proof must be identical to the plain path (domain 2^18 so that the vectors exceed the 4 MiB
+    threshold and span several 16 MiB slots... 8 MiB each: one slot, ragged)"""
+    import subprocess
+    import sys
+    code = r'''
+import os, sys, random
+import numpy as np
+sys.path.insert(0, os.path.join(os.getcwd(), "tests"))
+from gnark_b200 import groth16 as b200
+from oracle import groth16 as g16
+from oracle.params import CURVES
+from util import build_groth16_pk, pack_solution
+c = CURVES["bn254"]
+m = (1 << 18) - 5
+cs, W = g16.square_chain_r1cs(m), g16.square_chain_witness(c.r, m)
+pk, pkd, _, _ = build_groth16_pk(c, cs, g16.random_toxic(c, 9), 9)
+sol = pack_solution(c, cs, W)
+outs = []
+for threads in ("0", "4"):
+    os.environ["GB200_STAGE_THREADS"] = threads   # read once per process: the second value needs a fresh process
+    it = iter([123456789, 987654321])
+    p = b200.ProveSolution(pk, sol, b200.WithDeviceID(0), b200.WithRandomness(lambda q: next(it)), keep_msm=True)
+    outs.append(np.concatenate([p.msm, p.Ar.reshape(-1), p.Bs.reshape(-1), p.Krs.reshape(-1)]))
+print("EQUAL" if np.array_equal(outs[0], outs[1]) else "DIFFERENT")
+'''
+    # the knob is latched at first use, so each setting runs in its own interpreter and prints a digest
+    res = {}
+    for threads in ("0", "4"):
+        env = dict(os.environ, GB200_STAGE_THREADS=threads)
+        body = code.replace('for threads in ("0", "4"):', 'for threads in ("%s",):' % threads).replace(
+            'print("EQUAL" if np.array_equal(outs[0], outs[1]) else "DIFFERENT")',
+            'import hashlib; print("DIGEST", hashlib.sha256(outs[0].tobytes()).hexdigest())')
+        out = subprocess.run([sys.executable, "-c", body], env=env, capture_output=True, text=True, timeout=900,
+                             cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        assert out.returncode == 0, out.stderr[-2000:]
+        res[threads] = [ln for ln in out.stdout.splitlines() if ln.startswith("DIGEST")][0]
+    assert res["0"] == res["4"]
