@@ -14,6 +14,9 @@ timeout 600 python -m pytest tests/test_gpu_zz_late.py -q -m gpu -rxX 2>&1 | tai
 echo "== 2. bench, 1 GPU (with the asynchronous host path)" | tee -a $OUT/session.log
 timeout 600 python bench.py --steps 20 --warmup 3 --e2e-submit > $OUT/bench_n1.json 2> $OUT/bench_n1.err
 tail -c 2000 $OUT/bench_n1.json | tee -a $OUT/session.log
+# the Groth16 leg's pageable-input variant with threaded staging of the uploads
+GB200_STAGE_THREADS=4 timeout 600 python bench.py --steps 5 --warmup 3 > $OUT/bench_n1_stage4.json 2>> $OUT/bench_n1.err
+python -c "import json;d=json.load(open('$OUT/bench_n1_stage4.json'));print('groth16 with GB200_STAGE_THREADS=4:', d.get('groth16'))" | tee -a $OUT/session.log
 
 echo "== 2b. other configs on this GPU count: sharded MSMs (2^22 total), PLONK building blocks and the end-to-end PLONK prove" | tee -a $OUT/session.log
 timeout 900 python tools/bench_configs.py --total-log 22 --steps 3 > $OUT/configs.jsonl 2>> $OUT/session.err
