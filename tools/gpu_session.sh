@@ -30,6 +30,8 @@ timeout 600 python tools/sweep_msm.py bn254 2 20 --set GB200_MSM_WINDOW=14,16,18
 timeout 600 python tools/sweep_msm.py bn254 1 20 --set GB200_MSM_BATCH_AFFINE=0,2,4,5,6 > $OUT/sweep_bn254_ba.jsonl 2>> $OUT/session.err
 timeout 600 python tools/sweep_msm.py bn254 2 20 --set GB200_MSM_BATCH_AFFINE=0,3,5 > $OUT/sweep_bn254_g2_ba.jsonl 2>> $OUT/session.err
 timeout 600 python tools/sweep_msm.py bls12-381 1 20 --set GB200_MSM_BATCH_AFFINE=0,3,5 > $OUT/sweep_bls381_ba.jsonl 2>> $OUT/session.err
+timeout 600 python tools/sweep_msm.py bw6-761 1 18 --set GB200_MSM_HYBRID=0,30,50 > $OUT/sweep_bw6_hybrid.jsonl 2>> $OUT/session.err
+timeout 600 python tools/sweep_msm.py bw6-761 1 18 --set GB200_MSM_BATCH_AFFINE=0,4 > $OUT/sweep_bw6_ba.jsonl 2>> $OUT/session.err
 # compile-time variant: dedicated squaring + lazily reduced Fp2 product (built by `make -C gnark_b200/csrc opt`)
 if [ -f gnark_b200/lib/libgnark_b200_opt.so ]; then
   for cfg in "bn254 1" "bn254 2" "bls12-381 1"; do
