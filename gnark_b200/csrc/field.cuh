@@ -107,6 +107,64 @@ HD void wide_mul_raw(uint32_t* t, const uint32_t* a, const uint32_t* b) {
   (void)ptx::addc(0, 0);
 }
 
+// Karatsuba on top of wide_mul_raw (GB200_MONT_KARATSUBA, large fields): one level for N = 12 (3 x 6-limb products:
+// 108 multiplier operations instead of 144), two levels for N = 24 (9 x 6-limb: 324 instead of 576).
+//   a = aL + aH B, b = bL + bH B (B = 2^(32 N/2)):  a b = z0 + (z1 - z0 - z2) B + z2 B^2,
+//   z0 = aL bL, z2 = aH bH, z1 = (aL + aH)(bL + bH) with the two carry bits of the sums handled apart.
+template <int N>
+HD void wide_mul_karatsuba(uint32_t* t, const uint32_t* a, const uint32_t* b) {
+  if constexpr (N < 12 || (N % 2) != 0) {
+    wide_mul_raw<N>(t, a, b);
+  } else {
+    constexpr int H = N / 2;
+    uint32_t z0[2 * H], z2[2 * H], z1[2 * H + 2], sa[H], sb[H];
+    wide_mul_karatsuba<H>(z0, a, b);
+    wide_mul_karatsuba<H>(z2, a + H, b + H);
+    // sums with their carry bits
+    sa[0] = ptx::add_cc(a[0], a[H]);
+#pragma unroll
+    for (int k = 1; k < H; k++) sa[k] = ptx::addc_cc(a[k], a[H + k]);
+    const uint32_t ca = ptx::addc(0, 0);
+    sb[0] = ptx::add_cc(b[0], b[H]);
+#pragma unroll
+    for (int k = 1; k < H; k++) sb[k] = ptx::addc_cc(b[k], b[H + k]);
+    const uint32_t cb = ptx::addc(0, 0);
+    wide_mul_karatsuba<H>(z1, sa, sb);
+    z1[2 * H] = 0; z1[2 * H + 1] = 0;
+    // + ca * sb * 2^(32H) + cb * sa * 2^(32H) + ca cb 2^(64H)   (masks, no multiplications)
+    const uint32_t ma = 0u - ca, mb = 0u - cb;
+    z1[H] = ptx::add_cc(z1[H], sb[0] & ma);
+#pragma unroll
+    for (int k = 1; k < H; k++) z1[H + k] = ptx::addc_cc(z1[H + k], sb[k] & ma);
+    z1[2 * H] = ptx::addc(z1[2 * H], 0);
+    z1[H] = ptx::add_cc(z1[H], sa[0] & mb);
+#pragma unroll
+    for (int k = 1; k < H; k++) z1[H + k] = ptx::addc_cc(z1[H + k], sa[k] & mb);
+    z1[2 * H] = ptx::addc_cc(z1[2 * H], ca & cb);
+    z1[2 * H + 1] = ptx::addc(z1[2 * H + 1], 0);
+    // z1 -= z0 + z2   (the true middle term fits 2H + 1 limbs)
+    z1[0] = ptx::sub_cc(z1[0], z0[0]);
+#pragma unroll
+    for (int k = 1; k < 2 * H; k++) z1[k] = ptx::subc_cc(z1[k], z0[k]);
+    z1[2 * H] = ptx::subc_cc(z1[2 * H], 0);
+    z1[2 * H + 1] = ptx::subc(z1[2 * H + 1], 0);
+    z1[0] = ptx::sub_cc(z1[0], z2[0]);
+#pragma unroll
+    for (int k = 1; k < 2 * H; k++) z1[k] = ptx::subc_cc(z1[k], z2[k]);
+    z1[2 * H] = ptx::subc_cc(z1[2 * H], 0);
+    z1[2 * H + 1] = ptx::subc(z1[2 * H + 1], 0);
+    // assemble: t = z0 + z1 B + z2 B^2
+#pragma unroll
+    for (int k = 0; k < 2 * H; k++) { t[k] = z0[k]; t[2 * H + k] = z2[k]; }
+    t[H] = ptx::add_cc(t[H], z1[0]);
+#pragma unroll
+    for (int k = 1; k < 2 * H + 2 && H + k < 2 * N; k++) t[H + k] = ptx::addc_cc(t[H + k], z1[k]);
+#pragma unroll
+    for (int k = 3 * H + 2; k < 2 * N; k++) t[k] = ptx::addc_cc(t[k], 0);
+    (void)ptx::addc(0, 0);
+  }
+}
+
 // cross terms of a square: chains of a_i * a_j, j > i, all j of one parity
 template <int N, int I>
 struct SqrCross {
@@ -256,15 +314,24 @@ struct alignas(16) Fp {
 
   HD friend Fp operator+(const Fp& a, const Fp& b) { Fp r; mod_add_raw<P>(r.l, a.l, b.l); return r; }
   HD friend Fp operator-(const Fp& a, const Fp& b) { Fp r; mod_sub_raw<P>(r.l, a.l, b.l); return r; }
-#if defined(__CUDA_ARCH__)
-  // large fields: keep one copy of the unrolled product per kernel (I-cache, compile time)
-  static __device__ __noinline__ Fp mul_ni(const Fp& a, const Fp& b) { Fp r; mont_mul_raw<P>(r.l, a.l, b.l); return r; }
-  HD friend Fp operator*(const Fp& a, const Fp& b) {
-    if (N > 8) return mul_ni(a, b);
-    Fp r; mont_mul_raw<P>(r.l, a.l, b.l); return r;
+#if defined(GB200_MONT_KARATSUBA)
+  // large fields: Karatsuba product + separate reduction (fewer multiplier operations than the fused product)
+  HD static void mul_dispatch(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+    if constexpr (N >= 12) { uint32_t t[2 * N]; wide_mul_karatsuba<N>(t, a, b); mont_reduce_wide<P>(r, t); }
+    else mont_mul_raw<P>(r, a, b);
   }
 #else
-  HD friend Fp operator*(const Fp& a, const Fp& b) { Fp r; mont_mul_raw<P>(r.l, a.l, b.l); return r; }
+  HD static void mul_dispatch(uint32_t* r, const uint32_t* a, const uint32_t* b) { mont_mul_raw<P>(r, a, b); }
+#endif
+#if defined(__CUDA_ARCH__)
+  // large fields: keep one copy of the unrolled product per kernel (I-cache, compile time)
+  static __device__ __noinline__ Fp mul_ni(const Fp& a, const Fp& b) { Fp r; mul_dispatch(r.l, a.l, b.l); return r; }
+  HD friend Fp operator*(const Fp& a, const Fp& b) {
+    if (N > 8) return mul_ni(a, b);
+    Fp r; mul_dispatch(r.l, a.l, b.l); return r;
+  }
+#else
+  HD friend Fp operator*(const Fp& a, const Fp& b) { Fp r; mul_dispatch(r.l, a.l, b.l); return r; }
 #endif
 #if defined(GB200_MONT_SQR)
   HD Fp sqr() const {

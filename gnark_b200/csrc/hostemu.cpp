@@ -55,6 +55,7 @@ int wide_op(int op, const void* a_, const void* b_, void* out_) {
     case 0: wide_mul_raw<N>(out, a, b); return 0;
     case 1: wide_sqr_raw<N>(out, a); return 0;
     case 2: mont_reduce_wide<typename F::Params>(out, a); return 0;
+    case 3: wide_mul_karatsuba<N>(out, a, b); return 0;
   }
   return -1;
 }
@@ -519,6 +520,9 @@ int emu_build_options(void) {
 #endif
 #if defined(GB200_FP2_LAZY)
   v |= 2;
+#endif
+#if defined(GB200_MONT_KARATSUBA)
+  v |= 4;
 #endif
   return v;
 }

@@ -28,11 +28,11 @@ def hostemu():
 
 @pytest.fixture(scope="session")
 def hostemu_opt():
-    """the same templates compiled with the optional arithmetic paths (GB200_MONT_SQR, GB200_FP2_LAZY)"""
+    """the same templates compiled with the optional arithmetic paths (GB200_MONT_SQR, GB200_FP2_LAZY, GB200_MONT_KARATSUBA)"""
     import ctypes
     _make("../lib/libgb200_hostemu_opt.so")
     lib = ctypes.CDLL(os.path.join(ROOT, "gnark_b200", "lib", "libgb200_hostemu_opt.so"))
-    assert lib.emu_build_options() == 3
+    assert lib.emu_build_options() == 7
     return lib
 
 

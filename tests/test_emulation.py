@@ -87,6 +87,8 @@ def test_wide_arithmetic(hostemu, c):
             assert val(O) == a * b, (c.name, which, "wide_mul")
             assert hostemu.emu_wide_op(fid, 1, P(arr(a, L)), P(arr(a, L)), P(O)) == 0
             assert val(O) == a * a, (c.name, which, "wide_sqr")
+            assert hostemu.emu_wide_op(fid, 3, P(arr(a, L)), P(arr(b, L)), P(O)) == 0
+            assert val(O) == a * b, (c.name, which, "wide_mul_karatsuba")
         Rinv = pow(R, -1, q)
         ts = [0, q * R - 1, q * q, (q - 1) * (q - 1), 6 * q * q if 6 * q < R else q * q]
         ts += [rng.randrange(q * R) for _ in range(60)]
