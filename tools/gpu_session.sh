@@ -32,14 +32,20 @@ timeout 600 python tools/sweep_msm.py bn254 2 20 --set GB200_MSM_BATCH_AFFINE=0,
 timeout 600 python tools/sweep_msm.py bls12-381 1 20 --set GB200_MSM_BATCH_AFFINE=0,3,5 > $OUT/sweep_bls381_ba.jsonl 2>> $OUT/session.err
 timeout 600 python tools/sweep_msm.py bw6-761 1 18 --set GB200_MSM_HYBRID=0,30,50 > $OUT/sweep_bw6_hybrid.jsonl 2>> $OUT/session.err
 timeout 600 python tools/sweep_msm.py bw6-761 1 18 --set GB200_MSM_BATCH_AFFINE=0,4 > $OUT/sweep_bw6_ba.jsonl 2>> $OUT/session.err
-# compile-time variant: dedicated squaring + lazily reduced Fp2 product (built by `make -C gnark_b200/csrc opt`)
-if [ -f gnark_b200/lib/libgnark_b200_opt.so ]; then
-  for cfg in "bn254 1" "bn254 2" "bls12-381 1"; do
+# compile-time arithmetic variants (build before the call, they travel with the snapshot):
+#   make -C gnark_b200/csrc opt                                              -> libgnark_b200_opt.so (all three)
+#   make -C gnark_b200/csrc opt OPTFLAGS=-DGB200_MONT_SQR OPTNAME=sqr         -> libgnark_b200_sqr.so
+#   make -C gnark_b200/csrc opt OPTFLAGS=-DGB200_FP2_LAZY OPTNAME=lazy        -> libgnark_b200_lazy.so
+#   make -C gnark_b200/csrc opt OPTFLAGS=-DGB200_MONT_KARATSUBA OPTNAME=kara  -> libgnark_b200_kara.so
+for lib in gnark_b200/lib/libgnark_b200_*.so; do
+  [ -f "$lib" ] || continue
+  tag=$(basename $lib .so | sed 's/libgnark_b200_//')
+  for cfg in "bn254 1 20" "bn254 2 20" "bls12-381 1 20" "bw6-761 1 18"; do
     set -- $cfg
-    GB200_LIB=$PWD/gnark_b200/lib/libgnark_b200_opt.so timeout 600 python tools/sweep_msm.py $1 $2 20 --set GB200_MSM_BATCH_AFFINE=0,5 \
-        | sed 's/^{/{"lib": "opt", /' >> $OUT/sweep_optlib.jsonl 2>> $OUT/session.err
+    GB200_LIB=$PWD/$lib timeout 600 python tools/sweep_msm.py $1 $2 $3 --set GB200_MSM_BATCH_AFFINE=0,5 \
+        | sed "s/^{/{\"lib\": \"$tag\", /" >> $OUT/sweep_optlib.jsonl 2>> $OUT/session.err
   done
-fi
+done
 cat $OUT/sweep_*.jsonl | cut -c1-400 | tee -a $OUT/session.log
 
 echo "== 3b. NTT tile sizes" | tee -a $OUT/session.log
