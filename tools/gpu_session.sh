@@ -79,5 +79,9 @@ if [ "$NG" -gt 1 ]; then
   timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29612 \
       bench.py --gpus $NG --steps 20 --warmup 3 > $OUT/bench_n$NG.json 2>> $OUT/session.err
   tail -c 1500 $OUT/bench_n$NG.json | tee -a $OUT/session.log
+  # where does a sharded Groth16 proof spend its time (per-stage laps of every rank on stderr)
+  GB200_STEP_PROFILE=1 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 \
+      --master-port 29614 bench.py --gpus $NG --steps 3 --warmup 3 > /dev/null 2> $OUT/groth16_steps_n$NG.err
+  grep "gb200 step" $OUT/groth16_steps_n$NG.err | tail -40 | tee -a $OUT/session.log
 fi
 ls -la $OUT | tee -a $OUT/session.log
