@@ -22,16 +22,16 @@ def _make(target):
 def hostemu():
     """CPU build of the device templates (PTX carry chains emulated) - test scaffolding."""
     import ctypes
-    _make("../lib/libgb200_hostemu.so")
-    return ctypes.CDLL(os.path.join(ROOT, "gnark_b200", "lib", "libgb200_hostemu.so"))
+    _make("../../tests/_build/libgb200_hostemu.so")
+    return ctypes.CDLL(os.path.join(ROOT, "tests", "_build", "libgb200_hostemu.so"))
 
 
 @pytest.fixture(scope="session")
 def hostemu_opt():
     """the same templates compiled with the optional arithmetic paths (GB200_MONT_SQR, GB200_FP2_LAZY, GB200_MONT_KARATSUBA)"""
     import ctypes
-    _make("../lib/libgb200_hostemu_opt.so")
-    lib = ctypes.CDLL(os.path.join(ROOT, "gnark_b200", "lib", "libgb200_hostemu_opt.so"))
+    _make("../../tests/_build/libgb200_hostemu_opt.so")
+    lib = ctypes.CDLL(os.path.join(ROOT, "tests", "_build", "libgb200_hostemu_opt.so"))
     assert lib.emu_build_options() == 7
     return lib
 

@@ -16,7 +16,7 @@ from oracle import corelib, ec, ff, plonk_prover as pp
 from oracle.params import CURVES
 from util import jac_to_affine
 
-LIB = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gnark_b200", "lib", "libgb200_plonkmock.so")
+LIB = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_build", "libgb200_plonkmock.so")
 
 
 @pytest.fixture(scope="module")
