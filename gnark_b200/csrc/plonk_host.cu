@@ -35,6 +35,11 @@ struct b200_plonk_pk_s {
   b200_table_t srs = nullptr;         // canonical SRS, n + 3 points
   // BSB22 commitment gates: selectors Qcp_j (trace.Qcp), canonical bit-reversed / regular like the other key polys
   std::vector<void*> qcp_br, qcp_canon;
+  // The key polynomials never change between proofs: their evaluations on the four cosets of the quotient domain
+  // are computed once at key load and kept in HBM ((8 + n_qcp) x 4 x n elements: 4 GiB at n = 2^22 with 32-byte
+  // elements), so a proof runs 16 coset NTTs (l, r, o, z) instead of 48.  key_cos[i][k]: coset i, polynomial k in the
+  // order ql qr qm qo qk s1 s2 s3 qcp...; empty when GB200_PLONK_COSET_CACHE=0.
+  std::vector<std::vector<void*>> key_cos;
 };
 
 namespace gb200_plonk {
@@ -143,6 +148,7 @@ int32_t b200_plonk_pk_free(b200_plonk_pk_t pk) {
   if (pk->d_perm) b200_free(pk->dev, pk->d_perm);
   for (void* q : pk->qcp_br) if (q) b200_free(pk->dev, q);
   for (void* q : pk->qcp_canon) if (q) b200_free(pk->dev, q);
+  for (auto& v : pk->key_cos) for (void* q : v) if (q) b200_free(pk->dev, q);
   if (pk->srs) b200_table_free(pk->srs);
   delete pk;
   return 0;
@@ -218,6 +224,21 @@ int32_t b200_plonk_pk_load(int32_t dev, int32_t curve, const b200_plonk_pk_desc*
     RC(b200_ntt_async(pk->dom0[0], b, 1, B200_DIF, 0));
     RC(d2d(dev, c, b, n * fb));
     RC(b200_vec_bit_reverse(dev, curve, c, d->log2n));
+  }
+  {
+    const char* e = getenv("GB200_PLONK_COSET_CACHE");
+    if (!e || atoi(e) != 0) {
+      std::vector<void*> src;
+      for (int k = 0; k < 8; k++) src.push_back(pk->br[k]);
+      for (void* q : pk->qcp_br) src.push_back(q);
+      pk->key_cos.assign(4, std::vector<void*>(src.size(), nullptr));
+      for (int i = 0; i < 4; i++)
+        for (size_t k = 0; k < src.size(); k++) {
+          RC(b200_alloc(dev, n * fb, &pk->key_cos[i][k]));
+          RC(d2d(dev, pk->key_cos[i][k], src[k], n * fb));
+          RC(b200_ntt_async(pk->dom0[i], pk->key_cos[i][k], 0, B200_DIT, 1));   // canonical/bit-reversed -> coset i
+        }
+    }
   }
   RC(b200_table_upload(dev, curve, 1, d->srs_canonical, n + 3, B200_TABLE_PRECOMP, &pk->srs));
   RC(b200_sync(dev));
@@ -314,26 +335,33 @@ int32_t b200_plonk_quotient(b200_plonk_session_t s, const void* alpha, void* out
   // argument order of b200_plonk_coset_args: l r o z s1 s2 s3 ql qr qm qo qk
   const void* srcs[12] = {s->cb[0], s->cb[1], s->cb[2], s->cb[3], pk->br[S1], pk->br[S2], pk->br[S3],
                           pk->br[QL], pk->br[QR], pk->br[QM], pk->br[QO], pk->br[QK]};
+  const bool cached = !pk->key_cos.empty();
+  // position of the key polynomials in key_cos[i]: ql qr qm qo qk s1 s2 s3 ; srcs[4..11] = s1 s2 s3 ql qr qm qo qk
+  const int cos_idx[12] = {-1, -1, -1, -1, S1, S2, S3, QL, QR, QM, QO, QK};
   for (uint32_t i = 0; i < 4; i++) {
+    const void* on[12];
     for (int k = 0; k < 12; k++) {
+      if (cached && cos_idx[k] >= 0) { on[k] = pk->key_cos[i][cos_idx[k]]; continue; }
       RC(d2d(dev, onc[k], srcs[k], n * fb));
       RC(b200_ntt_async(pk->dom0[i], onc[k], 0, B200_DIT, 1));     // canonical/bit-reversed -> coset i, regular
+      on[k] = onc[k];
     }
     b200_plonk_coset_args a;
     memset(&a, 0, sizeof(a));
-    a.l = onc[0]; a.r = onc[1]; a.o = onc[2]; a.z = onc[3]; a.s1 = onc[4]; a.s2 = onc[5]; a.s3 = onc[6];
-    a.ql = onc[7]; a.qr = onc[8]; a.qm = onc[9]; a.qo = onc[10]; a.qk = onc[11];
+    a.l = on[0]; a.r = on[1]; a.o = on[2]; a.z = on[3]; a.s1 = on[4]; a.s2 = on[5]; a.s3 = on[6];
+    a.ql = on[7]; a.qr = on[8]; a.qm = on[9]; a.qo = on[10]; a.qk = on[11];
     a.alpha = s->alpha; a.beta = s->beta; a.gamma = s->gamma;
     a.bl = s->blind[0]; a.br = s->blind[1]; a.bo = s->blind[2]; a.bz = s->blind[3];
     a.nbl = 2; a.nbr = 2; a.nbo = 2; a.nbz = 3;
     a.coset_index = i; a.rho = 4; a.out = s->h;
     RC(b200_plonk_constraints_coset(pk->dom0[i], gb, w4b, &a));
     for (size_t j = 0; j < pk->qcp_br.size(); j++) {   // + Qcp_j * PI2_j on this coset (gateConstraint :881-884)
-      RC(d2d(dev, onc[0], pk->qcp_br[j], n * fb));
+      const void* qc = onc[0];
+      if (cached) qc = pk->key_cos[i][8 + j];
+      else { RC(d2d(dev, onc[0], pk->qcp_br[j], n * fb)); RC(b200_ntt_async(pk->dom0[i], onc[0], 0, B200_DIT, 1)); }
       RC(d2d(dev, onc[1], s->pi2_br[j], n * fb));
-      RC(b200_ntt_async(pk->dom0[i], onc[0], 0, B200_DIT, 1));
       RC(b200_ntt_async(pk->dom0[i], onc[1], 0, B200_DIT, 1));
-      RC(b200_plonk_bsb22_coset(pk->dom0[i], onc[0], onc[1], i, 4, s->h));
+      RC(b200_plonk_bsb22_coset(pk->dom0[i], qc, onc[1], i, 4, s->h));
     }
   }
   RC(b200_plonk_divide_by_zh(pk->dom1, pk->logn, s->h));      // -> h canonical regular (4n)

@@ -207,6 +207,19 @@ class ProvingKey:
             c = d.clone()
             _lib.vec_bit_reverse(dev, curve, c, log2n)
             pk.canon[name] = c
+        # the key polynomials never change between proofs: keep their evaluations on the four quotient cosets in
+        # HBM ((8 + n_commit) x 4 x n elements; 4 GiB at n = 2^22), so a proof runs 16 coset NTTs instead of 48.
+        # A sharded key keeps only the cosets this rank evaluates.  GB200_PLONK_COSET_CACHE=0 turns it off.
+        import os
+        pk.key_cos = {}
+        if os.environ.get("GB200_PLONK_COSET_CACHE", "1") != "0":
+            for i in range(4):
+                if i % pk.world != pk.rank:
+                    continue
+                for name, d in pk.polys.items():
+                    e = d.clone()
+                    pk.dom0[i].ntt_async(e, inverse=False, decimation=_lib.DIT, on_coset=True)
+                    pk.key_cos[(i, name)] = e
         from .parallel import shard_range
         srs = np.ascontiguousarray(srs_canonical).reshape(n + 3, -1)
         pk.srs_off, pk.srs_cnt = shard_range(n + 3, pk.world, pk.rank)
@@ -316,15 +329,21 @@ def _prove(pk: ProvingKey, l, r, o, ch: Challenges, pi2=()) -> Proof:
             continue
         on_coset = {}
         for name in names:
+            if (i, name) in pk.key_cos:
+                on_coset[name] = pk.key_cos[(i, name)]
+                continue
             src = cb[name] if name in cb else pk.polys[name]
             d = src.clone()
             pk.dom0[i].ntt_async(d, inverse=False, decimation=_lib.DIT, on_coset=True)   # canonical/bit-rev -> coset i, regular
             on_coset[name] = d
         _lib.plonk_constraints_coset(pk.dom0[i], g_m, w4_m, on_coset, a_m, b_m, c_m, blind, i, 4, cres)
         for j in range(len(pi2)):           # + Qcp_j * PI2_j on this coset (gateConstraint :881-884)
-            dq, dp = pk.polys[f"qcp{j}"].clone(), pi2_br[j].clone()
-            pk.dom0[i].ntt_async(dq, inverse=False, decimation=_lib.DIT, on_coset=True)
+            dp = pi2_br[j].clone()
             pk.dom0[i].ntt_async(dp, inverse=False, decimation=_lib.DIT, on_coset=True)
+            dq = pk.key_cos.get((i, f"qcp{j}"))
+            if dq is None:
+                dq = pk.polys[f"qcp{j}"].clone()
+                pk.dom0[i].ntt_async(dq, inverse=False, decimation=_lib.DIT, on_coset=True)
             _lib.plonk_bsb22_coset(pk.dom0[i], dq, dp, i, 4, cres)
         _lib.sync(dev)
         del on_coset

@@ -104,9 +104,12 @@ def test_plonk_host_orchestration_vs_oracle(mock, cname, logn):
 
 
 @pytest.mark.parametrize("n_commit", (1, 2))
-def test_plonk_host_bsb22_commitments(mock, n_commit):
+@pytest.mark.parametrize("coset_cache", ("1", "0"))
+def test_plonk_host_bsb22_commitments(mock, monkeypatch, n_commit, coset_cache):
     """keys with BSB22 commitment gates: gate term on every coset, [PI2_j], sum_j Qcp_j(zeta) PI2_j(X) in the linearised
     polynomial, Qcp openings - b200_plonk_prove against the oracle prover (extended verifier equations hold)"""
+    # GB200_PLONK_COSET_CACHE: key polynomials' coset evaluations kept from key load (default) or recomputed per proof
+    monkeypatch.setenv("GB200_PLONK_COSET_CACHE", coset_cache)
     c = CURVES["bn254"]
     logn = 4
     rng = random.Random(4000 + n_commit)

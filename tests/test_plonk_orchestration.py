@@ -199,17 +199,20 @@ def test_orchestration_against_oracle_prover(monkeypatch, cname, logn):
     # the library was pointed at the orchestrator's stream for the duration and handed back afterwards
     streams = [x[1] for x in calls if isinstance(x, tuple)]
     assert streams == [1234, 0, 1234, 0]
-    # per proof: 12 polys x 4 cosets + 4 canonical conversions (l, r, o, z) NTTs; 4 constraint calls; 10 commitments
-    assert calls.count("ntt") == 8 + 48 + 4 and calls.count("constraints") == 4 and calls.count("msm") == 10
+    # key load: 8 canonical conversions + 8 x 4 cached coset evaluations; per proof: 4 canonical conversions and
+    # 4 polys x 4 cosets; 4 constraint calls; 10 commitments
+    assert calls.count("ntt") == (8 + 32) + (4 + 16) and calls.count("constraints") == 4 and calls.count("msm") == 10
     pk.free()
 
 
 @pytest.mark.parametrize("n_commit", (1, 2))
-def test_orchestration_with_bsb22_commitments(monkeypatch, n_commit):
+@pytest.mark.parametrize("coset_cache", ("1", "0"))
+def test_orchestration_with_bsb22_commitments(monkeypatch, n_commit, coset_cache):
     """BSB22 commitment gates through the orchestrator: gate term on every coset, [PI2_j], the linearised-polynomial
     term sum_j Qcp_j(zeta) PI2_j(X) and the extra Qcp openings - against the oracle prover (whose proof passes the
     extended verifier equations)"""
     from gnark_b200 import lib as real_lib, plonk as b200_plonk
+    monkeypatch.setenv("GB200_PLONK_COSET_CACHE", coset_cache)
     c = CURVES["bn254"]
     calls = []
     monkeypatch.setattr(b200_plonk, "_lib", make_mock_lib(real_lib, calls))
