@@ -2,9 +2,12 @@
 // __graft_entry__.smoke() and by bench.py's cpu_baseline / --impl reference legs -
 // never by the product (gnark_b200/).
 //
-// PARITY UNPINNED: the reference holds no golden vectors for this path and its
-// arithmetic (github.com/consensys/gnark-crypto v0.21.0, go.mod:9) is not in
-// /root/reference.  This file restates the PUBLISHED ALGORITHMS that module
+// PARITY PARTLY PINNED (oracle/params.py header has the list): the reference's arithmetic
+// (github.com/consensys/gnark-crypto v0.21.0, go.mod:9) is not in /root/reference and it
+// holds no MSM / NTT result vectors as such; the external fixtures it does ship - the
+// Ethereum KZG ceremony SRS (BLS12-381 G1 MSM 4096 + Fr NTT 2^12) and gnark's serialised
+// verifying keys (BN254 / BLS12-381 constants) - are checked in tests/test_golden_kzg.py,
+// this file included.  Everything else is property-anchored.  This file restates the PUBLISHED ALGORITHMS that module
 // uses for the calls the reference makes, and is itself validated against the
 // big-int Python oracle (oracle/ec.py, oracle/ntt.py) in tests/test_oracle_c.py:
 //   * MultiExp (call sites backend/groth16/bn254/prove.go:194,207,227,237,283):

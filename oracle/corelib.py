@@ -1,5 +1,5 @@
 """ctypes front end of the C++ oracle (oracle/c/oracle.cpp).  TEST INFRASTRUCTURE ONLY
-(see oracle/params.py header; parity unpinned by the reference).
+(see oracle/params.py header for what pins parity and what does not).
 
 Builds oracle/_build/liboracle.so on demand with g++ (no reference sources are
 compiled: gnark is Go and its arithmetic is in an absent module, so there is no

@@ -1,6 +1,6 @@
 """Short-Weierstrass (a = 0) group law over Fp / Fp2, naive MSM, and point
 (de)serialisation in gnark memory layout.  TEST INFRASTRUCTURE ONLY
-(see oracle/params.py header; parity unpinned by the reference).
+(see oracle/params.py header for what pins parity and what does not).
 
 What the reference relies on:
   MultiExp(points, scalars) = sum_i scalars[i] * points[i] as a group element

@@ -1,5 +1,5 @@
 """Big-int field helpers + gnark-crypto memory layout.  TEST INFRASTRUCTURE ONLY
-(see oracle/params.py header; parity unpinned by the reference).
+(see oracle/params.py header for what pins parity and what does not).
 
 Layout restated from SURVEY.md Appendix A (evidence:
 backend/accelerated/icicle/groth16/bn254/icicle.go:119-130,266-315):

@@ -1,5 +1,5 @@
 """Groth16 trapdoor Setup / Prove restated on big ints.  TEST INFRASTRUCTURE ONLY
-(see oracle/params.py header; parity unpinned by the reference).
+(see oracle/params.py header for what pins parity and what does not).
 
 Follows:
   Setup      backend/groth16/bn254/setup.go:75-331 (scalar layout, InfinityA/B

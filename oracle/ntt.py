@@ -1,5 +1,5 @@
 """Radix-2 NTT over Fr in gnark-crypto's fft.Domain conventions.
-TEST INFRASTRUCTURE ONLY (see oracle/params.py header; parity unpinned).
+TEST INFRASTRUCTURE ONLY (see oracle/params.py header for what pins parity and what does not).
 
 gnark-crypto v0.21.0 source is absent; the conventions restated here are the
 ones the reference's call sites rely on:

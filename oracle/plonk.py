@@ -1,5 +1,5 @@
 """PLONK quotient pieces restated on big ints.  TEST INFRASTRUCTURE ONLY
-(see oracle/params.py header; parity unpinned by the reference).
+(see oracle/params.py header for what pins parity and what does not).
 
 Follows backend/plonk/bn254/prove.go:
   computeNumerator :841-1123  (gateConstraint :871-889, orderingConstraint :907-931,

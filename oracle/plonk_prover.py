@@ -1,5 +1,5 @@
 """PLONK prover restated on big ints, with a trapdoor SRS.  TEST INFRASTRUCTURE ONLY
-(see oracle/params.py header; parity unpinned by the reference).
+(see oracle/params.py header for what pins parity and what does not).
 
 Follows backend/plonk/bn254/prove.go (StatisticalZK off; BSB22 commitment gates :867-884 with the committed
 polynomials PI2_i GIVEN - in the reference they come from the solver hint :280-318 - their digests

@@ -3,6 +3,7 @@ file that sorts last so that, under `pytest -x`, the hardware-validated parity s
 plonk) has already reported before these run.
 
   * test_cuda_reproduces_golden   - the CUDA path on the committed known-answer vectors (tests/golden)
+  * test_cuda_reproduces_eth_kzg_srs - the CUDA path on the reference's external fixture (Ethereum KZG ceremony SRS)
   * test_full_prover_vs_oracle    - the device PLONK prover (gnark_b200/plonk.py) against the big-int oracle
                                     prover, same injected challenges (xfail-guarded until run on hardware)
   * test_msm_hybrid_accumulate    - opt-in experiment GB200_MSM_HYBRID (both multiplier pipes at once)
@@ -59,6 +60,39 @@ def test_cuda_reproduces_golden(gpu, c):
     got = d2.compute_h(*(ff.pack_elements(v, c.r, c.fr_limbs) for v in (A_, B_, C_)))
     assert ff.unpack_elements(got, c.r, c.fr_limbs) == [H(v) for v in gc["h_bitreversed"]]
     d.free(); d2.free()
+
+
+def test_cuda_reproduces_eth_kzg_srs(gpu):
+    """EXTERNAL known-answer vectors (tests/test_golden_kzg.py): the Ethereum KZG ceremony SRS the reference ships
+    (std/evmprecompiles/kzg_trusted_setup.json).  CUDA BLS12-381 G1 MSM of 4096 externally produced points against
+    externally produced answers, and the CUDA NTT pinned through MSM(monomial, c) = MSM(lagrange, NTT(c))."""
+    import random as _r
+    from oracle import kzg_srs, ntt
+    from oracle.params import BLS12_381 as C
+    from test_golden_kzg import kat_cases
+    mono, lag, _ = kzg_srs.load()
+    pts = {"mono": mono, "lag": lag}
+    F = ff.Fp(C.p)
+    N, LOGN = kzg_srs.N, kzg_srs.LOGN
+    aff = lambda out: ec.from_jac(F, ec.unpack_points(C, 1, out, ncoords=3)[0])
+    for precomp in (False, True):
+        T = {"MONO": gpu.Table(C.curve_id, 1, ec.pack_points(C, 1, mono), precomp=precomp),
+             "LAG": gpu.Table(C.curve_id, 1, ec.pack_points(C, 1, lag), precomp=precomp)}
+        for base, sc, (other, j) in kat_cases(_r.Random(1)):
+            assert aff(T[base].msm(ff.pack_elements(sc, C.r, C.fr_limbs))) == pts[other][j], (precomp, base, other, j)
+        rng = _r.Random(2)
+        c = [rng.randrange(C.r) for _ in range(N)]
+        commit = aff(T["MONO"].msm(ff.pack_elements(c, C.r, C.fr_limbs)))
+        d = gpu.Domain(C.curve_id, LOGN)
+        e_br = d.ntt(ff.pack_elements(c, C.r, C.fr_limbs), inverse=False, decimation=ntt.DIF)
+        e = d.ntt(ff.pack_elements(ntt.bit_reverse(list(c)), C.r, C.fr_limbs), inverse=False, decimation=ntt.DIT)
+        assert ntt.bit_reverse(ff.unpack_elements(e_br, C.r, C.fr_limbs)) == ff.unpack_elements(e, C.r, C.fr_limbs)
+        assert aff(T["LAG"].msm(e)) == commit
+        back = d.ntt(e.copy(), inverse=True, decimation=ntt.DIF)
+        assert ntt.bit_reverse(ff.unpack_elements(back, C.r, C.fr_limbs)) == c
+        d.free()
+        for t in T.values():
+            t.free()
 
 
 @pytest.mark.xfail(strict=False, reason="orchestrator written after this round's GPU budget was spent: every C-ABI "

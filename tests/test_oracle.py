@@ -1,5 +1,5 @@
-"""Oracle self-checks (CPU).  The reference pins nothing at the bit level for this
-path ('parity unpinned'), so the oracle is anchored on properties:
+"""Oracle self-checks (CPU).  Beyond the external fixtures of tests/test_golden_kzg.py the reference pins
+nothing at the bit level for this path, so the oracle is also anchored on properties:
 published constants property-checked, NTT against the O(n^2) definition, the
 Groth16 pipeline against the pairing equation evaluated in the exponent (the
 reference's own test is prove -> Verify, test/assert_checkcircuit.go:140-144)."""
