@@ -325,7 +325,13 @@ struct alignas(16) Fp {
 #endif
 #if defined(__CUDA_ARCH__)
   // large fields: keep one copy of the unrolled product per kernel (I-cache, compile time)
+#if defined(GB200_CALL_BYVAL)
+  // operands and result of the out-of-line product travel in registers: a reference parameter forces the caller to
+  // spill both operands to its stack frame and the callee to load them back (checked in SASS: 0 LDL/STL by value)
+  static __device__ __noinline__ Fp mul_ni(Fp a, Fp b) { Fp r; mul_dispatch(r.l, a.l, b.l); return r; }
+#else
   static __device__ __noinline__ Fp mul_ni(const Fp& a, const Fp& b) { Fp r; mul_dispatch(r.l, a.l, b.l); return r; }
+#endif
   HD friend Fp operator*(const Fp& a, const Fp& b) {
     if (N > 8) return mul_ni(a, b);
     Fp r; mul_dispatch(r.l, a.l, b.l); return r;
@@ -521,7 +527,11 @@ struct alignas(16) Fp2 {
     mont_reduce_wide<P>(r.a1.l, t2);
     return r;
   }
+#if defined(GB200_CALL_BYVAL) && defined(__CUDA_ARCH__)
+  HDNI static Fp2 mul(Fp2 x, Fp2 y) {
+#else
   HDNI static Fp2 mul(const Fp2& x, const Fp2& y) {
+#endif
 #if defined(GB200_FP2_LAZY)
     if constexpr (is_device_fp<F>::value) return mul_lazy<F>(x, y);
 #endif
@@ -535,6 +545,19 @@ struct alignas(16) Fp2 {
     return r;
   }
   HD friend Fp2 operator*(const Fp2& x, const Fp2& y) { return mul(x, y); }
+#if defined(GB200_CALL_BYVAL) && defined(__CUDA_ARCH__)
+  HDNI static Fp2 sqr_ni(Fp2 x) {
+    if (BETA == 1) {
+      Fp2 r;
+      F t = x.a0 * x.a1;
+      r.a0 = (x.a0 + x.a1) * (x.a0 - x.a1);
+      r.a1 = t + t;
+      return r;
+    }
+    return mul(x, x);
+  }
+  HD Fp2 sqr() const { return sqr_ni(*this); }
+#else
   HDNI Fp2 sqr() const {
     if (BETA == 1) {  // (a0+a1)(a0-a1), 2 a0 a1
       Fp2 r;
@@ -545,6 +568,7 @@ struct alignas(16) Fp2 {
     }
     return mul(*this, *this);
   }
+#endif
   HD Fp2 neg() const { Fp2 r; r.a0 = a0.neg(); r.a1 = a1.neg(); return r; }
   HD Fp2 dbl() const { Fp2 r; r.a0 = a0.dbl(); r.a1 = a1.dbl(); return r; }
   HD Fp2 inverse() const {
