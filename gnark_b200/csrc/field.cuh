@@ -323,6 +323,9 @@ struct alignas(16) Fp {
 #else
   HD static void mul_dispatch(uint32_t* r, const uint32_t* a, const uint32_t* b) { mont_mul_raw<P>(r, a, b); }
 #endif
+#ifndef GB200_INLINE_LIMBS
+#define GB200_INLINE_LIMBS 8      // fields of up to this many 32-bit limbs get the product inlined at every use
+#endif
 #if defined(__CUDA_ARCH__)
   // large fields: keep one copy of the unrolled product per kernel (I-cache, compile time)
 #if defined(GB200_CALL_BYVAL)
@@ -333,7 +336,7 @@ struct alignas(16) Fp {
   static __device__ __noinline__ Fp mul_ni(const Fp& a, const Fp& b) { Fp r; mul_dispatch(r.l, a.l, b.l); return r; }
 #endif
   HD friend Fp operator*(const Fp& a, const Fp& b) {
-    if (N > 8) return mul_ni(a, b);
+    if (N > GB200_INLINE_LIMBS) return mul_ni(a, b);
     Fp r; mul_dispatch(r.l, a.l, b.l); return r;
   }
 #else
@@ -484,6 +487,14 @@ struct alignas(16) Fp {
 // rule restated from std/algebra/emulated/fields_bn254/e2.go:203-213 and
 // std/algebra/native/fields_bls12377/e2.go:134.  Memory = gnark E2{A0, A1}.
 // ---------------------------------------------------------------------------
+// Fp2 product / square: out of line by default (one copy of the 3-multiplication body per kernel);
+// -DGB200_INLINE_FP2 inlines them at every use (A/B knob: no call, no stack round trip, larger code)
+#if defined(GB200_INLINE_FP2)
+#define HD_FP2 HD
+#else
+#define HD_FP2 HDNI
+#endif
+
 template <class T> struct is_device_fp { static constexpr bool value = false; };
 template <class P> struct is_device_fp<Fp<P>> { static constexpr bool value = true; };
 
@@ -528,9 +539,9 @@ struct alignas(16) Fp2 {
     return r;
   }
 #if defined(GB200_CALL_BYVAL) && defined(__CUDA_ARCH__)
-  HDNI static Fp2 mul(Fp2 x, Fp2 y) {
+  HD_FP2 static Fp2 mul(Fp2 x, Fp2 y) {
 #else
-  HDNI static Fp2 mul(const Fp2& x, const Fp2& y) {
+  HD_FP2 static Fp2 mul(const Fp2& x, const Fp2& y) {
 #endif
 #if defined(GB200_FP2_LAZY)
     if constexpr (is_device_fp<F>::value) return mul_lazy<F>(x, y);
@@ -558,7 +569,7 @@ struct alignas(16) Fp2 {
   }
   HD Fp2 sqr() const { return sqr_ni(*this); }
 #else
-  HDNI Fp2 sqr() const {
+  HD_FP2 Fp2 sqr() const {
     if (BETA == 1) {  // (a0+a1)(a0-a1), 2 a0 a1
       Fp2 r;
       F t = a0 * a1;
