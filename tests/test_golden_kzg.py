@@ -10,6 +10,9 @@ are given, so every check below compares a computation of OURS with points compu
   * Fr NTT (2^12, all orderings):           MSM(monomial, c) = MSM(lagrange, NTT(c)); if one output of the NTT were
                                              wrong, or in the wrong place, the two commitments would differ.
   * KZG commit as PLONK uses it (a9):       commitment in Lagrange form = commitment in canonical form.
+  * G2 MSM (65 points over Fp2):            e(MSM(g1_monomial[:65], c), G2) = e(G1, MSM(g2_monomial, c)) with the big-int
+                                             pairing of oracle/pairing_bls12_381.py - the fixture ties its G2 half to
+                                             its G1 half only through the pairing, so this is what pins Fp2 / G2 results.
 
 CPU here: the big-int oracle, the C++ oracle and the device templates compiled for the host (emulation).  The CUDA path
 runs the same checks in tests/test_gpu_zz_late.py::test_cuda_reproduces_eth_kzg_srs.
@@ -117,6 +120,43 @@ def test_device_templates_on_external_vectors(hostemu, srs):
     assert hostemu.emu_ntt(C.curve_id, P(A), LOGN, 0, ntt.DIF, 0, None, None) == 0
     e = ntt.bit_reverse(ff.unpack_elements(A, C.r, C.fr_limbs))
     assert cpp_msm(srs["LAG"], e) == cpp_msm(srs["MONO"], c)
+
+
+def g2_case(srs):
+    rng = random.Random(5)
+    c = [rng.randrange(C.r) for _ in range(kzg_srs.N_G2)]
+    c[3], c[7] = 0, C.r - 1
+    SC = ff.pack_elements(c, C.r, C.fr_limbs)
+    A = cpp_msm(ec.pack_points(C, 1, srs["mono"][:kzg_srs.N_G2]), c)      # G1 side: pinned by the known answers above
+    return c, SC, A
+
+
+def test_pairing_oracle_and_srs_consistency(srs):
+    from oracle import pairing_bls12_381 as pr
+    e = pr.pairing(C.g1, C.g2)
+    assert e != pr.Fp12.one() and e ** C.r == pr.Fp12.one()
+    F2 = ff.base_field(C, 2)
+    assert pr.pairing(ec.scalar_mul(F, 5, C.g1), C.g2) == pr.pairing(C.g1, ec.scalar_mul(F2, 5, C.g2)) == e ** 5
+    # the fixture: e(tau^k G1, G2) = e(G1, tau^k G2)
+    neg_g1 = ec.affine_neg(F, C.g1)
+    for k in (1, 2, kzg_srs.N_G2 - 1):
+        assert pr.pairing_product_is_one([(srs["mono"][k], C.g2), (neg_g1, srs["g2"][k])])
+    assert not pr.pairing_product_is_one([(srs["mono"][2], C.g2), (neg_g1, srs["g2"][3])])
+
+
+def test_g2_msm_pinned_by_pairing(hostemu, srs):
+    from oracle import pairing_bls12_381 as pr
+    F2 = ff.base_field(C, 2)
+    c, SC, A = g2_case(srs)
+    G2P = ec.pack_points(C, 2, srs["g2"])
+    B = ec.msm_naive(F2, srs["g2"], c)                                     # big-int oracle
+    assert pr.pairing_product_is_one([(A, C.g2), (ec.affine_neg(F, C.g1), B)])
+    out = corelib.msm(C, 2, G2P, SC)                                       # C++ oracle
+    assert ec.from_jac(F2, ec.unpack_points(C, 2, out, ncoords=3)[0]) == B
+    for (cw, pre, tl, ch) in ((8, 0, 16, 64), (12, 1, 64, 256)):           # device templates on the host
+        out = np.zeros(3 * 2 * C.fp_limbs, dtype=np.uint64)
+        assert hostemu.emu_msm(C.curve_id, 2, P(G2P), P(SC), kzg_srs.N_G2, cw, pre, tl, ch, P(out)) == 0
+        assert ec.from_jac(F2, ec.unpack_points(C, 2, out, ncoords=3)[0]) == B
 
 
 def test_gnark_vk_constants():

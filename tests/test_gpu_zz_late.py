@@ -93,6 +93,18 @@ def test_cuda_reproduces_eth_kzg_srs(gpu):
         d.free()
         for t in T.values():
             t.free()
+    # G2: CUDA MSM over the fixture's 65 G2 points, tied to the (known-answer-pinned) G1 side through the pairing
+    from oracle import pairing_bls12_381 as pr
+    from test_golden_kzg import g2_case
+    g2pts = kzg_srs.load()[2]
+    F2 = ff.base_field(C, 2)
+    c2, SC2, A = g2_case({"mono": mono})
+    for precomp in (False, True):
+        t2 = gpu.Table(C.curve_id, 2, ec.pack_points(C, 2, g2pts), precomp=precomp)
+        B = ec.from_jac(F2, ec.unpack_points(C, 2, t2.msm(SC2), ncoords=3)[0])
+        t2.free()
+        assert B == ec.msm_naive(F2, g2pts, c2)
+    assert pr.pairing_product_is_one([(A, C.g2), (ec.affine_neg(F, C.g1), B)])
 
 
 @pytest.mark.xfail(strict=False, reason="orchestrator written after this round's GPU budget was spent: every C-ABI "
