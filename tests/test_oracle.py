@@ -175,3 +175,18 @@ def test_plonk_prover_oracle_verifies(cname):
         l2[1] = (l2[1] + 1) % c.r                                # an unsatisfied trace does not divide
         with pytest.raises(AssertionError):
             pp.prove(c, circ, l2, rr, o, ch, tau)
+
+
+def test_groth16_verifies_under_the_real_pairing():
+    """prove -> Verify as the reference tests it (test/assert_checkcircuit.go:140-144), BLS12-381: the proof points of
+    the trapdoor prover satisfy the pairing equation, a tampered proof does not."""
+    c = CURVES["bls12-381"]
+    cs, W = g16.cubic_r1cs(), g16.cubic_witness(c.r)
+    pk = g16.setup_dlog(c, cs, g16.random_toxic(c, 3))
+    pr = g16.prove_dlog(c, cs, pk, W, 1234567, 7654321)
+    F1, F2 = ff.Fp(c.p), ff.base_field(c, 2)
+    pts = (ec.scalar_mul(F1, pr.ar, c.g1), ec.scalar_mul(F2, pr.bs, c.g2), ec.scalar_mul(F1, pr.krs, c.g1))
+    assert g16.verify_pairing(c, pk, *pts, W)
+    assert not g16.verify_pairing(c, pk, pts[0], pts[1], ec.scalar_mul(F1, pr.krs + 1, c.g1), W)
+    W2 = list(W); W2[1] = (W2[1] + 1) % c.r        # another public input
+    assert not g16.verify_pairing(c, pk, *pts, W2)
