@@ -229,16 +229,16 @@ def verify_dlog(curve, r1cs: R1CS, pk: ProvingKeyDlog, proof: ProofDlog, W) -> b
 def verify_pairing(curve, pk: ProvingKeyDlog, ar_pt, bs_pt, krs_pt, W) -> bool:
     """The reference's acceptance test for a proof (backend/groth16/bls12-381/verify.go:38-140, reached from
     test/assert_checkcircuit.go:140-144): e(Ar, Bs) = e(alpha, beta) * e(sum_i w_i K_i, gamma) * e(Krs, delta), on the
-    PROOF POINTS themselves with a real pairing (BLS12-381 only: oracle/pairing_bls12_381.py).  The verifying key is
-    derived from the trapdoor: alpha G1, beta G2, gamma G2, delta G2, K_i G1."""
-    from . import ec, ff
-    from . import pairing_bls12_381 as pr
-    assert curve.name == "bls12-381"
+    PROOF POINTS themselves with a real pairing (oracle/pairing.py: BN254 and BLS12-381, the curves whose G1 / G2
+    generators the oracle holds).  The verifying key is derived from the trapdoor: alpha G1, beta G2, gamma G2,
+    delta G2, K_i G1."""
+    from . import ec, ff, pairing
+    assert curve.name in pairing.TOWER
     r = curve.r
     F1, F2 = ff.Fp(curve.p), ff.base_field(curve, 2)
     pub = sum(k * W[i] for i, k in enumerate(pk.vk_K)) % r
     neg = lambda P: ec.affine_neg(F1, P)
-    return pr.pairing_product_is_one([
+    return pairing.get(curve).product_is_one([
         (ar_pt, bs_pt),
         (neg(ec.scalar_mul(F1, pk.alpha, curve.g1)), ec.scalar_mul(F2, pk.beta, curve.g2)),
         (neg(ec.scalar_mul(F1, pub, curve.g1)), ec.scalar_mul(F2, pk.gamma, curve.g2)),

@@ -177,10 +177,11 @@ def test_plonk_prover_oracle_verifies(cname):
             pp.prove(c, circ, l2, rr, o, ch, tau)
 
 
-def test_groth16_verifies_under_the_real_pairing():
-    """prove -> Verify as the reference tests it (test/assert_checkcircuit.go:140-144), BLS12-381: the proof points of
-    the trapdoor prover satisfy the pairing equation, a tampered proof does not."""
-    c = CURVES["bls12-381"]
+@pytest.mark.parametrize("cname", ["bn254", "bls12-381"])
+def test_groth16_verifies_under_the_real_pairing(cname):
+    """prove -> Verify as the reference tests it (test/assert_checkcircuit.go:140-144): the proof points of the
+    trapdoor prover satisfy the pairing equation, a tampered proof or another public input does not."""
+    c = CURVES[cname]
     cs, W = g16.cubic_r1cs(), g16.cubic_witness(c.r)
     pk = g16.setup_dlog(c, cs, g16.random_toxic(c, 3))
     pr = g16.prove_dlog(c, cs, pk, W, 1234567, 7654321)
@@ -190,3 +191,23 @@ def test_groth16_verifies_under_the_real_pairing():
     assert not g16.verify_pairing(c, pk, pts[0], pts[1], ec.scalar_mul(F1, pr.krs + 1, c.g1), W)
     W2 = list(W); W2[1] = (W2[1] + 1) % c.r        # another public input
     assert not g16.verify_pairing(c, pk, *pts, W2)
+
+
+@pytest.mark.parametrize("cname", ["bn254", "bls12-381"])
+def test_pairing_oracle_self_checks(cname):
+    """oracle/pairing.py (reduced Tate): non-degenerate, of order r, bilinear in both arguments; on BLS12-381 every
+    product check agrees with the independent ate implementation (oracle/pairing_bls12_381.py)."""
+    from oracle import pairing
+    c = CURVES[cname]
+    T = pairing.get(c)
+    F1, F2 = ff.Fp(c.p), ff.base_field(c, 2)
+    e = T.pairing(c.g1, c.g2)
+    assert e != T.K.one and T.K.pow(e, c.r) == T.K.one
+    a, b = 0xDEADBEEF, 0xC0FFEE123
+    assert T.pairing(ec.scalar_mul(F1, a, c.g1), ec.scalar_mul(F2, b, c.g2)) == T.K.pow(e, a * b % c.r)
+    good = [(ec.scalar_mul(F1, a, c.g1), ec.scalar_mul(F2, b, c.g2)), (ec.affine_neg(F1, c.g1), ec.scalar_mul(F2, a * b % c.r, c.g2))]
+    bad = [good[0], (good[1][0], ec.scalar_mul(F2, (a * b + 1) % c.r, c.g2))]
+    assert T.product_is_one(good) and not T.product_is_one(bad)
+    if cname == "bls12-381":
+        from oracle import pairing_bls12_381 as ate
+        assert ate.pairing_product_is_one(good) and not ate.pairing_product_is_one(bad)
