@@ -91,7 +91,12 @@ struct alignas(16) XYZZ {
     F PPP = P * PP;
     F Q = x * PP;
     F X3 = R.sqr() - PPP - Q.dbl();
+#if defined(GB200_XYZZ_LAZY)
+    if constexpr (is_device_fp<F>::value) y = F::mul_sub(R, Q - X3, y, PPP);   // one reduction instead of two
+    else y = R * (Q - X3) - y * PPP;
+#else
     y = R * (Q - X3) - y * PPP;
+#endif
     x = X3;
     zz = zz * PP;
     zzz = zzz * PPP;

@@ -109,11 +109,16 @@ HD void wide_mul_raw(uint32_t* t, const uint32_t* a, const uint32_t* b) {
 
 // Karatsuba on top of wide_mul_raw (GB200_MONT_KARATSUBA, large fields): one level for N = 12 (3 x 6-limb products:
 // 108 multiplier operations instead of 144), two levels for N = 24 (9 x 6-limb: 324 instead of 576).
+// -DGB200_KARATSUBA_MIN_LIMBS=8 extends it to the 8-limb fields (BN254: 3 x 4-limb = 48 instead of 64, so a Montgomery
+// product is 48 + 72 = 120 multiplier operations instead of 136; the 12 / 24-limb decomposition is unchanged).
+#ifndef GB200_KARATSUBA_MIN_LIMBS
+#define GB200_KARATSUBA_MIN_LIMBS 12
+#endif
 //   a = aL + aH B, b = bL + bH B (B = 2^(32 N/2)):  a b = z0 + (z1 - z0 - z2) B + z2 B^2,
 //   z0 = aL bL, z2 = aH bH, z1 = (aL + aH)(bL + bH) with the two carry bits of the sums handled apart.
 template <int N>
 HD void wide_mul_karatsuba(uint32_t* t, const uint32_t* a, const uint32_t* b) {
-  if constexpr (N < 12 || (N % 2) != 0) {
+  if constexpr (N < GB200_KARATSUBA_MIN_LIMBS || (N % 2) != 0) {
     wide_mul_raw<N>(t, a, b);
   } else {
     constexpr int H = N / 2;
@@ -317,7 +322,7 @@ struct alignas(16) Fp {
 #if defined(GB200_MONT_KARATSUBA)
   // large fields: Karatsuba product + separate reduction (fewer multiplier operations than the fused product)
   HD static void mul_dispatch(uint32_t* r, const uint32_t* a, const uint32_t* b) {
-    if constexpr (N >= 12) { uint32_t t[2 * N]; wide_mul_karatsuba<N>(t, a, b); mont_reduce_wide<P>(r, t); }
+    if constexpr (N >= GB200_KARATSUBA_MIN_LIMBS) { uint32_t t[2 * N]; wide_mul_karatsuba<N>(t, a, b); mont_reduce_wide<P>(r, t); }
     else mont_mul_raw<P>(r, a, b);
   }
 #else
@@ -351,6 +356,24 @@ struct alignas(16) Fp {
 #else
   HD Fp sqr() const { return (*this) * (*this); }
 #endif
+  // a*b - c*d with ONE Montgomery reduction: a b + (p^2 - c d) < 2 p^2 < p R (top bit of p clear), reduced once.
+  // Used by the XYZZ mixed addition under GB200_XYZZ_LAZY (Y3 = R (Q - X3) - Y1 PPP): one reduction (N^2 + N
+  // multiplier operations) less per addition.  Bit-exact with a*b - c*d (emulation: test_wide_arithmetic).
+  HD static Fp mul_sub(const Fp& a, const Fp& b, const Fp& c, const Fp& d) {
+    uint32_t t0[2 * N], t1[2 * N], q[2 * N];
+#if defined(GB200_MONT_KARATSUBA)
+    wide_mul_karatsuba<N>(t0, a.l, b.l);
+    wide_mul_karatsuba<N>(t1, c.l, d.l);
+#else
+    wide_mul_raw<N>(t0, a.l, b.l);
+    wide_mul_raw<N>(t1, c.l, d.l);
+#endif
+#pragma unroll
+    for (int k = 0; k < 2 * N; k++) q[k] = P::psq(k);
+    limbs_sub<2 * N>(q, q, t1);
+    limbs_add<2 * N>(t0, t0, q);
+    Fp r; mont_reduce_wide<P>(r.l, t0); return r;
+  }
   HD Fp neg() const { return is_zero() ? *this : (zero() - *this); }
   HD Fp dbl() const { return *this + *this; }
   // Montgomery -> canonical (multiply by 1) and back

@@ -38,6 +38,14 @@ int field_op(int op, const void* a_, const void* b_, void* out_) {
     case 5: r = a.sqr(); break;
     case 6: r = a.dbl(); break;
     case 7: r = a.inverse_gcd(); break;
+    case 8:   // a * b[0] - b[1] * b[2] with one reduction (Fp only)
+      if constexpr (is_device_fp<F>::value) {
+        const F* b = reinterpret_cast<const F*>(b_);
+        r = F::mul_sub(a, b[0], b[1], b[2]);
+        break;
+      } else {
+        return -1;
+      }
     default: return -1;
   }
   *reinterpret_cast<F*>(out_) = r;
@@ -523,6 +531,12 @@ int emu_build_options(void) {
 #endif
 #if defined(GB200_MONT_KARATSUBA)
   v |= 4;
+#endif
+#if defined(GB200_MONT_KARATSUBA) && GB200_KARATSUBA_MIN_LIMBS <= 8
+  v |= 8;
+#endif
+#if defined(GB200_XYZZ_LAZY)
+  v |= 16;
 #endif
   return v;
 }

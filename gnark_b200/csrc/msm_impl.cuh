@@ -47,8 +47,16 @@ static __global__ void k_msm_task_counts(const uint32_t* __restrict__ off, uint3
 }
 
 // one thread per task: partial[t] = sum of <= task_len consecutive entries of one bucket
+// -DGB200_ACC_MIN_BLOCKS=k: ask ptxas for k resident blocks per SM (register cap 65536 / (128 k), rounded down to the
+// allocation unit) - A/B knob for the arithmetic variants that land just above a register step
+#if defined(GB200_ACC_MIN_BLOCKS)
+// (applies to the 8-limb base-field kernels only: BN254 G1; larger fields keep the compiler's allocation)
+#define GB200_ACC_BOUNDS __launch_bounds__(128, (sizeof(F) <= 32) ? GB200_ACC_MIN_BLOCKS : 1)
+#else
+#define GB200_ACC_BOUNDS __launch_bounds__(128)
+#endif
 template <class F>
-__global__ void __launch_bounds__(128) k_msm_accumulate(MsmPlan pl, const Affine<F>* __restrict__ table,
+__global__ void GB200_ACC_BOUNDS k_msm_accumulate(MsmPlan pl, const Affine<F>* __restrict__ table,
                                                         const uint32_t* __restrict__ svals,
                                                         const uint32_t* __restrict__ off,
                                                         const uint32_t* __restrict__ task_off,

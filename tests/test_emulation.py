@@ -99,6 +99,26 @@ def test_wide_arithmetic(hostemu, c):
 
 
 @pytest.mark.parametrize("c", ALL, ids=lambda c: c.name)
+@pytest.mark.parametrize("opt", (False, True), ids=("default", "opt"))
+def test_mul_sub_single_reduction(hostemu, hostemu_opt, c, opt):
+    """Fp::mul_sub = a b - c d through ONE Montgomery reduction of a b + (p^2 - c d) (GB200_XYZZ_LAZY uses it for Y3 of
+    the mixed addition); extremes of both products included; default wide products and the Karatsuba ones"""
+    lib = hostemu_opt if opt else hostemu
+    rng = random.Random(31)
+    q, L = c.p, c.fp_limbs
+    fid = c.curve_id * 2
+    ext = [0, 1, q - 1, q - 2]
+    cases = [(a, b, cc, d) for a in ext for b in (0, q - 1) for cc in (0, q - 1) for d in ext]
+    cases += [tuple(rng.randrange(q) for _ in range(4)) for _ in range(60)]
+    for a, b, cc, d in cases:
+        A = ff.pack_elements([a], q, L)
+        B = ff.pack_elements([b, cc, d], q, L)
+        O = np.zeros_like(A)
+        assert lib.emu_field_op(fid, 8, P(A), P(B), P(O)) == 0
+        assert ff.unpack_elements(O, q, L)[0] == (a * b - cc * d) % q, (c.name, hex(a), hex(b), hex(cc), hex(d))
+
+
+@pytest.mark.parametrize("c", ALL, ids=lambda c: c.name)
 def test_optional_paths_field_ops(hostemu_opt, c):
     """field / Fp2 operations of the library compiled with GB200_MONT_SQR + GB200_FP2_LAZY against big-int"""
     test_field_ops.__wrapped__(hostemu_opt, c) if hasattr(test_field_ops, "__wrapped__") else test_field_ops(hostemu_opt, c)
@@ -106,7 +126,7 @@ def test_optional_paths_field_ops(hostemu_opt, c):
         test_fp2_ops(hostemu_opt, c)
 
 
-@pytest.mark.parametrize("c", [CURVES["bn254"], CURVES["bls12-377"]], ids=lambda c: c.name)
+@pytest.mark.parametrize("c", [CURVES["bn254"], CURVES["bls12-377"], CURVES["bw6-761"]], ids=lambda c: c.name)
 @pytest.mark.parametrize("group", (1, 2))
 def test_optional_paths_msm(hostemu_opt, c, group):
     """one MSM per group through the optional arithmetic paths (G2 of BLS12-377 exercises BETA = 5 in the lazy product)"""

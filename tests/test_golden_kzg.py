@@ -96,12 +96,13 @@ def test_ntt_pinned_through_commitments(srs):
     assert ff.unpack_elements(A, C.r, C.fr_limbs) == e_br
 
 
-def test_device_templates_on_external_vectors(hostemu, srs):
-    """the CUDA kernels' per-thread code, compiled for the host (tests/test_emulation.py), on the external vectors"""
+def test_device_templates_on_external_vectors(hostemu, hostemu_opt, srs):
+    """the CUDA kernels' per-thread code, compiled for the host (tests/test_emulation.py), on the external vectors;
+    the optional arithmetic paths (the A/B builds: dedicated squaring, Karatsuba, single-reduction Y3) as well"""
     base, sc, (other, j) = kat_cases(random.Random(3))[3]
-    for (cw, pre, tl, ch) in ((8, 0, 16, 64), (10, 0, 32, 128)):
+    for lib, (cw, pre, tl, ch) in ((hostemu, (8, 0, 16, 64)), (hostemu, (10, 0, 32, 128)), (hostemu_opt, (9, 0, 64, 128))):
         out = np.zeros(3 * C.fp_limbs, dtype=np.uint64)
-        assert hostemu.emu_msm(C.curve_id, 1, P(srs[base]), P(ff.pack_elements(sc, C.r, C.fr_limbs)), N, cw, pre, tl, ch, P(out)) == 0
+        assert lib.emu_msm(C.curve_id, 1, P(srs[base]), P(ff.pack_elements(sc, C.r, C.fr_limbs)), N, cw, pre, tl, ch, P(out)) == 0
         assert ec.from_jac(F, ec.unpack_points(C, 1, out, ncoords=3)[0]) == srs[other][j]
     # precomputed-window tables (one emulated doubling chain per point and window: kept to the 64-point identity
     # (1/64) sum_m monomial[64 m] = sum_j lagrange[64 j], right-hand side by big-int additions)
