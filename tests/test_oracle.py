@@ -26,7 +26,7 @@ def test_constants(c):
         assert ec.is_on_curve(F, c.g1, c.b % p)
         assert ec.scalar_mul(F, r, c.g1) is ec.INF
     if c.g2 is not None:
-        F2 = ff.Fp2(p, c.fp2_nonresidue)
+        F2 = ff.base_field(c, 2)          # Fp2, or Fp for BW6-761
         assert ec.scalar_mul(F2, r, c.g2) is ec.INF
 
 
