@@ -119,14 +119,15 @@ int32_t msm_on_stream(DeviceCtx* ctx, b200_table_s* t, size_t off, size_t n, con
   if (ba_levels < 0 || t->fmt52) ba_levels = 0;
   if (ba_levels > 12) ba_levels = 12;
   CK(t->ops->ws_bytes((uint32_t)n, (uint32_t)t->n, t->c, t->precomp, task_len, chunk, ba_levels, &ws_bytes));
-  void* ws = nullptr;
-  CK(cudaMallocAsync(&ws, ws_bytes, ctx->stream));
+  AsyncBuf ws_buf;
+  CK(ws_buf.alloc(ws_bytes, ctx->stream));
+  void* ws = ws_buf.p;
   MsmHybrid hy{t->d_points52, t->hybrid52_of_16, ctx->aux_stream, ctx->aux_fork_ev, ctx->aux_join_ev, ba_levels};
   cudaError_t e = t->ops->run(ctx->stream, (uint32_t)n, (uint32_t)t->n, (uint32_t)off, t->c, t->precomp, task_len, chunk,
                               t->d_points, d_scalars, d_out, ws, stage_events, pipelined ? ctx->tail_stream : nullptr,
                               ctx->fork_ev, t->fmt52, (t->hybrid52_of_16 > 0 || ba_levels > 0) ? &hy : nullptr);
   // the workspace is last used by the tail kernels
-  cudaError_t e2 = cudaFreeAsync(ws, pipelined ? ctx->tail_stream : ctx->stream);
+  cudaError_t e2 = ws_buf.release_on(pipelined ? ctx->tail_stream : ctx->stream);
   if (pipelined && e == cudaSuccess) {
     cudaError_t e3 = cudaEventRecord(ctx->tail_ev, ctx->tail_stream);
     if (e3 != cudaSuccess) return cuda_fail("cudaEventRecord", e3);
@@ -277,11 +278,11 @@ int32_t b200_table_upload(int32_t dev, int32_t curve, int32_t group, const void*
   if (t->fmt52) {
     t->bytes = slabs * n * ops->affine52_bytes;
     CK(cudaMalloc(&t->d_points, t->bytes));
-    void* d_src = nullptr;
-    CK(cudaMallocAsync(&d_src, n * ops->affine_bytes, ctx->stream));
-    CK(cudaMemcpyAsync(d_src, points, n * ops->affine_bytes, kind, ctx->stream));
-    CK(ops->precompute52(ctx->stream, (uint32_t)n, t->nwin, t->c, d_src, t->d_points));
-    CK(cudaFreeAsync(d_src, ctx->stream));
+    AsyncBuf d_src;
+    CK(d_src.alloc(n * ops->affine_bytes, ctx->stream));
+    CK(cudaMemcpyAsync(d_src.p, points, n * ops->affine_bytes, kind, ctx->stream));
+    CK(ops->precompute52(ctx->stream, (uint32_t)n, t->nwin, t->c, d_src.p, t->d_points));
+    CK(d_src.release_on(ctx->stream));
   } else {
     t->bytes = slabs * (n ? n : 1) * ops->affine_bytes;
     CK(cudaMalloc(&t->d_points, t->bytes));
@@ -350,18 +351,20 @@ int32_t b200_fixed_base_batch(int32_t dev, int32_t curve, int32_t group, const v
   rc = msm_join(ctx); if (rc) return rc;
   void* d_sc = const_cast<void*>(scalars);
   void* d_out = out_affine;
+  AsyncBuf sc_buf, out_buf;
   if (!scalars_on_device) {
-    CK(cudaMallocAsync(&d_sc, n * ops->fr_bytes, ctx->stream));
+    CK(sc_buf.alloc(n * ops->fr_bytes, ctx->stream));
+    d_sc = sc_buf.p;
     CK(cudaMemcpyAsync(d_sc, scalars, n * ops->fr_bytes, cudaMemcpyHostToDevice, ctx->stream));
   }
-  if (!out_on_device) CK(cudaMallocAsync(&d_out, n * ops->affine_bytes, ctx->stream));
+  if (!out_on_device) { CK(out_buf.alloc(n * ops->affine_bytes, ctx->stream)); d_out = out_buf.p; }
   int c = env_int("GB200_FIXED_BASE_WINDOW", 0);
   if (c < 2 || c > 16) c = fixed_base_window_for(n);
   cudaError_t e = ops->fixed_base(ctx->stream, base_affine, d_sc, n, c, d_out);
   if (e == cudaSuccess && !out_on_device)
     e = cudaMemcpyAsync(out_affine, d_out, n * ops->affine_bytes, cudaMemcpyDeviceToHost, ctx->stream);
-  if (!scalars_on_device) cudaFreeAsync(d_sc, ctx->stream);
-  if (!out_on_device) cudaFreeAsync(d_out, ctx->stream);
+  sc_buf.release_on(ctx->stream);
+  out_buf.release_on(ctx->stream);
   cudaError_t e2 = cudaStreamSynchronize(ctx->stream);   // host pointers are only borrowed for the call
   if (e != cudaSuccess) return cuda_fail("fixed_base_batch", e);
   if (e2 != cudaSuccess) return cuda_fail("fixed_base_batch", e2);
@@ -407,22 +410,21 @@ int32_t b200_msm(b200_table_t t, size_t off, size_t n, const void* scalars, int3
   if (!t) return set_error("msm: null table");
   if (n && !scalars) return set_error("msm: null scalars");
   GB_DEVICE(ctx, t->dev); [[maybe_unused]] int32_t rc = 0;
-  void* d_sc = nullptr;
-  void* d_out = nullptr;
-  CK(cudaMallocAsync(&d_out, t->ops->jac_bytes, ctx->stream));
+  AsyncBuf d_sc, d_out;      // released on every path, early error returns included
+  CK(d_out.alloc(t->ops->jac_bytes, ctx->stream));
   const void* sc = scalars;
   if (!on_dev && n) {
-    CK(cudaMallocAsync(&d_sc, n * t->ops->fr_bytes, ctx->stream));
-    CK(cudaMemcpyAsync(d_sc, scalars, n * t->ops->fr_bytes, cudaMemcpyHostToDevice, ctx->stream));
-    sc = d_sc;
+    CK(d_sc.alloc(n * t->ops->fr_bytes, ctx->stream));
+    CK(cudaMemcpyAsync(d_sc.p, scalars, n * t->ops->fr_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    sc = d_sc.p;
   }
-  rc = msm_on_stream(ctx, t, off, n, sc, d_out);
+  rc = msm_on_stream(ctx, t, off, n, sc, d_out.p);
   if (rc == 0) {
-    cudaError_t e = cudaMemcpyAsync(out_host, d_out, t->ops->jac_bytes, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t e = cudaMemcpyAsync(out_host, d_out.p, t->ops->jac_bytes, cudaMemcpyDeviceToHost, ctx->stream);
     if (e != cudaSuccess) rc = cuda_fail("msm result copy", e);
   }
-  if (d_sc) cudaFreeAsync(d_sc, ctx->stream);
-  cudaFreeAsync(d_out, ctx->stream);
+  d_sc.release_on(ctx->stream);
+  d_out.release_on(ctx->stream);
   cudaError_t e = cudaStreamSynchronize(ctx->stream);
   if (rc) return rc;
   if (e != cudaSuccess) return cuda_fail("msm", e);
@@ -439,28 +441,27 @@ int32_t b200_msm_submit(b200_table_t t, size_t off, size_t n, const void* scalar
   if (!t) return set_error("msm_submit: null table");
   if (!out_host || (n && !scalars_host)) return set_error("msm_submit: null argument");
   GB_DEVICE(ctx, t->dev); [[maybe_unused]] int32_t rc = 0;
-  void* d_sc = nullptr;
-  void* d_out = nullptr;
-  CK(cudaMallocAsync(&d_out, t->ops->jac_bytes, ctx->stream));
+  AsyncBuf d_sc, d_out;
+  CK(d_out.alloc(t->ops->jac_bytes, ctx->stream));
   if (n) {
-    CK(cudaMallocAsync(&d_sc, n * t->ops->fr_bytes, ctx->copy_stream));
-    CK(cudaMemcpyAsync(d_sc, scalars_host, n * t->ops->fr_bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+    CK(d_sc.alloc(n * t->ops->fr_bytes, ctx->copy_stream));
+    CK(cudaMemcpyAsync(d_sc.p, scalars_host, n * t->ops->fr_bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
     CK(cudaEventRecord(ctx->copy_ev, ctx->copy_stream));
     CK(cudaStreamWaitEvent(ctx->stream, ctx->copy_ev, 0));
   }
-  rc = msm_on_stream(ctx, t, off, n, d_sc, d_out, nullptr, /*pipelined=*/true);
+  rc = msm_on_stream(ctx, t, off, n, d_sc.p, d_out.p, nullptr, /*pipelined=*/true);
   // the result is produced on the tail stream when the call was pipelined (n > 0), else on the main stream
   cudaStream_t res_stream = (n > 0) ? ctx->tail_stream : ctx->stream;
   if (rc == 0) {
-    cudaError_t e = cudaMemcpyAsync(out_host, d_out, t->ops->jac_bytes, cudaMemcpyDeviceToHost, res_stream);
+    cudaError_t e = cudaMemcpyAsync(out_host, d_out.p, t->ops->jac_bytes, cudaMemcpyDeviceToHost, res_stream);
     if (e != cudaSuccess) rc = cuda_fail("msm_submit result copy", e);
     if (rc == 0 && n > 0) {   // the join point must cover the download too
       e = cudaEventRecord(ctx->tail_ev, ctx->tail_stream);
       if (e != cudaSuccess) rc = cuda_fail("cudaEventRecord", e);
     }
   }
-  if (d_sc) cudaFreeAsync(d_sc, ctx->stream);
-  cudaFreeAsync(d_out, res_stream);
+  d_sc.release_on(ctx->stream);       // last read by the decompose kernel on the main stream
+  d_out.release_on(res_stream);
   return rc;
   GUARD_END
 }
@@ -521,14 +522,16 @@ int32_t b200_ntt(b200_domain_t d, void* data, int32_t on_dev, int32_t inverse, i
   GB_DEVICE(ctx, d->dev); [[maybe_unused]] int32_t rc = 0;
   const size_t bytes = ((size_t)1 << d->logn) * d->ops->fr_bytes;
   void* buf = data;
+  AsyncBuf tmp;
   if (!on_dev) {
-    CK(cudaMallocAsync(&buf, bytes, ctx->stream));
+    CK(tmp.alloc(bytes, ctx->stream));
+    buf = tmp.p;
     CK(cudaMemcpyAsync(buf, data, bytes, cudaMemcpyHostToDevice, ctx->stream));
   }
   cudaError_t e = d->ops->ntt(ctx->stream, d->impl, buf, inverse, decimation, on_coset);
   if (!on_dev) {
     if (e == cudaSuccess) e = cudaMemcpyAsync(data, buf, bytes, cudaMemcpyDeviceToHost, ctx->stream);
-    cudaFreeAsync(buf, ctx->stream);
+    tmp.release_on(ctx->stream);
   }
   cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
   if (e != cudaSuccess) return cuda_fail("ntt", e);
@@ -545,18 +548,20 @@ int32_t b200_groth16_compute_h(b200_domain_t d, const void* a, const void* b, co
   const size_t n = (size_t)1 << d->logn;
   if (len > n) return set_error("compute_h: len exceeds the domain");
   const size_t fb = d->ops->fr_bytes;
+  AsyncBuf vb[3];
   void* v[3] = {nullptr, nullptr, nullptr};
   const void* src[3] = {a, b, c};
   const cudaMemcpyKind kind = in_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
   for (int k = 0; k < 3; k++) {
-    CK(cudaMallocAsync(&v[k], n * fb, ctx->stream));
+    CK(vb[k].alloc(n * fb, ctx->stream));
+    v[k] = vb[k].p;
     if (len) CK(cudaMemcpyAsync(v[k], src[k], len * fb, kind, ctx->stream));
     if (len < n) CK(cudaMemsetAsync((char*)v[k] + len * fb, 0, (n - len) * fb, ctx->stream));
   }
   cudaError_t e = d->ops->compute_h(ctx->stream, d->impl, v[0], v[1], v[2]);
   if (e == cudaSuccess)
     e = cudaMemcpyAsync(h_out, v[0], n * fb, out_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->stream);
-  for (int k = 0; k < 3; k++) cudaFreeAsync(v[k], ctx->stream);
+  for (int k = 0; k < 3; k++) vb[k].release_on(ctx->stream);
   cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
   if (e != cudaSuccess) return cuda_fail("compute_h", e);
   if (e2 != cudaSuccess) return cuda_fail("compute_h", e2);

@@ -154,9 +154,14 @@ cudaError_t fixed_base_enqueue(cudaStream_t st, const Affine<F>& base, const Fr*
   Affine<F>* table = nullptr;
   XYZZ<F>* tmp = nullptr;
   cudaError_t e;
+  auto release = [&]() {                 // stream-ordered: safe after the kernels above it were enqueued
+    if (tmp) cudaFreeAsync(tmp, st);
+    if (table) cudaFreeAsync(table, st);
+    if (Pw) cudaFreeAsync(Pw, st);
+  };
   if ((e = cudaMallocAsync(&Pw, (size_t)pl.nwin * sizeof(Affine<F>), st)) != cudaSuccess) return e;
-  if ((e = cudaMallocAsync(&table, entries * sizeof(Affine<F>), st)) != cudaSuccess) return e;
-  if ((e = cudaMallocAsync(&tmp, tmp_pts * sizeof(XYZZ<F>), st)) != cudaSuccess) return e;
+  if ((e = cudaMallocAsync(&table, entries * sizeof(Affine<F>), st)) != cudaSuccess) { release(); return e; }
+  if ((e = cudaMallocAsync(&tmp, tmp_pts * sizeof(XYZZ<F>), st)) != cudaSuccess) { release(); return e; }
   k_fb_window_bases<F><<<(pl.nwin + 63) / 64, 64, 0, st>>>(base, pl.c, pl.nwin, Pw);
   k_fb_table<F><<<(unsigned)((entries + 127) / 128), 128, 0, st>>>(pl, Pw, tmp);
   const size_t g1 = (entries + FB_CHUNK - 1) / FB_CHUNK;
@@ -165,9 +170,7 @@ cudaError_t fixed_base_enqueue(cudaStream_t st, const Affine<F>& base, const Fr*
   const size_t g2 = (n + FB_CHUNK - 1) / FB_CHUNK;
   k_fb_to_affine<F><<<(unsigned)((g2 + 127) / 128), 128, 0, st>>>(tmp, d_out, n);
   e = cudaGetLastError();
-  cudaFreeAsync(tmp, st);
-  cudaFreeAsync(table, st);
-  cudaFreeAsync(Pw, st);
+  release();
   return e;
 }
 #endif  // __CUDACC__
