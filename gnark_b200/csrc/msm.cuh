@@ -108,7 +108,24 @@ HD Affine<F> msm_load_point(const Affine<F>* table, uint32_t val) {
 template <class F>
 HD XYZZ<F> msm_accumulate_range(const Affine<F>* table, const uint32_t* vals, uint32_t begin, uint32_t end) {
   XYZZ<F> acc = XYZZ<F>::inf();
+#if defined(GB200_ACC_PREFETCH)
+  // A/B knob: the gather of entry e+1 (a random 64..192 B read from a GiB-sized table, ~10 % of the issue slots are
+  // long-scoreboard stalls in the ncu capture) is started as an L2 prefetch while the addition of entry e runs
+  if (begin >= end) return acc;
+  uint32_t v = vals[begin];
+  for (uint32_t e = begin; e < end; e++) {
+    const uint32_t cur = v;
+    if (e + 1 < end) {
+      v = vals[e + 1];
+      const char* nxt = reinterpret_cast<const char*>(table + (v & 0x7fffffffu));
+      ptx::prefetch_l2(nxt);
+      if (sizeof(Affine<F>) > 128) ptx::prefetch_l2(nxt + 128);
+    }
+    acc.add_mixed(msm_load_point(table, cur));
+  }
+#else
   for (uint32_t e = begin; e < end; e++) acc.add_mixed(msm_load_point(table, vals[e]));
+#endif
   return acc;
 }
 

@@ -102,5 +102,14 @@ HD uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) {
 }
 HD uint32_t mul_lo(uint32_t a, uint32_t b) { return a * b; }
 
+// L2 prefetch of the line holding p (no register destination, no fault on a bad address); no-op on the host
+HD void prefetch_l2(const void* p) {
+#ifdef __CUDA_ARCH__
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+  (void)p;
+#endif
+}
+
 }  // namespace ptx
 }  // namespace gb200

@@ -44,6 +44,7 @@ timeout 600 python tools/sweep_msm.py bw6-761 1 18 --set GB200_MSM_BATCH_AFFINE=
 #   make -C gnark_b200/csrc opt OPTFLAGS=-DGB200_INLINE_FP2 OPTNAME=inlfp2     -> Fp2 product / square inlined (G2)
 #   make -C gnark_b200/csrc opt OPTFLAGS="-DGB200_MONT_SQR -DGB200_XYZZ_LAZY -DGB200_ACC_MIN_BLOCKS=5" OPTNAME=sqrxlazy5
 #     (BN254 G1 accumulate: -9.4 % IMAD.WIDE at 96 registers - the first candidate, profiles/r01_sass_stats.md)
+#   make -C gnark_b200/csrc opt OPTFLAGS=-DGB200_ACC_PREFETCH OPTNAME=prefetch -> L2 prefetch of the next gathered point
 #   or all of them:  make -C gnark_b200/csrc variants
 for lib in gnark_b200/lib/libgnark_b200_*.so; do
   [ -f "$lib" ] || continue
