@@ -1,16 +1,27 @@
 #!/usr/bin/env bash
 # One gpurun call that validates everything written without a GPU and A/B-tests the opt-in kernels:
-#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/gpu_session.sh'
-# Outputs land in gpurun_out/ (copy what is worth keeping into profiles/).
+#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/gpu_session.sh 1 2'        # parity + bench        (~10 min)
+#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/gpu_session.sh 3v'         # arithmetic variants    (~8 min)
+#   /usr/local/graft/bin/gpurun --timeout 1800 -- 'bash tools/gpu_session.sh 3 3b'       # knob sweeps            (~20 min)
+#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/gpu_session.sh 2b 4'       # other configs + ncu
+#   /usr/local/graft/bin/gpurun --gpus 2 --timeout 1500 -- 'bash tools/gpu_session.sh 5' # multi-GPU
+# Stages: 1 parity, 2 bench, 2b configs, 3 MSM knob sweeps, 3v compile-time variants, 3b NTT tiles, 4 ncu, 5 multi-GPU;
+# no argument = all of them.  Outputs land in gpurun_out/ (copy what is worth keeping into profiles/).
 set -u
 OUT=gpurun_out
 mkdir -p $OUT
 export PYTHONUNBUFFERED=1
+STAGES=" ${*:-1 2 2b 3 3v 3b 4 5} "
+want() { [[ "$STAGES" == *" $1 "* ]]; }
+: >> $OUT/session.log
 
-echo "== 1. parity suite (validated part first, then the late file)" | tee $OUT/session.log
+if want 1; then
+echo "== 1. parity suite (validated part first, then the late file)" | tee -a $OUT/session.log
 timeout 900 python -m pytest tests -q -m gpu -x --deselect tests/test_gpu_zz_late.py 2>&1 | tail -5 | tee -a $OUT/session.log
 timeout 600 python -m pytest tests/test_gpu_zz_late.py -q -m gpu -rxX 2>&1 | tail -40 | tee -a $OUT/session.log
+fi
 
+if want 2; then
 echo "== 2. bench, 1 GPU (with the asynchronous host path)" | tee -a $OUT/session.log
 timeout 600 python bench.py --steps 20 --warmup 3 --e2e-submit > $OUT/bench_n1.json 2> $OUT/bench_n1.err
 tail -c 2000 $OUT/bench_n1.json | tee -a $OUT/session.log
@@ -18,10 +29,14 @@ tail -c 2000 $OUT/bench_n1.json | tee -a $OUT/session.log
 GB200_STAGE_THREADS=4 timeout 600 python bench.py --steps 5 --warmup 3 > $OUT/bench_n1_stage4.json 2>> $OUT/bench_n1.err
 python -c "import json;d=json.load(open('$OUT/bench_n1_stage4.json'));print('groth16 with GB200_STAGE_THREADS=4:', d.get('groth16'))" | tee -a $OUT/session.log
 
+fi
+if want 2b; then
 echo "== 2b. other configs on this GPU count: sharded MSMs (2^22 total), PLONK building blocks and the end-to-end PLONK prove" | tee -a $OUT/session.log
 timeout 900 python tools/bench_configs.py --total-log 22 --steps 3 > $OUT/configs.jsonl 2>> $OUT/session.err
 cut -c1-600 $OUT/configs.jsonl | tee -a $OUT/session.log
 
+fi
+if want 3; then
 echo "== 3. MSM knob sweeps (every configuration is checked against the known-dlog oracle)" | tee -a $OUT/session.log
 timeout 600 python tools/sweep_msm.py bn254 1 20 --set GB200_MSM_WINDOW=16,17,18,19,20,22 > $OUT/sweep_bn254_window.jsonl 2>> $OUT/session.err
 timeout 600 python tools/sweep_msm.py bn254 1 20 --set GB200_MSM_HYBRID=0,12,25,38,50,62 > $OUT/sweep_bn254_hybrid.jsonl 2>> $OUT/session.err
@@ -32,6 +47,9 @@ timeout 600 python tools/sweep_msm.py bn254 2 20 --set GB200_MSM_BATCH_AFFINE=0,
 timeout 600 python tools/sweep_msm.py bls12-381 1 20 --set GB200_MSM_BATCH_AFFINE=0,3,5 > $OUT/sweep_bls381_ba.jsonl 2>> $OUT/session.err
 timeout 600 python tools/sweep_msm.py bw6-761 1 18 --set GB200_MSM_HYBRID=0,30,50 > $OUT/sweep_bw6_hybrid.jsonl 2>> $OUT/session.err
 timeout 600 python tools/sweep_msm.py bw6-761 1 18 --set GB200_MSM_BATCH_AFFINE=0,4 > $OUT/sweep_bw6_ba.jsonl 2>> $OUT/session.err
+fi
+if want 3v; then
+echo "== 3v. compile-time arithmetic / calling-convention variants" | tee -a $OUT/session.log
 # compile-time arithmetic variants (build before the call, they travel with the snapshot):
 #   make -C gnark_b200/csrc opt                                              -> libgnark_b200_opt.so (all three)
 #   make -C gnark_b200/csrc opt OPTFLAGS=-DGB200_MONT_SQR OPTNAME=sqr         -> libgnark_b200_sqr.so
@@ -46,22 +64,40 @@ timeout 600 python tools/sweep_msm.py bw6-761 1 18 --set GB200_MSM_BATCH_AFFINE=
 #     (BN254 G1 accumulate: -9.4 % IMAD.WIDE at 96 registers - the first candidate, profiles/r01_sass_stats.md)
 #   make -C gnark_b200/csrc opt OPTFLAGS=-DGB200_ACC_PREFETCH OPTNAME=prefetch -> L2 prefetch of the next gathered point
 #   or all of them:  make -C gnark_b200/csrc variants
+# each library runs only the configurations its flags can change (a run = table upload + precompute + 10 MSMs, ~15 s)
 for lib in gnark_b200/lib/libgnark_b200_*.so; do
   [ -f "$lib" ] || continue
   tag=$(basename $lib .so | sed 's/libgnark_b200_//')
-  for cfg in "bn254 1 20" "bn254 2 20" "bls12-381 1 20" "bw6-761 1 18"; do
+  case "$tag" in
+    sqr|xlazy|sqrxlazy|sqrxlazy5|kara8) cfgs=("bn254 1 20") ;;
+    lazy|inlfp2)                        cfgs=("bn254 2 20") ;;
+    inl12)                              cfgs=("bls12-381 1 20") ;;
+    kara)                               cfgs=("bls12-381 1 20" "bw6-761 1 18") ;;
+    byval)                              cfgs=("bn254 2 20" "bls12-381 1 20" "bw6-761 1 18") ;;
+    *)                                  cfgs=("bn254 1 20" "bn254 2 20" "bls12-381 1 20" "bw6-761 1 18") ;;   # opt, prefetch
+  esac
+  for cfg in "${cfgs[@]}"; do
     set -- $cfg
-    GB200_LIB=$PWD/$lib timeout 600 python tools/sweep_msm.py $1 $2 $3 --set GB200_MSM_BATCH_AFFINE=0,5 \
+    GB200_LIB=$PWD/$lib timeout 300 python tools/sweep_msm.py $1 $2 $3 \
         | sed "s/^{/{\"lib\": \"$tag\", /" >> $OUT/sweep_optlib.jsonl 2>> $OUT/session.err
   done
 done
-cat $OUT/sweep_*.jsonl | cut -c1-400 | tee -a $OUT/session.log
+# the default library on the same four configurations, same script, for the comparison
+for cfg in "bn254 1 20" "bn254 2 20" "bls12-381 1 20" "bw6-761 1 18"; do
+  set -- $cfg
+  timeout 300 python tools/sweep_msm.py $1 $2 $3 | sed "s/^{/{\"lib\": \"default\", /" >> $OUT/sweep_optlib.jsonl 2>> $OUT/session.err
+done
+fi
+cat $OUT/sweep_*.jsonl 2>/dev/null | cut -c1-400 | tee -a $OUT/session.log
 
+if want 3b; then
 echo "== 3b. NTT tile sizes" | tee -a $OUT/session.log
 timeout 600 python tools/sweep_ntt.py --curve bn254 --logs 20,22,24 > $OUT/sweep_ntt.jsonl 2>> $OUT/session.err
 timeout 600 python tools/sweep_ntt.py --curve bls12-381 --logs 22 >> $OUT/sweep_ntt.jsonl 2>> $OUT/session.err
 cat $OUT/sweep_ntt.jsonl | tee -a $OUT/session.log
 
+fi
+if want 4; then
 echo "== 4. ncu: launch list of one Groth16-sized step and full captures of the NTT pass and the G2 accumulate" | tee -a $OUT/session.log
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_g2.csv \
     python tools/run_msm.py bn254 2 20 1 > $OUT/ncu_g2.log 2>&1
@@ -76,6 +112,8 @@ d = lib.Domain(lib.BN254, 22)
 x = torch.randint(0, 1 << 60, ((1 << 22) * 4,), dtype=torch.int64, device='cuda')
 d.ntt_async(x); lib.sync(0)
 " > $OUT/ncu_ntt.log 2>&1
+fi
+if want 5; then
 echo "== 5. (only under gpurun --gpus 2/4/8) sharded NTT and the sharded configs" | tee -a $OUT/session.log
 NG=$(python -c "import torch; print(torch.cuda.device_count())")
 if [ "$NG" -gt 1 ]; then
@@ -92,5 +130,6 @@ if [ "$NG" -gt 1 ]; then
   GB200_STEP_PROFILE=1 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 \
       --master-port 29614 bench.py --gpus $NG --steps 3 --warmup 3 > /dev/null 2> $OUT/groth16_steps_n$NG.err
   grep "gb200 step" $OUT/groth16_steps_n$NG.err | tail -40 | tee -a $OUT/session.log
+fi
 fi
 ls -la $OUT | tee -a $OUT/session.log
