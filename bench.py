@@ -111,6 +111,20 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+IMAD_WIDE_PER_ADD = 1360          # 10 products x (64 + 64 + 8) 32x32->64 multiplier operations, BN254
+IMAD_WIDE_LANES_PER_CLK_SM = 32   # measured issue rate of IMAD.WIDE (half-rate pipe), profiles/r01_microbench_pipes.txt
+N_SMS = 148
+
+
+def multiplier_roofline(entries, kernel_ms, clocks):
+    mhz = (clocks or {}).get("sm_mhz") or (clocks or {}).get("sm_max_mhz") or 1965.0
+    peak = N_SMS * IMAD_WIDE_LANES_PER_CLK_SM * mhz * 1e6 / 1e12
+    achieved = entries * IMAD_WIDE_PER_ADD / (kernel_ms / 1e3) / 1e12
+    return {"bound": "int32 multiplier issue", "achieved": achieved, "peak": peak, "unit": "T IMAD.WIDE/s",
+            "frac": achieved / peak, "sm_mhz": mhz,
+            "model": "bucket entries x 1360 IMAD.WIDE / accumulate time; peak = 148 SMs x 32 lanes/clk x SM clock under load"}
+
+
 def measured_peak_gbs():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -393,6 +407,10 @@ def run_b200(args):
                      "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01_ncu_accumulate_summary.md",
                      "binding_unit": {"unit": "sm__pipe_fmaheavy (IMAD.WIDE issue)", "pct_of_peak": 86.5,
                                       "source": "profiles/r01_ncu_accumulate_summary.md"},
+                     # the same kernel against the ceiling that binds it, computed live: one XYZZ mixed addition per
+                     # bucket entry = 10 Montgomery products x 136 IMAD.WIDE (static SASS count, profiles/r01_sass_stats.md);
+                     # the pipe issues 32 IMAD.WIDE lanes / clk / SM (tools/microbench.cu, profiles/r01_microbench_pipes.txt)
+                     "multiplier": multiplier_roofline(n * W, acc_ms, clocks),
                      "note": "integer-multiplier bound, not HBM bound: ~1360 IMAD.WIDE per gathered 68 B (DESIGN.md)"},
         "stage_ms": stage_ms,
         "e2e_submit": e2e_submit,
