@@ -72,23 +72,6 @@ int32_t msm_on_stream(DeviceCtx* ctx, b200_table_s* t, size_t off, size_t n, con
 int32_t msm_join(DeviceCtx* ctx);  // make ctx->stream wait for the pipelined tails
 }
 
-// Stream-ordered device buffer that cannot leak on an early return: freed on its allocation stream by the destructor
-// unless it was handed back with release_on() (success paths free on the stream of the LAST user).
-struct AsyncBuf {
-  void* p = nullptr;
-  cudaStream_t st = nullptr;
-  AsyncBuf() = default;
-  AsyncBuf(const AsyncBuf&) = delete;
-  AsyncBuf& operator=(const AsyncBuf&) = delete;
-  ~AsyncBuf() { if (p) cudaFreeAsync(p, st); }
-  cudaError_t alloc(size_t bytes, cudaStream_t s) { st = s; return cudaMallocAsync(&p, bytes ? bytes : 1, s); }
-  cudaError_t release_on(cudaStream_t s) {
-    if (!p) return cudaSuccess;
-    void* q = p; p = nullptr;
-    return cudaFreeAsync(q, s);
-  }
-};
-
 #define CK(x)                                                        \
   do {                                                               \
     cudaError_t e_ = (x);                                            \

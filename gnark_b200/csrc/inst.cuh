@@ -149,12 +149,13 @@ struct NttInst {
     Fr pw[64];
     Fr b = *reinterpret_cast<const Fr*>(g);
     for (int j = 0; j < 64; j++) { pw[j] = b; b = b.sqr(); }
-    Fr* d_pw = nullptr;
-    GB_CUDA_TRY(cudaMallocAsync(&d_pw, sizeof(pw), st));
+    AsyncBuf pwb;
+    GB_CUDA_TRY(pwb.alloc(sizeof(pw), st));
+    Fr* d_pw = (Fr*)pwb.p;
     GB_CUDA_TRY(cudaMemcpyAsync(d_pw, pw, sizeof(pw), cudaMemcpyHostToDevice, st));
     k_scale_powers<Fr><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_pw, *reinterpret_cast<const Fr*>(s), n, (Fr*)d);
     GB_CUDA_TRY(cudaGetLastError());
-    GB_CUDA_TRY(cudaFreeAsync(d_pw, st));
+    GB_CUDA_TRY(pwb.release_on(st));
     return cudaStreamSynchronize(st);
   }
   static cudaError_t batch_invert(cudaStream_t st, void* d, size_t n) {
@@ -193,14 +194,15 @@ struct NttInst {
     a.log_rho = 0;
     while ((1u << a.log_rho) < c.rho) a.log_rho++;
     if ((1u << a.log_rho) != c.rho || c.coset_index >= c.rho) return cudaErrorInvalidValue;
-    Fr* den = nullptr;
-    GB_CUDA_TRY(cudaMallocAsync(&den, (size_t)d.n * sizeof(Fr), st));
+    AsyncBuf denb;
+    GB_CUDA_TRY(denb.alloc((size_t)d.n * sizeof(Fr), st));
+    Fr* den = (Fr*)denb.p;
     k_plonk_denominators<Fr><<<(d.n + 255) / 256, 256, 0, st>>>(den, d.n, d.tw, coset);
     GB_CUDA_TRY(batch_invert(st, den, d.n));
     a.den_inv = den;
     k_plonk_constraints<Fr><<<(d.n + 255) / 256, 256, 0, st>>>(a);
     GB_CUDA_TRY(cudaGetLastError());
-    return cudaFreeAsync(den, st);
+    return denb.release_on(st);
   }
   static cudaError_t plonk_bsb22(cudaStream_t st, void* dom0, const void* qcp, const void* pi2, uint32_t coset_index,
                                  uint32_t rho, void* out) {
@@ -222,13 +224,14 @@ struct NttInst {
     for (uint32_t k = 0; k < log_n0; k++) { gn = gn.sqr(); wn = wn.sqr(); }
     Fr cur = gn;
     for (uint32_t i = 0; i < rho; i++) { tab[i] = (cur - Fr::one()).inverse(); cur = cur * wn; }
-    Fr* d_tab = nullptr;
-    GB_CUDA_TRY(cudaMallocAsync(&d_tab, sizeof(tab), st));
+    AsyncBuf tabb;
+    GB_CUDA_TRY(tabb.alloc(sizeof(tab), st));
+    Fr* d_tab = (Fr*)tabb.p;
     GB_CUDA_TRY(cudaMemcpyAsync(d_tab, tab, sizeof(Fr) * rho, cudaMemcpyHostToDevice, st));
     k_plonk_zh_scale<Fr><<<(d.n + 255) / 256, 256, 0, st>>>((Fr*)data, (uint32_t)d.logn, rho, d_tab);
     GB_CUDA_TRY(cudaGetLastError());
     GB_CUDA_TRY(ntt_enqueue<Fr>(st, d, (Fr*)data, true, NTT_DIT, true));
-    GB_CUDA_TRY(cudaFreeAsync(d_tab, st));
+    GB_CUDA_TRY(tabb.release_on(st));
     return cudaStreamSynchronize(st);  // tab is a stack buffer
   }
   static cudaError_t axpy(cudaStream_t st, void* y, const void* a, const void* x, size_t n) {
@@ -243,9 +246,10 @@ struct NttInst {
   static cudaError_t plonk_build_z(cudaStream_t st, void* dom0, const void* l, const void* r, const void* o,
                                    const int64_t* perm, const void* beta, const void* gamma, void* z) {
     const Dom& d = *reinterpret_cast<Dom*>(dom0);
-    Fr *num = nullptr, *den = nullptr;
-    GB_CUDA_TRY(cudaMallocAsync(&num, (size_t)d.n * sizeof(Fr), st));
-    GB_CUDA_TRY(cudaMallocAsync(&den, (size_t)d.n * sizeof(Fr), st));
+    AsyncBuf numb, denb;
+    GB_CUDA_TRY(numb.alloc((size_t)d.n * sizeof(Fr), st));
+    GB_CUDA_TRY(denb.alloc((size_t)d.n * sizeof(Fr), st));
+    Fr *num = (Fr*)numb.p, *den = (Fr*)denb.p;
     k_plonk_ratio_terms<Fr><<<(d.n + 255) / 256, 256, 0, st>>>(d.n, (const Fr*)l, (const Fr*)r, (const Fr*)o, perm, d.tw,
                                                             *(const Fr*)beta, *(const Fr*)gamma, d.coset, num, den);
     GB_CUDA_TRY(cudaGetLastError());
@@ -253,31 +257,32 @@ struct NttInst {
     k_plonk_shift_ratio<Fr><<<(d.n + 255) / 256, 256, 0, st>>>(d.n, num, den, (Fr*)z);
     GB_CUDA_TRY(cudaGetLastError());
     GB_CUDA_TRY((scan_enqueue<Fr, 0>(st, (Fr*)z, d.n, false)));
-    GB_CUDA_TRY(cudaFreeAsync(num, st));
-    return cudaFreeAsync(den, st);
+    GB_CUDA_TRY(numb.release_on(st));
+    return denb.release_on(st);
   }
-  static cudaError_t upload_pow_table(cudaStream_t st, const Fr& x, Fr** d_pw) {
+  static cudaError_t upload_pow_table(cudaStream_t st, const Fr& x, AsyncBuf& d_pw) {
     Fr pw[64];
     Fr b = x;
     for (int j = 0; j < 64; j++) { pw[j] = b; b = b.sqr(); }
-    GB_CUDA_TRY(cudaMallocAsync(d_pw, sizeof(pw), st));
-    GB_CUDA_TRY(cudaMemcpyAsync(*d_pw, pw, sizeof(pw), cudaMemcpyHostToDevice, st));
+    GB_CUDA_TRY(d_pw.alloc(sizeof(pw), st));
+    GB_CUDA_TRY(cudaMemcpyAsync(d_pw.p, pw, sizeof(pw), cudaMemcpyHostToDevice, st));
     return cudaStreamSynchronize(st);  // pw is a stack buffer
   }
   static cudaError_t poly_eval(cudaStream_t st, const void* c, size_t n, const void* x_, void* out_host) {
     const Fr x = *(const Fr*)x_;
     if (n == 0) { *(Fr*)out_host = Fr::zero(); return cudaSuccess; }
-    Fr* d_pw = nullptr;
-    GB_CUDA_TRY(upload_pow_table(st, x, &d_pw));
+    AsyncBuf pwb, sumsb;
+    GB_CUDA_TRY(upload_pow_table(st, x, pwb));
+    Fr* d_pw = (Fr*)pwb.p;
     const size_t nblocks = (n + 256 * EVAL_E - 1) / (256 * EVAL_E);
-    Fr* sums = nullptr;
-    GB_CUDA_TRY(cudaMallocAsync(&sums, (nblocks + 1) * sizeof(Fr), st));
+    GB_CUDA_TRY(sumsb.alloc((nblocks + 1) * sizeof(Fr), st));
+    Fr* sums = (Fr*)sumsb.p;
     k_poly_eval_partial<Fr><<<(unsigned)nblocks, 256, 0, st>>>((const Fr*)c, n, d_pw, x, sums);
     k_sum_reduce<Fr><<<1, 256, 0, st>>>(sums, nblocks, sums + nblocks);
     GB_CUDA_TRY(cudaGetLastError());
     GB_CUDA_TRY(cudaMemcpyAsync(out_host, sums + nblocks, sizeof(Fr), cudaMemcpyDeviceToHost, st));
-    GB_CUDA_TRY(cudaFreeAsync(sums, st));
-    GB_CUDA_TRY(cudaFreeAsync(d_pw, st));
+    GB_CUDA_TRY(sumsb.release_on(st));
+    GB_CUDA_TRY(pwb.release_on(st));
     return cudaStreamSynchronize(st);
   }
   // in place: coeffs[0..n-2] <- (p(X) - p(z)) / (X - z), coeffs[n-1] <- 0; remainder p(z) to the host
@@ -288,28 +293,30 @@ struct NttInst {
     if (z.is_zero()) {
       // q_i = c_{i+1}, remainder c_0
       GB_CUDA_TRY(cudaMemcpyAsync(rem_host, c, sizeof(Fr), cudaMemcpyDeviceToHost, st));
-      Fr* tmp = nullptr;
-      GB_CUDA_TRY(cudaMallocAsync(&tmp, n * sizeof(Fr), st));
+      AsyncBuf tmpb;
+      GB_CUDA_TRY(tmpb.alloc(n * sizeof(Fr), st));
+      Fr* tmp = (Fr*)tmpb.p;
       GB_CUDA_TRY(cudaMemcpyAsync(tmp, c, n * sizeof(Fr), cudaMemcpyDeviceToDevice, st));
       if (n > 1) GB_CUDA_TRY(cudaMemcpyAsync(c, tmp + 1, (n - 1) * sizeof(Fr), cudaMemcpyDeviceToDevice, st));
       GB_CUDA_TRY(cudaMemsetAsync(c + (n - 1), 0, sizeof(Fr), st));
-      GB_CUDA_TRY(cudaFreeAsync(tmp, st));
+      GB_CUDA_TRY(tmpb.release_on(st));
       return cudaStreamSynchronize(st);
     }
     const Fr zinv = z.inverse();
-    Fr *d_pw = nullptr, *d_pwi = nullptr, *t = nullptr, *d_rem = nullptr;
-    GB_CUDA_TRY(upload_pow_table(st, z, &d_pw));
-    GB_CUDA_TRY(upload_pow_table(st, zinv, &d_pwi));
-    GB_CUDA_TRY(cudaMallocAsync(&t, n * sizeof(Fr), st));
-    GB_CUDA_TRY(cudaMallocAsync(&d_rem, sizeof(Fr), st));
+    AsyncBuf pwb, pwib, tb, remb;
+    GB_CUDA_TRY(upload_pow_table(st, z, pwb));
+    GB_CUDA_TRY(upload_pow_table(st, zinv, pwib));
+    GB_CUDA_TRY(tb.alloc(n * sizeof(Fr), st));
+    GB_CUDA_TRY(remb.alloc(sizeof(Fr), st));
+    Fr *d_pw = (Fr*)pwb.p, *d_pwi = (Fr*)pwib.p, *t = (Fr*)tb.p, *d_rem = (Fr*)remb.p;
     const unsigned nb = (unsigned)((n + 256 * EVAL_E - 1) / (256 * EVAL_E));
     k_syndiv_pre<Fr><<<nb, 256, 0, st>>>(c, n, d_pwi, zinv, t);
     GB_CUDA_TRY((scan_enqueue<Fr, 1>(st, t, n, false)));
     k_syndiv_post<Fr><<<nb, 256, 0, st>>>(t, n, d_pw, z, c, d_rem);
     GB_CUDA_TRY(cudaGetLastError());
     GB_CUDA_TRY(cudaMemcpyAsync(rem_host, d_rem, sizeof(Fr), cudaMemcpyDeviceToHost, st));
-    GB_CUDA_TRY(cudaFreeAsync(t, st)); GB_CUDA_TRY(cudaFreeAsync(d_rem, st));
-    GB_CUDA_TRY(cudaFreeAsync(d_pw, st)); GB_CUDA_TRY(cudaFreeAsync(d_pwi, st));
+    GB_CUDA_TRY(tb.release_on(st)); GB_CUDA_TRY(remb.release_on(st));
+    GB_CUDA_TRY(pwb.release_on(st)); GB_CUDA_TRY(pwib.release_on(st));
     return cudaStreamSynchronize(st);
   }
   static cudaError_t gather(cudaStream_t st, void* out, const void* src, const uint32_t* idx, size_t n) {

@@ -10,6 +10,23 @@
 
 namespace gb200 {
 
+// Stream-ordered device buffer that cannot leak on an early return: freed on its allocation stream by the destructor
+// unless it was handed back with release_on() (success paths free on the stream of the LAST user).
+struct AsyncBuf {
+  void* p = nullptr;
+  cudaStream_t st = nullptr;
+  AsyncBuf() = default;
+  AsyncBuf(const AsyncBuf&) = delete;
+  AsyncBuf& operator=(const AsyncBuf&) = delete;
+  ~AsyncBuf() { if (p) cudaFreeAsync(p, st); }
+  cudaError_t alloc(size_t bytes, cudaStream_t s) { st = s; return cudaMallocAsync(&p, bytes ? bytes : 1, s); }
+  cudaError_t release_on(cudaStream_t s) {
+    if (!p) return cudaSuccess;
+    void* q = p; p = nullptr;
+    return cudaFreeAsync(q, s);
+  }
+};
+
 // Opt-in experiment (GB200_MSM_HYBRID=<percent>): the bucket-accumulate tasks are split between the
 // IMAD.WIDE kernel and its FP64-pipe twin, launched concurrently on two streams so that both multiplier
 // pipes of an SM are busy at once (the pipes are independent: profiles/r01_microbench_pipes.txt).
