@@ -43,6 +43,7 @@ class Config:
     ShardRank: int = 0           # multi-GPU (one process per GPU): this process's point-range shard
     ShardWorld: int = 1
     ProcessGroup: object = None  # torch.distributed group used to gather the partial MSM results
+    Devices: tuple = ()          # multi-GPU inside ONE process (WithDevices): one point-range shard per listed device
 
 
 Option = Callable[[Config], None]
@@ -95,6 +96,19 @@ def WithSharding(rank: int, world: int, process_group=None) -> Option:
     return f
 
 
+def WithDevices(*devs: int) -> Option:
+    """Several GPUs driven from ONE process - the shape a Go caller uses (a goroutine per device, no process group):
+    device devs[i] holds point-range shard i of every MSM table; the device parts run concurrently (the C ABI
+    serialises per device, not per process), the partial points are summed on the host and the proof is assembled
+    once.  The reference has one device per proof (`WithDeviceID`, opts.go:68-77); this is its multi-GPU extension."""
+    def f(c: Config):
+        if not devs or any(d < 0 for d in devs) or len(set(devs)) != len(devs):
+            raise ValueError(f"invalid device list {devs}")
+        c.Devices = tuple(devs)
+        c.DeviceID = devs[0]
+    return f
+
+
 def WithRandomness(fn: Callable[[int], int]) -> Option:
     """Deterministic r, s for parity tests (the reference samples crypto/rand, prove.go:170-182)."""
     def f(c: Config):
@@ -138,6 +152,7 @@ class ProvingKey:
         self.nb_public = 0
         self._handle = None
         self._dev = None
+        self._handles = {}           # (device, shard rank, shard world, precompute) -> C handle
 
     @classmethod
     def from_arrays(cls, curve, domain_size, alpha, beta, delta, A, B, Z, K, beta2, delta2, B2, inf_a, inf_b,
@@ -163,12 +178,11 @@ class ProvingKey:
         per = 2 * fpl * (deg if group == 2 else 1)
         return arr.size // per
 
-    def setup_device_pointers(self, cfg: Config):
-        """icicle.go:88-264 setupDevicePointers: once per key and device."""
-        key = (cfg.DeviceID, cfg.ShardRank, cfg.ShardWorld)
-        if self._handle is not None and self._dev == key:
-            return
-        self.free_gpu_resources()
+    def _load(self, dev: int, rank: int, world: int, precompute: bool):
+        """b200_groth16_pk_load of shard rank/world on device dev (cached per key)."""
+        key = (dev, rank, world, bool(precompute))
+        if key in self._handles:
+            return self._handles[key]
         d = _lib.Groth16PkDesc()
         d.curve = self.curve
         d.domain_size = self.domain_size
@@ -186,17 +200,31 @@ class ProvingKey:
         kr = getattr(self, "k_removed", None)
         if kr is not None and kr.size:
             d.k_removed, d.n_k_removed = p(kr), kr.size
-        d.flags = _lib.TABLE_PRECOMP if cfg.Precompute else 0
-        d.shard_rank, d.shard_world = cfg.ShardRank, cfg.ShardWorld
+        d.flags = _lib.TABLE_PRECOMP if precompute else 0
+        d.shard_rank, d.shard_world = rank, world
         h = ctypes.c_void_p(0)
-        _lib.check(_lib.load().b200_groth16_pk_load(cfg.DeviceID, ctypes.byref(d), ctypes.byref(h)))
-        self._handle, self._dev = h, key
+        _lib.check(_lib.load().b200_groth16_pk_load(dev, ctypes.byref(d), ctypes.byref(h)))
+        self._handles[key] = h
+        return h
+
+    def setup_device_pointers(self, cfg: Config):
+        """icicle.go:88-264 setupDevicePointers: once per key and device (per device AND shard with WithDevices)."""
+        if len(cfg.Devices) > 1:
+            want = {(dev, i, len(cfg.Devices), bool(cfg.Precompute)) for i, dev in enumerate(cfg.Devices)}
+        else:
+            want = {(cfg.DeviceID, cfg.ShardRank, cfg.ShardWorld, bool(cfg.Precompute))}
+        for key in [k for k in self._handles if k not in want]:      # another placement: release it first
+            _lib.check(_lib.load().b200_groth16_pk_free(self._handles.pop(key)))
+        for key in sorted(want):
+            self._load(*key)
+        first = min(want, key=lambda k: k[1])
+        self._handle, self._dev = self._handles[first], first
 
     def free_gpu_resources(self):
         """icicle.go:1493-1549 FreeGPUResources; safe to call repeatedly."""
-        if self._handle is not None:
-            _lib.check(_lib.load().b200_groth16_pk_free(self._handle))
-            self._handle = None
+        for key in list(self._handles):
+            _lib.check(_lib.load().b200_groth16_pk_free(self._handles.pop(key)))
+        self._handle = None
 
     def __del__(self):
         try:
@@ -237,6 +265,44 @@ def ProveSolution(pk: ProvingKey, sol: R1CSSolution, *opts: Option, keep_msm: bo
     bs = np.zeros(2 * fpl * deg, dtype=np.uint64)
     p = _lib.ptr
     L = _lib.load()
+    j1 = 3 * fpl
+    spans = [(k * j1, (k + 1) * j1, 1) for k in range(4)] + [(4 * j1, 4 * j1 + 3 * fpl * deg, 2)]
+
+    def fold(parts):
+        """five partial MSM results per shard -> their sums (host-side group additions, icicle.go:383-411)"""
+        acc = parts[0].copy()
+        for q in parts[1:]:
+            for lo, hi, grp in spans:
+                seg = np.ascontiguousarray(acc[lo:hi])
+                _lib.point_add_jac(pk.curve, grp, seg, np.ascontiguousarray(q[lo:hi]))
+                acc[lo:hi] = seg
+        return acc
+
+    if len(cfg.Devices) > 1:
+        # one process, several GPUs: the device parts of all shards run concurrently (ctypes releases the GIL,
+        # the C ABI locks per device); what a Go shim does with one goroutine per device
+        import threading
+        nd = len(cfg.Devices)
+        parts = [np.zeros(4 * 3 * fpl + 3 * fpl * deg, dtype=np.uint64) for _ in range(nd)]
+        errs = [None] * nd
+
+        def run(i, dev):
+            try:
+                h = pk._handles[(dev, i, nd, bool(cfg.Precompute))]
+                _lib.check(L.b200_groth16_msms(h, p(sol.W), p(sol.A), p(sol.B), p(sol.C), n_constraints, p(parts[i])))
+            except Exception as e:      # re-raised on the calling thread
+                errs[i] = e
+        ts = [threading.Thread(target=run, args=(i, dev)) for i, dev in enumerate(cfg.Devices)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        for e in errs:
+            if e is not None:
+                raise e
+        msm = fold(parts)
+        _lib.check(L.b200_groth16_assemble(pk._handle, p(msm), p(r), p(s), p(ar), p(bs), p(krs)))
+        return Proof(Ar=ar, Bs=bs, Krs=krs, msm=msm if keep_msm else None)
     if cfg.ShardWorld <= 1:
         msm = np.zeros(4 * 3 * fpl + 3 * fpl * deg, dtype=np.uint64) if keep_msm else None
         _lib.check(L.b200_groth16_prove(pk._handle, p(sol.W), p(sol.A), p(sol.B), p(sol.C), n_constraints,
@@ -253,14 +319,7 @@ def ProveSolution(pk: ProvingKey, sol: R1CSSolution, *opts: Option, keep_msm: bo
     parts = [torch.empty_like(t) for _ in range(cfg.ShardWorld)]
     dist.all_gather(parts, t, group=cfg.ProcessGroup)
     parts = [x.cpu().numpy().view(np.uint64) for x in parts]
-    msm = parts[0].copy()
-    j1 = 3 * fpl
-    spans = [(k * j1, (k + 1) * j1, 1) for k in range(4)] + [(4 * j1, 4 * j1 + 3 * fpl * deg, 2)]
-    for q in parts[1:]:
-        for lo, hi, grp in spans:
-            seg = np.ascontiguousarray(msm[lo:hi])
-            _lib.point_add_jac(pk.curve, grp, seg, np.ascontiguousarray(q[lo:hi]))
-            msm[lo:hi] = seg
+    msm = fold(parts)
     _lib.check(L.b200_groth16_assemble(pk._handle, p(msm), p(r), p(s), p(ar), p(bs), p(krs)))
     return Proof(Ar=ar, Bs=bs, Krs=krs, msm=msm if keep_msm else None)
 

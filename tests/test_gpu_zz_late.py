@@ -501,3 +501,27 @@ def test_ntt_full_size_identities(gpu, cname, logn):
         gpu.sync(0)
         assert torch.equal(y, x), (cname, logn, on_coset)
     d.free()
+
+
+@pytest.mark.xfail(strict=False, reason="one-process multi-GPU path written after this round's GPU budget was spent; its host logic "
+                   "is pinned on the CPU by tests/test_groth16_host_logic.py")
+def test_groth16_with_devices_in_one_process(gpu):
+    """WithDevices: every visible GPU holds one point-range shard of the key, the device parts run concurrently from
+    one process (what a Go caller does with a goroutine per device); the proof must equal the single-device proof."""
+    import torch
+    from gnark_b200 import groth16 as b200
+    from oracle import groth16 as g16o
+    from util import build_groth16_pk, pack_solution
+    nd = torch.cuda.device_count()
+    if nd < 2:
+        pytest.skip("needs at least two GPUs")
+    c = CURVES["bn254"]
+    m = 3000
+    cs, W = g16o.square_chain_r1cs(m), g16o.square_chain_witness(c.r, m)
+    pk, pkd, _, _ = build_groth16_pk(c, cs, g16o.random_toxic(c, 17), 17)
+    sol = pack_solution(c, cs, W)
+    rs = [12345, 67890]
+    one = b200.ProveSolution(pk, sol, b200.WithDeviceID(0), b200.WithRandomness(lambda q, it=iter(rs): next(it)))
+    many = b200.ProveSolution(pk, sol, b200.WithDevices(*range(nd)), b200.WithRandomness(lambda q, it=iter(rs): next(it)))
+    assert np.array_equal(one.Ar, many.Ar) and np.array_equal(one.Bs, many.Bs) and np.array_equal(one.Krs, many.Krs)
+    pk.free_gpu_resources()
