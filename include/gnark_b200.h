@@ -315,7 +315,8 @@ int32_t b200_groth16_pk_free(b200_pk_t pk);
 int32_t b200_groth16_prove(b200_pk_t pk, const void* wires, const void* a, const void* b, const void* c,
                            size_t n_constraints, const void* r, const void* s, void* ar_out, void* bs_out,
                            void* krs_out, void* msm_out);
-/* The two halves of b200_groth16_prove, for sharded keys (one process per GPU):
+/* The two halves of b200_groth16_prove, for sharded keys (one process per GPU, or one thread per GPU inside one
+ * process - entry points lock per device):
  *  - b200_groth16_msms: device part.  computeH + this shard's slice of the five MSMs; msm_out
  *    receives 4 G1Jac + 1 G2Jac partial sums (order A, B1, Z(h), K, B2).  Partial sums of all
  *    shards are added with b200_point_add_jac after one all_gather.
