@@ -78,6 +78,24 @@ def main():
                   + f" | {r['correct']} | {r['ms_standalone']:.3f} | {r['ms_pipelined']:.3f} | {r['ms_pipelined'] / base[key]:.3f} | "
                   f"{st.get('accumulate')} | {st.get('offsets_scan')} |")
         print()
+    # compile-time variants against the default library on the same configuration, best first
+    rows = jl(os.path.join(D, "sweep_optlib.jsonl"))
+    if rows:
+        print("## Compile-time variants vs the default library (sweep_optlib.jsonl), best first per configuration\n")
+        print("| curve | G | log2n | lib | correct | pipelined ms | vs default | accumulate ms | vs default |\n|---|---|---|---|---|---|---|---|---|")
+        by = {}
+        for r in rows:
+            if "error" not in r:
+                by.setdefault((r["curve"], r["group"], r["log2n"]), []).append(r)
+        for key, rs in sorted(by.items()):
+            d = next((r for r in rs if r.get("lib") == "default"), None)
+            for r in sorted(rs, key=lambda r: r["ms_pipelined"]):
+                acc = r.get("stage_ms", {}).get("accumulate")
+                rel = f"{r['ms_pipelined'] / d['ms_pipelined']:.3f}" if d else "n/a"
+                dacc = d.get("stage_ms", {}).get("accumulate") if d else None
+                rel_acc = f"{acc / dacc:.3f}" if (acc and dacc) else "n/a"
+                print(f"| {key[0]} | {key[1]} | {key[2]} | {r.get('lib')} | {r['correct']} | {r['ms_pipelined']:.3f} | {rel} | {acc} | {rel_acc} |")
+        print()
     for pat, title in (("configs.jsonl", "Other configurations"), ("sharded_ntt_n*.json", "Sharded NTT"), ("plonk_n*.json", "Sharded PLONK")):
         files = sorted(glob.glob(os.path.join(D, pat)))
         if not files:
