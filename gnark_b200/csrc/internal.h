@@ -37,6 +37,8 @@ struct MsmHybrid {
   cudaEvent_t fork_ev, join_ev;
   // second opt-in experiment (GB200_MSM_BATCH_AFFINE=<levels>, msm_batch.cuh): batched-affine tree levels
   int ba_levels;
+  // third opt-in experiment (GB200_MSM_PERSISTENT=1): accumulate on a grid sized to the SMs, tasks from an atomic counter
+  int persistent;
 };
 
 struct MsmOps {

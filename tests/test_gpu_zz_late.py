@@ -525,3 +525,20 @@ def test_groth16_with_devices_in_one_process(gpu):
     many = b200.ProveSolution(pk, sol, b200.WithDevices(*range(nd)), b200.WithRandomness(lambda q, it=iter(rs): next(it)))
     assert np.array_equal(one.Ar, many.Ar) and np.array_equal(one.Bs, many.Bs) and np.array_equal(one.Krs, many.Krs)
     pk.free_gpu_resources()
+
+
+@pytest.mark.xfail(strict=False, reason="opt-in experiment written after this round's GPU budget was spent; per-thread logic "
+                   "pinned by tests/test_emulation.py::test_msm_persistent_accumulate_logic")
+@pytest.mark.parametrize("cname,group", [("bn254", 1), ("bn254", 2), ("bls12-381", 1), ("bw6-761", 1)])
+def test_msm_persistent_accumulate(gpu, monkeypatch, cname, group):
+    """opt-in GB200_MSM_PERSISTENT: the accumulate stage on a grid sized to the SMs, tasks from an atomic counter;
+    known-dlog oracle, uniform and skewed scalars, precomputed and plain tables, sizes around the grid size"""
+    from util import known_dlog_instance
+    c = CURVES[cname]
+    monkeypatch.setenv("GB200_MSM_PERSISTENT", "1")
+    for n, skew in ((300, False), (9000, False), (9000, True), (150000 if c.fp_limbs <= 6 else 20000, False)):
+        _, _, pts, sc, expected = known_dlog_instance(c, group, n, seed=77 + group, skew=skew)
+        for precomp in (True, False):
+            t = gpu.Table(c.curve_id, group, pts, precomp=precomp)
+            assert jac_to_affine(c, group, t.msm(sc)) == expected, (n, skew, precomp)
+            t.free()

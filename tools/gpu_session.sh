@@ -39,6 +39,12 @@ fi
 if want 3; then
 echo "== 3. MSM knob sweeps (every configuration is checked against the known-dlog oracle)" | tee -a $OUT/session.log
 timeout 600 python tools/sweep_msm.py bn254 1 20 --set GB200_MSM_WINDOW=16,17,18,19,20,22 > $OUT/sweep_bn254_window.jsonl 2>> $OUT/session.err
+# persistent accumulate (grid = SMs x resident blocks, tasks from an atomic counter): removes the partial last wave and
+# the lanes idling behind the short last task of every bucket
+for cfg in "bn254 1 20" "bn254 2 20" "bls12-381 1 20" "bw6-761 1 18"; do
+  set -- $cfg
+  timeout 600 python tools/sweep_msm.py $1 $2 $3 --set GB200_MSM_PERSISTENT=0,1 >> $OUT/sweep_persistent.jsonl 2>> $OUT/session.err
+done
 # the PLONK config's MSM (2^22 points, BLS12-381): ten of these per proof
 timeout 900 python tools/sweep_msm.py bls12-381 1 22 --reps 3 --set GB200_MSM_WINDOW=16,18,20,22 > $OUT/sweep_bls381_2p22_window.jsonl 2>> $OUT/session.err
 timeout 600 python tools/sweep_msm.py bn254 1 20 --set GB200_MSM_HYBRID=0,12,25,38,50,62 > $OUT/sweep_bn254_hybrid.jsonl 2>> $OUT/session.err
