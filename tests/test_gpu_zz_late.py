@@ -22,6 +22,11 @@ from oracle.params import CURVES
 from util import jac_to_affine
 
 pytestmark = pytest.mark.gpu
+# Opt-in performance experiments (kernels that are not on the default path and have never run on hardware) are only
+# exercised when asked for (tools/gpu_session.sh sets GB200_RUN_EXPERIMENTS=1): a fault in one of them would poison the
+# CUDA context for every test after it, and none of them is needed for the parity of the product path.
+experiment = pytest.mark.skipif(os.environ.get("GB200_RUN_EXPERIMENTS") != "1",
+                                reason="opt-in performance experiment: set GB200_RUN_EXPERIMENTS=1 (tools/gpu_session.sh)")
 KAT = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "kat_v1.json")))
 ALL = list(CURVES.values())
 H = lambda s: int(s, 16)
@@ -170,6 +175,7 @@ def test_full_prover_vs_oracle(gpu, c, logn):
     pk.free()
 
 
+@experiment
 @pytest.mark.xfail(strict=False, reason="opt-in experiment written after this round's GPU budget was spent; both kernels "
                    "and the split geometry are validated separately, the concurrent launch is not yet")
 @pytest.mark.parametrize("cname", ["bn254", "bls12-381"])
@@ -275,6 +281,7 @@ def test_sharded_ntt_single_rank(gpu):
     sd.free()
 
 
+@experiment
 @pytest.mark.xfail(strict=False, reason="opt-in experiment written after this round's GPU budget was spent; per-thread logic "
                    "pinned by tests/test_emulation.py::test_msm_batched_affine_levels_logic")
 @pytest.mark.parametrize("cname,group", [("bn254", 1), ("bn254", 2), ("bls12-381", 1), ("bw6-761", 1)])
@@ -426,6 +433,7 @@ def test_plonk_prove_reproduces_golden(gpu, cname):
     key.free()
 
 
+@experiment
 @pytest.mark.xfail(strict=False, reason="opt-in upload path written after this round's GPU budget was spent")
 def test_groth16_threaded_staging_of_pageable_inputs(gpu):
     """GB200_STAGE_THREADS: W, A, B, C uploaded from pageable memory through two pinned slots filled by several
@@ -527,6 +535,7 @@ def test_groth16_with_devices_in_one_process(gpu):
     pk.free_gpu_resources()
 
 
+@experiment
 @pytest.mark.xfail(strict=False, reason="opt-in experiment written after this round's GPU budget was spent; per-thread logic "
                    "pinned by tests/test_emulation.py::test_msm_persistent_accumulate_logic")
 @pytest.mark.parametrize("cname,group", [("bn254", 1), ("bn254", 2), ("bls12-381", 1), ("bw6-761", 1)])

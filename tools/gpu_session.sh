@@ -11,6 +11,7 @@ set -u
 OUT=gpurun_out
 mkdir -p $OUT
 export PYTHONUNBUFFERED=1
+export GB200_RUN_EXPERIMENTS=1     # tests/test_gpu_zz_late.py: run the opt-in experiment tests too
 STAGES=" ${*:-1 2 2b 3 3v 3b 4 5} "
 want() { [[ "$STAGES" == *" $1 "* ]]; }
 : >> $OUT/session.log
