@@ -175,131 +175,6 @@ def test_full_prover_vs_oracle(gpu, c, logn):
     pk.free()
 
 
-@experiment
-@pytest.mark.xfail(strict=False, reason="opt-in experiment written after this round's GPU budget was spent; both kernels "
-                   "and the split geometry are validated separately, the concurrent launch is not yet")
-@pytest.mark.parametrize("cname", ["bn254", "bls12-381"])
-@pytest.mark.parametrize("pct", [30, 70])
-def test_msm_hybrid_accumulate(gpu, monkeypatch, cname, pct):
-    """opt-in GB200_MSM_HYBRID: accumulate tasks split between the IMAD.WIDE kernel and the FP64-pipe kernel on
-    two concurrent streams (CPU twin: tests/test_emulation.py::test_msm_hybrid_split_logic); known-dlog oracle"""
-    from util import known_dlog_instance
-    c = CURVES[cname]
-    monkeypatch.setenv("GB200_MSM_HYBRID", str(pct))
-    _, _, pts, sc, expected = known_dlog_instance(c, 1, 20000, seed=pct)
-    t = gpu.Table(c.curve_id, 1, pts, precomp=True)
-    for _ in range(3):      # repeated: the fork/join events are reused across calls
-        assert jac_to_affine(c, 1, t.msm(sc)) == expected
-    t.free()
-    monkeypatch.delenv("GB200_MSM_HYBRID")
-    t = gpu.Table(c.curve_id, 1, pts, precomp=True)
-    assert jac_to_affine(c, 1, t.msm(sc)) == expected
-    t.free()
-
-
-@pytest.mark.xfail(strict=False, reason="entry point written after this round's GPU budget was spent; the per-thread "
-                   "functions are pinned on the CPU by tests/test_emulation.py::test_fixed_base_batch_logic")
-@pytest.mark.parametrize("c", ALL, ids=lambda c: c.name)
-@pytest.mark.parametrize("group", (1, 2))
-def test_fixed_base_batch(gpu, c, group):
-    """b200_fixed_base_batch (curve.BatchScalarMultiplicationG1/G2, setup.go:233,302) against the C++ oracle's
-    fixed-base batch, bit-exact affine points; host and device I/O; edge scalars"""
-    import torch
-    from oracle import corelib
-    from util import pick_base
-    rng = random.Random(61 + group)
-    F, base = pick_base(c, group, rng)
-    n = 3001
-    ks = [rng.randrange(c.r) for _ in range(n)]
-    ks[0], ks[1], ks[2] = 0, 1, c.r - 1
-    KS = ff.pack_elements(ks, c.r, c.fr_limbs)
-    BA = ec.pack_points(c, group, [base])
-    want = corelib.fixed_base(c, group, BA, KS)
-    got = gpu.fixed_base_batch(c.curve_id, group, BA, KS)
-    assert np.array_equal(got.reshape(want.shape), want)
-    d_ks = torch.from_numpy(KS.view(np.int64)).cuda()
-    d_out = torch.zeros(want.size, dtype=torch.int64, device="cuda")
-    gpu.fixed_base_batch(c.curve_id, group, BA, d_ks, n=n, out=d_out)
-    assert np.array_equal(d_out.cpu().numpy().view(np.uint64).reshape(want.shape), want)
-    assert ec.unpack_points(c, group, got)[2] == ec.scalar_mul(F, c.r - 1, base)
-
-
-@pytest.mark.xfail(strict=False, reason="entry point written after this round's GPU budget was spent")
-def test_msm_submit_stream_of_msms(gpu):
-    """b200_msm_submit: a stream of MSMs from pinned host buffers (different scalars, different ranges), results
-    after b200_sync, each against the known-dlog oracle"""
-    import torch
-    from util import known_dlog_instance
-    c = CURVES["bn254"]
-    n = 6000
-    F, base, pts, sc, expected = known_dlog_instance(c, 1, n, seed=77)
-    t = gpu.Table(c.curve_id, 1, pts, precomp=True)
-    h_sc = torch.from_numpy(sc.view(np.int64).copy()).pin_memory()
-    K = 6
-    h_out = torch.zeros((K, 12), dtype=torch.int64).pin_memory()
-    for i in range(K):
-        t.msm_submit(h_sc, h_out[i], n=n)
-    gpu.sync(0)
-    for i in range(K):
-        assert jac_to_affine(c, 1, h_out[i].numpy().view(np.uint64)) == expected
-    # a sub-range and the empty sum
-    half = n // 2
-    h2 = torch.zeros((2, 12), dtype=torch.int64).pin_memory()
-    t.msm_submit(h_sc.view(n, 4)[:half], h2[0], n=half)
-    t.msm_submit(h_sc, h2[1], n=0)
-    gpu.sync(0)
-    want_half = jac_to_affine(c, 1, t.msm(sc[:half].copy(), n=half))
-    assert jac_to_affine(c, 1, h2[0].numpy().view(np.uint64)) == want_half
-    assert jac_to_affine(c, 1, h2[1].numpy().view(np.uint64)) is None
-    t.free()
-
-
-@pytest.mark.xfail(strict=False, reason="written after this round's GPU budget was spent; the decomposition is pinned on the "
-                   "CPU over gloo (tests/test_dist.py::test_sharded_ntt_gloo)")
-def test_sharded_ntt_single_rank(gpu):
-    """gnark_b200/parallel_ntt.py with world = 1 on the GPU: no exchange, but the stream scoping, the local
-    transform + bit reversal and the coset scaling are the ones every rank runs (multi-rank: tools/bench_sharded_ntt.py)"""
-    import torch
-    from gnark_b200 import parallel_ntt as pn
-    from oracle import ntt
-    c = CURVES["bn254"]
-    logn = 10
-    n = 1 << logn
-    rng = random.Random(5)
-    x = [rng.randrange(c.r) for _ in range(n)]
-    X = ff.pack_elements(x, c.r, c.fr_limbs).reshape(n, c.fr_limbs)
-    dom = ntt.Domain(c, n)
-    sd = pn.ShardedDomain(c.curve_id, logn, 0, 1)
-    for on_coset in (False, True):
-        d = torch.from_numpy(X.view(np.int64).reshape(-1).copy()).cuda()
-        got = sd.forward(d, on_coset=on_coset).cpu().numpy().view(np.uint64)
-        want = ntt.bit_reverse(dom.fft(list(x), ntt.DIF, on_coset=on_coset))
-        assert ff.unpack_elements(got, c.r, c.fr_limbs) == want
-        back = sd.inverse(sd.forward(torch.from_numpy(X.view(np.int64).reshape(-1).copy()).cuda(), on_coset=on_coset),
-                          on_coset=on_coset).cpu().numpy().view(np.uint64)
-        assert ff.unpack_elements(back, c.r, c.fr_limbs) == x
-    sd.free()
-
-
-@experiment
-@pytest.mark.xfail(strict=False, reason="opt-in experiment written after this round's GPU budget was spent; per-thread logic "
-                   "pinned by tests/test_emulation.py::test_msm_batched_affine_levels_logic")
-@pytest.mark.parametrize("cname,group", [("bn254", 1), ("bn254", 2), ("bls12-381", 1), ("bw6-761", 1)])
-@pytest.mark.parametrize("levels", [1, 4])
-def test_msm_batched_affine_levels(gpu, monkeypatch, cname, group, levels):
-    """opt-in GB200_MSM_BATCH_AFFINE: affine tree levels (one binary-GCD inversion per 32 additions) in front of the
-    XYZZ accumulate; known-dlog oracle, uniform and skewed scalars, precomputed and plain tables"""
-    from util import known_dlog_instance
-    c = CURVES[cname]
-    monkeypatch.setenv("GB200_MSM_BATCH_AFFINE", str(levels))
-    for skew in (False, True):
-        _, _, pts, sc, expected = known_dlog_instance(c, group, 9000, seed=levels + 10 * group, skew=skew)
-        for precomp in (True, False):
-            t = gpu.Table(c.curve_id, group, pts, precomp=precomp)
-            assert jac_to_affine(c, group, t.msm(sc)) == expected
-            t.free()
-
-
 @pytest.mark.xfail(strict=False, reason="C++ orchestration (plonk_host.cu) written after this round's GPU budget was spent: a "
                    "translation of gnark_b200/plonk.py, whose algebra is pinned on the CPU (tests/test_plonk_orchestration.py)")
 @pytest.mark.parametrize("c", [CURVES["bn254"], CURVES["bls12-381"]], ids=lambda c: c.name)
@@ -369,6 +244,32 @@ def test_plonk_prove_bsb22(gpu, n_commit):
     key.free()
 
 
+@pytest.mark.xfail(strict=False, reason="see test_plonk_prove_bsb22")
+@pytest.mark.parametrize("cname", ["bn254", "bls12-381"])
+def test_plonk_prove_reproduces_golden(gpu, cname):
+    """the committed PLONK known-answer vector (tests/golden/kat_plonk_v1.json) through b200_plonk_prove on the GPU"""
+    from oracle import corelib
+    from test_golden import _plonk_case
+    c, circ, l, rr, o, pi2, ch, tau, want = _plonk_case(cname)
+    r, L = c.r, c.fr_limbs
+    n, logn = circ.n, circ.n.bit_length() - 1
+    pe = lambda v: ff.pack_elements(v, r, L)
+    srs = corelib.fixed_base(c, 1, ec.pack_points(c, 1, [c.g1]), pe([pow(tau, i, r) for i in range(n + 3)]))
+    key = gpu.PlonkKey(c.curve_id, logn, pe(circ.ql), pe(circ.qr), pe(circ.qm), pe(circ.qo), pe(circ.qk),
+                       np.array(circ.perm, dtype=np.int64), srs, qcp=[pe(v) for v in circ.qcp])
+    pts, vals, bsb = key.prove(pe(l), pe(rr), pe(o), pe([ch.gamma]), pe([ch.beta]), pe([ch.alpha]), pe([ch.zeta]),
+                               pe([ch.v]), pe(ch.bl), pe(ch.br), pe(ch.bo), pe(ch.bz), pi2=[pe(v) for v in pi2])
+    F = ff.Fp(c.p)
+    dl = [H(want[k]) for k in ("L", "R", "O", "Z")] + [H(x) for x in want["H"]] + [H(want["lin"]), H(want["batch_opening"]),
+                                                                                  H(want["z_opening"])]
+    for k in range(10):
+        assert jac_to_affine(c, 1, pts[k]) == ec.scalar_mul(F, dl[k], c.g1), k
+    assert jac_to_affine(c, 1, bsb[0]) == ec.scalar_mul(F, H(want["bsb22"][0]), c.g1)
+    got = ff.unpack_elements(vals, r, L)
+    assert got[:6] + got[7:] == [H(x) for x in want["claimed"]] and got[6] == H(want["zu"])
+    key.free()
+
+
 @pytest.mark.xfail(strict=False, reason="K-wire filtering for keys with BSB22 commitments written after this round's GPU budget "
                    "was spent (same gather kernel as the validated A / B wire filters)")
 def test_groth16_committed_wires_filtered_from_k(gpu):
@@ -407,30 +308,188 @@ def test_groth16_committed_wires_filtered_from_k(gpu):
     pk2.free_gpu_resources()
 
 
-@pytest.mark.xfail(strict=False, reason="see test_plonk_prove_bsb22")
-@pytest.mark.parametrize("cname", ["bn254", "bls12-381"])
-def test_plonk_prove_reproduces_golden(gpu, cname):
-    """the committed PLONK known-answer vector (tests/golden/kat_plonk_v1.json) through b200_plonk_prove on the GPU"""
+@pytest.mark.xfail(strict=False, reason="full-size identity test written after this round's GPU budget was spent (validated kernels)")
+@pytest.mark.parametrize("cname,logn", [("bn254", 22), ("bls12-381", 24)])
+def test_ntt_full_size_identities(gpu, cname, logn):
+    """SURVEY.md §8c-4 at BASELINE sizes (2^22, 2^24), where no CPU oracle run is affordable: the inverse transform
+    undoes the forward one bit for bit, and X[k] = p(w^k) at a few random k (Horner evaluation of the 2^logn
+    coefficients by b200_poly_eval against the NTT output, plain and on the coset)."""
+    import torch
+    from oracle import ntt
+    c = CURVES[cname]
+    L = c.fr_limbs
+    n = 1 << logn
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randint(0, 1 << 62, (n, L), dtype=torch.int64, device="cuda", generator=g)
+    x[:, L - 1] &= (1 << 56) - 1                      # < r: valid Montgomery residues
+    x = x.reshape(-1).contiguous()
+    d = gpu.Domain(c.curve_id, logn)
+    dom = ntt.Domain(c, n)                             # generator / coset constants only
+    rng = random.Random(8)
+    for on_coset in (False, True):
+        y = x.clone()
+        d.ntt_async(y, inverse=False, decimation=gpu.DIF, on_coset=on_coset)      # natural -> bit-reversed
+        gpu.sync(0)
+        for _ in range(3):
+            k = rng.randrange(n)
+            point = pow(dom.generator, k, c.r) * (dom.coset_gen if on_coset else 1) % c.r
+            want = gpu.poly_eval(0, c.curve_id, x, n, ff.pack_elements([point], c.r, L))
+            pos = ntt.bitrev(k, logn)
+            got = y[pos * L:(pos + 1) * L].cpu().numpy().view(np.uint64)
+            assert np.array_equal(got, want.reshape(-1)), (cname, logn, on_coset, k)
+        d.ntt_async(y, inverse=True, decimation=gpu.DIT, on_coset=on_coset)       # bit-reversed -> natural
+        gpu.sync(0)
+        assert torch.equal(y, x), (cname, logn, on_coset)
+    d.free()
+
+
+@pytest.mark.xfail(strict=False, reason="written after this round's GPU budget was spent; the decomposition is pinned on the "
+                   "CPU over gloo (tests/test_dist.py::test_sharded_ntt_gloo)")
+def test_sharded_ntt_single_rank(gpu):
+    """gnark_b200/parallel_ntt.py with world = 1 on the GPU: no exchange, but the stream scoping, the local
+    transform + bit reversal and the coset scaling are the ones every rank runs (multi-rank: tools/bench_sharded_ntt.py)"""
+    import torch
+    from gnark_b200 import parallel_ntt as pn
+    from oracle import ntt
+    c = CURVES["bn254"]
+    logn = 10
+    n = 1 << logn
+    rng = random.Random(5)
+    x = [rng.randrange(c.r) for _ in range(n)]
+    X = ff.pack_elements(x, c.r, c.fr_limbs).reshape(n, c.fr_limbs)
+    dom = ntt.Domain(c, n)
+    sd = pn.ShardedDomain(c.curve_id, logn, 0, 1)
+    for on_coset in (False, True):
+        d = torch.from_numpy(X.view(np.int64).reshape(-1).copy()).cuda()
+        got = sd.forward(d, on_coset=on_coset).cpu().numpy().view(np.uint64)
+        want = ntt.bit_reverse(dom.fft(list(x), ntt.DIF, on_coset=on_coset))
+        assert ff.unpack_elements(got, c.r, c.fr_limbs) == want
+        back = sd.inverse(sd.forward(torch.from_numpy(X.view(np.int64).reshape(-1).copy()).cuda(), on_coset=on_coset),
+                          on_coset=on_coset).cpu().numpy().view(np.uint64)
+        assert ff.unpack_elements(back, c.r, c.fr_limbs) == x
+    sd.free()
+
+
+@pytest.mark.xfail(strict=False, reason="entry point written after this round's GPU budget was spent")
+def test_msm_submit_stream_of_msms(gpu):
+    """b200_msm_submit: a stream of MSMs from pinned host buffers (different scalars, different ranges), results
+    after b200_sync, each against the known-dlog oracle"""
+    import torch
+    from util import known_dlog_instance
+    c = CURVES["bn254"]
+    n = 6000
+    F, base, pts, sc, expected = known_dlog_instance(c, 1, n, seed=77)
+    t = gpu.Table(c.curve_id, 1, pts, precomp=True)
+    h_sc = torch.from_numpy(sc.view(np.int64).copy()).pin_memory()
+    K = 6
+    h_out = torch.zeros((K, 12), dtype=torch.int64).pin_memory()
+    for i in range(K):
+        t.msm_submit(h_sc, h_out[i], n=n)
+    gpu.sync(0)
+    for i in range(K):
+        assert jac_to_affine(c, 1, h_out[i].numpy().view(np.uint64)) == expected
+    # a sub-range and the empty sum
+    half = n // 2
+    h2 = torch.zeros((2, 12), dtype=torch.int64).pin_memory()
+    t.msm_submit(h_sc.view(n, 4)[:half], h2[0], n=half)
+    t.msm_submit(h_sc, h2[1], n=0)
+    gpu.sync(0)
+    want_half = jac_to_affine(c, 1, t.msm(sc[:half].copy(), n=half))
+    assert jac_to_affine(c, 1, h2[0].numpy().view(np.uint64)) == want_half
+    assert jac_to_affine(c, 1, h2[1].numpy().view(np.uint64)) is None
+    t.free()
+
+
+@pytest.mark.xfail(strict=False, reason="entry point written after this round's GPU budget was spent; the per-thread "
+                   "functions are pinned on the CPU by tests/test_emulation.py::test_fixed_base_batch_logic")
+@pytest.mark.parametrize("c", ALL, ids=lambda c: c.name)
+@pytest.mark.parametrize("group", (1, 2))
+def test_fixed_base_batch(gpu, c, group):
+    """b200_fixed_base_batch (curve.BatchScalarMultiplicationG1/G2, setup.go:233,302) against the C++ oracle's
+    fixed-base batch, bit-exact affine points; host and device I/O; edge scalars"""
+    import torch
     from oracle import corelib
-    from test_golden import _plonk_case
-    c, circ, l, rr, o, pi2, ch, tau, want = _plonk_case(cname)
-    r, L = c.r, c.fr_limbs
-    n, logn = circ.n, circ.n.bit_length() - 1
-    pe = lambda v: ff.pack_elements(v, r, L)
-    srs = corelib.fixed_base(c, 1, ec.pack_points(c, 1, [c.g1]), pe([pow(tau, i, r) for i in range(n + 3)]))
-    key = gpu.PlonkKey(c.curve_id, logn, pe(circ.ql), pe(circ.qr), pe(circ.qm), pe(circ.qo), pe(circ.qk),
-                       np.array(circ.perm, dtype=np.int64), srs, qcp=[pe(v) for v in circ.qcp])
-    pts, vals, bsb = key.prove(pe(l), pe(rr), pe(o), pe([ch.gamma]), pe([ch.beta]), pe([ch.alpha]), pe([ch.zeta]),
-                               pe([ch.v]), pe(ch.bl), pe(ch.br), pe(ch.bo), pe(ch.bz), pi2=[pe(v) for v in pi2])
-    F = ff.Fp(c.p)
-    dl = [H(want[k]) for k in ("L", "R", "O", "Z")] + [H(x) for x in want["H"]] + [H(want["lin"]), H(want["batch_opening"]),
-                                                                                  H(want["z_opening"])]
-    for k in range(10):
-        assert jac_to_affine(c, 1, pts[k]) == ec.scalar_mul(F, dl[k], c.g1), k
-    assert jac_to_affine(c, 1, bsb[0]) == ec.scalar_mul(F, H(want["bsb22"][0]), c.g1)
-    got = ff.unpack_elements(vals, r, L)
-    assert got[:6] + got[7:] == [H(x) for x in want["claimed"]] and got[6] == H(want["zu"])
-    key.free()
+    from util import pick_base
+    rng = random.Random(61 + group)
+    F, base = pick_base(c, group, rng)
+    n = 3001
+    ks = [rng.randrange(c.r) for _ in range(n)]
+    ks[0], ks[1], ks[2] = 0, 1, c.r - 1
+    KS = ff.pack_elements(ks, c.r, c.fr_limbs)
+    BA = ec.pack_points(c, group, [base])
+    want = corelib.fixed_base(c, group, BA, KS)
+    got = gpu.fixed_base_batch(c.curve_id, group, BA, KS)
+    assert np.array_equal(got.reshape(want.shape), want)
+    d_ks = torch.from_numpy(KS.view(np.int64)).cuda()
+    d_out = torch.zeros(want.size, dtype=torch.int64, device="cuda")
+    gpu.fixed_base_batch(c.curve_id, group, BA, d_ks, n=n, out=d_out)
+    assert np.array_equal(d_out.cpu().numpy().view(np.uint64).reshape(want.shape), want)
+    assert ec.unpack_points(c, group, got)[2] == ec.scalar_mul(F, c.r - 1, base)
+
+
+@pytest.mark.xfail(strict=False, reason="one-process multi-GPU path written after this round's GPU budget was spent; its host logic "
+                   "is pinned on the CPU by tests/test_groth16_host_logic.py")
+def test_groth16_with_devices_in_one_process(gpu):
+    """WithDevices: every visible GPU holds one point-range shard of the key, the device parts run concurrently from
+    one process (what a Go caller does with a goroutine per device); the proof must equal the single-device proof."""
+    import torch
+    from gnark_b200 import groth16 as b200
+    from oracle import groth16 as g16o
+    from util import build_groth16_pk, pack_solution
+    nd = torch.cuda.device_count()
+    if nd < 2:
+        pytest.skip("needs at least two GPUs")
+    c = CURVES["bn254"]
+    m = 3000
+    cs, W = g16o.square_chain_r1cs(m), g16o.square_chain_witness(c.r, m)
+    pk, pkd, _, _ = build_groth16_pk(c, cs, g16o.random_toxic(c, 17), 17)
+    sol = pack_solution(c, cs, W)
+    rs = [12345, 67890]
+    one = b200.ProveSolution(pk, sol, b200.WithDeviceID(0), b200.WithRandomness(lambda q, it=iter(rs): next(it)))
+    many = b200.ProveSolution(pk, sol, b200.WithDevices(*range(nd)), b200.WithRandomness(lambda q, it=iter(rs): next(it)))
+    assert np.array_equal(one.Ar, many.Ar) and np.array_equal(one.Bs, many.Bs) and np.array_equal(one.Krs, many.Krs)
+    pk.free_gpu_resources()
+
+
+@experiment
+@pytest.mark.xfail(strict=False, reason="opt-in experiment written after this round's GPU budget was spent; both kernels "
+                   "and the split geometry are validated separately, the concurrent launch is not yet")
+@pytest.mark.parametrize("cname", ["bn254", "bls12-381"])
+@pytest.mark.parametrize("pct", [30, 70])
+def test_msm_hybrid_accumulate(gpu, monkeypatch, cname, pct):
+    """opt-in GB200_MSM_HYBRID: accumulate tasks split between the IMAD.WIDE kernel and the FP64-pipe kernel on
+    two concurrent streams (CPU twin: tests/test_emulation.py::test_msm_hybrid_split_logic); known-dlog oracle"""
+    from util import known_dlog_instance
+    c = CURVES[cname]
+    monkeypatch.setenv("GB200_MSM_HYBRID", str(pct))
+    _, _, pts, sc, expected = known_dlog_instance(c, 1, 20000, seed=pct)
+    t = gpu.Table(c.curve_id, 1, pts, precomp=True)
+    for _ in range(3):      # repeated: the fork/join events are reused across calls
+        assert jac_to_affine(c, 1, t.msm(sc)) == expected
+    t.free()
+    monkeypatch.delenv("GB200_MSM_HYBRID")
+    t = gpu.Table(c.curve_id, 1, pts, precomp=True)
+    assert jac_to_affine(c, 1, t.msm(sc)) == expected
+    t.free()
+
+
+@experiment
+@pytest.mark.xfail(strict=False, reason="opt-in experiment written after this round's GPU budget was spent; per-thread logic "
+                   "pinned by tests/test_emulation.py::test_msm_batched_affine_levels_logic")
+@pytest.mark.parametrize("cname,group", [("bn254", 1), ("bn254", 2), ("bls12-381", 1), ("bw6-761", 1)])
+@pytest.mark.parametrize("levels", [1, 4])
+def test_msm_batched_affine_levels(gpu, monkeypatch, cname, group, levels):
+    """opt-in GB200_MSM_BATCH_AFFINE: affine tree levels (one binary-GCD inversion per 32 additions) in front of the
+    XYZZ accumulate; known-dlog oracle, uniform and skewed scalars, precomputed and plain tables"""
+    from util import known_dlog_instance
+    c = CURVES[cname]
+    monkeypatch.setenv("GB200_MSM_BATCH_AFFINE", str(levels))
+    for skew in (False, True):
+        _, _, pts, sc, expected = known_dlog_instance(c, group, 9000, seed=levels + 10 * group, skew=skew)
+        for precomp in (True, False):
+            t = gpu.Table(c.curve_id, group, pts, precomp=precomp)
+            assert jac_to_affine(c, group, t.msm(sc)) == expected
+            t.free()
 
 
 @experiment
@@ -474,65 +533,6 @@ print("EQUAL" if np.array_equal(outs[0], outs[1]) else "DIFFERENT")
         assert out.returncode == 0, out.stderr[-2000:]
         res[threads] = [ln for ln in out.stdout.splitlines() if ln.startswith("DIGEST")][0]
     assert res["0"] == res["4"]
-
-
-@pytest.mark.xfail(strict=False, reason="full-size identity test written after this round's GPU budget was spent (validated kernels)")
-@pytest.mark.parametrize("cname,logn", [("bn254", 22), ("bls12-381", 24)])
-def test_ntt_full_size_identities(gpu, cname, logn):
-    """SURVEY.md §8c-4 at BASELINE sizes (2^22, 2^24), where no CPU oracle run is affordable: the inverse transform
-    undoes the forward one bit for bit, and X[k] = p(w^k) at a few random k (Horner evaluation of the 2^logn
-    coefficients by b200_poly_eval against the NTT output, plain and on the coset)."""
-    import torch
-    from oracle import ntt
-    c = CURVES[cname]
-    L = c.fr_limbs
-    n = 1 << logn
-    g = torch.Generator(device="cuda").manual_seed(5)
-    x = torch.randint(0, 1 << 62, (n, L), dtype=torch.int64, device="cuda", generator=g)
-    x[:, L - 1] &= (1 << 56) - 1                      # < r: valid Montgomery residues
-    x = x.reshape(-1).contiguous()
-    d = gpu.Domain(c.curve_id, logn)
-    dom = ntt.Domain(c, n)                             # generator / coset constants only
-    rng = random.Random(8)
-    for on_coset in (False, True):
-        y = x.clone()
-        d.ntt_async(y, inverse=False, decimation=gpu.DIF, on_coset=on_coset)      # natural -> bit-reversed
-        gpu.sync(0)
-        for _ in range(3):
-            k = rng.randrange(n)
-            point = pow(dom.generator, k, c.r) * (dom.coset_gen if on_coset else 1) % c.r
-            want = gpu.poly_eval(0, c.curve_id, x, n, ff.pack_elements([point], c.r, L))
-            pos = ntt.bitrev(k, logn)
-            got = y[pos * L:(pos + 1) * L].cpu().numpy().view(np.uint64)
-            assert np.array_equal(got, want.reshape(-1)), (cname, logn, on_coset, k)
-        d.ntt_async(y, inverse=True, decimation=gpu.DIT, on_coset=on_coset)       # bit-reversed -> natural
-        gpu.sync(0)
-        assert torch.equal(y, x), (cname, logn, on_coset)
-    d.free()
-
-
-@pytest.mark.xfail(strict=False, reason="one-process multi-GPU path written after this round's GPU budget was spent; its host logic "
-                   "is pinned on the CPU by tests/test_groth16_host_logic.py")
-def test_groth16_with_devices_in_one_process(gpu):
-    """WithDevices: every visible GPU holds one point-range shard of the key, the device parts run concurrently from
-    one process (what a Go caller does with a goroutine per device); the proof must equal the single-device proof."""
-    import torch
-    from gnark_b200 import groth16 as b200
-    from oracle import groth16 as g16o
-    from util import build_groth16_pk, pack_solution
-    nd = torch.cuda.device_count()
-    if nd < 2:
-        pytest.skip("needs at least two GPUs")
-    c = CURVES["bn254"]
-    m = 3000
-    cs, W = g16o.square_chain_r1cs(m), g16o.square_chain_witness(c.r, m)
-    pk, pkd, _, _ = build_groth16_pk(c, cs, g16o.random_toxic(c, 17), 17)
-    sol = pack_solution(c, cs, W)
-    rs = [12345, 67890]
-    one = b200.ProveSolution(pk, sol, b200.WithDeviceID(0), b200.WithRandomness(lambda q, it=iter(rs): next(it)))
-    many = b200.ProveSolution(pk, sol, b200.WithDevices(*range(nd)), b200.WithRandomness(lambda q, it=iter(rs): next(it)))
-    assert np.array_equal(one.Ar, many.Ar) and np.array_equal(one.Bs, many.Bs) and np.array_equal(one.Krs, many.Krs)
-    pk.free_gpu_resources()
 
 
 @experiment
