@@ -146,12 +146,14 @@ int msm_emu(const void* points_, const void* scalars_, uint32_t n, int c, int pr
 }
 
 int g_ntt_tile_log = NTT_MAX_TILE_LOG;
+int g_ntt_radix8 = 0;
 template <class Fr>
 int ntt_emu(void* data_, unsigned logn, int inverse, int decimation, int on_coset, const void* gen_mont,
             const void* coset_mont) {
   Fr* data = reinterpret_cast<Fr*>(data_);
   NttDomainHost<Fr> dom;
   dom.tile_log = g_ntt_tile_log;
+  dom.radix8 = g_ntt_radix8;
   dom.init(logn, gen_mont ? reinterpret_cast<const Fr*>(gen_mont) : nullptr,
            coset_mont ? reinterpret_cast<const Fr*>(coset_mont) : nullptr);
   dom.transform(data, inverse != 0, decimation, on_coset != 0);
@@ -629,6 +631,8 @@ int emu_plonk_bsb22(int curve, const void* qcp, const void* pi2, void* out, uint
 }
 
 // plan tile size used by emu_ntt (GB200_NTT_TILE_LOG on the device)
+// 1: emu_ntt walks the register-round kernel (GB200_NTT_RADIX8 on the device) instead of the one-stage-per-barrier one
+int emu_ntt_set_radix8(int on) { g_ntt_radix8 = on ? 1 : 0; return 0; }
 int emu_ntt_set_tile_log(int t) { if (t < 2 || t > NTT_MAX_TILE_LOG) return -1; g_ntt_tile_log = t; return 0; }
 
 int emu_ntt(int curve, void* data, unsigned logn, int inverse, int decimation, int on_coset, const void* gen_mont,

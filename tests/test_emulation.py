@@ -292,6 +292,32 @@ def test_ntt_smaller_tiles(hostemu, c):
         hostemu.emu_ntt_set_tile_log(11)
 
 
+@pytest.mark.parametrize("c", [CURVES["bn254"], CURVES["bw6-761"]], ids=lambda c: c.name)
+def test_ntt_register_rounds(hostemu, c):
+    """opt-in GB200_NTT_RADIX8: up to three stages per shared-memory exchange, a group of 8 elements per thread in
+    registers (ntt_round / ntt_round_dispatch), walked thread by thread over padded shared-memory slots - every stage
+    count 1..11 per pass (round plans 3+3+3+2, 3+3+2+2, 2+2, 1 ...), passes with carried-along contiguous bits, all
+    four mode combinations"""
+    rng = random.Random(15)
+    try:
+        assert hostemu.emu_ntt_set_radix8(1) == 0
+        for tile_log, logn in ((11, 1), (11, 2), (11, 3), (11, 4), (11, 5), (11, 7), (11, 10), (11, 11), (11, 13),
+                               (10, 12), (6, 9), (4, 10), (7, 7), (9, 17 if c.fr_limbs <= 4 else 12)):
+            assert hostemu.emu_ntt_set_tile_log(tile_log) == 0
+            n = 1 << logn
+            dom = ntt.Domain(c, n)
+            a = [rng.randrange(c.r) for _ in range(n)]
+            A0 = ff.pack_elements(a, c.r, c.fr_limbs)
+            for inv, dec, cos in ((0, 0, 0), (1, 0, 1), (0, 1, 1), (1, 1, 0)):
+                A = A0.copy()
+                assert hostemu.emu_ntt(c.curve_id, P(A), logn, inv, dec, cos, None, None) == 0
+                exp = (dom.fft_inverse if inv else dom.fft)(a, dec, on_coset=bool(cos))
+                assert ff.unpack_elements(A, c.r, c.fr_limbs) == exp, (c.name, tile_log, logn, inv, dec, cos)
+    finally:
+        hostemu.emu_ntt_set_tile_log(11)
+        hostemu.emu_ntt_set_radix8(0)
+
+
 # ---- FP64-pipe path (field52.cuh / curve52.cuh): 52-bit limbs, DFMA round-toward-zero products ----
 def _limbs52(v, L):
     return np.array([(v >> (52 * i)) & ((1 << 52) - 1) for i in range(L)], dtype=np.uint64)

@@ -58,9 +58,9 @@ def main():
             continue
         print(f"### {os.path.basename(path)}\n")
         if "tile_log" in rows[0]:
-            print("| curve | log2n | tile_log | ms | matches default |\n|---|---|---|---|---|")
+            print("| curve | log2n | radix8 | tile_log | ms | matches default |\n|---|---|---|---|---|---|")
             for r in rows:
-                print(f"| {r['curve']} | {r['log2n']} | {r['tile_log']} | {r['ms']:.4f} | {r['matches_default']} |")
+                print(f"| {r['curve']} | {r['log2n']} | {r.get('radix8', 0)} | {r['tile_log']} | {r['ms']:.4f} | {r['matches_default']} |")
             print()
             continue
         knobs = [k for k in rows[0] if k.startswith("GB200_") or k == "lib"]
