@@ -213,6 +213,72 @@ def verify(curve, circ: Circuit, proof: Proof, ch: Challenges, tau: int) -> bool
     return True
 
 
+def verify_pairing(curve, circ: Circuit, points, values, ch: Challenges, tau: int, bsb22_points=()) -> bool:
+    """The verifier of backend/plonk/bn254/verify.go:38-320 on the PROOF POINTS, with real pairings (oracle/pairing.py;
+    BN254 and BLS12-381): what the reference's own test does with a proof (prove -> Verify).
+      points: the ten G1 points a prover returns - [L] [R] [O] [Z] [H1] [H2] [H3] [linearised] [batch opening] [Z opening]
+              (affine, canonical ints);  values: lin(zeta), l, r, o, s1, s2 at zeta, Z(w zeta), then Qcp_j(zeta).
+    The verifying key (digests of the selectors / permutation polynomials, [1]_2, [tau]_2) is derived from the circuit
+    and tau, as Setup would; the proof side uses nothing but the points and values handed in."""
+    from . import ec, ff, pairing
+    r, n = curve.r, circ.n
+    F1, F2 = ff.Fp(curve.p), ff.base_field(curve, 2)
+    G1, G2 = curve.g1, curve.g2
+    dom0 = Domain(curve, n)
+    g, w = dom0.coset_gen, dom0.generator
+    zeta, alpha, beta, gamma = ch.zeta, ch.alpha, ch.beta, ch.gamma
+    cmL, cmR, cmO, cmZ, cmH1, cmH2, cmH3, cmLin, cmBatch, cmZopen = points
+    lin_z, lz, rz, oz, s1z, s2z, zu = values[:7]
+    qcpz = list(values[7:])
+    assert len(qcpz) == len(circ.qcp) == len(bsb22_points)
+    mul = lambda k, P: ec.scalar_mul(F1, k % r, P)
+    add = lambda P, Q: ec.affine_add(F1, P, Q)
+    neg = lambda P: ec.affine_neg(F1, P)
+    # verifying key
+    s1, s2, s3 = sigma_polys(curve, dom0, circ.perm)
+    vk = lambda lag: mul(poly_eval(r, canonical(curve, dom0, lag), tau), G1)
+    vS1, vS2, vS3 = vk(s1), vk(s2), vk(s3)
+    vQl, vQr, vQm, vQo, vQk = vk(circ.ql), vk(circ.qr), vk(circ.qm), vk(circ.qo), vk(circ.qk)
+    vQcp = [vk(q_) for q_ in circ.qcp]
+    tau_g2 = ec.scalar_mul(F2, tau, G2)
+    # 1. the opened value of the linearised polynomial (verify.go: the constant part moved to the right-hand side)
+    zn = pow(zeta, n, r)
+    zh = (zn - 1) % r
+    l1 = zh * pow((zeta - 1) % r, -1, r) % r * dom0.cardinality_inv % r
+    want = (alpha * alpha % r * l1
+            - alpha * ((lz + beta * s1z + gamma) % r) % r * ((rz + beta * s2z + gamma) % r) % r * ((oz + gamma) % r) % r * zu) % r
+    if lin_z != want:
+        return False
+    # 2. the linearised digest, rebuilt from the key and the proof
+    c1 = (lz + beta * s1z + gamma) % r * ((rz + beta * s2z + gamma) % r) % r * zu % r * beta % r * alpha % r
+    uz, uuz = zeta * g % r, zeta * g % r * g % r
+    c2 = (-(lz + beta * zeta + gamma) % r * ((rz + beta * uz + gamma) % r) % r * ((oz + beta * uuz + gamma) % r) % r * alpha) % r
+    zn2 = zn * zeta % r * zeta % r
+    acc = mul((c2 + alpha * alpha % r * l1) % r, cmZ)
+    for k, P in ((c1, vS3), (rz * lz, vQm), (lz, vQl), (rz, vQr), (oz, vQo), (1, vQk)):
+        acc = add(acc, mul(k, P))
+    for q_, P in zip(qcpz, bsb22_points):
+        acc = add(acc, mul(q_, P))
+    hfold = add(add(mul(zn2 * zn2, cmH3), mul(zn2, cmH2)), cmH1)
+    acc = add(acc, neg(mul(zh, hfold)))
+    if acc != cmLin:
+        return False
+    # 3. the two KZG openings: e([f] - f(z)[1] + z [H], [1]_2) = e([H], [tau]_2)
+    digests = [cmLin, cmL, cmR, cmO, vS1, vS2] + vQcp
+    claimed = [lin_z, lz, rz, oz, s1z, s2z] + qcpz
+    Fd, fz, vp = None, 0, 1
+    for D, cval in zip(digests, claimed):
+        Fd = add(Fd, mul(vp, D))
+        fz = (fz + vp * cval) % r
+        vp = vp * ch.v % r
+    T = pairing.get(curve)
+    lhs = add(add(Fd, neg(mul(fz, G1))), mul(zeta, cmBatch))
+    if not T.product_is_one([(lhs, G2), (neg(cmBatch), tau_g2)]):
+        return False
+    lhs = add(add(cmZ, neg(mul(zu, G1))), mul(zeta * w, cmZopen))
+    return T.product_is_one([(lhs, G2), (neg(cmZopen), tau_g2)])
+
+
 def random_satisfied_instance(curve, n, seed, n_commit=0):
     """A random satisfied trace: random gates L*R-style with O solved, and a permutation built from
     cycles over slots that are FORCED to carry equal values (so the copy constraints hold).

@@ -205,6 +205,8 @@ def test_plonk_prove_c_abi_vs_oracle(gpu, c, logn):
         assert jac_to_affine(c, 1, pts[k]) == ec.scalar_mul(F, dl[k], c.g1), name
     got_vals = ff.unpack_elements(vals, r, L)
     assert got_vals[:6] == want.claimed and got_vals[6] == want.zu
+    # prove -> Verify: the verifier's equations on the CUDA prover's points, real pairings
+    assert pp.verify_pairing(c, circ, [jac_to_affine(c, 1, pts[k]) for k in range(10)], got_vals, ch, tau)
     key.free()
 
 

@@ -78,6 +78,13 @@ def test_plonk_host_orchestration_vs_oracle(mock, cname, logn):
         assert jac_to_affine(c, 1, pts[k]) == ec.scalar_mul(F, dl[k], c.g1), name
     got = ff.unpack_elements(vals, r, L)
     assert got[:6] == want.claimed and got[6] == want.zu
+    # prove -> Verify as the reference tests it: the verifier's equations on the proof points, real pairings
+    proof_pts = [jac_to_affine(c, 1, pts[k]) for k in range(10)]
+    assert pp.verify_pairing(c, circ, proof_pts, got, ch, tau)
+    tampered = list(proof_pts); tampered[8] = ec.affine_add(F, tampered[8], c.g1)
+    assert not pp.verify_pairing(c, circ, tampered, got, ch, tau)
+    bad_vals = list(got); bad_vals[2] = (bad_vals[2] + 1) % r
+    assert not pp.verify_pairing(c, circ, proof_pts, bad_vals, ch, tau)
     # the same proof round by round (the way a Fiat-Shamir transcript drives it), and the stage order is enforced
     jl = 3 * c.fp_limbs
     s_ = ctypes.c_void_p(0)
@@ -160,6 +167,9 @@ def test_plonk_host_bsb22_commitments(mock, monkeypatch, n_commit, coset_cache):
         assert jac_to_affine(c, 1, bsb[j]) == ec.scalar_mul(F, want.bsb22[j], c.g1)
     got = ff.unpack_elements(vals, r, L)
     assert got[:6] + got[7:] == want.claimed and got[6] == want.zu
+    if coset_cache == "1":      # Verify with real pairings, the BSB22 digests and Qcp openings included
+        assert pp.verify_pairing(c, circ, [jac_to_affine(c, 1, pts[k]) for k in range(10)], got, ch, tau,
+                                 bsb22_points=[jac_to_affine(c, 1, bsb[j]) for j in range(n_commit)])
     assert mock.b200_plonk_pk_free(h) == 0
 
 
