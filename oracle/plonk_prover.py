@@ -213,13 +213,16 @@ def verify(curve, circ: Circuit, proof: Proof, ch: Challenges, tau: int) -> bool
     return True
 
 
-def verify_pairing(curve, circ: Circuit, points, values, ch: Challenges, tau: int, bsb22_points=()) -> bool:
+def verify_pairing(curve, circ: Circuit, points, values, ch: Challenges, tau: int = None, bsb22_points=(), srs_g1=None,
+                   tau_g2=None, msm=None) -> bool:
     """The verifier of backend/plonk/bn254/verify.go:38-320 on the PROOF POINTS, with real pairings (oracle/pairing.py;
     BN254 and BLS12-381): what the reference's own test does with a proof (prove -> Verify).
       points: the ten G1 points a prover returns - [L] [R] [O] [Z] [H1] [H2] [H3] [linearised] [batch opening] [Z opening]
               (affine, canonical ints);  values: lin(zeta), l, r, o, s1, s2 at zeta, Z(w zeta), then Qcp_j(zeta).
     The verifying key (digests of the selectors / permutation polynomials, [1]_2, [tau]_2) is derived from the circuit
-    and tau, as Setup would; the proof side uses nothing but the points and values handed in."""
+    as Setup would: from tau when the trapdoor is known, or - no trapdoor anywhere - from an SRS given as points
+    (srs_g1 = [tau^k]_1 affine, tau_g2 = [tau]_2; e.g. the Ethereum KZG ceremony SRS the reference ships).  The proof
+    side uses nothing but the points and values handed in."""
     from . import ec, ff, pairing
     r, n = curve.r, circ.n
     F1, F2 = ff.Fp(curve.p), ff.base_field(curve, 2)
@@ -236,11 +239,16 @@ def verify_pairing(curve, circ: Circuit, points, values, ch: Challenges, tau: in
     neg = lambda P: ec.affine_neg(F1, P)
     # verifying key
     s1, s2, s3 = sigma_polys(curve, dom0, circ.perm)
-    vk = lambda lag: mul(poly_eval(r, canonical(curve, dom0, lag), tau), G1)
+    if srs_g1 is not None:
+        assert tau_g2 is not None and len(srs_g1) >= n
+        msm = msm or (lambda pts, sc: ec.msm_naive(F1, pts, sc))     # msm: optional faster MSM for large n
+        vk = lambda lag: msm(list(srs_g1[:n]), canonical(curve, dom0, lag))
+    else:
+        vk = lambda lag: mul(poly_eval(r, canonical(curve, dom0, lag), tau), G1)
+        tau_g2 = ec.scalar_mul(F2, tau, G2)
     vS1, vS2, vS3 = vk(s1), vk(s2), vk(s3)
     vQl, vQr, vQm, vQo, vQk = vk(circ.ql), vk(circ.qr), vk(circ.qm), vk(circ.qo), vk(circ.qk)
     vQcp = [vk(q_) for q_ in circ.qcp]
-    tau_g2 = ec.scalar_mul(F2, tau, G2)
     # 1. the opened value of the linearised polynomial (verify.go: the constant part moved to the right-hand side)
     zn = pow(zeta, n, r)
     zh = (zn - 1) % r

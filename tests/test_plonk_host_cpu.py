@@ -219,3 +219,49 @@ def test_plonk_host_reproduces_golden(mock, cname):
     got = ff.unpack_elements(vals, r, L)
     assert got[:6] + got[7:] == [Hx(x) for x in want["claimed"]] and got[6] == Hx(want["zu"])
     assert mock.b200_plonk_pk_free(h) == 0
+
+
+def test_plonk_proof_over_the_ethereum_srs_verifies(mock):
+    """No trapdoor anywhere: the C++ PLONK orchestration commits with the Ethereum KZG ceremony SRS the reference ships
+    (tests/golden/eth_kzg_srs_v1.bin, tau unknown), and the proof is checked by the verifier's pairing equations with
+    the fixture's own [tau]_2.  Every commitment is an MSM over externally produced points, every opening must be
+    consistent with them - there is no discrete log to compare with."""
+    from oracle import kzg_srs
+    c = CURVES["bls12-381"]
+    logn = 5
+    n = 1 << logn
+    r, L = c.r, c.fr_limbs
+    rng = random.Random(77)
+    mono, _, g2 = kzg_srs.load()
+    circ, l, rr, o = pp.random_satisfied_instance(c, n, seed=123)
+    rnd = lambda: rng.randrange(r)
+    ch = pp.Challenges(gamma=rnd(), beta=rnd(), alpha=rnd(), zeta=rnd(), v=rnd(), bl=[rnd(), rnd()], br=[rnd(), rnd()],
+                       bo=[rnd(), rnd()], bz=[rnd(), rnd(), rnd()])
+    pe = lambda v: np.ascontiguousarray(ff.pack_elements(v, r, L))
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    srs = np.ascontiguousarray(ec.pack_points(c, 1, mono[:n + 3]))
+    keep = {k: pe(getattr(circ, k)) for k in ("ql", "qr", "qm", "qo", "qk")}
+    perm = np.ascontiguousarray(np.array(circ.perm, dtype=np.int64))
+    d = b200.PlonkPkDesc()
+    d.log2n = logn
+    for k, a in keep.items():
+        setattr(d, k, P(a).value)
+    d.perm, d.srs_canonical = P(perm).value, P(srs).value
+    h = ctypes.c_void_p(0)
+    assert mock.b200_plonk_pk_load(0, c.curve_id, ctypes.byref(d), ctypes.byref(h)) == 0, mock.b200_last_error()
+    sc = {k: pe(v) for k, v in (("gamma", [ch.gamma]), ("beta", [ch.beta]), ("alpha", [ch.alpha]), ("zeta", [ch.zeta]),
+                                ("v", [ch.v]), ("bl", ch.bl), ("br", ch.br), ("bo", ch.bo), ("bz", ch.bz))}
+    cs = b200.PlonkChallenges()
+    for k, a in sc.items():
+        setattr(cs, k, P(a).value)
+    pts = np.zeros((10, 3 * c.fp_limbs), dtype=np.uint64)
+    vals = np.zeros((7, L), dtype=np.uint64)
+    L_, R_, O_ = pe(l), pe(rr), pe(o)
+    assert mock.b200_plonk_prove(h, P(L_), P(R_), P(O_), ctypes.byref(cs), P(pts), P(vals)) == 0, mock.b200_last_error()
+    proof_pts = [jac_to_affine(c, 1, pts[k]) for k in range(10)]
+    got = ff.unpack_elements(vals, r, L)
+    assert pp.verify_pairing(c, circ, proof_pts, got, ch, srs_g1=mono, tau_g2=g2[1])
+    assert not pp.verify_pairing(c, circ, proof_pts, got, ch, srs_g1=mono, tau_g2=g2[2])      # another [tau]_2
+    wrong = list(got); wrong[1] = (wrong[1] + 1) % r
+    assert not pp.verify_pairing(c, circ, proof_pts, wrong, ch, srs_g1=mono, tau_g2=g2[1])
+    assert mock.b200_plonk_pk_free(h) == 0
