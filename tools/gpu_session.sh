@@ -72,7 +72,8 @@ echo "== 3v. compile-time arithmetic / calling-convention variants" | tee -a $OU
 #   make -C gnark_b200/csrc opt OPTFLAGS="-DGB200_MONT_SQR -DGB200_XYZZ_LAZY -DGB200_ACC_MIN_BLOCKS=5" OPTNAME=sqrxlazy5
 #     (BN254 G1 accumulate: -9.4 % IMAD.WIDE at 96 registers - the first candidate, profiles/r01_sass_stats.md)
 #   make -C gnark_b200/csrc opt OPTFLAGS=-DGB200_ACC_PREFETCH OPTNAME=prefetch -> L2 prefetch of the next gathered point
-#   or all of them:  make -C gnark_b200/csrc variants
+#   or all of them:  make -j8 -C gnark_b200/csrc variants      (about an hour on 8 cores; `variants-top`: the four first
+#   candidates sqrxlazy5 / prefetch / inl12 / lazy in ~10 min)
 # each library runs only the configurations its flags can change (a run = table upload + precompute + 10 MSMs, ~15 s)
 for lib in gnark_b200/lib/libgnark_b200_*.so; do
   [ -f "$lib" ] || continue
