@@ -1,0 +1,91 @@
+#!/usr/bin/env python3
+"""Randomised soak of the device templates compiled for the host (tests/_build/libgb200_hostemu*.so: the default build and
+the A/B arithmetic build) against big-int arithmetic and the C++ oracle - longer than the unit tests allow:
+
+   python tools/fuzz_emulation.py field 60000      # mul / sqr / mul_sub / Fp2 mul, sqr on every field, special values mixed in
+   python tools/fuzz_emulation.py msm 60           # small MSMs with equal points, P and -P, infinities, special scalars
+
+Round 1: 960 k products + 480 k single-reduction mul_sub + Fp2 operations and 780 MSMs, no mismatch."""
+import sys
+MODE = sys.argv[1] if len(sys.argv) > 1 else "field"
+sys.argv = [sys.argv[0]] + sys.argv[2:]
+if MODE == "field":
+    import sys, ctypes, random, time
+    import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import numpy as np
+    from oracle import ff
+    from oracle.params import CURVES
+    P=lambda a:a.ctypes.data_as(ctypes.c_void_p)
+    libs={'default':ctypes.CDLL(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))+'/tests/_build/libgb200_hostemu.so'),'opt':ctypes.CDLL(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))+'/tests/_build/libgb200_hostemu_opt.so')}
+    rng=random.Random(12345)
+    N=int(sys.argv[1]) if len(sys.argv)>1 else 5000
+    def special(q,L):
+        top=1<<(64*L)
+        c=[0,1,q-1,q-2,(q+1)//2,2**32-1,2**64-1,(1<<(q.bit_length()-1)),q-(1<<32),q-(1<<64)]
+        return [x%q for x in c]
+    t0=time.time(); bad=0
+    for name,lib in libs.items():
+      for c in CURVES.values():
+        for which,(q,L) in enumerate(((c.p,c.fp_limbs),(c.r,c.fr_limbs))):
+          fid=c.curve_id*2+which
+          sp=special(q,L)
+          def pick(): return rng.choice(sp) if rng.random()<0.15 else rng.randrange(q)
+          for it in range(N):
+            a,b,cc,d=pick(),pick(),pick(),pick()
+            A=ff.pack_elements([a],q,L); B=ff.pack_elements([b,cc,d],q,L); O=np.zeros_like(A)
+            lib.emu_field_op(fid,2,P(A),P(B),P(O)); 
+            if ff.unpack_elements(O,q,L)[0]!=a*b%q: bad+=1; print('MUL',name,c.name,which,hex(a),hex(b))
+            lib.emu_field_op(fid,5,P(A),P(A),P(O))
+            if ff.unpack_elements(O,q,L)[0]!=a*a%q: bad+=1; print('SQR',name,c.name,which,hex(a))
+            if which==0:
+              lib.emu_field_op(fid,8,P(A),P(B),P(O))
+              if ff.unpack_elements(O,q,L)[0]!=(a*b-cc*d)%q: bad+=1; print('MULSUB',name,c.name,hex(a),hex(b),hex(cc),hex(d))
+        # Fp2
+        for c in [c for c in CURVES.values() if c.fp2_nonresidue is not None]:
+          F2=ff.Fp2(c.p,c.fp2_nonresidue); L=c.fp_limbs
+          for it in range(N//2):
+            a=(rng.randrange(c.p),rng.randrange(c.p)); b=(rng.randrange(c.p),rng.randrange(c.p))
+            A=ff.pack_elements(list(a),c.p,L).reshape(-1); B=ff.pack_elements(list(b),c.p,L).reshape(-1); O=np.zeros_like(A)
+            lib.emu_field_op(100+c.curve_id*2,2,P(A),P(B),P(O))
+            if tuple(ff.unpack_elements(O,c.p,L))!=F2.mul(a,b): bad+=1; print('FP2MUL',name,c.name)
+            lib.emu_field_op(100+c.curve_id*2,5,P(A),P(A),P(O))
+            if tuple(ff.unpack_elements(O,c.p,L))!=F2.sqr(a): bad+=1; print('FP2SQR',name,c.name)
+    print('done',N,'bad',bad,round(time.time()-t0,1),'s')
+
+else:
+    import sys, ctypes, random, time
+    import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import numpy as np
+    from oracle import ff, ec, corelib, derive
+    from oracle.params import CURVES
+    P=lambda a:a.ctypes.data_as(ctypes.c_void_p)
+    libs={'default':ctypes.CDLL(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))+'/tests/_build/libgb200_hostemu.so'),'opt':ctypes.CDLL(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))+'/tests/_build/libgb200_hostemu_opt.so')}
+    rng=random.Random(777); t0=time.time(); bad=0; runs=0
+    REPS=int(sys.argv[1])
+    for c in CURVES.values():
+      for group in (1,2):
+        F=ff.base_field(c,group); base=derive.subgroup_point(c,group)
+        deg=F.degree
+        pool=corelib.fixed_base(c,group,ec.pack_points(c,group,[base]),ff.pack_elements([rng.randrange(1,c.r) for _ in range(64)],c.r,c.fr_limbs))
+        pool=pool.reshape(64,-1)
+        for rep in range(REPS if c.fp_limbs<=6 else max(1,REPS//4)):
+          n=rng.choice([1,2,5,16,33])
+          idx=[rng.randrange(64) for _ in range(n)]
+          if n>2 and rng.random()<0.5: idx[1]=idx[0]           # equal points
+          pts=np.ascontiguousarray(pool[idx].copy())
+          if n>3 and rng.random()<0.3: pts[2]=0                 # infinity
+          sc=[rng.choice([0,1,c.r-1,2,rng.randrange(c.r)]) if rng.random()<0.3 else rng.randrange(c.r) for _ in range(n)]
+          if n>2 and rng.random()<0.5: sc[1]=sc[0]
+          if n>2 and rng.random()<0.3: sc[1]=(c.r-sc[0])%c.r    # P and -P meet
+          SA=ff.pack_elements(sc,c.r,c.fr_limbs)
+          want=corelib.msm(c,group,pts,SA,c=4)
+          wa=ec.from_jac(F,ec.unpack_points(c,group,want,ncoords=3)[0])
+          for name,lib in libs.items():
+            cw=rng.choice([3,5,8]); pre=rng.choice([0,1]) if c.fp_limbs<=6 else 0
+            out=np.zeros(3*deg*c.fp_limbs,dtype=np.uint64)
+            rc=lib.emu_msm(c.curve_id,group,P(pts),P(SA),n,cw,pre,rng.choice([2,3,64]),rng.choice([4,16]),P(out))
+            ga=ec.from_jac(F,ec.unpack_points(c,group,out,ncoords=3)[0])
+            runs+=1
+            if rc!=0 or ga!=wa: bad+=1; print('BAD',name,c.name,group,n,cw,pre)
+    print('runs',runs,'bad',bad,round(time.time()-t0,1),'s')
+
