@@ -124,10 +124,12 @@ int32_t msm_on_stream(DeviceCtx* ctx, b200_table_s* t, size_t off, size_t n, con
   void* ws = ws_buf.p;
   // opt-in: persistent accumulate (msm.cuh 4c); not combined with the FP64 / hybrid kernels
   const int persistent = (env_int("GB200_MSM_PERSISTENT", 0) > 0 && !t->fmt52 && t->hybrid52_of_16 == 0) ? 1 : 0;
-  MsmHybrid hy{t->d_points52, t->hybrid52_of_16, ctx->aux_stream, ctx->aux_fork_ev, ctx->aux_join_ev, ba_levels, persistent};
+  // opt-in: accumulator in shared memory (curve.cuh SmemXYZZ); the persistent kernel takes precedence
+  const int smem_acc = (env_int("GB200_MSM_SMEM_ACC", 0) > 0 && !persistent && !t->fmt52 && t->hybrid52_of_16 == 0) ? 1 : 0;
+  MsmHybrid hy{t->d_points52, t->hybrid52_of_16, ctx->aux_stream, ctx->aux_fork_ev, ctx->aux_join_ev, ba_levels, persistent, smem_acc};
   cudaError_t e = t->ops->run(ctx->stream, (uint32_t)n, (uint32_t)t->n, (uint32_t)off, t->c, t->precomp, task_len, chunk,
                               t->d_points, d_scalars, d_out, ws, stage_events, pipelined ? ctx->tail_stream : nullptr,
-                              ctx->fork_ev, t->fmt52, (t->hybrid52_of_16 > 0 || ba_levels > 0 || persistent) ? &hy : nullptr);
+                              ctx->fork_ev, t->fmt52, (t->hybrid52_of_16 > 0 || ba_levels > 0 || persistent || smem_acc) ? &hy : nullptr);
   // the workspace is last used by the tail kernels
   cudaError_t e2 = ws_buf.release_on(pipelined ? ctx->tail_stream : ctx->stream);
   if (pipelined && e == cudaSuccess) {

@@ -70,7 +70,7 @@ int wide_op(int op, const void* a_, const void* b_, void* out_) {
 
 template <class Fr, class F>
 int msm_emu(const void* points_, const void* scalars_, uint32_t n, int c, int precomp, uint32_t task_len,
-            uint32_t chunk, void* out_jac, int persistent_threads = 0) {
+            uint32_t chunk, void* out_jac, int persistent_threads = 0, bool smem_acc = false) {
   const Affine<F>* points = reinterpret_cast<const Affine<F>*>(points_);
   const Fr* scalars = reinterpret_cast<const Fr*>(scalars_);
   MsmPlan pl = msm_make_plan(n, n, 0, Fr::Params::BITS, c, precomp, task_len, chunk);
@@ -126,6 +126,16 @@ int msm_emu(const void* points_, const void* scalars_, uint32_t n, int c, int pr
     XYZZ<F> acc = XYZZ<F>::inf();
     for (uint32_t s = off[b]; s < off[b + 1]; s += pl.task_len) {
       uint32_t e = std::min(off[b + 1], s + pl.task_len);
+      if (smem_acc) {
+        // GB200_MSM_SMEM_ACC: the thread's accumulator lives in "shared memory" (strided words: 3 threads' worth, this
+        // thread in the middle, the neighbours' words must stay untouched)
+        constexpr int W4 = 4 * (int)(sizeof(F) / 4);
+        std::vector<uint32_t> sm((size_t)W4 * 3, 0xA5A5A5A5u);
+        acc.add(msm_accumulate_range_smem<F>(table.data(), svals.data(), s, e, sm.data() + 1, 3));
+        for (int k = 0; k < W4; k++)
+          if (sm[(size_t)k * 3] != 0xA5A5A5A5u || sm[(size_t)k * 3 + 2] != 0xA5A5A5A5u) return -3;
+        continue;
+      }
       acc.add(msm_accumulate_range<F>(table.data(), svals.data(), s, e));
     }
     buckets[b] = acc;
@@ -584,6 +594,22 @@ int emu_field_op(int field_id, int op, const void* a, const void* b, void* out) 
     case 100: return field_op<bn254_fp2>(op, a, b, out);
     case 102: return field_op<bls12_381_fp2>(op, a, b, out);
     case 104: return field_op<bls12_377_fp2>(op, a, b, out);
+  }
+  return -1;
+}
+
+// GB200_MSM_SMEM_ACC: the accumulate stage with the accumulator in (emulated) shared memory
+int emu_msm_smem(int curve, int group, const void* points, const void* scalars, uint32_t n, int c, int precomp,
+                 uint32_t task_len, uint32_t chunk, void* out_jac) {
+  switch (curve * 2 + (group - 1)) {
+    case 0: return msm_emu<bn254_fr, bn254_fp>(points, scalars, n, c, precomp, task_len, chunk, out_jac, 0, true);
+    case 1: return msm_emu<bn254_fr, bn254_fp2>(points, scalars, n, c, precomp, task_len, chunk, out_jac, 0, true);
+    case 2: return msm_emu<bls12_381_fr, bls12_381_fp>(points, scalars, n, c, precomp, task_len, chunk, out_jac, 0, true);
+    case 3: return msm_emu<bls12_381_fr, bls12_381_fp2>(points, scalars, n, c, precomp, task_len, chunk, out_jac, 0, true);
+    case 4: return msm_emu<bls12_377_fr, bls12_377_fp>(points, scalars, n, c, precomp, task_len, chunk, out_jac, 0, true);
+    case 5: return msm_emu<bls12_377_fr, bls12_377_fp2>(points, scalars, n, c, precomp, task_len, chunk, out_jac, 0, true);
+    case 6:
+    case 7: return msm_emu<bw6_761_fr, bw6_761_fp>(points, scalars, n, c, precomp, task_len, chunk, out_jac, 0, true);
   }
   return -1;
 }

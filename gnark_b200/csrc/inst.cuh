@@ -36,6 +36,7 @@ struct MsmInst {
     MsmPlan pl = plan(n, stride, off, c, precomp, task_len, chunk);
     pl.ba_levels = (hybrid && !fmt52) ? hybrid->ba_levels : 0;
     pl.persistent = (hybrid && !fmt52) ? hybrid->persistent : 0;
+    pl.smem_acc = (hybrid && !fmt52) ? hybrid->smem_acc : 0;
     MsmLayout<F> L;
     GB_CUDA_TRY(msm_layout<F>(pl, L));
     return msm_enqueue<Fr, F>(st, pl, reinterpret_cast<const Affine<F>*>(d_table),

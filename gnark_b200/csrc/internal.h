@@ -39,6 +39,8 @@ struct MsmHybrid {
   int ba_levels;
   // third opt-in experiment (GB200_MSM_PERSISTENT=1): accumulate on a grid sized to the SMs, tasks from an atomic counter
   int persistent;
+  // fourth opt-in experiment (GB200_MSM_SMEM_ACC=1): accumulator coordinates in shared memory, more resident warps
+  int smem_acc;
 };
 
 struct MsmOps {

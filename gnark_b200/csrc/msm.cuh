@@ -41,6 +41,7 @@ struct MsmPlan {
   uint32_t chunk;         // buckets per level-1 reduction chunk
   int ba_levels;          // batched-affine tree levels before the XYZZ accumulate (msm_batch.cuh), 0 = off
   int persistent;         // opt-in: accumulate tasks handed out by an atomic counter to a grid sized to the SMs
+  int smem_acc;           // opt-in: accumulator coordinates in shared memory (SmemXYZZ), register cap by field size
 };
 
 HD int msm_num_windows(int scalar_bits, int c) { return scalar_bits / c + 1; }
@@ -57,6 +58,7 @@ HD MsmPlan msm_make_plan(uint32_t n, uint32_t table_stride, uint32_t table_off, 
   p.task_len = task_len;
   p.ba_levels = 0;
   p.persistent = 0;
+  p.smem_acc = 0;
   p.chunk = chunk;
   return p;
 }
@@ -129,6 +131,16 @@ HD XYZZ<F> msm_accumulate_range(const Affine<F>* table, const uint32_t* vals, ui
   for (uint32_t e = begin; e < end; e++) acc.add_mixed(msm_load_point(table, vals[e]));
 #endif
   return acc;
+}
+
+// the same range with the accumulator in shared memory (SmemXYZZ, curve.cuh)
+template <class F>
+HD XYZZ<F> msm_accumulate_range_smem(const Affine<F>* table, const uint32_t* vals, uint32_t begin, uint32_t end,
+                                     uint32_t* smem_base, uint32_t stride) {
+  SmemXYZZ<F> acc{smem_base, stride};
+  acc.set(XYZZ<F>::inf());
+  for (uint32_t e = begin; e < end; e++) acc.add_mixed(msm_load_point(table, vals[e]));
+  return acc.get();
 }
 
 // FP64-pipe variant (field52.cuh / curve52.cuh): table entries are Affine52, the accumulator is

@@ -79,6 +79,27 @@ __global__ void GB200_ACC_BOUNDS k_msm_accumulate(MsmPlan pl, const Affine<F>* _
   partial[t] = msm_accumulate_range<F>(table, svals, begin, end);
 }
 
+// opt-in (GB200_MSM_SMEM_ACC): one thread per task as k_msm_accumulate, accumulator coordinates in shared memory.
+// The point of the exercise is occupancy, so the register cap follows the field size: 5 resident blocks for coordinates
+// of up to 64 B (BLS12-381 / BLS12-377 G1: 96 registers with ~220 B of spills instead of 126 and 4 blocks; BN254 G2: 96
+// instead of 144 registers and 3 blocks), 3 blocks for the 96-byte coordinates (BLS G2, BW6-761).  Shared memory per
+// block = 4 coordinates x sizeof(F) x 128 threads (24 .. 48 KiB).
+#ifndef GB200_SMEM_ACC_MIN_BLOCKS
+#define GB200_SMEM_ACC_MIN_BLOCKS (sizeof(F) <= 64 ? 5 : 3)
+#endif
+template <class F>
+__global__ void __launch_bounds__(128, GB200_SMEM_ACC_MIN_BLOCKS) k_msm_accumulate_smem(MsmPlan pl, const Affine<F>* __restrict__ table,
+                                                             const uint32_t* __restrict__ svals,
+                                                             const uint32_t* __restrict__ off,
+                                                             const uint32_t* __restrict__ task_off,
+                                                             XYZZ<F>* __restrict__ partial) {
+  extern __shared__ __align__(16) uint32_t acc_sm[];
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t begin, end;
+  if (!msm_task_bounds(pl, off, task_off, t, begin, end)) return;
+  partial[t] = msm_accumulate_range_smem<F>(table, svals, begin, end, acc_sm + threadIdx.x, blockDim.x);
+}
+
 // opt-in (GB200_MSM_PERSISTENT): the same tasks on a grid sized to the machine, handed out by an atomic counter
 // (msm_accumulate_persistent, msm.cuh 4c)
 template <class F>
@@ -421,6 +442,12 @@ cudaError_t msm_launch_accumulate(cudaStream_t stream, const MsmPlan& pl, const 
     if (grid > need) grid = need;
     GB_CUDA_TRY(cudaMemsetAsync(counter, 0, 4, stream));
     k_msm_accumulate_persistent<F><<<(unsigned)grid, 128, 0, stream>>>(pl, table, vals, off, task_off, partial, counter);
+  } else if (pl.smem_acc) {
+    const size_t smem = 4 * sizeof(F) * 128;
+    GB_CUDA_TRY(cudaFuncSetAttribute(k_msm_accumulate_smem<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GB_CUDA_TRY(cudaFuncSetAttribute(k_msm_accumulate_smem<F>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                     (int)cudaSharedmemCarveoutMaxShared));
+    k_msm_accumulate_smem<F><<<(unsigned)((L.max_tasks + 127) / 128), 128, smem, stream>>>(pl, table, vals, off, task_off, partial);
   } else {
     k_msm_accumulate<F><<<(unsigned)((L.max_tasks + 127) / 128), 128, 0, stream>>>(pl, table, vals, off, task_off, partial);
   }

@@ -253,6 +253,33 @@ def test_msm_persistent_accumulate_logic(hostemu, c, group):
         assert ec.from_jac(F, ec.unpack_points(c, group, out, ncoords=3)[0]) == exp, (c.name, group, cw, pre, threads)
 
 
+@pytest.mark.parametrize("c,group", [(CURVES["bn254"], 2), (CURVES["bls12-381"], 1), (CURVES["bls12-377"], 2), (CURVES["bw6-761"], 1)],
+                         ids=lambda v: getattr(v, "name", str(v)))
+def test_msm_shared_memory_accumulator_logic(hostemu, c, group):
+    """opt-in GB200_MSM_SMEM_ACC: the XYZZ accumulator of a task kept in strided shared-memory words (SmemXYZZ) -
+    same edge cases as test_msm_logic (infinity base, equal points -> doubling, P and -P -> cancellation, zero / r-1
+    scalars); the neighbouring threads' words must stay untouched"""
+    rng = random.Random(50 + group)
+    F, base = pick_base(c, group, rng)
+    n = 37
+    pts = [ec.scalar_mul(F, rng.randrange(1, 1 << 40), base) for _ in range(n)]
+    pts[3] = ec.INF
+    pts[5] = pts[4]
+    pts[7] = ec.affine_neg(F, pts[6])
+    sc = [rng.randrange(c.r) for _ in range(n)]
+    sc[0], sc[1], sc[2] = 0, c.r - 1, 1
+    sc[4] = sc[5]
+    sc[6] = sc[7] = 12345
+    exp = ec.msm_naive(F, pts, sc)
+    PA, SA = ec.pack_points(c, group, pts), ff.pack_elements(sc, c.r, c.fr_limbs)
+    for (cw, pre, tl, ch) in ((4, 0, 3, 4), (7, 1, 2, 16)):
+        if pre and c.fp_limbs > 6:
+            continue
+        out = np.zeros(3 * F.degree * c.fp_limbs, dtype=np.uint64)
+        assert hostemu.emu_msm_smem(c.curve_id, group, P(PA), P(SA), n, cw, pre, tl, ch, P(out)) == 0
+        assert ec.from_jac(F, ec.unpack_points(c, group, out, ncoords=3)[0]) == exp, (c.name, group, cw, pre)
+
+
 @pytest.mark.parametrize("c", ALL, ids=lambda c: c.name)
 def test_ntt_logic(hostemu, c):
     rng = random.Random(4)

@@ -611,3 +611,21 @@ def test_ntt_register_rounds(gpu, monkeypatch, cname):
                     got = d.ntt(x.copy(), inverse=inv, decimation=dec, on_coset=cos)
                     assert np.array_equal(got, want), (cname, tile, logn, inv, dec, cos)
         d.free()
+
+
+@experiment
+@pytest.mark.xfail(strict=False, reason="opt-in experiment written after this round's GPU budget was spent; per-thread logic "
+                   "pinned by tests/test_emulation.py::test_msm_shared_memory_accumulator_logic")
+@pytest.mark.parametrize("cname,group", [("bn254", 2), ("bls12-381", 1), ("bls12-381", 2), ("bw6-761", 1), ("bn254", 1)])
+def test_msm_shared_memory_accumulator(gpu, monkeypatch, cname, group):
+    """opt-in GB200_MSM_SMEM_ACC: XYZZ accumulators in shared memory (more resident warps for the wide fields); known-dlog
+    oracle, uniform and skewed scalars, precomputed and plain tables"""
+    from util import known_dlog_instance
+    c = CURVES[cname]
+    monkeypatch.setenv("GB200_MSM_SMEM_ACC", "1")
+    for n, skew in ((300, False), (9000, False), (9000, True)):
+        _, _, pts, sc, expected = known_dlog_instance(c, group, n, seed=91 + group, skew=skew)
+        for precomp in (True, False):
+            t = gpu.Table(c.curve_id, group, pts, precomp=precomp)
+            assert jac_to_affine(c, group, t.msm(sc)) == expected, (n, skew, precomp)
+            t.free()

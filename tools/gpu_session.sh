@@ -46,6 +46,12 @@ for cfg in "bn254 1 20" "bn254 2 20" "bls12-381 1 20" "bw6-761 1 18"; do
   set -- $cfg
   timeout 600 python tools/sweep_msm.py $1 $2 $3 --set GB200_MSM_PERSISTENT=0,1 >> $OUT/sweep_persistent.jsonl 2>> $OUT/session.err
 done
+# accumulators in shared memory (more resident warps for the wide fields: BN254 G2 96 instead of 144 registers, BLS12-381
+# G1 96 instead of 126)
+for cfg in "bn254 2 20" "bls12-381 1 20" "bls12-381 2 18" "bw6-761 1 18"; do
+  set -- $cfg
+  timeout 600 python tools/sweep_msm.py $1 $2 $3 --set GB200_MSM_SMEM_ACC=0,1 >> $OUT/sweep_smem_acc.jsonl 2>> $OUT/session.err
+done
 # the PLONK config's MSM (2^22 points, BLS12-381): ten of these per proof
 timeout 900 python tools/sweep_msm.py bls12-381 1 22 --reps 3 --set GB200_MSM_WINDOW=16,18,20,22 > $OUT/sweep_bls381_2p22_window.jsonl 2>> $OUT/session.err
 timeout 600 python tools/sweep_msm.py bn254 1 20 --set GB200_MSM_HYBRID=0,12,25,38,50,62 > $OUT/sweep_bn254_hybrid.jsonl 2>> $OUT/session.err
