@@ -123,7 +123,9 @@ int32_t msm_on_stream(DeviceCtx* ctx, b200_table_s* t, size_t off, size_t n, con
   CK(ws_buf.alloc(ws_bytes, ctx->stream));
   void* ws = ws_buf.p;
   // opt-in: persistent accumulate (msm.cuh 4c); not combined with the FP64 / hybrid kernels
-  const int persistent = (env_int("GB200_MSM_PERSISTENT", 0) > 0 && !t->fmt52 && t->hybrid52_of_16 == 0) ? 1 : 0;
+  // (2 = persistent grid AND accumulators in shared memory)
+  int persistent = (!t->fmt52 && t->hybrid52_of_16 == 0) ? env_int("GB200_MSM_PERSISTENT", 0) : 0;
+  if (persistent < 0 || persistent > 2) persistent = 0;
   // opt-in: accumulator in shared memory (curve.cuh SmemXYZZ); the persistent kernel takes precedence
   const int smem_acc = (env_int("GB200_MSM_SMEM_ACC", 0) > 0 && !persistent && !t->fmt52 && t->hybrid52_of_16 == 0) ? 1 : 0;
   MsmHybrid hy{t->d_points52, t->hybrid52_of_16, ctx->aux_stream, ctx->aux_fork_ev, ctx->aux_join_ev, ba_levels, persistent, smem_acc};

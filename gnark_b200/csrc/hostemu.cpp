@@ -108,11 +108,18 @@ int msm_emu(const void* points_, const void* scalars_, uint32_t n, int c, int pr
     const uint32_t G = (uint32_t)persistent_threads;
     for (uint32_t g = 0; g < G; g++) {
       uint32_t k = 0;
-      msm_accumulate_persistent<F>(pl, table.data(), svals.data(), off.data(), task_off.data(), partial.data(), [&]() {
+      auto next = [&]() {
         const uint64_t t = (uint64_t)g + (uint64_t)(k++) * G;
         if (t < ntasks) written[t]++;
         return (uint32_t)(t < ntasks ? t : ntasks + g);
-      });
+      };
+      if (smem_acc) {   // GB200_MSM_PERSISTENT=2: the same loop with the accumulator in (emulated) shared memory
+        std::vector<uint32_t> sm((size_t)4 * (sizeof(F) / 4) * 2, 0);
+        MsmSmemAcc<F> acc{SmemXYZZ<F>{sm.data() + 1, 2}};
+        msm_accumulate_persistent<F>(pl, table.data(), svals.data(), off.data(), task_off.data(), partial.data(), next, acc);
+      } else {
+        msm_accumulate_persistent<F>(pl, table.data(), svals.data(), off.data(), task_off.data(), partial.data(), next);
+      }
     }
     for (uint32_t t = 0; t < ntasks; t++)
       if (written[t] != 1) return -2;             // every task exactly once
@@ -615,18 +622,21 @@ int emu_msm_smem(int curve, int group, const void* points, const void* scalars, 
 }
 
 // GB200_MSM_PERSISTENT: the accumulate stage through msm_accumulate_persistent with `threads` simulated threads
+// (threads < 0: |threads| simulated threads with the accumulator in emulated shared memory, GB200_MSM_PERSISTENT=2)
 int emu_msm_persistent(int curve, int group, const void* points, const void* scalars, uint32_t n, int c, int precomp,
                        uint32_t task_len, uint32_t chunk, int threads, void* out_jac) {
-  if (threads < 1) return -1;
+  if (threads == 0) return -1;
+  const bool sm = threads < 0;
+  if (sm) threads = -threads;
   switch (curve * 2 + (group - 1)) {
-    case 0: return msm_emu<bn254_fr, bn254_fp>(points, scalars, n, c, precomp, task_len, chunk, out_jac, threads);
-    case 1: return msm_emu<bn254_fr, bn254_fp2>(points, scalars, n, c, precomp, task_len, chunk, out_jac, threads);
-    case 2: return msm_emu<bls12_381_fr, bls12_381_fp>(points, scalars, n, c, precomp, task_len, chunk, out_jac, threads);
-    case 3: return msm_emu<bls12_381_fr, bls12_381_fp2>(points, scalars, n, c, precomp, task_len, chunk, out_jac, threads);
-    case 4: return msm_emu<bls12_377_fr, bls12_377_fp>(points, scalars, n, c, precomp, task_len, chunk, out_jac, threads);
-    case 5: return msm_emu<bls12_377_fr, bls12_377_fp2>(points, scalars, n, c, precomp, task_len, chunk, out_jac, threads);
+    case 0: return msm_emu<bn254_fr, bn254_fp>(points, scalars, n, c, precomp, task_len, chunk, out_jac, threads, sm);
+    case 1: return msm_emu<bn254_fr, bn254_fp2>(points, scalars, n, c, precomp, task_len, chunk, out_jac, threads, sm);
+    case 2: return msm_emu<bls12_381_fr, bls12_381_fp>(points, scalars, n, c, precomp, task_len, chunk, out_jac, threads, sm);
+    case 3: return msm_emu<bls12_381_fr, bls12_381_fp2>(points, scalars, n, c, precomp, task_len, chunk, out_jac, threads, sm);
+    case 4: return msm_emu<bls12_377_fr, bls12_377_fp>(points, scalars, n, c, precomp, task_len, chunk, out_jac, threads, sm);
+    case 5: return msm_emu<bls12_377_fr, bls12_377_fp2>(points, scalars, n, c, precomp, task_len, chunk, out_jac, threads, sm);
     case 6:
-    case 7: return msm_emu<bw6_761_fr, bw6_761_fp>(points, scalars, n, c, precomp, task_len, chunk, out_jac, threads);
+    case 7: return msm_emu<bw6_761_fr, bw6_761_fp>(points, scalars, n, c, precomp, task_len, chunk, out_jac, threads, sm);
   }
   return -1;
 }

@@ -192,18 +192,34 @@ HD bool msm_task_bounds(const MsmPlan& pl, const uint32_t* off, const uint32_t* 
 // the next one.  A lane whose task was short goes straight on to another task instead of idling until the longest
 // task of its warp ends (every bucket's last task is a short one), and the last wave of a task-sized grid, which
 // fills only part of the machine, disappears.  partial[] is indexed by task as before, so nothing downstream changes.
-template <class F, class NEXT>
+// where a thread keeps the accumulator of its current task: registers (default) or shared memory (SmemXYZZ, curve.cuh)
+template <class F>
+struct MsmRegAcc {
+  XYZZ<F> v;
+  HD void reset() { v = XYZZ<F>::inf(); }
+  HD void add_mixed(const Affine<F>& a) { v.add_mixed(a); }
+  HD XYZZ<F> get() const { return v; }
+};
+template <class F>
+struct MsmSmemAcc {
+  SmemXYZZ<F> s;
+  HD void reset() { s.set(XYZZ<F>::inf()); }
+  HD void add_mixed(const Affine<F>& a) { s.add_mixed(a); }
+  HD XYZZ<F> get() const { return s.get(); }
+};
+
+template <class F, class NEXT, class ACC = MsmRegAcc<F>>
 HD void msm_accumulate_persistent(const MsmPlan& pl, const Affine<F>* table, const uint32_t* vals, const uint32_t* off,
-                                  const uint32_t* task_off, XYZZ<F>* partial, NEXT next_task) {
-  XYZZ<F> acc = XYZZ<F>::inf();
+                                  const uint32_t* task_off, XYZZ<F>* partial, NEXT next_task, ACC acc = ACC()) {
+  acc.reset();
   uint32_t e = 0, end = 0, t = 0;
   bool have = false;
   for (;;) {
     if (e == end) {
-      if (have) partial[t] = acc;
+      if (have) partial[t] = acc.get();
       t = next_task();
       if (!msm_task_bounds(pl, off, task_off, t, e, end)) return;   // past the last task
-      acc = XYZZ<F>::inf();
+      acc.reset();
       have = true;
       if (e == end) continue;                                        // an empty task stores infinity
     }

@@ -111,6 +111,17 @@ __global__ void GB200_ACC_BOUNDS k_msm_accumulate_persistent(MsmPlan pl, const A
   msm_accumulate_persistent<F>(pl, table, svals, off, task_off, partial, [counter]() { return atomicAdd(counter, 1u); });
 }
 
+// both opt-ins together: persistent grid, accumulators in shared memory
+template <class F>
+__global__ void __launch_bounds__(128, GB200_SMEM_ACC_MIN_BLOCKS)
+k_msm_accumulate_persistent_smem(MsmPlan pl, const Affine<F>* __restrict__ table, const uint32_t* __restrict__ svals,
+                                 const uint32_t* __restrict__ off, const uint32_t* __restrict__ task_off,
+                                 XYZZ<F>* __restrict__ partial, uint32_t* __restrict__ counter) {
+  extern __shared__ __align__(16) uint32_t acc_sm[];
+  MsmSmemAcc<F> acc{SmemXYZZ<F>{acc_sm + threadIdx.x, blockDim.x}};
+  msm_accumulate_persistent<F>(pl, table, svals, off, task_off, partial, [counter]() { return atomicAdd(counter, 1u); }, acc);
+}
+
 // FP64-pipe twin of k_msm_accumulate (field52.cuh / curve52.cuh): same task decomposition, table
 // entries are Affine52 (Montgomery R52, doubles), the accumulator lives in 52-bit limbs
 template <class F, class P52>
@@ -431,7 +442,7 @@ template <class F>
 cudaError_t msm_launch_accumulate(cudaStream_t stream, const MsmPlan& pl, const MsmLayout<F>& L, const Affine<F>* table,
                                   const uint32_t* vals, const uint32_t* off, const uint32_t* task_off, XYZZ<F>* partial,
                                   uint32_t* counter) {
-  if (pl.persistent) {
+  if (pl.persistent == 1) {
     int dev = 0, sms = 0, per_sm = 0;
     GB_CUDA_TRY(cudaGetDevice(&dev));
     GB_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -442,6 +453,22 @@ cudaError_t msm_launch_accumulate(cudaStream_t stream, const MsmPlan& pl, const 
     if (grid > need) grid = need;
     GB_CUDA_TRY(cudaMemsetAsync(counter, 0, 4, stream));
     k_msm_accumulate_persistent<F><<<(unsigned)grid, 128, 0, stream>>>(pl, table, vals, off, task_off, partial, counter);
+  } else if (pl.persistent == 2) {
+    // persistent grid + accumulators in shared memory
+    const size_t smem = 4 * sizeof(F) * 128;
+    int dev = 0, sms = 0, per_sm = 0;
+    GB_CUDA_TRY(cudaGetDevice(&dev));
+    GB_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    GB_CUDA_TRY(cudaFuncSetAttribute(k_msm_accumulate_persistent_smem<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GB_CUDA_TRY(cudaFuncSetAttribute(k_msm_accumulate_persistent_smem<F>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                     (int)cudaSharedmemCarveoutMaxShared));
+    GB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_msm_accumulate_persistent_smem<F>, 128, smem));
+    if (per_sm < 1) per_sm = 1;
+    size_t grid = (size_t)sms * per_sm;
+    const size_t need = (L.max_tasks + 127) / 128;
+    if (grid > need) grid = need;
+    GB_CUDA_TRY(cudaMemsetAsync(counter, 0, 4, stream));
+    k_msm_accumulate_persistent_smem<F><<<(unsigned)grid, 128, smem, stream>>>(pl, table, vals, off, task_off, partial, counter);
   } else if (pl.smem_acc) {
     const size_t smem = 4 * sizeof(F) * 128;
     GB_CUDA_TRY(cudaFuncSetAttribute(k_msm_accumulate_smem<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -247,7 +247,8 @@ def test_msm_persistent_accumulate_logic(hostemu, c, group):
         sc[i] = 3                      # 25 entries in one bucket of the lowest window
     exp = ec.msm_naive(F, pts, sc)
     PA, SA = ec.pack_points(c, group, pts), ff.pack_elements(sc, c.r, c.fr_limbs)
-    for (cw, pre, tl, ch, threads) in ((4, 0, 3, 4, 1), (4, 0, 3, 4, 7), (7, 1, 2, 16, 64), (5, 1, 4, 8, 5000)):
+    # negative thread counts: the same loop with the accumulator in emulated shared memory (GB200_MSM_PERSISTENT=2)
+    for (cw, pre, tl, ch, threads) in ((4, 0, 3, 4, 1), (4, 0, 3, 4, 7), (7, 1, 2, 16, 64), (5, 1, 4, 8, 5000), (4, 0, 3, 4, -5)):
         out = np.zeros(3 * F.degree * c.fp_limbs, dtype=np.uint64)
         assert hostemu.emu_msm_persistent(c.curve_id, group, P(PA), P(SA), n, cw, pre, tl, ch, threads, P(out)) == 0
         assert ec.from_jac(F, ec.unpack_points(c, group, out, ncoords=3)[0]) == exp, (c.name, group, cw, pre, threads)

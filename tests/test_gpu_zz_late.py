@@ -574,12 +574,13 @@ print("EQUAL" if np.array_equal(outs[0], outs[1]) else "DIFFERENT")
 @pytest.mark.xfail(strict=False, reason="opt-in experiment written after this round's GPU budget was spent; per-thread logic "
                    "pinned by tests/test_emulation.py::test_msm_persistent_accumulate_logic")
 @pytest.mark.parametrize("cname,group", [("bn254", 1), ("bn254", 2), ("bls12-381", 1), ("bw6-761", 1)])
-def test_msm_persistent_accumulate(gpu, monkeypatch, cname, group):
+@pytest.mark.parametrize("mode", ["1", "2"])
+def test_msm_persistent_accumulate(gpu, monkeypatch, cname, group, mode):
     """opt-in GB200_MSM_PERSISTENT: the accumulate stage on a grid sized to the SMs, tasks from an atomic counter;
     known-dlog oracle, uniform and skewed scalars, precomputed and plain tables, sizes around the grid size"""
     from util import known_dlog_instance
     c = CURVES[cname]
-    monkeypatch.setenv("GB200_MSM_PERSISTENT", "1")
+    monkeypatch.setenv("GB200_MSM_PERSISTENT", mode)       # 2 = persistent grid + accumulators in shared memory
     for n, skew in ((300, False), (9000, False), (9000, True), (150000 if c.fp_limbs <= 6 else 20000, False)):
         _, _, pts, sc, expected = known_dlog_instance(c, group, n, seed=77 + group, skew=skew)
         for precomp in (True, False):

@@ -44,7 +44,7 @@ timeout 600 python tools/sweep_msm.py bn254 1 20 --set GB200_MSM_WINDOW=16,17,18
 # the lanes idling behind the short last task of every bucket
 for cfg in "bn254 1 20" "bn254 2 20" "bls12-381 1 20" "bw6-761 1 18"; do
   set -- $cfg
-  timeout 600 python tools/sweep_msm.py $1 $2 $3 --set GB200_MSM_PERSISTENT=0,1 >> $OUT/sweep_persistent.jsonl 2>> $OUT/session.err
+  timeout 600 python tools/sweep_msm.py $1 $2 $3 --set GB200_MSM_PERSISTENT=0,1,2 >> $OUT/sweep_persistent.jsonl 2>> $OUT/session.err
 done
 # accumulators in shared memory (more resident warps for the wide fields: BN254 G2 96 instead of 144 registers, BLS12-381
 # G1 96 instead of 126)
