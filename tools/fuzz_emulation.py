@@ -5,7 +5,8 @@ the A/B arithmetic build) against big-int arithmetic and the C++ oracle - longer
    python tools/fuzz_emulation.py field 60000      # mul / sqr / mul_sub / Fp2 mul, sqr on every field, special values mixed in
    python tools/fuzz_emulation.py msm 60           # small MSMs with equal points, P and -P, infinities, special scalars
 
-Round 1: 960 k products + 480 k single-reduction mul_sub + Fp2 operations and 780 MSMs, no mismatch."""
+Round 1: 960 k products + 480 k single-reduction mul_sub + Fp2 operations and 2 080 MSMs (default build, A/B build, and the
+persistent / shared-memory-accumulator variants of the accumulate stage), no mismatch."""
 import sys
 MODE = sys.argv[1] if len(sys.argv) > 1 else "field"
 sys.argv = [sys.argv[0]] + sys.argv[2:]
@@ -87,5 +88,13 @@ else:
             ga=ec.from_jac(F,ec.unpack_points(c,group,out,ncoords=3)[0])
             runs+=1
             if rc!=0 or ga!=wa: bad+=1; print('BAD',name,c.name,group,n,cw,pre)
+            if name=='default':
+              # the run-time accumulate variants (GB200_MSM_PERSISTENT=1/2, GB200_MSM_SMEM_ACC) on the same input
+              for tag,call in (('persistent',lambda o: lib.emu_msm_persistent(c.curve_id,group,P(pts),P(SA),n,cw,pre,3,8,rng.choice([1,3,50]),P(o))),
+                               ('persistent_smem',lambda o: lib.emu_msm_persistent(c.curve_id,group,P(pts),P(SA),n,cw,pre,3,8,-rng.choice([1,4]),P(o))),
+                               ('smem',lambda o: lib.emu_msm_smem(c.curve_id,group,P(pts),P(SA),n,cw,pre,3,8,P(o)))):
+                out=np.zeros(3*deg*c.fp_limbs,dtype=np.uint64)
+                rc=call(out); runs+=1
+                if rc!=0 or ec.from_jac(F,ec.unpack_points(c,group,out,ncoords=3)[0])!=wa: bad+=1; print('BAD',tag,c.name,group,n,cw,pre,rc)
     print('runs',runs,'bad',bad,round(time.time()-t0,1),'s')
 
