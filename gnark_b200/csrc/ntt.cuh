@@ -38,7 +38,18 @@ struct NttPlan {
   NttPass pass[NTT_MAX_PASSES];  // in increasing bit order (DIT runs them 0.., DIF runs them reversed)
 };
 
+// passes a tile size needs for 2^logn points (first pass: tile_log stages, then <= tile_log - 2 stages per pass)
+inline int ntt_passes_needed(int logn, int tile_log) {
+  if (logn <= tile_log) return 1;
+  const int smax = tile_log - 2;
+  return 1 + (logn - tile_log + smax - 1) / smax;
+}
+
 inline NttPlan ntt_make_plan(int logn, int tile_log = NTT_MAX_TILE_LOG) {
+  // a tile too small for the size would need more than NTT_MAX_PASSES passes: use the smallest tile that fits
+  // (found by the randomised emulation soak, tools/fuzz_emulation.py: tile 2^3 at 2^13 points overran pass[])
+  if (tile_log < 3) tile_log = 3;
+  while (tile_log < NTT_MAX_TILE_LOG && ntt_passes_needed(logn, tile_log) > NTT_MAX_PASSES) tile_log++;
   NttPlan pl;
   pl.logn = logn;
   pl.npasses = 0;

@@ -4,9 +4,13 @@ the A/B arithmetic build) against big-int arithmetic and the C++ oracle - longer
 
    python tools/fuzz_emulation.py field 60000      # mul / sqr / mul_sub / Fp2 mul, sqr on every field, special values mixed in
    python tools/fuzz_emulation.py msm 60           # small MSMs with equal points, P and -P, infinities, special scalars
+   python tools/fuzz_emulation.py ba 300           # batched-affine levels on adversarial inputs (few distinct points, +-P)
+   python tools/fuzz_emulation.py ntt 400          # NTT pass walks, default and register rounds, random sizes / tiles / modes
 
 Round 1: 960 k products + 480 k single-reduction mul_sub + Fp2 operations and 2 080 MSMs (default build, A/B build, and the
-persistent / shared-memory-accumulator variants of the accumulate stage), no mismatch."""
+persistent / shared-memory-accumulator variants of the accumulate stage), 1 920 batched-affine MSMs and 1 600 NTTs: no
+mismatch.  (The NTT soak did find a bound that was missing in ntt_make_plan for tiles of 2^3 at 2^13 points - emulation
+only, device tiles are 2^6 and up - now guarded.)"""
 import sys
 MODE = sys.argv[1] if len(sys.argv) > 1 else "field"
 sys.argv = [sys.argv[0]] + sys.argv[2:]
@@ -53,7 +57,7 @@ if MODE == "field":
             if tuple(ff.unpack_elements(O,c.p,L))!=F2.sqr(a): bad+=1; print('FP2SQR',name,c.name)
     print('done',N,'bad',bad,round(time.time()-t0,1),'s')
 
-else:
+elif MODE == "msm":
     import sys, ctypes, random, time
     import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     import numpy as np
@@ -98,3 +102,53 @@ else:
                 if rc!=0 or ec.from_jac(F,ec.unpack_points(c,group,out,ncoords=3)[0])!=wa: bad+=1; print('BAD',tag,c.name,group,n,cw,pre,rc)
     print('runs',runs,'bad',bad,round(time.time()-t0,1),'s')
 
+
+if MODE in ("ba", "ntt"):
+    # appended modes:  ba <reps>  - batched-affine levels (GB200_MSM_BATCH_AFFINE) on adversarial small MSMs;
+    #                  ntt <reps> - NTT pass walks (default and register rounds) at random sizes / tile sizes / modes
+    import ctypes, os, random, time
+    import numpy as np
+    ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, ROOT)
+    from oracle import corelib, derive, ec, ff
+    from oracle.params import CURVES
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    lib = ctypes.CDLL(ROOT + "/tests/_build/libgb200_hostemu.so")
+    REPS = int(sys.argv[1]) if len(sys.argv) > 1 else 20
+    rng = random.Random(4242)
+    t0 = time.time(); bad = runs = 0
+    if MODE == "ba":
+        for c in CURVES.values():
+            for group in (1, 2):
+                F = ff.base_field(c, group); base = derive.subgroup_point(c, group); deg = F.degree
+                pool = corelib.fixed_base(c, group, ec.pack_points(c, group, [base]),
+                                          ff.pack_elements([rng.randrange(1, c.r) for _ in range(16)], c.r, c.fr_limbs)).reshape(16, -1)
+                for rep in range(REPS if c.fp_limbs <= 6 else max(1, REPS // 5)):
+                    n = rng.choice([3, 17, 64, 90])
+                    idx = [rng.randrange(rng.choice([2, 4, 16])) for _ in range(n)]          # few distinct points: P + P, 2P + 2P ...
+                    pts = np.ascontiguousarray(pool[idx].copy())
+                    if rng.random() < 0.3: pts[rng.randrange(n)] = 0
+                    small = [rng.randrange(c.r) for _ in range(3)]
+                    sc = [rng.choice(small + [0, 1, c.r - 1, (c.r - small[0]) % c.r]) if rng.random() < 0.7 else rng.randrange(c.r) for _ in range(n)]
+                    SA = ff.pack_elements(sc, c.r, c.fr_limbs)
+                    want = ec.from_jac(F, ec.unpack_points(c, group, corelib.msm(c, group, pts, SA, c=4), ncoords=3)[0])
+                    cw = rng.choice([3, 4, 6]); levels = rng.choice([1, 2, 3, 5, 12]); tl = rng.choice([2, 4, 64]); ch = rng.choice([2, 8])
+                    out = np.zeros(3 * deg * c.fp_limbs, dtype=np.uint64)
+                    rc = lib.emu_msm_ba(c.curve_id, group, P(pts), P(SA), n, cw, 0, tl, ch, levels, P(out)); runs += 1
+                    if rc != 0 or ec.from_jac(F, ec.unpack_points(c, group, out, ncoords=3)[0]) != want:
+                        bad += 1; print("BAD ba", c.name, group, n, cw, levels, tl, ch, rc)
+    else:
+        for c in CURVES.values():
+            for rep in range(REPS):
+                logn = rng.randrange(0, 14); tile = rng.randrange(3, 12); r8 = rng.randrange(2)
+                inv, dec, cos = rng.randrange(2), rng.randrange(2), rng.randrange(2)
+                n = 1 << logn
+                A = ff.pack_elements([rng.randrange(c.r) for _ in range(n)], c.r, c.fr_limbs)
+                want = corelib.ntt(c, A.copy(), logn, bool(inv), dec, bool(cos))
+                lib.emu_ntt_set_tile_log(max(2, tile)); lib.emu_ntt_set_radix8(r8)
+                B = A.copy()
+                rc = lib.emu_ntt(c.curve_id, P(B), logn, inv, dec, cos, None, None); runs += 1
+                if rc != 0 or not np.array_equal(B, want):
+                    bad += 1; print("BAD ntt", c.name, logn, tile, r8, inv, dec, cos, rc)
+        lib.emu_ntt_set_tile_log(11); lib.emu_ntt_set_radix8(0)
+    print("runs", runs, "bad", bad, round(time.time() - t0, 1), "s")
