@@ -6,10 +6,12 @@ the A/B arithmetic build) against big-int arithmetic and the C++ oracle - longer
    python tools/fuzz_emulation.py msm 60           # small MSMs with equal points, P and -P, infinities, special scalars
    python tools/fuzz_emulation.py ba 300           # batched-affine levels on adversarial inputs (few distinct points, +-P)
    python tools/fuzz_emulation.py ntt 400          # NTT pass walks, default and register rounds, random sizes / tiles / modes
+   python tools/fuzz_emulation.py fixed 25         # fixed-base batch templates against the C++ oracle (slow: emulated tables)
+   python tools/fuzz_emulation.py pipes 12         # FP64-pipe accumulate and the hybrid split
 
 Round 1: 960 k products + 480 k single-reduction mul_sub + Fp2 operations and 2 080 MSMs (default build, A/B build, and the
-persistent / shared-memory-accumulator variants of the accumulate stage), 1 920 batched-affine MSMs and 1 600 NTTs: no
-mismatch.  (The NTT soak did find a bound that was missing in ntt_make_plan for tiles of 2^3 at 2^13 points - emulation
+persistent / shared-memory-accumulator variants of the accumulate stage), 1 920 batched-affine MSMs, 1 600 NTTs, 156 fixed-base batches, 78 FP64-pipe / hybrid MSMs:
+no mismatch.  (The NTT soak did find a bound that was missing in ntt_make_plan for tiles of 2^3 at 2^13 points - emulation
 only, device tiles are 2^6 and up - now guarded.)"""
 import sys
 MODE = sys.argv[1] if len(sys.argv) > 1 else "field"
@@ -151,4 +153,53 @@ if MODE in ("ba", "ntt"):
                 if rc != 0 or not np.array_equal(B, want):
                     bad += 1; print("BAD ntt", c.name, logn, tile, r8, inv, dec, cos, rc)
         lib.emu_ntt_set_tile_log(11); lib.emu_ntt_set_radix8(0)
+    print("runs", runs, "bad", bad, round(time.time() - t0, 1), "s")
+
+if MODE in ("fixed", "pipes"):
+    # fixed <reps> - b200_fixed_base_batch's templates against the C++ oracle's fixed-base batch (random bases, window sizes,
+    #                batch sizes around the 16-point inversion chunks, special scalars);
+    # pipes <reps> - the FP64-pipe accumulate (emu_msm52) and the hybrid split (emu_msm_hybrid) on random precomputed-table MSMs
+    import ctypes, os, random, time
+    import numpy as np
+    ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, ROOT)
+    from oracle import corelib, derive, ec, ff
+    from oracle.params import CURVES
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    lib = ctypes.CDLL(ROOT + "/tests/_build/libgb200_hostemu.so")
+    REPS = int(sys.argv[1]) if len(sys.argv) > 1 else 10
+    rng = random.Random(99)
+    t0 = time.time(); bad = runs = 0
+    for c in CURVES.values():
+        for group in ((1, 2) if MODE == "fixed" else (1,)):
+            if group == 2 and c.fp2_nonresidue is None:
+                continue
+            F = ff.base_field(c, group); gen = derive.subgroup_point(c, group); deg = F.degree
+            for rep in range(REPS if c.fp_limbs <= 6 else max(1, REPS // 4)):
+                if MODE == "fixed":
+                    base = ec.scalar_mul(F, rng.randrange(1, c.r), gen)
+                    n = rng.choice([1, 15, 16, 17, 40])
+                    ks = [rng.choice([0, 1, 2, c.r - 1, c.r - 2, (1 << (c.r.bit_length() - 1)) - 1]) if rng.random() < 0.3 else rng.randrange(c.r) for _ in range(n)]
+                    KS = ff.pack_elements(ks, c.r, c.fr_limbs); BA = ec.pack_points(c, group, [base])
+                    want = corelib.fixed_base(c, group, BA, KS)
+                    out = np.zeros((n, 2 * deg * c.fp_limbs), dtype=np.uint64)
+                    rc = lib.emu_fixed_base(c.curve_id, group, P(BA), P(KS), n, rng.choice([2, 3, 5, 8, 11]), P(out)); runs += 1
+                    if rc != 0 or not np.array_equal(out.reshape(-1), np.asarray(want).reshape(-1)):
+                        bad += 1; print("BAD fixed", c.name, group, n, rc)
+                else:
+                    n = rng.choice([5, 37, 70])
+                    pts = corelib.fixed_base(c, 1, ec.pack_points(c, 1, [gen]), ff.pack_elements([rng.randrange(1, c.r) for _ in range(n)], c.r, c.fr_limbs))
+                    pts = np.ascontiguousarray(np.asarray(pts).reshape(n, -1))
+                    if n > 6: pts[3] = 0; pts[5] = pts[4]
+                    sc = [rng.choice([0, 1, c.r - 1]) if rng.random() < 0.2 else rng.randrange(c.r) for _ in range(n)]
+                    if n > 6: sc[4] = sc[5]
+                    SA = ff.pack_elements(sc, c.r, c.fr_limbs)
+                    want = ec.from_jac(F, ec.unpack_points(c, 1, corelib.msm(c, 1, pts, SA, c=4), ncoords=3)[0])
+                    cw = rng.choice([4, 7]) if c.fp_limbs > 6 else rng.choice([4, 7, 10])
+                    for tag, call in (("msm52", lambda o: lib.emu_msm52(c.curve_id, P(pts), P(SA), n, cw, rng.choice([2, 5, 64]), rng.choice([4, 16]), P(o))),
+                                      ("hybrid", lambda o: lib.emu_msm_hybrid(c.curve_id, P(pts), P(SA), n, cw, rng.choice([2, 5]), rng.choice([4, 16]), rng.randrange(1, 16), P(o)))):
+                        out = np.zeros(3 * c.fp_limbs, dtype=np.uint64)
+                        rc = call(out); runs += 1
+                        if rc != 0 or ec.from_jac(F, ec.unpack_points(c, 1, out, ncoords=3)[0]) != want:
+                            bad += 1; print("BAD", tag, c.name, n, cw, rc)
     print("runs", runs, "bad", bad, round(time.time() - t0, 1), "s")
