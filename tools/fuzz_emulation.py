@@ -8,10 +8,11 @@ the A/B arithmetic build) against big-int arithmetic and the C++ oracle - longer
    python tools/fuzz_emulation.py ntt 400          # NTT pass walks, default and register rounds, random sizes / tiles / modes
    python tools/fuzz_emulation.py fixed 25         # fixed-base batch templates against the C++ oracle (slow: emulated tables)
    python tools/fuzz_emulation.py pipes 12         # FP64-pipe accumulate and the hybrid split
+   python tools/fuzz_emulation.py plonk 40         # C++ PLONK orchestration (mocked kernels) on random instances + pairing Verify
 
 Round 1: 960 k products + 480 k single-reduction mul_sub + Fp2 operations and 2 080 MSMs (default build, A/B build, and the
-persistent / shared-memory-accumulator variants of the accumulate stage), 1 920 batched-affine MSMs, 1 600 NTTs, 156 fixed-base batches, 78 FP64-pipe / hybrid MSMs:
-no mismatch.  (The NTT soak did find a bound that was missing in ntt_make_plan for tiles of 2^3 at 2^13 points - emulation
+persistent / shared-memory-accumulator variants of the accumulate stage), 1 920 batched-affine MSMs, 1 600 NTTs, 156 fixed-base batches, 78 FP64-pipe / hybrid MSMs,
+40 PLONK proofs: no mismatch.  (The NTT soak did find a bound that was missing in ntt_make_plan for tiles of 2^3 at 2^13 points - emulation
 only, device tiles are 2^6 and up - now guarded.)"""
 import sys
 MODE = sys.argv[1] if len(sys.argv) > 1 else "field"
@@ -203,3 +204,65 @@ if MODE in ("fixed", "pipes"):
                         if rc != 0 or ec.from_jac(F, ec.unpack_points(c, 1, out, ncoords=3)[0]) != want:
                             bad += 1; print("BAD", tag, c.name, n, cw, rc)
     print("runs", runs, "bad", bad, round(time.time() - t0, 1), "s")
+
+if MODE == "plonk":
+    # plonk <reps> - the C++ PLONK orchestration on the mocked C ABI, random instances (sizes, BSB22 gates, cache on/off, two
+    # curves) against the oracle prover, every third one also through the pairing verifier
+    import sys, os, ctypes, random, time
+    ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT); sys.path.insert(0, ROOT + '/tests')
+    import numpy as np
+    from gnark_b200 import lib as b200
+    from oracle import corelib, ec, ff, plonk_prover as pp
+    from oracle.params import CURVES
+    from util import jac_to_affine
+    m = ctypes.CDLL(ROOT + '/tests/_build/libgb200_plonkmock.so')
+    vp, i32 = ctypes.c_void_p, ctypes.c_int32
+    m.b200_plonk_pk_load.argtypes = [i32, i32, ctypes.POINTER(b200.PlonkPkDesc), ctypes.POINTER(vp)]
+    m.b200_plonk_pk_free.argtypes = [vp]
+    m.b200_plonk_prove.argtypes = [vp, vp, vp, vp, ctypes.POINTER(b200.PlonkChallenges), vp, vp]
+    m.b200_last_error.restype = ctypes.c_char_p
+    rng = random.Random(2026); bad = 0; t0 = time.time(); runs = 0
+    REPS = int(sys.argv[1])
+    for rep in range(REPS):
+        c = CURVES[rng.choice(["bn254", "bls12-381"])]
+        logn = rng.choice([3, 4, 5, 6]); n = 1 << logn; r, L = c.r, c.fr_limbs
+        ncom = rng.choice([0, 0, 1, 2])
+        inst = pp.random_satisfied_instance(c, n, seed=rng.randrange(1 << 30), n_commit=ncom)
+        circ, l, rr, o = inst[:4]; pi2 = inst[4] if ncom else ()
+        rnd = lambda: rng.randrange(r)
+        ch = pp.Challenges(gamma=rnd(), beta=rnd(), alpha=rnd(), zeta=rnd(), v=rnd(), bl=[rnd(), rnd()], br=[rnd(), rnd()], bo=[rnd(), rnd()], bz=[rnd(), rnd(), rnd()])
+        tau = rnd()
+        want = pp.prove(c, circ, l, rr, o, ch, tau, pi2=pi2) if ncom else pp.prove(c, circ, l, rr, o, ch, tau)
+        pe = lambda v: np.ascontiguousarray(ff.pack_elements(v, r, L)); P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+        srs = np.ascontiguousarray(corelib.fixed_base(c, 1, ec.pack_points(c, 1, [c.g1]), pe([pow(tau, i, r) for i in range(n + 3)])))
+        keep = {k: pe(getattr(circ, k)) for k in ("ql", "qr", "qm", "qo", "qk")}
+        perm = np.ascontiguousarray(np.array(circ.perm, dtype=np.int64))
+        d = b200.PlonkPkDesc(); d.log2n = logn
+        for k, a in keep.items(): setattr(d, k, P(a).value)
+        d.perm, d.srs_canonical = P(perm).value, P(srs).value
+        qcp = [pe(v) for v in circ.qcp]
+        if ncom:
+            qarr = (ctypes.c_void_p * ncom)(*[a.ctypes.data for a in qcp]); d.n_qcp, d.qcp = ncom, ctypes.cast(qarr, ctypes.POINTER(ctypes.c_void_p))
+        os.environ["GB200_PLONK_COSET_CACHE"] = rng.choice(["0", "1"])
+        h = ctypes.c_void_p(0)
+        assert m.b200_plonk_pk_load(0, c.curve_id, ctypes.byref(d), ctypes.byref(h)) == 0, m.b200_last_error()
+        sc = {k: pe(v) for k, v in (("gamma", [ch.gamma]), ("beta", [ch.beta]), ("alpha", [ch.alpha]), ("zeta", [ch.zeta]), ("v", [ch.v]), ("bl", ch.bl), ("br", ch.br), ("bo", ch.bo), ("bz", ch.bz))}
+        cs = b200.PlonkChallenges()
+        for k, a in sc.items(): setattr(cs, k, P(a).value)
+        pts = np.zeros((10, 3 * c.fp_limbs), dtype=np.uint64); vals = np.zeros((7 + ncom, L), dtype=np.uint64); bsb = np.zeros((max(ncom,1), 3 * c.fp_limbs), dtype=np.uint64)
+        L_, R_, O_ = pe(l), pe(rr), pe(o)
+        if ncom:
+            pi2a = [pe(v) for v in pi2]; parr = (ctypes.c_void_p * ncom)(*[a.ctypes.data for a in pi2a])
+            cs.pi2, cs.out_bsb22 = ctypes.cast(parr, ctypes.POINTER(ctypes.c_void_p)), P(bsb).value
+        rc = m.b200_plonk_prove(h, P(L_), P(R_), P(O_), ctypes.byref(cs), P(pts), P(vals)); runs += 1
+        F = ff.Fp(c.p)
+        dl = [want.L, want.R, want.O, want.Z, want.H[0], want.H[1], want.H[2], want.lin, want.batch_opening, want.z_opening]
+        ok = rc == 0 and all(jac_to_affine(c, 1, pts[k]) == ec.scalar_mul(F, dl[k], c.g1) for k in range(10))
+        got = ff.unpack_elements(vals, r, L)
+        ok = ok and got[:6] + got[7:] == want.claimed and got[6] == want.zu
+        if ok and rep % 3 == 0:
+            ok = pp.verify_pairing(c, circ, [jac_to_affine(c, 1, pts[k]) for k in range(10)], got, ch, tau, bsb22_points=[jac_to_affine(c, 1, bsb[j]) for j in range(ncom)])
+        if not ok: bad += 1; print("BAD", c.name, logn, ncom, rc, m.b200_last_error())
+        m.b200_plonk_pk_free(h)
+    print("runs", runs, "bad", bad, round(time.time() - t0, 1), "s")
+
