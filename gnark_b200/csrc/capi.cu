@@ -1,7 +1,12 @@
 // C ABI of libgnark_b200.so (declared in include/gnark_b200.h): runtime, memory,
 // MSM base tables, MSM, NTT, vector ops.  The Groth16 host layer lives in
 // groth16_host.cu.  Requires a CUDA device: there is no CPU fallback.
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include "capi_common.h"
+#include "file_stage.h"
 #include "fixed_base.cuh"
 
 namespace gb200 {
@@ -309,6 +314,66 @@ int32_t b200_table_upload(int32_t dev, int32_t curve, int32_t group, const void*
   CK(cudaStreamSynchronize(ctx->stream));
   *out = t.release();
   return 0;
+  GUARD_END
+}
+
+// Table straight from a file region: the point slices of gnark's ProvingKey dump
+// (backend/groth16/bn254/marshal.go:375-539: G1.A, G1.B, G1.Z, G1.K, G2.B written by unsafe.WriteSlice as raw memory
+// images, i.e. exactly the device table layout) are read chunk by chunk into two pinned slots and copied to the device
+// while the next chunk is being read, then handed to b200_table_upload as a device-resident source.  The Go shim reads
+// the dump's header with gnark-crypto's own decoder and passes the byte offset of each slice's payload; a shard passes
+// the offset of ITS point range, so that no process ever holds the whole key in host memory.
+int32_t b200_table_upload_file(int32_t dev, int32_t curve, int32_t group, const char* path, uint64_t byte_offset, size_t n,
+                               int32_t flags, b200_table_t* out) {
+  GUARD_BEGIN
+  if (!path || !out) return set_error("table_upload_file: null argument");
+  if (flags & B200_TABLE_SRC_ON_DEVICE) return set_error("table_upload_file: the source is a file");
+  GB_DEVICE(ctx, dev); [[maybe_unused]] int32_t rc = 0;
+  const MsmOps* ops = get_msm_ops(curve, group);
+  if (!ops) return set_error("table_upload_file: unsupported curve/group");
+  const size_t bytes = n * ops->affine_bytes;
+  struct Fd { int fd = -1; ~Fd() { if (fd >= 0) close(fd); } } f;
+  f.fd = open(path, O_RDONLY | O_CLOEXEC);
+  if (f.fd < 0) return set_error(std::string("table_upload_file: cannot open ") + path + ": " + strerror(errno));
+  struct stat st;
+  if (fstat(f.fd, &st) != 0) return set_error(std::string("table_upload_file: fstat: ") + strerror(errno));
+  if ((uint64_t)st.st_size < byte_offset || (uint64_t)st.st_size - byte_offset < bytes)
+    return set_error("table_upload_file: [offset, offset + n * sizeof(point)) exceeds the file");
+  if (n == 0) return b200_table_upload(dev, curve, group, nullptr, 0, flags, out);
+  const size_t slot_bytes = bytes < ((size_t)32 << 20) ? bytes : ((size_t)32 << 20);
+  struct Pinned { void* p[2] = {nullptr, nullptr}; cudaEvent_t ev[2] = {nullptr, nullptr};
+                  ~Pinned() { for (int i = 0; i < 2; i++) { if (p[i]) cudaFreeHost(p[i]); if (ev[i]) cudaEventDestroy(ev[i]); } } } pin;
+  for (int i = 0; i < 2; i++) {
+    CK(cudaHostAlloc(&pin.p[i], slot_bytes, cudaHostAllocDefault));
+    CK(cudaEventCreateWithFlags(&pin.ev[i], cudaEventDisableTiming));
+  }
+  AsyncBuf d_src;
+  CK(d_src.alloc(bytes, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));          // the buffer exists before the copy stream writes to it
+  bool used[2] = {false, false};
+  cudaError_t ce = cudaSuccess;
+  std::string err;
+  const int r = stage_file_region(
+      f.fd, byte_offset, bytes, pin.p, slot_bytes,
+      [&](int slot, const void* data, size_t pos, size_t len) {
+        ce = cudaMemcpyAsync((char*)d_src.p + pos, data, len, cudaMemcpyHostToDevice, ctx->copy_stream);
+        if (ce == cudaSuccess) ce = cudaEventRecord(pin.ev[slot], ctx->copy_stream);
+        used[slot] = true;
+        return ce == cudaSuccess ? 0 : 1;
+      },
+      [&](int slot) {
+        if (!used[slot]) return 0;
+        ce = cudaEventSynchronize(pin.ev[slot]);
+        return ce == cudaSuccess ? 0 : 1;
+      },
+      &err);
+  cudaError_t ce2 = cudaStreamSynchronize(ctx->copy_stream);
+  if (ce != cudaSuccess) return cuda_fail("table_upload_file", ce);
+  if (r != 0) return set_error("table_upload_file: " + err);
+  if (ce2 != cudaSuccess) return cuda_fail("table_upload_file", ce2);
+  rc = b200_table_upload(dev, curve, group, d_src.p, n, flags | B200_TABLE_SRC_ON_DEVICE, out);
+  d_src.release_on(ctx->stream);
+  return rc;
   GUARD_END
 }
 

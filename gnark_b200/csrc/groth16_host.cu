@@ -124,11 +124,23 @@ int32_t b200_groth16_pk_load(int32_t dev, const b200_groth16_pk_desc* d, b200_pk
   b200_pk_t raw = pk.get();
 #define PK_TRY(x) do { int32_t rc_ = (x); if (rc_) { std::string m = b200_last_error(); b200_groth16_pk_free(pk.release()); set_error(m); return rc_; } } while (0)
   PK_TRY(b200_ntt_domain_new(dev, d->curve, (uint32_t)pk->logn, d->domain_gen, d->coset_gen, &raw->dom));
-  PK_TRY(b200_table_upload(dev, d->curve, 1, at(d->g1_a, off_a * ab1), cnt_a, d->flags, &raw->A));
-  PK_TRY(b200_table_upload(dev, d->curve, 1, at(d->g1_b, off_b * ab1), cnt_b, d->flags, &raw->B1));
-  PK_TRY(b200_table_upload(dev, d->curve, 1, at(d->g1_z, pk->off_z * ab1), pk->cnt_z, d->flags, &raw->Z));
-  PK_TRY(b200_table_upload(dev, d->curve, 1, at(d->g1_k, pk->off_k * ab1), pk->cnt_k, d->flags, &raw->K));
-  PK_TRY(b200_table_upload(dev, d->curve, 2, at(d->g2_b, off_b * ab2), cnt_b, d->flags, &raw->B2));
+  if (d->dump_path) {
+    // tables (this shard's ranges) straight from the ProvingKey dump file, marshal.go:375-539
+    PK_TRY(b200_table_upload_file(dev, d->curve, 1, d->dump_path, d->dump_off_a + off_a * ab1, cnt_a, d->flags, &raw->A));
+    PK_TRY(b200_table_upload_file(dev, d->curve, 1, d->dump_path, d->dump_off_b + off_b * ab1, cnt_b, d->flags, &raw->B1));
+    PK_TRY(b200_table_upload_file(dev, d->curve, 1, d->dump_path, d->dump_off_z + pk->off_z * ab1, pk->cnt_z, d->flags, &raw->Z));
+    PK_TRY(b200_table_upload_file(dev, d->curve, 1, d->dump_path, d->dump_off_k + pk->off_k * ab1, pk->cnt_k, d->flags, &raw->K));
+    PK_TRY(b200_table_upload_file(dev, d->curve, 2, d->dump_path, d->dump_off_b2 + off_b * ab2, cnt_b, d->flags, &raw->B2));
+  } else {
+    if (!d->g1_a || !d->g1_b || !d->g1_z || !d->g1_k || !d->g2_b) {
+      if (cnt_a || cnt_b || pk->cnt_z || pk->cnt_k) PK_TRY(set_error("pk_load: null table pointer (and no dump_path)"));
+    }
+    PK_TRY(b200_table_upload(dev, d->curve, 1, at(d->g1_a, off_a * ab1), cnt_a, d->flags, &raw->A));
+    PK_TRY(b200_table_upload(dev, d->curve, 1, at(d->g1_b, off_b * ab1), cnt_b, d->flags, &raw->B1));
+    PK_TRY(b200_table_upload(dev, d->curve, 1, at(d->g1_z, pk->off_z * ab1), pk->cnt_z, d->flags, &raw->Z));
+    PK_TRY(b200_table_upload(dev, d->curve, 1, at(d->g1_k, pk->off_k * ab1), pk->cnt_k, d->flags, &raw->K));
+    PK_TRY(b200_table_upload(dev, d->curve, 2, at(d->g2_b, off_b * ab2), cnt_b, d->flags, &raw->B2));
+  }
   auto up = [&](const std::vector<uint32_t>& v, uint32_t** dptr) -> int32_t {
     CK(cudaMalloc(dptr, (v.size() ? v.size() : 1) * sizeof(uint32_t)));
     if (!v.empty()) CK(cudaMemcpy(*dptr, v.data(), v.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));

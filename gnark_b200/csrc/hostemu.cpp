@@ -12,8 +12,11 @@
 
 #include <cfenv>
 
+#include <fcntl.h>
+
 #include "curve52.cuh"
 #include "fixed_base.cuh"
+#include "file_stage.h"
 #include "host_fr.h"
 #include "msm.cuh"
 #include "msm_batch.cuh"
@@ -664,6 +667,40 @@ int emu_plonk_bsb22(int curve, const void* qcp, const void* pi2, void* out, uint
     case 3: return bsb22_emu<bw6_761_fr>(qcp, pi2, out, logn, coset_index, rho);
   }
   return -1;
+}
+
+// file_stage.h (host half of b200_table_upload_file): read [off, off + bytes) of `path` through two slots of slot_bytes
+// into out; the slots are poisoned after each consumption so that a chunk delivered twice or a stale slot shows up.
+// Returns 0, -1 (open), -2 (staging error: short file ...), -3 (a slot was overwritten before it was consumed)
+int emu_stage_file(const char* path, uint64_t off, size_t bytes, size_t slot_bytes, void* out) {
+  int fd = open(path, O_RDONLY);
+  if (fd < 0) return -1;
+  std::vector<unsigned char> a(slot_bytes ? slot_bytes : 1), b(slot_bytes ? slot_bytes : 1);
+  void* slots[2] = {a.data(), b.data()};
+  bool pending[2] = {false, false};
+  bool overwritten = false;
+  std::string err;
+  int r = stage_file_region(
+      fd, off, bytes, slots, slot_bytes,
+      [&](int slot, const void* data, size_t pos, size_t len) {
+        memcpy((char*)out + pos, data, len);
+        memset(slots[slot], 0xEE, slot_bytes);
+        pending[slot] = true;
+        return 0;
+      },
+      [&](int slot) {
+        // the "copy engine" releases a slot only when asked: a slot still pending here must not have been touched
+        if (pending[slot]) {
+          const unsigned char* p = (const unsigned char*)slots[slot];
+          for (size_t i = 0; i < slot_bytes; i++) if (p[i] != 0xEE) overwritten = true;
+          pending[slot] = false;
+        }
+        return 0;
+      },
+      &err);
+  close(fd);
+  if (overwritten) return -3;
+  return r == 0 ? 0 : -2;
 }
 
 // plan tile size used by emu_ntt (GB200_NTT_TILE_LOG on the device)

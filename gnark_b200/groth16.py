@@ -13,6 +13,7 @@ Out of scope here, as in the reference's accelerated package: the R1CS solver
 """
 
 import ctypes
+import os
 import secrets
 from dataclasses import dataclass, field
 from typing import Callable, List, Optional
@@ -173,6 +174,16 @@ class ProvingKey:
         pk.nb_public = int(nb_public)
         return pk
 
+    def use_dump_file(self, path: str, off_a: int, off_b: int, off_z: int, off_k: int, off_b2: int):
+        """Load the five MSM tables from a ProvingKey dump file instead of the in-memory slices: byte offsets of the
+        payloads of G1.A, G1.B, G1.Z, G1.K and G2.B (element 0 of each slice); the slice lengths are taken from the
+        arrays this key was built with, which may then be dropped (set to None) by the caller."""
+        self.dump = {"path": path, "off_a": off_a, "off_b": off_b, "off_z": off_z, "off_k": off_k, "off_b2": off_b2,
+                     "n_a": self._count(self.G1_A, 1), "n_b": self._count(self.G1_B, 1), "n_z": self._count(self.G1_Z, 1),
+                     "n_k": self._count(self.G1_K, 1)}
+        for key in list(self._handles):
+            _lib.check(_lib.load().b200_groth16_pk_free(self._handles.pop(key)))
+
     def _count(self, arr, group):
         frl, fpl, deg = _lib.CURVE_SHAPES[self.curve]
         per = 2 * fpl * (deg if group == 2 else 1)
@@ -190,11 +201,20 @@ class ProvingKey:
         d.domain_gen, d.coset_gen = p(self.domain_gen), p(self.coset_gen)
         d.g1_alpha, d.g1_beta, d.g1_delta = p(self.G1_Alpha), p(self.G1_Beta), p(self.G1_Delta)
         d.g2_beta, d.g2_delta = p(self.G2_Beta), p(self.G2_Delta)
-        d.g1_a, d.n_a = p(self.G1_A), self._count(self.G1_A, 1)
-        d.g1_b, d.n_b = p(self.G1_B), self._count(self.G1_B, 1)
-        d.g1_z, d.n_z = p(self.G1_Z), self._count(self.G1_Z, 1)
-        d.g1_k, d.n_k = p(self.G1_K), self._count(self.G1_K, 1)
-        d.g2_b, d.n_b2 = p(self.G2_B), self._count(self.G2_B, 2)
+        dump = getattr(self, "dump", None)
+        if dump is not None:
+            # tables straight from gnark's ProvingKey dump file (marshal.go:375-539): payload offsets and lengths of
+            # the five point slices, as the Go shim reads them from the dump's header
+            d.dump_path = os.fsencode(dump["path"])
+            d.dump_off_a, d.dump_off_b, d.dump_off_z = dump["off_a"], dump["off_b"], dump["off_z"]
+            d.dump_off_k, d.dump_off_b2 = dump["off_k"], dump["off_b2"]
+            d.n_a, d.n_b, d.n_z, d.n_k, d.n_b2 = dump["n_a"], dump["n_b"], dump["n_z"], dump["n_k"], dump["n_b"]
+        else:
+            d.g1_a, d.n_a = p(self.G1_A), self._count(self.G1_A, 1)
+            d.g1_b, d.n_b = p(self.G1_B), self._count(self.G1_B, 1)
+            d.g1_z, d.n_z = p(self.G1_Z), self._count(self.G1_Z, 1)
+            d.g1_k, d.n_k = p(self.G1_K), self._count(self.G1_K, 1)
+            d.g2_b, d.n_b2 = p(self.G2_B), self._count(self.G2_B, 2)
         d.infinity_a, d.infinity_b = p(self.InfinityA), p(self.InfinityB)
         d.nb_wires, d.nb_public = self.nb_wires, self.nb_public
         kr = getattr(self, "k_removed", None)

@@ -26,7 +26,7 @@ CURVE_SHAPES = {BN254: (4, 4, 2), BLS12_381: (4, 6, 2), BLS12_377: (4, 6, 2), BW
 EXPORTS = [
     "b200_version", "b200_last_error", "b200_device_count", "b200_init", "b200_shutdown", "b200_set_stream",
     "b200_sync", "b200_alloc", "b200_free", "b200_h2d", "b200_d2h", "b200_host_alloc", "b200_host_free",
-    "b200_table_upload", "b200_table_free", "b200_table_info", "b200_msm", "b200_msm_g1", "b200_msm_g2",
+    "b200_table_upload", "b200_table_upload_file", "b200_table_free", "b200_table_info", "b200_msm", "b200_msm_g1", "b200_msm_g2",
     "b200_msm_async", "b200_msm_pipelined", "b200_msm_join", "b200_msm_profile", "b200_ntt_domain_new", "b200_ntt_domain_free", "b200_ntt", "b200_ntt_async",
     "b200_groth16_compute_h", "b200_vec_op", "b200_vec_bit_reverse", "b200_vec_scale_powers",
     "b200_vec_batch_invert", "b200_plonk_constraints_coset", "b200_plonk_divide_by_zh",
@@ -78,6 +78,9 @@ class Groth16PkDesc(ctypes.Structure):
         ("shard_world", ctypes.c_int32),
         ("k_removed", ctypes.c_void_p),
         ("n_k_removed", ctypes.c_size_t),
+        ("dump_path", ctypes.c_char_p),
+        ("dump_off_a", ctypes.c_uint64), ("dump_off_b", ctypes.c_uint64), ("dump_off_z", ctypes.c_uint64),
+        ("dump_off_k", ctypes.c_uint64), ("dump_off_b2", ctypes.c_uint64),
     ]
 
 
@@ -115,6 +118,7 @@ def load(path: str = None):
     lib.b200_host_alloc.argtypes = [sz, ctypes.POINTER(vp)]
     lib.b200_host_free.argtypes = [vp]
     lib.b200_table_upload.argtypes = [i32, i32, i32, vp, sz, i32, ctypes.POINTER(vp)]
+    lib.b200_table_upload_file.argtypes = [i32, i32, i32, ctypes.c_char_p, ctypes.c_uint64, sz, i32, ctypes.POINTER(vp)]
     lib.b200_table_free.argtypes = [vp]
     lib.b200_table_info.argtypes = [vp, ctypes.POINTER(sz), ctypes.POINTER(i32), ctypes.POINTER(i32),
                                     ctypes.POINTER(i32), ctypes.POINTER(sz)]
@@ -221,6 +225,21 @@ class Table:
         h = ctypes.c_void_p(0)
         check(load().b200_table_upload(dev, curve, group, ptr(points), n, flags, ctypes.byref(h)))
         self.handle = h
+
+    @classmethod
+    def from_file(cls, curve: int, group: int, path: str, byte_offset: int, n: int, dev: int = 0, precomp: bool = True):
+        """n affine points read straight from a file region (a point slice of gnark's ProvingKey dump) into HBM."""
+        t = cls.__new__(cls)
+        t.curve, t.group, t.dev = curve, group, dev
+        frl, fpl, deg = CURVE_SHAPES[curve]
+        t.fr_limbs = frl
+        t.coord_limbs = fpl * (deg if group == 2 else 1)
+        t.n = n
+        h = ctypes.c_void_p(0)
+        check(load().b200_table_upload_file(dev, curve, group, os.fsencode(path), byte_offset, n,
+                                            TABLE_PRECOMP if precomp else 0, ctypes.byref(h)))
+        t.handle = h
+        return t
 
     def info(self):
         n, c, w, p, b = ctypes.c_size_t(), ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32(), ctypes.c_size_t()

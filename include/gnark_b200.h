@@ -75,6 +75,14 @@ int32_t b200_host_free(void* pinned);
  *      PinToGPU uploads :185-261, FreeGPUResources :1493-1549) ---------------- */
 int32_t b200_table_upload(int32_t dev, int32_t curve, int32_t group /*1|2*/, const void* points_affine_mont,
                           size_t n, int32_t flags, b200_table_t* out);
+/* Table straight from a file region: n affine points (gnark memory layout) starting at byte_offset of `path` - the payload
+ * of one point slice of gnark's ProvingKey dump (ProvingKey.WriteDump / ReadDump, backend/groth16/bn254/marshal.go:375-539:
+ * G1.A, G1.B, G1.Z, G1.K, G2.B and the commitment bases are written by unsafe.WriteSlice as raw memory images; SURVEY.md
+ * §8f-1).  The file is read through two pinned slots while the previous chunk is copied to the device; no host copy of the
+ * slice is ever made.  The caller (the Go shim, which reads the dump's header with gnark-crypto's decoder) supplies the
+ * payload offset; a point-range shard supplies the offset and count of ITS range. */
+int32_t b200_table_upload_file(int32_t dev, int32_t curve, int32_t group /*1|2*/, const char* path, uint64_t byte_offset,
+                               size_t n, int32_t flags, b200_table_t* out);
 int32_t b200_table_free(b200_table_t t);
 int32_t b200_table_info(b200_table_t t, size_t* n, int32_t* window_bits, int32_t* n_windows, int32_t* precomp,
                         size_t* device_bytes);
@@ -301,6 +309,12 @@ typedef struct {
    * (CommitmentKeys[i].Commit / ProveKnowledge, prove.go:84,114) go through b200_table_upload + b200_msm_g1. */
   const uint32_t* k_removed;
   size_t n_k_removed;
+  /* Key tables from gnark's dump file instead of host memory: when dump_path is not NULL the five
+   * pointers g1_a, g1_b, g1_z, g1_k, g2_b are ignored and every table (or this process's shard of it) is read with
+   * b200_table_upload_file from the payload offsets below (the byte position of element 0 of each slice, i.e. just
+   * after the slice's length prefix); n_a .. n_b2 still give the slice lengths. */
+  const char* dump_path;
+  uint64_t dump_off_a, dump_off_b, dump_off_z, dump_off_k, dump_off_b2;
 } b200_groth16_pk_desc;
 
 int32_t b200_groth16_pk_load(int32_t dev, const b200_groth16_pk_desc* desc, b200_pk_t* out);

@@ -73,3 +73,24 @@ def test_host_point_helpers(b200lib):
             acc = J(p)
             lib.point_add_jac(c.curve_id, group, acc, J(p))           # doubling path
             assert ec.unpack_points(c, group, lib.point_to_affine(c.curve_id, group, acc))[0] == ec.affine_add(F, p, p)
+
+
+def test_file_staging_of_dump_slices(hostemu, tmp_path):
+    """file_stage.h - the host half of b200_table_upload_file (point slices of gnark's ProvingKey dump go from the file
+    to the device through two staging slots): every byte of the range exactly once and in place, ranges that are not a
+    multiple of the slot, a range inside a larger file, a file that is too short, a missing file."""
+    import ctypes
+    import numpy as np
+    rs = np.random.RandomState(3)
+    data = rs.randint(0, 256, size=100_003, dtype=np.uint8)
+    f = tmp_path / "dump.bin"
+    f.write_bytes(data.tobytes())
+    path = str(f).encode()
+    hostemu.emu_stage_file.argtypes = [ctypes.c_char_p, ctypes.c_uint64, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_void_p]
+    for off, nbytes, slot in ((0, 100_003, 4096), (17, 64 * 1000, 64 * 7), (99_000, 1003, 1 << 20), (5, 0, 128), (0, 4096, 4096)):
+        out = np.zeros(max(nbytes, 1), dtype=np.uint8)
+        assert hostemu.emu_stage_file(path, off, nbytes, slot, out.ctypes.data) == 0
+        assert np.array_equal(out[:nbytes], data[off:off + nbytes]), (off, nbytes, slot)
+    out = np.zeros(2000, dtype=np.uint8)
+    assert hostemu.emu_stage_file(path, 99_000, 2000, 512, out.ctypes.data) == -2         # range exceeds the file
+    assert hostemu.emu_stage_file(str(tmp_path / "missing").encode(), 0, 16, 16, out.ctypes.data) == -1

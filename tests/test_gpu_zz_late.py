@@ -462,6 +462,58 @@ def test_fixed_base_batch(gpu, c, group):
     assert ec.unpack_points(c, group, got)[2] == ec.scalar_mul(F, c.r - 1, base)
 
 
+@pytest.mark.xfail(strict=False, reason="entry point written after this round's GPU budget was spent; the host half (file_stage.h) is "
+                   "pinned on the CPU by tests/test_abi.py::test_file_staging_of_dump_slices")
+def test_tables_straight_from_a_dump_file(gpu, tmp_path):
+    """b200_table_upload_file and the dump_path form of b200_groth16_pk_load: point slices written the
+    way ProvingKey.WriteDump writes them (8-byte little-endian length, then the raw memory image) are read from the file
+    into HBM; MSM results and a whole proof must equal those of the in-memory path, also for a point-range shard."""
+    import struct
+    from gnark_b200 import groth16 as b200
+    from oracle import groth16 as g16o
+    from util import build_groth16_pk, known_dlog_instance, pack_solution
+    c = CURVES["bn254"]
+    # 1. one table
+    _, _, pts, sc, expected = known_dlog_instance(c, 1, 70000, seed=5)
+    f = tmp_path / "slice.bin"
+    with open(f, "wb") as fh:
+        fh.write(b"HEADER-OF-ANOTHER-KIND" + struct.pack("<Q", 70000))
+        off = fh.tell()
+        fh.write(np.ascontiguousarray(pts).tobytes())
+        fh.write(b"trailer")
+    for precomp in (False, True):
+        t = gpu.Table.from_file(c.curve_id, 1, str(f), off, 70000, precomp=precomp)
+        assert jac_to_affine(c, 1, t.msm(sc)) == expected
+        t.free()
+    per = 2 * c.fp_limbs * 8
+    t = gpu.Table.from_file(c.curve_id, 1, str(f), off + 1000 * per, 3000)                 # a point range of the slice
+    want = gpu.Table(c.curve_id, 1, np.ascontiguousarray(pts[1000:4000]))
+    sub = np.ascontiguousarray(sc[:3000])
+    assert jac_to_affine(c, 1, t.msm(sub)) == jac_to_affine(c, 1, want.msm(sub))
+    t.free(); want.free()
+    with pytest.raises(gpu.B200Error):
+        gpu.Table.from_file(c.curve_id, 1, str(f), off, 70001 + 10)                          # exceeds the file
+    # 2. a whole key
+    m = 2000
+    cs, W = g16o.square_chain_r1cs(m), g16o.square_chain_witness(c.r, m)
+    pk, pkd, _, _ = build_groth16_pk(c, cs, g16o.random_toxic(c, 21), 21)
+    sol = pack_solution(c, cs, W)
+    rs = [111, 222]
+    ref = b200.ProveSolution(pk, sol, b200.WithDeviceID(0), b200.WithRandomness(lambda q, it=iter(rs): next(it)))
+    dump = tmp_path / "pk.dump"
+    offs = {}
+    with open(dump, "wb") as fh:
+        fh.write(b"marker+domain+alpha..")                                                 # whatever precedes the slices
+        for name, arr in (("a", pk.G1_A), ("b", pk.G1_B), ("z", pk.G1_Z), ("k", pk.G1_K), ("b2", pk.G2_B)):
+            fh.write(struct.pack("<Q", 0))                                                 # the slice's length prefix
+            offs[name] = fh.tell()
+            fh.write(np.ascontiguousarray(arr).tobytes())
+    pk.use_dump_file(str(dump), offs["a"], offs["b"], offs["z"], offs["k"], offs["b2"])
+    got = b200.ProveSolution(pk, sol, b200.WithDeviceID(0), b200.WithRandomness(lambda q, it=iter(rs): next(it)))
+    assert np.array_equal(ref.Ar, got.Ar) and np.array_equal(ref.Bs, got.Bs) and np.array_equal(ref.Krs, got.Krs)
+    pk.free_gpu_resources()
+
+
 @pytest.mark.xfail(strict=False, reason="one-process multi-GPU path written after this round's GPU budget was spent; its host logic "
                    "is pinned on the CPU by tests/test_groth16_host_logic.py")
 def test_groth16_with_devices_in_one_process(gpu):
