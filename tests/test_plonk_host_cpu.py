@@ -265,3 +265,68 @@ def test_plonk_proof_over_the_ethereum_srs_verifies(mock):
     wrong = list(got); wrong[1] = (wrong[1] + 1) % r
     assert not pp.verify_pairing(c, circ, proof_pts, wrong, ch, srs_g1=mono, tau_g2=g2[1])
     assert mock.b200_plonk_pk_free(h) == 0
+
+
+def test_concurrent_callers_are_serialised_per_device(mock):
+    """The reference lets callers invoke Prove concurrently and serialises them per device (icicle.go:53-60); here every
+    entry point holds the device's lock from its lookup to its return.  Eight threads prove at once on the mocked C ABI -
+    four on one shared key, four on their own keys - and every proof must equal the single-threaded one (ctypes releases
+    the GIL during the calls, so the C++ orchestration really is entered concurrently)."""
+    import threading
+    c = CURVES["bn254"]
+    logn = 4
+    n = 1 << logn
+    r, L = c.r, c.fr_limbs
+    pe = lambda v: np.ascontiguousarray(ff.pack_elements(v, r, L))
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+
+    def make(seed):
+        rng = random.Random(seed)
+        circ, l, rr, o = pp.random_satisfied_instance(c, n, seed=seed)
+        rnd = lambda: rng.randrange(r)
+        ch = pp.Challenges(gamma=rnd(), beta=rnd(), alpha=rnd(), zeta=rnd(), v=rnd(), bl=[rnd(), rnd()], br=[rnd(), rnd()],
+                           bo=[rnd(), rnd()], bz=[rnd(), rnd(), rnd()])
+        tau = rnd()
+        keep = {"srs": np.ascontiguousarray(corelib.fixed_base(c, 1, ec.pack_points(c, 1, [c.g1]), pe([pow(tau, i, r) for i in range(n + 3)]))),
+                "perm": np.ascontiguousarray(np.array(circ.perm, dtype=np.int64)),
+                **{k: pe(getattr(circ, k)) for k in ("ql", "qr", "qm", "qo", "qk")}}
+        d = b200.PlonkPkDesc()
+        d.log2n = logn
+        for k in ("ql", "qr", "qm", "qo", "qk"):
+            setattr(d, k, P(keep[k]).value)
+        d.perm, d.srs_canonical = P(keep["perm"]).value, P(keep["srs"]).value
+        h = ctypes.c_void_p(0)
+        assert mock.b200_plonk_pk_load(0, c.curve_id, ctypes.byref(d), ctypes.byref(h)) == 0, mock.b200_last_error()
+        sc = {k: pe(v) for k, v in (("gamma", [ch.gamma]), ("beta", [ch.beta]), ("alpha", [ch.alpha]), ("zeta", [ch.zeta]),
+                                    ("v", [ch.v]), ("bl", ch.bl), ("br", ch.br), ("bo", ch.bo), ("bz", ch.bz))}
+        cs = b200.PlonkChallenges()
+        for k, a in sc.items():
+            setattr(cs, k, P(a).value)
+        return {"h": h, "cs": cs, "wit": (pe(l), pe(rr), pe(o)), "keep": (keep, sc)}
+
+    def prove(inst):
+        pts = np.zeros((10, 3 * c.fp_limbs), dtype=np.uint64)
+        vals = np.zeros((7, L), dtype=np.uint64)
+        rc = mock.b200_plonk_prove(inst["h"], P(inst["wit"][0]), P(inst["wit"][1]), P(inst["wit"][2]), ctypes.byref(inst["cs"]),
+                                   P(pts), P(vals))
+        return rc, pts, vals
+
+    insts = [make(900 + i) for i in range(5)]
+    want = [prove(i) for i in insts]
+    assert all(w[0] == 0 for w in want)
+    jobs = [insts[0]] * 4 + insts[1:]                     # four threads share one key, four have their own
+    refs = [want[0]] * 4 + want[1:]
+    got = [None] * len(jobs)
+
+    def run(k):
+        for _ in range(3):
+            got[k] = prove(jobs[k])
+    ts = [threading.Thread(target=run, args=(k,)) for k in range(len(jobs))]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    for g, w in zip(got, refs):
+        assert g[0] == 0 and np.array_equal(g[1], w[1]) and np.array_equal(g[2], w[2])
+    for i in insts:
+        assert mock.b200_plonk_pk_free(i["h"]) == 0
