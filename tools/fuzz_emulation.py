@@ -10,9 +10,9 @@ the A/B arithmetic build) against big-int arithmetic and the C++ oracle - longer
    python tools/fuzz_emulation.py pipes 12         # FP64-pipe accumulate and the hybrid split
    python tools/fuzz_emulation.py plonk 40         # C++ PLONK orchestration (mocked kernels) on random instances + pairing Verify
 
-Round 1: 960 k products + 480 k single-reduction mul_sub + Fp2 operations and 2 080 MSMs (default build, A/B build, and the
-persistent / shared-memory-accumulator variants of the accumulate stage), 1 920 batched-affine MSMs, 1 600 NTTs, 156 fixed-base batches, 78 FP64-pipe / hybrid MSMs,
-40 PLONK proofs: no mismatch.  (The NTT soak did find a bound that was missing in ntt_make_plan for tiles of 2^3 at 2^13 points - emulation
+Round 1: 1.4 M products + 720 k single-reduction mul_sub + Fp2 operations and 2 080 MSMs (default build, A/B build, and the
+persistent / shared-memory-accumulator variants of the accumulate stage), 1 920 batched-affine MSMs, 7 600 NTTs, 156 fixed-base batches, 78 FP64-pipe / hybrid MSMs,
+160 PLONK proofs: no mismatch.  (The NTT soak did find a bound that was missing in ntt_make_plan for tiles of 2^3 at 2^13 points - emulation
 only, device tiles are 2^6 and up - now guarded.)"""
 import sys
 MODE = sys.argv[1] if len(sys.argv) > 1 else "field"
