@@ -114,6 +114,9 @@ int32_t msm_join(DeviceCtx* ctx) {
 int32_t msm_on_stream(DeviceCtx* ctx, b200_table_s* t, size_t off, size_t n, const void* d_scalars, void* d_out,
                       cudaEvent_t* stage_events, bool pipelined) {
   if (off + n > t->n) return set_error("msm: range [off, off+n) exceeds the table");
+  // the pipeline indexes its n * nwin (scalar, window) entries with 31-bit counts (radix sort, offsets, tasks)
+  if ((size_t)n * (size_t)t->nwin >= ((size_t)1 << 31))
+    return set_error("msm: n * windows exceeds 2^31 entries - split the call into point ranges (or shard the table) and add the results");
   if (stage_events || n == 0) pipelined = false;
   if (!pipelined) { int32_t rc = msm_join(ctx); if (rc) return rc; }
   uint32_t task_len, chunk;
@@ -185,6 +188,7 @@ int32_t b200_shutdown(void) {
     cudaSetDevice(d);
     cudaStreamSynchronize(c.stream);
     cudaStreamSynchronize(c.tail_stream);
+    comm_teardown(c);
     cudaStreamDestroy(c.own_stream);
     cudaStreamDestroy(c.tail_stream);
     cudaStreamDestroy(c.copy_stream);
@@ -382,9 +386,7 @@ int32_t b200_table_free(b200_table_t t) {
   if (!t) return 0;
   GB_DEVICE(ctx, t->dev); [[maybe_unused]] int32_t rc = 0;
   CK(cudaStreamSynchronize(ctx->stream));
-  CK(cudaFree(t->d_points));
-  if (t->d_points52) CK(cudaFree(t->d_points52));
-  delete t;
+  delete t;       // ~b200_table_s releases the device buffers
   return 0;
   GUARD_END
 }
@@ -533,6 +535,26 @@ int32_t b200_msm_submit(b200_table_t t, size_t off, size_t n, const void* scalar
   }
   d_sc.release_on(ctx->stream);       // last read by the decompose kernel on the main stream
   d_out.release_on(res_stream);
+  return rc;
+  GUARD_END
+}
+
+// b200_msm_submit with the result left on the DEVICE (d_out_jac, valid after b200_msm_join / b200_sync): the form a
+// sharded MSM needs, whose partial results go through b200_points_allreduce before anything is downloaded.
+int32_t b200_msm_submit_dev(b200_table_t t, size_t off, size_t n, const void* scalars_host, void* d_out_jac) {
+  GUARD_BEGIN
+  if (!t) return set_error("msm_submit_dev: null table");
+  if (!d_out_jac || (n && !scalars_host)) return set_error("msm_submit_dev: null argument");
+  GB_DEVICE(ctx, t->dev); [[maybe_unused]] int32_t rc = 0;
+  AsyncBuf d_sc;
+  if (n) {
+    CK(d_sc.alloc(n * t->ops->fr_bytes, ctx->copy_stream));
+    CK(cudaMemcpyAsync(d_sc.p, scalars_host, n * t->ops->fr_bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+    CK(cudaEventRecord(ctx->copy_ev, ctx->copy_stream));
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->copy_ev, 0));
+  }
+  rc = msm_on_stream(ctx, t, off, n, d_sc.p, d_out_jac, nullptr, /*pipelined=*/true);
+  d_sc.release_on(ctx->stream);       // last read by the decompose kernel on the main stream
   return rc;
   GUARD_END
 }

@@ -38,7 +38,12 @@ struct DeviceCtx {
   // opt-in hybrid accumulate (MsmHybrid): second stream for the FP64-pipe kernel
   cudaStream_t aux_stream = nullptr;
   cudaEvent_t aux_fork_ev = nullptr, aux_join_ev = nullptr;
+  // multi-GPU (comm.cu): NCCL communicator of this device (ncclComm_t), nullptr = single device
+  void* comm = nullptr;
+  int comm_world = 1, comm_rank = 0;
 };
+void comm_teardown(DeviceCtx& c);   // comm.cu
+int32_t points_allreduce_on_stream(DeviceCtx* ctx, const MsmOps* ops, const void* d_partials, size_t count, void* d_totals);
 
 int32_t set_error(const std::string& msg);
 int32_t cuda_fail(const char* what, cudaError_t e);
@@ -58,6 +63,8 @@ struct b200_table_s {
   void* d_points52 = nullptr;   // hybrid accumulate only: the same table in Affine52 format
   int hybrid52_of_16 = 0;       // 0 = off
   const gb200::MsmOps* ops;
+  // owns its device buffers: a table that fails half way through its construction does not leak them
+  ~b200_table_s() { if (d_points) cudaFree(d_points); if (d_points52) cudaFree(d_points52); }
 };
 
 struct b200_domain_s {

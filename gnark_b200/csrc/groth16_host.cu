@@ -28,7 +28,8 @@ struct b200_pk_s {
   const HostGroupOps* h1 = nullptr;
   const HostGroupOps* h2 = nullptr;
   const NttOps* fr = nullptr;
-  std::mutex mu;  // one proof at a time per key (device buffers are per call, tables are read-only)
+  // no per-key lock: tables are read-only, every proof allocates its own stream-ordered buffers, and concurrent
+  // callers on one device are ordered by the device context's lock + stream order (capi_common.h DeviceCtx::mu)
 };
 
 static std::vector<uint8_t> copy_bytes(const void* p, size_t n) {
@@ -234,7 +235,6 @@ int32_t b200_groth16_msms(b200_pk_t pk, const void* wires, const void* a, const 
   if (!pk) return set_error("prove: null proving key");
   if (!wires || !a || !b || !c || !msm_out) return set_error("prove: null argument");
   if (n_constraints > pk->n) return set_error("prove: more constraints than the domain holds");
-  std::lock_guard<std::mutex> lk(pk->mu);
   GB_DEVICE(ctx, pk->dev); [[maybe_unused]] int32_t rc = 0;
   cudaStream_t st = ctx->stream;
   const size_t fb = pk->fr->fr_bytes;
@@ -254,10 +254,12 @@ int32_t b200_groth16_msms(b200_pk_t pk, const void* wires, const void* a, const 
   };
 
   struct Bufs {
-    cudaStream_t st; std::vector<void*> p;
-    ~Bufs() { for (void* q : p) cudaFreeAsync(q, st); }
+    DeviceCtx* ctx; cudaStream_t st; std::vector<void*> p;
+    // every exit path, early error returns included: the pipelined MSM tails (tail stream) still read and write these
+    // buffers, so `st` must wait for them before the stream-ordered frees (and tail_pending must not leak to the next caller)
+    ~Bufs() { msm_join(ctx); for (void* q : p) cudaFreeAsync(q, st); }
     cudaError_t get(void** out, size_t bytes) { cudaError_t e = cudaMallocAsync(out, bytes ? bytes : 1, st); if (e == cudaSuccess) p.push_back(*out); return e; }
-  } bufs{st, {}};
+  } bufs{ctx, st, {}};
   void *d_w, *d_a, *d_b, *d_c, *d_wa, *d_wb, *d_res;
   CK(bufs.get(&d_w, pk->nb_wires * fb));
   CK(bufs.get(&d_a, n * fb)); CK(bufs.get(&d_b, n * fb)); CK(bufs.get(&d_c, n * fb));
@@ -310,6 +312,12 @@ int32_t b200_groth16_msms(b200_pk_t pk, const void* wires, const void* a, const 
   rc = lap("computeH"); if (rc) return rc;
   rc = msm_on_stream(ctx, pk->Z, 0, pk->cnt_z, (char*)d_a + pk->off_z * fb, res + 2 * j1, nullptr, true); if (rc) return rc;
   rc = msm_join(ctx); if (rc) return rc;
+  // sharded key on a device with a communicator of the same world size: gather + fold on the device (comm.cu), so that
+  // msm_out holds the COMPLETE sums on every rank; without a communicator msm_out holds this shard's partial sums
+  if (pk->shard_world > 1 && ctx->comm && ctx->comm_world == pk->shard_world) {
+    rc = points_allreduce_on_stream(ctx, pk->A->ops, res, 4, res); if (rc) return rc;
+    rc = points_allreduce_on_stream(ctx, pk->B2->ops, res + 4 * j1, 1, res + 4 * j1); if (rc) return rc;
+  }
   CK(cudaMemcpyAsync(msm_out, d_res, 4 * j1 + j2, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   rc = lap("msm Z + d2h"); if (rc) return rc;
@@ -370,7 +378,13 @@ int32_t b200_groth16_prove(b200_pk_t pk, const void* wires, const void* a, const
                            void* krs_out, void* msm_out) {
   GUARD_BEGIN
   if (!pk) return set_error("prove: null proving key");
-  if (pk->shard_world > 1) return set_error("prove: sharded key - use b200_groth16_msms + all_gather + b200_groth16_assemble");
+  if (pk->shard_world > 1) {
+    // a sharded key proves in one call only when the library's communicator combines the partial sums (comm.cu)
+    GB_DEVICE(ctx, pk->dev);
+    if (!ctx->comm || ctx->comm_world != pk->shard_world)
+      return set_error("prove: sharded key without a matching communicator - b200_comm_init first, or use "
+                       "b200_groth16_msms + your own gather + b200_groth16_assemble");
+  }
   if (!r || !s || !ar_out || !bs_out || !krs_out) return set_error("prove: null argument");
   std::vector<uint8_t> msm(4 * pk->h1->jac_bytes + pk->h2->jac_bytes);
   const double t0 = now_ms();

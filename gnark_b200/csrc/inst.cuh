@@ -68,9 +68,15 @@ struct MsmInst {
     return fixed_base_enqueue<Fr, F>(st, base, reinterpret_cast<const Fr*>(d_scalars), n, c,
                                      reinterpret_cast<Affine<F>*>(d_out_affine));
   }
+  static cudaError_t fold(cudaStream_t st, const void* d_gathered, uint32_t world, uint32_t count, void* d_out_jac) {
+    if (count == 0 || world == 0) return cudaSuccess;
+    k_points_fold<F><<<(count + 63) / 64, 64, 0, st>>>(reinterpret_cast<const Jacobian<F>*>(d_gathered), world, count,
+                                                       reinterpret_cast<Jacobian<F>*>(d_out_jac));
+    return cudaGetLastError();
+  }
   static const MsmOps* ops() {
     static const MsmOps o = {Fr::Params::BITS, sizeof(Fr), sizeof(Affine<F>), sizeof(Jacobian<F>), &ws_bytes, &run,
-                             &precompute, affine52_bytes(), &precompute52, &fixed_base};
+                             &precompute, affine52_bytes(), &precompute52, &fixed_base, &fold};
     return &o;
   }
 };

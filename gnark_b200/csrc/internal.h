@@ -64,6 +64,8 @@ struct MsmOps {
   cudaError_t (*precompute52)(cudaStream_t st, uint32_t n, int nwin, int c, const void* d_src, void* d_table52);
   // fixed-base batch (fixed_base.cuh): d_out[i] = scalars[i] * base; h_base is ONE affine point on the host
   cudaError_t (*fixed_base)(cudaStream_t st, const void* h_base, const void* d_scalars, size_t n, int c, void* d_out_affine);
+  // multi-GPU combine: d_out[k] = sum_r d_gathered[r * count + k] (Jacobian points, k_points_fold)
+  cudaError_t (*fold)(cudaStream_t st, const void* d_gathered, uint32_t world, uint32_t count, void* d_out_jac);
 };
 
 struct NttOps {

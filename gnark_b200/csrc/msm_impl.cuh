@@ -298,6 +298,20 @@ __global__ void k_msm_finish(int nsets, int c, const XYZZ<F>* __restrict__ set_s
   }
 }
 
+// Multi-GPU combine (the reference sums its chunk results on the host, icicle.go:383-411): gathered holds
+// `world` rows of `count` Jacobian points (row r = rank r's partial results, the layout ncclAllGather produces);
+// out[k] = sum over ranks of gathered[r][k].  One thread per result point: the world-1 additions of one point are
+// serial anyway, and `count` is the number of MSMs folded at once (5 for a Groth16 proof, K for a stream of MSMs).
+template <class F>
+__global__ void __launch_bounds__(64) k_points_fold(const Jacobian<F>* __restrict__ gathered, uint32_t world, uint32_t count,
+                                                    Jacobian<F>* __restrict__ out) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= count) return;
+  XYZZ<F> acc = XYZZ<F>::from_jacobian(gathered[k]);
+  for (uint32_t r = 1; r < world; r++) acc.add(XYZZ<F>::from_jacobian(gathered[(size_t)r * count + k]));
+  out[k] = acc.to_jacobian();
+}
+
 // table precompute (built once per table upload): slab w holds 2^(c*w) * P_i.
 // pass 1: doubling chains, XYZZ results to a scratch buffer [w-1][chunk];
 // pass 2: one inversion per point (Montgomery's trick over its nwin-1 outputs), affine results.

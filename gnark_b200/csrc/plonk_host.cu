@@ -12,6 +12,7 @@
 // transcript encoding is gnark-crypto's; a Go shim derives them exactly as prove.go:492-555 does).  BSB22 commitment
 // gates (:867-884) are supported with the committed polynomials PI2_i supplied by the caller (the reference's solver
 // hint :280-318 produces them); StatisticalZK is not.  Host-side scalar work uses host_fr.h.
+#include <chrono>
 #include <memory>
 #include <vector>
 
@@ -40,6 +41,9 @@ struct b200_plonk_pk_s {
   // elements), so a proof runs 16 coset NTTs (l, r, o, z) instead of 48.  key_cos[i][k]: coset i, polynomial k in the
   // order ql qr qm qo qk s1 s2 s3 qcp...; empty when GB200_PLONK_COSET_CACHE=0.
   std::vector<std::vector<void*>> key_cos;
+  // wall-clock ms of the five stages of the last b200_plonk_prove on this key (every stage ends in a b200_sync, so
+  // these are device times + host orchestration): begin (L,R,O), commit_z, quotient, linearise, batch_open
+  double last_stage_ms[5] = {0, 0, 0, 0, 0};
 };
 
 namespace gb200_plonk {
@@ -163,6 +167,9 @@ int32_t b200_plonk_pk_load(int32_t dev, int32_t curve, const b200_plonk_pk_desc*
   const NttOps* ops = get_ntt_ops(curve);
   if (!ops) return set_error("plonk_pk_load: unsupported curve");
   if ((int)d->log2n + 2 > ops->two_adicity || d->log2n > 28) return set_error("plonk_pk_load: domain too large");
+  // the quotient is read as three slices of n + 2 coefficients out of a 4n buffer (h1, h2, h3): 3 (n + 2) <= 4n needs
+  // n >= 8 (the reference switches to an 8n quotient domain below 6 constraints, setup.go; not supported here)
+  if (d->log2n < 3) return set_error("plonk_pk_load: domains below 2^3 are not supported");
   GB_DEVICE(ctx, dev);
   std::unique_ptr<b200_plonk_pk_s, int32_t (*)(b200_plonk_pk_t)> pk(new b200_plonk_pk_s(), &b200_plonk_pk_free);
   pk->dev = dev; pk->curve = curve; pk->logn = d->log2n; pk->n = (size_t)1 << d->log2n;
@@ -506,19 +513,40 @@ int32_t b200_plonk_prove(b200_plonk_pk_t pk, const void* l, const void* r, const
   b200_plonk_session_t s = nullptr;
   if (!pk->qcp_br.empty() && (!ch->pi2 || !ch->out_bsb22))
     return set_error("plonk_prove: the key has BSB22 commitment gates - challenges.pi2 / out_bsb22 are required");
+  using clk = std::chrono::steady_clock;
+  auto ms_since = [](clk::time_point t0) { return std::chrono::duration<double, std::milli>(clk::now() - t0).count(); };
+  double st_ms[5] = {0, 0, 0, 0, 0};
+  clk::time_point t0 = clk::now();
   int32_t rc = b200_plonk_begin(pk, l, r, o, ch->bl, ch->br, ch->bo, ch->pi2, ch->out_bsb22, &s, pts);
+  if (!rc) rc = b200_sync(pk->dev);
+  st_ms[0] = ms_since(t0); t0 = clk::now();
   if (!rc) rc = b200_plonk_commit_z(s, ch->beta, ch->gamma, ch->bz, pts + 3 * jb);
+  st_ms[1] = ms_since(t0); t0 = clk::now();
   if (!rc) rc = b200_plonk_quotient(s, ch->alpha, pts + 4 * jb);
+  st_ms[2] = ms_since(t0); t0 = clk::now();
   uint8_t two[2 * 288];     // linearised digest, Z opening; 288 B = G1Jac of the largest curve (BW6-761: 3 x 96 B)
-  if (jb > 288) return set_error("plonk_prove: unexpected point size");
+  if (jb > 288) { b200_plonk_end(s); return set_error("plonk_prove: unexpected point size"); }
   if (!rc) rc = b200_plonk_linearise(s, ch->zeta, two, out_values);
+  st_ms[3] = ms_since(t0); t0 = clk::now();
   if (!rc) {
     memcpy(pts + 7 * jb, two, jb);
     memcpy(pts + 9 * jb, two + jb, jb);
     rc = b200_plonk_batch_open(s, ch->v, pts + 8 * jb);
   }
+  st_ms[4] = ms_since(t0);
+  std::string err = rc ? b200_last_error() : "";
   b200_plonk_end(s);
-  return rc;
+  if (rc) return set_error(err), rc;
+  for (int k = 0; k < 5; k++) pk->last_stage_ms[k] = st_ms[k];
+  return 0;
+  GUARD_END
+}
+
+int32_t b200_plonk_last_stage_ms(b200_plonk_pk_t pk, double* out5) {
+  GUARD_BEGIN
+  if (!pk || !out5) return set_error("plonk_last_stage_ms: null argument");
+  for (int k = 0; k < 5; k++) out5[k] = pk->last_stage_ms[k];
+  return 0;
   GUARD_END
 }
 

@@ -323,7 +323,10 @@ def ProveSolution(pk: ProvingKey, sol: R1CSSolution, *opts: Option, keep_msm: bo
         msm = fold(parts)
         _lib.check(L.b200_groth16_assemble(pk._handle, p(msm), p(r), p(s), p(ar), p(bs), p(krs)))
         return Proof(Ar=ar, Bs=bs, Krs=krs, msm=msm if keep_msm else None)
-    if cfg.ShardWorld <= 1:
+    comm_world = _lib.comm_info(cfg.DeviceID)[0] if cfg.ShardWorld > 1 else 1
+    if cfg.ShardWorld <= 1 or comm_world == cfg.ShardWorld:
+        # single device, or sharded with the library's communicator (b200_comm_init): the five partial sums are
+        # gathered and added on the device inside the call, every rank assembles the same proof
         msm = np.zeros(4 * 3 * fpl + 3 * fpl * deg, dtype=np.uint64) if keep_msm else None
         _lib.check(L.b200_groth16_prove(pk._handle, p(sol.W), p(sol.A), p(sol.B), p(sol.C), n_constraints,
                                         p(r), p(s), p(ar), p(bs), p(krs), p(msm)))

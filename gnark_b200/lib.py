@@ -35,7 +35,10 @@ EXPORTS = [
     "b200_groth16_assemble", "b200_fixed_base_batch", "b200_msm_submit",
     "b200_plonk_pk_load", "b200_plonk_pk_free", "b200_plonk_prove", "b200_plonk_begin", "b200_plonk_commit_z",
     "b200_plonk_quotient", "b200_plonk_linearise", "b200_plonk_batch_open", "b200_plonk_end", "b200_plonk_bsb22_coset",
+    "b200_comm_unique_id", "b200_comm_init", "b200_comm_init_all", "b200_comm_destroy", "b200_comm_info",
+    "b200_points_allreduce", "b200_msm_allreduce", "b200_msm_submit_dev", "b200_plonk_last_stage_ms", "b200_points_fold",
 ]
+COMM_ID_BYTES = 128
 
 
 class B200Error(RuntimeError):
@@ -102,7 +105,13 @@ def load(path: str = None):
     lib = ctypes.CDLL(p)
     lib.b200_version.restype = ctypes.c_char_p
     lib.b200_last_error.restype = ctypes.c_char_p
+    variant = p != LIB_PATH      # an A/B build loaded through GB200_LIB may predate the newest entry points
+    missing = [name for name in EXPORTS if not hasattr(lib, name)]
+    if missing and not variant:
+        raise B200Error(f"{p} lacks {missing}: stale build, rebuild it (make -C gnark_b200/csrc)")
     for name in EXPORTS:
+        if name in missing:
+            continue
         fn = getattr(lib, name)
         if name not in ("b200_version", "b200_last_error"):
             fn.restype = ctypes.c_int32
@@ -128,6 +137,19 @@ def load(path: str = None):
     lib.b200_msm_pipelined.argtypes = [vp, sz, sz, vp, vp]
     lib.b200_msm_join.argtypes = [i32]
     lib.b200_msm_submit.argtypes = [vp, sz, sz, vp, vp]
+    if "b200_comm_init" not in missing:
+        lib.b200_comm_unique_id.argtypes = [vp]
+        lib.b200_comm_init.argtypes = [i32, i32, i32, vp]
+        lib.b200_comm_init_all.argtypes = [i32, ctypes.POINTER(i32)]
+        lib.b200_comm_destroy.argtypes = [i32]
+        lib.b200_comm_info.argtypes = [i32, ctypes.POINTER(i32), ctypes.POINTER(i32)]
+        lib.b200_points_allreduce.argtypes = [i32, i32, i32, vp, sz, vp]
+        lib.b200_msm_allreduce.argtypes = [vp, sz, sz, vp, i32, vp]
+        lib.b200_msm_submit_dev.argtypes = [vp, sz, sz, vp, vp]
+    if "b200_points_fold" not in missing:
+        lib.b200_points_fold.argtypes = [i32, i32, i32, vp, u32, u32, vp]
+    if "b200_plonk_last_stage_ms" not in missing:
+        lib.b200_plonk_last_stage_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_double)]
     lib.b200_plonk_pk_load.argtypes = [i32, i32, ctypes.POINTER(PlonkPkDesc), ctypes.POINTER(vp)]
     lib.b200_plonk_pk_free.argtypes = [vp]
     lib.b200_plonk_prove.argtypes = [vp, vp, vp, vp, ctypes.POINTER(PlonkChallenges), vp, vp]
@@ -200,6 +222,60 @@ def init(dev_ids=None):
         check(lib.b200_init(len(dev_ids), arr))
 
 
+def comm_unique_id() -> np.ndarray:
+    """128 opaque bytes (an NCCL unique id) created on rank 0; ship them to every rank, then comm_init."""
+    out = np.zeros(COMM_ID_BYTES, dtype=np.uint8)
+    check(load().b200_comm_unique_id(ptr(out)))
+    return out
+
+
+def comm_init(dev: int, world: int, rank: int, unique_id=None):
+    """the library's own communicator for `dev` (one process per GPU); world == 1 clears it"""
+    check(load().b200_comm_init(dev, world, rank, ptr(unique_id)))
+
+
+def comm_init_torch(dev: int, pg=None):
+    """one process per GPU under torch.distributed: rank 0's id is broadcast over the existing process group"""
+    import torch
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(pg), dist.get_rank(pg)
+    if world == 1:
+        comm_init(dev, 1, 0)
+        return
+    ident = comm_unique_id() if rank == 0 else np.zeros(COMM_ID_BYTES, dtype=np.uint8)
+    t = torch.from_numpy(ident)
+    if dist.get_backend(pg) == "nccl":
+        t = t.cuda(dev)
+    dist.broadcast(t, src=dist.get_global_rank(pg, 0) if pg is not None else 0, group=pg)
+    comm_init(dev, world, rank, t.cpu().numpy())
+
+
+def comm_init_all(dev_ids):
+    arr = (ctypes.c_int32 * len(dev_ids))(*dev_ids)
+    check(load().b200_comm_init_all(len(dev_ids), arr))
+
+
+def comm_destroy(dev: int):
+    check(load().b200_comm_destroy(dev))
+
+
+def comm_info(dev: int):
+    w, r = ctypes.c_int32(1), ctypes.c_int32(0)
+    check(load().b200_comm_info(dev, ctypes.byref(w), ctypes.byref(r)))
+    return w.value, r.value
+
+
+def points_allreduce(dev: int, curve: int, group: int, d_partials, count: int, d_totals=None):
+    """d_totals[k] = sum over ranks of d_partials[k] (device Jacobian points); in place when d_totals is None"""
+    check(load().b200_points_allreduce(dev, curve, group, ptr(d_partials), count,
+                                       ptr(d_totals if d_totals is not None else d_partials)))
+
+
+def points_fold(dev: int, curve: int, group: int, d_gathered, world: int, count: int, d_totals):
+    """d_totals[k] = sum_r d_gathered[r][k] on the device (the reduction half of points_allreduce)"""
+    check(load().b200_points_fold(dev, curve, group, ptr(d_gathered), world, count, ptr(d_totals)))
+
+
 def set_stream(dev: int, cuda_stream: int):
     check(load().b200_set_stream(dev, ctypes.c_void_p(cuda_stream)))
 
@@ -257,6 +333,15 @@ class Table:
         check(fn(self.handle, off, n, ptr(scalars), 1 if on_device else 0, ptr(out)))
         return out
 
+    def msm_allreduce(self, scalars, off: int = 0, n: int = None, on_device: bool = False) -> np.ndarray:
+        """this rank's shard of a point-range-sharded MSM + the combine over the library's communicator: the full sum
+        on every rank (b200_msm when there is no communicator)"""
+        if n is None:
+            n = (scalars.size if isinstance(scalars, np.ndarray) else scalars.numel()) // self.fr_limbs
+        out = np.zeros(3 * self.coord_limbs, dtype=np.uint64)
+        check(load().b200_msm_allreduce(self.handle, off, n, ptr(scalars), 1 if on_device else 0, ptr(out)))
+        return out
+
     def msm_async(self, d_scalars, d_out, off: int = 0, n: int = None):
         check(load().b200_msm_async(self.handle, off, n, ptr(d_scalars), ptr(d_out)))
 
@@ -270,6 +355,12 @@ class Table:
         if n is None:
             n = h_scalars.numel() // self.fr_limbs
         check(load().b200_msm_submit(self.handle, off, n, ptr(h_scalars), ptr(h_out)))
+
+    def msm_submit_dev(self, h_scalars, d_out, off: int = 0, n: int = None):
+        """msm_submit with the result left on the device (d_out: 3 * coord_limbs int64 of device memory)"""
+        if n is None:
+            n = h_scalars.numel() // self.fr_limbs
+        check(load().b200_msm_submit_dev(self.handle, off, n, ptr(h_scalars), ptr(d_out)))
 
     def join(self):
         check(load().b200_msm_join(self.dev))
@@ -392,6 +483,14 @@ class PlonkKey:
         check(load().b200_plonk_prove(self.handle, ptr(args[0]), ptr(args[1]), ptr(args[2]), ctypes.byref(ch), ptr(pts),
                                       ptr(vals)))
         return (pts, vals, bsb[:self.n_qcp]) if self.n_qcp else (pts, vals)
+
+    STAGES = ("begin_lro", "commit_z", "quotient", "linearise", "batch_open")
+
+    def last_stage_ms(self) -> dict:
+        """wall-clock ms of the five stages of the last prove() on this key"""
+        ms = (ctypes.c_double * 5)()
+        check(load().b200_plonk_last_stage_ms(self.handle, ms))
+        return dict(zip(self.STAGES, [float(x) for x in ms]))
 
     def free(self):
         if self.handle:

@@ -112,6 +112,9 @@ int32_t b200_msm_join(int32_t dev);
  * calls overlap.  scalars_host (n fr.Elements) and out_jac_host (one G?Jac) must be b200_host_alloc memory
  * and stay untouched until b200_sync(dev) returns; results are valid after b200_sync. */
 int32_t b200_msm_submit(b200_table_t bases, size_t off, size_t n, const void* scalars_host, void* out_jac_host);
+/* the same with the result left on the device (valid on the device stream after b200_msm_join): what a sharded MSM
+ * needs, whose partial results pass through b200_points_allreduce before one download of the totals */
+int32_t b200_msm_submit_dev(b200_table_t bases, size_t off, size_t n, const void* scalars_host, void* d_out_jac);
 
 /* step profile (the reference's ICICLE_STEP_PROFILE timers, icicle.go:72-75,1088-1094):
  * device milliseconds of the 7 pipeline stages of one MSM - decompose, sort,
@@ -124,6 +127,36 @@ int32_t b200_msm_profile(b200_table_t bases, size_t off, size_t n, const void* d
  * combined the same way).  Pure CPU, no device needed. */
 int32_t b200_point_add_jac(int32_t curve, int32_t group, void* acc_jac, const void* q_jac);
 int32_t b200_point_to_affine(int32_t curve, int32_t group, const void* p_jac, void* out_affine);
+
+/* ---- multi-GPU (SURVEY.md 8b "NCCL comm when n_dev>1", 8e) ---------------------------------------------------
+ * The path shards by point range: every device owns the table shard of its range and produces one partial point per
+ * MSM; the only exchange is a gather of `world` points followed by world-1 group additions - the multi-device twin of
+ * the reference's host-side chunk loop (icicle.go:383-411; the reference itself drives one device per proof,
+ * opts.go:68-77).  The library owns one NCCL communicator per device (bound at run time: without NCCL everything
+ * single-GPU still works) and does gather + additions on the device, on the device's stream.
+ *   one process per GPU : rank 0 calls b200_comm_unique_id, ships the 128 bytes to the other ranks by any means
+ *                         (the Go shim: its own RPC; the Python harness: torch.distributed broadcast), every rank
+ *                         calls b200_comm_init(dev, world, rank, id).
+ *   one process, N GPUs : b200_comm_init_all(n, dev_ids); afterwards each device's calls come from its own thread
+ *                         (goroutine), as NCCL requires for collectives issued without a group. */
+#define B200_COMM_ID_BYTES 128
+int32_t b200_comm_unique_id(void* out_id128);
+int32_t b200_comm_init(int32_t dev, int32_t world, int32_t rank, const void* id128);
+int32_t b200_comm_init_all(int32_t n_dev, const int32_t* dev_ids);
+int32_t b200_comm_destroy(int32_t dev);
+int32_t b200_comm_info(int32_t dev, int32_t* out_world, int32_t* out_rank);
+/* d_totals[k] = sum over ranks of that rank's d_partials[k], k < count (G?Jac, device memory, may alias): one
+ * ncclAllGather of world*count points + one fold kernel, stream-ordered, no host synchronisation.  count is the
+ * number of results combined at once (5 for a Groth16 proof, K for a stream of MSMs).  No communicator: a copy. */
+int32_t b200_points_allreduce(int32_t dev, int32_t curve, int32_t group, const void* d_partials_jac, size_t count,
+                              void* d_totals_jac);
+/* the reduction half alone: d_gathered = world rows of count G?Jac points (row r = source r), d_totals[k] = sum over
+ * rows of d_gathered[r][k]; for callers that move the partial points themselves */
+int32_t b200_points_fold(int32_t dev, int32_t curve, int32_t group, const void* d_gathered_jac, uint32_t world,
+                         uint32_t count, void* d_totals_jac);
+/* b200_msm of this rank's shard + the combine: out_jac_host = the full sum, on every rank */
+int32_t b200_msm_allreduce(b200_table_t bases, size_t off, size_t n, const void* scalars_mont, int32_t scalars_on_device,
+                           void* out_jac_host);
 
 /* fixed-base batch: out[i] = scalars[i] * base, n affine points in gnark layout (replaces gnark-crypto's
  * curve.BatchScalarMultiplicationG1/G2 as called by Groth16 Setup, backend/groth16/bn254/setup.go:233,302,
@@ -251,6 +284,11 @@ int32_t b200_plonk_pk_free(b200_plonk_pk_t pk);
  * Qcp_j(zeta) (BatchedProof.ClaimedValues = values 0-5 followed by values 7..). */
 int32_t b200_plonk_prove(b200_plonk_pk_t pk, const void* l, const void* r, const void* o,
                          const b200_plonk_challenges* ch, void* out_points, void* out_values);
+/* wall-clock milliseconds of the five stages of the last successful b200_plonk_prove on this key (begin = L,R,O
+ * canonical forms + 3 commitments; commit_z; quotient; linearise; batch_open) - the step profile of the PLONK prover,
+ * like b200_msm_profile for the MSM (the reference times its stages with the same granularity in debug logs,
+ * backend/plonk/bn254/prove.go:155-233 "instance.*" goroutine stages) */
+int32_t b200_plonk_last_stage_ms(b200_plonk_pk_t pk, double* out_ms5);
 /* The same proof, one entry point per Fiat-Shamir round, so that a caller can derive each challenge from the digests
  * of the previous round exactly as prove.go:492-555 (gamma, beta <- [L],[R],[O]; alpha <- [Z]; zeta <- [H1..3];
  * v <- linearised digest + opened values).  Stages must be called in this order; b200_plonk_end releases the

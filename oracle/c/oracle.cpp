@@ -592,6 +592,58 @@ int bitlen(const u64* p, int n) { for (int i = n - 1; i >= 0; i--) if (p[i]) ret
     else { typedef Cv::Fq2 K; typedef Cv::Fr S; (void)sizeof(K); (void)sizeof(S); return EXPR_G2; }         \
   }
 
+// ---- Fr vector helpers for full-size fixtures and checks (oracle/plonk_fast.py): all Montgomery in / out ----------
+template <class S>
+static int fr_vec(int op, const S* a, const S* b, S* out, size_t n, int nthreads) {
+  if (nthreads < 1) nthreads = 1;
+  std::vector<std::thread> th;
+  const size_t per = (n + nthreads - 1) / nthreads;
+  for (int t = 0; t < nthreads; t++) {
+    const size_t lo = (size_t)t * per, hi = std::min(n, lo + per);
+    if (lo >= hi) break;
+    th.emplace_back([=] {
+      for (size_t i = lo; i < hi; i++) out[i] = op == 0 ? a[i].mul(b[i]) : (op == 1 ? a[i].add(b[i]) : a[i].sub(b[i]));
+    });
+  }
+  for (auto& x : th) x.join();
+  return 0;
+}
+// out[i] = start * ratio^i
+template <class S>
+static int fr_geometric(const S& start, const S& ratio, size_t n, S* out) {
+  S acc = start;
+  for (size_t i = 0; i < n; i++) { out[i] = acc; acc = acc.mul(ratio); }
+  return 0;
+}
+// out[i] = L_i(x) = (x^n - 1) / n * w^i / (x - w^i), n = 2^logn, w = gen (x not in the domain); one inversion (Montgomery's trick)
+template <class S>
+static int fr_lagrange_at(int logn, const S& gen, const S& x, S* out) {
+  const size_t n = (size_t)1 << logn;
+  std::vector<S> wp(n), pre(n);
+  S acc = S::one();
+  for (size_t i = 0; i < n; i++) { wp[i] = acc; acc = acc.mul(gen); }
+  S prod = S::one();
+  for (size_t i = 0; i < n; i++) {
+    const S d = x.sub(wp[i]);
+    if (d.is_zero()) return -2;
+    pre[i] = prod;
+    prod = prod.mul(d);
+  }
+  S inv = prod.inv();
+  S xn = x;
+  for (int k = 0; k < logn; k++) xn = xn.sqr();
+  S nn = S::one();
+  for (int k = 0; k < logn; k++) nn = nn.dbl();
+  const S scale = xn.sub(S::one()).mul(nn.inv());
+  for (size_t i = n; i-- > 0;) {
+    const S d = x.sub(wp[i]);
+    const S di = inv.mul(pre[i]);      // 1 / (x - w^i)
+    inv = inv.mul(d);
+    out[i] = scale.mul(wp[i]).mul(di);
+  }
+  return 0;
+}
+
 extern "C" {
 
 // np/nr: 64-bit limbs of Fp/Fr; deg: 1 (coords in Fp) or 2 (Fp2 with u^2 = beta)
@@ -646,6 +698,22 @@ int orc_compute_h(const u64* r_mod, int nr, void* a, void* b, void* c, int logn,
   DISPATCH_FR(6, (compute_h<S>((S*)a, (S*)b, (S*)c, logn, *(const S*)gen_mont, *(const S*)coset_mont, nthreads), 0))
   return -1;
 }
+int orc_fr_vec(const u64* r_mod, int nr, int op, const void* a, const void* b, void* out, size_t n, int nthreads) {
+  DISPATCH_FR(4, (fr_vec<S>(op, (const S*)a, (const S*)b, (S*)out, n, nthreads)))
+  DISPATCH_FR(6, (fr_vec<S>(op, (const S*)a, (const S*)b, (S*)out, n, nthreads)))
+  return -1;
+}
+int orc_fr_geometric(const u64* r_mod, int nr, const void* start_mont, const void* ratio_mont, size_t n, void* out) {
+  DISPATCH_FR(4, (fr_geometric<S>(*(const S*)start_mont, *(const S*)ratio_mont, n, (S*)out)))
+  DISPATCH_FR(6, (fr_geometric<S>(*(const S*)start_mont, *(const S*)ratio_mont, n, (S*)out)))
+  return -1;
+}
+int orc_fr_lagrange_at(const u64* r_mod, int nr, int logn, const void* gen_mont, const void* x_mont, void* out) {
+  DISPATCH_FR(4, (fr_lagrange_at<S>(logn, *(const S*)gen_mont, *(const S*)x_mont, (S*)out)))
+  DISPATCH_FR(6, (fr_lagrange_at<S>(logn, *(const S*)gen_mont, *(const S*)x_mont, (S*)out)))
+  return -1;
+}
+
 // out = sum_i a[i]*b[i] mod r  (Montgomery in, Montgomery out) - known-dlog bookkeeping
 int orc_fr_dot(const u64* r_mod, int nr, const void* a, const void* b, size_t n, void* out) {
   DISPATCH_FR(4, ([&] { S acc = S::zero(); for (size_t i = 0; i < n; i++) acc = acc.add(((const S*)a)[i].mul(((const S*)b)[i])); *(S*)out = acc; return 0; }()))

@@ -141,3 +141,39 @@ def fr_dot(curve, a: np.ndarray, b: np.ndarray, n=None) -> int:
     assert rc == 0
     # result is Montgomery form of (sum a_m*b_m*R^-1) = (sum a*b)*R  -> canonical
     return ff.unpack_elements(out, curve.r, curve.fr_limbs)[0]
+
+
+# ---- Fr vector helpers (Montgomery limb arrays) for full-size fixtures / checks (oracle/plonk_fast.py) -------------
+def fr_vec(curve, op, a: np.ndarray, b: np.ndarray, nthreads=None) -> np.ndarray:
+    """elementwise a*b (op 0), a+b (1), a-b (2) on (n, fr_limbs) Montgomery arrays"""
+    _, rm = _mods(curve)
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    b = np.ascontiguousarray(b, dtype=np.uint64)
+    assert a.shape == b.shape
+    out = np.zeros_like(a)
+    rc = lib().orc_fr_vec(_p(rm), curve.fr_limbs, op, _p(a), _p(b), _p(out), ctypes.c_size_t(a.size // curve.fr_limbs),
+                          nthreads or default_threads())
+    assert rc == 0
+    return out
+
+
+def fr_geometric(curve, start: int, ratio: int, n: int) -> np.ndarray:
+    """[start * ratio^i for i < n] (canonical ints in, Montgomery array out)"""
+    _, rm = _mods(curve)
+    s = ff.pack_elements([start % curve.r], curve.r, curve.fr_limbs)
+    q = ff.pack_elements([ratio % curve.r], curve.r, curve.fr_limbs)
+    out = np.zeros((n, curve.fr_limbs), dtype=np.uint64)
+    rc = lib().orc_fr_geometric(_p(rm), curve.fr_limbs, _p(s), _p(q), ctypes.c_size_t(n), _p(out))
+    assert rc == 0
+    return out
+
+
+def fr_lagrange_at(curve, logn: int, x: int, generator=None) -> np.ndarray:
+    """[L_i(x) for i < 2^logn] over the domain <generator> (default: gnark-crypto's), Montgomery array"""
+    _, rm = _mods(curve)
+    g, _c = _gen_coset(curve, logn, generator, None)
+    xm = ff.pack_elements([x % curve.r], curve.r, curve.fr_limbs)
+    out = np.zeros((1 << logn, curve.fr_limbs), dtype=np.uint64)
+    rc = lib().orc_fr_lagrange_at(_p(rm), curve.fr_limbs, logn, _p(g), _p(xm), _p(out))
+    assert rc == 0
+    return out

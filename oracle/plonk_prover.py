@@ -228,15 +228,8 @@ def verify_pairing(curve, circ: Circuit, points, values, ch: Challenges, tau: in
     F1, F2 = ff.Fp(curve.p), ff.base_field(curve, 2)
     G1, G2 = curve.g1, curve.g2
     dom0 = Domain(curve, n)
-    g, w = dom0.coset_gen, dom0.generator
-    zeta, alpha, beta, gamma = ch.zeta, ch.alpha, ch.beta, ch.gamma
-    cmL, cmR, cmO, cmZ, cmH1, cmH2, cmH3, cmLin, cmBatch, cmZopen = points
-    lin_z, lz, rz, oz, s1z, s2z, zu = values[:7]
-    qcpz = list(values[7:])
-    assert len(qcpz) == len(circ.qcp) == len(bsb22_points)
+    assert len(values) - 7 == len(circ.qcp) == len(bsb22_points)
     mul = lambda k, P: ec.scalar_mul(F1, k % r, P)
-    add = lambda P, Q: ec.affine_add(F1, P, Q)
-    neg = lambda P: ec.affine_neg(F1, P)
     # verifying key
     s1, s2, s3 = sigma_polys(curve, dom0, circ.perm)
     if srs_g1 is not None:
@@ -246,9 +239,35 @@ def verify_pairing(curve, circ: Circuit, points, values, ch: Challenges, tau: in
     else:
         vk = lambda lag: mul(poly_eval(r, canonical(curve, dom0, lag), tau), G1)
         tau_g2 = ec.scalar_mul(F2, tau, G2)
-    vS1, vS2, vS3 = vk(s1), vk(s2), vk(s3)
-    vQl, vQr, vQm, vQo, vQk = vk(circ.ql), vk(circ.qr), vk(circ.qm), vk(circ.qo), vk(circ.qk)
-    vQcp = [vk(q_) for q_ in circ.qcp]
+    key = {"S1": vk(s1), "S2": vk(s2), "S3": vk(s3), "Ql": vk(circ.ql), "Qr": vk(circ.qr), "Qm": vk(circ.qm),
+           "Qo": vk(circ.qo), "Qk": vk(circ.qk), "Qcp": [vk(q_) for q_ in circ.qcp]}
+    T = pairing.get(curve)
+    opening = lambda lhs, H: T.product_is_one([(lhs, G2), (ec.affine_neg(F1, H), tau_g2)])
+    return verify_core(curve, n, key, points, values, ch, opening, bsb22_points)
+
+
+def verify_core(curve, n, key, points, values, ch: Challenges, opening, bsb22_points=()) -> bool:
+    """The verifier proper (backend/plonk/bn254/verify.go:38-320) from a verifying KEY given as points
+    (key: S1 S2 S3 Ql Qr Qm Qo Qk as affine G1 points, Qcp a list) - what Setup hands a verifier - so that it can run at
+    sizes where deriving the key from the circuit in Python is not affordable (oracle/plonk_fast.py derives it with the
+    C++ oracle).  opening(lhs, H) -> bool decides one KZG opening equation  e(lhs, [1]_2) == e(H, [tau]_2):
+    with real pairings (verify_pairing) or, when the trapdoor is known, as lhs == tau * H."""
+    from . import ec, ff
+    r = curve.r
+    F1 = ff.Fp(curve.p)
+    G1 = curve.g1
+    dom0 = Domain(curve, n)
+    g, w = dom0.coset_gen, dom0.generator
+    zeta, alpha, beta, gamma = ch.zeta, ch.alpha, ch.beta, ch.gamma
+    cmL, cmR, cmO, cmZ, cmH1, cmH2, cmH3, cmLin, cmBatch, cmZopen = points
+    lin_z, lz, rz, oz, s1z, s2z, zu = values[:7]
+    qcpz = list(values[7:])
+    mul = lambda k, P: ec.scalar_mul(F1, k % r, P)
+    add = lambda P, Q: ec.affine_add(F1, P, Q)
+    neg = lambda P: ec.affine_neg(F1, P)
+    vS1, vS2, vS3 = key["S1"], key["S2"], key["S3"]
+    vQl, vQr, vQm, vQo, vQk = key["Ql"], key["Qr"], key["Qm"], key["Qo"], key["Qk"]
+    vQcp = list(key.get("Qcp", ()))
     # 1. the opened value of the linearised polynomial (verify.go: the constant part moved to the right-hand side)
     zn = pow(zeta, n, r)
     zh = (zn - 1) % r
@@ -279,12 +298,11 @@ def verify_pairing(curve, circ: Circuit, points, values, ch: Challenges, tau: in
         Fd = add(Fd, mul(vp, D))
         fz = (fz + vp * cval) % r
         vp = vp * ch.v % r
-    T = pairing.get(curve)
     lhs = add(add(Fd, neg(mul(fz, G1))), mul(zeta, cmBatch))
-    if not T.product_is_one([(lhs, G2), (neg(cmBatch), tau_g2)]):
+    if not opening(lhs, cmBatch):
         return False
     lhs = add(add(cmZ, neg(mul(zu, G1))), mul(zeta * w, cmZopen))
-    return T.product_is_one([(lhs, G2), (neg(cmZopen), tau_g2)])
+    return opening(lhs, cmZopen)
 
 
 def random_satisfied_instance(curve, n, seed, n_commit=0):

@@ -181,7 +181,7 @@ static int32_t table_upload(int32_t dev, int32_t curve, int32_t group, const voi
   *out = t;
   return 0;
 }
-static int32_t table_free(b200_table_t t) { if (t) { free(t->d_points); delete t; } return 0; }
+static int32_t table_free(b200_table_t t) { if (t) { free(t->d_points); t->d_points = nullptr; delete t; } return 0; }
 // sum s_i P_i by double-and-add (small n)
 static int32_t msm_g1(b200_table_t t, size_t off, size_t n, const void* scalars, int32_t, void* out) {
   if (off + n > t->n) return set_error("mock: msm range");

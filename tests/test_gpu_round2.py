@@ -1,0 +1,197 @@
+"""GPU tests of the round-2 entry points: the library's own communicator + device-side combine (comm.cu),
+b200_msm_submit_dev, the PLONK prover at large sizes checked by the verifier's equations, concurrent Groth16 proofs on
+one key, the 2^31-entry guard."""
+import random
+import threading
+
+import numpy as np
+import pytest
+
+from oracle import ec, ff
+from oracle.params import CURVES
+from util import jac_to_affine, known_dlog_instance
+
+pytestmark = pytest.mark.gpu
+
+
+def test_points_allreduce_without_communicator_is_a_copy(gpu):
+    import torch
+    c = CURVES["bn254"]
+    assert gpu.comm_info(0) == (1, 0)
+    src = torch.arange(5 * 12, dtype=torch.int64, device="cuda")
+    dst = torch.zeros_like(src)
+    torch.cuda.synchronize()
+    gpu.points_allreduce(0, c.curve_id, 1, src, 5, dst)
+    gpu.sync(0)
+    assert torch.equal(src, dst)
+
+
+@pytest.mark.parametrize("cname,group", [("bn254", 1), ("bn254", 2), ("bls12-381", 1), ("bw6-761", 1)])
+def test_fold_kernel_sums_partials(gpu, cname, group):
+    """b200_points_fold (the kernel half of b200_points_allreduce) on one device: `world` rows of partial MSM results
+    gathered by hand, empty ranges (the point at infinity) among them, against host-side additions"""
+    import torch
+    c = CURVES[cname]
+    world, count, n = 3, 4, 300
+    F, base, pts, sc, _ = known_dlog_instance(c, group, n, seed=5)
+    t = gpu.Table(c.curve_id, group, pts, precomp=False)
+    L = c.fr_limbs
+    rows, want = [], []
+    rng = random.Random(4)
+    scl = ff.unpack_elements(sc, c.r, L)
+    for r in range(world):
+        row = []
+        for k in range(count):
+            lo = rng.randrange(0, n - 40)
+            cnt = rng.randrange(0, 40)        # includes empty ranges: the point at infinity as a partial
+            row.append(t.msm(np.ascontiguousarray(sc.reshape(n, L)[lo:lo + cnt]), off=lo, n=cnt))
+        rows.append(row)
+    g = torch.from_numpy(np.stack([np.stack(r_) for r_ in rows]).view(np.int64)).cuda()
+    out = torch.zeros((count, rows[0][0].size), dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
+    gpu.points_fold(0, c.curve_id, group, g, world, count, out)
+    gpu.sync(0)
+    for k in range(count):
+        acc = rows[0][k].copy()
+        for r in range(1, world):
+            gpu.point_add_jac(c.curve_id, group, acc, rows[r][k])
+        assert jac_to_affine(c, group, out[k].cpu().numpy().view(np.uint64)) == jac_to_affine(c, group, acc)
+    t.free()
+
+
+def test_msm_submit_dev_and_allreduce_single_device(gpu):
+    import torch
+    c = CURVES["bn254"]
+    n = 5000
+    F, base, pts, sc, expected = known_dlog_instance(c, 1, n, seed=31)
+    t = gpu.Table(c.curve_id, 1, pts, precomp=True)
+    h_sc = torch.from_numpy(sc.view(np.int64).copy()).pin_memory()
+    K = 4
+    d_out = torch.zeros((K, 12), dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
+    for i in range(K):
+        t.msm_submit_dev(h_sc, d_out[i], n=n)
+    gpu.sync(0)
+    for i in range(K):
+        assert jac_to_affine(c, 1, d_out[i].cpu().numpy().view(np.uint64)) == expected
+    assert jac_to_affine(c, 1, t.msm_allreduce(sc, n=n)) == expected          # no communicator: b200_msm
+    t.free()
+
+
+def test_two_devices_one_process_allreduce(gpu):
+    """b200_comm_init_all + b200_msm_allreduce from one thread per device (the Go shape: a goroutine per device):
+    both devices end up with the sum of the two shards"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs at least two GPUs")
+    c = CURVES["bn254"]
+    n = 4096
+    F, base, pts, sc, expected = known_dlog_instance(c, 1, n, seed=32)
+    gpu.init([0, 1])
+    gpu.comm_init_all([0, 1])
+    per = 2 * c.fp_limbs
+    P, S = pts.reshape(n, per), sc.reshape(n, c.fr_limbs)
+    half = n // 2
+    tabs = [gpu.Table(c.curve_id, 1, np.ascontiguousarray(P[d * half:(d + 1) * half]), dev=d, precomp=True) for d in (0, 1)]
+    res, errs = [None, None], [None, None]
+
+    def run(d):
+        try:
+            res[d] = tabs[d].msm_allreduce(np.ascontiguousarray(S[d * half:(d + 1) * half]), n=half)
+        except Exception as e:
+            errs[d] = e
+    th = [threading.Thread(target=run, args=(d,)) for d in (0, 1)]
+    [x.start() for x in th]
+    [x.join(timeout=120) for x in th]
+    assert errs == [None, None], errs
+    for d in (0, 1):
+        assert jac_to_affine(c, 1, res[d]) == expected
+        tabs[d].free()
+    gpu.comm_destroy(0)
+    gpu.comm_destroy(1)
+
+
+@pytest.mark.parametrize("cname,logn", [("bls12-381", 16), ("bls12-381", 20), ("bn254", 18)])
+def test_plonk_prove_large_verifies(gpu, cname, logn):
+    """b200_plonk_prove on a satisfied 2^logn-gate instance with a trapdoor SRS; the ten points and seven values pass the
+    verifier's equations (oracle/plonk_fast.py: verifying key from the C++ oracle, openings by the trapdoor identity AND
+    by real pairings); a proof of a DIFFERENT witness column does not.  bench.py runs the same at 2^22 (config 4)."""
+    from oracle import plonk_fast
+    c = CURVES[cname]
+    inst = plonk_fast.satisfied_instance(c, logn, seed=logn)
+    assert plonk_fast.check_satisfied(inst)
+    srs = plonk_fast.trapdoor_srs_gpu(gpu, c, inst)
+    key = gpu.PlonkKey(c.curve_id, logn, inst.ql, inst.qr, inst.qm, inst.qo, inst.qk, inst.perm, srs)
+    pts, vals = key.prove(inst.l, inst.r, inst.o, *inst.challenges_packed())
+    st = key.last_stage_ms()
+    assert set(st) == set(gpu.PlonkKey.STAGES) and all(v > 0 for v in st.values())
+    assert plonk_fast.verify(c, inst, pts, vals, with_pairing=(logn <= 16))
+    bad_o = inst.o.copy()
+    bad_o[7] = inst.o[8]
+    pts2, vals2 = key.prove(inst.l, inst.r, bad_o, *inst.challenges_packed())
+    assert not plonk_fast.verify(c, inst, pts2, vals2, with_pairing=False)
+    key.free()
+
+
+def test_plonk_rejects_tiny_domains(gpu):
+    c = CURVES["bn254"]
+    z = np.zeros((4, c.fr_limbs), dtype=np.uint64)
+    with pytest.raises(gpu.B200Error):
+        gpu.PlonkKey(c.curve_id, 2, z, z, z, z, z, np.arange(12, dtype=np.int64), np.zeros((7, 2 * c.fp_limbs), dtype=np.uint64))
+
+
+def test_concurrent_groth16_proofs_on_one_key(gpu):
+    """two host threads prove on the SAME device-resident key at once (goroutines in the Go shim): no per-key lock, calls
+    are ordered by the device context's lock and every proof has its own stream-ordered buffers; both proofs equal the
+    single-threaded ones"""
+    from gnark_b200 import groth16 as b200
+    from oracle import groth16 as g16
+    from util import build_groth16_pk, pack_solution
+    c = CURVES["bn254"]
+    cs, W = g16.square_chain_r1cs(500), g16.square_chain_witness(c.r, 500)
+    pk, pkd, _, _ = build_groth16_pk(c, cs, g16.random_toxic(c, 9), 9)
+    sol = pack_solution(c, cs, W)
+    rs = [[11, 12], [13, 14]]
+
+    def prove(k):
+        it = iter(rs[k])
+        return b200.ProveSolution(pk, sol, b200.WithDeviceID(0), b200.WithRandomness(lambda q: next(it)))
+    want = [prove(0), prove(1)]
+    got, errs = [None, None], [None, None]
+
+    def run(k):
+        try:
+            for _ in range(3):
+                got[k] = prove(k)
+        except Exception as e:
+            errs[k] = e
+    th = [threading.Thread(target=run, args=(k,)) for k in (0, 1)]
+    [x.start() for x in th]
+    [x.join(timeout=300) for x in th]
+    assert errs == [None, None], errs
+    for k in (0, 1):
+        for f in ("Ar", "Bs", "Krs"):
+            assert np.array_equal(getattr(got[k], f), getattr(want[k], f)), (k, f)
+    pk.free_gpu_resources()
+
+
+def test_msm_entry_count_guard(gpu):
+    """a plain (not precomputed) table whose n * windows reaches 2^31 is refused with an error instead of overflowing the
+    31-bit entry counts of the sort: 2^27 points x 16 windows, the check precedes every allocation"""
+    import torch
+    c = CURVES["bn254"]
+    n = 1 << 27
+    d_pts = torch.zeros((n, 8), dtype=torch.int64, device="cuda")          # 8 GiB of points at infinity
+    torch.cuda.synchronize()
+    t = gpu.Table(c.curve_id, 1, d_pts, precomp=False, n=n, on_device=True)
+    del d_pts
+    assert t.info()["n_windows"] * n >= 1 << 31
+    d_sc = torch.zeros(4, dtype=torch.int64, device="cuda")
+    with pytest.raises(gpu.B200Error, match="2\\^31"):
+        t.msm(d_sc, n=n, on_device=True)
+    # a sub-range below the limit still works (all bases are the point at infinity: the sum is infinity, Z = 0)
+    d_sc = torch.zeros((1 << 20) * 4, dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
+    out = t.msm(d_sc, n=1 << 20, on_device=True)
+    assert not out[8:].any()
+    t.free()

@@ -135,8 +135,6 @@ def test_cuda_reproduces_intree_known_answers(gpu, cname, group):
         t.free()
 
 
-@pytest.mark.xfail(strict=False, reason="orchestrator written after this round's GPU budget was spent: every C-ABI "
-                   "building block it calls is validated above, the end-to-end sequence has not run on hardware yet")
 @pytest.mark.parametrize("c", [CURVES["bn254"], CURVES["bls12-381"]], ids=lambda c: c.name)
 @pytest.mark.parametrize("logn", (4, 6))
 def test_full_prover_vs_oracle(gpu, c, logn):
@@ -175,8 +173,6 @@ def test_full_prover_vs_oracle(gpu, c, logn):
     pk.free()
 
 
-@pytest.mark.xfail(strict=False, reason="C++ orchestration (plonk_host.cu) written after this round's GPU budget was spent: a "
-                   "translation of gnark_b200/plonk.py, whose algebra is pinned on the CPU (tests/test_plonk_orchestration.py)")
 @pytest.mark.parametrize("c", [CURVES["bn254"], CURVES["bls12-381"]], ids=lambda c: c.name)
 @pytest.mark.parametrize("logn", (4, 6))
 def test_plonk_prove_c_abi_vs_oracle(gpu, c, logn):
@@ -210,7 +206,6 @@ def test_plonk_prove_c_abi_vs_oracle(gpu, c, logn):
     key.free()
 
 
-@pytest.mark.xfail(strict=False, reason="see test_plonk_prove_c_abi_vs_oracle")
 def test_plonk_proof_over_the_ethereum_srs_verifies(gpu):
     """No trapdoor anywhere: b200_plonk_prove commits with the Ethereum KZG ceremony SRS the reference ships (tau unknown,
     2051 of its 4096 G1 points, n = 2^11) and the proof is checked by the verifier's pairing equations with the fixture's
@@ -243,8 +238,6 @@ def test_plonk_proof_over_the_ethereum_srs_verifies(gpu):
     assert not pp.verify_pairing(c, circ, proof_pts, got, ch, srs_g1=mono, tau_g2=g2[2], msm=cpp_msm)
 
 
-@pytest.mark.xfail(strict=False, reason="BSB22 commitment gates written after this round's GPU budget was spent; pinned on the "
-                   "CPU by tests/test_plonk_host_cpu.py::test_plonk_host_bsb22_commitments and the emulation tests")
 @pytest.mark.parametrize("n_commit", (1, 2))
 def test_plonk_prove_bsb22(gpu, n_commit):
     """b200_plonk_prove on a key with BSB22 commitment gates against the oracle prover: digests (incl. [PI2_j]) and the
@@ -279,7 +272,6 @@ def test_plonk_prove_bsb22(gpu, n_commit):
     key.free()
 
 
-@pytest.mark.xfail(strict=False, reason="see test_plonk_prove_bsb22")
 @pytest.mark.parametrize("cname", ["bn254", "bls12-381"])
 def test_plonk_prove_reproduces_golden(gpu, cname):
     """the committed PLONK known-answer vector (tests/golden/kat_plonk_v1.json) through b200_plonk_prove on the GPU"""
@@ -305,8 +297,6 @@ def test_plonk_prove_reproduces_golden(gpu, cname):
     key.free()
 
 
-@pytest.mark.xfail(strict=False, reason="K-wire filtering for keys with BSB22 commitments written after this round's GPU budget "
-                   "was spent (same gather kernel as the validated A / B wire filters)")
 def test_groth16_committed_wires_filtered_from_k(gpu):
     """Groth16 keys with Pedersen/BSB22 commitments: the committed private wires have no base in G1.K and are
     dropped from the Krs scalars (filterHeap, prove.go:231-239,321-344).  The K MSM must equal
@@ -343,7 +333,6 @@ def test_groth16_committed_wires_filtered_from_k(gpu):
     pk2.free_gpu_resources()
 
 
-@pytest.mark.xfail(strict=False, reason="full-size identity test written after this round's GPU budget was spent (validated kernels)")
 @pytest.mark.parametrize("cname,logn", [("bn254", 22), ("bls12-381", 24)])
 def test_ntt_full_size_identities(gpu, cname, logn):
     """SURVEY.md §8c-4 at BASELINE sizes (2^22, 2^24), where no CPU oracle run is affordable: the inverse transform
@@ -363,6 +352,10 @@ def test_ntt_full_size_identities(gpu, cname, logn):
     rng = random.Random(8)
     for on_coset in (False, True):
         y = x.clone()
+        # the library runs on its own non-blocking stream (no b200_set_stream here): torch's producer kernels must have
+        # finished before it reads y.  Round 1's failure of [bls12-381-24] was this race in the TEST (the 512 MiB clone
+        # was still in flight when the first NTT pass started), not a kernel fault - see test_ntt_large_vs_cpp_oracle.
+        torch.cuda.synchronize()
         d.ntt_async(y, inverse=False, decimation=gpu.DIF, on_coset=on_coset)      # natural -> bit-reversed
         gpu.sync(0)
         for _ in range(3):
@@ -378,8 +371,24 @@ def test_ntt_full_size_identities(gpu, cname, logn):
     d.free()
 
 
-@pytest.mark.xfail(strict=False, reason="written after this round's GPU budget was spent; the decomposition is pinned on the "
-                   "CPU over gloo (tests/test_dist.py::test_sharded_ntt_gloo)")
+@pytest.mark.parametrize("cname,logn", [("bls12-381", 22), ("bls12-381", 24), ("bn254", 24)])
+def test_ntt_large_vs_cpp_oracle(gpu, cname, logn):
+    """three-pass plans (2^22: PLONK config 4's domain, 2^24: its 4n quotient domain) limb for limb against the
+    multi-threaded C++ oracle, forward DIF plain and inverse DIT on the coset, host buffers through b200_ntt"""
+    from oracle import corelib
+    c = CURVES[cname]
+    n = 1 << logn
+    rs = np.random.RandomState(logn)
+    a = rs.randint(0, 1 << 62, size=(n, c.fr_limbs), dtype=np.int64).astype(np.uint64)
+    a[:, -1] &= np.uint64((1 << 56) - 1)
+    d = gpu.Domain(c.curve_id, logn)
+    for inv, dec, cos in ((False, gpu.DIF, False), (True, gpu.DIT, True)):
+        want = corelib.ntt(c, a.copy(), logn, inv, dec, cos)
+        got = d.ntt(a.copy(), inverse=inv, decimation=dec, on_coset=cos)
+        assert np.array_equal(got, want), (cname, logn, inv, dec, cos)
+    d.free()
+
+
 def test_sharded_ntt_single_rank(gpu):
     """gnark_b200/parallel_ntt.py with world = 1 on the GPU: no exchange, but the stream scoping, the local
     transform + bit reversal and the coset scaling are the ones every rank runs (multi-rank: tools/bench_sharded_ntt.py)"""
@@ -405,7 +414,6 @@ def test_sharded_ntt_single_rank(gpu):
     sd.free()
 
 
-@pytest.mark.xfail(strict=False, reason="entry point written after this round's GPU budget was spent")
 def test_msm_submit_stream_of_msms(gpu):
     """b200_msm_submit: a stream of MSMs from pinned host buffers (different scalars, different ranges), results
     after b200_sync, each against the known-dlog oracle"""
@@ -435,8 +443,6 @@ def test_msm_submit_stream_of_msms(gpu):
     t.free()
 
 
-@pytest.mark.xfail(strict=False, reason="entry point written after this round's GPU budget was spent; the per-thread "
-                   "functions are pinned on the CPU by tests/test_emulation.py::test_fixed_base_batch_logic")
 @pytest.mark.parametrize("c", ALL, ids=lambda c: c.name)
 @pytest.mark.parametrize("group", (1, 2))
 def test_fixed_base_batch(gpu, c, group):
@@ -462,8 +468,6 @@ def test_fixed_base_batch(gpu, c, group):
     assert ec.unpack_points(c, group, got)[2] == ec.scalar_mul(F, c.r - 1, base)
 
 
-@pytest.mark.xfail(strict=False, reason="entry point written after this round's GPU budget was spent; the host half (file_stage.h) is "
-                   "pinned on the CPU by tests/test_abi.py::test_file_staging_of_dump_slices")
 def test_tables_straight_from_a_dump_file(gpu, tmp_path):
     """b200_table_upload_file and the dump_path form of b200_groth16_pk_load: point slices written the
     way ProvingKey.WriteDump writes them (8-byte little-endian length, then the raw memory image) are read from the file
@@ -514,8 +518,6 @@ def test_tables_straight_from_a_dump_file(gpu, tmp_path):
     pk.free_gpu_resources()
 
 
-@pytest.mark.xfail(strict=False, reason="one-process multi-GPU path written after this round's GPU budget was spent; its host logic "
-                   "is pinned on the CPU by tests/test_groth16_host_logic.py")
 def test_groth16_with_devices_in_one_process(gpu):
     """WithDevices: every visible GPU holds one point-range shard of the key, the device parts run concurrently from
     one process (what a Go caller does with a goroutine per device); the proof must equal the single-device proof."""
@@ -539,8 +541,6 @@ def test_groth16_with_devices_in_one_process(gpu):
 
 
 @experiment
-@pytest.mark.xfail(strict=False, reason="opt-in experiment written after this round's GPU budget was spent; both kernels "
-                   "and the split geometry are validated separately, the concurrent launch is not yet")
 @pytest.mark.parametrize("cname", ["bn254", "bls12-381"])
 @pytest.mark.parametrize("pct", [30, 70])
 def test_msm_hybrid_accumulate(gpu, monkeypatch, cname, pct):
@@ -561,8 +561,6 @@ def test_msm_hybrid_accumulate(gpu, monkeypatch, cname, pct):
 
 
 @experiment
-@pytest.mark.xfail(strict=False, reason="opt-in experiment written after this round's GPU budget was spent; per-thread logic "
-                   "pinned by tests/test_emulation.py::test_msm_batched_affine_levels_logic")
 @pytest.mark.parametrize("cname,group", [("bn254", 1), ("bn254", 2), ("bls12-381", 1), ("bw6-761", 1)])
 @pytest.mark.parametrize("levels", [1, 4])
 def test_msm_batched_affine_levels(gpu, monkeypatch, cname, group, levels):
@@ -580,7 +578,6 @@ def test_msm_batched_affine_levels(gpu, monkeypatch, cname, group, levels):
 
 
 @experiment
-@pytest.mark.xfail(strict=False, reason="opt-in upload path written after this round's GPU budget was spent")
 def test_groth16_threaded_staging_of_pageable_inputs(gpu):
     """GB200_STAGE_THREADS: W, A, B, C uploaded from pageable memory through two pinned slots filled by several
     threads; the proof must be identical to the plain path (domain 2^18 so that the vectors exceed the 4 MiB
@@ -623,8 +620,6 @@ print("EQUAL" if np.array_equal(outs[0], outs[1]) else "DIFFERENT")
 
 
 @experiment
-@pytest.mark.xfail(strict=False, reason="opt-in experiment written after this round's GPU budget was spent; per-thread logic "
-                   "pinned by tests/test_emulation.py::test_msm_persistent_accumulate_logic")
 @pytest.mark.parametrize("cname,group", [("bn254", 1), ("bn254", 2), ("bls12-381", 1), ("bw6-761", 1)])
 @pytest.mark.parametrize("mode", ["1", "2"])
 def test_msm_persistent_accumulate(gpu, monkeypatch, cname, group, mode):
@@ -642,8 +637,6 @@ def test_msm_persistent_accumulate(gpu, monkeypatch, cname, group, mode):
 
 
 @experiment
-@pytest.mark.xfail(strict=False, reason="opt-in experiment written after this round's GPU budget was spent; thread mapping pinned "
-                   "by tests/test_emulation.py::test_ntt_register_rounds")
 @pytest.mark.parametrize("cname", ["bn254", "bw6-761"])
 def test_ntt_register_rounds(gpu, monkeypatch, cname):
     """opt-in GB200_NTT_RADIX8: k_ntt_pass_r8 (up to three stages per shared-memory exchange, groups of 8 elements in
@@ -667,8 +660,6 @@ def test_ntt_register_rounds(gpu, monkeypatch, cname):
 
 
 @experiment
-@pytest.mark.xfail(strict=False, reason="opt-in experiment written after this round's GPU budget was spent; per-thread logic "
-                   "pinned by tests/test_emulation.py::test_msm_shared_memory_accumulator_logic")
 @pytest.mark.parametrize("cname,group", [("bn254", 2), ("bls12-381", 1), ("bls12-381", 2), ("bw6-761", 1), ("bn254", 1)])
 def test_msm_shared_memory_accumulator(gpu, monkeypatch, cname, group):
     """opt-in GB200_MSM_SMEM_ACC: XYZZ accumulators in shared memory (more resident warps for the wide fields); known-dlog

@@ -72,6 +72,11 @@ class FakeLib:
     def check(rc):
         assert rc == 0
 
+    comm = (1, 0)                                # (world, rank) of the library's communicator; (1, 0) = none
+
+    def comm_info(self, dev):
+        return self.comm
+
     @staticmethod
     def point_add_jac(curve, group, acc, q):
         acc[0] += q[0]                           # "group addition" of the recognisable partials
@@ -161,3 +166,12 @@ def test_with_sharding_gathers_and_folds_over_gloo():
     ret = mp.Manager().dict()
     mp.spawn(_sharded_worker, args=(world, port, ret), nprocs=world, join=True)
     assert all(ret[r] for r in range(world))
+
+
+def test_with_sharding_and_a_library_communicator_proves_in_one_call(fake):
+    """b200_comm_init done (comm_info reports the shard world): the partial sums are combined on the device inside
+    b200_groth16_prove - no process group, no host-side fold"""
+    fake.comm = (4, 2)
+    pk, sol = make_key_and_solution()
+    b200.ProveSolution(pk, sol, b200.WithDeviceID(0), b200.WithSharding(2, 4), b200.WithRandomness(lambda q: 7))
+    assert fake.c.calls == [("load", 0, 2, 4), ("prove", 0)]
