@@ -73,14 +73,14 @@ void comm_teardown(DeviceCtx& c) {
 // gather + fold of `count` Jacobian points on ctx->stream; d_partials and d_totals may alias
 int32_t points_allreduce_on_stream(DeviceCtx* ctx, const MsmOps* ops, const void* d_partials, size_t count, void* d_totals) {
   if (count == 0) return 0;
+  int32_t rc = msm_join(ctx);           // partial results may still be in flight on the tail stream
+  if (rc) return rc;
   if (!ctx->comm || ctx->comm_world <= 1) {
     if (d_totals != d_partials)
       CK(cudaMemcpyAsync(d_totals, d_partials, count * ops->jac_bytes, cudaMemcpyDeviceToDevice, ctx->stream));
     return 0;
   }
   NcclApi* api = nccl_api();
-  int32_t rc = msm_join(ctx);           // partial results may still be in flight on the tail stream
-  if (rc) return rc;
   AsyncBuf gathered;
   CK(gathered.alloc((size_t)ctx->comm_world * count * ops->jac_bytes, ctx->stream));
   NCK(api, api->AllGather(d_partials, gathered.p, count * ops->jac_bytes, ncclUint8, reinterpret_cast<ncclComm_t>(ctx->comm),

@@ -39,6 +39,7 @@ def main():
     t = lib.Table(c.curve_id, group, pts, precomp=True)
     d_sc = torch.from_numpy(sc.view(np.int64)).cuda()
     d_out = torch.zeros(3 * t.coord_limbs, dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()      # the library runs on its own stream: torch's uploads must have landed
     for _ in range(2):
         t.msm_async(d_sc, d_out, n=n)
     lib.sync(0)
