@@ -37,6 +37,7 @@ EXPORTS = [
     "b200_plonk_quotient", "b200_plonk_linearise", "b200_plonk_batch_open", "b200_plonk_end", "b200_plonk_bsb22_coset",
     "b200_comm_unique_id", "b200_comm_init", "b200_comm_init_all", "b200_comm_destroy", "b200_comm_info",
     "b200_points_allreduce", "b200_msm_allreduce", "b200_msm_submit_dev", "b200_plonk_last_stage_ms", "b200_points_fold",
+    "b200_msm_gather", "b200_pedersen_key_load", "b200_pedersen_key_free", "b200_pedersen_commit", "b200_pedersen_fold",
 ]
 COMM_ID_BYTES = 128
 
@@ -146,6 +147,12 @@ def load(path: str = None):
         lib.b200_points_allreduce.argtypes = [i32, i32, i32, vp, sz, vp]
         lib.b200_msm_allreduce.argtypes = [vp, sz, sz, vp, i32, vp]
         lib.b200_msm_submit_dev.argtypes = [vp, sz, sz, vp, vp]
+    if "b200_msm_gather" not in missing:
+        lib.b200_msm_gather.argtypes = [vp, sz, vp, sz, i32, vp, sz, i32, vp]
+        lib.b200_pedersen_key_load.argtypes = [i32, i32, vp, vp, sz, ctypes.POINTER(vp)]
+        lib.b200_pedersen_key_free.argtypes = [vp]
+        lib.b200_pedersen_commit.argtypes = [vp, vp, sz, i32, vp, vp]
+        lib.b200_pedersen_fold.argtypes = [i32, vp, sz, vp, vp]
     if "b200_points_fold" not in missing:
         lib.b200_points_fold.argtypes = [i32, i32, i32, vp, u32, u32, vp]
     if "b200_plonk_last_stage_ms" not in missing:
@@ -342,6 +349,19 @@ class Table:
         check(load().b200_msm_allreduce(self.handle, off, n, ptr(scalars), 1 if on_device else 0, ptr(out)))
         return out
 
+    def msm_gather(self, idx, scalars, off: int = 0) -> np.ndarray:
+        """sum_j scalars[idx[j]] * bases[off + j] (wire filtering on the device); idx: uint32 host array or int32/uint32
+        device tensor, scalars: the full wire vector (host array or device tensor)"""
+        idx_dev, sc_dev = hasattr(idx, "data_ptr"), hasattr(scalars, "data_ptr")
+        n_idx = idx.numel() if idx_dev else idx.size
+        n_sc = (scalars.numel() if sc_dev else scalars.size) // self.fr_limbs
+        if not idx_dev:
+            idx = np.ascontiguousarray(idx, dtype=np.uint32)
+        out = np.zeros(3 * self.coord_limbs, dtype=np.uint64)
+        check(load().b200_msm_gather(self.handle, off, ptr(idx), n_idx, 1 if idx_dev else 0, ptr(scalars), n_sc,
+                                     1 if sc_dev else 0, ptr(out)))
+        return out
+
     def msm_async(self, d_scalars, d_out, off: int = 0, n: int = None):
         check(load().b200_msm_async(self.handle, off, n, ptr(d_scalars), ptr(d_out)))
 
@@ -502,6 +522,52 @@ class PlonkKey:
             self.free()
         except Exception:
             pass
+
+
+class PedersenKey:
+    """device-resident pedersen.ProvingKey{Basis, BasisExpSigma} of one Groth16 commitment (ProvingKey.CommitmentKeys[i])"""
+
+    def __init__(self, curve: int, basis, basis_exp_sigma, dev: int = 0):
+        self.curve, self.dev = curve, dev
+        self.fr_limbs, self.fp_limbs, _ = CURVE_SHAPES[curve]
+        basis = np.ascontiguousarray(basis, dtype=np.uint64)
+        sig = np.ascontiguousarray(basis_exp_sigma, dtype=np.uint64)
+        self.n = basis.size // (2 * self.fp_limbs)
+        if sig.size != basis.size:
+            raise ValueError("Basis and BasisExpSigma differ in length")
+        h = ctypes.c_void_p(0)
+        check(load().b200_pedersen_key_load(dev, curve, ptr(basis), ptr(sig), self.n, ctypes.byref(h)))
+        self.handle = h
+
+    def commit(self, values, want_commitment=True, want_pok=True):
+        """(commitment, pok) as G1Affine limb arrays (None for the one not asked for): Commit (prove.go:84) and
+        ProveKnowledge (prove.go:114) over one upload of the values"""
+        on_dev = hasattr(values, "data_ptr")
+        n = (values.numel() if on_dev else values.size) // self.fr_limbs
+        cm = np.zeros(2 * self.fp_limbs, dtype=np.uint64) if want_commitment else None
+        pok = np.zeros(2 * self.fp_limbs, dtype=np.uint64) if want_pok else None
+        check(load().b200_pedersen_commit(self.handle, ptr(values), n, 1 if on_dev else 0, ptr(cm), ptr(pok)))
+        return cm, pok
+
+    def free(self):
+        if self.handle:
+            check(load().b200_pedersen_key_free(self.handle))
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def pedersen_fold(curve: int, poks: np.ndarray, challenge: np.ndarray) -> np.ndarray:
+    """ProofOfKnowledge.Fold (prove.go:127): sum_i challenge^i * poks[i]; host CPU"""
+    fpl = CURVE_SHAPES[curve][1]
+    poks = np.ascontiguousarray(poks, dtype=np.uint64)
+    out = np.zeros(2 * fpl, dtype=np.uint64)
+    check(load().b200_pedersen_fold(curve, ptr(poks), poks.size // (2 * fpl), ptr(challenge), ptr(out)))
+    return out
 
 
 def point_add_jac(curve: int, group: int, acc: np.ndarray, q: np.ndarray) -> np.ndarray:

@@ -158,6 +158,30 @@ int32_t b200_points_fold(int32_t dev, int32_t curve, int32_t group, const void* 
 int32_t b200_msm_allreduce(b200_table_t bases, size_t off, size_t n, const void* scalars_mont, int32_t scalars_on_device,
                            void* out_jac_host);
 
+/* ---- witness-side MSMs ----------------------------------------------------------------
+ * gather-index MSM: sum_j scalars[idx[j]] * bases[off + j], j < n_idx.  The table holds the bases that are not the
+ * point at infinity; idx lists the wires they belong to, so the solver's wire vector is used as is - replaces the
+ * filtered copies of backend/groth16/bn254/prove.go:147-168 ("worst memory allocation offender", :232; GPU twin
+ * icicle.go:1018-1070).  idx / scalars: host or device memory. */
+int32_t b200_msm_gather(b200_table_t bases, size_t off, const uint32_t* idx, size_t n_idx, int32_t idx_on_device,
+                        const void* scalars_mont, size_t n_scalars, int32_t scalars_on_device, void* out_jac_host);
+
+/* Pedersen / BSB22 commitment keys (gnark-crypto pedersen.ProvingKey{Basis, BasisExpSigma}, one per commitment:
+ * ProvingKey.CommitmentKeys, backend/groth16/bn254/setup.go:46).  b200_pedersen_commit runs
+ *   commitment = sum_i values[i] * Basis[i]            (pk.CommitmentKeys[i].Commit,         prove.go:84, inside the solver hint)
+ *   pok        = sum_i values[i] * BasisExpSigma[i]    (pk.CommitmentKeys[i].ProveKnowledge, prove.go:114)
+ * over ONE upload of the values (either output may be NULL); results are G1Affine in gnark layout.  n must equal the
+ * basis length (gnark-crypto returns an error otherwise).  b200_pedersen_fold is ProofOfKnowledge.Fold (prove.go:127):
+ * sum_i challenge^i * poks[i], host CPU.  Hashing the commitment into the hint's output (prove.go:90-98) stays in Go. */
+typedef struct b200_pedersen_key_s* b200_pedersen_key_t;
+int32_t b200_pedersen_key_load(int32_t dev, int32_t curve, const void* basis_affine, const void* basis_exp_sigma_affine,
+                               size_t n, b200_pedersen_key_t* out);
+int32_t b200_pedersen_key_free(b200_pedersen_key_t key);
+int32_t b200_pedersen_commit(b200_pedersen_key_t key, const void* values_mont, size_t n, int32_t values_on_device,
+                             void* out_commitment_affine, void* out_pok_affine);
+int32_t b200_pedersen_fold(int32_t curve, const void* poks_affine, size_t count, const void* challenge_mont,
+                           void* out_affine);
+
 /* fixed-base batch: out[i] = scalars[i] * base, n affine points in gnark layout (replaces gnark-crypto's
  * curve.BatchScalarMultiplicationG1/G2 as called by Groth16 Setup, backend/groth16/bn254/setup.go:233,302,
  * and by the SRS generators test/unsafekzg/kzgsrs.go:198 - SURVEY.md §8(f)-3).  base_affine: ONE point on the

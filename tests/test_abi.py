@@ -94,3 +94,25 @@ def test_file_staging_of_dump_slices(hostemu, tmp_path):
     out = np.zeros(2000, dtype=np.uint8)
     assert hostemu.emu_stage_file(path, 99_000, 2000, 512, out.ctypes.data) == -2         # range exceeds the file
     assert hostemu.emu_stage_file(str(tmp_path / "missing").encode(), 0, 16, 16, out.ctypes.data) == -1
+
+
+def test_pedersen_fold_host(b200lib):
+    """b200_pedersen_fold (ProofOfKnowledge.Fold, backend/groth16/bn254/prove.go:127) is pure CPU: sum_i c^i * pok_i
+    against the big-int oracle, for 0, 1 and several proofs of knowledge, a challenge of 0 and a pok at infinity"""
+    import random
+    from gnark_b200 import lib
+    from oracle import ec, ff
+    from oracle.params import CURVES
+    rng = random.Random(12)
+    for c in (CURVES["bn254"], CURVES["bls12-381"], CURVES["bw6-761"]):
+        F = ff.Fp(c.p)
+        for count, chal in ((0, 5), (1, rng.randrange(c.r)), (4, rng.randrange(c.r)), (3, 0), (3, 1)):
+            pts = [ec.scalar_mul(F, rng.randrange(1, c.r), c.g1) for _ in range(count)]
+            if count == 4:
+                pts[2] = None                                               # a pok at infinity: (0, 0) in gnark's layout
+            want = None
+            for i, P in enumerate(pts):
+                want = ec.affine_add(F, want, ec.scalar_mul(F, pow(chal, i, c.r), P))
+            packed = ec.pack_points(c, 1, pts) if count else np.zeros(0, dtype=np.uint64)
+            got = lib.pedersen_fold(c.curve_id, packed, ff.pack_elements([chal], c.r, c.fr_limbs))
+            assert ec.unpack_points(c, 1, got)[0] == want, (c.name, count, chal)

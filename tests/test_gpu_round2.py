@@ -195,3 +195,73 @@ def test_msm_entry_count_guard(gpu):
     out = t.msm(d_sc, n=1 << 20, on_device=True)
     assert not out[8:].any()
     t.free()
+
+
+@pytest.mark.parametrize("cname", ["bn254", "bls12-381"])
+def test_pedersen_commit_prove_knowledge_fold(gpu, cname):
+    """backend/groth16/bn254/prove.go:72-129 through the ABI: per commitment Commit (:84) and ProveKnowledge (:114) as
+    two MSMs over one upload, then Fold (:127).  Keys built like gnark-crypto's pedersen.Setup with a trapdoor
+    (Basis_i = a_i G, BasisExpSigma_i = sigma a_i G): commitment = (sum v a) G, pok = sigma * commitment, and the
+    verifier's relation of the folded proof  sum c^i pok_i = sum c^i sigma_i commitment_i.  Sizes as in
+    backend/groth16/bn254/commitment_test.go (1 and 2 committed values) and two larger ones."""
+    from oracle import corelib
+    c = CURVES[cname]
+    F = ff.Fp(c.p)
+    rng = random.Random(91)
+    r, L = c.r, c.fr_limbs
+    pe = lambda v: ff.pack_elements(v, r, L)
+    G = ec.pack_points(c, 1, [c.g1])
+    sizes = (1, 2, 57, 20000)
+    poks, want_fold, chal = [], None, rng.randrange(r)
+    for i, n in enumerate(sizes):
+        a = [rng.randrange(1, r) for _ in range(n)]
+        sigma = rng.randrange(1, r)
+        v = [rng.randrange(r) for _ in range(n)]
+        if n > 2:
+            v[3] = 0                                     # a zero value and a repeated basis element
+            a[5] = a[4]
+        basis = corelib.fixed_base(c, 1, G, pe(a))
+        basis_sigma = corelib.fixed_base(c, 1, G, pe([x * sigma % r for x in a]))
+        key = gpu.PedersenKey(c.curve_id, basis, basis_sigma)
+        cm, pok = key.commit(pe(v))
+        dl = sum(x * y for x, y in zip(v, a)) % r
+        assert ec.unpack_points(c, 1, cm)[0] == ec.scalar_mul(F, dl, c.g1), n
+        assert ec.unpack_points(c, 1, pok)[0] == ec.scalar_mul(F, dl * sigma % r, c.g1), n
+        cm_only, none = key.commit(pe(v), want_pok=False)
+        assert none is None and np.array_equal(cm_only, cm)
+        with pytest.raises(gpu.B200Error):
+            key.commit(pe(v + [1]))                      # length mismatch is an error, as in gnark-crypto
+        key.free()
+        poks.append(pok)
+        want_fold = ec.affine_add(F, want_fold, ec.scalar_mul(F, pow(chal, i, r) * dl % r * sigma % r, c.g1))
+    got = gpu.pedersen_fold(c.curve_id, np.concatenate(poks), pe([chal]))
+    assert ec.unpack_points(c, 1, got)[0] == want_fold
+
+
+@pytest.mark.parametrize("on_device", [False, True])
+def test_msm_gather_is_the_filtered_msm(gpu, on_device):
+    """b200_msm_gather: the wire vector is used as is, the table holds only the bases that are not infinity
+    (prove.go:147-168): equals the MSM over the filtered copies, host and device operands, sub-range of the table"""
+    import torch
+    c = CURVES["bn254"]
+    n_wires, n = 9000, 6000
+    F, base, pts, sc, _ = known_dlog_instance(c, 1, n, seed=41)
+    rng = random.Random(6)
+    idx = np.array(sorted(rng.sample(range(n_wires), n)), dtype=np.uint32)
+    wires = ff.pack_elements([rng.randrange(c.r) for _ in range(n_wires)], c.r, c.fr_limbs).reshape(n_wires, c.fr_limbs)
+    t = gpu.Table(c.curve_id, 1, pts, precomp=True)
+    want = t.msm(np.ascontiguousarray(wires[idx]), n=n)
+    if on_device:
+        d_idx = torch.from_numpy(idx.astype(np.int32)).cuda()
+        d_w = torch.from_numpy(wires.view(np.int64).copy()).cuda()
+        torch.cuda.synchronize()
+        got = t.msm_gather(d_idx, d_w)
+    else:
+        got = t.msm_gather(idx, wires)
+    assert jac_to_affine(c, 1, got) == jac_to_affine(c, 1, want)
+    # a sub-range of the table with its own index list
+    got2 = t.msm_gather(idx[100:1100], wires, off=100)
+    assert jac_to_affine(c, 1, got2) == jac_to_affine(c, 1, t.msm(np.ascontiguousarray(wires[idx[100:1100]]), off=100, n=1000))
+    with pytest.raises(gpu.B200Error):
+        t.msm_gather(np.array([n_wires], dtype=np.uint32), wires)           # index out of range
+    t.free()
