@@ -82,6 +82,9 @@ struct b200_plonk_session_s {
   void* cb[4] = {nullptr};        // l, r, o, z: canonical, bit-reversed (n)
   void* bl[4] = {nullptr};        // blinded canonical regular (n + 2, n + 2, n + 2, n + 3)
   std::vector<void*> pi2_br, pi2_canon;   // BSB22 committed polynomials, canonical (bit-reversed / regular)
+  // per-proof Qk (b200_plonk_set_qk): the key's Qk with the public inputs and the BSB22 commitment values folded in
+  // (completeQk, prove.go:349-373); canonical bit-reversed / regular, nullptr = the key's own Qk
+  void *qk_br = nullptr, *qk_canon = nullptr;
   void* h = nullptr;              // quotient, canonical regular (4n)
   void* lin = nullptr;            // linearised polynomial (n + 3)
   uint8_t blind[4][3 * 8 * HOSTFR_MAX_LIMBS];   // bl, br, bo (2 each), bz (3)
@@ -304,6 +307,24 @@ int32_t b200_plonk_begin(b200_plonk_pk_t pk, const void* l, const void* r, const
   GUARD_END
 }
 
+// completeQk (prove.go:349-373): Qk of THIS proof = the trace's Qk with the public inputs written into its first rows and the
+// BSB22 commitment values at their constraint rows; Lagrange / regular, n elements on the host.  Optional (keys whose Qk
+// is already complete, circuits without public inputs); any time after plonk_begin and before plonk_quotient.
+int32_t b200_plonk_set_qk(b200_plonk_session_t s, const void* qk_lagrange) {
+  GUARD_BEGIN
+  if (!s || !qk_lagrange) return set_error("plonk_set_qk: null argument");
+  if (s->stage != 1 && s->stage != 2) return set_error("plonk_set_qk: call after plonk_begin and before plonk_quotient");
+  b200_plonk_pk_s* pk = s->pk;
+  const size_t n = pk->n, fb = pk->fb;
+  if (!s->qk_br) { RC(s->S.alloc(n * fb, &s->qk_br)); RC(s->S.alloc(n * fb, &s->qk_canon)); }
+  RC(b200_h2d(pk->dev, s->qk_br, qk_lagrange, n * fb));
+  RC(b200_ntt_async(pk->dom0[0], s->qk_br, 1, B200_DIF, 0));       // Lagrange/regular -> canonical/bit-reversed
+  RC(d2d(pk->dev, s->qk_canon, s->qk_br, n * fb));
+  RC(b200_vec_bit_reverse(pk->dev, pk->curve, s->qk_canon, pk->logn));
+  return 0;
+  GUARD_END
+}
+
 // buildRatioCopyConstraint :635-668 + commit Z
 int32_t b200_plonk_commit_z(b200_plonk_session_t s, const void* beta, const void* gamma, const void* bz, void* out_z) {
   GUARD_BEGIN
@@ -341,14 +362,14 @@ int32_t b200_plonk_quotient(b200_plonk_session_t s, const void* alpha, void* out
   fr->store(gb, pk->g); fr->store(w4b, pk->w4);
   // argument order of b200_plonk_coset_args: l r o z s1 s2 s3 ql qr qm qo qk
   const void* srcs[12] = {s->cb[0], s->cb[1], s->cb[2], s->cb[3], pk->br[S1], pk->br[S2], pk->br[S3],
-                          pk->br[QL], pk->br[QR], pk->br[QM], pk->br[QO], pk->br[QK]};
+                          pk->br[QL], pk->br[QR], pk->br[QM], pk->br[QO], s->qk_br ? s->qk_br : pk->br[QK]};
   const bool cached = !pk->key_cos.empty();
   // position of the key polynomials in key_cos[i]: ql qr qm qo qk s1 s2 s3 ; srcs[4..11] = s1 s2 s3 ql qr qm qo qk
   const int cos_idx[12] = {-1, -1, -1, -1, S1, S2, S3, QL, QR, QM, QO, QK};
   for (uint32_t i = 0; i < 4; i++) {
     const void* on[12];
     for (int k = 0; k < 12; k++) {
-      if (cached && cos_idx[k] >= 0) { on[k] = pk->key_cos[i][cos_idx[k]]; continue; }
+      if (cached && cos_idx[k] >= 0 && !(k == 11 && s->qk_br)) { on[k] = pk->key_cos[i][cos_idx[k]]; continue; }
       RC(d2d(dev, onc[k], srcs[k], n * fb));
       RC(b200_ntt_async(pk->dom0[i], onc[k], 0, B200_DIT, 1));     // canonical/bit-reversed -> coset i, regular
       on[k] = onc[k];
@@ -428,7 +449,7 @@ int32_t b200_plonk_linearise(b200_plonk_session_t s, const void* zeta_, void* ou
   RC(axpy(pk, lin, lz, pk->canon[QL], n));
   RC(axpy(pk, lin, rz, pk->canon[QR], n));
   RC(axpy(pk, lin, oz, pk->canon[QO], n));
-  RC(axpy(pk, lin, fr->one_(), pk->canon[QK], n));
+  RC(axpy(pk, lin, fr->one_(), s->qk_canon ? s->qk_canon : pk->canon[QK], n));
   // + sum_j Qcp_j(zeta) PI2_j(X)   (:1457-1460); Qcp_j(zeta) are claimed values 6.. of the batch opening
   for (size_t j = 0; j < pk->qcp_canon.size(); j++) {
     HostFr qz;
@@ -518,6 +539,7 @@ int32_t b200_plonk_prove(b200_plonk_pk_t pk, const void* l, const void* r, const
   double st_ms[5] = {0, 0, 0, 0, 0};
   clk::time_point t0 = clk::now();
   int32_t rc = b200_plonk_begin(pk, l, r, o, ch->bl, ch->br, ch->bo, ch->pi2, ch->out_bsb22, &s, pts);
+  if (!rc && ch->qk) rc = b200_plonk_set_qk(s, ch->qk);
   if (!rc) rc = b200_sync(pk->dev);
   st_ms[0] = ms_since(t0); t0 = clk::now();
   if (!rc) rc = b200_plonk_commit_z(s, ch->beta, ch->gamma, ch->bz, pts + 3 * jb);

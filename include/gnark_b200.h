@@ -298,6 +298,9 @@ typedef struct {
    * (prove.go:280-318), n fr.Elements each, Lagrange/regular; out_bsb22 receives [PI2_j] (n_qcp G1Jac) */
   const void* const* pi2;
   void* out_bsb22;
+  /* this proof's complete Qk (completeQk, prove.go:349-373: public inputs and BSB22 commitment values folded into the
+   * trace's Qk), n fr.Elements, Lagrange/regular; NULL = the Qk the key was loaded with */
+  const void* qk;
 } b200_plonk_challenges;
 int32_t b200_plonk_pk_load(int32_t dev, int32_t curve, const b200_plonk_pk_desc* desc, b200_plonk_pk_t* out);
 int32_t b200_plonk_pk_free(b200_plonk_pk_t pk);
@@ -329,6 +332,8 @@ typedef struct b200_plonk_session_s* b200_plonk_session_t;
 int32_t b200_plonk_begin(b200_plonk_pk_t pk, const void* l, const void* r, const void* o, const void* bl /*2*/,
                          const void* br /*2*/, const void* bo /*2*/, const void* const* pi2 /* n_qcp or NULL */,
                          void* out_bsb22 /* n_qcp G1Jac or NULL */, b200_plonk_session_t* out, void* out_lro);
+/* optional, between begin and quotient: this proof's complete Qk (see b200_plonk_challenges.qk) */
+int32_t b200_plonk_set_qk(b200_plonk_session_t s, const void* qk_lagrange);
 int32_t b200_plonk_commit_z(b200_plonk_session_t s, const void* beta, const void* gamma, const void* bz /*3*/,
                             void* out_z);
 int32_t b200_plonk_quotient(b200_plonk_session_t s, const void* alpha, void* out_h);

@@ -60,6 +60,8 @@ cudaError_t cudaMemcpyAsync(void* dst, const void* src, size_t count, enum cudaM
   return cudaSuccess;
 }
 cudaError_t cudaMemsetAsync(void* p, int v, size_t count, cudaStream_t) { memset(p, v, count); return cudaSuccess; }
+// ~b200_table_s (capi_common.h) releases its device buffers; the mock's tables null theirs before delete
+cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
 
 const char* b200_last_error(void) { return g_err.c_str(); }
 int32_t b200_alloc(int32_t, size_t bytes, void** out) { *out = malloc(bytes ? bytes : 1); return *out ? 0 : 1; }

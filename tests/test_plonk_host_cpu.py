@@ -101,6 +101,35 @@ def test_plonk_host_orchestration_vs_oracle(mock, cname, logn):
     assert mock.b200_plonk_end(s_) == 0
     staged = np.concatenate([lro, zpt[None], hpts, two[0:1], bpt[None], two[1:2]])
     assert np.array_equal(staged, pts) and np.array_equal(vals2, vals)
+    # completeQk (prove.go:349-373): a key loaded with an INCOMPLETE Qk (public rows still zero) proves the same when the
+    # proof's complete Qk is handed in - through the one-call entry point and through b200_plonk_set_qk
+    qk_incomplete = keep["qk"].copy()
+    qk_incomplete[:2] = 0
+    d.qk = P(qk_incomplete).value
+    h3 = ctypes.c_void_p(0)
+    assert mock.b200_plonk_pk_load(0, c.curve_id, ctypes.byref(d), ctypes.byref(h3)) == 0, mock.b200_last_error()
+    pts3, vals3 = np.zeros_like(pts), np.zeros_like(vals)
+    assert mock.b200_plonk_prove(h3, P(L_), P(R_), P(O_), ctypes.byref(cs), P(pts3), P(vals3)) == 0
+    assert not np.array_equal(pts3, pts)                       # the incomplete key alone proves something else
+    cs.qk = P(keep["qk"]).value
+    assert mock.b200_plonk_prove(h3, P(L_), P(R_), P(O_), ctypes.byref(cs), P(pts3), P(vals3)) == 0, mock.b200_last_error()
+    assert np.array_equal(pts3, pts) and np.array_equal(vals3, vals)
+    cs.qk = None
+    mock.b200_plonk_set_qk.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    s3 = ctypes.c_void_p(0)
+    assert mock.b200_plonk_set_qk(s3, P(keep["qk"])) != 0
+    assert mock.b200_plonk_begin(h3, P(L_), P(R_), P(O_), P(sc["bl"]), P(sc["br"]), P(sc["bo"]), None, None,
+                                 ctypes.byref(s3), P(lro)) == 0
+    assert mock.b200_plonk_commit_z(s3, P(sc["beta"]), P(sc["gamma"]), P(sc["bz"]), P(zpt)) == 0
+    assert mock.b200_plonk_set_qk(s3, P(keep["qk"])) == 0
+    assert mock.b200_plonk_quotient(s3, P(sc["alpha"]), P(hpts)) == 0
+    assert mock.b200_plonk_set_qk(s3, P(keep["qk"])) != 0 and b"before plonk_quotient" in mock.b200_last_error()
+    assert mock.b200_plonk_linearise(s3, P(sc["zeta"]), P(two), P(vals2)) == 0
+    assert mock.b200_plonk_batch_open(s3, P(sc["v"]), P(bpt)) == 0
+    assert mock.b200_plonk_end(s3) == 0
+    assert np.array_equal(np.concatenate([lro, zpt[None], hpts, two[0:1], bpt[None], two[1:2]]), pts)
+    assert mock.b200_plonk_pk_free(h3) == 0
+    d.qk = P(keep["qk"]).value
     # a permutation entry out of range is refused, not dereferenced
     bad = perm.copy(); bad[1] = 3 * n
     d.perm = P(bad).value
