@@ -58,9 +58,6 @@ int32_t device_ctx(int dev, DeviceCtx** out) {
     CK(cudaEventCreateWithFlags(&c.tail_ev, cudaEventDisableTiming));
     CK(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&c.copy_ev, cudaEventDisableTiming));
-    CK(cudaStreamCreateWithFlags(&c.aux_stream, cudaStreamNonBlocking));
-    CK(cudaEventCreateWithFlags(&c.aux_fork_ev, cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&c.aux_join_ev, cudaEventDisableTiming));
     cudaMemPool_t pool;
     CK(cudaDeviceGetDefaultMemPool(&pool, dev));
     uint64_t thr = UINT64_MAX;  // keep freed workspace cached in the pool
@@ -122,24 +119,15 @@ int32_t msm_on_stream(DeviceCtx* ctx, b200_table_s* t, size_t off, size_t n, con
   uint32_t task_len, chunk;
   msm_tuning(n, t->nwin, t->c, t->precomp, &task_len, &chunk);
   size_t ws_bytes = 0;
-  // opt-in: batched-affine tree levels before the XYZZ accumulate (msm_batch.cuh); 0 = off (default)
-  int ba_levels = env_int("GB200_MSM_BATCH_AFFINE", 0);
-  if (ba_levels < 0 || t->fmt52) ba_levels = 0;
-  if (ba_levels > 12) ba_levels = 12;
-  CK(t->ops->ws_bytes((uint32_t)n, (uint32_t)t->n, t->c, t->precomp, task_len, chunk, ba_levels, &ws_bytes));
+  CK(t->ops->ws_bytes((uint32_t)n, (uint32_t)t->n, t->c, t->precomp, task_len, chunk, &ws_bytes));
   AsyncBuf ws_buf;
   CK(ws_buf.alloc(ws_bytes, ctx->stream));
   void* ws = ws_buf.p;
-  // opt-in: persistent accumulate (msm.cuh 4c); not combined with the FP64 / hybrid kernels
-  // (2 = persistent grid AND accumulators in shared memory)
-  int persistent = (!t->fmt52 && t->hybrid52_of_16 == 0) ? env_int("GB200_MSM_PERSISTENT", 0) : 0;
-  if (persistent < 0 || persistent > 2) persistent = 0;
-  // opt-in: accumulator in shared memory (curve.cuh SmemXYZZ); the persistent kernel takes precedence
-  const int smem_acc = (env_int("GB200_MSM_SMEM_ACC", 0) > 0 && !persistent && !t->fmt52 && t->hybrid52_of_16 == 0) ? 1 : 0;
-  MsmHybrid hy{t->d_points52, t->hybrid52_of_16, ctx->aux_stream, ctx->aux_fork_ev, ctx->aux_join_ev, ba_levels, persistent, smem_acc};
+  // GB200_MSM_PERSISTENT=1 (opt-in, msm.cuh 4c): accumulate on a grid sized to the machine, tasks from an atomic counter
+  const int persistent = env_int("GB200_MSM_PERSISTENT", 0) == 1 ? 1 : 0;
   cudaError_t e = t->ops->run(ctx->stream, (uint32_t)n, (uint32_t)t->n, (uint32_t)off, t->c, t->precomp, task_len, chunk,
                               t->d_points, d_scalars, d_out, ws, stage_events, pipelined ? ctx->tail_stream : nullptr,
-                              ctx->fork_ev, t->fmt52, (t->hybrid52_of_16 > 0 || ba_levels > 0 || persistent || smem_acc) ? &hy : nullptr);
+                              ctx->fork_ev, persistent);
   // the workspace is last used by the tail kernels
   cudaError_t e2 = ws_buf.release_on(pipelined ? ctx->tail_stream : ctx->stream);
   if (pipelined && e == cudaSuccess) {
@@ -195,13 +183,10 @@ int32_t b200_shutdown(void) {
     cudaEventDestroy(c.copy_ev);
     cudaEventDestroy(c.fork_ev);
     cudaEventDestroy(c.tail_ev);
-    cudaStreamDestroy(c.aux_stream);
-    cudaEventDestroy(c.aux_fork_ev);
-    cudaEventDestroy(c.aux_join_ev);
     // back to the initial state (the lock itself stays)
     c.ready = false; c.tail_pending = false;
-    c.own_stream = c.stream = c.tail_stream = c.copy_stream = c.aux_stream = nullptr;
-    c.copy_ev = c.fork_ev = c.tail_ev = c.aux_fork_ev = c.aux_join_ev = nullptr;
+    c.own_stream = c.stream = c.tail_stream = c.copy_stream = nullptr;
+    c.copy_ev = c.fork_ev = c.tail_ev = nullptr;
   }
   return 0;
   GUARD_END
@@ -270,14 +255,15 @@ int32_t b200_host_free(void* p) {
 }
 
 // ---- tables ------------------------------------------------------------------
-int32_t b200_table_upload(int32_t dev, int32_t curve, int32_t group, const void* points, size_t n, int32_t flags,
-                          b200_table_t* out) {
-  GUARD_BEGIN
-  GB_DEVICE(ctx, dev); [[maybe_unused]] int32_t rc = 0;
+}  // extern "C"
+
+namespace gb200 {
+// device table of n points with room for the precomputed slabs; slab 0 (= the first n entries of d_points) is filled by
+// the caller - from host / device memory, from a file region, or by the point decoder - and table_finish builds the rest
+static int32_t table_new(int dev, int curve, int group, size_t n, int flags, std::unique_ptr<b200_table_s>& t) {
   const MsmOps* ops = get_msm_ops(curve, group);
   if (!ops) return set_error("table_upload: unsupported curve/group");
-  if (n && !points) return set_error("table_upload: null points");
-  std::unique_ptr<b200_table_s> t(new b200_table_s());
+  t.reset(new b200_table_s());
   t->dev = dev; t->curve = curve; t->group = group; t->n = n; t->ops = ops;
   t->c = msm_window_for(n ? n : 1);
   while (msm_num_windows(ops->scalar_bits, t->c) > 64) t->c++;   // MSM_MAX_WINDOWS of the table precompute
@@ -286,36 +272,71 @@ int32_t b200_table_upload(int32_t dev, int32_t curve, int32_t group, const void*
   if (env_int("GB200_MSM_PRECOMP", -1) >= 0) t->precomp = env_int("GB200_MSM_PRECOMP", 0) ? 1 : 0;
   const size_t slabs = t->precomp ? (size_t)t->nwin : 1;
   if (slabs * n >= (1ull << 31)) return set_error("table_upload: table too large for 31-bit point indices; shard it");
+  t->bytes = slabs * (n ? n : 1) * ops->affine_bytes;
+  CK(cudaMalloc(&t->d_points, t->bytes));
+  return 0;
+}
+static int32_t table_finish(DeviceCtx* ctx, b200_table_s* t) {
+  if (t->precomp) CK(t->ops->precompute(ctx->stream, (uint32_t)t->n, t->nwin, t->c, t->d_points));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+}  // namespace gb200
+
+extern "C" {
+
+int32_t b200_table_upload(int32_t dev, int32_t curve, int32_t group, const void* points, size_t n, int32_t flags,
+                          b200_table_t* out) {
+  GUARD_BEGIN
+  GB_DEVICE(ctx, dev); [[maybe_unused]] int32_t rc = 0;
+  if (!out) return set_error("table_upload: null argument");
+  if (n && !points) return set_error("table_upload: null points");
+  std::unique_ptr<b200_table_s> t;
+  rc = table_new(dev, curve, group, n, flags, t); if (rc) return rc;
   const cudaMemcpyKind kind = (flags & B200_TABLE_SRC_ON_DEVICE) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-  // FP64-pipe accumulate (field52.cuh) for precomputed G1 tables: opt-in (GB200_MSM_FP64=1).  Measured on
-  // B200 it is SLOWER than the IMAD.WIDE path (profiles/r01_fp64_pipe_experiment.md), so it is off by default.
-  t->fmt52 = (t->precomp && ops->affine52_bytes && env_int("GB200_MSM_FP64", 0) && n > 0) ? 1 : 0;
-  if (t->fmt52) {
-    t->bytes = slabs * n * ops->affine52_bytes;
-    CK(cudaMalloc(&t->d_points, t->bytes));
-    AsyncBuf d_src;
-    CK(d_src.alloc(n * ops->affine_bytes, ctx->stream));
-    CK(cudaMemcpyAsync(d_src.p, points, n * ops->affine_bytes, kind, ctx->stream));
-    CK(ops->precompute52(ctx->stream, (uint32_t)n, t->nwin, t->c, d_src.p, t->d_points));
-    CK(d_src.release_on(ctx->stream));
-  } else {
-    t->bytes = slabs * (n ? n : 1) * ops->affine_bytes;
-    CK(cudaMalloc(&t->d_points, t->bytes));
-    if (n) CK(cudaMemcpyAsync(t->d_points, points, n * ops->affine_bytes, kind, ctx->stream));
-    if (t->precomp) CK(ops->precompute(ctx->stream, (uint32_t)n, t->nwin, t->c, t->d_points));
-    // opt-in hybrid accumulate: GB200_MSM_HYBRID = percentage of the accumulate work given to the FP64-pipe
-    // kernel running concurrently with the IMAD.WIDE kernel; needs the table in both formats
-    const int pct = env_int("GB200_MSM_HYBRID", 0);
-    if (pct > 0 && pct < 100 && t->precomp && ops->affine52_bytes && n > 0) {
-      int k = (pct * 16 + 50) / 100;
-      t->hybrid52_of_16 = k < 1 ? 1 : (k > 15 ? 15 : k);
-      const size_t bytes52 = slabs * n * ops->affine52_bytes;
-      CK(cudaMalloc(&t->d_points52, bytes52));
-      CK(ops->precompute52(ctx->stream, (uint32_t)n, t->nwin, t->c, t->d_points, t->d_points52));
-      t->bytes += bytes52;
+  if (n) CK(cudaMemcpyAsync(t->d_points, points, n * t->ops->affine_bytes, kind, ctx->stream));
+  rc = table_finish(ctx, t.get()); if (rc) return rc;
+  *out = t.release();
+  return 0;
+  GUARD_END
+}
+
+// Table from a slice in gnark-crypto's SERIALISED point encoding (points_decode.cuh): what backend/plonk/<curve>/marshal.go
+// writes for pk.Kzg / pk.KzgLagrange (compressed with WriteTo, uncompressed with WriteRawTo) after the slice's uint32
+// length.  The bytes go up as they are; one thread per point decodes (a square root per compressed point) straight into
+// the table.  Every point is checked (canonical coordinates, on the curve); subgroup membership is not, as with
+// gnark's UnsafeReadFrom.  An invalid point fails the call with its index.
+int32_t b200_table_upload_encoded(int32_t dev, int32_t curve, int32_t group, const void* bytes, size_t n, int32_t encoding,
+                                  int32_t flags, b200_table_t* out) {
+  GUARD_BEGIN
+  GB_DEVICE(ctx, dev); [[maybe_unused]] int32_t rc = 0;
+  if (!out || (n && !bytes)) return set_error("table_upload_encoded: null argument");
+  if (flags & B200_TABLE_SRC_ON_DEVICE) return set_error("table_upload_encoded: the encoded slice is read from host memory");
+  if (curve < 0 || curve > 3) return set_error("table_upload_encoded: unsupported curve");
+  std::unique_ptr<b200_table_s> t;
+  rc = table_new(dev, curve, group, n, flags, t); if (rc) return rc;
+  const size_t per = t->ops->encoded_bytes(encoding);
+  if (per == 0) return set_error("table_upload_encoded: encoding not supported for this group (compressed: G1 only; 1 = raw, 2 = compressed)");
+  static const int b_small[4] = {3, 4, 1, -1};       // y^2 = x^3 + b: BN254, BLS12-381, BLS12-377, BW6-761
+  if (n) {
+    AsyncBuf d_bytes, d_status;
+    CK(d_bytes.alloc(n * per, ctx->stream));
+    CK(d_status.alloc(2 * sizeof(uint32_t), ctx->stream));
+    CK(cudaMemsetAsync(d_status.p, 0, 2 * sizeof(uint32_t), ctx->stream));
+    CK(cudaMemcpyAsync(d_bytes.p, bytes, n * per, cudaMemcpyHostToDevice, ctx->stream));
+    cudaError_t e = t->ops->decode(ctx->stream, d_bytes.p, n, encoding, b_small[curve], t->d_points, (uint32_t*)d_status.p);
+    if (e == cudaErrorNotSupported)
+      return set_error("table_upload_encoded: compressed points need p = 3 mod 4 (BLS12-377: use the raw encoding)");
+    if (e != cudaSuccess) return cuda_fail("points decode", e);
+    uint32_t status[2] = {0, 0};
+    CK(cudaMemcpyAsync(status, d_status.p, sizeof(status), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (status[0]) {
+      static const char* why[] = {"", "invalid metadata bits", "coordinate not reduced modulo p", "point not on the curve"};
+      return set_error(std::string("table_upload_encoded: point ") + std::to_string(status[1]) + ": " + why[status[0] < 4 ? status[0] : 0]);
     }
   }
-  CK(cudaStreamSynchronize(ctx->stream));
+  rc = table_finish(ctx, t.get()); if (rc) return rc;
   *out = t.release();
   return 0;
   GUARD_END
@@ -343,41 +364,44 @@ int32_t b200_table_upload_file(int32_t dev, int32_t curve, int32_t group, const 
   if (fstat(f.fd, &st) != 0) return set_error(std::string("table_upload_file: fstat: ") + strerror(errno));
   if ((uint64_t)st.st_size < byte_offset || (uint64_t)st.st_size - byte_offset < bytes)
     return set_error("table_upload_file: [offset, offset + n * sizeof(point)) exceeds the file");
-  if (n == 0) return b200_table_upload(dev, curve, group, nullptr, 0, flags, out);
-  const size_t slot_bytes = bytes < ((size_t)32 << 20) ? bytes : ((size_t)32 << 20);
-  struct Pinned { void* p[2] = {nullptr, nullptr}; cudaEvent_t ev[2] = {nullptr, nullptr};
-                  ~Pinned() { for (int i = 0; i < 2; i++) { if (p[i]) cudaFreeHost(p[i]); if (ev[i]) cudaEventDestroy(ev[i]); } } } pin;
-  for (int i = 0; i < 2; i++) {
-    CK(cudaHostAlloc(&pin.p[i], slot_bytes, cudaHostAllocDefault));
-    CK(cudaEventCreateWithFlags(&pin.ev[i], cudaEventDisableTiming));
+  std::unique_ptr<b200_table_s> t;
+  rc = table_new(dev, curve, group, n, flags, t); if (rc) return rc;
+  if (n) {
+    // the file region goes through two pinned slots straight into slab 0 of the table: no second device copy of the
+    // slice, peak HBM = the table itself
+    const size_t slot_bytes = bytes < ((size_t)32 << 20) ? bytes : ((size_t)32 << 20);
+    struct Pinned { void* p[2] = {nullptr, nullptr}; cudaEvent_t ev[2] = {nullptr, nullptr};
+                    ~Pinned() { for (int i = 0; i < 2; i++) { if (p[i]) cudaFreeHost(p[i]); if (ev[i]) cudaEventDestroy(ev[i]); } } } pin;
+    for (int i = 0; i < 2; i++) {
+      CK(cudaHostAlloc(&pin.p[i], slot_bytes, cudaHostAllocDefault));
+      CK(cudaEventCreateWithFlags(&pin.ev[i], cudaEventDisableTiming));
+    }
+    bool used[2] = {false, false};
+    cudaError_t ce = cudaSuccess;
+    std::string err;
+    char* dst = reinterpret_cast<char*>(t->d_points);
+    const int r = stage_file_region(
+        f.fd, byte_offset, bytes, pin.p, slot_bytes,
+        [&](int slot, const void* data, size_t pos, size_t len) {
+          ce = cudaMemcpyAsync(dst + pos, data, len, cudaMemcpyHostToDevice, ctx->copy_stream);
+          if (ce == cudaSuccess) ce = cudaEventRecord(pin.ev[slot], ctx->copy_stream);
+          used[slot] = true;
+          return ce == cudaSuccess ? 0 : 1;
+        },
+        [&](int slot) {
+          if (!used[slot]) return 0;
+          ce = cudaEventSynchronize(pin.ev[slot]);
+          return ce == cudaSuccess ? 0 : 1;
+        },
+        &err);
+    cudaError_t ce2 = cudaStreamSynchronize(ctx->copy_stream);
+    if (ce != cudaSuccess) return cuda_fail("table_upload_file", ce);
+    if (r != 0) return set_error("table_upload_file: " + err);
+    if (ce2 != cudaSuccess) return cuda_fail("table_upload_file", ce2);
   }
-  AsyncBuf d_src;
-  CK(d_src.alloc(bytes, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));          // the buffer exists before the copy stream writes to it
-  bool used[2] = {false, false};
-  cudaError_t ce = cudaSuccess;
-  std::string err;
-  const int r = stage_file_region(
-      f.fd, byte_offset, bytes, pin.p, slot_bytes,
-      [&](int slot, const void* data, size_t pos, size_t len) {
-        ce = cudaMemcpyAsync((char*)d_src.p + pos, data, len, cudaMemcpyHostToDevice, ctx->copy_stream);
-        if (ce == cudaSuccess) ce = cudaEventRecord(pin.ev[slot], ctx->copy_stream);
-        used[slot] = true;
-        return ce == cudaSuccess ? 0 : 1;
-      },
-      [&](int slot) {
-        if (!used[slot]) return 0;
-        ce = cudaEventSynchronize(pin.ev[slot]);
-        return ce == cudaSuccess ? 0 : 1;
-      },
-      &err);
-  cudaError_t ce2 = cudaStreamSynchronize(ctx->copy_stream);
-  if (ce != cudaSuccess) return cuda_fail("table_upload_file", ce);
-  if (r != 0) return set_error("table_upload_file: " + err);
-  if (ce2 != cudaSuccess) return cuda_fail("table_upload_file", ce2);
-  rc = b200_table_upload(dev, curve, group, d_src.p, n, flags | B200_TABLE_SRC_ON_DEVICE, out);
-  d_src.release_on(ctx->stream);
-  return rc;
+  rc = table_finish(ctx, t.get()); if (rc) return rc;
+  *out = t.release();
+  return 0;
   GUARD_END
 }
 

@@ -35,9 +35,6 @@ struct DeviceCtx {
   cudaEvent_t fork_ev = nullptr;   // accumulate done (recorded on stream)
   cudaEvent_t tail_ev = nullptr;   // tail done (recorded on tail_stream)
   bool tail_pending = false;
-  // opt-in hybrid accumulate (MsmHybrid): second stream for the FP64-pipe kernel
-  cudaStream_t aux_stream = nullptr;
-  cudaEvent_t aux_fork_ev = nullptr, aux_join_ev = nullptr;
   // multi-GPU (comm.cu): NCCL communicator of this device (ncclComm_t), nullptr = single device
   void* comm = nullptr;
   int comm_world = 1, comm_rank = 0;
@@ -57,14 +54,11 @@ struct b200_table_s {
   int dev, curve, group;
   size_t n;          // bases
   int c, nwin, precomp;
-  int fmt52 = 0;     // entries are Affine52 (FP64-pipe accumulate)
   size_t bytes;
   void* d_points = nullptr;
-  void* d_points52 = nullptr;   // hybrid accumulate only: the same table in Affine52 format
-  int hybrid52_of_16 = 0;       // 0 = off
   const gb200::MsmOps* ops;
-  // owns its device buffers: a table that fails half way through its construction does not leak them
-  ~b200_table_s() { if (d_points) cudaFree(d_points); if (d_points52) cudaFree(d_points52); }
+  // owns its device buffer: a table that fails half way through its construction does not leak it
+  ~b200_table_s() { if (d_points) cudaFree(d_points); }
 };
 
 struct b200_domain_s {

@@ -91,12 +91,7 @@ struct alignas(16) XYZZ {
     F PPP = P * PP;
     F Q = x * PP;
     F X3 = R.sqr() - PPP - Q.dbl();
-#if defined(GB200_XYZZ_LAZY)
-    if constexpr (is_device_fp<F>::value) y = F::mul_sub(R, Q - X3, y, PPP);   // one reduction instead of two
-    else y = R * (Q - X3) - y * PPP;
-#else
     y = R * (Q - X3) - y * PPP;
-#endif
     x = X3;
     zz = zz * PP;
     zzz = zzz * PPP;
@@ -149,54 +144,6 @@ struct alignas(16) XYZZ {
     a.x = x * zi2;
     a.y = y * zi;
     return a;
-  }
-};
-
-// XYZZ accumulator kept in SHARED memory (opt-in GB200_MSM_SMEM_ACC): for the wide fields the four accumulator
-// coordinates are most of a thread's register budget (BN254 G2: 64 of ~146 registers, 3 blocks/SM; BLS12-381 G1: 48 of 126),
-// while one mixed addition touches each of them only two or three times.  Word l of coordinate k of the thread at
-// `base` lives at base[(k * NW + l) * stride] (stride = blockDim.x: consecutive threads hit consecutive banks).
-template <class F>
-struct SmemXYZZ {
-  static constexpr int NW = sizeof(F) / 4;
-  uint32_t* base;
-  uint32_t stride;
-  HD F ld(int k) const {
-    F v;
-    uint32_t* w = reinterpret_cast<uint32_t*>(&v);
-#pragma unroll
-    for (int l = 0; l < NW; l++) w[l] = base[(size_t)(k * NW + l) * stride];
-    return v;
-  }
-  HD void st(int k, const F& v) const {
-    const uint32_t* w = reinterpret_cast<const uint32_t*>(&v);
-#pragma unroll
-    for (int l = 0; l < NW; l++) base[(size_t)(k * NW + l) * stride] = w[l];
-  }
-  HD void set(const XYZZ<F>& p) const { st(0, p.x); st(1, p.y); st(2, p.zz); st(3, p.zzz); }
-  HD XYZZ<F> get() const { XYZZ<F> p; p.x = ld(0); p.y = ld(1); p.zz = ld(2); p.zzz = ld(3); return p; }
-
-  // acc += a (affine), same cases as XYZZ::add_mixed; the doubling / cancellation cases go through registers
-  HD void add_mixed(const Affine<F>& a) const {
-    if (a.is_inf()) return;
-    const F zz = ld(2);
-    if (zz.is_zero()) { st(0, a.x); st(1, a.y); st(2, F::one()); st(3, F::one()); return; }
-    const F P = a.x * zz - ld(0);
-    const F R = a.y * ld(3) - ld(1);
-    if (P.is_zero()) {
-      XYZZ<F> t = get();
-      t.add_mixed(a);
-      set(t);
-      return;
-    }
-    const F PP = P.sqr();
-    const F PPP = P * PP;
-    const F Q = ld(0) * PP;
-    const F X3 = R.sqr() - PPP - Q.dbl();
-    st(1, R * (Q - X3) - ld(1) * PPP);
-    st(0, X3);
-    st(2, zz * PP);
-    st(3, ld(3) * PPP);
   }
 };
 

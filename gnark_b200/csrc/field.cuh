@@ -85,9 +85,9 @@ HD void mont_mul_raw(uint32_t* r, const uint32_t* a, const uint32_t* b) {
 }
 
 // ---------------------------------------------------------------------------
-// Wide (unreduced) products and a separate Montgomery reduction: the building blocks of the dedicated squaring
-// (GB200_MONT_SQR) and of the lazily reduced Fp2 product (GB200_FP2_LAZY).  Compile-time options, off by default;
-// bit-exact against the fused product (tests/test_emulation.py::test_wide_arithmetic and the *_opt emulation runs).
+// Wide (unreduced) products and a separate Montgomery reduction: the building blocks of the lazily reduced Fp2 product
+// (Fp2::mul_lazy: 3 wide products + 2 reductions instead of 3 + 3; measured on B200, round 2: BN254 G2 accumulate
+// 11.4 -> 10.2 ms).  Bit-exact against the fused product (tests/test_emulation.py::test_wide_arithmetic).
 // ---------------------------------------------------------------------------
 
 // t[0..2N) = a * b for ANY N-limb a, b (no reduction).  Same even/odd carry chains as mont_mul_raw without the m*p rows.
@@ -104,106 +104,6 @@ HD void wide_mul_raw(uint32_t* t, const uint32_t* a, const uint32_t* b) {
   t[0] = ptx::add_cc(acc[0][0], acc[1][0]);
 #pragma unroll
   for (int k = 1; k < 2 * N; k++) t[k] = ptx::addc_cc(acc[0][k], acc[1][k]);
-  (void)ptx::addc(0, 0);
-}
-
-// Karatsuba on top of wide_mul_raw (GB200_MONT_KARATSUBA, large fields): one level for N = 12 (3 x 6-limb products:
-// 108 multiplier operations instead of 144), two levels for N = 24 (9 x 6-limb: 324 instead of 576).
-// -DGB200_KARATSUBA_MIN_LIMBS=8 extends it to the 8-limb fields (BN254: 3 x 4-limb = 48 instead of 64, so a Montgomery
-// product is 48 + 72 = 120 multiplier operations instead of 136; the 12 / 24-limb decomposition is unchanged).
-#ifndef GB200_KARATSUBA_MIN_LIMBS
-#define GB200_KARATSUBA_MIN_LIMBS 12
-#endif
-//   a = aL + aH B, b = bL + bH B (B = 2^(32 N/2)):  a b = z0 + (z1 - z0 - z2) B + z2 B^2,
-//   z0 = aL bL, z2 = aH bH, z1 = (aL + aH)(bL + bH) with the two carry bits of the sums handled apart.
-template <int N>
-HD void wide_mul_karatsuba(uint32_t* t, const uint32_t* a, const uint32_t* b) {
-  if constexpr (N < GB200_KARATSUBA_MIN_LIMBS || (N % 2) != 0) {
-    wide_mul_raw<N>(t, a, b);
-  } else {
-    constexpr int H = N / 2;
-    uint32_t z0[2 * H], z2[2 * H], z1[2 * H + 2], sa[H], sb[H];
-    wide_mul_karatsuba<H>(z0, a, b);
-    wide_mul_karatsuba<H>(z2, a + H, b + H);
-    // sums with their carry bits
-    sa[0] = ptx::add_cc(a[0], a[H]);
-#pragma unroll
-    for (int k = 1; k < H; k++) sa[k] = ptx::addc_cc(a[k], a[H + k]);
-    const uint32_t ca = ptx::addc(0, 0);
-    sb[0] = ptx::add_cc(b[0], b[H]);
-#pragma unroll
-    for (int k = 1; k < H; k++) sb[k] = ptx::addc_cc(b[k], b[H + k]);
-    const uint32_t cb = ptx::addc(0, 0);
-    wide_mul_karatsuba<H>(z1, sa, sb);
-    z1[2 * H] = 0; z1[2 * H + 1] = 0;
-    // + ca * sb * 2^(32H) + cb * sa * 2^(32H) + ca cb 2^(64H)   (masks, no multiplications)
-    const uint32_t ma = 0u - ca, mb = 0u - cb;
-    z1[H] = ptx::add_cc(z1[H], sb[0] & ma);
-#pragma unroll
-    for (int k = 1; k < H; k++) z1[H + k] = ptx::addc_cc(z1[H + k], sb[k] & ma);
-    z1[2 * H] = ptx::addc(z1[2 * H], 0);
-    z1[H] = ptx::add_cc(z1[H], sa[0] & mb);
-#pragma unroll
-    for (int k = 1; k < H; k++) z1[H + k] = ptx::addc_cc(z1[H + k], sa[k] & mb);
-    z1[2 * H] = ptx::addc_cc(z1[2 * H], ca & cb);
-    z1[2 * H + 1] = ptx::addc(z1[2 * H + 1], 0);
-    // z1 -= z0 + z2   (the true middle term fits 2H + 1 limbs)
-    z1[0] = ptx::sub_cc(z1[0], z0[0]);
-#pragma unroll
-    for (int k = 1; k < 2 * H; k++) z1[k] = ptx::subc_cc(z1[k], z0[k]);
-    z1[2 * H] = ptx::subc_cc(z1[2 * H], 0);
-    z1[2 * H + 1] = ptx::subc(z1[2 * H + 1], 0);
-    z1[0] = ptx::sub_cc(z1[0], z2[0]);
-#pragma unroll
-    for (int k = 1; k < 2 * H; k++) z1[k] = ptx::subc_cc(z1[k], z2[k]);
-    z1[2 * H] = ptx::subc_cc(z1[2 * H], 0);
-    z1[2 * H + 1] = ptx::subc(z1[2 * H + 1], 0);
-    // assemble: t = z0 + z1 B + z2 B^2
-#pragma unroll
-    for (int k = 0; k < 2 * H; k++) { t[k] = z0[k]; t[2 * H + k] = z2[k]; }
-    t[H] = ptx::add_cc(t[H], z1[0]);
-#pragma unroll
-    for (int k = 1; k < 2 * H + 2 && H + k < 2 * N; k++) t[H + k] = ptx::addc_cc(t[H + k], z1[k]);
-#pragma unroll
-    for (int k = 3 * H + 2; k < 2 * N; k++) t[k] = ptx::addc_cc(t[k], 0);
-    (void)ptx::addc(0, 0);
-  }
-}
-
-// cross terms of a square: chains of a_i * a_j, j > i, all j of one parity
-template <int N, int I>
-struct SqrCross {
-  HD static void run(uint32_t (*acc)[2 * N + 3], const uint32_t* a) {
-    if constexpr (I + 1 < N) mad_chain<N, I + 1, false>(acc[1], I, a, a[I]);   // positions 2I+1, 2I+3, ... (odd)
-    if constexpr (I + 2 < N) mad_chain<N, I + 2, false>(acc[0], I, a, a[I]);   // positions 2I+2, 2I+4, ... (even)
-    if constexpr (I + 2 < N) SqrCross<N, I + 1>::run(acc, a);
-  }
-};
-
-// t[0..2N) = a * a:  2 * sum_{i<j} a_i a_j 2^(32(i+j)) + sum_i a_i^2 2^(64 i)   (N(N-1)/2 + N products instead of N^2)
-template <int N>
-HD void wide_sqr_raw(uint32_t* t, const uint32_t* a) {
-  uint32_t acc[2][2 * N + 3];
-#pragma unroll
-  for (int k = 0; k < 2 * N + 3; k++) { acc[0][k] = 0; acc[1][k] = 0; }
-  SqrCross<N, 0>::run(acc, a);
-  uint32_t c[2 * N];
-  c[0] = ptx::add_cc(acc[0][0], acc[1][0]);
-#pragma unroll
-  for (int k = 1; k < 2 * N; k++) c[k] = ptx::addc_cc(acc[0][k], acc[1][k]);
-  (void)ptx::addc(0, 0);
-  // double (the cross sum is < 2^(64N - 1))
-#pragma unroll
-  for (int k = 2 * N - 1; k > 0; k--) c[k] = (c[k] << 1) | (c[k - 1] >> 31);
-  c[0] <<= 1;
-  // add the diagonal a_i^2 at words 2i, 2i+1
-  t[0] = ptx::mad_lo_cc(a[0], a[0], c[0]);
-  t[1] = ptx::madc_hi_cc(a[0], a[0], c[1]);
-#pragma unroll
-  for (int i = 1; i < N; i++) {
-    t[2 * i] = ptx::madc_lo_cc(a[i], a[i], c[2 * i]);
-    t[2 * i + 1] = ptx::madc_hi_cc(a[i], a[i], c[2 * i + 1]);
-  }
   (void)ptx::addc(0, 0);
 }
 
@@ -319,61 +219,21 @@ struct alignas(16) Fp {
 
   HD friend Fp operator+(const Fp& a, const Fp& b) { Fp r; mod_add_raw<P>(r.l, a.l, b.l); return r; }
   HD friend Fp operator-(const Fp& a, const Fp& b) { Fp r; mod_sub_raw<P>(r.l, a.l, b.l); return r; }
-#if defined(GB200_MONT_KARATSUBA)
-  // large fields: Karatsuba product + separate reduction (fewer multiplier operations than the fused product)
-  HD static void mul_dispatch(uint32_t* r, const uint32_t* a, const uint32_t* b) {
-    if constexpr (N >= GB200_KARATSUBA_MIN_LIMBS) { uint32_t t[2 * N]; wide_mul_karatsuba<N>(t, a, b); mont_reduce_wide<P>(r, t); }
-    else mont_mul_raw<P>(r, a, b);
-  }
-#else
-  HD static void mul_dispatch(uint32_t* r, const uint32_t* a, const uint32_t* b) { mont_mul_raw<P>(r, a, b); }
-#endif
-#ifndef GB200_INLINE_LIMBS
-#define GB200_INLINE_LIMBS 8      // fields of up to this many 32-bit limbs get the product inlined at every use
-#endif
+  // Fields of up to 8 limbs get the product inlined at every use; larger ones keep ONE copy of the unrolled product per
+  // kernel (I-cache, compile time), called with operands and result in REGISTERS: a reference parameter makes the
+  // caller spill both operands to its stack frame and the callee load them back (round-2 A/B on B200: BLS12-381 G1
+  // accumulate 8.39 -> 6.75 ms, BW6-761 18.4 -> 12.6 ms, BN254 G2 11.4 -> 10.0 ms with operands by value).
+  static constexpr int INLINE_LIMBS = 8;
 #if defined(__CUDA_ARCH__)
-  // large fields: keep one copy of the unrolled product per kernel (I-cache, compile time)
-#if defined(GB200_CALL_BYVAL)
-  // operands and result of the out-of-line product travel in registers: a reference parameter forces the caller to
-  // spill both operands to its stack frame and the callee to load them back (checked in SASS: 0 LDL/STL by value)
-  static __device__ __noinline__ Fp mul_ni(Fp a, Fp b) { Fp r; mul_dispatch(r.l, a.l, b.l); return r; }
-#else
-  static __device__ __noinline__ Fp mul_ni(const Fp& a, const Fp& b) { Fp r; mul_dispatch(r.l, a.l, b.l); return r; }
-#endif
+  static __device__ __noinline__ Fp mul_ni(Fp a, Fp b) { Fp r; mont_mul_raw<P>(r.l, a.l, b.l); return r; }
   HD friend Fp operator*(const Fp& a, const Fp& b) {
-    if (N > GB200_INLINE_LIMBS) return mul_ni(a, b);
-    Fp r; mul_dispatch(r.l, a.l, b.l); return r;
+    if (N > INLINE_LIMBS) return mul_ni(a, b);
+    Fp r; mont_mul_raw<P>(r.l, a.l, b.l); return r;
   }
 #else
-  HD friend Fp operator*(const Fp& a, const Fp& b) { Fp r; mul_dispatch(r.l, a.l, b.l); return r; }
+  HD friend Fp operator*(const Fp& a, const Fp& b) { Fp r; mont_mul_raw<P>(r.l, a.l, b.l); return r; }
 #endif
-#if defined(GB200_MONT_SQR)
-  HD Fp sqr() const {
-    uint32_t t[2 * N];
-    wide_sqr_raw<N>(t, l);
-    Fp r; mont_reduce_wide<P>(r.l, t); return r;
-  }
-#else
   HD Fp sqr() const { return (*this) * (*this); }
-#endif
-  // a*b - c*d with ONE Montgomery reduction: a b + (p^2 - c d) < 2 p^2 < p R (top bit of p clear), reduced once.
-  // Used by the XYZZ mixed addition under GB200_XYZZ_LAZY (Y3 = R (Q - X3) - Y1 PPP): one reduction (N^2 + N
-  // multiplier operations) less per addition.  Bit-exact with a*b - c*d (emulation: test_wide_arithmetic).
-  HD static Fp mul_sub(const Fp& a, const Fp& b, const Fp& c, const Fp& d) {
-    uint32_t t0[2 * N], t1[2 * N], q[2 * N];
-#if defined(GB200_MONT_KARATSUBA)
-    wide_mul_karatsuba<N>(t0, a.l, b.l);
-    wide_mul_karatsuba<N>(t1, c.l, d.l);
-#else
-    wide_mul_raw<N>(t0, a.l, b.l);
-    wide_mul_raw<N>(t1, c.l, d.l);
-#endif
-#pragma unroll
-    for (int k = 0; k < 2 * N; k++) q[k] = P::psq(k);
-    limbs_sub<2 * N>(q, q, t1);
-    limbs_add<2 * N>(t0, t0, q);
-    Fp r; mont_reduce_wide<P>(r.l, t0); return r;
-  }
   HD Fp neg() const { return is_zero() ? *this : (zero() - *this); }
   HD Fp dbl() const { return *this + *this; }
   // Montgomery -> canonical (multiply by 1) and back
@@ -393,101 +253,6 @@ struct alignas(16) Fp {
       }
     }
     return result;
-  }
-  // Same result as inverse() by the binary extended Euclidean algorithm (Kaliski's "almost Montgomery inverse"):
-  // shifts, additions and subtractions only, on the ALU pipe instead of ~1.5*BITS Montgomery products on the
-  // multiplier pipe.  Phase 1 gives x^-1 * 2^k mod p (BITS <= k <= 2*BITS) for the stored value x = a*R;
-  // a^-1 * R = x^-1 * R^2 = x^-1 * 2^(64N), so phase 2 is 64N - k modular doublings.  Needs the top bit of the top
-  // limb of p clear (r, s < 2p must fit N limbs): true for every modulus here.
-  // Kaliski's single-bit cases are merged so that a warp does not diverge: with u, v both odd and (u, r) kept as
-  // the larger pair (conditional swap), one iteration is  u -= v; r += s; t = ctz(u); u >>= t; s <<= t; k += t
-  // (his "u > v" step followed by t-1 "u even" steps), about 0.8*BITS iterations in all.
-  HD Fp inverse_gcd() const {
-    if (is_zero()) return zero();
-    uint32_t u[N], v[N], r[N], s[N];
-#pragma unroll
-    for (int i = 0; i < N; i++) { u[i] = P::mod(i); v[i] = l[i]; r[i] = 0; s[i] = 0; }
-    s[0] = 1;
-    auto ctz32 = [](uint32_t x) -> int {
-#if defined(__CUDA_ARCH__)
-      return __ffs((int)x) - 1;
-#else
-      return __builtin_ctz(x);
-#endif
-    };
-    auto shr = [](uint32_t* a, int t) {       // 0 < t < 32
-#pragma unroll
-      for (int i = 0; i < N - 1; i++) a[i] = (a[i] >> t) | (a[i + 1] << (32 - t));
-      a[N - 1] >>= t;
-    };
-    auto shl = [](uint32_t* a, int t) {       // 0 < t < 32
-#pragma unroll
-      for (int i = N - 1; i > 0; i--) a[i] = (a[i] << t) | (a[i - 1] >> (32 - t));
-      a[0] <<= t;
-    };
-    auto shr_limb = [](uint32_t* a) {
-#pragma unroll
-      for (int i = 0; i < N - 1; i++) a[i] = a[i + 1];
-      a[N - 1] = 0;
-    };
-    auto shl_limb = [](uint32_t* a) {
-#pragma unroll
-      for (int i = N - 1; i > 0; i--) a[i] = a[i - 1];
-      a[0] = 0;
-    };
-    auto add = [](uint32_t* a, const uint32_t* b) {
-      uint64_t c = 0;
-#pragma unroll
-      for (int i = 0; i < N; i++) { c += (uint64_t)a[i] + b[i]; a[i] = (uint32_t)c; c >>= 32; }
-    };
-    auto sub = [](uint32_t* a, const uint32_t* b) {
-      uint64_t br = 0;
-#pragma unroll
-      for (int i = 0; i < N; i++) { const uint64_t d = (uint64_t)a[i] - b[i] - br; a[i] = (uint32_t)d; br = (d >> 32) & 1; }
-    };
-    // -1 / 0 / +1 for a < b / a == b / a > b, without data-dependent branches
-    auto cmp = [](const uint32_t* a, const uint32_t* b) -> int {
-      int res = 0;
-#pragma unroll
-      for (int i = 0; i < N; i++) res = a[i] != b[i] ? (a[i] > b[i] ? 1 : -1) : res;
-      return res;
-    };
-    int k = 0;
-    // x is non-zero: strip its trailing zeros (Kaliski's "v even" steps; r = 0 so r <<= t is a no-op)
-    while (v[0] == 0) { shr_limb(v); k += 32; }
-    { const int t = ctz32(v[0]); if (t) { shr(v, t); k += t; } }
-    bool swapped = false;                    // false: (u, r) / (v, s) are Kaliski's pairs; true: exchanged
-    for (;;) {
-      const int c = cmp(u, v);
-      if (c == 0) break;
-      if (c < 0) {                           // keep u > v
-#pragma unroll
-        for (int i = 0; i < N; i++) {
-          const uint32_t tu = u[i]; u[i] = v[i]; v[i] = tu;
-          const uint32_t tr = r[i]; r[i] = s[i]; s[i] = tr;
-        }
-        swapped = !swapped;
-      }
-      sub(u, v);
-      add(r, s);
-      while (u[0] == 0) { shr_limb(u); shl_limb(s); k += 32; }
-      const int t = ctz32(u[0]);             // u - v is even and non-zero: t >= 1 unless whole limbs were stripped
-      if (t) { shr(u, t); shl(s, t); k += t; }
-    }
-    // u == v (== gcd = 1): Kaliski's last step  v = 0, s += r, r = 2r, k++  ->  result r
-    uint32_t* rr = swapped ? s : r;
-    shl(rr, 1);
-    k++;
-    uint32_t pm[N];
-#pragma unroll
-    for (int i = 0; i < N; i++) pm[i] = P::mod(i);
-    if (cmp(rr, pm) >= 0) sub(rr, pm);
-    sub(pm, rr);                             // p - r = x^-1 * 2^k mod p
-    Fp out;
-#pragma unroll
-    for (int i = 0; i < N; i++) out.l[i] = pm[i];
-    for (; k < 64 * N; k++) out = out.dbl();
-    return out;
   }
   // multiply by a small unsigned constant via additions
   HD Fp mul_small(unsigned k) const {
@@ -510,14 +275,7 @@ struct alignas(16) Fp {
 // rule restated from std/algebra/emulated/fields_bn254/e2.go:203-213 and
 // std/algebra/native/fields_bls12377/e2.go:134.  Memory = gnark E2{A0, A1}.
 // ---------------------------------------------------------------------------
-// Fp2 product / square: out of line by default (one copy of the 3-multiplication body per kernel);
-// -DGB200_INLINE_FP2 inlines them at every use (A/B knob: no call, no stack round trip, larger code)
-#if defined(GB200_INLINE_FP2)
-#define HD_FP2 HD
-#else
-#define HD_FP2 HDNI
-#endif
-
+// Fp2 product / square: out of line (one copy of the 3-multiplication body per kernel), operands by value on the device
 template <class T> struct is_device_fp { static constexpr bool value = false; };
 template <class P> struct is_device_fp<Fp<P>> { static constexpr bool value = true; };
 
@@ -561,15 +319,9 @@ struct alignas(16) Fp2 {
     mont_reduce_wide<P>(r.a1.l, t2);
     return r;
   }
-#if defined(GB200_CALL_BYVAL) && defined(__CUDA_ARCH__)
-  HD_FP2 static Fp2 mul(Fp2 x, Fp2 y) {
-#else
-  HD_FP2 static Fp2 mul(const Fp2& x, const Fp2& y) {
-#endif
-#if defined(GB200_FP2_LAZY)
+  HDNI static Fp2 mul(Fp2 x, Fp2 y) {        // by value: operands travel in registers (see Fp::mul_ni)
     if constexpr (is_device_fp<F>::value) return mul_lazy<F>(x, y);
-#endif
-    // Karatsuba: 3 base multiplications
+    // generic base field (host-side 64-bit limbs): Karatsuba, 3 base multiplications
     F v0 = x.a0 * y.a0;
     F v1 = x.a1 * y.a1;
     F s = (x.a0 + x.a1) * (y.a0 + y.a1);
@@ -579,9 +331,8 @@ struct alignas(16) Fp2 {
     return r;
   }
   HD friend Fp2 operator*(const Fp2& x, const Fp2& y) { return mul(x, y); }
-#if defined(GB200_CALL_BYVAL) && defined(__CUDA_ARCH__)
   HDNI static Fp2 sqr_ni(Fp2 x) {
-    if (BETA == 1) {
+    if (BETA == 1) {  // (a0+a1)(a0-a1), 2 a0 a1
       Fp2 r;
       F t = x.a0 * x.a1;
       r.a0 = (x.a0 + x.a1) * (x.a0 - x.a1);
@@ -591,18 +342,6 @@ struct alignas(16) Fp2 {
     return mul(x, x);
   }
   HD Fp2 sqr() const { return sqr_ni(*this); }
-#else
-  HD_FP2 Fp2 sqr() const {
-    if (BETA == 1) {  // (a0+a1)(a0-a1), 2 a0 a1
-      Fp2 r;
-      F t = a0 * a1;
-      r.a0 = (a0 + a1) * (a0 - a1);
-      r.a1 = t + t;
-      return r;
-    }
-    return mul(*this, *this);
-  }
-#endif
   HD Fp2 neg() const { Fp2 r; r.a0 = a0.neg(); r.a1 = a1.neg(); return r; }
   HD Fp2 dbl() const { Fp2 r; r.a0 = a0.dbl(); r.a1 = a1.dbl(); return r; }
   HD Fp2 inverse() const {
@@ -611,20 +350,7 @@ struct alignas(16) Fp2 {
     Fp2 r; r.a0 = a0 * ni; r.a1 = (a1 * ni).neg();
     return r;
   }
-  HD Fp2 inverse_gcd() const {
-    F n = a0.sqr() + mul_beta(a1.sqr());
-    F ni = n.inverse_gcd();
-    Fp2 r; r.a0 = a0 * ni; r.a1 = (a1 * ni).neg();
-    return r;
-  }
 };
-
-// 52-bit-limb (FP64 pipe) parameter pack of a base field, when one exists (field52.cuh)
-template <class F> struct F52Traits { static constexpr bool ok = false; using P52 = void; };
-template <> struct F52Traits<Fp<bn254_fp_params>> { static constexpr bool ok = true; using P52 = bn254_fp_params52; };
-template <> struct F52Traits<Fp<bls12_381_fp_params>> { static constexpr bool ok = true; using P52 = bls12_381_fp_params52; };
-template <> struct F52Traits<Fp<bls12_377_fp_params>> { static constexpr bool ok = true; using P52 = bls12_377_fp_params52; };
-template <> struct F52Traits<Fp<bw6_761_fp_params>> { static constexpr bool ok = true; using P52 = bw6_761_fp_params52; };
 
 // concrete fields
 using bn254_fp = Fp<bn254_fp_params>;

@@ -20,46 +20,28 @@ struct MsmInst {
                       uint32_t chunk) {
     return msm_make_plan(n, stride, off, Fr::Params::BITS, c, precomp, task_len, chunk);
   }
-  static cudaError_t ws_bytes(uint32_t n, uint32_t stride, int c, int precomp, uint32_t task_len, uint32_t chunk,
-                              int ba_levels, size_t* out) {
+  static cudaError_t ws_bytes(uint32_t n, uint32_t stride, int c, int precomp, uint32_t task_len, uint32_t chunk, size_t* out) {
     MsmLayout<F> L;
     MsmPlan pl = plan(n, stride, 0, c, precomp, task_len, chunk);
-    pl.ba_levels = ba_levels;
     GB_CUDA_TRY(msm_layout<F>(pl, L));
     *out = L.total;
     return cudaSuccess;
   }
   static cudaError_t run(cudaStream_t st, uint32_t n, uint32_t stride, uint32_t off, int c, int precomp,
                          uint32_t task_len, uint32_t chunk, const void* d_table, const void* d_scalars,
-                         void* d_out_jac, void* ws, cudaEvent_t* ev, cudaStream_t tail, cudaEvent_t fork_ev, int fmt52,
-                         const MsmHybrid* hybrid) {
+                         void* d_out_jac, void* ws, cudaEvent_t* ev, cudaStream_t tail, cudaEvent_t fork_ev, int persistent) {
     MsmPlan pl = plan(n, stride, off, c, precomp, task_len, chunk);
-    pl.ba_levels = (hybrid && !fmt52) ? hybrid->ba_levels : 0;
-    pl.persistent = (hybrid && !fmt52) ? hybrid->persistent : 0;
-    pl.smem_acc = (hybrid && !fmt52) ? hybrid->smem_acc : 0;
+    pl.persistent = persistent;
     MsmLayout<F> L;
     GB_CUDA_TRY(msm_layout<F>(pl, L));
     return msm_enqueue<Fr, F>(st, pl, reinterpret_cast<const Affine<F>*>(d_table),
-                              reinterpret_cast<const Fr*>(d_scalars), reinterpret_cast<Jacobian<F>*>(d_out_jac), ws, L, ev, tail, fork_ev, fmt52, hybrid);
+                              reinterpret_cast<const Fr*>(d_scalars), reinterpret_cast<Jacobian<F>*>(d_out_jac), ws, L, ev, tail, fork_ev);
   }
   // d_table holds the n bases in slab 0 already; slabs 1.. are filled in place
   static cudaError_t precompute(cudaStream_t st, uint32_t n, int nwin, int c, void* d_table) {
     if (n == 0 || nwin <= 1) return cudaSuccess;
     Affine<F>* t = reinterpret_cast<Affine<F>*>(d_table);
-    return msm_precompute_enqueue<F, Affine<F>, ConvIdentity<F>>(st, n, nwin, c, t, t);
-  }
-  static size_t affine52_bytes() {
-    if constexpr (F52Traits<F>::ok) return sizeof(Affine52<typename F52Traits<F>::P52>);
-    else return 0;
-  }
-  static cudaError_t precompute52(cudaStream_t st, uint32_t n, int nwin, int c, const void* d_src, void* d_table52) {
-    if constexpr (F52Traits<F>::ok) {
-      using P52 = typename F52Traits<F>::P52;
-      return msm_precompute_enqueue<F, Affine52<P52>, ConvTo52<F, P52>>(st, n, nwin, c, reinterpret_cast<const Affine<F>*>(d_src),
-                                                                      reinterpret_cast<Affine52<P52>*>(d_table52));
-    } else {
-      return cudaErrorNotSupported;
-    }
+    return msm_precompute_enqueue<F>(st, n, nwin, c, t, t);
   }
   static cudaError_t fixed_base(cudaStream_t st, const void* h_base, const void* d_scalars, size_t n, int c,
                                 void* d_out_affine) {
@@ -74,9 +56,27 @@ struct MsmInst {
                                                        reinterpret_cast<Jacobian<F>*>(d_out_jac));
     return cudaGetLastError();
   }
+  using FB = typename F::Base;
+  static size_t encoded_bytes(int encoding) {
+    if (encoding == POINTS_RAW) return sizeof(Affine<F>);
+    if (encoding == POINTS_COMPRESSED && F::DEGREE == 1) return sizeof(F);
+    return 0;
+  }
+  static cudaError_t decode(cudaStream_t st, const void* d_bytes, size_t n, int encoding, int b_small, void* d_out_affine,
+                            uint32_t* d_status) {
+    if (n == 0) return cudaSuccess;
+    if (encoded_bytes(encoding) == 0) return cudaErrorNotSupported;
+    const DecodeConsts<FB> k = decode_make_consts<FB>(b_small);
+    if (encoding == POINTS_COMPRESSED && !k.sqrt_ok) return cudaErrorNotSupported;     // p = 1 mod 4: Tonelli-Shanks not built
+    const size_t stride = encoded_bytes(encoding);
+    k_points_decode<F, FB><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(reinterpret_cast<const uint8_t*>(d_bytes), n, stride,
+                                                                       encoding == POINTS_COMPRESSED ? 1 : 0, k,
+                                                                       reinterpret_cast<Affine<F>*>(d_out_affine), d_status);
+    return cudaGetLastError();
+  }
   static const MsmOps* ops() {
     static const MsmOps o = {Fr::Params::BITS, sizeof(Fr), sizeof(Affine<F>), sizeof(Jacobian<F>), &ws_bytes, &run,
-                             &precompute, affine52_bytes(), &precompute52, &fixed_base, &fold};
+                             &precompute, &fixed_base, &fold, &encoded_bytes, &decode};
     return &o;
   }
 };

@@ -27,45 +27,30 @@ struct AsyncBuf {
   }
 };
 
-// Opt-in experiment (GB200_MSM_HYBRID=<percent>): the bucket-accumulate tasks are split between the
-// IMAD.WIDE kernel and its FP64-pipe twin, launched concurrently on two streams so that both multiplier
-// pipes of an SM are busy at once (the pipes are independent: profiles/r01_microbench_pipes.txt).
-struct MsmHybrid {
-  const void* d_table52;   // same table in Affine52 format
-  int blocks52_of_16;      // of every 16 consecutive 128-task blocks, this many go to the FP64 kernel (1..15)
-  cudaStream_t aux;        // second stream
-  cudaEvent_t fork_ev, join_ev;
-  // second opt-in experiment (GB200_MSM_BATCH_AFFINE=<levels>, msm_batch.cuh): batched-affine tree levels
-  int ba_levels;
-  // third opt-in experiment (GB200_MSM_PERSISTENT=1): accumulate on a grid sized to the SMs, tasks from an atomic counter
-  int persistent;
-  // fourth opt-in experiment (GB200_MSM_SMEM_ACC=1): accumulator coordinates in shared memory, more resident warps
-  int smem_acc;
-};
-
 struct MsmOps {
   int scalar_bits;      // Fr bit length
   size_t fr_bytes;      // sizeof(fr.Element)
   size_t affine_bytes;  // sizeof(G?Affine)
   size_t jac_bytes;     // sizeof(G?Jac)
   // workspace bytes for an MSM of n scalars with the given parameters
-  cudaError_t (*ws_bytes)(uint32_t n, uint32_t stride, int c, int precomp, uint32_t task_len, uint32_t chunk,
-                          int ba_levels, size_t* out);
+  cudaError_t (*ws_bytes)(uint32_t n, uint32_t stride, int c, int precomp, uint32_t task_len, uint32_t chunk, size_t* out);
   // enqueue a full MSM (all pointers on device)
   cudaError_t (*run)(cudaStream_t st, uint32_t n, uint32_t stride, uint32_t off, int c, int precomp,
                      uint32_t task_len, uint32_t chunk, const void* d_table, const void* d_scalars, void* d_out_jac,
                      void* ws, cudaEvent_t* stage_events /* nullable, 8 entries */,
-                     cudaStream_t tail /* nullable */, cudaEvent_t fork_ev, int fmt52,
-                     const MsmHybrid* hybrid /* nullable */);
+                     cudaStream_t tail /* nullable */, cudaEvent_t fork_ev, int persistent /* GB200_MSM_PERSISTENT */);
   // fill slabs 1..nwin-1 of a [nwin][n] table whose slab 0 holds the bases
   cudaError_t (*precompute)(cudaStream_t st, uint32_t n, int nwin, int c, void* d_table);
-  // FP64-pipe table format (field52.cuh): bytes per entry, 0 when the group has no such path
-  size_t affine52_bytes;
-  cudaError_t (*precompute52)(cudaStream_t st, uint32_t n, int nwin, int c, const void* d_src, void* d_table52);
   // fixed-base batch (fixed_base.cuh): d_out[i] = scalars[i] * base; h_base is ONE affine point on the host
   cudaError_t (*fixed_base)(cudaStream_t st, const void* h_base, const void* d_scalars, size_t n, int c, void* d_out_affine);
   // multi-GPU combine: d_out[k] = sum_r d_gathered[r * count + k] (Jacobian points, k_points_fold)
   cudaError_t (*fold)(cudaStream_t st, const void* d_gathered, uint32_t world, uint32_t count, void* d_out_jac);
+  // serialised point slices (gnark-crypto encodings, points_decode.cuh): bytes per point of an encoding (0 = not
+  // supported for this group), and the decode kernel.  b_small: the curve coefficient as a small signed integer;
+  // d_status: two uint32 (DECODE_* code, index), zeroed by the caller
+  size_t (*encoded_bytes)(int encoding);
+  cudaError_t (*decode)(cudaStream_t st, const void* d_bytes, size_t n, int encoding, int b_small, void* d_out_affine,
+                        uint32_t* d_status);
 };
 
 struct NttOps {

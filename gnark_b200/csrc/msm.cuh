@@ -23,7 +23,6 @@
 // all windows share ONE bucket set.  PLAIN: table = the n points; W bucket sets.
 #pragma once
 #include "curve.cuh"
-#include "curve52.cuh"
 
 namespace gb200 {
 
@@ -39,9 +38,7 @@ struct MsmPlan {
   uint32_t total_buckets; // nsets * set_size ; also the "no entry" key
   uint32_t task_len;      // max entries per accumulate task
   uint32_t chunk;         // buckets per level-1 reduction chunk
-  int ba_levels;          // batched-affine tree levels before the XYZZ accumulate (msm_batch.cuh), 0 = off
   int persistent;         // opt-in: accumulate tasks handed out by an atomic counter to a grid sized to the SMs
-  int smem_acc;           // opt-in: accumulator coordinates in shared memory (SmemXYZZ), register cap by field size
 };
 
 HD int msm_num_windows(int scalar_bits, int c) { return scalar_bits / c + 1; }
@@ -56,9 +53,7 @@ HD MsmPlan msm_make_plan(uint32_t n, uint32_t table_stride, uint32_t table_off, 
   p.set_size = 1u << (c - 1);
   p.total_buckets = (uint32_t)p.nsets * p.set_size;
   p.task_len = task_len;
-  p.ba_levels = 0;
   p.persistent = 0;
-  p.smem_acc = 0;
   p.chunk = chunk;
   return p;
 }
@@ -112,63 +107,10 @@ HD Affine<F> msm_load_point(const Affine<F>* table, uint32_t val) {
 template <class F>
 HD XYZZ<F> msm_accumulate_range(const Affine<F>* table, const uint32_t* vals, uint32_t begin, uint32_t end) {
   XYZZ<F> acc = XYZZ<F>::inf();
-#if defined(GB200_ACC_PREFETCH)
-  // A/B knob: the gather of entry e+1 (a random 64..192 B read from a GiB-sized table, ~10 % of the issue slots are
-  // long-scoreboard stalls in the ncu capture) is started as an L2 prefetch while the addition of entry e runs
-  if (begin >= end) return acc;
-  uint32_t v = vals[begin];
-  for (uint32_t e = begin; e < end; e++) {
-    const uint32_t cur = v;
-    if (e + 1 < end) {
-      v = vals[e + 1];
-      const char* nxt = reinterpret_cast<const char*>(table + (v & 0x7fffffffu));
-      ptx::prefetch_l2(nxt);
-      if (sizeof(Affine<F>) > 128) ptx::prefetch_l2(nxt + 128);
-    }
-    acc.add_mixed(msm_load_point(table, cur));
-  }
-#else
   for (uint32_t e = begin; e < end; e++) acc.add_mixed(msm_load_point(table, vals[e]));
-#endif
   return acc;
 }
 
-// the same range with the accumulator in shared memory (SmemXYZZ, curve.cuh)
-template <class F>
-HD XYZZ<F> msm_accumulate_range_smem(const Affine<F>* table, const uint32_t* vals, uint32_t begin, uint32_t end,
-                                     uint32_t* smem_base, uint32_t stride) {
-  SmemXYZZ<F> acc{smem_base, stride};
-  acc.set(XYZZ<F>::inf());
-  for (uint32_t e = begin; e < end; e++) acc.add_mixed(msm_load_point(table, vals[e]));
-  return acc.get();
-}
-
-// FP64-pipe variant (field52.cuh / curve52.cuh): table entries are Affine52, the accumulator is
-// XYZZ52, the task result is converted once to the 32-bit representation of the reduction kernels
-template <class P52, class F>
-HD XYZZ<F> msm_accumulate_range52(const Affine52<P52>* table, const uint32_t* vals, uint32_t begin, uint32_t end) {
-  XYZZ52<P52> acc = XYZZ52<P52>::inf();
-  for (uint32_t e = begin; e < end; e++) {
-    const uint32_t v = vals[e];
-    const Affine52<P52>& a = table[v & 0x7fffffffu];
-    D52<P52> ax, ay;
-#pragma unroll
-    for (int i = 0; i < P52::L; i++) { ax.d[i] = a.x[i]; ay.d[i] = a.y[i]; }
-    acc.add_mixed(ax, ay, (v >> 31) != 0);
-  }
-  return acc.template to_xyzz32<F>();
-}
-
-// ---- 4b. hybrid split of the accumulate tasks ---------------------------------
-// Hybrid split (opt-in, MsmHybrid): the same two kernels over a SUBSET of the 128-task blocks.  Of every
-// `period` consecutive virtual blocks, `count` starting at `first` belong to this launch:
-//   virtual block = (blockIdx / count) * period + first + blockIdx % count
-HD uint32_t msm_virtual_block(uint32_t block, uint32_t period, uint32_t first, uint32_t count) {
-  return (block / count) * period + first + block % count;
-}
-HD uint32_t msm_split_grid(uint32_t total_blocks, uint32_t period, uint32_t count) {
-  return ((total_blocks + period - 1) / period) * count;
-}
 // entries [begin, end) of task t (false: t is past the last task); the same arithmetic as k_msm_accumulate
 HD bool msm_task_bounds(const MsmPlan& pl, const uint32_t* off, const uint32_t* task_off, uint32_t t, uint32_t& begin,
                         uint32_t& end) {
@@ -192,34 +134,18 @@ HD bool msm_task_bounds(const MsmPlan& pl, const uint32_t* off, const uint32_t* 
 // the next one.  A lane whose task was short goes straight on to another task instead of idling until the longest
 // task of its warp ends (every bucket's last task is a short one), and the last wave of a task-sized grid, which
 // fills only part of the machine, disappears.  partial[] is indexed by task as before, so nothing downstream changes.
-// where a thread keeps the accumulator of its current task: registers (default) or shared memory (SmemXYZZ, curve.cuh)
-template <class F>
-struct MsmRegAcc {
-  XYZZ<F> v;
-  HD void reset() { v = XYZZ<F>::inf(); }
-  HD void add_mixed(const Affine<F>& a) { v.add_mixed(a); }
-  HD XYZZ<F> get() const { return v; }
-};
-template <class F>
-struct MsmSmemAcc {
-  SmemXYZZ<F> s;
-  HD void reset() { s.set(XYZZ<F>::inf()); }
-  HD void add_mixed(const Affine<F>& a) { s.add_mixed(a); }
-  HD XYZZ<F> get() const { return s.get(); }
-};
-
-template <class F, class NEXT, class ACC = MsmRegAcc<F>>
+template <class F, class NEXT>
 HD void msm_accumulate_persistent(const MsmPlan& pl, const Affine<F>* table, const uint32_t* vals, const uint32_t* off,
-                                  const uint32_t* task_off, XYZZ<F>* partial, NEXT next_task, ACC acc = ACC()) {
-  acc.reset();
+                                  const uint32_t* task_off, XYZZ<F>* partial, NEXT next_task) {
+  XYZZ<F> acc = XYZZ<F>::inf();
   uint32_t e = 0, end = 0, t = 0;
   bool have = false;
   for (;;) {
     if (e == end) {
-      if (have) partial[t] = acc.get();
+      if (have) partial[t] = acc;
       t = next_task();
       if (!msm_task_bounds(pl, off, task_off, t, e, end)) return;   // past the last task
-      acc.reset();
+      acc = XYZZ<F>::inf();
       have = true;
       if (e == end) continue;                                        // an empty task stores infinity
     }

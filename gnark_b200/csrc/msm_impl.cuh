@@ -6,7 +6,7 @@
 
 #include "internal.h"
 #include "msm.cuh"
-#include "msm_batch.cuh"
+#include "points_decode.cuh"
 
 namespace gb200 {
 
@@ -47,16 +47,8 @@ static __global__ void k_msm_task_counts(const uint32_t* __restrict__ off, uint3
 }
 
 // one thread per task: partial[t] = sum of <= task_len consecutive entries of one bucket
-// -DGB200_ACC_MIN_BLOCKS=k: ask ptxas for k resident blocks per SM (register cap 65536 / (128 k), rounded down to the
-// allocation unit) - A/B knob for the arithmetic variants that land just above a register step
-#if defined(GB200_ACC_MIN_BLOCKS)
-// (applies to the 8-limb base-field kernels only: BN254 G1; larger fields keep the compiler's allocation)
-#define GB200_ACC_BOUNDS __launch_bounds__(128, (sizeof(F) <= 32) ? GB200_ACC_MIN_BLOCKS : 1)
-#else
-#define GB200_ACC_BOUNDS __launch_bounds__(128)
-#endif
 template <class F>
-__global__ void GB200_ACC_BOUNDS k_msm_accumulate(MsmPlan pl, const Affine<F>* __restrict__ table,
+__global__ void __launch_bounds__(128) k_msm_accumulate(MsmPlan pl, const Affine<F>* __restrict__ table,
                                                         const uint32_t* __restrict__ svals,
                                                         const uint32_t* __restrict__ off,
                                                         const uint32_t* __restrict__ task_off,
@@ -79,120 +71,15 @@ __global__ void GB200_ACC_BOUNDS k_msm_accumulate(MsmPlan pl, const Affine<F>* _
   partial[t] = msm_accumulate_range<F>(table, svals, begin, end);
 }
 
-// opt-in (GB200_MSM_SMEM_ACC): one thread per task as k_msm_accumulate, accumulator coordinates in shared memory.
-// The point of the exercise is occupancy, so the register cap follows the field size: 5 resident blocks for coordinates
-// of up to 64 B (BLS12-381 / BLS12-377 G1: 96 registers with ~220 B of spills instead of 126 and 4 blocks; BN254 G2: 96
-// instead of 144 registers and 3 blocks), 3 blocks for the 96-byte coordinates (BLS G2, BW6-761).  Shared memory per
-// block = 4 coordinates x sizeof(F) x 128 threads (24 .. 48 KiB).
-#ifndef GB200_SMEM_ACC_MIN_BLOCKS
-#define GB200_SMEM_ACC_MIN_BLOCKS (sizeof(F) <= 64 ? 5 : 3)
-#endif
-template <class F>
-__global__ void __launch_bounds__(128, GB200_SMEM_ACC_MIN_BLOCKS) k_msm_accumulate_smem(MsmPlan pl, const Affine<F>* __restrict__ table,
-                                                             const uint32_t* __restrict__ svals,
-                                                             const uint32_t* __restrict__ off,
-                                                             const uint32_t* __restrict__ task_off,
-                                                             XYZZ<F>* __restrict__ partial) {
-  extern __shared__ __align__(16) uint32_t acc_sm[];
-  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  uint32_t begin, end;
-  if (!msm_task_bounds(pl, off, task_off, t, begin, end)) return;
-  partial[t] = msm_accumulate_range_smem<F>(table, svals, begin, end, acc_sm + threadIdx.x, blockDim.x);
-}
-
 // opt-in (GB200_MSM_PERSISTENT): the same tasks on a grid sized to the machine, handed out by an atomic counter
 // (msm_accumulate_persistent, msm.cuh 4c)
 template <class F>
-__global__ void GB200_ACC_BOUNDS k_msm_accumulate_persistent(MsmPlan pl, const Affine<F>* __restrict__ table,
+__global__ void __launch_bounds__(128) k_msm_accumulate_persistent(MsmPlan pl, const Affine<F>* __restrict__ table,
                                                              const uint32_t* __restrict__ svals,
                                                              const uint32_t* __restrict__ off,
                                                              const uint32_t* __restrict__ task_off,
                                                              XYZZ<F>* __restrict__ partial, uint32_t* __restrict__ counter) {
   msm_accumulate_persistent<F>(pl, table, svals, off, task_off, partial, [counter]() { return atomicAdd(counter, 1u); });
-}
-
-// both opt-ins together: persistent grid, accumulators in shared memory
-template <class F>
-__global__ void __launch_bounds__(128, GB200_SMEM_ACC_MIN_BLOCKS)
-k_msm_accumulate_persistent_smem(MsmPlan pl, const Affine<F>* __restrict__ table, const uint32_t* __restrict__ svals,
-                                 const uint32_t* __restrict__ off, const uint32_t* __restrict__ task_off,
-                                 XYZZ<F>* __restrict__ partial, uint32_t* __restrict__ counter) {
-  extern __shared__ __align__(16) uint32_t acc_sm[];
-  MsmSmemAcc<F> acc{SmemXYZZ<F>{acc_sm + threadIdx.x, blockDim.x}};
-  msm_accumulate_persistent<F>(pl, table, svals, off, task_off, partial, [counter]() { return atomicAdd(counter, 1u); }, acc);
-}
-
-// FP64-pipe twin of k_msm_accumulate (field52.cuh / curve52.cuh): same task decomposition, table
-// entries are Affine52 (Montgomery R52, doubles), the accumulator lives in 52-bit limbs
-template <class F, class P52>
-__global__ void __launch_bounds__(128) k_msm_accumulate52(MsmPlan pl, const Affine52<P52>* __restrict__ table,
-                                                          const uint32_t* __restrict__ svals,
-                                                          const uint32_t* __restrict__ off,
-                                                          const uint32_t* __restrict__ task_off,
-                                                          XYZZ<F>* __restrict__ partial) {
-  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  const uint32_t nb = pl.total_buckets;
-  if (t >= __ldg(task_off + nb)) return;
-  uint32_t lo = 0, hi = nb;
-  while (lo < hi) {
-    const uint32_t mid = lo + ((hi - lo + 1) >> 1);
-    if (__ldg(task_off + mid) <= t) lo = mid; else hi = mid - 1;
-  }
-  const uint32_t b = lo;
-  const uint32_t j = t - __ldg(task_off + b);
-  const uint32_t begin = __ldg(off + b) + j * pl.task_len;
-  uint32_t end = begin + pl.task_len;
-  const uint32_t bend = __ldg(off + b + 1);
-  if (end > bend) end = bend;
-  partial[t] = msm_accumulate_range52<P52, F>(table, svals, begin, end);
-}
-
-// Hybrid split (opt-in, MsmHybrid; index helpers in msm.cuh)
-template <class F>
-__global__ void __launch_bounds__(128) k_msm_accumulate_split(MsmPlan pl, const Affine<F>* __restrict__ table,
-                                                              const uint32_t* __restrict__ svals,
-                                                              const uint32_t* __restrict__ off,
-                                                              const uint32_t* __restrict__ task_off,
-                                                              XYZZ<F>* __restrict__ partial, uint32_t period,
-                                                              uint32_t first, uint32_t count) {
-  const uint32_t t = msm_virtual_block(blockIdx.x, period, first, count) * blockDim.x + threadIdx.x;
-  uint32_t begin, end;
-  if (!msm_task_bounds(pl, off, task_off, t, begin, end)) return;
-  partial[t] = msm_accumulate_range<F>(table, svals, begin, end);
-}
-template <class F, class P52>
-__global__ void __launch_bounds__(128) k_msm_accumulate52_split(MsmPlan pl, const Affine52<P52>* __restrict__ table,
-                                                                const uint32_t* __restrict__ svals,
-                                                                const uint32_t* __restrict__ off,
-                                                                const uint32_t* __restrict__ task_off,
-                                                                XYZZ<F>* __restrict__ partial, uint32_t period,
-                                                                uint32_t first, uint32_t count) {
-  const uint32_t t = msm_virtual_block(blockIdx.x, period, first, count) * blockDim.x + threadIdx.x;
-  uint32_t begin, end;
-  if (!msm_task_bounds(pl, off, task_off, t, begin, end)) return;
-  partial[t] = msm_accumulate_range52<P52, F>(table, svals, begin, end);
-}
-
-// ---- batched-affine tree levels (opt-in, msm_batch.cuh) ----------------------------------
-// cnt[b] = ceil(k_b / 2) for b < nb, cnt[nb] = 0 (so that the exclusive scan yields nb + 1 offsets)
-static __global__ void k_msm_ba_next_counts(const uint32_t* __restrict__ off_in, uint32_t nb, uint32_t* __restrict__ cnt) {
-  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b > nb) return;
-  cnt[b] = b < nb ? msm_ba_next_count(off_in[b + 1] - off_in[b]) : 0u;
-}
-template <class F, class SRC>
-__global__ void __launch_bounds__(128) k_msm_ba_level(SRC src, const uint32_t* __restrict__ off_in,
-                                                      const uint32_t* __restrict__ off_out, uint32_t nb,
-                                                      Affine<F>* __restrict__ out, uint32_t batch) {
-  const uint32_t total = off_out[nb];
-  const uint64_t o_begin = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * batch;
-  if (o_begin >= total) return;
-  const uint32_t o_end = (uint32_t)(o_begin + batch < total ? o_begin + batch : total);
-  msm_ba_level_thread<F, SRC>(src, off_in, off_out, nb, (uint32_t)o_begin, o_end, out);
-}
-static __global__ void k_msm_iota(uint32_t* __restrict__ v, uint32_t n) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) v[i] = i;
 }
 
 // one thread per bucket: sum of its task partials.  Buckets with more than MSM_HEAVY partials
@@ -312,6 +199,20 @@ __global__ void __launch_bounds__(64) k_points_fold(const Jacobian<F>* __restric
   out[k] = acc.to_jacobian();
 }
 
+// one thread per point of a serialised slice (points_decode.cuh); status[0] = first non-zero DECODE_* code seen,
+// status[1] = index of a point that failed
+template <class F, class FB>
+__global__ void __launch_bounds__(128) k_points_decode(const uint8_t* __restrict__ bytes, size_t n, size_t stride, int compressed,
+                                                       DecodeConsts<FB> k, Affine<F>* __restrict__ out,
+                                                       uint32_t* __restrict__ status) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Affine<F> a = Affine<F>::inf();
+  const int rc = decode_point<F, FB>(bytes + i * stride, compressed, k, a);
+  out[i] = a;
+  if (rc != DECODE_OK && atomicCAS(status, 0u, (uint32_t)rc) == 0u) status[1] = (uint32_t)i;
+}
+
 // table precompute (built once per table upload): slab w holds 2^(c*w) * P_i.
 // pass 1: doubling chains, XYZZ results to a scratch buffer [w-1][chunk];
 // pass 2: one inversion per point (Montgomery's trick over its nwin-1 outputs), affine results.
@@ -327,15 +228,13 @@ __global__ void __launch_bounds__(128) k_msm_precompute_dbl(uint32_t cnt, int nw
     tmp[(size_t)(w - 1) * cnt + i] = q;
   }
 }
-// OUT = Affine<F> (32-bit layout) or Affine52<P52>; conv(affine) -> OUT
-template <class F, class OUT, class CONV>
+template <class F>
 __global__ void __launch_bounds__(128) k_msm_precompute_affine(uint32_t cnt, uint32_t n, uint32_t first, int nwin,
                                                                const Affine<F>* __restrict__ src,
-                                                               const XYZZ<F>* __restrict__ tmp, OUT* __restrict__ table,
-                                                               CONV conv) {
+                                                               const XYZZ<F>* __restrict__ tmp, Affine<F>* __restrict__ table) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= cnt) return;
-  table[first + i] = conv(src[i]);
+  table[first + i] = src[i];
   F pre[MSM_MAX_WINDOWS];
   F acc = F::one();
   for (int w = 1; w < nwin; w++) {
@@ -354,15 +253,13 @@ __global__ void __launch_bounds__(128) k_msm_precompute_affine(uint32_t cnt, uin
       a.x = q.x * zi2;
       a.y = q.y * zi3;
     }
-    table[(size_t)w * n + first + i] = conv(a);
+    table[(size_t)w * n + first + i] = a;
   }
 }
-template <class F> struct ConvIdentity { __device__ Affine<F> operator()(const Affine<F>& a) const { return a; } };
-template <class F, class P52> struct ConvTo52 { __device__ Affine52<P52> operator()(const Affine<F>& a) const { return affine_to_52<P52, F>(a); } };
 
-// d_src: n affine points; d_table: [nwin][n] entries of OUT
-template <class F, class OUT, class CONV>
-cudaError_t msm_precompute_enqueue(cudaStream_t st, uint32_t n, int nwin, int c, const Affine<F>* d_src, OUT* d_table) {
+// d_src: n affine points (may be slab 0 of d_table itself); d_table: [nwin][n] affine points
+template <class F>
+cudaError_t msm_precompute_enqueue(cudaStream_t st, uint32_t n, int nwin, int c, const Affine<F>* d_src, Affine<F>* d_table) {
   if (n == 0) return cudaSuccess;
   if (nwin > MSM_MAX_WINDOWS) return cudaErrorInvalidValue;
   const uint32_t chunk = n < (1u << 18) ? n : (1u << 18);
@@ -371,8 +268,7 @@ cudaError_t msm_precompute_enqueue(cudaStream_t st, uint32_t n, int nwin, int c,
   for (uint32_t first = 0; first < n; first += chunk) {
     const uint32_t cnt = n - first < chunk ? n - first : chunk;
     if (nwin > 1) k_msm_precompute_dbl<F><<<(cnt + 127) / 128, 128, 0, st>>>(cnt, nwin, c, d_src + first, tmp);
-    k_msm_precompute_affine<F, OUT, CONV><<<(cnt + 127) / 128, 128, 0, st>>>(cnt, n, first, nwin, d_src + first, tmp,
-                                                                          d_table, CONV());
+    k_msm_precompute_affine<F><<<(cnt + 127) / 128, 128, 0, st>>>(cnt, n, first, nwin, d_src + first, tmp, d_table);
   }
   GB_CUDA_TRY(cudaGetLastError());
   if (tmp) GB_CUDA_TRY(cudaFreeAsync(tmp, st));
@@ -392,9 +288,6 @@ struct MsmLayout {
   // offsets into the workspace
   size_t o_keys0, o_keys1, o_vals0, o_vals1, o_off, o_ntasks, o_task_off, o_partial, o_buckets, o_chunks, o_sets, o_heavy, o_cub,
       o_ctr, total;
-  // batched-affine levels (pl.ba_levels > 0): two ping-pong point buffers, two offset arrays, counts
-  size_t ba_cap_a, ba_cap_b;   // capacities in points
-  size_t o_ba_a, o_ba_b, o_ba_off_a, o_ba_off_b, o_ba_cnt;
 };
 
 inline size_t gb_align(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
@@ -427,18 +320,6 @@ cudaError_t msm_layout(const MsmPlan& pl, MsmLayout<F>& L) {
   L.o_heavy = o; o += gb_align((L.max_tasks / MSM_HEAVY + 2) * 4);  // [0] = count, [1..] = bucket ids
   L.o_cub = o; o += gb_align(L.cub_bytes);
   L.o_ctr = o; o += gb_align(4);      // task counter of the persistent accumulate
-  L.ba_cap_a = L.ba_cap_b = 0;
-  L.o_ba_a = L.o_ba_b = L.o_ba_off_a = L.o_ba_off_b = L.o_ba_cnt = 0;
-  if (pl.ba_levels > 0) {
-    // level l holds at most m / 2^l + nb entries (every bucket rounds up once per level)
-    L.ba_cap_a = L.m / 2 + pl.total_buckets + 1;
-    L.ba_cap_b = L.m / 4 + pl.total_buckets + 1;
-    L.o_ba_a = o; o += gb_align(L.ba_cap_a * sizeof(Affine<F>));
-    L.o_ba_b = o; o += gb_align(L.ba_cap_b * sizeof(Affine<F>));
-    L.o_ba_off_a = o; o += gb_align(((size_t)pl.total_buckets + 2) * 4);
-    L.o_ba_off_b = o; o += gb_align(((size_t)pl.total_buckets + 2) * 4);
-    L.o_ba_cnt = o; o += gb_align(((size_t)pl.total_buckets + 2) * 4);
-  }
   L.total = o;
   return cudaSuccess;
 }
@@ -451,7 +332,8 @@ inline int msm_set_sum_threads(size_t budget = 160 * 1024) {
   return t;
 }
 
-// the XYZZ accumulate: one thread per task (default) or, opt-in, a persistent grid fed by an atomic task counter
+// the XYZZ accumulate: one thread per task (default) or, opt-in (GB200_MSM_PERSISTENT=1), a persistent grid fed by an
+// atomic task counter
 template <class F>
 cudaError_t msm_launch_accumulate(cudaStream_t stream, const MsmPlan& pl, const MsmLayout<F>& L, const Affine<F>* table,
                                   const uint32_t* vals, const uint32_t* off, const uint32_t* task_off, XYZZ<F>* partial,
@@ -467,28 +349,6 @@ cudaError_t msm_launch_accumulate(cudaStream_t stream, const MsmPlan& pl, const 
     if (grid > need) grid = need;
     GB_CUDA_TRY(cudaMemsetAsync(counter, 0, 4, stream));
     k_msm_accumulate_persistent<F><<<(unsigned)grid, 128, 0, stream>>>(pl, table, vals, off, task_off, partial, counter);
-  } else if (pl.persistent == 2) {
-    // persistent grid + accumulators in shared memory
-    const size_t smem = 4 * sizeof(F) * 128;
-    int dev = 0, sms = 0, per_sm = 0;
-    GB_CUDA_TRY(cudaGetDevice(&dev));
-    GB_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    GB_CUDA_TRY(cudaFuncSetAttribute(k_msm_accumulate_persistent_smem<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    GB_CUDA_TRY(cudaFuncSetAttribute(k_msm_accumulate_persistent_smem<F>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                     (int)cudaSharedmemCarveoutMaxShared));
-    GB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_msm_accumulate_persistent_smem<F>, 128, smem));
-    if (per_sm < 1) per_sm = 1;
-    size_t grid = (size_t)sms * per_sm;
-    const size_t need = (L.max_tasks + 127) / 128;
-    if (grid > need) grid = need;
-    GB_CUDA_TRY(cudaMemsetAsync(counter, 0, 4, stream));
-    k_msm_accumulate_persistent_smem<F><<<(unsigned)grid, 128, smem, stream>>>(pl, table, vals, off, task_off, partial, counter);
-  } else if (pl.smem_acc) {
-    const size_t smem = 4 * sizeof(F) * 128;
-    GB_CUDA_TRY(cudaFuncSetAttribute(k_msm_accumulate_smem<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    GB_CUDA_TRY(cudaFuncSetAttribute(k_msm_accumulate_smem<F>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                     (int)cudaSharedmemCarveoutMaxShared));
-    k_msm_accumulate_smem<F><<<(unsigned)((L.max_tasks + 127) / 128), 128, smem, stream>>>(pl, table, vals, off, task_off, partial);
   } else {
     k_msm_accumulate<F><<<(unsigned)((L.max_tasks + 127) / 128), 128, 0, stream>>>(pl, table, vals, off, task_off, partial);
   }
@@ -500,8 +360,7 @@ cudaError_t msm_launch_accumulate(cudaStream_t stream, const MsmPlan& pl, const 
 template <class Fr, class F>
 cudaError_t msm_enqueue(cudaStream_t stream, const MsmPlan& pl, const Affine<F>* d_table, const Fr* d_scalars,
                         Jacobian<F>* d_out, void* ws, const MsmLayout<F>& L, cudaEvent_t* ev = nullptr,
-                        cudaStream_t tail = nullptr, cudaEvent_t fork_ev = nullptr, int fmt52 = 0,
-                        const MsmHybrid* hybrid = nullptr) {
+                        cudaStream_t tail = nullptr, cudaEvent_t fork_ev = nullptr) {
   // tail (optional): the latency-bound reduction kernels that follow the accumulate kernel are
   // enqueued on this second stream (forked with fork_ev), so that in a pipeline of MSMs they
   // overlap the next MSM's sort/accumulate instead of idling 140+ SMs.
@@ -538,77 +397,11 @@ cudaError_t msm_enqueue(cudaStream_t stream, const MsmPlan& pl, const Affine<F>*
                                               stream));
   GB_EV(2);
   k_msm_bucket_offsets<<<(nb + 1 + 255) / 256, 256, 0, stream>>>(keys1, (uint32_t)L.m, nb, off);
-  // what the XYZZ accumulate reads: the table through the sorted values, or (batched-affine levels on) the last
-  // level's points through identity values
-  const Affine<F>* acc_table = d_table;
-  const uint32_t* acc_vals = vals1;
-  if (pl.ba_levels > 0 && !fmt52) {
-    Affine<F>* bufs[2] = {(Affine<F>*)(w + L.o_ba_a), (Affine<F>*)(w + L.o_ba_b)};
-    uint32_t* offs[2] = {(uint32_t*)(w + L.o_ba_off_a), (uint32_t*)(w + L.o_ba_off_b)};
-    uint32_t* cnt = (uint32_t*)(w + L.o_ba_cnt);
-    const uint32_t* off_in = off;
-    size_t bound = L.m;                       // upper bound of the entries of the current level
-    for (int lvl = 0; lvl < pl.ba_levels; lvl++) {
-      uint32_t* off_out = offs[lvl & 1];
-      Affine<F>* out_pts = bufs[lvl & 1];
-      k_msm_ba_next_counts<<<(nb + 1 + 255) / 256, 256, 0, stream>>>(off_in, nb, cnt);
-      cub_bytes = L.cub_bytes;
-      GB_CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, cnt, off_out, (int)nb + 1, stream));
-      bound = bound / 2 + nb + 1;
-      if (bound > ((lvl & 1) ? L.ba_cap_b : L.ba_cap_a)) bound = (lvl & 1) ? L.ba_cap_b : L.ba_cap_a;
-      const uint32_t batch = msm_ba_batch_for(bound);
-      const size_t threads = (bound + batch - 1) / batch;
-      const unsigned grid = (unsigned)((threads + 127) / 128);
-      if (lvl == 0) {
-        BaSrcTable<F> src{d_table, vals1};
-        k_msm_ba_level<F, BaSrcTable<F>><<<grid, 128, 0, stream>>>(src, off_in, off_out, nb, out_pts, batch);
-      } else {
-        BaSrcPoints<F> src{bufs[(lvl - 1) & 1]};
-        k_msm_ba_level<F, BaSrcPoints<F>><<<grid, 128, 0, stream>>>(src, off_in, off_out, nb, out_pts, batch);
-      }
-      off_in = off_out;
-    }
-    // identity values over the surviving entries (vals0 is free after the sort)
-    if (bound > L.m) bound = L.m;             // entries never increase: the true count is <= m (vals0 holds m)
-    k_msm_iota<<<(unsigned)((bound + 255) / 256), 256, 0, stream>>>(vals0, (uint32_t)bound);
-    acc_table = bufs[(pl.ba_levels - 1) & 1];
-    acc_vals = vals0;
-    off = const_cast<uint32_t*>(off_in);
-  }
   k_msm_task_counts<<<(nb + 1 + 255) / 256, 256, 0, stream>>>(off, nb, pl.task_len, ntasks);
   cub_bytes = L.cub_bytes;
   GB_CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, ntasks, task_off, (int)nb + 1, stream));
   GB_EV(3);
-  bool done = false;
-  if constexpr (F52Traits<F>::ok) {
-    if (hybrid && !fmt52 && pl.ba_levels == 0 && hybrid->d_table52 && hybrid->blocks52_of_16 > 0 &&
-        hybrid->blocks52_of_16 < 16) {
-      using P52 = typename F52Traits<F>::P52;
-      const uint32_t period = 16, n52 = (uint32_t)hybrid->blocks52_of_16, n32 = period - n52;
-      const uint32_t total_blocks = (uint32_t)((L.max_tasks + 127) / 128);
-      GB_CUDA_TRY(cudaEventRecord(hybrid->fork_ev, stream));
-      GB_CUDA_TRY(cudaStreamWaitEvent(hybrid->aux, hybrid->fork_ev, 0));
-      k_msm_accumulate52_split<F, P52><<<msm_split_grid(total_blocks, period, n52), 128, 0, hybrid->aux>>>(
-          pl, reinterpret_cast<const Affine52<P52>*>(hybrid->d_table52), vals1, off, task_off, partial, period, n32, n52);
-      GB_CUDA_TRY(cudaEventRecord(hybrid->join_ev, hybrid->aux));
-      k_msm_accumulate_split<F><<<msm_split_grid(total_blocks, period, n32), 128, 0, stream>>>(
-          pl, d_table, vals1, off, task_off, partial, period, 0, n32);
-      GB_CUDA_TRY(cudaStreamWaitEvent(stream, hybrid->join_ev, 0));
-      done = true;
-    }
-  }
-  if (done) {
-  } else if constexpr (F52Traits<F>::ok) {
-    if (fmt52) {
-      using P52 = typename F52Traits<F>::P52;
-      k_msm_accumulate52<F, P52><<<(unsigned)((L.max_tasks + 127) / 128), 128, 0, stream>>>(
-          pl, reinterpret_cast<const Affine52<P52>*>(d_table), vals1, off, task_off, partial);
-    } else {
-      GB_CUDA_TRY((msm_launch_accumulate<F>(stream, pl, L, acc_table, acc_vals, off, task_off, partial, (uint32_t*)(w + L.o_ctr))));
-    }
-  } else {
-    GB_CUDA_TRY((msm_launch_accumulate<F>(stream, pl, L, acc_table, acc_vals, off, task_off, partial, (uint32_t*)(w + L.o_ctr))));
-  }
+  GB_CUDA_TRY((msm_launch_accumulate<F>(stream, pl, L, d_table, vals1, off, task_off, partial, (uint32_t*)(w + L.o_ctr))));
   GB_EV(4);
   if (tail) {
     GB_CUDA_TRY(cudaEventRecord(fork_ev, stream));

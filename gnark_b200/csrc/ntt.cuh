@@ -23,7 +23,8 @@
 namespace gb200 {
 
 enum { NTT_DIF = 0, NTT_DIT = 1 };
-constexpr int NTT_MAX_TILE_LOG = 11;   // 2048 elements per tile
+constexpr int NTT_MAX_TILE_LOG = 11;   // 2048 elements per tile (the kernel's launch bound)
+constexpr int NTT_DEFAULT_TILE_LOG = 9; // 512 elements per tile: see NttDomainDev::init
 constexpr int NTT_MAX_PASSES = 8;
 
 struct NttPass {
@@ -115,80 +116,6 @@ HD void ntt_bfly_dit(Fr& a, Fr& b, const Fr& w) {
 }
 
 // ---------------------------------------------------------------------------
-// Register rounds (opt-in, GB200_NTT_RADIX8): instead of one stage per barrier with 2 elements per thread, a thread
-// holds a group of 2^R elements (R <= 3) whose local indices differ in R consecutive bits and runs those R stages in
-// registers: a pass of S stages needs ceil(S / 3) shared-memory exchanges and barriers instead of S, and a group of 8
-// reads 7 twiddles for its 12 butterflies (butterflies that agree on the index bits below the stage bit share one).
-// ---------------------------------------------------------------------------
-constexpr int NTT_ROUND_MAX = 3;
-
-// split the S stages of a pass into rounds of <= 3 stages, in increasing bit order; returns the number of rounds
-HD int ntt_round_plan(int S, int* first, int* len) {
-  int n = 0, s = 0;
-  while (s < S) {
-    const int rem = S - s;
-    const int r = rem >= 3 && rem != 4 ? 3 : (rem >= 2 ? 2 : 1);     // 4 = 2 + 2, never 3 + 1
-    first[n] = s; len[n] = r; n++;
-    s += r;
-  }
-  return n;
-}
-
-// conflict-free shared-memory slot of local element e (one extra word every 32): strides 2^k hit distinct banks
-HD uint32_t ntt_pad(uint32_t e) { return e + (e >> 5); }
-
-// One thread's share of one register round of pass p: group `u` (0 <= u < tile_elems / 2^R) of tile `tile`, the R
-// stages on local bits [cb + s0, cb + s0 + R).  ld(e) / st(e, v) read and write local element e of the tile.
-template <class Fr, int R, bool DIT, class LD, class ST>
-HD void ntt_round(const NttPass& p, int logn, int s0, uint32_t tile, uint32_t u, const Fr* tw, LD ld, ST st) {
-  constexpr int G = 1 << R;
-  const int lb0 = p.cb + s0;
-  const uint32_t base = ((u >> lb0) << (lb0 + R)) | (u & ((1u << lb0) - 1u));
-  Fr x[G];
-#pragma unroll
-  for (int j = 0; j < G; j++) x[j] = ld(base | ((uint32_t)j << lb0));
-#pragma unroll
-  for (int q = 0; q < R; q++) {
-    const int sp = DIT ? q : R - 1 - q;          // stage bit inside the group (DIT ascending, DIF descending);
-                                                 // compile-time after unrolling, so that x[] stays in registers
-    const int beta = p.lo_bit + s0 + sp;
-#pragma unroll
-    for (int jl = 0; jl < (1 << sp); jl++) {
-      // the twiddle depends on the index bits below the stage bit only: shared by the 2^(R-1-sp) butterflies above
-      const uint32_t gi = ntt_tile_index(p, tile, base | ((uint32_t)jl << lb0));
-      const Fr w = tw[ntt_twiddle_index(logn, gi, beta)];
-#pragma unroll
-      for (int jh = 0; jh < (1 << (R - 1 - sp)); jh++) {
-        const int j = jl | (jh << (sp + 1));
-        if (DIT) ntt_bfly_dit(x[j], x[j | (1 << sp)], w);
-        else ntt_bfly_dif(x[j], x[j | (1 << sp)], w);
-      }
-    }
-  }
-#pragma unroll
-  for (int j = 0; j < G; j++) st(base | ((uint32_t)j << lb0), x[j]);
-}
-
-// all groups of one round that belong to thread t of a block of `nthreads` threads (tile_elems / 8 threads: a round
-// of 2^R-element groups has tile_elems / 2^R groups, i.e. 8 / 2^R per thread)
-template <class Fr, class LD, class ST>
-HD void ntt_round_dispatch(const NttPass& p, int logn, bool dit, int s0, int R, uint32_t tile, uint32_t t,
-                           uint32_t nthreads, uint32_t tile_elems, const Fr* tw, LD ld, ST st) {
-  const uint32_t groups = tile_elems >> R;
-  for (uint32_t u = t; u < groups; u += nthreads) {
-    if (dit) {
-      if (R == 3) ntt_round<Fr, 3, true>(p, logn, s0, tile, u, tw, ld, st);
-      else if (R == 2) ntt_round<Fr, 2, true>(p, logn, s0, tile, u, tw, ld, st);
-      else ntt_round<Fr, 1, true>(p, logn, s0, tile, u, tw, ld, st);
-    } else {
-      if (R == 3) ntt_round<Fr, 3, false>(p, logn, s0, tile, u, tw, ld, st);
-      else if (R == 2) ntt_round<Fr, 2, false>(p, logn, s0, tile, u, tw, ld, st);
-      else ntt_round<Fr, 1, false>(p, logn, s0, tile, u, tw, ld, st);
-    }
-  }
-}
-
-// ---------------------------------------------------------------------------
 // Host-side domain: builds the tables the device domain uploads, and (for the
 // CPU emulation tests) runs the same pass/tile/stage walk sequentially.
 // ---------------------------------------------------------------------------
@@ -244,7 +171,6 @@ struct NttDomainHost {
 
   // sequential walk of the kernel structure (emulation)
   int tile_log = NTT_MAX_TILE_LOG;   // emulation tests lower it to walk multi-pass plans at small sizes
-  int radix8 = 0;                    // emulate the register-round kernel (GB200_NTT_RADIX8) thread by thread
   void transform(Fr* data, bool inverse, int decimation, bool on_coset) const {
     NttPlan plan = ntt_make_plan(logn, tile_log);
     const std::vector<Fr>& T = inverse ? itw : tw;
@@ -262,21 +188,6 @@ struct NttDomainHost {
       std::vector<Fr> loc(tile_elems);
       for (uint32_t tile = 0; tile < ntiles; tile++) {
         for (uint32_t e = 0; e < tile_elems; e++) loc[e] = data[ntt_tile_index(p, tile, e)];
-        if (radix8) {
-          // k_ntt_pass_r8: rounds in pass order, every thread of the block between two barriers; padded slots
-          std::vector<Fr> sm(ntt_pad(tile_elems) + 1);
-          for (uint32_t e = 0; e < tile_elems; e++) sm[ntt_pad(e)] = loc[e];
-          int first[NTT_MAX_TILE_LOG], len[NTT_MAX_TILE_LOG];
-          const int nr = ntt_round_plan(p.S, first, len);
-          const uint32_t nthreads = tile_elems >= 8 ? tile_elems / 8 : 1;
-          for (int ri = 0; ri < nr; ri++) {
-            const int r = decimation == NTT_DIT ? ri : nr - 1 - ri;
-            for (uint32_t t = 0; t < nthreads; t++)
-              ntt_round_dispatch<Fr>(p, logn, decimation == NTT_DIT, first[r], len[r], tile, t, nthreads, tile_elems, T.data(),
-                                     [&](uint32_t e) { return sm[ntt_pad(e)]; }, [&](uint32_t e, const Fr& v) { sm[ntt_pad(e)] = v; });
-          }
-          for (uint32_t e = 0; e < tile_elems; e++) loc[e] = sm[ntt_pad(e)];
-        } else
         for (int k = 0; k < p.S; k++) {
           const int s = decimation == NTT_DIT ? k : p.S - 1 - k;
           const int lb = p.cb + s;

@@ -80,64 +80,6 @@ k_ntt_pass(NttPass p, int logn, int dit, const Fr* __restrict__ tw, Fr* __restri
   }
 }
 
-#ifndef GB200_NTT_R8_MIN_BLOCKS
-#define GB200_NTT_R8_MIN_BLOCKS 1     // 2 caps the kernel at 128 registers (two 256-thread blocks per SM)
-#endif
-// Opt-in twin of k_ntt_pass (GB200_NTT_RADIX8): blockDim = tile / 8, each thread keeps groups of up to 8 elements in
-// registers for up to three stages between two barriers (ntt_round, ntt.cuh); shared memory is limb-major with one
-// padding word per 32 elements, so that the strided group accesses of every round are bank-conflict free.
-template <class Fr>
-__global__ void __launch_bounds__(1 << (NTT_MAX_TILE_LOG - 3), GB200_NTT_R8_MIN_BLOCKS)
-k_ntt_pass_r8(NttPass p, int logn, int dit, const Fr* __restrict__ tw, Fr* __restrict__ data,
-              const Fr* __restrict__ pre, int pre_bitrev, const Fr* __restrict__ post, int post_bitrev,
-              int use_const, Fr post_const) {
-  constexpr int N = Fr::N;
-  extern __shared__ __align__(16) uint32_t sm[];
-  const uint32_t tile_elems = 1u << (p.S + p.cb);
-  const uint32_t plane = ntt_pad(tile_elems) + 1;      // words per limb plane
-  const uint32_t nthreads = blockDim.x;
-  const uint32_t t = threadIdx.x;
-  const uint32_t tile = blockIdx.x;
-
-  for (uint32_t e = t; e < tile_elems; e += nthreads) {     // load (+ optional pre-scale), coalesced in e
-    const uint32_t gi = ntt_tile_index(p, tile, e);
-    Fr v = data[gi];
-    if (pre) v = v * pre[pre_bitrev ? ntt_bitrev(gi, logn) : gi];
-    const uint32_t slot = ntt_pad(e);
-#pragma unroll
-    for (int l = 0; l < N; l++) sm[l * plane + slot] = v.l[l];
-  }
-  __syncthreads();
-
-  auto ld = [&](uint32_t e) {
-    Fr v;
-    const uint32_t slot = ntt_pad(e);
-#pragma unroll
-    for (int l = 0; l < N; l++) v.l[l] = sm[l * plane + slot];
-    return v;
-  };
-  auto st = [&](uint32_t e, const Fr& v) {
-    const uint32_t slot = ntt_pad(e);
-#pragma unroll
-    for (int l = 0; l < N; l++) sm[l * plane + slot] = v.l[l];
-  };
-  int first[NTT_MAX_TILE_LOG], len[NTT_MAX_TILE_LOG];
-  const int nr = ntt_round_plan(p.S, first, len);
-  for (int ri = 0; ri < nr; ri++) {
-    const int r = dit ? ri : nr - 1 - ri;
-    ntt_round_dispatch<Fr>(p, logn, dit != 0, first[r], len[r], tile, t, nthreads, tile_elems, tw, ld, st);
-    __syncthreads();
-  }
-
-  for (uint32_t e = t; e < tile_elems; e += nthreads) {     // store (+ optional post-scale)
-    const uint32_t gi = ntt_tile_index(p, tile, e);
-    Fr v = ld(e);
-    if (post) v = v * post[post_bitrev ? ntt_bitrev(gi, logn) : gi];
-    else if (use_const) v = v * post_const;
-    data[gi] = v;
-  }
-}
-
 // n == 1 degenerate transform: only scaling applies
 template <class Fr>
 __global__ void k_ntt_scale1(Fr* data, Fr c) { if (threadIdx.x == 0 && blockIdx.x == 0) data[0] = data[0] * c; }
@@ -153,7 +95,6 @@ struct NttDomainDev {
   Fr* cos = nullptr;   // g^j,  j < n
   Fr* icos = nullptr;  // g^-j / n
   NttPlan plan;
-  int radix8 = 0;      // GB200_NTT_RADIX8: register rounds (k_ntt_pass_r8) instead of one stage per barrier
 
   size_t table_bytes() const { return ((size_t)(n > 1 ? n / 2 : 1) * 2 + (size_t)n * 2) * sizeof(Fr); }
 
@@ -170,12 +111,14 @@ struct NttDomainDev {
   cudaError_t init(cudaStream_t st, int logn_, const Fr* gen_mont, const Fr* coset_mont) {
     logn = logn_;
     n = 1u << logn;
-    // GB200_NTT_TILE_LOG (opt-in, 6..11): smaller tiles = smaller blocks, so that two blocks share an SM and one
-    // block's loads / barriers overlap the other's butterflies (default 11: one 1024-thread block per SM)
-    int tile_log = NTT_MAX_TILE_LOG;
+    // Tile = 2^9 elements (256 threads, 16 KiB of shared memory per block): a pass is a chain of barrier-separated phases
+    // (load, one stage per barrier, store), so SMALL blocks - many resident per SM - overlap one block's loads and
+    // barriers with another's butterflies.  Measured on B200 (round 2, tools/sweep_ntt.py): BN254 2^20 0.327 ms with 2^11
+    // tiles (one 1024-thread block per SM, IMAD pipe at 45 %), 0.256 with 2^10, 0.228 with 2^9 although the smaller tile
+    // needs a third pass; BLS12-381 2^22 1.49 -> 1.02 ms.  GB200_NTT_TILE_LOG (6..11) overrides.
+    int tile_log = NTT_DEFAULT_TILE_LOG;
     if (const char* e = getenv("GB200_NTT_TILE_LOG")) { const int v = atoi(e); if (v >= 6 && v <= NTT_MAX_TILE_LOG) tile_log = v; }
     plan = ntt_make_plan(logn, tile_log);
-    if (const char* e = getenv("GB200_NTT_RADIX8")) radix8 = atoi(e) > 0 ? 1 : 0;
     gen = gen_mont ? *gen_mont : NttDomainHost<Fr>::default_generator(logn);
     coset = coset_mont ? *coset_mont : NttDomainHost<Fr>::default_coset();
     gen_inv = gen.inverse();
@@ -226,16 +169,6 @@ cudaError_t ntt_enqueue(cudaStream_t st, const NttDomainDev<Fr>& d, Fr* data, bo
     const uint32_t tile_elems = 1u << (p.S + p.cb);
     const uint32_t ntiles = d.n >> (p.S + p.cb);
     const size_t smem = (size_t)tile_elems * sizeof(Fr);
-    if (d.radix8) {
-      const size_t smem8 = (size_t)(ntt_pad(tile_elems) + 1) * sizeof(Fr);
-      const size_t smem8_max = (size_t)(ntt_pad(1u << NTT_MAX_TILE_LOG) + 1) * sizeof(Fr);
-      GB_CUDA_TRY(cudaFuncSetAttribute(k_ntt_pass_r8<Fr>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8_max));
-      const uint32_t threads = tile_elems >= 8 ? tile_elems / 8 : 1;
-      k_ntt_pass_r8<Fr><<<ntiles, threads, smem8, st>>>(p, d.logn, dit ? 1 : 0, T, data, pre, pre_br, post, post_br,
-                                                       use_const, d.ninv);
-      GB_CUDA_TRY(cudaGetLastError());
-      continue;
-    }
     GB_CUDA_TRY(cudaFuncSetAttribute(k_ntt_pass<Fr>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(NTT_MAX_TILE_LOG >= 11 ? (sizeof(Fr) << NTT_MAX_TILE_LOG) : smem)));
     k_ntt_pass<Fr><<<ntiles, tile_elems / 2, smem, st>>>(p, d.logn, dit ? 1 : 0, T, data, pre, pre_br, post, post_br,
                                                         use_const, d.ninv);

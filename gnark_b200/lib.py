@@ -17,6 +17,7 @@ BN254, BLS12_381, BLS12_377, BW6_761 = 0, 1, 2, 3
 DIF, DIT = 0, 1
 TABLE_PRECOMP = 1
 TABLE_SRC_ON_DEVICE = 2
+POINTS_RAW, POINTS_COMPRESSED = 1, 2
 VEC_MUL, VEC_ADD, VEC_SUB = 0, 1, 2
 
 CURVE_IDS = {"bn254": BN254, "bls12-381": BLS12_381, "bls12-377": BLS12_377, "bw6-761": BW6_761}
@@ -37,7 +38,7 @@ EXPORTS = [
     "b200_plonk_quotient", "b200_plonk_linearise", "b200_plonk_batch_open", "b200_plonk_end", "b200_plonk_bsb22_coset",
     "b200_comm_unique_id", "b200_comm_init", "b200_comm_init_all", "b200_comm_destroy", "b200_comm_info",
     "b200_points_allreduce", "b200_msm_allreduce", "b200_msm_submit_dev", "b200_plonk_last_stage_ms", "b200_points_fold",
-    "b200_plonk_set_qk", "b200_msm_gather", "b200_pedersen_key_load", "b200_pedersen_key_free", "b200_pedersen_commit", "b200_pedersen_fold",
+    "b200_plonk_set_qk", "b200_table_upload_encoded", "b200_msm_gather", "b200_pedersen_key_load", "b200_pedersen_key_free", "b200_pedersen_commit", "b200_pedersen_fold",
 ]
 COMM_ID_BYTES = 128
 
@@ -153,6 +154,8 @@ def load(path: str = None):
         lib.b200_pedersen_key_free.argtypes = [vp]
         lib.b200_pedersen_commit.argtypes = [vp, vp, sz, i32, vp, vp]
         lib.b200_pedersen_fold.argtypes = [i32, vp, sz, vp, vp]
+    if "b200_table_upload_encoded" not in missing:
+        lib.b200_table_upload_encoded.argtypes = [i32, i32, i32, vp, sz, i32, i32, ctypes.POINTER(vp)]
     if "b200_plonk_set_qk" not in missing:
         lib.b200_plonk_set_qk.argtypes = [vp, vp]
     if "b200_points_fold" not in missing:
@@ -323,6 +326,22 @@ class Table:
         h = ctypes.c_void_p(0)
         check(load().b200_table_upload_file(dev, curve, group, os.fsencode(path), byte_offset, n,
                                             TABLE_PRECOMP if precomp else 0, ctypes.byref(h)))
+        t.handle = h
+        return t
+
+    @classmethod
+    def from_encoded(cls, curve: int, group: int, data: bytes, n: int, encoding: int, dev: int = 0, precomp: bool = True):
+        """n points in gnark-crypto's serialised encoding (POINTS_RAW / POINTS_COMPRESSED), decoded on the device"""
+        t = cls.__new__(cls)
+        t.curve, t.group, t.dev = curve, group, dev
+        frl, fpl, deg = CURVE_SHAPES[curve]
+        t.fr_limbs = frl
+        t.coord_limbs = fpl * (deg if group == 2 else 1)
+        t.n = n
+        buf = np.frombuffer(data, dtype=np.uint8).copy() if n else np.zeros(1, dtype=np.uint8)
+        h = ctypes.c_void_p(0)
+        check(load().b200_table_upload_encoded(dev, curve, group, ptr(buf), n, encoding, TABLE_PRECOMP if precomp else 0,
+                                               ctypes.byref(h)))
         t.handle = h
         return t
 

@@ -83,6 +83,18 @@ int32_t b200_table_upload(int32_t dev, int32_t curve, int32_t group /*1|2*/, con
  * payload offset; a point-range shard supplies the offset and count of ITS range. */
 int32_t b200_table_upload_file(int32_t dev, int32_t curve, int32_t group /*1|2*/, const char* path, uint64_t byte_offset,
                                size_t n, int32_t flags, b200_table_t* out);
+/* Table from a point slice in gnark-crypto's SERIALISED encoding - what backend/plonk/<curve>/marshal.go:96-129 writes
+ * for pk.Kzg / pk.KzgLagrange and backend/groth16/<curve>/marshal.go:136-214 for the Groth16 slices outside the dump
+ * format: after the encoder's uint32 length, n points of fixed size, big-endian canonical coordinates with metadata
+ * bits in the first byte (B200_POINTS_COMPRESSED = what WriteTo emits, x only, sizeof(fp) bytes per G1 point;
+ * B200_POINTS_RAW = what WriteRawTo emits, x || y).  The bytes are uploaded as they are and decoded on the device, one
+ * thread per point: byte order, Montgomery form, and for compressed points the square root that dominates ReadFrom on the
+ * CPU.  Compressed: G1 of BN254, BLS12-381 and BW6-761 (p = 3 mod 4); raw: G1 and G2 of every curve.  Each point is
+ * checked to be canonical and on the curve (G1); subgroup membership is not checked, as with UnsafeReadFrom.  An
+ * invalid point fails the call and names its index. */
+enum { B200_POINTS_RAW = 1, B200_POINTS_COMPRESSED = 2 };
+int32_t b200_table_upload_encoded(int32_t dev, int32_t curve, int32_t group, const void* bytes, size_t n,
+                                  int32_t encoding, int32_t flags, b200_table_t* out);
 int32_t b200_table_free(b200_table_t t);
 int32_t b200_table_info(b200_table_t t, size_t* n, int32_t* window_bits, int32_t* n_windows, int32_t* precomp,
                         size_t* device_bytes);

@@ -27,16 +27,6 @@ def hostemu():
 
 
 @pytest.fixture(scope="session")
-def hostemu_opt():
-    """the same templates compiled with the optional arithmetic paths (GB200_MONT_SQR, GB200_FP2_LAZY, GB200_MONT_KARATSUBA down to 8 limbs, GB200_XYZZ_LAZY)"""
-    import ctypes
-    _make("../../tests/_build/libgb200_hostemu_opt.so")
-    lib = ctypes.CDLL(os.path.join(ROOT, "tests", "_build", "libgb200_hostemu_opt.so"))
-    assert lib.emu_build_options() == 31
-    return lib
-
-
-@pytest.fixture(scope="session")
 def b200lib():
     """The product library (dlopen only; no CUDA call)."""
     path = os.path.join(ROOT, "gnark_b200", "lib", "libgnark_b200.so")

@@ -96,11 +96,11 @@ def test_ntt_pinned_through_commitments(srs):
     assert ff.unpack_elements(A, C.r, C.fr_limbs) == e_br
 
 
-def test_device_templates_on_external_vectors(hostemu, hostemu_opt, srs):
+def test_device_templates_on_external_vectors(hostemu, srs):
     """the CUDA kernels' per-thread code, compiled for the host (tests/test_emulation.py), on the external vectors;
-    the optional arithmetic paths (the A/B builds: dedicated squaring, Karatsuba, single-reduction Y3) as well"""
+    several window / task / chunk geometries"""
     base, sc, (other, j) = kat_cases(random.Random(3))[3]
-    for lib, (cw, pre, tl, ch) in ((hostemu, (8, 0, 16, 64)), (hostemu, (10, 0, 32, 128)), (hostemu_opt, (9, 0, 64, 128))):
+    for lib, (cw, pre, tl, ch) in ((hostemu, (8, 0, 16, 64)), (hostemu, (10, 0, 32, 128)), (hostemu, (9, 0, 64, 128))):
         out = np.zeros(3 * C.fp_limbs, dtype=np.uint64)
         assert lib.emu_msm(C.curve_id, 1, P(srs[base]), P(ff.pack_elements(sc, C.r, C.fr_limbs)), N, cw, pre, tl, ch, P(out)) == 0
         assert ec.from_jac(F, ec.unpack_points(C, 1, out, ncoords=3)[0]) == srs[other][j]
@@ -190,3 +190,28 @@ def test_gnark_vk_constants():
         larger = (g2[0] >> 6) == 3 if c is BN254 else bool(g2[0] & 0x20)
         assert g2[0] & 0x80 and (x0, x1) == (gx0, gx1)
         assert larger == ((gy1 > half) if gy1 != 0 else (gy0 > half))
+
+
+def test_encoding_matches_reference_bytes():
+    """oracle/encoding.py (gnark-crypto's point encodings, which the device decoder of b200_table_upload_encoded is
+    checked against) on bytes the reference holds: re-encoding the decoded Ethereum ceremony points reproduces the
+    fixture's 8192 compressed BLS12-381 G1 encodings byte for byte, and the compressed G1 generators inside gnark's own
+    serialised PLONK verifying keys decode to the generators (BN254: the 2-bit metadata scheme, BLS12-381: 3 bits)."""
+    import json
+    import os
+    from oracle import encoding, kzg_srs
+    from oracle.params import CURVES
+    c = CURVES["bls12-381"]
+    blob = open(kzg_srs.PATH, "rb").read()
+    mono, lag, _ = kzg_srs.load()
+    for i, P_ in enumerate(mono + lag):
+        enc = blob[48 * i:48 * (i + 1)]
+        assert encoding.encode_g1(c, P_, True) == enc, i
+        if i % 97 == 0:
+            assert encoding.decode_g1(c, enc) == P_
+            assert encoding.decode_g1(c, encoding.encode_g1(c, P_, False)) == P_
+    vk = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "gnark_vk_constants_v1.json")))
+    for k in vk["keys"]:
+        cc = CURVES["bn254" if k["curve"] == "bn254" else "bls12-381"]
+        assert encoding.decode_g1(cc, bytes.fromhex(k["kzg_g1_compressed"])) == cc.g1
+        assert encoding.encode_g1(cc, cc.g1, True).hex() == k["kzg_g1_compressed"]

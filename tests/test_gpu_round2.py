@@ -265,3 +265,78 @@ def test_msm_gather_is_the_filtered_msm(gpu, on_device):
     with pytest.raises(gpu.B200Error):
         t.msm_gather(np.array([n_wires], dtype=np.uint32), wires)           # index out of range
     t.free()
+
+
+def test_table_from_the_ethereum_srs_in_gnark_encoding(gpu):
+    """b200_table_upload_encoded on EXTERNAL bytes: the 4096 compressed BLS12-381 G1 points of the Ethereum KZG ceremony
+    file the reference ships (gnark-crypto's compressed encoding = the ZCash convention) are decoded on the device - one
+    square root per point - and the table commits like the table built from the oracle-decoded points; the same points
+    re-encoded uncompressed give the same table; a corrupted point is refused with its index."""
+    from oracle import encoding, kzg_srs
+    c = CURVES["bls12-381"]
+    blob = open(kzg_srs.PATH, "rb").read()
+    mono, _, _ = kzg_srs.load()
+    n = len(mono)
+    rng = random.Random(3)
+    sc = ff.pack_elements([rng.randrange(c.r) for _ in range(n)], c.r, c.fr_limbs)
+    want_t = gpu.Table(c.curve_id, 1, ec.pack_points(c, 1, mono), precomp=False)
+    want = jac_to_affine(c, 1, want_t.msm(sc))
+    want_t.free()
+    t = gpu.Table.from_encoded(c.curve_id, 1, blob[:48 * n], n, gpu.POINTS_COMPRESSED, precomp=True)
+    assert jac_to_affine(c, 1, t.msm(sc)) == want
+    t.free()
+    raw = b"".join(encoding.encode_g1(c, P_, False) for P_ in mono)
+    t = gpu.Table.from_encoded(c.curve_id, 1, raw, n, gpu.POINTS_RAW, precomp=False)
+    assert jac_to_affine(c, 1, t.msm(sc)) == want
+    t.free()
+    bad = bytearray(blob[:48 * n])
+    bad[48 * 1234 + 47] ^= 1
+    with pytest.raises(gpu.B200Error, match="point 1234"):
+        gpu.Table.from_encoded(c.curve_id, 1, bytes(bad), n, gpu.POINTS_COMPRESSED)
+
+
+@pytest.mark.parametrize("cname", ["bn254", "bw6-761", "bls12-377"])
+def test_table_from_encoded_points_other_curves(gpu, cname):
+    """the decoder on the other curves against oracle/encoding.py: BN254's two-bit metadata, BW6-761's 96-byte
+    coordinates, BLS12-377 raw only (compressed needs Tonelli-Shanks: refused); infinity inside the slice; G2 raw"""
+    from oracle import encoding
+    c = CURVES[cname]
+    n = 300
+    F, base, pts, sc, expected = known_dlog_instance(c, 1, n, seed=15)
+    P1 = ec.unpack_points(c, 1, pts)
+    on_curve = cname != "bw6-761"          # the oracle's BW6-761 base lives on another a = 0 curve (no b in the group law)
+    if on_curve:
+        for enc, compressed in ((gpu.POINTS_RAW, False), (gpu.POINTS_COMPRESSED, True)):
+            data = b"".join(encoding.encode_g1(c, P_, compressed) for P_ in P1)
+            if compressed and c.p % 4 != 3:
+                with pytest.raises(gpu.B200Error, match="p = 3 mod 4"):
+                    gpu.Table.from_encoded(c.curve_id, 1, data, n, enc)
+                continue
+            t = gpu.Table.from_encoded(c.curve_id, 1, data, n, enc, precomp=False)
+            assert jac_to_affine(c, 1, t.msm(sc)) == expected, (cname, enc)
+            t.free()
+    else:
+        rng = random.Random(5)
+        P1 = []
+        while len(P1) < n:
+            x = rng.randrange(c.p)
+            y2 = (x ** 3 - 1) % c.p
+            y = pow(y2, (c.p + 1) // 4, c.p)
+            if y * y % c.p == y2:
+                P1.append((x, y))
+        P1[7] = None
+        s1 = [rng.randrange(1 << 20) for _ in range(n)]
+        want = ec.msm_naive(ff.Fp(c.p), P1, s1)
+        for enc, compressed in ((gpu.POINTS_RAW, False), (gpu.POINTS_COMPRESSED, True)):
+            data = b"".join(encoding.encode_g1(c, P_, compressed) for P_ in P1)
+            t = gpu.Table.from_encoded(c.curve_id, 1, data, n, enc, precomp=False)
+            assert jac_to_affine(c, 1, t.msm(ff.pack_elements(s1, c.r, c.fr_limbs))) == want, enc
+            t.free()
+    if c.fp2_nonresidue is not None:
+        F2, base2, pts2, sc2, exp2 = known_dlog_instance(c, 2, 64, seed=16)
+        data = b"".join(encoding.encode_g2_raw(c, Q) for Q in ec.unpack_points(c, 2, pts2))
+        t = gpu.Table.from_encoded(c.curve_id, 2, data, 64, gpu.POINTS_RAW, precomp=False)
+        assert jac_to_affine(c, 2, t.msm(sc2)) == exp2
+        t.free()
+        with pytest.raises(gpu.B200Error):
+            gpu.Table.from_encoded(c.curve_id, 2, data, 64, gpu.POINTS_COMPRESSED)
