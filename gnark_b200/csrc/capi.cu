@@ -100,6 +100,20 @@ void msm_tuning(size_t n, int nwin, int c, int precomp, uint32_t* task_len, uint
   *chunk = (uint32_t)env_int("GB200_MSM_CHUNK", c >= 12 ? 8 : 4);
 }
 
+int32_t scratch_alloc(int dev, size_t bytes, void** out) {
+  GB_DEVICE(ctx, dev);
+  CK(cudaMallocAsync(out, bytes ? bytes : 1, ctx->stream));
+  return 0;
+}
+int32_t scratch_free(int dev, void* p) {
+  if (!p) return 0;
+  GB_DEVICE(ctx, dev);
+  int32_t rc = msm_join(ctx);          // pipelined MSM tails may still read the buffer on the tail stream
+  if (rc) return rc;
+  CK(cudaFreeAsync(p, ctx->stream));
+  return 0;
+}
+
 int32_t msm_join(DeviceCtx* ctx) {
   if (ctx->tail_pending) {
     CK(cudaStreamWaitEvent(ctx->stream, ctx->tail_ev, 0));

@@ -68,6 +68,11 @@ struct b200_domain_s {
 };
 
 namespace gb200 {
+// stream-ordered scratch memory for the host orchestrations (plonk_host.cu): cudaMallocAsync / cudaFreeAsync on the
+// device's stream, served from the never-shrinking pool - a proof allocates and releases GiBs of temporaries, and
+// cudaMalloc / cudaFree (b200_alloc / b200_free: synchronous, unmap on free) were a visible part of its wall time
+int32_t scratch_alloc(int dev, size_t bytes, void** out);
+int32_t scratch_free(int dev, void* p);
 int32_t msm_on_stream(DeviceCtx* ctx, b200_table_s* t, size_t off, size_t n, const void* d_scalars, void* d_out,
                       cudaEvent_t* stage_events = nullptr, bool pipelined = false);
 int32_t msm_join(DeviceCtx* ctx);  // make ctx->stream wait for the pipelined tails

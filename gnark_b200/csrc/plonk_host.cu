@@ -56,14 +56,14 @@ enum { QL = 0, QR, QM, QO, QK, S1, S2, S3 };
     if (rc__) return rc__;           \
   } while (0)
 
-// device buffers freed on scope exit (after the stream has drained)
+// stream-ordered device buffers, released on scope exit in the device stream's order (no host synchronisation)
 struct Scratch {
   int dev;
   std::vector<void*> bufs;
   explicit Scratch(int d) : dev(d) {}
-  ~Scratch() { for (void* p : bufs) if (p) b200_free(dev, p); }
+  ~Scratch() { for (void* p : bufs) if (p) scratch_free(dev, p); }
   int32_t alloc(size_t bytes, void** out) {
-    RC(b200_alloc(dev, bytes, out));
+    RC(scratch_alloc(dev, bytes, out));
     bufs.push_back(*out);
     return 0;
   }

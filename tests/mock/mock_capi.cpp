@@ -50,6 +50,8 @@ const MsmOps* get_msm_ops(int curve, int group) {
   else { o[1].scalar_bits = 255; o[1].fr_bytes = 32; o[1].affine_bytes = sizeof(Affine<Fp<bls12_381_fp_params>>); o[1].jac_bytes = sizeof(Jacobian<Fp<bls12_381_fp_params>>); }
   return &o[curve];
 }
+int32_t scratch_alloc(int, size_t bytes, void** out) { *out = malloc(bytes ? bytes : 1); return *out ? 0 : 1; }
+int32_t scratch_free(int, void* p) { free(p); return 0; }
 }  // namespace gb200
 
 extern "C" {
