@@ -291,8 +291,10 @@ int32_t b200_poly_div_by_linear(int32_t dev, int32_t curve, void* d_coeffs, size
  *      canonical KZG SRS (pk.Kzg.G1, n + 3 points); sigma polynomials are rebuilt from S (setup.go:289-392).
  *      Challenges and blinding coefficients are INPUTS: the Go shim derives gamma, beta, alpha, zeta, v from its
  *      Fiat-Shamir transcript exactly as prove.go:492-555 and samples the blinding polynomials (:1211-1220);
- *      passing them in also makes every intermediate result reproducible.  BSB22 commitments / StatisticalZK are
- *      not supported.  All scalars are fr.Elements (Montgomery) on the host. */
+ *      passing them in also makes every intermediate result reproducible.  BSB22 commitment gates are supported
+ *      (n_qcp / qcp in the key, the committed polynomials in b200_plonk_challenges.pi2 / b200_plonk_begin);
+ *      StatisticalZK is not.  Domains below 2^3 are refused (the CPU prover switches to an 8n quotient domain there,
+ *      prove.go:248).  All scalars are fr.Elements (Montgomery) on the host. */
 typedef struct b200_plonk_pk_s* b200_plonk_pk_t;
 typedef struct {
   uint32_t log2n;                        /* domain0 = 2^log2n rows */
@@ -381,11 +383,12 @@ typedef struct {
    * shards of every table; 0/0 or world <= 1 = the whole key. */
   int32_t shard_rank;
   int32_t shard_world;
-  /* BSB22 commitments: the private wires committed by Pedersen commitments are excluded from Krs
-   * (filterHeap, backend/groth16/bn254/prove.go:231-239,321-344; pk.G1.K has no base for them):
-   * sorted absolute wire indices, internal.ConcatAll(commitmentInfo.PrivateCommitted...); n_k then equals
-   * nb_wires - nb_public - n_k_removed.  NULL / 0 = no commitments.  The commitment MSMs themselves
-   * (CommitmentKeys[i].Commit / ProveKnowledge, prove.go:84,114) go through b200_table_upload + b200_msm_g1. */
+  /* BSB22 commitments: the wires that have no base in G1.K are excluded from the Krs MSM (filterHeap,
+   * backend/groth16/bn254/prove.go:231-239,321-344): sorted absolute wire indices of
+   * internal.ConcatAll(commitmentInfo.GetPrivateCommitted()..., commitmentInfo.CommitmentIndexes()), i.e. the private
+   * committed wires AND the commitment wires themselves; n_k then equals nb_wires - nb_public - n_k_removed.
+   * NULL / 0 = no commitments.  The commitment MSMs themselves (CommitmentKeys[i].Commit / ProveKnowledge,
+   * prove.go:84,114) are b200_pedersen_commit. */
   const uint32_t* k_removed;
   size_t n_k_removed;
   /* Key tables from gnark's dump file instead of host memory: when dump_path is not NULL the five
@@ -404,15 +407,18 @@ int32_t b200_groth16_pk_free(b200_pk_t pk);
  * them exactly as prove.go:170-182 does.  Outputs are gnark affine points:
  * ar, krs: G1Affine; bs: G2Affine.  msm_out (optional, may be NULL): the five raw
  * MSM results as Jacobian points in the order A, B1, Z(h), K, B2 - the
- * deterministic sub-results parity tests pin. */
+ * deterministic sub-results parity tests pin.  Sharded keys (shard_world > 1): the call works when the device has a
+ * communicator of the same world size (b200_comm_init / b200_comm_init_all) - the five partial sums are gathered and
+ * added on the device, every rank returns the same proof; without one it is refused (use the two halves below). */
 int32_t b200_groth16_prove(b200_pk_t pk, const void* wires, const void* a, const void* b, const void* c,
                            size_t n_constraints, const void* r, const void* s, void* ar_out, void* bs_out,
                            void* krs_out, void* msm_out);
 /* The two halves of b200_groth16_prove, for sharded keys (one process per GPU, or one thread per GPU inside one
  * process - entry points lock per device):
  *  - b200_groth16_msms: device part.  computeH + this shard's slice of the five MSMs; msm_out
- *    receives 4 G1Jac + 1 G2Jac partial sums (order A, B1, Z(h), K, B2).  Partial sums of all
- *    shards are added with b200_point_add_jac after one all_gather.
+ *    receives 4 G1Jac + 1 G2Jac partial sums (order A, B1, Z(h), K, B2).  With a communicator of the key's
+ *    world size on the device the sums are already COMPLETE (b200_points_allreduce inside the call); without one
+ *    the caller adds the shards' partial sums (b200_point_add_jac, or its own group arithmetic).
  *  - b200_groth16_assemble: host part (prove.go:185,199-214,241-269,287-292) from the five
  *    complete MSM results. */
 int32_t b200_groth16_msms(b200_pk_t pk, const void* wires, const void* a, const void* b, const void* c,

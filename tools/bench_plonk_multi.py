@@ -5,9 +5,9 @@
 
 gnark_b200/plonk.py with shard=(rank, world): every KZG commitment is a point-range-sharded MSM (all_gather of
 the partial digests), coset i of the quotient is evaluated on rank i mod N (one all_reduce of the disjoint quarters),
-the O(n) stages are replicated.  Synthetic (unsatisfied) instance: same work as a real proof, timing only - the
-parity of the sharded prover is pinned on the CPU over gloo (tests/test_dist.py::test_sharded_plonk_gloo) and of the
-single-GPU prover on hardware at small sizes.  One JSON line on rank 0 (wall clock around Prove, max over ranks)."""
+the O(n) stages are replicated.  Satisfied instance + trapdoor SRS (oracle/plonk_fast.py); the proof of the last
+timed step is checked by the verifier's equations on rank 0.  The sharded prover's parity is also pinned on the CPU over
+gloo (tests/test_dist.py::test_sharded_plonk_gloo).  One JSON line on rank 0 (wall clock around Prove, max over ranks)."""
 import argparse
 import json
 import os
@@ -24,7 +24,6 @@ def main():
     import torch
     import torch.distributed as dist
     from gnark_b200 import lib, plonk
-    from oracle import corelib, ec           # fixture generation only
     from oracle.params import CURVES
     ap = argparse.ArgumentParser()
     ap.add_argument("--curve", default="bls12-381")
@@ -43,23 +42,18 @@ def main():
     c = CURVES[args.curve]
     L = c.fr_limbs
     n = 1 << args.log2n
-    rs = np.random.RandomState(21)                       # the same instance on every rank
-
-    def rand_fr(count):
-        a = rs.randint(0, 1 << 62, size=(count, L), dtype=np.int64).astype(np.uint64)
-        a[:, L - 1] &= np.uint64((1 << (c.r.bit_length() - 64 * (L - 1) - 1)) - 1)
-        return a
-    cols = {k: rand_fr(n) for k in ("ql", "qr", "qm", "qo", "qk", "l", "r", "o")}
-    perm = rs.permutation(3 * n).astype(np.int64)
-    small = 1 << 14
-    srs = np.tile(corelib.fixed_base(c, 1, ec.pack_points(c, 1, [c.g1]), rand_fr(small)), ((n + 3) // small + 1, 1))[:n + 3].copy()
+    # the same SATISFIED instance on every rank (oracle/plonk_fast.py), trapdoor SRS built on this rank's GPU
+    from oracle import plonk_fast
+    inst = plonk_fast.satisfied_instance(c, args.log2n, seed=22)
+    cols = {"ql": inst.ql, "qr": inst.qr, "qm": inst.qm, "qo": inst.qo, "qk": inst.qk, "l": inst.l, "r": inst.r, "o": inst.o}
+    perm = inst.perm
+    srs = plonk_fast.trapdoor_srs_gpu(lib, c, inst, dev=local)
     t0 = time.perf_counter()
     pk = plonk.ProvingKey.from_trace(c.curve_id, args.log2n, cols["ql"], cols["qr"], cols["qm"], cols["qo"], cols["qk"], perm,
                                      srs, dev=local, shard=(rank, world, None))
     load_s = time.perf_counter() - t0
-    ri = lambda: int(rs.randint(1, 1 << 62))
-    ch = plonk.Challenges(gamma=ri(), beta=ri(), alpha=ri(), zeta=ri(), v=ri(), bl=[ri(), ri()], br=[ri(), ri()],
-                          bo=[ri(), ri()], bz=[ri(), ri(), ri()])
+    ic = inst.ch
+    ch = plonk.Challenges(gamma=ic.gamma, beta=ic.beta, alpha=ic.alpha, zeta=ic.zeta, v=ic.v, bl=ic.bl, br=ic.br, bo=ic.bo, bz=ic.bz)
     times, stages = [], None
     for _ in range(args.steps + 1):
         if world > 1:
@@ -74,18 +68,31 @@ def main():
             dt = float(tt[0])
         times.append(dt)
         stages = proof.timings_ms
+    verified = None
+    if rank == 0:
+        # the sharded prover's proof through the verifier's equations (trapdoor identity for the two openings)
+        from oracle import ff
+        pts = np.stack([proof.LRO[0], proof.LRO[1], proof.LRO[2], proof.Z, proof.H[0], proof.H[1], proof.H[2],
+                        proof.LinearizedDigest, proof.BatchedProofH, proof.ZShiftedOpeningH])
+        vals = ff.pack_elements(list(proof.BatchedClaimedValues[:6]) + [proof.ZShiftedClaimedValue], c.r, c.fr_limbs)
+        verified = bool(plonk_fast.verify(c, inst, pts, vals, with_pairing=False))
     if rank == 0:
         os.write(real_stdout, (json.dumps({
             "config": f"PLONK prove 2^{args.log2n} {args.curve}, {world} GPU(s): sharded KZG commitments + coset-parallel quotient",
             "n_gpus": world, "metric": "plonk_prove_ms", "value": float(np.median(times[1:])), "first_call_ms": times[0],
-            "stage_ms_rank0": stages, "key_load_s": load_s, "data": "synthetic (unsatisfied instance)",
+            "verified": verified, "stage_ms_rank0": stages, "key_load_s": load_s, "data": "synthetic satisfied instance, trapdoor SRS",
             "excludes": "solver, Fiat-Shamir hashing (challenges injected)"}) + "\n").encode())
-    try:
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-    finally:
-        os._exit(0)
+    # orderly exit: barrier, synchronize, tear the process group down (a watchdog only for a hung teardown)
+    import threading
+    dog = threading.Timer(120, lambda: os._exit(0))
+    dog.daemon = True
+    dog.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.destroy_process_group()
+    dog.cancel()
 
 
 if __name__ == "__main__":

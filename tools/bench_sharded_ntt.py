@@ -90,12 +90,17 @@ def main():
             "config": f"{args.curve} NTT 2^{args.log2n}, CYCLIC -> SLICED over {world} GPU(s), one all-to-all",
             "n_gpus": world, "ms_per_transform": float(t[0]), "single_gpu_ms": single_ms, "correct": float(t[1]) == 0.0,
             "exchange_bytes_per_rank": (n // world) * L * 8 * (world - 1) // world}) + "\n").encode())
-    try:
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-    finally:
-        os._exit(0)
+    # orderly exit: barrier, synchronize, tear the process group down (a watchdog only for a hung teardown)
+    import threading
+    dog = threading.Timer(120, lambda: os._exit(0))
+    dog.daemon = True
+    dog.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.destroy_process_group()
+    dog.cancel()
 
 
 if __name__ == "__main__":
