@@ -211,15 +211,20 @@ def cpu_best_config(C, pts, sc, threads):
     return best[0], best[1]
 
 
-def cpu_msm_rate(C, pts, sc, sample_n, reps, threads):
-    """oracle port (restatement of gnark-crypto's MultiExp algorithm, NOT gnark-crypto) on host cores."""
+def cpu_msm_rate(C, pts, sc, sample_n, budget_s, threads):
+    """oracle port (restatement of gnark-crypto's MultiExp algorithm, NOT gnark-crypto) on host cores: window and
+    thread count by a sweep, then as many repetitions as fit `budget_s` seconds of wall clock (at least 3)"""
     p, s = pts[:sample_n], sc[:sample_n]
     c, th = cpu_best_config(C, p, s, threads)
+    t0 = time.perf_counter()
+    cpu_msm(C, p, s, c, th)
+    one = time.perf_counter() - t0
+    reps = max(3, min(200, int(budget_s / max(one, 1e-3))))
     t0 = time.perf_counter()
     for _ in range(reps):
         cpu_msm(C, p, s, c, th)
     dt = (time.perf_counter() - t0) / reps
-    return sample_n / dt, dt, th, c
+    return sample_n / dt, dt, th, c, reps
 
 
 def run_reference(args):
@@ -441,12 +446,12 @@ def msm_leg(ctx):
     # the CPU arm beside it (rank 0, N = 1 only): bounded sample of the same workload
     threads = host_threads()
     if world == 1 and not args.no_cpu:
-        sample_n = n if threads >= 32 else 1 << 18   # many-core hosts need the full problem to scale
-        cpu_rate, cpu_dt, cpu_th, cpu_c = cpu_msm_rate(C, pts, sc, sample_n, 3, threads)
+        sample_n = n if threads >= 16 else 1 << 18   # many-core hosts need the full problem to scale
+        cpu_rate, cpu_dt, cpu_th, cpu_c, cpu_reps = cpu_msm_rate(C, pts, sc, sample_n, 8.0, threads)
         out["cpu_baseline"] = {"value": cpu_rate, "unit": UNIT, "cores": cpu_th, "kind": "port",
-                               "sample": f"3 x BN254 G1 MSM of 2^{int(np.log2(sample_n))} points of the same workload "
-                                         f"({cpu_dt:.2f} s each; window c={cpu_c} and thread count {cpu_th} of {threads} "
-                                         f"usable picked by a sweep)"}
+                               "sample": f"{cpu_reps} x BN254 G1 MSM of 2^{int(np.log2(sample_n))} points of the same workload "
+                                         f"({cpu_dt:.3f} s each, ~{cpu_reps * cpu_dt * cpu_th:.0f} core-seconds; window c={cpu_c} and "
+                                         f"thread count {cpu_th} of {threads} usable picked by a sweep)"}
     else:
         out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": threads, "kind": "port",
                                "sample": "timed on rank 0 at N=1 only (see the N=1 line)"}
@@ -580,14 +585,22 @@ def plonk_leg(ctx, log2n):
     key = lib.PlonkKey(c.curve_id, log2n, inst.ql, inst.qr, inst.qm, inst.qo, inst.qk, inst.perm, srs, dev=ctx.local)
     load_s = time.perf_counter() - t0
     ch = inst.challenges_packed()
+    # the solver's output columns in pinned host memory (b200_host_alloc in the Go shim), as in the
+    # Groth16 leg; one run from pageable memory is reported beside it
+    torch = ctx.torch
+    keep = [torch.from_numpy(v.view(np.int64)).pin_memory() for v in (inst.l, inst.r, inst.o)]
+    lp, rp, op = [k.numpy().view(np.uint64) for k in keep]
     times, stage_runs = [], []
     pts = vals = None
     for _ in range(5):
-        ctx.torch.cuda.synchronize()
+        torch.cuda.synchronize()
         t0 = time.perf_counter()
-        pts, vals = key.prove(inst.l, inst.r, inst.o, *ch)
+        pts, vals = key.prove(lp, rp, op, *ch)
         times.append(1e3 * (time.perf_counter() - t0))
         stage_runs.append(key.last_stage_ms())
+    t0 = time.perf_counter()
+    key.prove(inst.l, inst.r, inst.o, *ch)
+    pageable_ms = 1e3 * (time.perf_counter() - t0)
     # per-stage median over the calls after the first
     stages = {k: float(np.median([r[k] for r in stage_runs[1:]])) for k in stage_runs[0]}
     key.free()
@@ -596,10 +609,10 @@ def plonk_leg(ctx, log2n):
     verify_s = time.perf_counter() - t0
     return {"metric": "plonk_prove_ms", "curve": "bls12-381", "log2_gates": log2n, "n_gpus": 1,
             "prove_ms_median": float(np.median(times[1:])), "prove_ms_min": float(min(times[1:])), "first_call_ms": times[0],
-            "verified": bool(ok), "check": "verifier's equations on the ten proof points and seven values (trapdoor SRS: "
+            "prove_ms_pageable": pageable_ms, "verified": bool(ok), "check": "verifier's equations on the ten proof points and seven values (trapdoor SRS: "
             "openings checked as [f] - f(z)[1] + z[H] == tau [H]; oracle/plonk_fast.py), satisfied instance",
             "stage_ms": stages, "prove_ms_all": times, "key_load_s": load_s, "fixture_s": gen_s, "verify_s": verify_s,
-            "includes": "H2D of L,R,O, NTTs, 4 fused constraint passes, iNTT 4n, 10 KZG commitments (MSM), grand product, "
+            "includes": "H2D of L,R,O (3 x 128 MiB, pinned host buffers; pageable variant beside it), NTTs, 4 fused constraint passes, iNTT 4n, 10 KZG commitments (MSM), grand product, "
                         "evaluations, opening quotients, D2H of 10 points + 7 values",
             "excludes": "solver, Fiat-Shamir hashing (challenges injected by the caller, as the Go shim does)"}
 

@@ -86,17 +86,35 @@ int msm_window_for(size_t n) {
   if (c > 16) c = 16;
   return c;
 }
-void msm_tuning(size_t n, int nwin, int c, int precomp, uint32_t* task_len, uint32_t* chunk) {
+void msm_tuning(size_t n, int nwin, int c, int precomp, int acc_blocks_per_sm, uint32_t* task_len, uint32_t* chunk) {
   const size_t m = n * (size_t)nwin;
-  // enough tasks to fill the GPU (~150k), but no more than ~8 partial sums per bucket on average
-  // (each partial costs the combine kernel one serial XYZZ addition)
   const size_t buckets = (precomp ? (size_t)1 : (size_t)nwin) << (c - 1);
-  size_t tl = m / 300000;
-  const size_t per_bucket = (m / buckets + 7) / 8;
-  if (per_bucket > tl) tl = per_bucket;
-  if (tl < 8) tl = 8;
-  if (tl > 64) tl = 64;   // 128 measured slower at 2^20 (fewer, longer tasks: wave quantisation)
-  *task_len = (uint32_t)env_int("GB200_MSM_TASK_LEN", (int)tl);
+  // Task length.  One thread adds a task's entries; a bucket of k entries is cut into ceil(k / task_len) tasks.  Short
+  // tasks fill the machine evenly (the accumulate grid is many waves deep, the short last task of every bucket idles its
+  // lane for less) at the price of more partial sums for the combine kernel.  Measured on B200 (round 2, BN254 G1 2^20,
+  // pipelined ms per MSM): 16: 3.50, 24: 3.42, 32: 3.43, 40: 3.45, 48: 3.49, 64: 3.54; BN254 G2 / BLS12-381 G1: 32 beats
+  // 64 by 4-5 %.  Within [24, 40] the length is picked so that the grid is as close as possible to a whole number of
+  // waves of resident blocks (148 SMs x blocks per SM from the occupancy API): the last, partly filled wave is the
+  // other loss (BW6-761 2^18 with 64-entry tasks: 3.04 waves of 296 blocks, a quarter of the kernel's time on 4 % of it).
+  size_t lo = 24, hi = 40;
+  const size_t per_bucket = m / (buckets ? buckets : 1);
+  if (per_bucket < 2 * hi) { lo = 8; hi = per_bucket / 2 > 8 ? per_bucket / 2 : 8; }     // small problems: >= 2 tasks per bucket
+  if (hi > 40) hi = 40;
+  if (lo > hi) lo = hi;
+  int sms = 148;
+  { int dev = 0; if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+  const double resident = (double)sms * (acc_blocks_per_sm > 0 ? acc_blocks_per_sm : 1);
+  size_t best = hi;
+  double best_waste = 2.0;
+  for (size_t tl = hi; tl >= lo; tl--) {
+    const double blocks = ((double)m / (double)tl + 0.5 * (double)buckets) / 128.0;    // expected tasks / threads per block
+    const double waves = blocks / resident;
+    const double full = waves <= 1.0 ? 1.0 : (double)(size_t)(waves + 0.999999);
+    const double waste = (full - waves) / full;
+    if (waste < best_waste - 0.005) { best_waste = waste; best = tl; }                 // ties: the longer task
+    if (tl == lo) break;
+  }
+  *task_len = (uint32_t)env_int("GB200_MSM_TASK_LEN", (int)best);
   *chunk = (uint32_t)env_int("GB200_MSM_CHUNK", c >= 12 ? 8 : 4);
 }
 
@@ -131,17 +149,15 @@ int32_t msm_on_stream(DeviceCtx* ctx, b200_table_s* t, size_t off, size_t n, con
   if (stage_events || n == 0) pipelined = false;
   if (!pipelined) { int32_t rc = msm_join(ctx); if (rc) return rc; }
   uint32_t task_len, chunk;
-  msm_tuning(n, t->nwin, t->c, t->precomp, &task_len, &chunk);
+  msm_tuning(n, t->nwin, t->c, t->precomp, t->ops->acc_blocks_per_sm(), &task_len, &chunk);
   size_t ws_bytes = 0;
   CK(t->ops->ws_bytes((uint32_t)n, (uint32_t)t->n, t->c, t->precomp, task_len, chunk, &ws_bytes));
   AsyncBuf ws_buf;
   CK(ws_buf.alloc(ws_bytes, ctx->stream));
   void* ws = ws_buf.p;
-  // GB200_MSM_PERSISTENT=1 (opt-in, msm.cuh 4c): accumulate on a grid sized to the machine, tasks from an atomic counter
-  const int persistent = env_int("GB200_MSM_PERSISTENT", 0) == 1 ? 1 : 0;
   cudaError_t e = t->ops->run(ctx->stream, (uint32_t)n, (uint32_t)t->n, (uint32_t)off, t->c, t->precomp, task_len, chunk,
                               t->d_points, d_scalars, d_out, ws, stage_events, pipelined ? ctx->tail_stream : nullptr,
-                              ctx->fork_ev, persistent);
+                              ctx->fork_ev);
   // the workspace is last used by the tail kernels
   cudaError_t e2 = ws_buf.release_on(pipelined ? ctx->tail_stream : ctx->stream);
   if (pipelined && e == cudaSuccess) {

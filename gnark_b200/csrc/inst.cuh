@@ -29,9 +29,8 @@ struct MsmInst {
   }
   static cudaError_t run(cudaStream_t st, uint32_t n, uint32_t stride, uint32_t off, int c, int precomp,
                          uint32_t task_len, uint32_t chunk, const void* d_table, const void* d_scalars,
-                         void* d_out_jac, void* ws, cudaEvent_t* ev, cudaStream_t tail, cudaEvent_t fork_ev, int persistent) {
+                         void* d_out_jac, void* ws, cudaEvent_t* ev, cudaStream_t tail, cudaEvent_t fork_ev) {
     MsmPlan pl = plan(n, stride, off, c, precomp, task_len, chunk);
-    pl.persistent = persistent;
     MsmLayout<F> L;
     GB_CUDA_TRY(msm_layout<F>(pl, L));
     return msm_enqueue<Fr, F>(st, pl, reinterpret_cast<const Affine<F>*>(d_table),
@@ -42,6 +41,17 @@ struct MsmInst {
     if (n == 0 || nwin <= 1) return cudaSuccess;
     Affine<F>* t = reinterpret_cast<Affine<F>*>(d_table);
     return msm_precompute_enqueue<F>(st, n, nwin, c, t, t);
+  }
+  static int acc_blocks_per_sm() {
+    static const int cached = [] {
+      int per_sm = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_msm_accumulate<F>, 128, 0) != cudaSuccess || per_sm < 1) {
+        cudaGetLastError();
+        per_sm = 1;
+      }
+      return per_sm;
+    }();
+    return cached;
   }
   static cudaError_t fixed_base(cudaStream_t st, const void* h_base, const void* d_scalars, size_t n, int c,
                                 void* d_out_affine) {
@@ -76,7 +86,7 @@ struct MsmInst {
   }
   static const MsmOps* ops() {
     static const MsmOps o = {Fr::Params::BITS, sizeof(Fr), sizeof(Affine<F>), sizeof(Jacobian<F>), &ws_bytes, &run,
-                             &precompute, &fixed_base, &fold, &encoded_bytes, &decode};
+                             &precompute, &acc_blocks_per_sm, &fixed_base, &fold, &encoded_bytes, &decode};
     return &o;
   }
 };

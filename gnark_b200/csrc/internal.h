@@ -38,9 +38,12 @@ struct MsmOps {
   cudaError_t (*run)(cudaStream_t st, uint32_t n, uint32_t stride, uint32_t off, int c, int precomp,
                      uint32_t task_len, uint32_t chunk, const void* d_table, const void* d_scalars, void* d_out_jac,
                      void* ws, cudaEvent_t* stage_events /* nullable, 8 entries */,
-                     cudaStream_t tail /* nullable */, cudaEvent_t fork_ev, int persistent /* GB200_MSM_PERSISTENT */);
+                     cudaStream_t tail /* nullable */, cudaEvent_t fork_ev);
   // fill slabs 1..nwin-1 of a [nwin][n] table whose slab 0 holds the bases
   cudaError_t (*precompute)(cudaStream_t st, uint32_t n, int nwin, int c, void* d_table);
+  // resident 128-thread blocks of the accumulate kernel per SM (occupancy API): the task length is chosen so that the
+  // accumulate grid is close to a whole number of waves
+  int (*acc_blocks_per_sm)();
   // fixed-base batch (fixed_base.cuh): d_out[i] = scalars[i] * base; h_base is ONE affine point on the host
   cudaError_t (*fixed_base)(cudaStream_t st, const void* h_base, const void* d_scalars, size_t n, int c, void* d_out_affine);
   // multi-GPU combine: d_out[k] = sum_r d_gathered[r * count + k] (Jacobian points, k_points_fold)

@@ -38,7 +38,6 @@ struct MsmPlan {
   uint32_t total_buckets; // nsets * set_size ; also the "no entry" key
   uint32_t task_len;      // max entries per accumulate task
   uint32_t chunk;         // buckets per level-1 reduction chunk
-  int persistent;         // opt-in: accumulate tasks handed out by an atomic counter to a grid sized to the SMs
 };
 
 HD int msm_num_windows(int scalar_bits, int c) { return scalar_bits / c + 1; }
@@ -53,7 +52,6 @@ HD MsmPlan msm_make_plan(uint32_t n, uint32_t table_stride, uint32_t table_off, 
   p.set_size = 1u << (c - 1);
   p.total_buckets = (uint32_t)p.nsets * p.set_size;
   p.task_len = task_len;
-  p.persistent = 0;
   p.chunk = chunk;
   return p;
 }
@@ -126,32 +124,6 @@ HD bool msm_task_bounds(const MsmPlan& pl, const uint32_t* off, const uint32_t* 
   end = begin + pl.task_len;
   if (end > off[lo + 1]) end = off[lo + 1];
   return true;
-}
-
-// ---- 4c. persistent accumulate (opt-in, GB200_MSM_PERSISTENT) -------------------------------------------
-// One thread of a grid sized to the machine (SMs x resident blocks) instead of one thread per task: a thread takes a
-// task from `next_task` (an atomic counter on the device), adds its <= task_len entries, stores partial[t] and takes
-// the next one.  A lane whose task was short goes straight on to another task instead of idling until the longest
-// task of its warp ends (every bucket's last task is a short one), and the last wave of a task-sized grid, which
-// fills only part of the machine, disappears.  partial[] is indexed by task as before, so nothing downstream changes.
-template <class F, class NEXT>
-HD void msm_accumulate_persistent(const MsmPlan& pl, const Affine<F>* table, const uint32_t* vals, const uint32_t* off,
-                                  const uint32_t* task_off, XYZZ<F>* partial, NEXT next_task) {
-  XYZZ<F> acc = XYZZ<F>::inf();
-  uint32_t e = 0, end = 0, t = 0;
-  bool have = false;
-  for (;;) {
-    if (e == end) {
-      if (have) partial[t] = acc;
-      t = next_task();
-      if (!msm_task_bounds(pl, off, task_off, t, e, end)) return;   // past the last task
-      acc = XYZZ<F>::inf();
-      have = true;
-      if (e == end) continue;                                        // an empty task stores infinity
-    }
-    acc.add_mixed(msm_load_point(table, vals[e]));
-    e++;
-  }
 }
 
 // ---- 5. reduce -------------------------------------------------------------

@@ -71,17 +71,6 @@ __global__ void __launch_bounds__(128) k_msm_accumulate(MsmPlan pl, const Affine
   partial[t] = msm_accumulate_range<F>(table, svals, begin, end);
 }
 
-// opt-in (GB200_MSM_PERSISTENT): the same tasks on a grid sized to the machine, handed out by an atomic counter
-// (msm_accumulate_persistent, msm.cuh 4c)
-template <class F>
-__global__ void __launch_bounds__(128) k_msm_accumulate_persistent(MsmPlan pl, const Affine<F>* __restrict__ table,
-                                                             const uint32_t* __restrict__ svals,
-                                                             const uint32_t* __restrict__ off,
-                                                             const uint32_t* __restrict__ task_off,
-                                                             XYZZ<F>* __restrict__ partial, uint32_t* __restrict__ counter) {
-  msm_accumulate_persistent<F>(pl, table, svals, off, task_off, partial, [counter]() { return atomicAdd(counter, 1u); });
-}
-
 // one thread per bucket: sum of its task partials.  Buckets with more than MSM_HEAVY partials
 // (skewed witnesses: many equal small scalars; a short top window) are queued for the
 // block-cooperative kernel below instead of being summed serially.
@@ -286,8 +275,7 @@ struct MsmLayout {
   uint32_t chunks_per_set;
   size_t cub_bytes;
   // offsets into the workspace
-  size_t o_keys0, o_keys1, o_vals0, o_vals1, o_off, o_ntasks, o_task_off, o_partial, o_buckets, o_chunks, o_sets, o_heavy, o_cub,
-      o_ctr, total;
+  size_t o_keys0, o_keys1, o_vals0, o_vals1, o_off, o_ntasks, o_task_off, o_partial, o_buckets, o_chunks, o_sets, o_heavy, o_cub, total;
 };
 
 inline size_t gb_align(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
@@ -319,7 +307,6 @@ cudaError_t msm_layout(const MsmPlan& pl, MsmLayout<F>& L) {
   L.o_sets = o; o += gb_align((size_t)pl.nsets * sizeof(XYZZ<F>));
   L.o_heavy = o; o += gb_align((L.max_tasks / MSM_HEAVY + 2) * 4);  // [0] = count, [1..] = bucket ids
   L.o_cub = o; o += gb_align(L.cub_bytes);
-  L.o_ctr = o; o += gb_align(4);      // task counter of the persistent accumulate
   L.total = o;
   return cudaSuccess;
 }
@@ -330,29 +317,6 @@ inline int msm_set_sum_threads(size_t budget = 160 * 1024) {
   int t = 256;  // __launch_bounds__ of k_msm_set_sum (register budget: up to 255 regs/thread)
   while ((size_t)t * sizeof(XYZZ<F>) > budget) t >>= 1;
   return t;
-}
-
-// the XYZZ accumulate: one thread per task (default) or, opt-in (GB200_MSM_PERSISTENT=1), a persistent grid fed by an
-// atomic task counter
-template <class F>
-cudaError_t msm_launch_accumulate(cudaStream_t stream, const MsmPlan& pl, const MsmLayout<F>& L, const Affine<F>* table,
-                                  const uint32_t* vals, const uint32_t* off, const uint32_t* task_off, XYZZ<F>* partial,
-                                  uint32_t* counter) {
-  if (pl.persistent == 1) {
-    int dev = 0, sms = 0, per_sm = 0;
-    GB_CUDA_TRY(cudaGetDevice(&dev));
-    GB_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    GB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_msm_accumulate_persistent<F>, 128, 0));
-    if (per_sm < 1) per_sm = 1;
-    size_t grid = (size_t)sms * per_sm;                   // one resident wave: 148 SMs x blocks per SM on B200
-    const size_t need = (L.max_tasks + 127) / 128;
-    if (grid > need) grid = need;
-    GB_CUDA_TRY(cudaMemsetAsync(counter, 0, 4, stream));
-    k_msm_accumulate_persistent<F><<<(unsigned)grid, 128, 0, stream>>>(pl, table, vals, off, task_off, partial, counter);
-  } else {
-    k_msm_accumulate<F><<<(unsigned)((L.max_tasks + 127) / 128), 128, 0, stream>>>(pl, table, vals, off, task_off, partial);
-  }
-  return cudaGetLastError();
 }
 
 // Enqueue a full MSM on `stream`.  d_scalars: n Fr elements (Montgomery) on device.
@@ -401,7 +365,7 @@ cudaError_t msm_enqueue(cudaStream_t stream, const MsmPlan& pl, const Affine<F>*
   cub_bytes = L.cub_bytes;
   GB_CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, ntasks, task_off, (int)nb + 1, stream));
   GB_EV(3);
-  GB_CUDA_TRY((msm_launch_accumulate<F>(stream, pl, L, d_table, vals1, off, task_off, partial, (uint32_t*)(w + L.o_ctr))));
+  k_msm_accumulate<F><<<(unsigned)((L.max_tasks + 127) / 128), 128, 0, stream>>>(pl, d_table, vals1, off, task_off, partial);
   GB_EV(4);
   if (tail) {
     GB_CUDA_TRY(cudaEventRecord(fork_ev, stream));

@@ -24,7 +24,7 @@ namespace gb200 {
 
 enum { NTT_DIF = 0, NTT_DIT = 1 };
 constexpr int NTT_MAX_TILE_LOG = 11;   // 2048 elements per tile (the kernel's launch bound)
-constexpr int NTT_DEFAULT_TILE_LOG = 9; // 512 elements per tile: see NttDomainDev::init
+constexpr int NTT_DEFAULT_TILE_LOG = 8; // 256 elements per tile: see NttDomainDev::init
 constexpr int NTT_MAX_PASSES = 8;
 
 struct NttPass {

@@ -111,11 +111,14 @@ struct NttDomainDev {
   cudaError_t init(cudaStream_t st, int logn_, const Fr* gen_mont, const Fr* coset_mont) {
     logn = logn_;
     n = 1u << logn;
-    // Tile = 2^9 elements (256 threads, 16 KiB of shared memory per block): a pass is a chain of barrier-separated phases
+    // Tile = 2^8 elements (128 threads, 8 KiB of shared memory per block): a pass is a chain of barrier-separated phases
     // (load, one stage per barrier, store), so SMALL blocks - many resident per SM - overlap one block's loads and
-    // barriers with another's butterflies.  Measured on B200 (round 2, tools/sweep_ntt.py): BN254 2^20 0.327 ms with 2^11
-    // tiles (one 1024-thread block per SM, IMAD pipe at 45 %), 0.256 with 2^10, 0.228 with 2^9 although the smaller tile
-    // needs a third pass; BLS12-381 2^22 1.49 -> 1.02 ms.  GB200_NTT_TILE_LOG (6..11) overrides.
+    // barriers with another's butterflies.  Measured on B200 (round 2, tools/sweep_ntt.py, ms per transform):
+    //   tile            2^11    2^10    2^9     2^8     2^7
+    //   BN254 2^20      0.327   0.255   0.229   0.216   0.220     (2^11: one 1024-thread block per SM, IMAD pipe at 45 %)
+    //   BN254 2^24      5.54    4.58    4.03    3.79    3.82
+    //   BLS12-381 2^22  1.49    1.23    1.02    0.977   0.968
+    // although the smaller tiles need more passes (2^20: 2 passes at 2^11, 3 at 2^9 / 2^8).  GB200_NTT_TILE_LOG (6..11) overrides.
     int tile_log = NTT_DEFAULT_TILE_LOG;
     if (const char* e = getenv("GB200_NTT_TILE_LOG")) { const int v = atoi(e); if (v >= 6 && v <= NTT_MAX_TILE_LOG) tile_log = v; }
     plan = ntt_make_plan(logn, tile_log);

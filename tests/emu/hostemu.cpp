@@ -60,7 +60,7 @@ int wide_op(int op, const void* a_, const void* b_, void* out_) {
 
 template <class Fr, class F>
 int msm_emu(const void* points_, const void* scalars_, uint32_t n, int c, int precomp, uint32_t task_len,
-            uint32_t chunk, void* out_jac, int persistent_threads = 0) {
+            uint32_t chunk, void* out_jac) {
   const Affine<F>* points = reinterpret_cast<const Affine<F>*>(points_);
   const Fr* scalars = reinterpret_cast<const Fr*>(scalars_);
   MsmPlan pl = msm_make_plan(n, n, 0, Fr::Params::BITS, c, precomp, task_len, chunk);
@@ -85,34 +85,6 @@ int msm_emu(const void* points_, const void* scalars_, uint32_t n, int c, int pr
     off[b] = (uint32_t)(std::lower_bound(skeys.begin(), skeys.end(), b) - skeys.begin());
   // accumulate with tasks, then combine
   std::vector<XYZZ<F>> buckets(pl.total_buckets);
-  if (persistent_threads > 0) {
-    // GB200_MSM_PERSISTENT: task table as k_msm_task_counts + the exclusive scan build it, G simulated threads running
-    // the device loop; simulated thread g is handed tasks g, g + G, g + 2G, ... (one of the orders the atomic counter
-    // can produce) and then an index past the end
-    const uint32_t nb = pl.total_buckets;
-    std::vector<uint32_t> task_off(nb + 1, 0);
-    for (uint32_t b = 0; b < nb; b++) task_off[b + 1] = task_off[b] + (off[b + 1] - off[b] + pl.task_len - 1) / pl.task_len;
-    const uint32_t ntasks = task_off[nb];
-    std::vector<XYZZ<F>> partial(ntasks + 1);
-    std::vector<int> written(ntasks, 0);
-    const uint32_t G = (uint32_t)persistent_threads;
-    for (uint32_t g = 0; g < G; g++) {
-      uint32_t k = 0;
-      auto next = [&]() {
-        const uint64_t t = (uint64_t)g + (uint64_t)(k++) * G;
-        if (t < ntasks) written[t]++;
-        return (uint32_t)(t < ntasks ? t : ntasks + g);
-      };
-      msm_accumulate_persistent<F>(pl, table.data(), svals.data(), off.data(), task_off.data(), partial.data(), next);
-    }
-    for (uint32_t t = 0; t < ntasks; t++)
-      if (written[t] != 1) return -2;             // every task exactly once
-    for (uint32_t b = 0; b < nb; b++) {
-      XYZZ<F> acc = XYZZ<F>::inf();
-      for (uint32_t t = task_off[b]; t < task_off[b + 1]; t++) acc.add(partial[t]);
-      buckets[b] = acc;
-    }
-  } else
   for (uint32_t b = 0; b < pl.total_buckets; b++) {
     XYZZ<F> acc = XYZZ<F>::inf();
     for (uint32_t s = off[b]; s < off[b + 1]; s += pl.task_len) {
@@ -309,24 +281,6 @@ int emu_field_op(int field_id, int op, const void* a, const void* b, void* out) 
   return -1;
 }
 
-
-// GB200_MSM_PERSISTENT: the accumulate stage through msm_accumulate_persistent with `threads` simulated threads
-// (threads < 0: |threads| simulated threads with the accumulator in emulated shared memory, GB200_MSM_PERSISTENT=2)
-int emu_msm_persistent(int curve, int group, const void* points, const void* scalars, uint32_t n, int c, int precomp,
-                       uint32_t task_len, uint32_t chunk, int threads, void* out_jac) {
-  if (threads <= 0) return -1;
-  switch (curve * 2 + (group - 1)) {
-    case 0: return msm_emu<bn254_fr, bn254_fp>(points, scalars, n, c, precomp, task_len, chunk, out_jac, threads);
-    case 1: return msm_emu<bn254_fr, bn254_fp2>(points, scalars, n, c, precomp, task_len, chunk, out_jac, threads);
-    case 2: return msm_emu<bls12_381_fr, bls12_381_fp>(points, scalars, n, c, precomp, task_len, chunk, out_jac, threads);
-    case 3: return msm_emu<bls12_381_fr, bls12_381_fp2>(points, scalars, n, c, precomp, task_len, chunk, out_jac, threads);
-    case 4: return msm_emu<bls12_377_fr, bls12_377_fp>(points, scalars, n, c, precomp, task_len, chunk, out_jac, threads);
-    case 5: return msm_emu<bls12_377_fr, bls12_377_fp2>(points, scalars, n, c, precomp, task_len, chunk, out_jac, threads);
-    case 6:
-    case 7: return msm_emu<bw6_761_fr, bw6_761_fp>(points, scalars, n, c, precomp, task_len, chunk, out_jac, threads);
-  }
-  return -1;
-}
 
 int emu_msm(int curve, int group, const void* points, const void* scalars, uint32_t n, int c, int precomp,
             uint32_t task_len, uint32_t chunk, void* out_jac) {

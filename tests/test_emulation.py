@@ -143,32 +143,6 @@ def test_msm_logic(hostemu, c, group):
         assert got == exp, (c.name, group, cw, pre)
 
 
-@pytest.mark.parametrize("c,group", [(CURVES["bn254"], 1), (CURVES["bn254"], 2), (CURVES["bls12-381"], 1)],
-                         ids=lambda v: getattr(v, "name", str(v)))
-def test_msm_persistent_accumulate_logic(hostemu, c, group):
-    """opt-in GB200_MSM_PERSISTENT: the accumulate stage on a fixed number of threads that take tasks from a counter
-    (msm_accumulate_persistent) - every task exactly once, same result; thread counts below, equal to and above the
-    number of tasks; skewed scalars (one very long bucket, many empty ones)"""
-    rng = random.Random(40 + group)
-    F, base = pick_base(c, group, rng)
-    n = 61
-    pts = [ec.scalar_mul(F, rng.randrange(1, 1 << 40), base) for _ in range(n)]
-    pts[3] = ec.INF
-    pts[5] = pts[4]
-    pts[7] = ec.affine_neg(F, pts[6])
-    sc = [rng.randrange(c.r) for _ in range(n)]
-    sc[0], sc[1], sc[2] = 0, c.r - 1, 1
-    sc[6] = sc[7] = 12345
-    for i in range(20, 45):
-        sc[i] = 3                      # 25 entries in one bucket of the lowest window
-    exp = ec.msm_naive(F, pts, sc)
-    PA, SA = ec.pack_points(c, group, pts), ff.pack_elements(sc, c.r, c.fr_limbs)
-    for (cw, pre, tl, ch, threads) in ((4, 0, 3, 4, 1), (4, 0, 3, 4, 7), (7, 1, 2, 16, 64), (5, 1, 4, 8, 5000)):
-        out = np.zeros(3 * F.degree * c.fp_limbs, dtype=np.uint64)
-        assert hostemu.emu_msm_persistent(c.curve_id, group, P(PA), P(SA), n, cw, pre, tl, ch, threads, P(out)) == 0
-        assert ec.from_jac(F, ec.unpack_points(c, group, out, ncoords=3)[0]) == exp, (c.name, group, cw, pre, threads)
-
-
 @pytest.mark.parametrize("c", ALL, ids=lambda c: c.name)
 def test_ntt_logic(hostemu, c):
     rng = random.Random(4)

@@ -290,7 +290,10 @@ def test_table_from_the_ethereum_srs_in_gnark_encoding(gpu):
     assert jac_to_affine(c, 1, t.msm(sc)) == want
     t.free()
     bad = bytearray(blob[:48 * n])
-    bad[48 * 1234 + 47] ^= 1
+    x = int.from_bytes(blob[48 * 1234:48 * 1235], "big") & ((1 << 381) - 1)
+    while pow((x ** 3 + 4) % c.p, (c.p - 1) // 2, c.p) == 1:        # the next x that is NOT on the curve
+        x += 1
+    bad[48 * 1234:48 * 1235] = (x | (0b100 << 381)).to_bytes(48, "big")
     with pytest.raises(gpu.B200Error, match="point 1234"):
         gpu.Table.from_encoded(c.curve_id, 1, bytes(bad), n, gpu.POINTS_COMPRESSED)
 

@@ -571,18 +571,3 @@ print("EQUAL" if np.array_equal(outs[0], outs[1]) else "DIFFERENT")
         assert out.returncode == 0, out.stderr[-2000:]
         res[threads] = [ln for ln in out.stdout.splitlines() if ln.startswith("DIGEST")][0]
     assert res["0"] == res["4"]
-
-
-@pytest.mark.parametrize("cname,group", [("bn254", 1), ("bn254", 2), ("bls12-381", 1), ("bw6-761", 1)])
-def test_msm_persistent_accumulate(gpu, monkeypatch, cname, group, mode="1"):
-    """opt-in GB200_MSM_PERSISTENT: the accumulate stage on a grid sized to the SMs, tasks from an atomic counter;
-    known-dlog oracle, uniform and skewed scalars, precomputed and plain tables, sizes around the grid size"""
-    from util import known_dlog_instance
-    c = CURVES[cname]
-    monkeypatch.setenv("GB200_MSM_PERSISTENT", mode)
-    for n, skew in ((300, False), (9000, False), (9000, True), (150000 if c.fp_limbs <= 6 else 20000, False)):
-        _, _, pts, sc, expected = known_dlog_instance(c, group, n, seed=77 + group, skew=skew)
-        for precomp in (True, False):
-            t = gpu.Table(c.curve_id, group, pts, precomp=precomp)
-            assert jac_to_affine(c, group, t.msm(sc)) == expected, (n, skew, precomp)
-            t.free()

@@ -7,9 +7,9 @@ known-discrete-log oracle for every configuration before it is timed):
    e.g.  python tools/sweep_msm.py bn254 1 20 --set GB200_MSM_WINDOW=16,18,20,22 --set GB200_MSM_HYBRID=0,30,50
 
 Knobs (read by the library at table upload / MSM time): GB200_MSM_WINDOW (window bits c), GB200_MSM_TASK_LEN,
-GB200_MSM_CHUNK, GB200_MSM_PRECOMP, GB200_MSM_PERSISTENT (1 = accumulate on a persistent grid fed by an atomic task
-counter).  The cartesian product of all --set lists is run.  (Round 2 measured and removed the other round-1 knobs:
-hybrid / FP64-pipe accumulate, batched-affine levels, shared-memory accumulators - profiles/r02_ab_session.md.)
+GB200_MSM_CHUNK, GB200_MSM_PRECOMP.  The cartesian product of all --set lists is run.  (Round 2 measured and removed the other round-1 knobs:
+hybrid / FP64-pipe accumulate, batched-affine levels, shared-memory accumulators, persistent grid -
+profiles/r02_ab_session.md.)
 """
 import argparse
 import itertools
