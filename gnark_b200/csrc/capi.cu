@@ -36,6 +36,11 @@ int32_t cuda_fail(const char* what, cudaError_t e) {
   return 2;
 }
 
+// MSM tuning (mirrors the reference's env knob ICICLE_MSM_MAX_WINDOW, icicle.go:586-598)
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
 static std::mutex g_ctx_mu;
 static DeviceCtx g_ctx[GB200_MAX_DEVICES];
 
@@ -62,6 +67,9 @@ int32_t device_ctx(int dev, DeviceCtx** out) {
     CK(cudaDeviceGetDefaultMemPool(&pool, dev));
     uint64_t thr = UINT64_MAX;  // keep freed workspace cached in the pool
     CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    // GB200_L2_FETCH=32|64|128 (experiment): L2 fill granularity on a miss.  The bucket accumulate gathers 64-byte points
+    // at random; ncu shows 128 bytes of DRAM traffic per gather with the default setting (profiles/r02_ncu_accumulate_*)
+    if (const int g = env_int("GB200_L2_FETCH", 0)) CK(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)g));
     c.dev = dev;
     c.ready = true;
   }
@@ -71,11 +79,6 @@ int32_t device_ctx(int dev, DeviceCtx** out) {
   return 0;
 }
 
-// MSM tuning (mirrors the reference's env knob ICICLE_MSM_MAX_WINDOW, icicle.go:586-598)
-static int env_int(const char* name, int dflt) {
-  const char* v = getenv(name);
-  return v ? atoi(v) : dflt;
-}
 int msm_window_for(size_t n) {
   int c = env_int("GB200_MSM_WINDOW", 0);
   if (c > 0) return c < 2 ? 2 : (c > 24 ? 24 : c);

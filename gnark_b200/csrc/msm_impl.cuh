@@ -47,8 +47,12 @@ static __global__ void k_msm_task_counts(const uint32_t* __restrict__ off, uint3
 }
 
 // one thread per task: partial[t] = sum of <= task_len consecutive entries of one bucket
+// resident blocks per SM asked of ptxas (register cap 65536 / (128 k)); 1 = the compiler's own allocation
+#ifndef GB200_ACC_MIN_BLOCKS_WIDE
+#define GB200_ACC_MIN_BLOCKS_WIDE 1        // coordinates of 64 bytes and more (Fp2 over 8 limbs: 224 registers, 2 blocks / SM)
+#endif
 template <class F>
-__global__ void __launch_bounds__(128) k_msm_accumulate(MsmPlan pl, const Affine<F>* __restrict__ table,
+__global__ void __launch_bounds__(128, sizeof(F) >= 64 ? GB200_ACC_MIN_BLOCKS_WIDE : 1) k_msm_accumulate(MsmPlan pl, const Affine<F>* __restrict__ table,
                                                         const uint32_t* __restrict__ svals,
                                                         const uint32_t* __restrict__ off,
                                                         const uint32_t* __restrict__ task_off,
