@@ -96,17 +96,20 @@ void msm_tuning(size_t n, int nwin, int c, int precomp, int acc_blocks_per_sm, u
   // tasks fill the machine evenly (the accumulate grid is many waves deep, the short last task of every bucket idles its
   // lane for less) at the price of more partial sums for the combine kernel.  Measured on B200 (round 2, BN254 G1 2^20,
   // pipelined ms per MSM): 16: 3.50, 24: 3.42, 32: 3.43, 40: 3.45, 48: 3.49, 64: 3.54; BN254 G2 / BLS12-381 G1: 32 beats
-  // 64 by 4-5 %.  Within [24, 40] the length is picked so that the grid is as close as possible to a whole number of
+  // 64 by 4-5 %.  Within [24, 40] ([48, 64] for grids of a dozen waves and more) the length is picked so that the grid is as close as possible to a whole number of
   // waves of resident blocks (148 SMs x blocks per SM from the occupancy API): the last, partly filled wave is the
   // other loss (BW6-761 2^18 with 64-entry tasks: 3.04 waves of 296 blocks, a quarter of the kernel's time on 4 % of it).
-  size_t lo = 24, hi = 40;
-  const size_t per_bucket = m / (buckets ? buckets : 1);
-  if (per_bucket < 2 * hi) { lo = 8; hi = per_bucket / 2 > 8 ? per_bucket / 2 : 8; }     // small problems: >= 2 tasks per bucket
-  if (hi > 40) hi = 40;
-  if (lo > hi) lo = hi;
   int sms = 148;
   { int dev = 0; if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
   const double resident = (double)sms * (acc_blocks_per_sm > 0 ? acc_blocks_per_sm : 1);
+  // a grid a dozen waves deep loses little to its last wave: there the longer task wins again, because every partial
+  // costs the combine kernel one full addition (2^24 points, 64-entry tasks: combine 3.2 of 50 ms; at 40 entries 5 ms)
+  const double waves64 = ((double)m / 64.0 + 0.5 * (double)buckets) / 128.0 / resident;
+  size_t lo = waves64 >= 12.0 ? 48 : 24, hi = waves64 >= 12.0 ? 64 : 40;
+  const size_t per_bucket = m / (buckets ? buckets : 1);
+  if (per_bucket < 2 * hi) { lo = 8; hi = per_bucket / 2 > 8 ? per_bucket / 2 : 8; }     // small problems: >= 2 tasks per bucket
+  if (hi > 64) hi = 64;
+  if (lo > hi) lo = hi;
   size_t best = hi;
   double best_waste = 2.0;
   for (size_t tl = hi; tl >= lo; tl--) {
