@@ -54,12 +54,16 @@ int32_t device_ctx(int dev, DeviceCtx** out) {
     if (e != cudaSuccess) return cuda_fail("cudaGetDeviceCount (a CUDA device is required; no CPU fallback)", e);
     if (dev >= count) return set_error("device " + std::to_string(dev) + " not present (" + std::to_string(count) + " visible)");
     CK(cudaSetDevice(dev));
-    CK(cudaStreamCreateWithFlags(&c.own_stream, cudaStreamNonBlocking));
-    c.stream = c.own_stream;
+    // priorities: reduction tail (latency-bound, few blocks) > the library's main stream (MSM fronts, NTTs) > accumulate
+    // (fills the machine for milliseconds; the next MSM's sort slips into the SM slots its blocks free)
     int lo_prio = 0, hi_prio = 0;
     CK(cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));
+    CK(cudaStreamCreateWithPriority(&c.own_stream, cudaStreamNonBlocking, (lo_prio + hi_prio) / 2));
+    c.stream = c.own_stream;
     CK(cudaStreamCreateWithPriority(&c.tail_stream, cudaStreamNonBlocking, hi_prio));
-    CK(cudaEventCreateWithFlags(&c.fork_ev, cudaEventDisableTiming));
+    CK(cudaStreamCreateWithPriority(&c.acc_stream, cudaStreamNonBlocking, lo_prio));
+    CK(cudaEventCreateWithFlags(&c.front_ev, cudaEventDisableTiming));
+    for (int k = 0; k < 2; k++) CK(cudaEventCreateWithFlags(&c.acc_ev[k], cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c.tail_ev, cudaEventDisableTiming));
     CK(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&c.copy_ev, cudaEventDisableTiming));
@@ -142,6 +146,7 @@ int32_t msm_join(DeviceCtx* ctx) {
   if (ctx->tail_pending) {
     CK(cudaStreamWaitEvent(ctx->stream, ctx->tail_ev, 0));
     ctx->tail_pending = false;
+    ctx->pipe_seq = 0;
   }
   return 0;
 }
@@ -161,9 +166,20 @@ int32_t msm_on_stream(DeviceCtx* ctx, b200_table_s* t, size_t off, size_t n, con
   AsyncBuf ws_buf;
   CK(ws_buf.alloc(ws_bytes, ctx->stream));
   void* ws = ws_buf.p;
+  MsmPipe pipe;
+  if (pipelined) {
+    // at most one front ahead of the accumulate stream (bounds the live workspaces): the front of MSM k waits for the
+    // accumulate of MSM k - 2, whose event slot it then reuses
+    const int slot = (int)(ctx->pipe_seq & 1);
+    if (ctx->pipe_seq >= 2) CK(cudaStreamWaitEvent(ctx->stream, ctx->acc_ev[slot], 0));
+    pipe.acc = env_int("GB200_MSM_ACC_STREAM", 1) ? ctx->acc_stream : nullptr;
+    pipe.tail = ctx->tail_stream;
+    pipe.front_ev = ctx->front_ev;
+    pipe.acc_ev = ctx->acc_ev[slot];
+    ctx->pipe_seq++;
+  }
   cudaError_t e = t->ops->run(ctx->stream, (uint32_t)n, (uint32_t)t->n, (uint32_t)off, t->c, t->precomp, task_len, chunk,
-                              t->d_points, d_scalars, d_out, ws, stage_events, pipelined ? ctx->tail_stream : nullptr,
-                              ctx->fork_ev);
+                              t->d_points, d_scalars, d_out, ws, stage_events, pipelined ? &pipe : nullptr);
   // the workspace is last used by the tail kernels
   cudaError_t e2 = ws_buf.release_on(pipelined ? ctx->tail_stream : ctx->stream);
   if (pipelined && e == cudaSuccess) {
@@ -211,18 +227,22 @@ int32_t b200_shutdown(void) {
     if (!c.ready) continue;
     cudaSetDevice(d);
     cudaStreamSynchronize(c.stream);
+    cudaStreamSynchronize(c.acc_stream);
     cudaStreamSynchronize(c.tail_stream);
     comm_teardown(c);
     cudaStreamDestroy(c.own_stream);
+    cudaStreamDestroy(c.acc_stream);
     cudaStreamDestroy(c.tail_stream);
     cudaStreamDestroy(c.copy_stream);
     cudaEventDestroy(c.copy_ev);
-    cudaEventDestroy(c.fork_ev);
+    cudaEventDestroy(c.front_ev);
+    cudaEventDestroy(c.acc_ev[0]);
+    cudaEventDestroy(c.acc_ev[1]);
     cudaEventDestroy(c.tail_ev);
     // back to the initial state (the lock itself stays)
-    c.ready = false; c.tail_pending = false;
-    c.own_stream = c.stream = c.tail_stream = c.copy_stream = nullptr;
-    c.copy_ev = c.fork_ev = c.tail_ev = nullptr;
+    c.ready = false; c.tail_pending = false; c.pipe_seq = 0;
+    c.own_stream = c.stream = c.acc_stream = c.tail_stream = c.copy_stream = nullptr;
+    c.copy_ev = c.front_ev = c.acc_ev[0] = c.acc_ev[1] = c.tail_ev = nullptr;
   }
   return 0;
   GUARD_END

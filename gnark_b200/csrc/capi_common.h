@@ -28,11 +28,15 @@ struct DeviceCtx {
   int dev = 0;
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;  // own_stream or the caller's (b200_set_stream)
-  // pipelined MSMs: reduction tail of MSM i runs here while MSM i+1 sorts/accumulates on `stream`
+  // pipelined MSMs (MsmPipe, internal.h): the accumulate kernel of MSM i runs on acc_stream and its reduction tail on
+  // tail_stream while MSM i+1 decomposes and sorts on `stream`
+  cudaStream_t acc_stream = nullptr;
   cudaStream_t tail_stream = nullptr;
   cudaStream_t copy_stream = nullptr;  // H2D of later-needed inputs overlaps compute on `stream`
   cudaEvent_t copy_ev = nullptr;
-  cudaEvent_t fork_ev = nullptr;   // accumulate done (recorded on stream)
+  cudaEvent_t front_ev = nullptr;  // front done (recorded on stream)
+  cudaEvent_t acc_ev[2] = {nullptr, nullptr};   // accumulate of pipelined MSM k done (recorded on acc_stream), slot k & 1
+  uint64_t pipe_seq = 0;           // pipelined MSMs enqueued since the last join
   cudaEvent_t tail_ev = nullptr;   // tail done (recorded on tail_stream)
   bool tail_pending = false;
   // multi-GPU (comm.cu): NCCL communicator of this device (ncclComm_t), nullptr = single device

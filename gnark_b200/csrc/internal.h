@@ -27,6 +27,16 @@ struct AsyncBuf {
   }
 };
 
+// Streams of a pipelined MSM (null members: that stage stays on the call's stream).  The front (decompose, sort,
+// offsets: DRAM-bound) stays on the caller's stream; the accumulate kernel (integer-multiplier-bound) runs on `acc`;
+// the latency-bound reduction tail on `tail` - so MSM i+1's front overlaps MSM i's accumulate, and MSM i's tail overlaps both.
+struct MsmPipe {
+  cudaStream_t acc = nullptr;
+  cudaStream_t tail = nullptr;
+  cudaEvent_t front_ev = nullptr;  // recorded on the call's stream after the front
+  cudaEvent_t acc_ev = nullptr;    // recorded on `acc` (or the call's stream) after the accumulate kernel
+};
+
 struct MsmOps {
   int scalar_bits;      // Fr bit length
   size_t fr_bytes;      // sizeof(fr.Element)
@@ -38,7 +48,7 @@ struct MsmOps {
   cudaError_t (*run)(cudaStream_t st, uint32_t n, uint32_t stride, uint32_t off, int c, int precomp,
                      uint32_t task_len, uint32_t chunk, const void* d_table, const void* d_scalars, void* d_out_jac,
                      void* ws, cudaEvent_t* stage_events /* nullable, 8 entries */,
-                     cudaStream_t tail /* nullable */, cudaEvent_t fork_ev);
+                     const MsmPipe* pipe /* nullable: everything on st */);
   // fill slabs 1..nwin-1 of a [nwin][n] table whose slab 0 holds the bases
   cudaError_t (*precompute)(cudaStream_t st, uint32_t n, int nwin, int c, void* d_table);
   // resident 128-thread blocks of the accumulate kernel per SM (occupancy API): the task length is chosen so that the

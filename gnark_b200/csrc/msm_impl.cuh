@@ -353,10 +353,10 @@ inline uint32_t msm_set_slices(uint32_t chunks_per_set) {
 template <class Fr, class F>
 cudaError_t msm_enqueue(cudaStream_t stream, const MsmPlan& pl, const Affine<F>* d_table, const Fr* d_scalars,
                         Jacobian<F>* d_out, void* ws, const MsmLayout<F>& L, cudaEvent_t* ev = nullptr,
-                        cudaStream_t tail = nullptr, cudaEvent_t fork_ev = nullptr) {
-  // tail (optional): the latency-bound reduction kernels that follow the accumulate kernel are
-  // enqueued on this second stream (forked with fork_ev), so that in a pipeline of MSMs they
-  // overlap the next MSM's sort/accumulate instead of idling 140+ SMs.
+                        const MsmPipe* pipe = nullptr) {
+  // pipe (optional, internal.h): the accumulate kernel and the latency-bound reduction kernels that follow it are
+  // enqueued on their own streams (forked with events), so that in a pipeline of MSMs the next MSM's DRAM-bound
+  // front overlaps this one's multiplier-bound accumulate, and the tail overlaps both instead of idling 140+ SMs.
   // ev (optional, MSM_NUM_EVENTS entries): stage boundaries for the step profile
   // (the reference's ICICLE_STEP_PROFILE timers, icicle.go:72-75,1088-1094)
 #define GB_EV(k) do { if (ev) GB_CUDA_TRY(cudaEventRecord(ev[k], stream)); } while (0)
@@ -394,12 +394,17 @@ cudaError_t msm_enqueue(cudaStream_t stream, const MsmPlan& pl, const Affine<F>*
   cub_bytes = L.cub_bytes;
   GB_CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, ntasks, task_off, (int)nb + 1, stream));
   GB_EV(3);
+  if (pipe && pipe->acc) {
+    GB_CUDA_TRY(cudaEventRecord(pipe->front_ev, stream));
+    GB_CUDA_TRY(cudaStreamWaitEvent(pipe->acc, pipe->front_ev, 0));
+    stream = pipe->acc;
+  }
   k_msm_accumulate<F><<<(unsigned)((L.max_tasks + 127) / 128), 128, 0, stream>>>(pl, d_table, vals1, off, task_off, partial);
   GB_EV(4);
-  if (tail) {
-    GB_CUDA_TRY(cudaEventRecord(fork_ev, stream));
-    GB_CUDA_TRY(cudaStreamWaitEvent(tail, fork_ev, 0));
-    stream = tail;
+  if (pipe && pipe->acc_ev) GB_CUDA_TRY(cudaEventRecord(pipe->acc_ev, stream));
+  if (pipe && pipe->tail) {
+    GB_CUDA_TRY(cudaStreamWaitEvent(pipe->tail, pipe->acc_ev, 0));
+    stream = pipe->tail;
   }
   uint32_t* heavy = (uint32_t*)(w + L.o_heavy);
   GB_CUDA_TRY(cudaMemsetAsync(heavy, 0, 4, stream));

@@ -24,6 +24,22 @@ __global__ void __launch_bounds__(256) k_powers(const Fr* __restrict__ pw, Fr sc
   out[k] = acc;
 }
 
+// Read-only table element (twiddle, coset factor) as 16-byte loads.  Left to the compiler, `tw[k]` feeding a product
+// is split into one 4-byte load per limb (8 LDG.32 per twiddle, each a separate 32-lane gather); two LDG.128 fetch the
+// same sectors with a quarter of the requests.
+template <class Fr>
+__device__ __forceinline__ Fr ntt_ldg(const Fr* __restrict__ p) {
+  static_assert(sizeof(Fr) % 16 == 0 && Fr::N % 4 == 0, "Fr is a whole number of 16-byte words");
+  Fr v;
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+  for (int k = 0; k < Fr::N / 4; k++) {
+    const uint4 x = __ldg(q + k);
+    v.l[4 * k] = x.x; v.l[4 * k + 1] = x.y; v.l[4 * k + 2] = x.z; v.l[4 * k + 3] = x.w;
+  }
+  return v;
+}
+
 // One pass: tile of 2^(S+cb) elements in shared memory (limb-major), blockDim = tile/2.
 template <class Fr>
 __global__ void __launch_bounds__(1 << (NTT_MAX_TILE_LOG - 1))
@@ -43,7 +59,7 @@ k_ntt_pass(NttPass p, int logn, int dit, const Fr* __restrict__ tw, Fr* __restri
     const uint32_t e = t + r * half;
     const uint32_t gi = ntt_tile_index(p, tile, e);
     Fr v = data[gi];
-    if (pre) v = v * pre[pre_bitrev ? ntt_bitrev(gi, logn) : gi];
+    if (pre) v = v * ntt_ldg(pre + (pre_bitrev ? ntt_bitrev(gi, logn) : gi));
 #pragma unroll
     for (int l = 0; l < N; l++) sm[l * tile_elems + e] = v.l[l];
   }
@@ -55,12 +71,18 @@ k_ntt_pass(NttPass p, int logn, int dit, const Fr* __restrict__ tw, Fr* __restri
     const int beta = p.lo_bit + s;
     const uint32_t lo = ((t >> lb) << (lb + 1)) | (t & ((1u << lb) - 1u));
     const uint32_t hi = lo | (1u << lb);
-    const uint32_t gi = ntt_tile_index(p, tile, lo);
-    const Fr w = tw[ntt_twiddle_index(logn, gi, beta)];
     Fr a, b;
 #pragma unroll
     for (int l = 0; l < N; l++) { a.l[l] = sm[l * tile_elems + lo]; b.l[l] = sm[l * tile_elems + hi]; }
-    if (dit) ntt_bfly_dit(a, b, w); else ntt_bfly_dif(a, b, w);
+    if (beta == 0) {
+      // index bit 0: every twiddle is w^0 = 1 (block-uniform branch), the butterfly is (a + b, a - b)
+      const Fr d = a - b;
+      a = a + b;
+      b = d;
+    } else {
+      const Fr w = ntt_ldg(tw + ntt_twiddle_index(logn, ntt_tile_index(p, tile, lo), beta));
+      if (dit) ntt_bfly_dit(a, b, w); else ntt_bfly_dif(a, b, w);
+    }
 #pragma unroll
     for (int l = 0; l < N; l++) { sm[l * tile_elems + lo] = a.l[l]; sm[l * tile_elems + hi] = b.l[l]; }
     __syncthreads();
@@ -74,7 +96,7 @@ k_ntt_pass(NttPass p, int logn, int dit, const Fr* __restrict__ tw, Fr* __restri
     Fr v;
 #pragma unroll
     for (int l = 0; l < N; l++) v.l[l] = sm[l * tile_elems + e];
-    if (post) v = v * post[post_bitrev ? ntt_bitrev(gi, logn) : gi];
+    if (post) v = v * ntt_ldg(post + (post_bitrev ? ntt_bitrev(gi, logn) : gi));
     else if (use_const) v = v * post_const;
     data[gi] = v;
   }
