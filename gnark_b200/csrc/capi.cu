@@ -71,9 +71,12 @@ int32_t device_ctx(int dev, DeviceCtx** out) {
     CK(cudaDeviceGetDefaultMemPool(&pool, dev));
     uint64_t thr = UINT64_MAX;  // keep freed workspace cached in the pool
     CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
-    // GB200_L2_FETCH=32|64|128 (experiment): L2 fill granularity on a miss.  The bucket accumulate gathers 64-byte points
-    // at random; ncu shows 128 bytes of DRAM traffic per gather with the default setting (profiles/r02_ncu_accumulate_*)
-    if (const int g = env_int("GB200_L2_FETCH", 0)) CK(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)g));
+    // L2 fill granularity on a miss: 64 bytes.  The bucket accumulate gathers 64-byte (BN254 G1) / 96..192-byte points at
+    // random from a table far larger than L2; with the driver's default (128) ncu shows 2.33 GB of DRAM traffic for
+    // 1.14 GB of gathered points, with 64 it is 1.24 GB (profiles/r02_session4.md).  The kernels are multiplier-bound,
+    // so the time does not move - this removes wasted HBM traffic, nothing else.  GB200_L2_FETCH=32|64|128 overrides, 0 leaves
+    // the device limit alone.
+    if (const int g = env_int("GB200_L2_FETCH", 64)) CK(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)g));
     c.dev = dev;
     c.ready = true;
   }

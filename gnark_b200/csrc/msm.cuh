@@ -141,29 +141,6 @@ HD XYZZ<F> msm_reduce_chunk(const XYZZ<F>* set_buckets, uint32_t lo, uint32_t hi
   return acc;
 }
 
-// the same through the lane-cooperative additions (curve.cuh): what the kernel runs, one quad of lanes per chunk
-template <class F, class Q>
-HD XYZZ<F> msm_reduce_chunk_coop(const XYZZ<F>* set_buckets, uint32_t lo, uint32_t hi, const Q& quad) {
-  XYZZ<F> run = XYZZ<F>::inf();
-  XYZZ<F> acc = XYZZ<F>::inf();
-  for (uint32_t k = hi; k-- > lo;) {
-    const XYZZ<F> bk = set_buckets[k];
-    xyzz_add_coop<F, Q>(run, bk, quad);
-    xyzz_add_coop<F, Q>(acc, run, quad);
-  }
-  if (lo) xyzz_add_coop<F, Q>(acc, xyzz_mul_small_coop<F, Q>(run, lo, quad), quad);
-  return acc;
-}
-template <class F, class Q>
-HD XYZZ<F> msm_horner_coop(const XYZZ<F>* set_sums, int nsets, int c, const Q& quad) {
-  XYZZ<F> acc = set_sums[nsets - 1];
-  for (int w = nsets - 2; w >= 0; w--) {
-    for (int k = 0; k < c; k++) xyzz_dbl_coop<F, Q>(acc, quad);
-    xyzz_add_coop<F, Q>(acc, set_sums[w], quad);
-  }
-  return acc;
-}
-
 // Horner over bucket sets: sum_w 2^(c*w) * S_w
 template <class F>
 HD XYZZ<F> msm_horner(const XYZZ<F>* set_sums, int nsets, int c) {

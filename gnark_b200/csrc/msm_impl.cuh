@@ -47,12 +47,16 @@ static __global__ void k_msm_task_counts(const uint32_t* __restrict__ off, uint3
 }
 
 // one thread per task: partial[t] = sum of <= task_len consecutive entries of one bucket
-// resident blocks per SM asked of ptxas (register cap 65536 / (128 k)); 1 = the compiler's own allocation
-#ifndef GB200_ACC_MIN_BLOCKS_WIDE
-#define GB200_ACC_MIN_BLOCKS_WIDE 1        // coordinates of 64 bytes and more (Fp2 over 8 limbs: 224 registers, 2 blocks / SM)
+// Resident blocks per SM asked of ptxas (register cap 65536 / (128 k)); 1 = the compiler's own allocation.
+// 64-byte coordinates (Fp2 over 8 limbs, BN254 G2): left alone ptxas takes 224 registers = 2 blocks / SM and the IMAD pipe
+// sits at 77 %; capped at 168 registers (3 blocks / SM, 212 bytes of spills) the kernel is 7 % faster (8.46 -> 7.89 ms
+// at 2^20, profiles/r02_session4.md).  96-byte coordinates (Fp2 over 12 limbs, BW6-761 Fp) already spill at 255
+// registers = 2 blocks / SM and are left alone.
+#ifndef GB200_ACC_MIN_BLOCKS_64
+#define GB200_ACC_MIN_BLOCKS_64 3
 #endif
 template <class F>
-__global__ void __launch_bounds__(128, sizeof(F) >= 64 ? GB200_ACC_MIN_BLOCKS_WIDE : 1) k_msm_accumulate(MsmPlan pl, const Affine<F>* __restrict__ table,
+__global__ void __launch_bounds__(128, sizeof(F) == 64 ? GB200_ACC_MIN_BLOCKS_64 : 1) k_msm_accumulate(MsmPlan pl, const Affine<F>* __restrict__ table,
                                                         const uint32_t* __restrict__ svals,
                                                         const uint32_t* __restrict__ off,
                                                         const uint32_t* __restrict__ task_off,
@@ -75,27 +79,26 @@ __global__ void __launch_bounds__(128, sizeof(F) >= 64 ? GB200_ACC_MIN_BLOCKS_WI
   partial[t] = msm_accumulate_range<F>(table, svals, begin, end);
 }
 
-// one QUAD of lanes per bucket: sum of its task partials through lane-cooperative additions (curve.cuh: 4 lanes share
-// the products of one addition - the tail is latency-bound).  Buckets with more than MSM_HEAVY partials (skewed witnesses:
-// many equal small scalars; a short top window; very large MSMs) are queued for the warp-per-bucket kernel below.
-constexpr uint32_t MSM_HEAVY = 48;
+// one thread per bucket: sum of its task partials.  Buckets with more than MSM_HEAVY partials
+// (skewed witnesses: many equal small scalars; a short top window) are queued for the
+// block-cooperative kernel below instead of being summed serially.
+constexpr uint32_t MSM_HEAVY = 48;   // below this a single thread's serial sum beats the warp tree (measured)
 template <class F>
 __global__ void __launch_bounds__(128) k_msm_combine(MsmPlan pl, const uint32_t* __restrict__ task_off,
                                                      const XYZZ<F>* __restrict__ partial,
                                                      XYZZ<F>* __restrict__ buckets, uint32_t* __restrict__ heavy_count,
                                                      uint32_t* __restrict__ heavy_list) {
-  const QuadDev quad = QuadDev::make();
-  const uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;
-  if (b >= pl.total_buckets) return;            // whole quads leave together
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= pl.total_buckets) return;
   const uint32_t t0 = task_off[b], t1 = task_off[b + 1];
   if (t1 - t0 > MSM_HEAVY) {
-    if (quad.sub == 0) heavy_list[atomicAdd(heavy_count, 1u)] = b;
+    heavy_list[atomicAdd(heavy_count, 1u)] = b;
     return;
   }
   XYZZ<F> acc = XYZZ<F>::inf();
   if (t0 < t1) acc = partial[t0];
-  for (uint32_t t = t0 + 1; t < t1; t++) xyzz_add_coop<F, QuadDev>(acc, partial[t], quad);
-  if (quad.sub == 0) buckets[b] = acc;
+  for (uint32_t t = t0 + 1; t < t1; t++) acc.add(partial[t]);
+  buckets[b] = acc;
 }
 
 // one WARP per heavy bucket (grid-stride over the queue): lanes stride the partials, then a
@@ -133,72 +136,75 @@ __global__ void __launch_bounds__(128) k_msm_combine_heavy(const uint32_t* __res
   }
 }
 
-// one quad per (set, chunk): weighted running sum of `chunk` buckets
+// one thread per (set, chunk): weighted running sum of `chunk` buckets
 template <class F>
 __global__ void __launch_bounds__(128) k_msm_reduce_chunks(MsmPlan pl, uint32_t chunks_per_set,
                                                            const XYZZ<F>* __restrict__ buckets,
                                                            XYZZ<F>* __restrict__ chunk_sums) {
-  const QuadDev quad = QuadDev::make();
-  const uint32_t g = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+  const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= chunks_per_set * (uint32_t)pl.nsets) return;
   const uint32_t s = g / chunks_per_set, t = g % chunks_per_set;
   const uint32_t lo = t * pl.chunk;
   uint32_t hi = lo + pl.chunk;
   if (hi > pl.set_size) hi = pl.set_size;
-  const XYZZ<F> r = msm_reduce_chunk_coop<F, QuadDev>(buckets + (size_t)s * pl.set_size, lo, hi, quad);
-  if (quad.sub == 0) chunk_sums[g] = r;
+  chunk_sums[g] = msm_reduce_chunk<F>(buckets + (size_t)s * pl.set_size, lo, hi);
 }
 
-// gridDim = (slices, nsets): block (j, s) sums slice j of set s's chunk sums - quads stride the slice, then a tree over the
-// block's quads through shared memory (dynamic: blockDim / 4 points)
+// The tail is a chain of dependent point additions (5-7 us each on an otherwise idle SM), so its cost is its DEPTH: the
+// chunk sums of a set are added as a pure tree - block (slice, set) reduces one slice of them in shared memory, one entry
+// per thread where the slice allows, k_msm_finish adds the slice sums - 12 levels for 4096 chunk sums.
 template <class F>
 __global__ void __launch_bounds__(256) k_msm_set_sum(uint32_t chunks_per_set, const XYZZ<F>* __restrict__ chunk_sums,
-                                                     XYZZ<F>* __restrict__ slice_sums) {
+                              XYZZ<F>* __restrict__ slice_sums) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   XYZZ<F>* sm = reinterpret_cast<XYZZ<F>*>(smem_raw);
-  const QuadDev quad = QuadDev::make();
-  const uint32_t nq = blockDim.x >> 2, q = threadIdx.x >> 2;
-  const uint32_t slices = gridDim.x, j = blockIdx.x, s = blockIdx.y;
+  const uint32_t s = blockIdx.y, slices = gridDim.x;
   const uint32_t per = (chunks_per_set + slices - 1) / slices;
-  const uint32_t lo = j * per, hi = lo + per < chunks_per_set ? lo + per : chunks_per_set;
+  const uint32_t lo = blockIdx.x * per;
+  const uint32_t hi = lo + per < chunks_per_set ? lo + per : chunks_per_set;
   const XYZZ<F>* src = chunk_sums + (size_t)s * chunks_per_set;
   XYZZ<F> acc = XYZZ<F>::inf();
-  for (uint32_t k = lo + q; k < hi; k += nq) xyzz_add_coop<F, QuadDev>(acc, src[k], quad);
-  if (quad.sub == 0) sm[q] = acc;
+  for (uint32_t k = lo + threadIdx.x; k < hi; k += blockDim.x) acc.add(src[k]);
+  sm[threadIdx.x] = acc;
   __syncthreads();
-  for (uint32_t w = nq >> 1; w > 0; w >>= 1) {
-    if (q < w) {
-      XYZZ<F> a = sm[q];
-      xyzz_add_coop<F, QuadDev>(a, sm[q + w], quad);
-      if (quad.sub == 0) sm[q] = a;
+  for (uint32_t w = blockDim.x >> 1; w > 0; w >>= 1) {
+    if (threadIdx.x < w) {
+      XYZZ<F> a = sm[threadIdx.x];
+      a.add(sm[threadIdx.x + w]);
+      sm[threadIdx.x] = a;
     }
     __syncthreads();
   }
-  if (threadIdx.x == 0) slice_sums[(size_t)s * slices + j] = sm[0];
+  if (threadIdx.x == 0) slice_sums[(size_t)s * slices + blockIdx.x] = sm[0];
 }
 
-// one quad: per set the sum of its slice sums, then Horner over the sets; result in gnark's Jacobian layout
+// slice sums -> set sums (warp w takes sets w, w + warps, ...: a 5-level tree over at most 32 slices), then Horner over
+// the sets on one thread; result in gnark Jacobian layout.  set_totals: nsets entries of scratch.
 template <class F>
-__global__ void __launch_bounds__(32) k_msm_finish(int nsets, int c, uint32_t slices, XYZZ<F>* __restrict__ slice_sums,
-                                                   Jacobian<F>* __restrict__ out) {
-  if (blockIdx.x != 0 || threadIdx.x >= 4) return;
-  const QuadDev quad = QuadDev::make();
-  XYZZ<F> r = XYZZ<F>::inf();
-  if (nsets > 0) {
-    // set sums are written back over slot [s * slices] of every set (the quad is the only reader and writer)
-    for (int s = 0; s < nsets; s++) {
-      XYZZ<F> acc = slice_sums[(size_t)s * slices];
-      for (uint32_t j = 1; j < slices; j++) xyzz_add_coop<F, QuadDev>(acc, slice_sums[(size_t)s * slices + j], quad);
-      if (quad.sub == 0) slice_sums[(size_t)s * slices] = acc;
-      __syncwarp(quad.mask);
+__global__ void __launch_bounds__(256) k_msm_finish(int nsets, int c, uint32_t slices, const XYZZ<F>* __restrict__ slice_sums,
+                                                    XYZZ<F>* __restrict__ set_totals, Jacobian<F>* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  XYZZ<F>* sm = reinterpret_cast<XYZZ<F>*>(smem_raw) + (threadIdx.x & ~31u);
+  const uint32_t lane = threadIdx.x & 31u;
+  for (int s = (int)(threadIdx.x >> 5); s < nsets; s += (int)(blockDim.x >> 5)) {
+    sm[lane] = lane < slices ? slice_sums[(size_t)s * slices + lane] : XYZZ<F>::inf();
+    __syncwarp();
+    for (uint32_t w = 16; w > 0; w >>= 1) {
+      if (lane < w && lane + w < slices) {
+        XYZZ<F> a = sm[lane];
+        a.add(sm[lane + w]);
+        sm[lane] = a;
+      }
+      __syncwarp();
     }
-    r = slice_sums[(size_t)(nsets - 1) * slices];
-    for (int w = nsets - 2; w >= 0; w--) {
-      for (int k = 0; k < c; k++) xyzz_dbl_coop<F, QuadDev>(r, quad);
-      xyzz_add_coop<F, QuadDev>(r, slice_sums[(size_t)w * slices], quad);
-    }
+    if (lane == 0) set_totals[s] = sm[0];
+    __syncwarp();
   }
-  if (quad.sub == 0) *out = r.to_jacobian();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    XYZZ<F> r = nsets > 0 ? msm_horner<F>(set_totals, nsets, c) : XYZZ<F>::inf();
+    *out = r.to_jacobian();
+  }
 }
 
 // Multi-GPU combine (the reference sums its chunk results on the host, icicle.go:383-411): gathered holds
@@ -208,12 +214,11 @@ __global__ void __launch_bounds__(32) k_msm_finish(int nsets, int c, uint32_t sl
 template <class F>
 __global__ void __launch_bounds__(64) k_points_fold(const Jacobian<F>* __restrict__ gathered, uint32_t world, uint32_t count,
                                                     Jacobian<F>* __restrict__ out) {
-  const QuadDev quad = QuadDev::make();
-  const uint32_t k = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;      // one quad of lanes per result point
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= count) return;
   XYZZ<F> acc = XYZZ<F>::from_jacobian(gathered[k]);
-  for (uint32_t r = 1; r < world; r++) xyzz_add_coop<F, QuadDev>(acc, XYZZ<F>::from_jacobian(gathered[(size_t)r * count + k]), quad);
-  if (quad.sub == 0) out[k] = acc.to_jacobian();
+  for (uint32_t r = 1; r < world; r++) acc.add(XYZZ<F>::from_jacobian(gathered[(size_t)r * count + k]));
+  out[k] = acc.to_jacobian();
 }
 
 // one thread per point of a serialised slice (points_decode.cuh); status[0] = first non-zero DECODE_* code seen,
@@ -296,7 +301,7 @@ cudaError_t msm_precompute_enqueue(cudaStream_t st, uint32_t n, int nwin, int c,
 // workspace + driver
 // ---------------------------------------------------------------------------
 constexpr int MSM_NUM_EVENTS = 8;
-constexpr uint32_t MSM_SET_SLICES = 16;   // upper bound of the blocks k_msm_set_sum spends on one bucket set
+constexpr uint32_t MSM_SET_SLICES = 32;   // upper bound of the blocks k_msm_set_sum spends on one bucket set
 template <class F>
 struct MsmLayout {
   size_t m;            // entries
@@ -333,19 +338,19 @@ cudaError_t msm_layout(const MsmPlan& pl, MsmLayout<F>& L) {
   L.o_partial = o; o += gb_align(L.max_tasks * sizeof(XYZZ<F>));
   L.o_buckets = o; o += gb_align((size_t)pl.total_buckets * sizeof(XYZZ<F>));
   L.o_chunks = o; o += gb_align((size_t)L.chunks_per_set * pl.nsets * sizeof(XYZZ<F>));
-  L.o_sets = o; o += gb_align((size_t)pl.nsets * MSM_SET_SLICES * sizeof(XYZZ<F>));   // slice sums of every set
+  L.o_sets = o; o += gb_align((size_t)pl.nsets * (MSM_SET_SLICES + 1) * sizeof(XYZZ<F>));   // slice sums, then set totals
   L.o_heavy = o; o += gb_align((L.max_tasks / MSM_HEAVY + 2) * 4);  // [0] = count, [1..] = bucket ids
   L.o_cub = o; o += gb_align(L.cub_bytes);
   L.total = o;
   return cudaSuccess;
 }
 
-// slices a set's chunk sums are cut into for k_msm_set_sum (one block each): at least 32 chunk sums per slice
-inline uint32_t msm_set_slices(uint32_t chunks_per_set) {
-  uint32_t s = chunks_per_set / 32;
-  if (s < 1) s = 1;
-  if (s > MSM_SET_SLICES) s = MSM_SET_SLICES;
-  return s;
+// largest power-of-two block that fits `budget` bytes of XYZZ<F> in shared memory
+template <class F>
+inline int msm_set_sum_threads(size_t budget = 160 * 1024) {
+  int t = 256;  // __launch_bounds__ of k_msm_set_sum (register budget: up to 255 regs/thread)
+  while ((size_t)t * sizeof(XYZZ<F>) > budget) t >>= 1;
+  return t;
 }
 
 // Enqueue a full MSM on `stream`.  d_scalars: n Fr elements (Montgomery) on device.
@@ -378,7 +383,7 @@ cudaError_t msm_enqueue(cudaStream_t stream, const MsmPlan& pl, const Affine<F>*
 
   if (pl.n == 0) {
     // empty sum = infinity
-    k_msm_finish<F><<<1, 32, 0, stream>>>(0, pl.c, 1, sets, d_out);  // nsets = 0: the point at infinity
+    k_msm_finish<F><<<1, 32, 32 * sizeof(XYZZ<F>), stream>>>(0, pl.c, 1, sets, sets, d_out);  // nsets = 0: the point at infinity
     return cudaGetLastError();
   }
   GB_EV(0);
@@ -408,7 +413,7 @@ cudaError_t msm_enqueue(cudaStream_t stream, const MsmPlan& pl, const Affine<F>*
   }
   uint32_t* heavy = (uint32_t*)(w + L.o_heavy);
   GB_CUDA_TRY(cudaMemsetAsync(heavy, 0, 4, stream));
-  k_msm_combine<F><<<(unsigned)(((size_t)nb * 4 + 127) / 128), 128, 0, stream>>>(pl, task_off, partial, buckets, heavy, heavy + 1);
+  k_msm_combine<F><<<(nb + 127) / 128, 128, 0, stream>>>(pl, task_off, partial, buckets, heavy, heavy + 1);
   {
     const int ht = 128;  // 4 warps = 4 buckets in flight per block
     const size_t hsmem = (size_t)ht * sizeof(XYZZ<F>);
@@ -417,16 +422,19 @@ cudaError_t msm_enqueue(cudaStream_t stream, const MsmPlan& pl, const Affine<F>*
   }
   GB_EV(5);
   const uint32_t nchunks = L.chunks_per_set * (uint32_t)pl.nsets;
-  k_msm_reduce_chunks<F><<<(unsigned)(((size_t)nchunks * 4 + 127) / 128), 128, 0, stream>>>(pl, L.chunks_per_set, buckets, chunks);
+  k_msm_reduce_chunks<F><<<(nchunks + 127) / 128, 128, 0, stream>>>(pl, L.chunks_per_set, buckets, chunks);
   GB_EV(6);
-  const uint32_t slices = msm_set_slices(L.chunks_per_set);
-  const uint32_t per_slice = (L.chunks_per_set + slices - 1) / slices;
-  int st = 256;                                      // 64 quads; fewer when a slice holds fewer chunk sums
-  while (st > 32 && (uint32_t)(st / 4) > per_slice) st >>= 1;
-  const size_t smem = (size_t)(st / 4) * sizeof(XYZZ<F>);
+  int st = msm_set_sum_threads<F>();
+  while (st > 32 && (uint32_t)st > L.chunks_per_set) st >>= 1;
+  uint32_t slices = (L.chunks_per_set + (uint32_t)st - 1) / (uint32_t)st;       // one chunk sum per thread where 32 slices allow
+  if (slices > MSM_SET_SLICES) slices = MSM_SET_SLICES;
+  const size_t smem = (size_t)st * sizeof(XYZZ<F>);
   GB_CUDA_TRY(cudaFuncSetAttribute(k_msm_set_sum<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_msm_set_sum<F><<<dim3(slices, (unsigned)pl.nsets), st, smem, stream>>>(L.chunks_per_set, chunks, sets);
-  k_msm_finish<F><<<1, 32, 0, stream>>>(pl.nsets, pl.c, slices, sets, d_out);
+  const int fw = pl.nsets < 8 ? (pl.nsets > 0 ? pl.nsets : 1) : 8;                // warps of the finish block
+  const size_t fsmem = (size_t)fw * 32 * sizeof(XYZZ<F>);
+  GB_CUDA_TRY(cudaFuncSetAttribute(k_msm_finish<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+  k_msm_finish<F><<<1, 32 * fw, fsmem, stream>>>(pl.nsets, pl.c, slices, sets, sets + (size_t)pl.nsets * MSM_SET_SLICES, d_out);
   GB_EV(7);
 #undef GB_EV
   return cudaGetLastError();

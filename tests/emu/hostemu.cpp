@@ -58,8 +58,6 @@ int wide_op(int op, const void* a_, const void* b_, void* out_) {
   return -1;
 }
 
-int g_msm_coop = 0;
-
 template <class Fr, class F>
 int msm_emu(const void* points_, const void* scalars_, uint32_t n, int c, int precomp, uint32_t task_len,
             uint32_t chunk, void* out_jac) {
@@ -85,16 +83,13 @@ int msm_emu(const void* points_, const void* scalars_, uint32_t n, int c, int pr
   std::vector<uint32_t> off(pl.total_buckets + 1);
   for (uint32_t b = 0; b <= pl.total_buckets; b++)
     off[b] = (uint32_t)(std::lower_bound(skeys.begin(), skeys.end(), b) - skeys.begin());
-  // accumulate with tasks, then combine (g_msm_coop: the lane-cooperative additions of the kernels' tail, host policy)
-  const QuadHost quad;
+  // accumulate with tasks, then combine
   std::vector<XYZZ<F>> buckets(pl.total_buckets);
   for (uint32_t b = 0; b < pl.total_buckets; b++) {
     XYZZ<F> acc = XYZZ<F>::inf();
     for (uint32_t s = off[b]; s < off[b + 1]; s += pl.task_len) {
       uint32_t e = std::min(off[b + 1], s + pl.task_len);
-      const XYZZ<F> part = msm_accumulate_range<F>(table.data(), svals.data(), s, e);
-      if (g_msm_coop) xyzz_add_coop<F, QuadHost>(acc, part, quad);
-      else acc.add(part);
+      acc.add(msm_accumulate_range<F>(table.data(), svals.data(), s, e));
     }
     buckets[b] = acc;
   }
@@ -104,19 +99,11 @@ int msm_emu(const void* points_, const void* scalars_, uint32_t n, int c, int pr
     XYZZ<F> tot = XYZZ<F>::inf();
     for (uint32_t lo = 0; lo < pl.set_size; lo += pl.chunk) {
       uint32_t hi = std::min(pl.set_size, lo + pl.chunk);
-      if (g_msm_coop) {
-        const XYZZ<F> cs = msm_reduce_chunk_coop<F, QuadHost>(buckets.data() + (size_t)s * pl.set_size, lo, hi, quad);
-        // bit for bit the one-thread version: same formulas, same products
-        const XYZZ<F> ref = msm_reduce_chunk<F>(buckets.data() + (size_t)s * pl.set_size, lo, hi);
-        if (memcmp(&cs, &ref, sizeof(cs)) != 0) return -4;
-        xyzz_add_coop<F, QuadHost>(tot, cs, quad);
-      } else {
-        tot.add(msm_reduce_chunk<F>(buckets.data() + (size_t)s * pl.set_size, lo, hi));
-      }
+      tot.add(msm_reduce_chunk<F>(buckets.data() + (size_t)s * pl.set_size, lo, hi));
     }
     set_sums[s] = tot;
   }
-  XYZZ<F> res = g_msm_coop ? msm_horner_coop<F, QuadHost>(set_sums.data(), pl.nsets, c, quad) : msm_horner<F>(set_sums.data(), pl.nsets, c);
+  XYZZ<F> res = msm_horner<F>(set_sums.data(), pl.nsets, c);
   *reinterpret_cast<Jacobian<F>*>(out_jac) = res.to_jacobian();
   return 0;
 }
@@ -356,7 +343,6 @@ int emu_stage_file(const char* path, uint64_t off, size_t bytes, size_t slot_byt
 
 // plan tile size used by emu_ntt (GB200_NTT_TILE_LOG on the device)
 // 1: emu_ntt walks the register-round kernel (GB200_NTT_RADIX8 on the device) instead of the one-stage-per-barrier one
-int emu_msm_set_coop(int on) { g_msm_coop = on ? 1 : 0; return 0; }
 int emu_ntt_set_tile_log(int t) { if (t < 2 || t > NTT_MAX_TILE_LOG) return -1; g_ntt_tile_log = t; return 0; }
 
 int emu_ntt(int curve, void* data, unsigned logn, int inverse, int decimation, int on_coset, const void* gen_mont,

@@ -141,15 +141,6 @@ def test_msm_logic(hostemu, c, group):
         assert hostemu.emu_msm(c.curve_id, group, P(PA), P(SA), n, cw, pre, tl, ch, P(out)) == 0
         got = ec.from_jac(F, ec.unpack_points(c, group, out, ncoords=3)[0])
         assert got == exp, (c.name, group, cw, pre)
-        # the reduction tail through the lane-cooperative additions (xyzz_add_coop / xyzz_dbl_coop with the host quad
-        # policy): the same Jacobian representative limb for limb, every chunk sum compared inside the emulation
-        out2 = np.zeros_like(out)
-        hostemu.emu_msm_set_coop(1)
-        try:
-            assert hostemu.emu_msm(c.curve_id, group, P(PA), P(SA), n, cw, pre, tl, ch, P(out2)) == 0
-        finally:
-            hostemu.emu_msm_set_coop(0)
-        assert np.array_equal(out, out2), (c.name, group, cw, pre, "coop")
 
 
 @pytest.mark.parametrize("c", ALL, ids=lambda c: c.name)

@@ -1,10 +1,9 @@
 #!/usr/bin/env python3
-"""NTT timing on cuda:0 for the tile sizes of GB200_NTT_TILE_LOG (11 = default: one 1024-thread block per SM;
-10 / 9: two / four smaller blocks per SM) and for the register-round kernel (GB200_NTT_RADIX8=1: three stages per
-shared-memory exchange).  One JSON line per (curve, log2n, radix8, tile); every variant must reproduce
-the default variant's output bit for bit (the default is pinned against the oracle by tests/test_gpu_ntt.py).
+"""NTT timing on cuda:0 for the tile sizes of GB200_NTT_TILE_LOG (8 = default: 128-thread blocks, eight per SM;
+11: one 1024-thread block per SM).  One JSON line per (curve, log2n, tile); every tile size must reproduce the first
+one's output bit for bit (the default is pinned against the oracle by tests/test_gpu_ntt.py).
 
-   python tools/sweep_ntt.py [--curve bn254] [--logs 20,22,24] [--tiles 11,10,9] [--reps 20]"""
+   python tools/sweep_ntt.py [--curve bn254] [--logs 20,22,24] [--tiles 8,9,10,11] [--reps 20]"""
 import argparse
 import json
 import os
@@ -22,8 +21,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--curve", default="bn254")
     ap.add_argument("--logs", default="20,22,24")
-    ap.add_argument("--tiles", default="11,10,9")
-    ap.add_argument("--radix8", default="0,1", help="GB200_NTT_RADIX8 values (1 = register rounds, k_ntt_pass_r8)")
+    ap.add_argument("--tiles", default="8,9,10,11")
     ap.add_argument("--reps", type=int, default=20)
     args = ap.parse_args()
     curve = {"bn254": lib.BN254, "bls12-381": lib.BLS12_381, "bls12-377": lib.BLS12_377, "bw6-761": lib.BW6_761}[args.curve]
@@ -39,9 +37,8 @@ def main():
         X[:, L - 1] &= np.uint64((1 << 56) - 1)
         x0 = torch.from_numpy(X.view(np.int64).reshape(-1)).cuda()
         ref = None
-        for r8, tile in [(int(r), int(t)) for r in args.radix8.split(",") for t in args.tiles.split(",")]:
+        for tile in [int(t) for t in args.tiles.split(",")]:
             os.environ["GB200_NTT_TILE_LOG"] = str(tile)
-            os.environ["GB200_NTT_RADIX8"] = str(r8)
             d = lib.Domain(curve, logn)
             outs = []
             for inv, dec, cos in ((False, lib.DIF, False), (True, lib.DIT, True)):
@@ -61,11 +58,10 @@ def main():
             e1.record()
             lib.sync(0)
             ms = e0.elapsed_time(e1) / args.reps
-            print(json.dumps({"curve": args.curve, "log2n": logn, "tile_log": tile, "radix8": r8, "ms": ms, "matches_default": bool(same),
+            print(json.dumps({"curve": args.curve, "log2n": logn, "tile_log": tile, "ms": ms, "matches_first": bool(same),
                               "GBps_model": 2 * n * L * 8 * (2 if logn <= 2 * tile else 3) / ms / 1e6}), flush=True)
             d.free()
         os.environ.pop("GB200_NTT_TILE_LOG", None)
-        os.environ.pop("GB200_NTT_RADIX8", None)
 
 
 if __name__ == "__main__":
