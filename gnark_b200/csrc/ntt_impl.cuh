@@ -85,10 +85,9 @@ k_ntt_pass(NttPass p, int logn, int dit, const Fr* __restrict__ tw, Fr* __restri
     }
 #pragma unroll
     for (int l = 0; l < N; l++) { sm[l * tile_elems + lo] = a.l[l]; sm[l * tile_elems + hi] = b.l[l]; }
-    // A stage on local bit lb <= 5 only touches slots [64 w, 64 w + 64) of warp w (lo = t with a zero spliced in at bit
-    // lb), so between two such stages the warp synchronises with itself and drifts freely from the block's other warps.
-    const int lb_next = k + 1 < p.S ? p.cb + (dit ? k + 1 : p.S - 2 - k) : 32;
-    if (lb <= 5 && lb_next <= 5) __syncwarp(); else __syncthreads();
+    // (between two stages on local bits <= 5 a warp only touches its own 64 slots and __syncwarp() would do; measured
+    // 1 % slower than the block barrier, profiles/r02_session5.md)
+    __syncthreads();
   }
 
   // store (+ optional post-scale)
