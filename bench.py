@@ -299,10 +299,11 @@ class Ctx:
         return [float(x) for x in t]
 
     def sum_mod_r(self, value, r):
-        """sum over ranks of a residue < 2^256 (all_gather of 4 x 64-bit limbs)"""
+        """sum over ranks of a residue below r (all_gather of its 64-bit limbs)"""
         if self.world == 1:
             return value % r
-        limbs = [(value >> (64 * k)) & ((1 << 63) - 1 | (1 << 63)) for k in range(4)]
+        nl = (r.bit_length() + 63) // 64
+        limbs = [(value >> (64 * k)) & ((1 << 64) - 1) for k in range(nl)]
         t = self.torch.tensor([x - (1 << 64) if x >= (1 << 63) else x for x in limbs], dtype=self.torch.int64, device="cuda")
         parts = [self.torch.empty_like(t) for _ in range(self.world)]
         self.dist.all_gather(parts, t)
@@ -463,7 +464,7 @@ def strong_leg(ctx, curve_name="bn254", total_log=24, steps=5):
     configs[4]: BW6-761 2^24): every rank builds ITS shard of known-discrete-log bases on its GPU
     (b200_fixed_base_batch), the result of every step is checked on the full known-dlog sum."""
     torch, lib = ctx.torch, ctx.lib
-    from oracle import corelib, ec, ff
+    from oracle import corelib, derive, ec, ff
     from oracle.params import CURVES
     C = CURVES[curve_name]
     world, rank, local = ctx.world, ctx.rank, ctx.local
@@ -477,13 +478,19 @@ def strong_leg(ctx, curve_name="bn254", total_log=24, steps=5):
     d_pts = torch.zeros((n, 2 * FL), dtype=torch.int64, device="cuda")
     d_ks = torch.from_numpy(ks.view(np.int64)).cuda()
     torch.cuda.synchronize()
-    lib.fixed_base_batch(C.curve_id, 1, ec.pack_points(C, 1, [C.g1]), d_ks, n=n, dev=local, out=d_pts)
+    # the generator where the oracle holds gnark-crypto's (BN254, BLS12-381), else a derived point of order r on an
+    # a = 0 curve over the same field (oracle/derive.py; BW6-761 - the group law never uses b): never the point at
+    # infinity, which would make every base trivial
+    base = C.g1 if C.g1 is not None else derive.subgroup_point(C, 1)
+    assert base is not None
+    lib.fixed_base_batch(C.curve_id, 1, ec.pack_points(C, 1, [base]), d_ks, n=n, dev=local, out=d_pts)
     table = lib.Table(C.curve_id, 1, d_pts, dev=local, precomp=True, n=n, on_device=True)
     del d_pts, d_ks
     load_s = time.perf_counter() - t0
     info = table.info()
     dot = corelib.fr_dot(C, ks, sc)
-    expected = ec.scalar_mul(ff.Fp(C.p), ctx.sum_mod_r(dot, C.r), C.g1)
+    expected = ec.scalar_mul(ff.Fp(C.p), ctx.sum_mod_r(dot, C.r), base)
+    assert expected is not None
     d_sc = torch.from_numpy(sc.view(np.int64)).cuda()
     d_parts = torch.zeros((steps, 3 * FL), dtype=torch.int64, device="cuda")
     d_tot = torch.zeros((steps, 3 * FL), dtype=torch.int64, device="cuda")
@@ -521,35 +528,46 @@ def strong_leg(ctx, curve_name="bn254", total_log=24, steps=5):
             "combine": "one ncclAllGather + k_points_fold on the device" if world > 1 else "none (single GPU)"}
 
 
-def groth16_leg(ctx, g1_pts):
+def groth16_leg(ctx):
     """Secondary BASELINE metric: Groth16 prove ms at 2^20 R1CS (configs[2]), BN254.
     From "A,B,C,W on the host" to "3 proof points on the host" (solver excluded):
-    7 NTT(2^20) + 4 G1 MSM + 1 G2 MSM + host-side assembly.  Synthetic key: the G1 tables reuse the benchmark's 2^20
-    distinct known-dlog points, G2.B = 2^20 distinct points built on the GPU (b200_fixed_base_batch); synthetic
-    (unsatisfied) solution vectors - timing only, the pipeline's parity is pinned by tests/test_gpu_groth16.py."""
+    7 NTT(2^20) + 4 G1 MSM + 1 G2 MSM + host-side assembly.  The instance is a SATISFIED circuit of 2^20 - 1
+    constraints with a trapdoor key (oracle/groth16_fast.py; key points built on the GPU with b200_fixed_base_batch):
+    before timing, one proof with injected r, s is checked - the three proof points equal dlog * generator and the
+    verifier's pairing equation holds on them (backend/groth16/bn254/verify.go:38-140)."""
     from gnark_b200 import groth16 as g16
     from oracle import ec
+    from oracle import groth16_fast as gf
     from oracle.params import BN254 as C
     torch, lib = ctx.torch, ctx.lib
     dev, rank, world = ctx.local, ctx.rank, ctx.world
-    n = 1 << LOG_N
-    rs = rng(5)
-    nb_wires, nb_public = n + 2, 2
-    # the same synthetic key on every rank (each loads its shard of it)
-    g2_b = lib.fixed_base_batch(C.curve_id, 2, ec.pack_points(C, 2, [C.g2]), rand_fr(rs, nb_wires), n=nb_wires, dev=dev)
-    g1 = np.concatenate([g1_pts, g1_pts[:2]])
-    pk = g16.ProvingKey.from_arrays(
-        g16.BN254, n, g1[0], g1[1], g1[2], g1[:nb_wires], g1[:nb_wires], g1[:n - 1], g1[:nb_wires - nb_public],
-        g2_b[0], g2_b[1], g2_b, np.zeros(nb_wires, dtype=np.uint8), np.zeros(nb_wires, dtype=np.uint8),
-        nb_public)
+    t0 = time.perf_counter()
+    inst = gf.satisfied_instance(C, LOG_N, seed=20)          # the same instance on every rank (each loads its shard)
+    fb = lambda group, dl: lib.fixed_base_batch(C.curve_id, group, ec.pack_points(C, group, [C.g1 if group == 1 else C.g2]),
+                                                np.ascontiguousarray(dl), dev=dev)
+    kp = gf.key_points(inst, fb)
+    pk = g16.ProvingKey.from_arrays(g16.BN254, inst.n, kp["alpha"], kp["beta"], kp["delta"], kp["A"], kp["B"], kp["Z"], kp["K"],
+                                    kp["beta2"], kp["delta2"], kp["B2"], inst.inf_a, inst.inf_b, inst.nb_public)
+    fixture_s = time.perf_counter() - t0
     opts = [g16.WithDeviceID(dev), g16.WithSharding(rank, world)]
     t0 = time.perf_counter()
     pk.setup_device_pointers(g16.NewConfig(*opts))
     setup_s = time.perf_counter() - t0
-    sol_pageable = g16.R1CSSolution(W=rand_fr(rs, nb_wires), A=rand_fr(rs, n - 1), B=rand_fr(rs, n - 1), C=rand_fr(rs, n - 1))
+    a, b, c = inst.solution_abc()
+    sol_pageable = g16.R1CSSolution(W=inst.wires(), A=a, B=b, C=c)
     # the solver's output vectors live in C-owned pinned buffers (b200_host_alloc, INTEGRATION.md §3)
     keep = [torch.from_numpy(v.view(np.int64)).pin_memory() for v in (sol_pageable.W, sol_pageable.A, sol_pageable.B, sol_pageable.C)]
     sol = g16.R1CSSolution(*[k.numpy().view(np.uint64) for k in keep])
+    # one checked proof (r, s injected, the same on every rank)
+    rs = iter([0x5EED << 200 | 1, 0xFACE << 190 | 2])
+    proof = g16.ProveSolution(pk, sol, *opts, g16.WithRandomness(lambda q: next(rs)))
+    verified = None
+    if rank == 0:
+        t0 = time.perf_counter()
+        e = gf.expected(inst, 0x5EED << 200 | 1, 0xFACE << 190 | 2)
+        verified = bool(gf.verify_points(inst, ec.unpack_points(C, 1, proof.Ar)[0], ec.unpack_points(C, 2, proof.Bs)[0],
+                                         ec.unpack_points(C, 1, proof.Krs)[0], e, with_pairing=True))
+        verify_s = time.perf_counter() - t0
     times = []
     for i in range(10):          # fixed count on every rank
         cur = sol if i < 6 else sol_pageable
@@ -558,15 +576,22 @@ def groth16_leg(ctx, g1_pts):
         g16.ProveSolution(pk, cur, *opts)
         times.append(ctx.max_over_ranks(1e3 * (time.perf_counter() - t0))[0])
     pk.free_gpu_resources()
-    return {"metric": "groth16_prove_ms", "n_constraints": n - 1, "curve": "bn254", "n_gpus": world,
-            "parallelism": ("every MSM table point-range sharded x%d, computeH replicated, 5 partial points combined on the "
-                            "device (ncclAllGather + fold)" % world) if world > 1 else "single GPU",
-            "prove_ms_median": float(np.median(times[1:6])), "prove_ms_min": float(min(times[1:6])),
-            "prove_ms_pageable_median": float(np.median(times[6:])),
-            "first_call_ms": times[0], "key_load_s": setup_s,
-            "includes": "H2D of W,A,B,C (4 x 32 MiB, pinned host buffers; pageable variant reported beside it), "
-                        "computeH (7 NTT), 5 MSM, combine, D2H, host assembly",
-            "excludes": "R1CS solver (CPU, out of scope)", "data": "synthetic key (2^20 distinct bases per table), unsatisfied vectors"}
+    out = {"metric": "groth16_prove_ms", "n_constraints": inst.m, "n_wires": inst.nb_wires, "curve": "bn254", "n_gpus": world,
+           "parallelism": ("every MSM table point-range sharded x%d, computeH replicated, 5 partial points combined on the "
+                           "device (ncclAllGather + fold)" % world) if world > 1 else "single GPU",
+           "prove_ms_median": float(np.median(times[1:6])), "prove_ms_min": float(min(times[1:6])),
+           "prove_ms_pageable_median": float(np.median(times[6:])),
+           "first_call_ms": times[0], "key_load_s": setup_s, "fixture_s": fixture_s,
+           "includes": "H2D of W,A,B,C (4 x 32 MiB, pinned host buffers; pageable variant reported beside it), "
+                       "computeH (7 NTT), 5 MSM, combine, D2H, host assembly",
+           "excludes": "R1CS solver (CPU, out of scope)",
+           "data": "satisfied product-network circuit, trapdoor key with 2^20 distinct bases per table (oracle/groth16_fast.py)"}
+    if rank == 0:
+        out["verified"] = verified
+        out["verify_s"] = verify_s
+        out["check"] = ("proof points == dlog * generator (trapdoor key) and e(Ar,Bs) = e(alpha,beta) e(sum w_i K_i, gamma) "
+                        "e(Krs,delta) on the proof points with a real pairing")
+    return out
 
 
 def plonk_leg(ctx, log2n):
@@ -631,7 +656,7 @@ def run_b200(args):
     if not args.no_strong:
         legs.append(("strong", lambda: strong_leg(ctx, "bn254", args.strong_log)))
     if not args.no_groth16:
-        legs.append(("groth16", lambda: groth16_leg(ctx, pts)))
+        legs.append(("groth16", lambda: groth16_leg(ctx)))
     if args.bw6 or (args.bw6 is None and ctx.world == 8):
         legs.append(("bw6", lambda: strong_leg(ctx, "bw6-761", args.bw6_log, steps=3)))
     for name, fn in legs:

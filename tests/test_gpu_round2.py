@@ -343,3 +343,37 @@ def test_table_from_encoded_points_other_curves(gpu, cname):
         t.free()
         with pytest.raises(gpu.B200Error):
             gpu.Table.from_encoded(c.curve_id, 2, data, 64, gpu.POINTS_COMPRESSED)
+
+
+@pytest.mark.parametrize("cname,logn", [("bn254", 20), ("bls12-381", 16)])
+def test_groth16_full_size_proof_verifies(gpu, cname, logn):
+    """BASELINE configs[2] at size: a SATISFIED 2^20 - 1 constraint circuit (oracle/groth16_fast.py; its small sizes are
+    checked against the big-int oracle in tests/test_groth16_fast.py), trapdoor key built with b200_fixed_base_batch,
+    one b200_groth16_prove with r, s injected.  Checked: each of the five MSM results and the three proof points equal
+    dlog * generator (bit-exact affine points), and the reference's own acceptance test of a proof - Verify, the pairing
+    equation on the proof points (backend/groth16/bn254/verify.go:38-140)."""
+    from gnark_b200 import groth16 as b200
+    from oracle import groth16_fast as gf
+    c = CURVES[cname]
+    inst = gf.satisfied_instance(c, logn, seed=2020)
+    assert gf.check_satisfied(inst)
+    fb = lambda group, dl: gpu.fixed_base_batch(c.curve_id, group, ec.pack_points(c, group, [c.g1 if group == 1 else c.g2]),
+                                                np.ascontiguousarray(dl))
+    kp = gf.key_points(inst, fb)
+    pk = b200.ProvingKey.from_arrays(c.curve_id, inst.n, kp["alpha"], kp["beta"], kp["delta"], kp["A"], kp["B"], kp["Z"],
+                                     kp["K"], kp["beta2"], kp["delta2"], kp["B2"], inst.inf_a, inst.inf_b, inst.nb_public)
+    a, b, cc = inst.solution_abc()
+    sol = b200.R1CSSolution(W=inst.wires(), A=a, B=b, C=cc)
+    rs = [0x1234567 << 100 | 0x89, 0xABCDEF << 90 | 0x77]
+    it = iter(rs)
+    proof = b200.ProveSolution(pk, sol, b200.WithDeviceID(0), b200.WithRandomness(lambda q: next(it)), keep_msm=True)
+    e = gf.expected(inst, rs[0], rs[1])
+    F1, F2 = ff.Fp(c.p), ff.base_field(c, 2)
+    L = 3 * c.fp_limbs
+    for k, dlog in enumerate((e.msm_a, e.msm_b, e.msm_z, e.msm_k)):
+        got = ec.from_jac(F1, ec.unpack_points(c, 1, proof.msm[k * L:(k + 1) * L], ncoords=3)[0])
+        assert got == ec.scalar_mul(F1, dlog, c.g1), ("msm", k)
+    assert ec.from_jac(F2, ec.unpack_points(c, 2, proof.msm[4 * L:], ncoords=3)[0]) == ec.scalar_mul(F2, e.msm_b, c.g2)
+    assert gf.verify_points(inst, ec.unpack_points(c, 1, proof.Ar)[0], ec.unpack_points(c, 2, proof.Bs)[0],
+                            ec.unpack_points(c, 1, proof.Krs)[0], e, with_pairing=True)
+    pk.free_gpu_resources()
