@@ -11,7 +11,8 @@
 // values and digests cross to the host.  Challenges and blinding coefficients are INPUTS (the Fiat-Shamir
 // transcript encoding is gnark-crypto's; a Go shim derives them exactly as prove.go:492-555 does).  BSB22 commitment
 // gates (:867-884) are supported with the committed polynomials PI2_i supplied by the caller (the reference's solver
-// hint :280-318 produces them); StatisticalZK is not.  Host-side scalar work uses host_fr.h.
+// hint :280-318 produces them), and so is StatisticalZK (:239-242,689-722,1476-1481: the two quotient-shard randomisers are
+// inputs like the blinding coefficients).  Host-side scalar work uses host_fr.h.
 #include <chrono>
 #include <memory>
 #include <vector>
@@ -87,8 +88,12 @@ struct b200_plonk_session_s {
   void *qk_br = nullptr, *qk_canon = nullptr;
   void* h = nullptr;              // quotient, canonical regular (4n)
   void* lin = nullptr;            // linearised polynomial (n + 3)
-  uint8_t blind[4][3 * 8 * HOSTFR_MAX_LIMBS];   // bl, br, bo (2 each), bz (3)
-  uint8_t beta[8 * HOSTFR_MAX_LIMBS], gamma[8 * HOSTFR_MAX_LIMBS], alpha[8 * HOSTFR_MAX_LIMBS], zeta[8 * HOSTFR_MAX_LIMBS];
+  // field elements kept as bytes; 16-byte aligned because callees may read them as limb structs
+  alignas(16) uint8_t blind[4][3 * 8 * HOSTFR_MAX_LIMBS];   // bl, br, bo (2 each), bz (3)
+  alignas(16) uint8_t beta[8 * HOSTFR_MAX_LIMBS], gamma[8 * HOSTFR_MAX_LIMBS], alpha[8 * HOSTFR_MAX_LIMBS], zeta[8 * HOSTFR_MAX_LIMBS];
+  // StatisticalZK: quotientShardsRandomizers b1, b2 (b200_plonk_set_quotient_randomizers); szk = false: plain shards
+  alignas(16) uint8_t hr[2][8 * HOSTFR_MAX_LIMBS];
+  bool szk = false;
   explicit b200_plonk_session_s(b200_plonk_pk_s* p) : pk(p), S(p->dev) {}
 };
 
@@ -124,19 +129,28 @@ int32_t canonical_blinded(b200_plonk_pk_s* pk, const void* d_lagrange, const uin
   return 0;
 }
 
+// element `idx` of a device vector += delta (one element crosses to the host and back, like the blinding patches)
+int32_t add_to_element(b200_plonk_pk_s* pk, void* d_vec, size_t idx, const HostFr& delta) {
+  alignas(16) uint8_t e[8 * HOSTFR_MAX_LIMBS];
+  uint8_t* p = (uint8_t*)d_vec + idx * pk->fb;
+  RC(b200_d2h(pk->dev, e, p, pk->fb));
+  pk->fr->store(e, pk->fr->add(pk->fr->load(e), delta));
+  return b200_h2d(pk->dev, p, e, pk->fb);
+}
+
 int32_t commit(b200_plonk_pk_s* pk, const void* d_coeffs, size_t count, void* out_jac) {
   return b200_msm_g1(pk->srs, 0, count, d_coeffs, 1, out_jac);
 }
 
 int32_t eval_at(b200_plonk_pk_s* pk, const void* d_coeffs, size_t count, const HostFr& x, HostFr* out) {
-  uint8_t xb[8 * HOSTFR_MAX_LIMBS], ob[8 * HOSTFR_MAX_LIMBS];
+  alignas(16) uint8_t xb[8 * HOSTFR_MAX_LIMBS], ob[8 * HOSTFR_MAX_LIMBS];
   pk->fr->store(xb, x);
   RC(b200_poly_eval(pk->dev, pk->curve, d_coeffs, count, xb, ob));
   *out = pk->fr->load(ob);
   return 0;
 }
 int32_t axpy(b200_plonk_pk_s* pk, void* d_y, const HostFr& a, const void* d_x, size_t count) {
-  uint8_t ab[8 * HOSTFR_MAX_LIMBS];
+  alignas(16) uint8_t ab[8 * HOSTFR_MAX_LIMBS];
   pk->fr->store(ab, a);
   return b200_vec_axpy(pk->dev, pk->curve, d_y, ab, d_x, count);
 }
@@ -185,7 +199,7 @@ int32_t b200_plonk_pk_load(int32_t dev, int32_t curve, const b200_plonk_pk_desc*
   // domain0 handles for the four cosets g * w4^i (computeNumerator :943-948) and the big domain
   HostFr coset = pk->g;
   for (int i = 0; i < 4; i++) {
-    uint8_t cb[8 * HOSTFR_MAX_LIMBS];
+    alignas(16) uint8_t cb[8 * HOSTFR_MAX_LIMBS];
     fr->store(cb, coset);
     RC(b200_ntt_domain_new(dev, curve, d->log2n, nullptr, cb, &pk->dom0[i]));
     coset = fr->mul(coset, pk->w4);
@@ -326,6 +340,19 @@ int32_t b200_plonk_set_qk(b200_plonk_session_t s, const void* qk_lagrange) {
 }
 
 // buildRatioCopyConstraint :635-668 + commit Z
+// optional, between begin and quotient: StatisticalZK (backend.WithStatisticalZeroKnowledge; newInstance samples the two
+// quotientShardsRandomizers, prove.go:239-242)
+int32_t b200_plonk_set_quotient_randomizers(b200_plonk_session_t s, const void* hr2) {
+  GUARD_BEGIN
+  if (!s || !hr2) return set_error("plonk_set_quotient_randomizers: null argument");
+  if (s->stage < 1 || s->stage > 2) return set_error("plonk_set_quotient_randomizers: call after plonk_begin and before plonk_quotient");
+  memcpy(s->hr[0], hr2, s->pk->fb);
+  memcpy(s->hr[1], (const uint8_t*)hr2 + s->pk->fb, s->pk->fb);
+  s->szk = true;
+  return 0;
+  GUARD_END
+}
+
 int32_t b200_plonk_commit_z(b200_plonk_session_t s, const void* beta, const void* gamma, const void* bz, void* out_z) {
   GUARD_BEGIN
   if (!s || !beta || !gamma || !bz || !out_z) return set_error("plonk_commit_z: null argument");
@@ -358,7 +385,7 @@ int32_t b200_plonk_quotient(b200_plonk_session_t s, const void* alpha, void* out
   Scratch T(dev);     // the 12 polynomials on the current coset: released when this stage ends
   void* onc[12];
   for (int k = 0; k < 12; k++) RC(T.alloc(n * fb, &onc[k]));
-  uint8_t gb[8 * HOSTFR_MAX_LIMBS], w4b[8 * HOSTFR_MAX_LIMBS];
+  alignas(16) uint8_t gb[8 * HOSTFR_MAX_LIMBS], w4b[8 * HOSTFR_MAX_LIMBS];
   fr->store(gb, pk->g); fr->store(w4b, pk->w4);
   // argument order of b200_plonk_coset_args: l r o z s1 s2 s3 ql qr qm qo qk
   const void* srcs[12] = {s->cb[0], s->cb[1], s->cb[2], s->cb[3], pk->br[S1], pk->br[S2], pk->br[S3],
@@ -393,8 +420,24 @@ int32_t b200_plonk_quotient(b200_plonk_session_t s, const void* alpha, void* out
     }
   }
   RC(b200_plonk_divide_by_zh(pk->dom1, pk->logn, s->h));      // -> h canonical regular (4n)
-  for (int k = 0; k < 3; k++)
-    RC(commit(pk, (uint8_t*)s->h + (size_t)k * (n + 2) * fb, n + 2, (uint8_t*)out_h + (size_t)k * s->jb));
+  if (!s->szk) {
+    for (int k = 0; k < 3; k++)
+      RC(commit(pk, (uint8_t*)s->h + (size_t)k * (n + 2) * fb, n + 2, (uint8_t*)out_h + (size_t)k * s->jb));
+  } else {
+    // StatisticalZK (h1(), h2(), h3(), prove.go:689-722): h1 + b1 X^(n+2), h2 - b1 + b2 X^(n+2), h3 - b2.  The shards
+    // are adjacent slices of s->h, so each randomised shard is committed from a copy; s->h keeps the plain quotient
+    // and the linearised polynomial gets the matching correction (b200_plonk_linearise).
+    const HostFr b1 = fr->load(s->hr[0]), b2 = fr->load(s->hr[1]);
+    void* tmp;
+    RC(T.alloc((n + 3) * fb, &tmp));
+    for (int k = 0; k < 3; k++) {
+      RC(dzero(dev, (uint8_t*)tmp + (n + 2) * fb, fb));
+      RC(d2d(dev, tmp, (uint8_t*)s->h + (size_t)k * (n + 2) * fb, (n + 2) * fb));
+      if (k > 0) RC(add_to_element(pk, tmp, 0, fr->neg(k == 1 ? b1 : b2)));
+      if (k < 2) RC(b200_h2d(dev, (uint8_t*)tmp + (n + 2) * fb, s->hr[k], fb));
+      RC(commit(pk, tmp, k < 2 ? n + 3 : n + 2, (uint8_t*)out_h + (size_t)k * s->jb));
+    }
+  }
   RC(b200_sync(dev));   // T's buffers are in use until here
   s->stage = 3;
   return 0;
@@ -462,6 +505,13 @@ int32_t b200_plonk_linearise(b200_plonk_session_t s, const void* zeta_, void* ou
     RC(axpy(pk, lin, fr->neg(hc), h + (size_t)k * (n + 2) * fb, n + 2));
     hc = M(hc, zn2);
   }
+  if (s->szk) {
+    // the randomised shards differ from the plain ones by (b1 + b2 zeta^(n+2)) (X^(n+2) - zeta^(n+2)) in
+    // h1 + zeta^(n+2) h2 + zeta^(2(n+2)) h3   (prove.go:1466-1481: coefficient n + 2 exists in h1, h2 only)
+    const HostFr d = M(zh, A(fr->load(s->hr[0]), M(fr->load(s->hr[1]), zn2)));
+    RC(add_to_element(pk, lin, n + 2, fr->neg(d)));
+    RC(add_to_element(pk, lin, 0, M(d, zn2)));
+  }
   RC(commit(pk, lin, n + 3, out_points));
   // claimed values of the batch opening (BatchedProof.ClaimedValues) - needed by the caller to derive v
   const void* open_p[6] = {lin, s->bl[0], s->bl[1], s->bl[2], pk->canon[S1], pk->canon[S2]};
@@ -472,7 +522,7 @@ int32_t b200_plonk_linearise(b200_plonk_session_t s, const void* zeta_, void* ou
     fr->store(vals + (size_t)k * fb, e);
   }
   // Z-shifted opening: (Z(X) - Z(w zeta)) / (X - w zeta)
-  uint8_t zb[8 * HOSTFR_MAX_LIMBS], rem[8 * HOSTFR_MAX_LIMBS];
+  alignas(16) uint8_t zb[8 * HOSTFR_MAX_LIMBS], rem[8 * HOSTFR_MAX_LIMBS];
   Scratch T(dev);
   void* zq;
   RC(T.alloc((n + 3) * fb, &zq));
@@ -513,7 +563,7 @@ int32_t b200_plonk_batch_open(b200_plonk_session_t s, const void* v_, void* out_
     RC(axpy(pk, fold, vp, pk->qcp_canon[j], n));
     vp = fr->mul(vp, v);
   }
-  uint8_t rem[8 * HOSTFR_MAX_LIMBS];
+  alignas(16) uint8_t rem[8 * HOSTFR_MAX_LIMBS];
   RC(b200_poly_div_by_linear(dev, curve, fold, n + 3, s->zeta, rem));
   RC(commit(pk, fold, n + 2, out_point));
   RC(b200_sync(dev));
@@ -540,6 +590,7 @@ int32_t b200_plonk_prove(b200_plonk_pk_t pk, const void* l, const void* r, const
   clk::time_point t0 = clk::now();
   int32_t rc = b200_plonk_begin(pk, l, r, o, ch->bl, ch->br, ch->bo, ch->pi2, ch->out_bsb22, &s, pts);
   if (!rc && ch->qk) rc = b200_plonk_set_qk(s, ch->qk);
+  if (!rc && ch->hr) rc = b200_plonk_set_quotient_randomizers(s, ch->hr);
   if (!rc) rc = b200_sync(pk->dev);
   st_ms[0] = ms_since(t0); t0 = clk::now();
   if (!rc) rc = b200_plonk_commit_z(s, ch->beta, ch->gamma, ch->bz, pts + 3 * jb);

@@ -38,7 +38,7 @@ EXPORTS = [
     "b200_plonk_quotient", "b200_plonk_linearise", "b200_plonk_batch_open", "b200_plonk_end", "b200_plonk_bsb22_coset",
     "b200_comm_unique_id", "b200_comm_init", "b200_comm_init_all", "b200_comm_destroy", "b200_comm_info",
     "b200_points_allreduce", "b200_msm_allreduce", "b200_msm_submit_dev", "b200_plonk_last_stage_ms", "b200_points_fold",
-    "b200_plonk_set_qk", "b200_table_upload_encoded", "b200_msm_gather", "b200_pedersen_key_load", "b200_pedersen_key_free", "b200_pedersen_commit", "b200_pedersen_fold",
+    "b200_plonk_set_qk", "b200_plonk_set_quotient_randomizers", "b200_table_upload_encoded", "b200_msm_gather", "b200_pedersen_key_load", "b200_pedersen_key_free", "b200_pedersen_commit", "b200_pedersen_fold",
 ]
 COMM_ID_BYTES = 128
 
@@ -55,7 +55,8 @@ class PlonkPkDesc(ctypes.Structure):
 
 class PlonkChallenges(ctypes.Structure):
     _fields_ = ([(k, ctypes.c_void_p) for k in ("gamma", "beta", "alpha", "zeta", "v", "bl", "br", "bo", "bz")]
-                + [("pi2", ctypes.POINTER(ctypes.c_void_p)), ("out_bsb22", ctypes.c_void_p), ("qk", ctypes.c_void_p)])
+                + [("pi2", ctypes.POINTER(ctypes.c_void_p)), ("out_bsb22", ctypes.c_void_p), ("qk", ctypes.c_void_p),
+                   ("hr", ctypes.c_void_p)])
 
 
 class Groth16PkDesc(ctypes.Structure):
@@ -158,6 +159,8 @@ def load(path: str = None):
         lib.b200_table_upload_encoded.argtypes = [i32, i32, i32, vp, sz, i32, i32, ctypes.POINTER(vp)]
     if "b200_plonk_set_qk" not in missing:
         lib.b200_plonk_set_qk.argtypes = [vp, vp]
+    if "b200_plonk_set_quotient_randomizers" not in missing:
+        lib.b200_plonk_set_quotient_randomizers.argtypes = [vp, vp]
     if "b200_points_fold" not in missing:
         lib.b200_points_fold.argtypes = [i32, i32, i32, vp, u32, u32, vp]
     if "b200_plonk_last_stage_ms" not in missing:
@@ -504,9 +507,9 @@ class PlonkKey:
         check(load().b200_plonk_pk_load(dev, curve, ctypes.byref(d), ctypes.byref(h)))
         self.handle = h
 
-    def prove(self, l, r, o, gamma, beta, alpha, zeta, v, bl, br, bo, bz, pi2=(), qk=None):
+    def prove(self, l, r, o, gamma, beta, alpha, zeta, v, bl, br, bo, bz, pi2=(), qk=None, hr=None):
         """all scalars: uint64 limb arrays (Montgomery); bl/br/bo: (2, limbs), bz: (3, limbs); pi2: one committed
-        polynomial per BSB22 gate of the key.  Returns (points (10, 3*fp_limbs) Jacobian, values (7 + n_qcp,
+        polynomial per BSB22 gate of the key; hr: (2, limbs) quotient-shard randomisers = StatisticalZK.  Returns (points (10, 3*fp_limbs) Jacobian, values (7 + n_qcp,
         fr_limbs)[, bsb22 digests (n_qcp, 3*fp_limbs)])."""
         args = [np.ascontiguousarray(a, dtype=np.uint64) for a in (l, r, o, gamma, beta, alpha, zeta, v, bl, br, bo, bz)]
         ch = PlonkChallenges()
@@ -515,6 +518,9 @@ class PlonkKey:
         if qk is not None:       # this proof's complete Qk (public inputs folded in), Lagrange / regular
             qk = np.ascontiguousarray(qk, dtype=np.uint64)
             ch.qk = ptr(qk).value
+        if hr is not None:
+            hr = np.ascontiguousarray(hr, dtype=np.uint64)
+            ch.hr = ptr(hr).value
         pts = np.zeros((10, 3 * self.fp_limbs), dtype=np.uint64)
         vals = np.zeros((7 + self.n_qcp, self.fr_limbs), dtype=np.uint64)
         pk_ = [np.ascontiguousarray(a, dtype=np.uint64) for a in pi2]

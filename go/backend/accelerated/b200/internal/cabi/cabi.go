@@ -262,6 +262,12 @@ func (s *PlonkSession) SetQk(qk unsafe.Pointer) error {
 	return Call(func() int32 { return int32(C.b200_plonk_set_qk(s.h, qk)) })
 }
 
+// SetQuotientRandomizers is b200_plonk_set_quotient_randomizers: StatisticalZK, the two quotientShardsRandomizers of
+// newInstance (prove.go:239-242), 2 fr.Elements; to be called before Quotient.
+func (s *PlonkSession) SetQuotientRandomizers(hr unsafe.Pointer) error {
+	return Call(func() int32 { return int32(C.b200_plonk_set_quotient_randomizers(s.h, hr)) })
+}
+
 // CommitZ is b200_plonk_commit_z (buildRatioCopyConstraint, prove.go:635-668).
 func (s *PlonkSession) CommitZ(beta, gamma, bz, outZ unsafe.Pointer) error {
 	return Call(func() int32 { return int32(C.b200_plonk_commit_z(s.h, beta, gamma, bz, outZ)) })

@@ -168,9 +168,6 @@ func Prove(spr *cs.SparseR1CS, pk *ProvingKey, fullWitness witness.Witness, cfg 
 	if err != nil {
 		return nil, fmt.Errorf("get prover options: %w", err)
 	}
-	if opt.StatisticalZK {
-		return nil, errors.New("b200 plonk: StatisticalZK is not supported")
-	}
 	if opt.HashToFieldFn == nil {
 		opt.HashToFieldFn = hash_to_field.New([]byte("BSB22-Plonk"))
 	}
@@ -314,6 +311,16 @@ func Prove(spr *cs.SparseR1CS, pk *ProvingKey, fullWitness witness.Witness, cfg 
 	}
 	if err := sess.SetQk(ptrOf(qk)); err != nil {
 		return nil, err
+	}
+	if opt.StatisticalZK { // quotientShardsRandomizers (newInstance, prove.go:239-242; h1(), h2(), h3() :689-722)
+		hr, err := randomCoefficients(1)
+		if err != nil {
+			return nil, err
+		}
+		pinner.Pin(unsafe.SliceData(hr))
+		if err := sess.SetQuotientRandomizers(ptrOf(hr)); err != nil {
+			return nil, err
+		}
 	}
 
 	// gamma, beta (deriveGammaAndBeta, prove.go:492-523)

@@ -292,8 +292,8 @@ int32_t b200_poly_div_by_linear(int32_t dev, int32_t curve, void* d_coeffs, size
  *      Challenges and blinding coefficients are INPUTS: the Go shim derives gamma, beta, alpha, zeta, v from its
  *      Fiat-Shamir transcript exactly as prove.go:492-555 and samples the blinding polynomials (:1211-1220);
  *      passing them in also makes every intermediate result reproducible.  BSB22 commitment gates are supported
- *      (n_qcp / qcp in the key, the committed polynomials in b200_plonk_challenges.pi2 / b200_plonk_begin);
- *      StatisticalZK is not.  Domains below 2^3 are refused (the CPU prover switches to an 8n quotient domain there,
+ *      (n_qcp / qcp in the key, the committed polynomials in b200_plonk_challenges.pi2 / b200_plonk_begin), and so is
+ *      StatisticalZK (b200_plonk_challenges.hr / b200_plonk_set_quotient_randomizers).  Domains below 2^3 are refused (the CPU prover switches to an 8n quotient domain there,
  *      prove.go:248).  All scalars are fr.Elements (Montgomery) on the host. */
 typedef struct b200_plonk_pk_s* b200_plonk_pk_t;
 typedef struct {
@@ -315,6 +315,11 @@ typedef struct {
   /* this proof's complete Qk (completeQk, prove.go:349-373: public inputs and BSB22 commitment values folded into the
    * trace's Qk), n fr.Elements, Lagrange/regular; NULL = the Qk the key was loaded with */
   const void* qk;
+  /* StatisticalZK (backend.WithStatisticalZeroKnowledge, backend/backend.go:141-147): the two
+   * quotientShardsRandomizers of newInstance (prove.go:239-242), 2 fr.Elements; NULL = off.  [H1], [H2], [H3] become the
+   * commitments of h1 + b1 X^(n+2), h2 - b1 + b2 X^(n+2), h3 - b2 (prove.go:689-722) and the linearised polynomial
+   * follows (prove.go:1466-1481); the verifier is unchanged. */
+  const void* hr;
 } b200_plonk_challenges;
 int32_t b200_plonk_pk_load(int32_t dev, int32_t curve, const b200_plonk_pk_desc* desc, b200_plonk_pk_t* out);
 int32_t b200_plonk_pk_free(b200_plonk_pk_t pk);
@@ -348,6 +353,8 @@ int32_t b200_plonk_begin(b200_plonk_pk_t pk, const void* l, const void* r, const
                          void* out_bsb22 /* n_qcp G1Jac or NULL */, b200_plonk_session_t* out, void* out_lro);
 /* optional, between begin and quotient: this proof's complete Qk (see b200_plonk_challenges.qk) */
 int32_t b200_plonk_set_qk(b200_plonk_session_t s, const void* qk_lagrange);
+/* optional, between begin and quotient: StatisticalZK, the two quotientShardsRandomizers (see b200_plonk_challenges.hr) */
+int32_t b200_plonk_set_quotient_randomizers(b200_plonk_session_t s, const void* hr /*2*/);
 int32_t b200_plonk_commit_z(b200_plonk_session_t s, const void* beta, const void* gamma, const void* bz /*3*/,
                             void* out_z);
 int32_t b200_plonk_quotient(b200_plonk_session_t s, const void* alpha, void* out_h);

@@ -53,6 +53,10 @@ class Challenges:
     br: List[int] = field(default_factory=lambda: [0, 0])
     bo: List[int] = field(default_factory=lambda: [0, 0])
     bz: List[int] = field(default_factory=lambda: [0, 0, 0])
+    # StatisticalZK (backend.WithStatisticalZeroKnowledge, prove.go:239-242): the two quotientShardsRandomizers, or
+    # None.  h1 += b1 X^(n+2);  h2 += -b1 + b2 X^(n+2);  h3 += -b2   (prove.go:689-722) - the quotient itself,
+    # h1 + X^(n+2) h2 + X^(2(n+2)) h3, does not change, its three commitments and the linearised polynomial do.
+    hr: List[int] = None
 
 
 @dataclass
@@ -115,6 +119,11 @@ def prove(curve, circ: Circuit, l, rr, o, ch: Challenges, tau: int, pi2=()) -> P
     h = plonk.divide_by_zh(curve, n, 4, cres)
     assert all(x == 0 for x in h[3 * (n + 2):]), "numerator not divisible by X^n - 1: unsatisfied trace"
     h1, h2, h3 = h[:n + 2], h[n + 2:2 * (n + 2)], h[2 * (n + 2):3 * (n + 2)]
+    if ch.hr is not None:                   # h1(), h2(), h3() with StatisticalZK, prove.go:689-722
+        b1, b2 = ch.hr
+        h1 = h1 + [b1 % r]
+        h2 = [(h2[0] - b1) % r] + h2[1:] + [b2 % r]
+        h3 = [(h3[0] - b2) % r] + h3[1:]
     # --- openings at zeta
     zeta = ch.zeta
     zu = ev(zb, zeta * w % r)
@@ -144,8 +153,10 @@ def prove(curve, circ: Circuit, l, rr, o, ch: Challenges, tau: int, pi2=()) -> P
             for j in range(len(cqcp)):              # + sum_j Qcp_j(zeta) PI2_j(X)   (:1457-1460)
                 t = (t + cpi2[j][i] * qcpz[j]) % r
         t = (t + zb[i] * a2l1) % r
-        if i < n + 2:
+        if i < len(h3):
             t = (t - zh * ((h3[i] * zn2 + h2[i]) % r * zn2 % r + h1[i])) % r
+        elif ch.hr is not None:             # prove.go:1476-1481: h1, h2 are one coefficient longer than h3
+            t = (t - zh * ((h2[i] * zn2 + h1[i]) % r)) % r
         lin.append(t)
     # batchOpening :796-837
     to_open = [lin, lb, rb, ob, cs1, cs2] + cqcp

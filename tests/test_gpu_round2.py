@@ -377,3 +377,54 @@ def test_groth16_full_size_proof_verifies(gpu, cname, logn):
     assert gf.verify_points(inst, ec.unpack_points(c, 1, proof.Ar)[0], ec.unpack_points(c, 2, proof.Bs)[0],
                             ec.unpack_points(c, 1, proof.Krs)[0], e, with_pairing=True)
     pk.free_gpu_resources()
+
+
+@pytest.mark.parametrize("cname,logn", [("bn254", 6), ("bls12-381", 4), ("bn254", 12)])
+def test_plonk_prove_statistical_zk(gpu, cname, logn):
+    """backend.WithStatisticalZeroKnowledge through b200_plonk_prove (b200_plonk_challenges.hr: the two
+    quotientShardsRandomizers, prove.go:239-242,689-722,1476-1481): at small sizes all ten digests and the opened values
+    against the big-int oracle prover with the same randomisers, and Verify with real pairings; at 2^12 (no big-int
+    prover) the verifier's equations of oracle/plonk_fast.py, plus: the randomisers change [H1..3] and the linearised
+    digest and nothing else."""
+    from oracle import corelib, plonk_prover as pp
+    c = CURVES[cname]
+    r, L = c.r, c.fr_limbs
+    pe = lambda v: ff.pack_elements(v, r, L)
+    rng = random.Random(7000 + logn)
+    rnd = lambda: rng.randrange(r)
+    if logn <= 8:
+        n = 1 << logn
+        circ, l, rr, o = pp.random_satisfied_instance(c, n, seed=logn + 60)
+        ch = pp.Challenges(gamma=rnd(), beta=rnd(), alpha=rnd(), zeta=rnd(), v=rnd(), bl=[rnd(), rnd()], br=[rnd(), rnd()],
+                           bo=[rnd(), rnd()], bz=[rnd(), rnd(), rnd()], hr=[rnd(), rnd()])
+        tau = rnd()
+        want = pp.prove(c, circ, l, rr, o, ch, tau)
+        assert pp.verify(c, circ, want, ch, tau)
+        srs = corelib.fixed_base(c, 1, ec.pack_points(c, 1, [c.g1]), pe([pow(tau, i, r) for i in range(n + 3)]))
+        key = gpu.PlonkKey(c.curve_id, logn, pe(circ.ql), pe(circ.qr), pe(circ.qm), pe(circ.qo), pe(circ.qk),
+                           np.array(circ.perm, dtype=np.int64), srs)
+        pts, vals = key.prove(pe(l), pe(rr), pe(o), pe([ch.gamma]), pe([ch.beta]), pe([ch.alpha]), pe([ch.zeta]), pe([ch.v]),
+                              pe(ch.bl), pe(ch.br), pe(ch.bo), pe(ch.bz), hr=pe(ch.hr))
+        F = ff.Fp(c.p)
+        dl = [want.L, want.R, want.O, want.Z, want.H[0], want.H[1], want.H[2], want.lin, want.batch_opening, want.z_opening]
+        for k, name in enumerate(("L", "R", "O", "Z", "H1", "H2", "H3", "lin", "batch", "zopen")):
+            assert jac_to_affine(c, 1, pts[k]) == ec.scalar_mul(F, dl[k], c.g1), name
+        got_vals = ff.unpack_elements(vals, r, L)
+        assert got_vals[:6] == want.claimed and got_vals[6] == want.zu
+        assert pp.verify_pairing(c, circ, [jac_to_affine(c, 1, pts[k]) for k in range(10)], got_vals, ch, tau)
+        key.free()
+        return
+    from oracle import plonk_fast
+    inst = plonk_fast.satisfied_instance(c, logn, seed=logn)
+    srs = plonk_fast.trapdoor_srs_gpu(gpu, c, inst)
+    key = gpu.PlonkKey(c.curve_id, logn, inst.ql, inst.qr, inst.qm, inst.qo, inst.qk, inst.perm, srs)
+    chp = inst.challenges_packed()
+    plain_pts, plain_vals = key.prove(inst.l, inst.r, inst.o, *chp)
+    pts, vals = key.prove(inst.l, inst.r, inst.o, *chp, hr=pe([rnd(), rnd()]))
+    key.free()
+    assert plonk_fast.verify(c, inst, plain_pts, plain_vals) and plonk_fast.verify(c, inst, pts, vals)
+    assert np.array_equal(vals, plain_vals)
+    same = [jac_to_affine(c, 1, pts[k]) == jac_to_affine(c, 1, plain_pts[k]) for k in range(10)]
+    # L R O Z unchanged; H1 H2 H3 and the linearised digest differ; the batch opening differs (it folds the linearised
+    # polynomial); the Z opening is unchanged
+    assert same == [True, True, True, True, False, False, False, False, False, True]

@@ -16,7 +16,7 @@ from oracle import corelib, ec, ff, plonk_prover as pp
 from oracle.params import CURVES
 from util import jac_to_affine
 
-LIB = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_build", "libgb200_plonkmock.so")
+LIB = os.environ.get("GB200_PLONKMOCK") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "_build", "libgb200_plonkmock.so")
 
 
 @pytest.fixture(scope="module")
@@ -359,3 +359,71 @@ def test_concurrent_callers_are_serialised_per_device(mock):
         assert g[0] == 0 and np.array_equal(g[1], w[1]) and np.array_equal(g[2], w[2])
     for i in insts:
         assert mock.b200_plonk_pk_free(i["h"]) == 0
+
+
+@pytest.mark.parametrize("cname,logn", [("bn254", 4), ("bls12-381", 3)])
+def test_plonk_host_statistical_zk(mock, cname, logn):
+    """backend.WithStatisticalZeroKnowledge (prove.go:239-242,689-722,1476-1481): with the two quotient-shard
+    randomisers injected, [H1], [H2], [H3] and the linearised digest change as the oracle's do, the opened values do not,
+    and the proof verifies (the verifier is the same) - one call and round by round."""
+    c = CURVES[cname]
+    rng = random.Random(4100 + logn)
+    r, L = c.r, c.fr_limbs
+    n = 1 << logn
+    circ, l, rr, o = pp.random_satisfied_instance(c, n, seed=logn + 11)
+    rnd = lambda: rng.randrange(r)
+    base = dict(gamma=rnd(), beta=rnd(), alpha=rnd(), zeta=rnd(), v=rnd(), bl=[rnd(), rnd()], br=[rnd(), rnd()],
+                bo=[rnd(), rnd()], bz=[rnd(), rnd(), rnd()])
+    ch = pp.Challenges(**base, hr=[rnd(), rnd()])
+    tau = rnd()
+    want = pp.prove(c, circ, l, rr, o, ch, tau)
+    plain = pp.prove(c, circ, l, rr, o, pp.Challenges(**base), tau)
+    assert pp.verify(c, circ, want, ch, tau) and want.H != plain.H and want.lin != plain.lin
+    pe = lambda v: np.ascontiguousarray(ff.pack_elements(v, r, L))
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    srs = np.ascontiguousarray(corelib.fixed_base(c, 1, ec.pack_points(c, 1, [c.g1]), pe([pow(tau, i, r) for i in range(n + 3)])))
+    keep = {k: pe(getattr(circ, k)) for k in ("ql", "qr", "qm", "qo", "qk")}
+    perm = np.ascontiguousarray(np.array(circ.perm, dtype=np.int64))
+    d = b200.PlonkPkDesc()
+    d.log2n = logn
+    for k, a in keep.items():
+        setattr(d, k, P(a).value)
+    d.perm, d.srs_canonical = P(perm).value, P(srs).value
+    h = ctypes.c_void_p(0)
+    assert mock.b200_plonk_pk_load(0, c.curve_id, ctypes.byref(d), ctypes.byref(h)) == 0, mock.b200_last_error()
+    sc = {k: pe(v) for k, v in (("gamma", [ch.gamma]), ("beta", [ch.beta]), ("alpha", [ch.alpha]), ("zeta", [ch.zeta]),
+                                ("v", [ch.v]), ("bl", ch.bl), ("br", ch.br), ("bo", ch.bo), ("bz", ch.bz), ("hr", ch.hr))}
+    cs = b200.PlonkChallenges()
+    for k, a in sc.items():
+        setattr(cs, k, P(a).value)
+    pts = np.zeros((10, 3 * c.fp_limbs), dtype=np.uint64)
+    vals = np.zeros((7, L), dtype=np.uint64)
+    L_, R_, O_ = pe(l), pe(rr), pe(o)
+    assert mock.b200_plonk_prove(h, P(L_), P(R_), P(O_), ctypes.byref(cs), P(pts), P(vals)) == 0, mock.b200_last_error()
+    F = ff.Fp(c.p)
+    dl = [want.L, want.R, want.O, want.Z, want.H[0], want.H[1], want.H[2], want.lin, want.batch_opening, want.z_opening]
+    for k, name in enumerate(("L", "R", "O", "Z", "H1", "H2", "H3", "lin", "batch", "zopen")):
+        assert jac_to_affine(c, 1, pts[k]) == ec.scalar_mul(F, dl[k], c.g1), name
+    got = ff.unpack_elements(vals, r, L)
+    assert got[:6] == want.claimed == plain.claimed and got[6] == want.zu
+    proof_pts = [jac_to_affine(c, 1, pts[k]) for k in range(10)]
+    assert pp.verify_pairing(c, circ, proof_pts, got, ch, tau)
+    # round by round; the randomisers are refused before begin and after the quotient
+    mock.b200_plonk_set_quotient_randomizers.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    jl = 3 * c.fp_limbs
+    s_ = ctypes.c_void_p(0)
+    lro, zpt, hpts = np.zeros((3, jl), dtype=np.uint64), np.zeros(jl, dtype=np.uint64), np.zeros((3, jl), dtype=np.uint64)
+    two, vals2, bpt = np.zeros((2, jl), dtype=np.uint64), np.zeros((7, L), dtype=np.uint64), np.zeros(jl, dtype=np.uint64)
+    assert mock.b200_plonk_set_quotient_randomizers(s_, P(sc["hr"])) != 0
+    assert mock.b200_plonk_begin(h, P(L_), P(R_), P(O_), P(sc["bl"]), P(sc["br"]), P(sc["bo"]), None, None,
+                                 ctypes.byref(s_), P(lro)) == 0
+    assert mock.b200_plonk_commit_z(s_, P(sc["beta"]), P(sc["gamma"]), P(sc["bz"]), P(zpt)) == 0
+    assert mock.b200_plonk_set_quotient_randomizers(s_, P(sc["hr"])) == 0
+    assert mock.b200_plonk_quotient(s_, P(sc["alpha"]), P(hpts)) == 0
+    assert mock.b200_plonk_set_quotient_randomizers(s_, P(sc["hr"])) != 0 and b"before plonk_quotient" in mock.b200_last_error()
+    assert mock.b200_plonk_linearise(s_, P(sc["zeta"]), P(two), P(vals2)) == 0
+    assert mock.b200_plonk_batch_open(s_, P(sc["v"]), P(bpt)) == 0
+    assert mock.b200_plonk_end(s_) == 0
+    assert np.array_equal(np.concatenate([lro, zpt[None], hpts, two[0:1], bpt[None], two[1:2]]), pts)
+    assert np.array_equal(vals2, vals)
+    assert mock.b200_plonk_pk_free(h) == 0
