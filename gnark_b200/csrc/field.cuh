@@ -108,6 +108,11 @@ HD void wide_mul_raw(uint32_t* t, const uint32_t* a, const uint32_t* b) {
 }
 
 // r = T * R^-1 mod p for a 2N-limb T < p * R; output < p.  The m*p rows of mont_mul_raw on their own.
+// Only the LOW half of T goes through the accumulators: T / R = T_hi + (T_lo + sum_i m_i p 2^(32 i)) / R, and T_hi is
+// added after the rows.  mad_chain adds the carry out of a chain to the next word WITHOUT propagating further, which
+// is sound only if that word holds nothing but earlier carries; with all of T preloaded (round 2's first version) the
+// word was T[i + N] and a carry was lost whenever it was 0xffffffff - once in ~2^33 reductions, found by the verified
+// 2^20 Groth16 proof (one G2 table point in 10^6; regression vectors in tests/test_emulation.py).
 template <class P>
 HD void mont_reduce_wide(uint32_t* r, const uint32_t* T) {
   constexpr int N = P::N;
@@ -116,7 +121,7 @@ HD void mont_reduce_wide(uint32_t* r, const uint32_t* T) {
 #pragma unroll
   for (int k = 0; k < N; k++) p[k] = P::mod(k);
 #pragma unroll
-  for (int k = 0; k < 2 * N + 3; k++) { acc[0][k] = k < 2 * N ? T[k] : 0; acc[1][k] = 0; }
+  for (int k = 0; k < 2 * N + 3; k++) { acc[0][k] = k < N ? T[k] : 0; acc[1][k] = 0; }
 #pragma unroll
   for (int i = 0; i < N; i++) {
     uint32_t* X = acc[i & 1];
@@ -131,10 +136,16 @@ HD void mont_reduce_wide(uint32_t* r, const uint32_t* T) {
     }
     mad_chain<N, 0, false>(X, i, p, m);           // X[i] becomes 0
   }
+  // (T_lo + sum m_i p 2^(32 i)) / R <= p, then + T_hi < p: the sum stays below 2p + 1 < 2^(32 N), no carry out
   uint32_t s[N];
   s[0] = ptx::add_cc(acc[0][N], acc[1][N]);
 #pragma unroll
   for (int k = 1; k < N; k++) s[k] = ptx::addc_cc(acc[0][N + k], acc[1][N + k]);
+  (void)ptx::addc(0, 0);
+  s[0] = ptx::add_cc(s[0], T[N]);
+#pragma unroll
+  for (int k = 1; k < N; k++) s[k] = ptx::addc_cc(s[k], T[N + k]);
+  (void)ptx::addc(0, 0);
   uint32_t d[N];
   d[0] = ptx::sub_cc(s[0], p[0]);
 #pragma unroll

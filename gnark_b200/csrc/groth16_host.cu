@@ -8,6 +8,7 @@
 #include "capi_common.h"
 
 #include <chrono>
+#include <future>
 #include <cstdio>
 
 using namespace gb200;
@@ -325,21 +326,33 @@ int32_t b200_groth16_msms(b200_pk_t pk, const void* wires, const void* a, const 
   GUARD_END
 }
 
-int32_t b200_groth16_assemble(b200_pk_t pk, const void* msm5, const void* r, const void* s, void* ar_out,
-                              void* bs_out, void* krs_out) {
-  GUARD_BEGIN
-  if (!pk || !msm5 || !r || !s || !ar_out || !bs_out || !krs_out) return set_error("assemble: null argument");
+}  // extern "C"
+
+namespace {
+// deltas = [r, s, -rs] * delta in G1 and s * delta in G2 (prove.go:185): four scalar multiplications on the host that
+// need nothing from the device, so b200_groth16_prove computes them on a second host thread while the MSMs run
+struct Groth16Deltas {
+  std::vector<uint8_t> rd, sd, krd, sd2;
+};
+Groth16Deltas groth16_deltas(b200_pk_t pk, const void* r, const void* s) {
   const HostGroupOps* h1 = pk->h1;
   const HostGroupOps* h2 = pk->h2;
-  const size_t fb = pk->fr->fr_bytes;
   const size_t j1 = h1->jac_bytes, j2 = h2->jac_bytes;
-  // deltas = [r, s, -rs] * delta (prove.go:185)
-  std::vector<uint8_t> kr(fb), rd(j1), sd(j1), krd(j1), sd2(j2);
+  Groth16Deltas d{std::vector<uint8_t>(j1), std::vector<uint8_t>(j1), std::vector<uint8_t>(j1), std::vector<uint8_t>(j2)};
+  std::vector<uint8_t> kr(pk->fr->fr_bytes);
   h1->fr_neg_mul(r, s, kr.data());
-  h1->scalar_mul_affine(pk->delta.data(), r, rd.data());
-  h1->scalar_mul_affine(pk->delta.data(), s, sd.data());
-  h1->scalar_mul_affine(pk->delta.data(), kr.data(), krd.data());
-  h2->scalar_mul_affine(pk->delta2.data(), s, sd2.data());
+  h1->scalar_mul_affine(pk->delta.data(), r, d.rd.data());
+  h1->scalar_mul_affine(pk->delta.data(), s, d.sd.data());
+  h1->scalar_mul_affine(pk->delta.data(), kr.data(), d.krd.data());
+  h2->scalar_mul_affine(pk->delta2.data(), s, d.sd2.data());
+  return d;
+}
+
+void groth16_assemble_with(b200_pk_t pk, const void* msm5, const void* r, const void* s, const Groth16Deltas& d,
+                           void* ar_out, void* bs_out, void* krs_out) {
+  const HostGroupOps* h1 = pk->h1;
+  const HostGroupOps* h2 = pk->h2;
+  const size_t j1 = h1->jac_bytes, j2 = h2->jac_bytes;
   const uint8_t* m = reinterpret_cast<const uint8_t*>(msm5);
   const uint8_t* mA = m;
   const uint8_t* mB1 = m + j1;
@@ -349,14 +362,14 @@ int32_t b200_groth16_assemble(b200_pk_t pk, const void* msm5, const void* r, con
   // ar = A + alpha + r*delta (prove.go:207-214)
   std::vector<uint8_t> ar(mA, mA + j1);
   h1->add_mixed(ar.data(), pk->alpha.data());
-  h1->add_jac(ar.data(), rd.data());
+  h1->add_jac(ar.data(), d.rd.data());
   // bs1 = B + beta + s*delta (prove.go:194-200)
   std::vector<uint8_t> bs1(mB1, mB1 + j1);
   h1->add_mixed(bs1.data(), pk->beta.data());
-  h1->add_jac(bs1.data(), sd.data());
+  h1->add_jac(bs1.data(), d.sd.data());
   // krs = K + Z.h + (-rs)*delta + s*ar + r*bs1 (prove.go:227-269)
   std::vector<uint8_t> krs(mK, mK + j1), tmp(j1);
-  h1->add_jac(krs.data(), krd.data());
+  h1->add_jac(krs.data(), d.krd.data());
   h1->add_jac(krs.data(), mZ);
   h1->scalar_mul_jac(ar.data(), s, tmp.data());
   h1->add_jac(krs.data(), tmp.data());
@@ -364,11 +377,21 @@ int32_t b200_groth16_assemble(b200_pk_t pk, const void* msm5, const void* r, con
   h1->add_jac(krs.data(), tmp.data());
   // bs2 = B2 + s*delta2 + beta2 (prove.go:283-292)
   std::vector<uint8_t> bs2(mB2, mB2 + j2);
-  h2->add_jac(bs2.data(), sd2.data());
+  h2->add_jac(bs2.data(), d.sd2.data());
   h2->add_mixed(bs2.data(), pk->beta2.data());
   h1->to_affine(ar.data(), ar_out);
   h1->to_affine(krs.data(), krs_out);
   h2->to_affine(bs2.data(), bs_out);
+}
+}  // namespace
+
+extern "C" {
+
+int32_t b200_groth16_assemble(b200_pk_t pk, const void* msm5, const void* r, const void* s, void* ar_out,
+                              void* bs_out, void* krs_out) {
+  GUARD_BEGIN
+  if (!pk || !msm5 || !r || !s || !ar_out || !bs_out || !krs_out) return set_error("assemble: null argument");
+  groth16_assemble_with(pk, msm5, r, s, groth16_deltas(pk, r, s), ar_out, bs_out, krs_out);
   return 0;
   GUARD_END
 }
@@ -388,13 +411,16 @@ int32_t b200_groth16_prove(b200_pk_t pk, const void* wires, const void* a, const
   if (!r || !s || !ar_out || !bs_out || !krs_out) return set_error("prove: null argument");
   std::vector<uint8_t> msm(4 * pk->h1->jac_bytes + pk->h2->jac_bytes);
   const double t0 = now_ms();
+  // the delta multiples (prove.go:185) on a second host thread, under the device work
+  std::future<Groth16Deltas> deltas = std::async(std::launch::async, [&] { return groth16_deltas(pk, r, s); });
   int32_t rc = b200_groth16_msms(pk, wires, a, b, c, n_constraints, msm.data());
-  if (rc) return rc;
   const double t1 = now_ms();
+  const Groth16Deltas d = deltas.get();      // joined on every path: the lambda reads pk, r, s
+  if (rc) return rc;
   if (msm_out) memcpy(msm_out, msm.data(), msm.size());
-  rc = b200_groth16_assemble(pk, msm.data(), r, s, ar_out, bs_out, krs_out);
+  groth16_assemble_with(pk, msm.data(), r, s, d, ar_out, bs_out, krs_out);
   if (getenv("GB200_STEP_PROFILE")) fprintf(stderr, "[gb200 step] %-14s %8.3f ms (device part %.3f ms)\n", "host assembly", now_ms() - t1, t1 - t0);
-  return rc;
+  return 0;
   GUARD_END
 }
 

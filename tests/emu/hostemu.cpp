@@ -145,6 +145,42 @@ int fixed_base_emu(const void* base_, const void* scalars_, uint32_t n, int c, v
 }
 
 
+// k_msm_precompute_dbl + k_msm_precompute_affine (msm_impl.cuh) for ONE point: the XYZZ doubling chain that is never
+// normalised between slabs, then one inversion for the nwin - 1 slab points (Montgomery's trick); out: nwin affine points
+template <class F>
+int precompute_emu(const void* point_, int nwin, int c, void* out_) {
+  const Affine<F> src = *reinterpret_cast<const Affine<F>*>(point_);
+  Affine<F>* out = reinterpret_cast<Affine<F>*>(out_);
+  std::vector<XYZZ<F>> tmp(nwin > 1 ? nwin - 1 : 0);
+  XYZZ<F> q = XYZZ<F>::from_affine(src);
+  for (int w = 1; w < nwin; w++) {
+    for (int k = 0; k < c; k++) q.dbl();
+    tmp[w - 1] = q;
+  }
+  out[0] = src;
+  std::vector<F> pre(nwin + 1);
+  F acc = F::one();
+  for (int w = 1; w < nwin; w++) {
+    pre[w] = acc;
+    const F zzz = tmp[w - 1].zzz;
+    if (!zzz.is_zero()) acc = acc * zzz;
+  }
+  F inv = acc.inverse();
+  for (int w = nwin - 1; w >= 1; w--) {
+    const XYZZ<F> t = tmp[w - 1];
+    Affine<F> a = Affine<F>::inf();
+    if (!t.zzz.is_zero()) {
+      const F zi3 = inv * pre[w];
+      inv = inv * t.zzz;
+      const F zi2 = (zi3 * t.zz).sqr();
+      a.x = t.x * zi2;
+      a.y = t.y * zi3;
+    }
+    out[w] = a;
+  }
+  return 0;
+}
+
 // k_plonk_add_bsb22 walked over the n points of one coset (BN254 / BLS12-381 / BW6 Fr by curve id)
 template <class Fr>
 int bsb22_emu(const void* qcp, const void* pi2, void* out, uint32_t logn, uint32_t coset_index, uint32_t rho) {
@@ -202,6 +238,20 @@ int emu_decode_points(int curve, int group, const void* bytes, size_t n, int enc
     case 5: return decode_emu<bls12_377_fp2>(bytes, n, encoding, b_small, out);
     case 6:
     case 7: return decode_emu<bw6_761_fp>(bytes, n, encoding, b_small, out);
+  }
+  return -1;
+}
+
+int emu_precompute(int curve, int group, const void* point, int nwin, int c, void* out_affine) {
+  switch (curve * 2 + (group - 1)) {
+    case 0: return precompute_emu<bn254_fp>(point, nwin, c, out_affine);
+    case 1: return precompute_emu<bn254_fp2>(point, nwin, c, out_affine);
+    case 2: return precompute_emu<bls12_381_fp>(point, nwin, c, out_affine);
+    case 3: return precompute_emu<bls12_381_fp2>(point, nwin, c, out_affine);
+    case 4: return precompute_emu<bls12_377_fp>(point, nwin, c, out_affine);
+    case 5: return precompute_emu<bls12_377_fp2>(point, nwin, c, out_affine);
+    case 6:
+    case 7: return precompute_emu<bw6_761_fp>(point, nwin, c, out_affine);
   }
   return -1;
 }

@@ -3,6 +3,7 @@ host with the PTX carry chains emulated, against the oracle.  This checks the
 kernels' per-thread logic on a box without a GPU; the -m gpu tests check the real
 thing through the C ABI."""
 import ctypes
+import os
 import random
 
 import numpy as np
@@ -67,6 +68,61 @@ def test_wide_arithmetic(hostemu, c):
             O = np.zeros(L, dtype=np.uint64)
             assert hostemu.emu_wide_op(fid, 2, P(arr(t, 2 * L)), P(arr(0, L)), P(O)) == 0
             assert val(O) == t * Rinv % q, (c.name, which, "mont_reduce_wide")
+
+
+@pytest.mark.parametrize("c", ALL, ids=lambda c: c.name)
+def test_mont_reduce_wide_saturated_high_words(hostemu, c):
+    """Directed regression for the carry that round 2's first mont_reduce_wide lost once in ~2^33 reductions (a word of
+    the HIGH half of T equal to 0xffffffff under a chain-end carry, field.cuh): T with saturated 32-bit words in its high
+    half - every position, runs of them, and the all-ones high half that still satisfies T < p R - against big ints."""
+    rng = random.Random(4242)
+    for which, (q, L) in enumerate(((c.p, c.fp_limbs), (c.r, c.fr_limbs))):
+        fid = c.curve_id * 2 + which
+        R = 1 << (64 * L)
+        Rinv = pow(R, -1, q)
+        arr = lambda x, limbs: np.frombuffer(int(x).to_bytes(8 * limbs, "little"), dtype=np.uint64).copy()
+        val = lambda a: int.from_bytes(a.tobytes(), "little")
+        W = 2 * L                     # 32-bit words of one half
+        ts = []
+        for _ in range(40):
+            lo = rng.randrange(R)
+            hi = rng.randrange(q)
+            for k in range(W):        # one saturated word at every position of the high half, then runs
+                t = lo + (((hi | (0xFFFFFFFF << (32 * k))) % R) << (64 * L))
+                if t < q * R:
+                    ts.append(t)
+            for k in range(1, W):
+                t = lo + ((((1 << (32 * k)) - 1) | (hi >> (32 * k) << (32 * k))) << (64 * L))
+                if t < q * R:
+                    ts.append(t)
+        ts.append(q * R - 1)
+        ts.append((R - 1) + (((q - 1) | 0xFFFFFFFF) << (64 * L)) if ((q - 1) | 0xFFFFFFFF) < q else q * R - 1)
+        assert len(ts) > 500
+        for t in ts:
+            O = np.zeros(L, dtype=np.uint64)
+            assert hostemu.emu_wide_op(fid, 2, P(arr(t, 2 * L)), P(arr(0, L)), P(O)) == 0
+            assert val(O) == t * Rinv % q, (c.name, which, hex(t))
+
+
+def test_g2_doubling_chain_known_failure(hostemu):
+    """The BN254 G2 point whose precomputed slabs 11..15 came out wrong on the GPU (found by the verified 2^20 Groth16
+    proof of bench.py: index 116963 of G2.B, seed 20): the device table build - an XYZZ doubling chain that is never
+    normalised, then one inversion per point - emulated on the CPU, every slab against 2^(16 w) P of the big-int oracle;
+    and the 1-point MSM of the scalar it was paired with."""
+    c = CURVES["bn254"]
+    F = ff.base_field(c, 2)
+    here = os.path.dirname(os.path.abspath(__file__))
+    pt = np.load(os.path.join(here, "golden", "bn254_g2_lost_carry_point.npy"))
+    sc = np.load(os.path.join(here, "golden", "bn254_g2_lost_carry_scalar.npy"))
+    Pt = ec.unpack_points(c, 2, pt)[0]
+    out = np.zeros((16, 4 * c.fp_limbs), dtype=np.uint64)
+    assert hostemu.emu_precompute(c.curve_id, 2, P(pt), 16, 16, P(out)) == 0
+    for w in range(16):
+        assert ec.unpack_points(c, 2, out[w])[0] == ec.scalar_mul(F, 1 << (16 * w), Pt), w
+    s = ff.unpack_elements(sc, c.r, c.fr_limbs)[0]
+    res = np.zeros(6 * c.fp_limbs, dtype=np.uint64)
+    assert hostemu.emu_msm(c.curve_id, 2, P(pt), P(sc), 1, 16, 1, 32, 8, P(res)) == 0
+    assert ec.from_jac(F, ec.unpack_points(c, 2, res, ncoords=3)[0]) == ec.scalar_mul(F, s, Pt)
 
 
 @pytest.mark.parametrize("c", ALL, ids=lambda c: c.name)

@@ -345,8 +345,8 @@ def test_table_from_encoded_points_other_curves(gpu, cname):
             gpu.Table.from_encoded(c.curve_id, 2, data, 64, gpu.POINTS_COMPRESSED)
 
 
-@pytest.mark.parametrize("cname,logn", [("bn254", 20), ("bls12-381", 16)])
-def test_groth16_full_size_proof_verifies(gpu, cname, logn):
+@pytest.mark.parametrize("cname,logn,seed", [("bn254", 20, 2020), ("bn254", 20, 20), ("bls12-381", 16, 2020)])
+def test_groth16_full_size_proof_verifies(gpu, cname, logn, seed):
     """BASELINE configs[2] at size: a SATISFIED 2^20 - 1 constraint circuit (oracle/groth16_fast.py; its small sizes are
     checked against the big-int oracle in tests/test_groth16_fast.py), trapdoor key built with b200_fixed_base_batch,
     one b200_groth16_prove with r, s injected.  Checked: each of the five MSM results and the three proof points equal
@@ -355,7 +355,9 @@ def test_groth16_full_size_proof_verifies(gpu, cname, logn):
     from gnark_b200 import groth16 as b200
     from oracle import groth16_fast as gf
     c = CURVES[cname]
-    inst = gf.satisfied_instance(c, logn, seed=2020)
+    # seed 20 at 2^20 is the instance whose G2.B table had one wrong point before the carry fix of mont_reduce_wide
+    # (field.cuh; tests/test_emulation.py::test_g2_doubling_chain_known_failure)
+    inst = gf.satisfied_instance(c, logn, seed=seed)
     assert gf.check_satisfied(inst)
     fb = lambda group, dl: gpu.fixed_base_batch(c.curve_id, group, ec.pack_points(c, group, [c.g1 if group == 1 else c.g2]),
                                                 np.ascontiguousarray(dl))
@@ -428,3 +430,26 @@ def test_plonk_prove_statistical_zk(gpu, cname, logn):
     # L R O Z unchanged; H1 H2 H3 and the linearised digest differ; the batch opening differs (it folds the linearised
     # polynomial); the Z opening is unchanged
     assert same == [True, True, True, True, False, False, False, False, False, True]
+
+
+def test_g2_table_point_known_failure(gpu):
+    """the BN254 G2 point of tests/golden/bn254_g2_lost_carry_point.npy: its precomputed slabs 11..15 were wrong on the
+    GPU before the carry fix of mont_reduce_wide (field.cuh) - every slab (s = 2^(16 w)) and the scalar it was paired
+    with, on a precomputed and on a plain table, alone and behind other points"""
+    import os
+    c = CURVES["bn254"]
+    F = ff.base_field(c, 2)
+    here = os.path.dirname(os.path.abspath(__file__))
+    pt = np.load(os.path.join(here, "golden", "bn254_g2_lost_carry_point.npy"))
+    sc = np.load(os.path.join(here, "golden", "bn254_g2_lost_carry_scalar.npy"))
+    P = ec.unpack_points(c, 2, pt)[0]
+    s = ff.unpack_elements(sc, c.r, c.fr_limbs)[0]
+    pe = lambda v: ff.pack_elements(v, c.r, c.fr_limbs)
+    for pad in (0, 37):
+        tab = np.ascontiguousarray(np.concatenate([ec.pack_points(c, 2, [c.g2] * pad), pt]) if pad else pt)
+        for precomp in (True, False):
+            t = gpu.Table(c.curve_id, 2, tab, precomp=precomp)
+            assert jac_to_affine(c, 2, t.msm(sc, off=pad, n=1)) == ec.scalar_mul(F, s, P), (pad, precomp)
+            for w in range(16):
+                assert jac_to_affine(c, 2, t.msm(pe([1 << (16 * w)]), off=pad, n=1)) == ec.scalar_mul(F, 1 << (16 * w), P), (pad, precomp, w)
+            t.free()
