@@ -9,6 +9,8 @@ import (
 	"testing"
 
 	"github.com/consensys/gnark-crypto/ecc"
+	"github.com/consensys/gnark/backend"
+	"github.com/consensys/gnark/backend/accelerated/b200"
 	b200_plonk "github.com/consensys/gnark/backend/accelerated/b200/plonk"
 	native_plonk "github.com/consensys/gnark/backend/plonk"
 	"github.com/consensys/gnark/frontend"
@@ -75,6 +77,40 @@ func TestProveVerify(t *testing.T) {
 			assert.NoError(err)
 			assert.NoError(b200_plonk.Verify(proofNative, vk, pw))
 			assert.NoError(b200_plonk.Verify(proofAcc, vk, pw))
+		})
+	}
+}
+
+// backend.WithStatisticalZeroKnowledge: the quotient shards are randomised (backend/plonk/bn254/prove.go:239-242,
+// 689-722); the proof must verify with the unchanged verifier, and two proofs of the same witness must differ in H
+func TestProveVerifyStatisticalZK(t *testing.T) {
+	for _, curve := range curves {
+		t.Run(fmt.Sprintf("curve=%s", curve.String()), func(t *testing.T) {
+			assert := test.NewAssert(t)
+			ccs, err := frontend.Compile(curve.ScalarField(), scs.NewBuilder, &circuit{})
+			assert.NoError(err)
+			srs, srsLagrange, err := unsafekzg.NewSRS(ccs)
+			assert.NoError(err)
+			pk, vk, err := b200_plonk.Setup(ccs, srs, srsLagrange)
+			assert.NoError(err)
+			assignment := circuit{X: 3, Y: witnessY(3, curve.ScalarField())}
+			w, err := frontend.NewWitness(&assignment, curve.ScalarField())
+			assert.NoError(err)
+			pw, err := w.Public()
+			assert.NoError(err)
+			szk := b200.WithProverOptions(backend.WithStatisticalZeroKnowledge())
+			proof1, err := b200_plonk.Prove(ccs, pk, w, szk)
+			assert.NoError(err)
+			proof2, err := b200_plonk.Prove(ccs, pk, w, szk)
+			assert.NoError(err)
+			assert.NoError(b200_plonk.Verify(proof1, vk, pw))
+			assert.NoError(b200_plonk.Verify(proof2, vk, pw))
+			var b1, b2 bytes.Buffer
+			_, err = proof1.WriteTo(&b1)
+			assert.NoError(err)
+			_, err = proof2.WriteTo(&b2)
+			assert.NoError(err)
+			assert.False(bytes.Equal(b1.Bytes(), b2.Bytes()))
 		})
 	}
 }

@@ -150,7 +150,35 @@ def case_gather(rs, seed):
     return aff(c, 1, got) == aff(c, 1, want), dict(curve=c.name, n=n, nv=nv)
 
 
-CASES = {"msm": (case_msm, 5), "ntt": (case_ntt, 3), "compute_h": (case_compute_h, 1), "fixed_base": (case_fixed_base, 1),
+def case_known_dlog_big(rs, seed):
+    """rare-event detector: a 2^17..2^20-point MSM over DISTINCT bases k_i * G built on the GPU (b200_fixed_base_batch),
+    checked against (sum s_i k_i) * G - one dot product and one scalar multiplication on the CPU.  One such case runs
+    10^8..10^10 field reductions (table build included), which is what it took to see the lost carry of round 2's first
+    mont_reduce_wide (about 2^-32.5 per reduction)."""
+    import torch
+    c = CURVES[NAMES[int(rs.integers(0, 4))]]
+    group = int(rs.integers(1, 3))
+    logn = int(rs.integers(17, 21))
+    if c.fp_limbs > 6:
+        logn = min(logn, 18)
+    if group == 2 and c.fp_limbs > 4:
+        logn = min(logn, 19)
+    n = (1 << logn) - int(rs.integers(0, 1000))
+    ks, sc = rand_fr(rs, c, n, "uniform"), rand_fr(rs, c, n, ["uniform", "uniform", "skewed"][int(rs.integers(0, 3))])
+    G = base_point(c, group)
+    deg = 1 if group == 1 or c.name == "bw6-761" else 2
+    d_pts = torch.zeros((n, 2 * deg * c.fp_limbs), dtype=torch.int64, device="cuda")
+    lib.fixed_base_batch(c.curve_id, group, ec.pack_points(c, group, [G]), torch.from_numpy(ks.view(np.int64)).cuda(), n=n, out=d_pts)
+    precomp = bool(rs.integers(0, 2))
+    t = lib.Table(c.curve_id, group, d_pts, precomp=precomp, n=n, on_device=True)
+    del d_pts
+    got = aff(c, group, t.msm(sc))
+    t.free()
+    want = ec.scalar_mul(ff.base_field(c, group), corelib.fr_dot(c, ks, sc), G)
+    return got == want, dict(curve=c.name, group=group, n=n, precomp=precomp)
+
+
+CASES = {"msm": (case_msm, 5), "known_dlog_big": (case_known_dlog_big, 0), "ntt": (case_ntt, 3), "compute_h": (case_compute_h, 1), "fixed_base": (case_fixed_base, 1),
          "gather": (case_gather, 1)}
 
 
@@ -159,11 +187,12 @@ def main():
     ap.add_argument("--seconds", type=float, default=120)
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--only", default="")
+    ap.add_argument("--big", type=float, default=0.0, help="weight of the 2^17..2^20 known-discrete-log MSM cases (0 = off)")
     args = ap.parse_args()
     lib.load()
     lib.init([0])
     names = [k for k in CASES if not args.only or k in args.only.split(",")]
-    weights = np.array([CASES[k][1] for k in names], dtype=float)
+    weights = np.array([args.big if k == "known_dlog_big" else CASES[k][1] for k in names], dtype=float)
     weights /= weights.sum()
     top = np.random.Generator(np.random.PCG64(args.seed))
     stats = {k: {"cases": 0, "failures": []} for k in names}
