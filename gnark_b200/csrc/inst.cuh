@@ -184,7 +184,7 @@ struct NttInst {
   }
   static cudaError_t plonk_coset(cudaStream_t st, void* dom0, const void* big_coset_gen, const void* big_gen,
                                  const void* args_) {
-    const Dom& d = *reinterpret_cast<Dom*>(dom0);
+    Dom& d = *reinterpret_cast<Dom*>(dom0);
     const b200_plonk_coset_args& c = *reinterpret_cast<const b200_plonk_coset_args*>(args_);
     PlonkCosetArgs<Fr> a;
     a.l = (const Fr*)c.l; a.r = (const Fr*)c.r; a.o = (const Fr*)c.o; a.z = (const Fr*)c.z;
@@ -205,20 +205,31 @@ struct NttInst {
     Fr* bdst[4] = {a.bl, a.br, a.bo, a.bz};
     for (int q = 0; q < 4; q++) {
       if (bn[q] < 0 || bn[q] > PLONK_MAX_BLIND) return cudaErrorInvalidValue;
-      for (int k = 0; k < PLONK_MAX_BLIND; k++) bdst[q][k] = k < bn[q] ? ((const Fr*)bsrc[q])[k] : Fr::zero();
+      plonk_set_blinding<Fr>(a, bdst[q], (const Fr*)bsrc[q], bn[q]);
     }
     a.nbl = c.nbl; a.nbr = c.nbr; a.nbo = c.nbo; a.nbz = c.nbz;
     a.n = d.n; a.logn = (uint32_t)d.logn; a.rho = c.rho; a.coset_index = c.coset_index;
     a.log_rho = 0;
     while ((1u << a.log_rho) < c.rho) a.log_rho++;
     if ((1u << a.log_rho) != c.rho || c.coset_index >= c.rho) return cudaErrorInvalidValue;
+    // denominators of L1 on this coset: cached in the domain handle (one handle per coset in the prover), else per call
+    static const bool den_cache = [] { const char* e = getenv("GB200_PLONK_DEN_CACHE"); return !e || atoi(e) != 0; }();
     AsyncBuf denb;
-    GB_CUDA_TRY(denb.alloc((size_t)d.n * sizeof(Fr), st));
-    Fr* den = (Fr*)denb.p;
-    k_plonk_denominators<Fr><<<(d.n + 255) / 256, 256, 0, st>>>(den, d.n, d.tw, coset);
-    GB_CUDA_TRY(batch_invert(st, den, d.n));
+    Fr* den;
+    if (den_cache) {
+      if (!d.den_inv) GB_CUDA_TRY(cudaMalloc(&d.den_inv, (size_t)d.n * sizeof(Fr)));
+      den = d.den_inv;
+    } else {
+      GB_CUDA_TRY(denb.alloc((size_t)d.n * sizeof(Fr), st));
+      den = (Fr*)denb.p;
+    }
+    if (!den_cache || !d.den_valid || !(d.den_coset == coset)) {
+      k_plonk_denominators<Fr><<<(d.n + 255) / 256, 256, 0, st>>>(den, d.n, d.tw, coset);
+      GB_CUDA_TRY(batch_invert(st, den, d.n));
+      if (den_cache) { d.den_coset = coset; d.den_valid = true; }
+    }
     a.den_inv = den;
-    k_plonk_constraints<Fr><<<(d.n + 255) / 256, 256, 0, st>>>(a);
+    k_plonk_constraints<Fr><<<(d.n + 127) / 128, 128, 0, st>>>(a);
     GB_CUDA_TRY(cudaGetLastError());
     return denb.release_on(st);
   }

@@ -119,6 +119,12 @@ struct NttDomainDev {
   Fr* cos = nullptr;   // g^j,  j < n
   Fr* icos = nullptr;  // g^-j / n
   NttPlan plan;
+  // PLONK: 1 / (c w^j - 1), j < n, for the coset c the last constraint pass on this handle ran on (precomputedDenominators,
+  // backend/plonk/bn254/prove.go:1002-1007).  The prover keeps one handle per coset of the quotient domain, so after the
+  // first proof this is a pure cache (n elements of HBM per handle; GB200_PLONK_DEN_CACHE=0 computes it per call)
+  Fr* den_inv = nullptr;
+  Fr den_coset;
+  bool den_valid = false;
 
   size_t table_bytes() const { return ((size_t)(n > 1 ? n / 2 : 1) * 2 + (size_t)n * 2) * sizeof(Fr); }
 
@@ -167,8 +173,9 @@ struct NttDomainDev {
     return cudaFree(d_pw);
   }
   void destroy() {
-    cudaFree(tw); cudaFree(itw); cudaFree(cos); cudaFree(icos);
-    tw = itw = cos = icos = nullptr;
+    cudaFree(tw); cudaFree(itw); cudaFree(cos); cudaFree(icos); cudaFree(den_inv);
+    tw = itw = cos = icos = den_inv = nullptr;
+    den_valid = false;
   }
 };
 

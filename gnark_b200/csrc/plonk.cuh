@@ -26,16 +26,25 @@ struct PlonkCosetArgs {
   Fr cs, css;            // domain1.FrMultiplicativeGen and its square (:891-893)
   Fr coset_n_minus_one;  // coset^n - 1
   Fr lone_scale;         // (coset^n - 1) / n
+  // blinding coefficients ALREADY multiplied by coset^n - 1 (plonk_set_blinding): on a coset X^n - 1 is that constant, so
+  // p + (X^n - 1) b(X) costs deg(b) multiplications per point instead of deg(b) + 2 (the reference pre-scales too, :967-981)
   Fr bl[PLONK_MAX_BLIND], br[PLONK_MAX_BLIND], bo[PLONK_MAX_BLIND], bz[PLONK_MAX_BLIND];
-  int nbl, nbr, nbo, nbz;  // number of blinding coefficients (original, unscaled)
+  int nbl, nbr, nbo, nbz;  // number of blinding coefficients
   uint32_t n, logn, rho, log_rho, coset_index;
 };
 
 template <class Fr>
 HD Fr plonk_horner(const Fr* c, int nc, const Fr& x) {
-  Fr acc = Fr::zero();
-  for (int k = nc - 1; k >= 0; k--) acc = acc * x + c[k];
+  if (nc <= 0) return Fr::zero();
+  Fr acc = c[nc - 1];
+  for (int k = nc - 2; k >= 0; k--) acc = acc * x + c[k];
   return acc;
+}
+
+// dst[k] = (coset^n - 1) * src[k] for k < nb, zero above; a.coset_n_minus_one must be set
+template <class Fr>
+HD void plonk_set_blinding(const PlonkCosetArgs<Fr>& a, Fr* dst, const Fr* src, int nb) {
+  for (int k = 0; k < PLONK_MAX_BLIND; k++) dst[k] = k < nb ? a.coset_n_minus_one * src[k] : Fr::zero();
 }
 
 // One point of one coset.  wj = w^j, wj1 = w^(j+1 mod n).
@@ -46,11 +55,11 @@ HD Fr plonk_all_constraints(const PlonkCosetArgs<Fr>& a, uint32_t j, const Fr& w
   const Fr x1 = a.coset * wj1;
   // blinded L, R, O, Z, ZS: p + (X^n - 1) b(X) on the coset (:967-981; the reference pre-scales b's
   // coefficients so that evaluating at w^j yields exactly this value)
-  Fr L = a.l[j] + a.coset_n_minus_one * plonk_horner(a.bl, a.nbl, x);
-  Fr R = a.r[j] + a.coset_n_minus_one * plonk_horner(a.br, a.nbr, x);
-  Fr O = a.o[j] + a.coset_n_minus_one * plonk_horner(a.bo, a.nbo, x);
-  Fr Z = a.z[j] + a.coset_n_minus_one * plonk_horner(a.bz, a.nbz, x);
-  Fr ZS = a.z[j1] + a.coset_n_minus_one * plonk_horner(a.bz, a.nbz, x1);
+  Fr L = a.l[j] + plonk_horner(a.bl, a.nbl, x);
+  Fr R = a.r[j] + plonk_horner(a.br, a.nbr, x);
+  Fr O = a.o[j] + plonk_horner(a.bo, a.nbo, x);
+  Fr Z = a.z[j] + plonk_horner(a.bz, a.nbz, x);
+  Fr ZS = a.z[j1] + plonk_horner(a.bz, a.nbz, x1);
   // gate (:871-889)
   Fr gate = a.ql[j] * L + a.qr[j] * R + a.qm[j] * L * R + a.qo[j] * O + a.qk[j];
   // ordering (:907-931)
@@ -90,8 +99,11 @@ __global__ void __launch_bounds__(256) k_plonk_add_bsb22(const Fr* __restrict__ 
   if (j < n) plonk_add_bsb22_point<Fr>(qcp, pi2, out, j, coset_index, rho, logn, log_rho);
 }
 
+// 128-thread blocks, 4 resident per SM asked of ptxas (<= 128 registers): left alone the kernel takes 136 registers and,
+// with the 256-thread blocks of round 1, ran ONE block = 8 warps per SM - a chain of ~30 dependent field products per
+// thread with nothing to overlap it (4.3 ms per coset at 2^22 against a 1.9 ms multiplier bound)
 template <class Fr>
-__global__ void __launch_bounds__(256) k_plonk_constraints(PlonkCosetArgs<Fr> a) {
+__global__ void __launch_bounds__(128, 4) k_plonk_constraints(PlonkCosetArgs<Fr> a) {
   const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= a.n) return;
   const uint32_t half = a.n >> 1;

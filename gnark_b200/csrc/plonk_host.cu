@@ -142,6 +142,17 @@ int32_t commit(b200_plonk_pk_s* pk, const void* d_coeffs, size_t count, void* ou
   return b200_msm_g1(pk->srs, 0, count, d_coeffs, 1, out_jac);
 }
 
+// Independent commitments of one round (L, R, O; H1, H2, H3) go through the pipelined MSM: results stay on the device,
+// the reduction tail of one MSM and the upload / transforms of the next polynomial run under the next accumulate, and
+// ONE join + download ends the round (the synchronous commit() pays a tail and a download per commitment).
+int32_t commit_async(b200_plonk_pk_s* pk, const void* d_coeffs, size_t count, void* d_out_jac) {
+  return b200_msm_pipelined(pk->srs, 0, count, d_coeffs, d_out_jac);
+}
+int32_t commit_join(b200_plonk_pk_s* pk, const void* d_res, size_t bytes, void* out_host) {
+  RC(b200_msm_join(pk->dev));
+  return b200_d2h(pk->dev, out_host, d_res, bytes);
+}
+
 int32_t eval_at(b200_plonk_pk_s* pk, const void* d_coeffs, size_t count, const HostFr& x, HostFr* out) {
   alignas(16) uint8_t xb[8 * HOSTFR_MAX_LIMBS], ob[8 * HOSTFR_MAX_LIMBS];
   pk->fr->store(xb, x);
@@ -296,12 +307,18 @@ int32_t b200_plonk_begin(b200_plonk_pk_t pk, const void* l, const void* r, const
   memcpy(s->blind[0], bl, 2 * fb); memcpy(s->blind[1], br, 2 * fb); memcpy(s->blind[2], bo, 2 * fb);
   // ---- commitToLRO :404-489
   RC(s->S.alloc(n * fb, &s->d_l)); RC(s->S.alloc(n * fb, &s->d_r)); RC(s->S.alloc(n * fb, &s->d_o));
-  RC(b200_h2d(dev, s->d_l, l, n * fb)); RC(b200_h2d(dev, s->d_r, r, n * fb)); RC(b200_h2d(dev, s->d_o, o, n * fb));
   const int nbl[4] = {2, 2, 2, 3};
   for (int k = 0; k < 4; k++) { RC(s->S.alloc(n * fb, &s->cb[k])); RC(s->S.alloc((n + nbl[k]) * fb, &s->bl[k])); }
-  const void* lag[3] = {s->d_l, s->d_r, s->d_o};
-  for (int k = 0; k < 3; k++) RC(canonical_blinded(pk, lag[k], s->blind[k], 2, s->cb[k], s->bl[k]));
-  for (int k = 0; k < 3; k++) RC(commit(pk, s->bl[k], n + 2, (uint8_t*)out_lro + (size_t)k * s->jb));
+  void* lag[3] = {s->d_l, s->d_r, s->d_o};
+  const void* host[3] = {l, r, o};
+  void* d_lro;
+  RC(s->S.alloc(3 * s->jb, &d_lro));
+  for (int k = 0; k < 3; k++) {       // upload and transforms of wire k + 1 run under the MSM of wire k
+    RC(b200_h2d(dev, lag[k], host[k], n * fb));
+    RC(canonical_blinded(pk, lag[k], s->blind[k], 2, s->cb[k], s->bl[k]));
+    RC(commit_async(pk, s->bl[k], n + 2, (uint8_t*)d_lro + (size_t)k * s->jb));
+  }
+  RC(commit_join(pk, d_lro, 3 * s->jb, out_lro));
   // BSB22: committed polynomials -> canonical, and their digests (Bsb22Commitments :300; canonical SRS here, the
   // same group element as the reference's Lagrange-SRS commitment)
   for (size_t j = 0; j < pk->qcp_br.size(); j++) {
@@ -420,9 +437,11 @@ int32_t b200_plonk_quotient(b200_plonk_session_t s, const void* alpha, void* out
     }
   }
   RC(b200_plonk_divide_by_zh(pk->dom1, pk->logn, s->h));      // -> h canonical regular (4n)
+  void* d_hres;
+  RC(T.alloc(3 * s->jb, &d_hres));
   if (!s->szk) {
     for (int k = 0; k < 3; k++)
-      RC(commit(pk, (uint8_t*)s->h + (size_t)k * (n + 2) * fb, n + 2, (uint8_t*)out_h + (size_t)k * s->jb));
+      RC(commit_async(pk, (uint8_t*)s->h + (size_t)k * (n + 2) * fb, n + 2, (uint8_t*)d_hres + (size_t)k * s->jb));
   } else {
     // StatisticalZK (h1(), h2(), h3(), prove.go:689-722): h1 + b1 X^(n+2), h2 - b1 + b2 X^(n+2), h3 - b2.  The shards
     // are adjacent slices of s->h, so each randomised shard is committed from a copy; s->h keeps the plain quotient
@@ -435,9 +454,11 @@ int32_t b200_plonk_quotient(b200_plonk_session_t s, const void* alpha, void* out
       RC(d2d(dev, tmp, (uint8_t*)s->h + (size_t)k * (n + 2) * fb, (n + 2) * fb));
       if (k > 0) RC(add_to_element(pk, tmp, 0, fr->neg(k == 1 ? b1 : b2)));
       if (k < 2) RC(b200_h2d(dev, (uint8_t*)tmp + (n + 2) * fb, s->hr[k], fb));
-      RC(commit(pk, tmp, k < 2 ? n + 3 : n + 2, (uint8_t*)out_h + (size_t)k * s->jb));
+      // tmp is rewritten for the next shard in stream order, after this MSM's digit extraction has read it
+      RC(commit_async(pk, tmp, k < 2 ? n + 3 : n + 2, (uint8_t*)d_hres + (size_t)k * s->jb));
     }
   }
+  RC(commit_join(pk, d_hres, 3 * s->jb, out_h));
   RC(b200_sync(dev));   // T's buffers are in use until here
   s->stage = 3;
   return 0;
@@ -512,7 +533,12 @@ int32_t b200_plonk_linearise(b200_plonk_session_t s, const void* zeta_, void* ou
     RC(add_to_element(pk, lin, n + 2, fr->neg(d)));
     RC(add_to_element(pk, lin, 0, M(d, zn2)));
   }
-  RC(commit(pk, lin, n + 3, out_points));
+  // the two commitments of this round go through the pipelined MSM: the evaluations and the division below run under the
+  // accumulate of the linearised digest, one join + download at the end
+  Scratch T(dev);
+  void* d_two;
+  RC(T.alloc(2 * s->jb, &d_two));
+  RC(commit_async(pk, lin, n + 3, d_two));
   // claimed values of the batch opening (BatchedProof.ClaimedValues) - needed by the caller to derive v
   const void* open_p[6] = {lin, s->bl[0], s->bl[1], s->bl[2], pk->canon[S1], pk->canon[S2]};
   const size_t open_n[6] = {n + 3, n + 2, n + 2, n + 2, n, n};
@@ -523,14 +549,14 @@ int32_t b200_plonk_linearise(b200_plonk_session_t s, const void* zeta_, void* ou
   }
   // Z-shifted opening: (Z(X) - Z(w zeta)) / (X - w zeta)
   alignas(16) uint8_t zb[8 * HOSTFR_MAX_LIMBS], rem[8 * HOSTFR_MAX_LIMBS];
-  Scratch T(dev);
   void* zq;
   RC(T.alloc((n + 3) * fb, &zq));
   RC(d2d(dev, zq, s->bl[3], (n + 3) * fb));
   fr->store(zb, wz);
   RC(b200_poly_div_by_linear(dev, curve, zq, n + 3, zb, rem));
   if (!fr->eq(fr->load(rem), zu)) return set_error("plonk_linearise: Z(w zeta) from the division differs from the evaluation");
-  RC(commit(pk, zq, n + 2, (uint8_t*)out_points + s->jb));
+  RC(commit_async(pk, zq, n + 2, (uint8_t*)d_two + s->jb));
+  RC(commit_join(pk, d_two, 2 * s->jb, out_points));
   fr->store(vals + 6 * fb, zu);
   RC(b200_sync(dev));
   s->stage = 4;

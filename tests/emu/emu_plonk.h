@@ -34,9 +34,7 @@ int plonk_coset_emu(const void* const* polys, const void* abg, const void* const
   a.coset_n_minus_one = cn - Fr::one();
   a.lone_scale = a.coset_n_minus_one * dom0.ninv;
   Fr* bd[4] = {a.bl, a.br, a.bo, a.bz};
-  for (int q = 0; q < 4; q++)
-    for (int k = 0; k < PLONK_MAX_BLIND; k++)
-      bd[q][k] = k < nblind[q] ? reinterpret_cast<const Fr*>(blind[q])[k] : Fr::zero();
+  for (int q = 0; q < 4; q++) plonk_set_blinding<Fr>(a, bd[q], reinterpret_cast<const Fr*>(blind[q]), nblind[q]);
   a.nbl = nblind[0]; a.nbr = nblind[1]; a.nbo = nblind[2]; a.nbz = nblind[3];
   a.n = n; a.logn = logn; a.rho = rho; a.log_rho = log_rho; a.coset_index = coset_index;
   std::vector<Fr> wp(n), den(n);

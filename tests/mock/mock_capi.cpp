@@ -226,4 +226,7 @@ int32_t b200_poly_div_by_linear(int32_t dev, int32_t curve, void* c, size_t n, c
 int32_t b200_table_upload(int32_t dev, int32_t curve, int32_t group, const void* pts, size_t n, int32_t flags, b200_table_t* out) { DISPATCH(curve, table_upload(dev, curve, group, pts, n, flags, out)); }
 int32_t b200_table_free(b200_table_t t) { if (!t) return 0; DISPATCH(t->curve, table_free(t)); }
 int32_t b200_msm_g1(b200_table_t t, size_t off, size_t n, const void* scalars, int32_t on_dev, void* out) { DISPATCH(t->curve, msm_g1(t, off, n, scalars, on_dev, out)); }
+// the pipelined MSM of the library (device scalars -> device result, joined later): here computed on the spot
+int32_t b200_msm_pipelined(b200_table_t t, size_t off, size_t n, const void* d_scalars, void* d_out) { DISPATCH(t->curve, msm_g1(t, off, n, d_scalars, 1, d_out)); }
+int32_t b200_msm_join(int32_t) { return 0; }
 }  // extern "C"
