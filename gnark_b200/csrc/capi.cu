@@ -375,17 +375,15 @@ int32_t b200_table_upload_encoded(int32_t dev, int32_t curve, int32_t group, con
   std::unique_ptr<b200_table_s> t;
   rc = table_new(dev, curve, group, n, flags, t); if (rc) return rc;
   const size_t per = t->ops->encoded_bytes(encoding);
-  if (per == 0) return set_error("table_upload_encoded: encoding not supported for this group (compressed: G1 only; 1 = raw, 2 = compressed)");
-  static const int b_small[4] = {3, 4, 1, -1};       // y^2 = x^3 + b: BN254, BLS12-381, BLS12-377, BW6-761
+  if (per == 0) return set_error("table_upload_encoded: unknown encoding (1 = raw, 2 = compressed)");
   if (n) {
     AsyncBuf d_bytes, d_status;
     CK(d_bytes.alloc(n * per, ctx->stream));
     CK(d_status.alloc(2 * sizeof(uint32_t), ctx->stream));
     CK(cudaMemsetAsync(d_status.p, 0, 2 * sizeof(uint32_t), ctx->stream));
     CK(cudaMemcpyAsync(d_bytes.p, bytes, n * per, cudaMemcpyHostToDevice, ctx->stream));
-    cudaError_t e = t->ops->decode(ctx->stream, d_bytes.p, n, encoding, b_small[curve], t->d_points, (uint32_t*)d_status.p);
-    if (e == cudaErrorNotSupported)
-      return set_error("table_upload_encoded: compressed points need p = 3 mod 4 (BLS12-377: use the raw encoding)");
+    cudaError_t e = t->ops->decode(ctx->stream, d_bytes.p, n, encoding, curve, group, t->d_points, (uint32_t*)d_status.p);
+    if (e == cudaErrorNotSupported) return set_error("table_upload_encoded: encoding not supported for this group");
     if (e != cudaSuccess) return cuda_fail("points decode", e);
     uint32_t status[2] = {0, 0};
     CK(cudaMemcpyAsync(status, d_status.p, sizeof(status), cudaMemcpyDeviceToHost, ctx->stream));

@@ -293,6 +293,7 @@ template <class P> struct is_device_fp<Fp<P>> { static constexpr bool value = tr
 template <class F, unsigned BETA>
 struct alignas(16) Fp2 {
   static constexpr int DEGREE = 2;
+  static constexpr unsigned BETA_VALUE = BETA;
   using Base = F;
   F a0, a1;
   HD static Fp2 zero() { Fp2 r; r.a0 = F::zero(); r.a1 = F::zero(); return r; }

@@ -69,15 +69,14 @@ struct MsmInst {
   using FB = typename F::Base;
   static size_t encoded_bytes(int encoding) {
     if (encoding == POINTS_RAW) return sizeof(Affine<F>);
-    if (encoding == POINTS_COMPRESSED && F::DEGREE == 1) return sizeof(F);
+    if (encoding == POINTS_COMPRESSED) return sizeof(F);      // X only (G2: X.A1 || X.A0)
     return 0;
   }
-  static cudaError_t decode(cudaStream_t st, const void* d_bytes, size_t n, int encoding, int b_small, void* d_out_affine,
-                            uint32_t* d_status) {
+  static cudaError_t decode(cudaStream_t st, const void* d_bytes, size_t n, int encoding, int curve, int group,
+                            void* d_out_affine, uint32_t* d_status) {
     if (n == 0) return cudaSuccess;
     if (encoded_bytes(encoding) == 0) return cudaErrorNotSupported;
-    const DecodeConsts<FB> k = decode_make_consts<FB>(b_small);
-    if (encoding == POINTS_COMPRESSED && !k.sqrt_ok) return cudaErrorNotSupported;     // p = 1 mod 4: Tonelli-Shanks not built
+    const DecodeConsts<FB> k = decode_make_consts<F, FB>(curve, group);
     const size_t stride = encoded_bytes(encoding);
     k_points_decode<F, FB><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(reinterpret_cast<const uint8_t*>(d_bytes), n, stride,
                                                                        encoding == POINTS_COMPRESSED ? 1 : 0, k,

@@ -59,10 +59,10 @@ struct MsmOps {
   // multi-GPU combine: d_out[k] = sum_r d_gathered[r * count + k] (Jacobian points, k_points_fold)
   cudaError_t (*fold)(cudaStream_t st, const void* d_gathered, uint32_t world, uint32_t count, void* d_out_jac);
   // serialised point slices (gnark-crypto encodings, points_decode.cuh): bytes per point of an encoding (0 = not
-  // supported for this group), and the decode kernel.  b_small: the curve coefficient as a small signed integer;
+  // supported for this group), and the decode kernel.  curve / group: which curve coefficient (or twist coefficient) applies;
   // d_status: two uint32 (DECODE_* code, index), zeroed by the caller
   size_t (*encoded_bytes)(int encoding);
-  cudaError_t (*decode)(cudaStream_t st, const void* d_bytes, size_t n, int encoding, int b_small, void* d_out_affine,
+  cudaError_t (*decode)(cudaStream_t st, const void* d_bytes, size_t n, int encoding, int curve, int group, void* d_out_affine,
                         uint32_t* d_status);
 };
 

@@ -89,7 +89,8 @@ int32_t b200_table_upload_file(int32_t dev, int32_t curve, int32_t group /*1|2*/
  * bits in the first byte (B200_POINTS_COMPRESSED = what WriteTo emits, x only, sizeof(fp) bytes per G1 point;
  * B200_POINTS_RAW = what WriteRawTo emits, x || y).  The bytes are uploaded as they are and decoded on the device, one
  * thread per point: byte order, Montgomery form, and for compressed points the square root that dominates ReadFrom on the
- * CPU.  Compressed: G1 of BN254, BLS12-381 and BW6-761 (p = 3 mod 4); raw: G1 and G2 of every curve.  Each point is
+ * CPU.  Compressed and raw: G1 and G2 of every curve (square roots by exponentiation where p = 3 mod 4, Tonelli-Shanks
+ * for BLS12-377; in Fp2 by the norm).  Each point is
  * checked to be canonical and on the curve (G1); subgroup membership is not checked, as with UnsafeReadFrom.  An
  * invalid point fails the call and names its index. */
 enum { B200_POINTS_RAW = 1, B200_POINTS_COMPRESSED = 2 };

@@ -193,12 +193,10 @@ int bsb22_emu(const void* qcp, const void* pi2, void* out, uint32_t logn, uint32
 
 // points_decode.cuh: n serialised points -> affine Montgomery points; returns the first DECODE_* status that is not OK
 template <class F>
-static int decode_emu(const void* bytes, size_t n, int encoding, int b_small, void* out) {
+static int decode_emu(const void* bytes, size_t n, int encoding, int curve, int group, void* out) {
   using FB = typename F::Base;
   const size_t stride = encoding == POINTS_RAW ? sizeof(Affine<F>) : sizeof(F);
-  if (encoding == POINTS_COMPRESSED && F::DEGREE != 1) return -2;
-  const DecodeConsts<FB> k = decode_make_consts<FB>(b_small);
-  if (encoding == POINTS_COMPRESSED && !k.sqrt_ok) return -3;
+  const DecodeConsts<FB> k = decode_make_consts<F, FB>(curve, group);
   int first = 0;
   for (size_t i = 0; i < n; i++) {
     Affine<F> a = Affine<F>::inf();
@@ -228,16 +226,16 @@ int emu_plonk_constraints_coset(int curve, const void* const* polys, const void*
 
 
 
-int emu_decode_points(int curve, int group, const void* bytes, size_t n, int encoding, int b_small, void* out) {
+int emu_decode_points(int curve, int group, const void* bytes, size_t n, int encoding, void* out) {
   switch (curve * 2 + (group - 1)) {
-    case 0: return decode_emu<bn254_fp>(bytes, n, encoding, b_small, out);
-    case 1: return decode_emu<bn254_fp2>(bytes, n, encoding, b_small, out);
-    case 2: return decode_emu<bls12_381_fp>(bytes, n, encoding, b_small, out);
-    case 3: return decode_emu<bls12_381_fp2>(bytes, n, encoding, b_small, out);
-    case 4: return decode_emu<bls12_377_fp>(bytes, n, encoding, b_small, out);
-    case 5: return decode_emu<bls12_377_fp2>(bytes, n, encoding, b_small, out);
+    case 0: return decode_emu<bn254_fp>(bytes, n, encoding, curve, group, out);
+    case 1: return decode_emu<bn254_fp2>(bytes, n, encoding, curve, group, out);
+    case 2: return decode_emu<bls12_381_fp>(bytes, n, encoding, curve, group, out);
+    case 3: return decode_emu<bls12_381_fp2>(bytes, n, encoding, curve, group, out);
+    case 4: return decode_emu<bls12_377_fp>(bytes, n, encoding, curve, group, out);
+    case 5: return decode_emu<bls12_377_fp2>(bytes, n, encoding, curve, group, out);
     case 6:
-    case 7: return decode_emu<bw6_761_fp>(bytes, n, encoding, b_small, out);
+    case 7: return decode_emu<bw6_761_fp>(bytes, n, encoding, curve, group, out);
   }
   return -1;
 }

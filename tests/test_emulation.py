@@ -320,17 +320,15 @@ def test_point_decoding_logic(hostemu, c):
     rng = random.Random(77)
     F1 = ff.Fp(c.p)
     b_small = {"bn254": 3, "bls12-381": 4, "bls12-377": 1, "bw6-761": -1}[c.name]
-    hostemu.emu_decode_points.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int,
-                                          ctypes.c_void_p]
+    hostemu.emu_decode_points.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p]
     if c.g1 is not None:
         pts = [ec.scalar_mul(F1, rng.randrange(1, c.r), c.g1) for _ in range(12)] + [None]
-    else:           # no generator recalled for this curve (BW6-761): random points of y^2 = x^3 + b, p = 3 mod 4
+    else:           # no generator recalled for this curve (BW6-761): random points of y^2 = x^3 + b
         pts = []
         while len(pts) < 12:
             x = rng.randrange(c.p)
-            y2 = (x ** 3 + b_small) % c.p
-            y = pow(y2, (c.p + 1) // 4, c.p)
-            if y * y % c.p == y2:
+            y = encoding.sqrt_fp(c.p, x ** 3 + b_small)
+            if y is not None:
                 pts.append((x, y if rng.random() < 0.5 else c.p - y))
         pts.append(None)
     pts.append(ec.affine_neg(F1, pts[0]))                  # the other root for the same x
@@ -338,15 +336,12 @@ def test_point_decoding_logic(hostemu, c):
         blob = b"".join(encoding.encode_g1(c, P_, compressed) for P_ in pts)
         raw = np.frombuffer(blob, dtype=np.uint8).copy()
         out = np.zeros((len(pts), 2 * c.fp_limbs), dtype=np.uint64)
-        rc = hostemu.emu_decode_points(c.curve_id, 1, P(raw), len(pts), 2 if compressed else 1, b_small, P(out))
-        if compressed and c.p % 4 != 3:
-            assert rc == -3                                  # p = 1 mod 4 (BLS12-377): compressed form not supported
-            continue
-        assert rc == 0, (c.name, compressed)
+        rc = hostemu.emu_decode_points(c.curve_id, 1, P(raw), len(pts), 2 if compressed else 1, P(out))
+        assert rc == 0, (c.name, compressed)                 # BLS12-377 (p = 1 mod 4): Tonelli-Shanks
         assert ec.unpack_points(c, 1, out) == pts, (c.name, compressed)
         assert [encoding.decode_g1(c, blob[i * len(blob) // len(pts):(i + 1) * len(blob) // len(pts)]) for i in range(len(pts))] == pts
     # rejected inputs
-    one = lambda bts, enc: hostemu.emu_decode_points(c.curve_id, 1, P(np.frombuffer(bts, dtype=np.uint8).copy()), 1, enc, b_small,
+    one = lambda bts, enc: hostemu.emu_decode_points(c.curve_id, 1, P(np.frombuffer(bts, dtype=np.uint8).copy()), 1, enc,
                                                      P(np.zeros(2 * c.fp_limbs, dtype=np.uint64)))
     good = encoding.encode_g1(c, pts[0], False)
     bad_curve = good[:-1] + bytes([good[-1] ^ 1])          # y changed: not on the curve
@@ -356,7 +351,7 @@ def test_point_decoding_logic(hostemu, c):
         assert one(too_big, 1) == 2                        # x = p is not reduced
     flagged = bytes([good[0] | 0x80]) + good[1:]           # "compressed" bit on an uncompressed point
     assert one(flagged, 1) == 1
-    if c.p % 4 == 3:
+    if True:
         comp = encoding.encode_g1(c, pts[0], True)
         # find an x that is not on the curve
         x = 5
@@ -372,5 +367,81 @@ def test_point_decoding_logic(hostemu, c):
         g2pts = [ec.scalar_mul(F2, rng.randrange(1, c.r), g2) for _ in range(4)] + [None]
         blob = b"".join(encoding.encode_g2_raw(c, Q) for Q in g2pts)
         out = np.zeros((len(g2pts), 4 * c.fp_limbs), dtype=np.uint64)
-        assert hostemu.emu_decode_points(c.curve_id, 2, P(np.frombuffer(blob, dtype=np.uint8).copy()), len(g2pts), 1, b_small, P(out)) == 0
+        assert hostemu.emu_decode_points(c.curve_id, 2, P(np.frombuffer(blob, dtype=np.uint8).copy()), len(g2pts), 1, P(out)) == 0
         assert ec.unpack_points(c, 2, out) == g2pts
+
+
+@pytest.mark.parametrize("c", ALL, ids=lambda c: c.name)
+def test_g2_compressed_decoding(hostemu, c):
+    """compressed G2 through points_decode.cuh (square roots in Fp2 by the norm, Tonelli-Shanks under them for
+    BLS12-377; BW6-761: G2 over Fp on y^2 = x^3 + 4) against oracle/encoding.py - random points of the twist, both roots,
+    infinity, an x that is not on the twist; and the EXTERNAL vectors: the compressed G2 generators inside gnark's
+    serialised verifying keys (BN254, BLS12-381) and the 65 compressed G2 points of the Ethereum KZG ceremony file."""
+    import json
+    import os
+    from oracle import encoding
+    rng = random.Random(99)
+    hostemu.emu_decode_points.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p]
+    p = c.p
+    deg = c.g2_degree
+    F2 = ff.base_field(c, 2)
+    bt = encoding.twist_b(c)
+    if c.g2 is not None:                       # the recalled generator is on the twist this module states
+        x, y = c.g2
+        assert F2.eq(F2.sqr(y), F2.add(F2.mul(F2.sqr(x), x), bt if deg == 2 else F2.from_int(bt)))
+    pts = []
+    while len(pts) < 10:                       # random points of the twist (the decoder does not check the subgroup)
+        if deg == 2:
+            x = (rng.randrange(p), rng.randrange(p) if len(pts) != 3 else 0)
+            y = encoding.sqrt_fp2(c, F2.add(F2.mul(F2.sqr(x), x), bt))
+        else:
+            x = rng.randrange(p)
+            y = encoding.sqrt_fp(p, x ** 3 + bt)
+        if y is not None:
+            pts.append((x, y))
+    pts.append((pts[0][0], F2.neg(pts[0][1])))
+    pts.append(None)
+    if c.g2 is not None:
+        pts.append(c.g2)
+    blob = b"".join(encoding.encode_g2(c, Q, True) for Q in pts)
+    per = len(blob) // len(pts)
+    assert per == deg * 8 * c.fp_limbs
+    assert [encoding.decode_g2(c, blob[i * per:(i + 1) * per]) for i in range(len(pts))] == pts
+    out = np.zeros((len(pts), 2 * deg * c.fp_limbs), dtype=np.uint64)
+    assert hostemu.emu_decode_points(c.curve_id, 2, P(np.frombuffer(blob, dtype=np.uint8).copy()), len(pts), 2, P(out)) == 0
+    assert ec.unpack_points(c, 2, out) == pts
+    # raw encoding of the same points (BW6-761 G2: the on-curve check must use b = 4, not G1's -1)
+    rawb = b"".join(encoding.encode_g2(c, Q, False) for Q in pts)
+    assert hostemu.emu_decode_points(c.curve_id, 2, P(np.frombuffer(rawb, dtype=np.uint8).copy()), len(pts), 1, P(out)) == 0
+    assert ec.unpack_points(c, 2, out) == pts
+    # an x that is not on the twist is refused
+    while True:
+        x = (rng.randrange(p), rng.randrange(p)) if deg == 2 else rng.randrange(p)
+        rhs = F2.add(F2.mul(F2.sqr(x), x), bt) if deg == 2 else (x ** 3 + bt) % p
+        if (encoding.sqrt_fp2(c, rhs) if deg == 2 else encoding.sqrt_fp(p, rhs)) is None:
+            break
+    fake = ((x, (1, 1)) if deg == 2 else (x, 1))
+    bad = encoding.encode_g2(c, fake, True)
+    assert hostemu.emu_decode_points(c.curve_id, 2, P(np.frombuffer(bad, dtype=np.uint8).copy()), 1, 2,
+                                     P(np.zeros(2 * deg * c.fp_limbs, dtype=np.uint64))) == 3
+    # external vectors
+    here = os.path.dirname(os.path.abspath(__file__))
+    vk = json.load(open(os.path.join(here, "golden", "gnark_vk_constants_v1.json")))
+    name = {"bn254": "bn254", "bls12-381": "bls12-381"}.get(c.name)
+    for key in vk["keys"]:
+        if name and key["curve"] == name:
+            raw = bytes.fromhex(key["kzg_g2_0_compressed"])
+            assert encoding.decode_g2(c, raw) == c.g2 and encoding.encode_g2(c, c.g2, True) == raw
+            o1 = np.zeros((1, 4 * c.fp_limbs), dtype=np.uint64)
+            assert hostemu.emu_decode_points(c.curve_id, 2, P(np.frombuffer(raw, dtype=np.uint8).copy()), 1, 2, P(o1)) == 0
+            assert ec.unpack_points(c, 2, o1) == [c.g2]
+    if c.name == "bls12-381":
+        from oracle import kzg_srs
+        blob = open(kzg_srs.PATH, "rb").read()
+        off = 2 * kzg_srs.N * 48
+        g2b = blob[off:off + 96 * kzg_srs.N_G2]
+        want = kzg_srs.load()[2]
+        o65 = np.zeros((kzg_srs.N_G2, 4 * c.fp_limbs), dtype=np.uint64)
+        assert hostemu.emu_decode_points(c.curve_id, 2, P(np.frombuffer(g2b, dtype=np.uint8).copy()), kzg_srs.N_G2, 2, P(o65)) == 0
+        assert ec.unpack_points(c, 2, o65) == want
+        assert b"".join(encoding.encode_g2(c, Q, True) for Q in want) == g2b

@@ -301,7 +301,7 @@ def test_table_from_the_ethereum_srs_in_gnark_encoding(gpu):
 @pytest.mark.parametrize("cname", ["bn254", "bw6-761", "bls12-377"])
 def test_table_from_encoded_points_other_curves(gpu, cname):
     """the decoder on the other curves against oracle/encoding.py: BN254's two-bit metadata, BW6-761's 96-byte
-    coordinates, BLS12-377 raw only (compressed needs Tonelli-Shanks: refused); infinity inside the slice; G2 raw"""
+    coordinates, BLS12-377 compressed through Tonelli-Shanks; infinity inside the slice; G2 raw"""
     from oracle import encoding
     c = CURVES[cname]
     n = 300
@@ -311,10 +311,6 @@ def test_table_from_encoded_points_other_curves(gpu, cname):
     if on_curve:
         for enc, compressed in ((gpu.POINTS_RAW, False), (gpu.POINTS_COMPRESSED, True)):
             data = b"".join(encoding.encode_g1(c, P_, compressed) for P_ in P1)
-            if compressed and c.p % 4 != 3:
-                with pytest.raises(gpu.B200Error, match="p = 3 mod 4"):
-                    gpu.Table.from_encoded(c.curve_id, 1, data, n, enc)
-                continue
             t = gpu.Table.from_encoded(c.curve_id, 1, data, n, enc, precomp=False)
             assert jac_to_affine(c, 1, t.msm(sc)) == expected, (cname, enc)
             t.free()
@@ -453,3 +449,46 @@ def test_g2_table_point_known_failure(gpu):
             for w in range(16):
                 assert jac_to_affine(c, 2, t.msm(pe([1 << (16 * w)]), off=pad, n=1)) == ec.scalar_mul(F, 1 << (16 * w), P), (pad, precomp, w)
             t.free()
+
+
+def test_table_from_compressed_g2(gpu):
+    """compressed G2 slices decoded on the device (Fp2 square roots; points_decode.cuh): the 65 compressed BLS12-381 G2
+    points of the Ethereum KZG ceremony file (EXTERNAL bytes; oracle/kzg_srs.py decodes them for the expected sum) and
+    random multiples of the BN254 G2 generator, each as an MSM against the C++ oracle; a corrupted x is refused."""
+    from oracle import corelib, encoding, kzg_srs
+    rng = random.Random(31)
+    c = CURVES["bls12-381"]
+    blob = open(kzg_srs.PATH, "rb").read()
+    off = 2 * kzg_srs.N * 48
+    n = kzg_srs.N_G2
+    data = blob[off:off + 96 * n]
+    want_pts = kzg_srs.load()[2]
+    sc = ff.pack_elements([rng.randrange(c.r) for _ in range(n)], c.r, c.fr_limbs)
+    want = jac_to_affine(c, 2, corelib.msm(c, 2, ec.pack_points(c, 2, want_pts), sc))
+    for precomp in (False, True):
+        t = gpu.Table.from_encoded(c.curve_id, 2, data, n, gpu.POINTS_COMPRESSED, precomp=precomp)
+        assert jac_to_affine(c, 2, t.msm(sc)) == want
+        t.free()
+    # an x that is not on the twist, at position 9: refused with its index
+    F2 = ff.base_field(c, 2)
+    bad = bytearray(data)
+    x0 = int.from_bytes(data[96 * 9 + 48:96 * 10], "big")
+    x1 = int.from_bytes(data[96 * 9:96 * 9 + 48], "big") & ((1 << 381) - 1)
+    while True:
+        x0 = (x0 + 1) % c.p
+        if encoding.sqrt_fp2(c, F2.add(F2.mul(F2.sqr((x0, x1)), (x0, x1)), encoding.twist_b(c))) is None:
+            break
+    bad[96 * 9 + 48:96 * 10] = x0.to_bytes(48, "big")
+    with pytest.raises(gpu.B200Error, match="point 9"):
+        gpu.Table.from_encoded(c.curve_id, 2, bytes(bad), n, gpu.POINTS_COMPRESSED)
+    c = CURVES["bn254"]
+    F2 = ff.base_field(c, 2)
+    m = 200
+    pts = [ec.scalar_mul(F2, rng.randrange(1, c.r), c.g2) for _ in range(m)]
+    pts[11] = None
+    data = b"".join(encoding.encode_g2(c, Q, True) for Q in pts)
+    sc = ff.pack_elements([rng.randrange(c.r) for _ in range(m)], c.r, c.fr_limbs)
+    want = jac_to_affine(c, 2, corelib.msm(c, 2, ec.pack_points(c, 2, pts), sc))
+    t = gpu.Table.from_encoded(c.curve_id, 2, data, m, gpu.POINTS_COMPRESSED, precomp=True)
+    assert jac_to_affine(c, 2, t.msm(sc)) == want
+    t.free()
