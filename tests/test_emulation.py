@@ -445,3 +445,39 @@ def test_g2_compressed_decoding(hostemu, c):
         assert hostemu.emu_decode_points(c.curve_id, 2, P(np.frombuffer(g2b, dtype=np.uint8).copy()), kzg_srs.N_G2, 2, P(o65)) == 0
         assert ec.unpack_points(c, 2, o65) == want
         assert b"".join(encoding.encode_g2(c, Q, True) for Q in want) == g2b
+
+
+@pytest.mark.parametrize("c", ALL, ids=lambda c: c.name)
+def test_point_decoding_round_trip_many(hostemu, c):
+    """wider net for the square roots of points_decode.cuh (exponentiation, Tonelli-Shanks with its data-dependent loop,
+    the two candidate branches of the Fp2 root): 150 random points per group through encode (oracle) -> decode
+    (device logic, host build), compressed, both groups"""
+    from oracle import encoding
+    rng = random.Random(2024)
+    hostemu.emu_decode_points.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p]
+    p = c.p
+    b1 = {"bn254": 3, "bls12-381": 4, "bls12-377": 1, "bw6-761": -1}[c.name]
+    deg = c.g2_degree
+    F2 = ff.base_field(c, 2)
+    bt = encoding.twist_b(c)
+    g1, g2 = [], []
+    while len(g1) < 150:
+        x = rng.randrange(p)
+        y = encoding.sqrt_fp(p, x ** 3 + b1)
+        if y is not None:
+            g1.append((x, y if rng.random() < 0.5 else (p - y) % p))
+    while len(g2) < 150:
+        if deg == 2:
+            x = (rng.randrange(p), rng.randrange(p))
+            y = encoding.sqrt_fp2(c, F2.add(F2.mul(F2.sqr(x), x), bt))
+        else:
+            x = rng.randrange(p)
+            y = encoding.sqrt_fp(p, x ** 3 + bt)
+        if y is not None:
+            g2.append((x, y if rng.random() < 0.5 else F2.neg(y)))
+    for group, pts, enc in ((1, g1, lambda Q: encoding.encode_g1(c, Q, True)), (2, g2, lambda Q: encoding.encode_g2(c, Q, True))):
+        blob = b"".join(enc(Q) for Q in pts)
+        width = 2 * (deg if group == 2 else 1) * c.fp_limbs
+        out = np.zeros((len(pts), width), dtype=np.uint64)
+        assert hostemu.emu_decode_points(c.curve_id, group, P(np.frombuffer(blob, dtype=np.uint8).copy()), len(pts), 2, P(out)) == 0
+        assert ec.unpack_points(c, group, out) == pts, (c.name, group)
