@@ -157,7 +157,7 @@ def case_known_dlog_big(rs, seed):
     mont_reduce_wide (about 2^-32.5 per reduction)."""
     import torch
     c = CURVES[NAMES[int(rs.integers(0, 4))]]
-    group = int(rs.integers(1, 3))
+    group = BIG_GROUP or int(rs.integers(1, 3))
     logn = int(rs.integers(17, 21))
     if c.fp_limbs > 6:
         logn = min(logn, 18)
@@ -178,6 +178,9 @@ def case_known_dlog_big(rs, seed):
     return got == want, dict(curve=c.name, group=group, n=n, precomp=precomp)
 
 
+BIG_GROUP = 0     # --big-group: 1 / 2 pins the group of the big cases (2: the Fp2 arithmetic)
+
+
 CASES = {"msm": (case_msm, 5), "known_dlog_big": (case_known_dlog_big, 0), "ntt": (case_ntt, 3), "compute_h": (case_compute_h, 1), "fixed_base": (case_fixed_base, 1),
          "gather": (case_gather, 1)}
 
@@ -188,7 +191,10 @@ def main():
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--only", default="")
     ap.add_argument("--big", type=float, default=0.0, help="weight of the 2^17..2^20 known-discrete-log MSM cases (0 = off)")
+    ap.add_argument("--big-group", type=int, default=0, help="pin the group (1 or 2) of the big cases")
     args = ap.parse_args()
+    global BIG_GROUP
+    BIG_GROUP = args.big_group
     lib.load()
     lib.init([0])
     names = [k for k in CASES if not args.only or k in args.only.split(",")]
